@@ -1,0 +1,661 @@
+"""CPU oracle for the denovo3D solve+score hot path.  TEST INFRASTRUCTURE ONLY.
+
+This module is a CPU restatement (numpy/scipy) of the reference's algorithm
+(jianglab/helicon, ``src/helicon/webApps/denovo3D/solver_linear_regression.py``,
+abbreviated SLR below, and ``src/helicon/lib/analysis.py``).  It exists to CHECK
+the CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` leg may import it; nothing under
+``helicon_b200/`` does.
+
+Parity status: the reference's own tests hold no numeric golden vectors for this
+path, so the oracle is pinned against OUTPUTS OF THE
+REFERENCE ITSELF, generated in the build container by ``oracle/make_golden.py``
+(which imports ``/root/reference/src``) and committed under ``tests/golden/``.
+``tests/test_oracle_golden.py`` checks every function here against them.
+
+Third-party arithmetic that the reference calls and that is NOT in
+``/root/reference`` (versions installed in this image define parity):
+  * scipy 1.18.1  ``scipy.optimize.lsq_linear`` -> ``scipy.sparse.linalg.lsmr``
+    and ``scipy.optimize._lsq.trf_linear`` (call site SLR:258-270).  The oracle
+    calls the same scipy functions (``solve_lsq``); ``lsmr_mixed`` below
+    additionally restates LSMR (Fong & Saunders 2011) with the exact precision
+    map scipy executes for float32 CSR input so that the
+    CUDA recurrences can be checked iteration by iteration.
+  * ``scipy.spatial.transform.Rotation`` (SLR:1225-1238, 1393-1394, 1576-1577,
+    1712-1717): called directly, so coordinates carry the same last-bit noise
+    as the reference's.
+  * ``scipy.stats.qmc.Halton`` (SLR:1566-1571, 1785-1790): restated in
+    ``halton_indices`` (van der Corput base 2) and checked against scipy.
+"""
+
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+from scipy.sparse import csr_matrix, vstack
+
+MAX_EQUATIONS = 2**26  # SLR:131
+
+
+# ----------------------------------------------------------------------------
+# helpers (lib/analysis.py)
+# ----------------------------------------------------------------------------
+def cylindrical_mask(nz, ny, nx, rmin=0, rmax=-1):
+    """lib/analysis.py:731-774 ``get_cylindrical_mask`` (bool (nz,ny,nx))."""
+    j = np.arange(0, ny, dtype=np.int32) - ny // 2
+    i = np.arange(0, nx, dtype=np.int32) - nx // 2
+    Y, X = np.meshgrid(j, i, indexing="ij")
+    if rmax < 0:
+        rmax = ny // 2 - 1
+    m2 = X * X + Y * Y < rmax * rmax
+    if 0 < rmin < rmax:
+        m2 &= X * X + Y * Y >= rmin * rmin
+    return np.broadcast_to(m2, (nz, ny, nx)).copy()
+
+
+def cosine_similarity(a, b):
+    """lib/analysis.py:802-821."""
+    norm = np.linalg.norm(a) * np.linalg.norm(b)
+    if norm == 0:
+        return 0
+    return np.sum(a * b) / norm
+
+
+def halton_indices(n):
+    """Restates ``qmc.Halton(d=1, scramble=False).integers(0, n, n=n)``
+    (SLR:1566-1571): floor(n * vdc2(i)) for i = 0..n-1 (not a permutation:
+    it has duplicates and omissions)."""
+    out = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        f, r, k = 0.5, 0.0, i
+        while k:
+            if k & 1:
+                r += f
+            k >>= 1
+            f *= 0.5
+        out[i] = int(math.floor(r * n))
+    return out
+
+
+def data_copies(rise_pixel, csym, L3, L2):
+    """Ordered (h, c) symmetry copies of build_A_data_matrix (SLR:1559-1571)."""
+    hsym_max = max(1, int(np.ceil(L3 + L2) / 2 / rise_pixel))
+    hc = list(itertools.product(range(-hsym_max, hsym_max + 1), range(csym)))
+    hc.sort(key=lambda x: (abs(x[0]), x[1]))
+    return [hc[int(i)] for i in halton_indices(len(hc))]
+
+
+def sorted_hsym_csym_pairs(twist, rise, csym, nz):
+    """SLR:1749-1791."""
+    hsym_max = max(1, int(np.ceil(nz / (2 * rise))))
+    hcsyms = itertools.product(range(-hsym_max, hsym_max + 1), range(csym))
+    out = []
+    for p in itertools.combinations(hcsyms, r=2):
+        (h1, c1), (h2, c2) = p
+        a1 = twist * h1 + c1 * 360 / csym
+        a2 = twist * h2 + c2 * 360 / csym
+        angle = round(abs((a2 - a1 + 180) % 360 - 180), 2)
+        out.append((angle, abs(h1 + h2), abs(h1 - h2), abs(h1), abs(h2), p))
+    out.sort(key=lambda x: x[:-1])
+    return [out[int(i)] for i in halton_indices(len(out))]
+
+
+# ----------------------------------------------------------------------------
+# geometry (SLR:1657-1746)
+# ----------------------------------------------------------------------------
+def back_project_2d_coords_to_3d_coords(image, scale2d_to_3d, D2=-1, L2=-1):
+    """SLR:1657-1746.  Returns ((X,Y,Z) each (L2,D2,D2) float64, pixel_vals (D2,L2))."""
+    from scipy.spatial.transform import Rotation as R
+
+    ny, nx = image.shape
+    if D2 <= 0:
+        D2 = ny
+    if L2 <= 0:
+        L2 = nx
+    D2 = int(np.rint(D2))
+    L2 = int(np.rint(L2))
+    k = np.arange(0, D2, dtype=np.int32) - D2 // 2
+    j = np.arange(0, D2, dtype=np.int32) - D2 // 2
+    i = np.arange(0, L2, dtype=np.int32) - L2 // 2
+    pix = image[np.ix_(j + ny // 2, i + nx // 2)]
+    Z, Y, X = np.meshgrid(
+        k.astype(np.float32), j.astype(np.float32), i.astype(np.float32), indexing="ij"
+    )
+    coords = np.vstack((X.ravel(), Y.ravel(), Z.ravel())).transpose()
+    coords = R.from_euler("y", 90, degrees=True).apply(coords, inverse=True)
+    if scale2d_to_3d != 1.0:
+        coords *= scale2d_to_3d
+    out = []
+    for c in range(3):
+        out.append(np.swapaxes(coords[:, c].reshape((D2, D2, L2)), 0, 2))
+    return tuple(out), pix
+
+
+def _disk_index(nz, ny, nx, rmin, rmax):
+    mask = cylindrical_mask(nz, ny, nx, rmin, rmax)
+    n_x = int(np.count_nonzero(mask))
+    idx = np.zeros(mask.shape, dtype=np.int64) - 1
+    idx[np.nonzero(mask)] = np.arange(n_x)
+    return mask, idx, n_x
+
+
+# ----------------------------------------------------------------------------
+# forward model rows (SLR:1301-1654)
+# ----------------------------------------------------------------------------
+def build_A_data_matrix(
+    image,
+    scale2d_to_3d,
+    twist_degree,
+    rise_pixel,
+    csym,
+    tilt_degree,
+    psi_degree,
+    dy_pixel,
+    reconstruct_diameter_2d_pixel,
+    reconstruct_length_2d_pixel,
+    reconstruct_diameter_3d_pixel,
+    reconstruct_diameter_3d_inner_pixel,
+    reconstruct_length_3d_pixel,
+    min_projection_lines,
+    interpolation,
+    verbose=0,
+    cpu=1,
+    return_blocks=False,
+):
+    """Literal (full 3-D coordinate table) restatement of SLR:1301-1654 with the
+    numba triple loop (SLR:1403-1557) vectorised per symmetry copy.  Supports
+    general tilt/psi/dy.  Row order, duplicate summation and the early stop are
+    the reference's (cpu=1 path)."""
+    from scipy.spatial.transform import Rotation as R
+
+    (X0, Y0, Z0), pix = back_project_2d_coords_to_3d_coords(
+        image,
+        scale2d_to_3d,
+        reconstruct_diameter_2d_pixel,
+        reconstruct_length_2d_pixel,
+    )
+    rmin = reconstruct_diameter_3d_inner_pixel / 2
+    rmax = reconstruct_diameter_3d_pixel // 2 - 1
+    nz, ny, nx = X0.shape
+    L3 = reconstruct_length_3d_pixel
+    if L3 <= 0:
+        L3 = nz
+    mask, idx, n_x = _disk_index(L3, ny, nx, rmin, rmax)
+    coords0 = np.vstack((X0.ravel(), Y0.ravel(), Z0.ravel())).transpose()
+    coords0[:, 1] -= dy_pixel
+    coords0 = R.from_euler("yx", (tilt_degree, psi_degree), degrees=True).apply(
+        coords0, inverse=True
+    )
+    linear = interpolation in ["linear", "linear10", "linear11"]
+    blocks, bs, pids, used = [], [], [], []
+    n_b = 0
+    kk, jj = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+    for hi, ci in data_copies(rise_pixel, csym, L3, nz):
+        angle = twist_degree * hi + 360 * ci / csym
+        coords = R.from_euler("z", angle, degrees=True).apply(coords0, inverse=True)
+        coords[:, 2] -= hi * rise_pixel
+        X = coords[:, 0].reshape((nz, ny, nx)) + nx // 2
+        Y = coords[:, 1].reshape((nz, ny, nx)) + ny // 2
+        Z = coords[:, 2].reshape((nz, ny, nx)) + L3 // 2
+        if linear:
+            A_blk, rows_kj = _rows_linear(Z, Y, X, mask, idx, n_x)
+        else:
+            A_blk, rows_kj = _rows_nn(Z, Y, X, mask, idx, n_x)
+        nrow = len(rows_kj)
+        n_b += nrow
+        if nrow:
+            k_r, j_r = rows_kj // ny, rows_kj % ny
+            blocks.append(A_blk)
+            bs.append(pix[j_r, k_r].astype(np.float32))
+            pids.append((k_r * ny + j_r).astype(np.int32))
+            used.append((hi, ci, nrow))
+        if min_projection_lines > 0 and n_b > min_projection_lines:
+            break
+    A = vstack(blocks).tocsr()
+    b = np.concatenate(bs, dtype=np.float32)
+    b_pid = np.concatenate(pids)
+    if return_blocks:
+        return A, b, b_pid, used
+    return A, b, b_pid
+
+
+def _rows_nn(Z, Y, X, mask, idx, n_x):
+    """SLR:1514-1557 (half-to-even rounding like numba's round())."""
+    nz, ny, nx = Z.shape
+    mz, my, mx = mask.shape
+    zi = np.rint(Z).astype(np.int64)
+    yi = np.rint(Y).astype(np.int64)
+    xi = np.rint(X).astype(np.int64)
+    ok = (zi >= 0) & (zi <= mz - 1) & (yi >= 0) & (yi <= my - 1) & (xi >= 0) & (xi <= mx - 1)
+    col = np.full(Z.shape, -1, dtype=np.int64)
+    col[ok] = idx[zi[ok], yi[ok], xi[ok]]
+    hit = col >= 0
+    ray_has = hit.reshape(nz * ny, nx).any(axis=1)
+    rows_kj = np.nonzero(ray_has)[0]
+    rank = np.cumsum(ray_has) - 1
+    ray_of_sample = np.repeat(np.arange(nz * ny), nx).reshape(Z.shape)
+    r = rank[ray_of_sample[hit]]
+    c = col[hit]
+    A = csr_matrix(
+        (np.ones(len(r), dtype=np.float32), (r, c)),
+        shape=(len(rows_kj), n_x),
+        dtype=np.float32,
+    )
+    return A, rows_kj
+
+
+def _rows_linear(Z, Y, X, mask, idx, n_x):
+    """SLR:1403-1510: int() truncation corner, all 8 corners in range and in
+    mask, trilinear weights accumulated per row in float64 then stored f32."""
+    nz, ny, nx = Z.shape
+    mz, my, mx = mask.shape
+    zi = np.trunc(Z).astype(np.int64)
+    yi = np.trunc(Y).astype(np.int64)
+    xi = np.trunc(X).astype(np.int64)
+    ok = (
+        (zi >= 0) & (zi + 1 <= mz - 1) & (yi >= 0) & (yi + 1 <= my - 1) & (xi >= 0) & (xi + 1 <= mx - 1)
+    )
+    z_, y_, x_ = zi[ok], yi[ok], xi[ok]
+    allin = np.ones(len(z_), dtype=bool)
+    for dz, dy, dx in itertools.product((0, 1), (0, 1), (0, 1)):
+        allin &= mask[z_ + dz, y_ + dy, x_ + dx]
+    okk = np.zeros(Z.shape, dtype=bool)
+    okk[ok] = allin
+    ray_has = okk.reshape(nz * ny, nx).any(axis=1)
+    rows_kj = np.nonzero(ray_has)[0]
+    rank = np.cumsum(ray_has) - 1
+    ray_of_sample = np.repeat(np.arange(nz * ny), nx).reshape(Z.shape)
+    r = rank[ray_of_sample[okk]]
+    z_, y_, x_ = zi[okk], yi[okk], xi[okk]
+    zf, yf, xf = Z[okk] - z_, Y[okk] - y_, X[okk] - x_
+    rr, cc, dd = [], [], []
+    for dz, dy, dx in itertools.product((0, 1), (0, 1), (0, 1)):
+        w = (zf if dz else 1 - zf) * (yf if dy else 1 - yf) * (xf if dx else 1 - xf)
+        rr.append(r)
+        cc.append(idx[z_ + dz, y_ + dy, x_ + dx])
+        dd.append(w)
+    rr, cc, dd = np.concatenate(rr), np.concatenate(cc), np.concatenate(dd)
+    # the reference accumulates per-row weights in a float64 dict, then stores f32
+    A64 = csr_matrix((dd, (rr, cc)), shape=(len(rows_kj), n_x), dtype=np.float64)
+    A64.sum_duplicates()
+    return A64.astype(np.float32), rows_kj
+
+
+# ----------------------------------------------------------------------------
+# symmetry rows (SLR:844-1298)
+# ----------------------------------------------------------------------------
+def build_A_helical_sym_matrix(
+    nz, ny, nx, twist_degree, rise_pixel, csym, rmin, rmax, min_sym_pairs, interpolation, verbose=0
+):
+    """SLR:844-1298.  nn: rows +1@a -1@b with first-seen-wins de-duplication of
+    unordered (a,b) across pairs (list order) then voxels (mask order);
+    linear: truncation corners, |dz|,|dy|,|dx|>=3, the corner-110 weight typo
+    of SLR:1089/1125 reproduced."""
+    from scipy.spatial.transform import Rotation as R
+
+    pairs = sorted_hsym_csym_pairs(twist_degree, rise_pixel, csym, nz)
+    mask, idx, n_x = _disk_index(nz, ny, nx, rmin, rmax)
+    kz, jy, ix = np.nonzero(mask)
+    xyz = np.stack([ix - nx // 2, jy - ny // 2, kz - nz // 2], axis=1).astype(np.float64)
+    linear = interpolation in ["linear", "linear01", "linear11"]
+    seen = set()
+    blocks = []
+    row_count = 0
+
+    def image_of(h, c):
+        t = R.from_euler("z", twist_degree * h + c * 360 / csym, degrees=True).apply(xyz, inverse=False)
+        return t[:, 2] + nz // 2 + rise_pixel * h, t[:, 1] + ny // 2, t[:, 0] + nx // 2
+
+    for p in pairs:
+        (hi, ci), (hj, cj) = p[-1]
+        Zi, Yi, Xi = image_of(hi, ci)
+        Zj, Yj, Xj = image_of(hj, cj)
+        if linear:
+            blk, nrow = _hsym_rows_linear(Zi, Yi, Xi, Zj, Yj, Xj, mask, idx, n_x, seen)
+        else:
+            blk, nrow = _hsym_rows_nn(Zi, Yi, Xi, Zj, Yj, Xj, mask, idx, n_x, seen)
+        row_count += nrow
+        if nrow:
+            blocks.append(blk)
+        if row_count >= min_sym_pairs:
+            break
+    if blocks:
+        return vstack(blocks).tocsr(), np.zeros(row_count, dtype=np.float32)
+    return None, None
+
+
+def _valid_index(Zr, Yr, Xr, mask, idx):
+    mz, my, mx = mask.shape
+    ok = (Zr >= 0) & (Zr <= mz - 1) & (Yr >= 0) & (Yr <= my - 1) & (Xr >= 0) & (Xr <= mx - 1)
+    q = np.full(len(Zr), -1, dtype=np.int64)
+    q[ok] = idx[Zr[ok], Yr[ok], Xr[ok]]
+    return q
+
+
+def _dedup_first_seen(a, b, n, seen):
+    """Sequential first-seen-wins on unordered (a,b) (SLR:1197-1202)."""
+    keep = np.zeros(len(a), dtype=bool)
+    for t in range(len(a)):
+        key = int(a[t]) * n + int(b[t])
+        if key in seen:
+            continue
+        seen.add(key)
+        seen.add(int(b[t]) * n + int(a[t]))
+        keep[t] = True
+    return keep
+
+
+def _hsym_rows_nn(Zi, Yi, Xi, Zj, Yj, Xj, mask, idx, n_x, seen):
+    r_ = lambda v: np.rint(v).astype(np.int64)
+    a = _valid_index(r_(Zi), r_(Yi), r_(Xi), mask, idx)
+    b = _valid_index(r_(Zj), r_(Yj), r_(Xj), mask, idx)
+    cand = np.nonzero((a >= 0) & (b >= 0))[0]
+    keep = _dedup_first_seen(a[cand], b[cand], n_x, seen)
+    sel = cand[keep]
+    nrow = len(sel)
+    if nrow == 0:
+        return None, 0
+    rows = np.repeat(np.arange(nrow), 2)
+    cols = np.stack([a[sel], b[sel]], axis=1).ravel()
+    vals = np.tile(np.array([1, -1], dtype=np.float32), nrow)
+    return csr_matrix((vals, (rows, cols)), shape=(nrow, n_x), dtype=np.float32), nrow
+
+
+def _hsym_rows_linear(Zi, Yi, Xi, Zj, Yj, Xj, mask, idx, n_x, seen):
+    mz, my, mx = mask.shape
+    t_ = lambda v: np.trunc(v).astype(np.int64)
+    r_ = lambda v: np.rint(v).astype(np.int64)
+
+    def corners_ok(Z, Y, X):
+        z, y, x = t_(Z), t_(Y), t_(X)
+        ok = (z >= 0) & (z + 1 <= mz - 1) & (y >= 0) & (y + 1 <= my - 1) & (x >= 0) & (x + 1 <= mx - 1)
+        res = np.zeros(len(Z), dtype=bool)
+        zz, yy, xx = z[ok], y[ok], x[ok]
+        allin = np.ones(len(zz), dtype=bool)
+        for dz, dy, dx in itertools.product((0, 1), (0, 1), (0, 1)):
+            allin &= mask[zz + dz, yy + dy, xx + dx]
+        res[ok] = allin
+        return res, z, y, x
+
+    oki, zi, yi, xi = corners_ok(Zi, Yi, Xi)
+    okj, zj, yj, xj = corners_ok(Zj, Yj, Xj)
+    far = ~((np.abs(zi - zj) < 3) | (np.abs(yi - yj) < 3) | (np.abs(xi - xj) < 3))
+    cand = np.nonzero(oki & okj & far)[0]
+    # dedup key from ROUNDED indices looked up WITHOUT bounds checks (SLR:1045-1058);
+    # numba wraps negative indices like numpy, so emulate with modular indexing.
+    ir = idx[r_(Zi[cand]) % mz, r_(Yi[cand]) % my, r_(Xi[cand]) % mx]
+    jr = idx[r_(Zj[cand]) % mz, r_(Yj[cand]) % my, r_(Xj[cand]) % mx]
+    n_indices = n_x
+    keep = np.zeros(len(cand), dtype=bool)
+    for t in range(len(cand)):
+        key = int(ir[t]) * n_indices + int(jr[t])
+        if key in seen:
+            continue
+        seen.add(key)
+        seen.add(int(jr[t]) * n_indices + int(ir[t]))
+        keep[t] = True
+    sel = cand[keep]
+    nrow = len(sel)
+    if nrow == 0:
+        return None, 0
+    rr, cc, dd = [], [], []
+    for sign, (Z, Y, X, z, y, x) in ((1.0, (Zi, Yi, Xi, zi, yi, xi)), (-1.0, (Zj, Yj, Xj, zj, yj, xj))):
+        zf, yf, xf = Z[sel] - z[sel], Y[sel] - y[sel], X[sel] - x[sel]
+        w = {
+            (0, 0, 0): (1 - zf) * (1 - yf) * (1 - xf),
+            (0, 0, 1): (1 - zf) * (1 - yf) * xf,
+            (0, 1, 0): (1 - zf) * yf * (1 - xf),
+            (0, 1, 1): (1 - zf) * yf * xf,
+            (1, 0, 0): zf * (1 - yf) * (1 - xf),
+            (1, 0, 1): zf * (1 - yf) * xf,
+            (1, 1, 0): xf * yf * (1 - xf),  # reference typo (SLR:1089, 1125), kept
+            (1, 1, 1): xf * yf * zf,
+        }
+        for (dz, dy, dx), wv in w.items():
+            rr.append(np.arange(nrow))
+            cc.append(idx[z[sel] + dz, y[sel] + dy, x[sel] + dx])
+            dd.append((sign * wv).astype(np.float32))
+    A = csr_matrix(
+        (np.concatenate(dd), (np.concatenate(rr), np.concatenate(cc))), shape=(nrow, n_x), dtype=np.float32
+    )
+    return A, nrow
+
+
+# ----------------------------------------------------------------------------
+# solve + score (SLR:31-547)
+# ----------------------------------------------------------------------------
+def positive_rule(positive_constraint, rise_pixel, twist_degree, L3):
+    """SLR:352-355."""
+    pitch_pixel = round(rise_pixel * 360 / abs(twist_degree))
+    return positive_constraint > 0 or (positive_constraint < 0 and pitch_pixel > round(L3 * 2))
+
+
+def solve_lsq(A_data, b_data, A_hsym, b_hsym, positive):
+    """SLR:218-270 with algorithm={'model':'lsq'}: the reference's own scipy call."""
+    from scipy.optimize import lsq_linear
+
+    if not (A_hsym is None or b_hsym is None):
+        A = vstack((A_data, A_hsym))
+        b = np.concatenate((b_data, b_hsym))
+    else:
+        A, b = A_data, b_data
+    if positive:
+        lb, ub = 0.0, np.max(b_data)
+    else:
+        lb, ub = -np.inf, np.inf
+    res = lsq_linear(A, b, bounds=(lb, ub), tol=1e-2, max_iter=200, lsmr_maxiter=1000, lsmr_tol="auto", verbose=0)
+    return res.x.astype(np.float32), res
+
+
+def lsq_reconstruct(
+    projection_image,
+    scale2d_to_3d,
+    twist_degree,
+    rise_pixel,
+    csym=1,
+    tilt_degree=0,
+    psi_degree=0,
+    dy_pixel=0,
+    thresh_fraction=-1,
+    positive_constraint=-1,
+    reconstruct_diameter_3d_inner_pixel=0,
+    reconstruct_diameter_2d_pixel=-1,
+    reconstruct_diameter_3d_pixel=-1,
+    reconstruct_length_2d_pixel=-1,
+    reconstruct_length_3d_pixel=-1,
+    sym_oversample=1,
+    interpolation="nn",
+    return_details=False,
+):
+    """SLR:31-547 for algorithm={'model':'lsq'}, fsc_test=0, score_metric='cosine',
+    no tilt/psi/dy refinement."""
+    D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
+    rmin = reconstruct_diameter_3d_inner_pixel / 2
+    rmax = D3 // 2 - 1
+    mask = cylindrical_mask(L3, D3, D3, rmin, rmax)
+    n3 = int(np.count_nonzero(mask))
+    n2 = reconstruct_diameter_2d_pixel * reconstruct_length_2d_pixel
+    target = min(MAX_EQUATIONS, int(max(n2, n3) * sym_oversample))
+    A_data, b_data, b_pid = build_A_data_matrix(
+        projection_image,
+        scale2d_to_3d,
+        twist_degree,
+        rise_pixel,
+        csym,
+        tilt_degree,
+        psi_degree,
+        dy_pixel,
+        reconstruct_diameter_2d_pixel,
+        reconstruct_length_2d_pixel,
+        D3,
+        reconstruct_diameter_3d_inner_pixel,
+        L3,
+        target,
+        interpolation,
+    )
+    A_hsym, b_hsym = build_A_helical_sym_matrix(
+        L3, D3, D3, twist_degree, rise_pixel, csym, rmin, rmax, target, interpolation
+    )
+    positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
+    x, res = solve_lsq(A_data, b_data, A_hsym, b_hsym, positive)
+    pred = A_data.dot(x)
+    if thresh_fraction >= 0:
+        pred = np.clip(pred, 0, None)
+    score = cosine_similarity(pred, b_data)
+    rec3d = np.zeros((L3, D3, D3), dtype=np.float32)
+    rec3d[mask] = x
+    if return_details:
+        return (rec3d, None, None), score, dict(
+            A_data=A_data, b_data=b_data, b_pid=b_pid, A_hsym=A_hsym, x=x, res=res, positive=positive
+        )
+    return (rec3d, None, None), score
+
+
+# ----------------------------------------------------------------------------
+# LSMR with scipy's executed precision map, for
+# iteration-by-iteration checks of the CUDA recurrences.
+# ----------------------------------------------------------------------------
+def _sym_ortho32(a, b):
+    """scipy lsqr.py:62-94 with float32 in/out, math.sqrt in float64."""
+    f = np.float32
+    if b == 0:
+        return f(np.sign(a)), f(0), f(abs(a))
+    elif a == 0:
+        return f(0), f(np.sign(b)), f(abs(b))
+    elif abs(b) > abs(a):
+        tau = f(a / b)
+        s = f(np.sign(b) / math.sqrt(f(1 + tau * tau)))
+        c = f(s * tau)
+        r = f(b / s)
+    else:
+        tau = f(b / a)
+        c = f(np.sign(a) / math.sqrt(f(1 + tau * tau)))
+        s = f(c * tau)
+        r = f(a / c)
+    return c, s, r
+
+
+def lsmr_mixed(A, b, atol=1e-4, btol=1e-4, conlim=1e8, maxiter=1000, fixed_iters=None, trace=None):
+    """scipy ``lsmr`` (lsmr.py:197-480) for float32 CSR ``A`` and float32 ``b``,
+    damp=0, x0=None: u,v,h float32; x,hbar float64; scalars float32.  Calls the
+    real scipy on the same input give the same iterates up to summation order.
+    ``fixed_iters`` runs exactly that many iterations ignoring stop tests."""
+    f = np.float32
+    A = A.tocsr()
+    AT = A.T.tocsr()
+    m, n = A.shape
+    u = b.astype(f).copy()
+    normb = f(np.linalg.norm(u))
+    x = np.zeros(n, np.float64)
+    beta = f(normb)
+    if beta > 0:
+        u = f(1 / beta) * u
+        v = AT.dot(u)
+        alpha = f(np.linalg.norm(v))
+    else:
+        v = np.zeros(n, f)
+        alpha = f(0)
+    if alpha > 0:
+        v = f(1 / alpha) * v
+    itn = 0
+    zetabar = f(alpha * beta)
+    alphabar = alpha
+    rho = rhobar = cbar = f(1)
+    sbar = f(0)
+    h = v.copy()
+    hbar = np.zeros(n, np.float64)
+    betadd, betad = beta, f(0)
+    rhodold, tautildeold, thetatilde, zeta, d = f(1), f(0), f(0), f(0), f(0)
+    normA2 = f(alpha * alpha)
+    maxrbar, minrbar = f(0), 1e100
+    normA = math.sqrt(normA2)
+    condA, normx = 1, 0.0
+    istop = 0
+    ctol = 1 / conlim if conlim > 0 else 0
+    normr = beta
+    normar = f(alpha * beta)
+    if normar == 0 or normb == 0:
+        return x, istop, itn, normr, normar, normA, condA, normx
+    limit = maxiter if fixed_iters is None else fixed_iters
+    with np.errstate(over="ignore"):
+        while itn < limit:
+            itn += 1
+            u *= -alpha
+            u += A.dot(v)
+            beta = f(np.linalg.norm(u))
+            if beta > 0:
+                u *= f(1 / beta)
+                v *= -beta
+                v += AT.dot(u)
+                alpha = f(np.linalg.norm(v))
+                if alpha > 0:
+                    v *= f(1 / alpha)
+            chat, shat, alphahat = _sym_ortho32(alphabar, 0.0)
+            rhoold = rho
+            c, s, rho = _sym_ortho32(alphahat, beta)
+            thetanew = f(s * alpha)
+            alphabar = f(c * alpha)
+            rhobarold, zetaold = rhobar, zeta
+            thetabar = f(sbar * rho)
+            rhotemp = f(cbar * rho)
+            cbar, sbar, rhobar = _sym_ortho32(f(cbar * rho), thetanew)
+            zeta = f(cbar * zetabar)
+            zetabar = f(-sbar * zetabar)
+            hbar *= np.float64(f(-(f(thetabar * rho) / f(rhoold * rhobarold))))
+            hbar += h
+            x += np.float64(f(zeta / f(rho * rhobar))) * hbar
+            h *= f(-(thetanew / rho))
+            h += v
+            betaacute = f(chat * betadd)
+            betacheck = f(-shat * betadd)
+            betahat = f(c * betaacute)
+            betadd = f(-s * betaacute)
+            thetatildeold = thetatilde
+            ctildeold, stildeold, rhotildeold = _sym_ortho32(rhodold, thetabar)
+            thetatilde = f(stildeold * rhobar)
+            rhodold = f(ctildeold * rhobar)
+            betad = f(f(-stildeold * betad) + f(ctildeold * betahat))
+            tautildeold = f(f(zetaold - f(thetatildeold * tautildeold)) / rhotildeold)
+            taud = f(f(zeta - f(thetatilde * tautildeold)) / rhodold)
+            d = f(d + f(betacheck * betacheck))
+            dd = f(betad - taud)
+            normr = math.sqrt(f(f(d + f(dd * dd)) + f(betadd * betadd)))
+            normA2 = f(normA2 + f(beta * beta))
+            normA = math.sqrt(normA2)
+            normA2 = f(normA2 + f(alpha * alpha))
+            maxrbar = max(maxrbar, rhobarold)
+            if itn > 1:
+                minrbar = min(minrbar, rhobarold)
+            condA = max(maxrbar, rhotemp) / min(minrbar, rhotemp)
+            normar = abs(zetabar)
+            normx = np.linalg.norm(x)
+            test1 = normr / normb
+            test2 = normar / (normA * normr) if (normA * normr) != 0 else np.inf
+            test3 = 1 / condA
+            t1 = test1 / (1 + normA * normx / normb)
+            rtol = btol + atol * normA * normx / normb
+            if trace is not None:
+                trace.append(dict(itn=itn, alpha=float(alpha), beta=float(beta), rho=float(rho), rhobar=float(rhobar),
+                                  zeta=float(zeta), normr=float(normr), normA=float(normA), normx=float(normx),
+                                  test1=float(test1), test2=float(test2)))
+            if fixed_iters is not None:
+                continue
+            if itn >= maxiter:
+                istop = 7
+            if 1 + test3 <= 1:
+                istop = 6
+            if 1 + test2 <= 1:
+                istop = 5
+            if 1 + t1 <= 1:
+                istop = 4
+            if test3 <= ctol:
+                istop = 3
+            if test2 <= atol:
+                istop = 2
+            if test1 <= rtol:
+                istop = 1
+            if istop > 0:
+                break
+    return x, istop, itn, normr, normar, normA, condA, normx
