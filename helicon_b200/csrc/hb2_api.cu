@@ -1,0 +1,756 @@
+// helicon_b200: C-ABI host side (include/helicon_b200.h).  One translation unit.
+#include "../../include/helicon_b200.h"
+#include "hb2_kernels.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) {                                                                              \
+      char buf_[512];                                                                                     \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return fail(HB2_ERR_CUDA, buf_);                                                                    \
+    }                                                                                                     \
+  } while (0)
+#define CKL()                                                                                             \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                                  \
+    if (e_ != cudaSuccess) {                                                                              \
+      char buf_[512];                                                                                     \
+      snprintf(buf_, sizeof buf_, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return fail(HB2_ERR_CUDA, buf_);                                                                    \
+    }                                                                                                     \
+  } while (0)
+
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+struct hb2_problem {
+  int device = 0;
+  hb2_geometry g{};
+  int ndisk = 0;
+  float* d_pix = nullptr;          // [D2][L2]  pix[j][k] = image[j - D2//2 + ny//2, k - L2//2 + nx//2]
+  int* d_rank_data = nullptr;      // [D2*D2]
+  int* d_rank_sym = nullptr;       // [D3*D3]
+  short2* d_yx_data = nullptr;     // [ndisk] (row y, column x) on the data grid
+  short2* d_yx_sym = nullptr;      // [ndisk] on the symmetry grid
+  std::vector<int> h_rank_data;
+};
+
+struct DevPool {  // owns device allocations of a batch
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  template <typename T>
+  cudaError_t alloc(T** p, size_t count, bool zero, cudaStream_t st) {
+    size_t nb = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)p, nb);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(*p);
+    bytes += nb;
+    if (zero) e = cudaMemsetAsync(*p, 0, nb, st);
+    return e;
+  }
+  void release(void* p) {
+    for (auto& q : ptrs)
+      if (q == p) { cudaFree(q); q = nullptr; }
+  }
+  void free_all() {
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+    ptrs.clear();
+  }
+};
+
+struct hb2_batch {
+  hb2_problem* P = nullptr;
+  cudaStream_t stream = nullptr;
+  DevPool pool;
+  BD B{};
+  bool idx16 = true;
+  bool created = false;
+  int nviews = 0;
+  // host copies
+  std::vector<hb2_candidate> cands;
+  std::vector<int> h_view_count, h_view_begin, h_mdata, h_msym;
+  std::vector<long long> h_uoff, h_symoff, h_symcap, h_cscoff;
+  std::vector<int> tie_per_angle;
+  std::vector<int> h_view_angle;
+  std::vector<uint32_t> cand_flags;
+  long long u_total = 0;
+  // device (non-const views of BD members)
+  double* d_cs = nullptr;
+  void* d_fmap = nullptr;
+  uint8_t* d_rayvalid = nullptr;
+  int* d_tie = nullptr;
+  uint16_t* d_amap = nullptr;
+  int* d_sym_a = nullptr; int* d_sym_b = nullptr; int* d_csc_ptr = nullptr; int* d_csc_ent = nullptr;
+  float* d_bmax = nullptr;
+  float* d_score = nullptr;
+  int* d_nactive = nullptr;
+  int* h_nactive = nullptr;  // pinned
+  double timing[8] = {0};
+  bool solved = false;
+};
+
+extern "C" const char* hb2_last_error(void) { return g_err.c_str(); }
+extern "C" int hb2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" const char* hb2_build_info(void) { return "helicon_b200 sm_100a " __DATE__ " " __TIME__; }
+
+// ---------------------------------------------------------------------------
+// problem
+// ---------------------------------------------------------------------------
+static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, std::vector<short2>& yx) {
+  // lib/analysis.py:731-774: X*X + Y*Y < rmax*rmax, and >= rmin*rmin when 0 < rmin < rmax
+  rank.assign((size_t)G * G, -1);
+  yx.clear();
+  int c0 = G / 2;
+  for (int y = 0; y < G; ++y)
+    for (int x = 0; x < G; ++x) {
+      long long r2 = (long long)(x - c0) * (x - c0) + (long long)(y - c0) * (y - c0);
+      bool in = r2 < (long long)rmax * rmax;
+      if (in && rmin > 0 && rmin < rmax) in = (double)r2 >= rmin * rmin;
+      if (in) {
+        rank[(size_t)y * G + x] = (int)yx.size();
+        yx.push_back(make_short2((short)y, (short)x));
+      }
+    }
+}
+
+extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const hb2_geometry* g, int device, void* stream) {
+  if (!out || !image || !g) return fail(HB2_ERR_ARG, "null argument");
+  if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
+  if (g->interpolation != 0) return fail(HB2_ERR_GEOMETRY, "only interpolation='nn' is implemented on the CUDA path");
+  if (g->D2 <= 0 || g->L2 <= 0 || g->D3 <= 0 || g->D2 > 32000 || g->L2 > 32000)
+    return fail(HB2_ERR_ARG, "bad reconstruct sizes");
+  if (g->D2 / 2 > g->ny / 2 + 0 && (g->D2 > g->ny)) return fail(HB2_ERR_ARG, "D2 larger than the image");
+  if (g->L2 > g->nx) return fail(HB2_ERR_ARG, "L2 larger than the image");
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  auto* P = new hb2_problem();
+  P->device = device;
+  P->g = *g;
+  std::vector<int> rd, rs;
+  std::vector<short2> yd, ys;
+  disk_tables(g->D2, g->rmin, g->rmax, rd, yd);
+  disk_tables(g->D3, g->rmin, g->rmax, rs, ys);
+  if (yd.size() != ys.size() || yd.empty()) {
+    delete P;
+    return fail(HB2_ERR_GEOMETRY,
+                "the cylinder mask has a different voxel count on the 2-D (D2) and 3-D (D3) grids (or is empty); "
+                "the reference cannot scatter such a solution either (SLR:538)");
+  }
+  P->ndisk = (int)yd.size();
+  P->h_rank_data = rd;
+  // crop: SLR:1706-1708
+  std::vector<float> pix((size_t)g->D2 * g->L2);
+  for (int j = 0; j < g->D2; ++j)
+    for (int k = 0; k < g->L2; ++k) {
+      int yy = j - g->D2 / 2 + g->ny / 2, xx = k - g->L2 / 2 + g->nx / 2;
+      // numpy fancy indexing wraps negative indices (odd sizes can reach -1)
+      if (yy < 0) yy += g->ny;
+      if (xx < 0) xx += g->nx;
+      pix[(size_t)j * g->L2 + k] = image[(size_t)yy * g->nx + xx];
+    }
+  CK(cudaMalloc(&P->d_pix, pix.size() * sizeof(float)));
+  CK(cudaMalloc(&P->d_rank_data, rd.size() * sizeof(int)));
+  CK(cudaMalloc(&P->d_rank_sym, rs.size() * sizeof(int)));
+  CK(cudaMalloc(&P->d_yx_data, yd.size() * sizeof(short2)));
+  CK(cudaMalloc(&P->d_yx_sym, ys.size() * sizeof(short2)));
+  CK(cudaMemcpyAsync(P->d_pix, pix.data(), pix.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_rank_data, rd.data(), rd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_rank_sym, rs.data(), rs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_yx_data, yd.data(), yd.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_yx_sym, ys.data(), ys.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // host vectors go out of scope
+  *out = P;
+  return HB2_OK;
+}
+
+extern "C" void hb2_problem_destroy(hb2_problem* P) {
+  if (!P) return;
+  cudaSetDevice(P->device);
+  cudaFree(P->d_pix); cudaFree(P->d_rank_data); cudaFree(P->d_rank_sym); cudaFree(P->d_yx_data); cudaFree(P->d_yx_sym);
+  delete P;
+}
+extern "C" int hb2_problem_ndisk(const hb2_problem* P) { return P ? P->ndisk : 0; }
+extern "C" int hb2_problem_rank_table(const hb2_problem* P, int32_t* out) {
+  if (!P || !out) return fail(HB2_ERR_ARG, "null argument");
+  memcpy(out, P->h_rank_data.data(), P->h_rank_data.size() * sizeof(int));
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch step 1: in-plane maps
+// ---------------------------------------------------------------------------
+extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int32_t MC, int32_t nA, const double* cos_sin,
+                               int32_t* nvalid_rays, int32_t* tie_samples, void* stream) {
+  if (!out || !P || !cos_sin || nA <= 0 || L3 <= 0 || MC <= 0) return fail(HB2_ERR_ARG, "bad argument");
+  if ((long long)L3 * MC > HB2_MAX_ZMC) return fail(HB2_ERR_GEOMETRY, "L3*MC exceeds HB2_MAX_ZMC");
+  if ((long long)L3 * P->ndisk >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many unknowns");
+  CK(cudaSetDevice(P->device));
+  auto* b = new hb2_batch();
+  b->P = P;
+  b->stream = (cudaStream_t)stream;
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  const hb2_geometry& g = P->g;
+  B.D2 = g.D2; B.L2 = g.L2; B.D3 = g.D3; B.ndisk = P->ndisk; B.L3 = L3; B.MC = MC; B.ZMC = L3 * MC;
+  B.n = L3 * P->ndisk; B.npad = (B.n + 31) / 32 * 32; B.rows_per_view = L3 * MC * g.D2;
+  B.nA = nA; B.s = g.scale2d_to_3d; B.only_cand = -1;
+  b->idx16 = P->ndisk < 65535;
+  size_t ns = (size_t)nA * g.D2 * g.D2;
+#define BEGIN_FAIL(e) do { b->pool.free_all(); delete b; return (e); } while (0)
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); b->pool.free_all(); delete b; return fail(HB2_ERR_CUDA, m_); } } while (0)
+  CKB(b->pool.alloc(&b->d_cs, (size_t)2 * nA, false, st));
+  CKB(cudaMemcpyAsync(b->d_cs, cos_sin, sizeof(double) * 2 * nA, cudaMemcpyHostToDevice, st));
+  if (b->idx16) { uint16_t* p; CKB(b->pool.alloc(&p, ns, false, st)); b->d_fmap = p; }
+  else { uint32_t* p; CKB(b->pool.alloc(&p, ns, false, st)); b->d_fmap = p; }
+  CKB(b->pool.alloc(&b->d_rayvalid, (size_t)nA * g.D2, true, st));
+  CKB(b->pool.alloc(&b->d_tie, (size_t)nA, true, st));
+  if (b->idx16)
+    k_build_fmap<uint16_t><<<cdiv(ns, 256), 256, 0, st>>>(nA, g.D2, g.scale2d_to_3d, b->d_cs, P->d_rank_data, (uint16_t*)b->d_fmap, b->d_rayvalid, b->d_tie);
+  else
+    k_build_fmap<uint32_t><<<cdiv(ns, 256), 256, 0, st>>>(nA, g.D2, g.scale2d_to_3d, b->d_cs, P->d_rank_data, (uint32_t*)b->d_fmap, b->d_rayvalid, b->d_tie);
+  CKB(cudaGetLastError());
+  std::vector<uint8_t> rv((size_t)nA * g.D2);
+  b->tie_per_angle.resize(nA);
+  CKB(cudaMemcpyAsync(rv.data(), b->d_rayvalid, rv.size(), cudaMemcpyDeviceToHost, st));
+  CKB(cudaMemcpyAsync(b->tie_per_angle.data(), b->d_tie, sizeof(int) * nA, cudaMemcpyDeviceToHost, st));
+  CKB(cudaStreamSynchronize(st));
+  for (int a = 0; a < nA; ++a) {
+    int cnt = 0;
+    for (int j = 0; j < g.D2; ++j) cnt += rv[(size_t)a * g.D2 + j];
+    if (nvalid_rays) nvalid_rays[a] = cnt;
+    if (tie_samples) tie_samples[a] = b->tie_per_angle[a];
+  }
+  B.fmap = b->d_fmap; B.rayvalid = b->d_rayvalid;
+  *out = b;
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out) {
+  if (!b || !out) return fail(HB2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->P->device));
+  CK(cudaMemcpyAsync(out, b->d_rayvalid, (size_t)b->B.nA * b->B.D2, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_angle_map(hb2_batch* b, int32_t angle, int32_t* out) {
+  if (!b || !out || angle < 0 || angle >= b->B.nA) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  size_t n = (size_t)b->B.D2 * b->B.D2;
+  if (b->idx16) {
+    std::vector<uint16_t> t(n);
+    CK(cudaMemcpyAsync(t.data(), (uint16_t*)b->d_fmap + n * angle, n * 2, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFu ? -1 : (int)t[i];
+  } else {
+    std::vector<uint32_t> t(n);
+    CK(cudaMemcpyAsync(t.data(), (uint32_t*)b->d_fmap + n * angle, n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFFFFFu ? -1 : (int)t[i];
+  }
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch step 2: candidates
+// ---------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(DevPool& pool, const T** dst, const std::vector<T>& src, cudaStream_t st) {
+  T* p = nullptr;
+  cudaError_t e = pool.alloc(&p, src.size(), false, st);
+  if (e != cudaSuccess) return e;
+  if (!src.empty()) e = cudaMemcpyAsync(p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  *dst = p;
+  return e;
+}
+
+extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* cands, int32_t nviews, const hb2_view* views,
+                                int32_t ncolk, const int32_t* colk, int32_t npairs, const hb2_pair* pairs) {
+  if (!b || !cands || nc <= 0 || !views || nviews <= 0 || !colk) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "batch already created");
+  if (nc > 65535) return fail(HB2_ERR_ARG, "at most 65535 candidates per batch");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  B.nc = nc;
+  b->nviews = nviews;
+  b->cands.assign(cands, cands + nc);
+  const int D2 = B.D2, ntiles = (D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  // ---- host tables ---------------------------------------------------------
+  std::vector<int> view_cand(nviews, -1), view_angle(nviews), view_colbegin(nviews);
+  std::vector<long long> view_uoff(nviews);
+  b->h_view_begin.resize(nc); b->h_view_count.resize(nc); b->h_mdata.resize(nc); b->h_msym.assign(nc, 0);
+  b->h_uoff.resize(nc); b->h_symoff.resize(nc); b->h_symcap.resize(nc); b->h_cscoff.resize(nc);
+  b->cand_flags.assign(nc, 0);
+  std::vector<int> pair_begin(nc), pair_count(nc);
+  std::vector<long long> min_pairs(nc), tab_off(nc), tab_cap(nc);
+  long long uo = 0, so = 0, to = 0;
+  int expect_view = 0;
+  for (int c = 0; c < nc; ++c) {
+    const hb2_candidate& q = cands[c];
+    if (q.view_begin != expect_view || q.view_count < 0 || q.view_begin + q.view_count > nviews)
+      return fail(HB2_ERR_ARG, "candidate views must tile the view array in order");
+    expect_view += q.view_count;
+    if (q.pair_count < 0 || q.pair_begin < 0 || q.pair_begin + q.pair_count > npairs) return fail(HB2_ERR_ARG, "bad pair range");
+    b->h_view_begin[c] = q.view_begin; b->h_view_count[c] = q.view_count;
+    long long md = (long long)q.view_count * B.rows_per_view;
+    if (md >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many data rows in one candidate");
+    b->h_mdata[c] = (int)md;
+    long long cap = std::min<long long>(q.min_sym_pairs + B.n, (long long)q.pair_count * B.n);
+    if (q.pair_count == 0 || q.min_sym_pairs < 0) cap = 0;
+    if (cap >= (1ll << 31) - 1) return fail(HB2_ERR_GEOMETRY, "too many symmetry rows in one candidate");
+    b->h_symcap[c] = cap;
+    b->h_uoff[c] = uo; b->h_symoff[c] = so; b->h_cscoff[c] = 2 * so;
+    for (int v = 0; v < q.view_count; ++v) {
+      int vi = q.view_begin + v;
+      const hb2_view& w = views[vi];
+      if (w.angle < 0 || w.angle >= B.nA || w.col_begin < 0 || w.col_begin + B.ZMC > ncolk) return fail(HB2_ERR_ARG, "bad view");
+      view_cand[vi] = c; view_angle[vi] = w.angle; view_colbegin[vi] = w.col_begin;
+      view_uoff[vi] = uo + (long long)v * B.rows_per_view;
+      if (b->tie_per_angle[w.angle] > 0) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
+    }
+    b->cand_flags[c] |= q.flags_in;
+    if (q.view_count == 0) b->cand_flags[c] |= HB2_FLAG_NO_ROWS;
+    uo += md + cap; so += cap;
+    pair_begin[c] = q.pair_begin; pair_count[c] = q.pair_count; min_pairs[c] = q.min_sym_pairs;
+    tab_off[c] = to; tab_cap[c] = 2 * cap + 17; to += tab_cap[c];
+  }
+  if (expect_view != nviews) return fail(HB2_ERR_ARG, "views not fully assigned to candidates");
+  if (2 * so >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "batch too large: symmetry-row lists exceed 2^31 entries; use smaller batches");
+  if ((long long)nc * B.npad >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "batch too large: nc*n exceeds 2^31; use smaller batches");
+  b->u_total = uo;
+  b->h_view_angle = view_angle;
+  for (int e = 0; e < ncolk; ++e)
+    if (colk[e] >= B.L2) return fail(HB2_ERR_ARG, "column index out of range");
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  // ---- device tables -------------------------------------------------------
+  CKC(upload(b->pool, &B.view_cand, view_cand, st));
+  CKC(upload(b->pool, &B.view_angle, view_angle, st));
+  CKC(upload(b->pool, &B.view_colbegin, view_colbegin, st));
+  CKC(upload(b->pool, &B.view_uoff, view_uoff, st));
+  std::vector<int> colk_v(colk, colk + ncolk);
+  CKC(upload(b->pool, &B.colk, colk_v, st));
+  CKC(upload(b->pool, &B.cand_view_begin, b->h_view_begin, st));
+  CKC(upload(b->pool, &B.cand_view_count, b->h_view_count, st));
+  CKC(upload(b->pool, &B.cand_uoff, b->h_uoff, st));
+  CKC(upload(b->pool, &B.cand_mdata, b->h_mdata, st));
+  CKC(upload(b->pool, &B.cand_symoff, b->h_symoff, st));
+  CKC(upload(b->pool, &B.cand_cscoff, b->h_cscoff, st));
+  CKC(b->pool.alloc(&B.cand_msym, nc, true, st));
+  // ---- adjoint maps --------------------------------------------------------
+  {
+    int* d_kmax; unsigned long long *d_h1, *d_h2;
+    CKC(b->pool.alloc(&d_kmax, 1, true, st));
+    CKC(b->pool.alloc(&d_h1, B.nA, true, st));
+    CKC(b->pool.alloc(&d_h2, B.nA, true, st));
+    long long na = (long long)B.nA * B.ndisk;
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
+    CKL();
+    int K = 0;
+    CKC(cudaMemcpyAsync(&K, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    if (K < 1) K = 1;
+    if (K > 8) return fail(HB2_ERR_CAPACITY, "more than 8 samples of one view land in one voxel (scale2d_to_3d too small)");
+    B.K = K;
+    CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.ndisk, false, st));
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
+    CKL();
+    // consistency: every hit of the forward map must appear in the adjoint map
+    long long ns = (long long)B.nA * D2 * D2;
+    if (b->idx16) k_count_hits<uint16_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint16_t*)b->d_fmap, d_h1);
+    else k_count_hits<uint32_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint32_t*)b->d_fmap, d_h1);
+    k_count_amap<<<cdiv((long long)B.nA * K * B.ndisk, 256), 256, 0, st>>>(B.nA, K, B.ndisk, b->d_amap, d_h2);
+    CKL();
+    std::vector<unsigned long long> h1(B.nA), h2(B.nA);
+    CKC(cudaMemcpyAsync(h1.data(), d_h1, 8 * B.nA, cudaMemcpyDeviceToHost, st));
+    CKC(cudaMemcpyAsync(h2.data(), d_h2, 8 * B.nA, cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    for (int a = 0; a < B.nA; ++a)
+      if (h1[a] != h2[a]) return fail(HB2_ERR_CAPACITY, "adjoint map does not cover the forward map (internal error)");
+    B.amap = b->d_amap;
+    b->pool.release(d_kmax); b->pool.release(d_h1); b->pool.release(d_h2);
+  }
+  // ---- vectors -----------------------------------------------------------------
+  size_t nv = (size_t)nc * B.npad;
+  CKC(b->pool.alloc(&B.u, (size_t)uo, true, st));
+  CKC(b->pool.alloc(&B.b, (size_t)uo, true, st));
+  CKC(b->pool.alloc(&B.v, nv, true, st));
+  CKC(b->pool.alloc(&B.h, nv, true, st));
+  CKC(b->pool.alloc(&B.xs, nv, true, st));
+  CKC(b->pool.alloc(&B.x, nv, true, st));
+  CKC(b->pool.alloc(&B.hbar, nv, true, st));
+  CKC(b->pool.alloc(&B.st, nc, true, st));
+  CKC(b->pool.alloc(&b->d_bmax, nc, false, st));
+  CKC(b->pool.alloc(&b->d_score, nc, true, st));
+  CKC(b->pool.alloc(&b->d_nactive, 1, true, st));
+  CKC(cudaMallocHost(&b->h_nactive, sizeof(int)));
+  {
+    std::vector<int> neg(nc, (int)0x80000000);  // ordered-int encoding of -inf-ish
+    CKC(cudaMemcpyAsync(b->d_bmax, neg.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+    CKC(cudaStreamSynchronize(st));
+  }
+  // partial-sum buffers
+  B.part_u_n = nviews * ntiles;
+  int max_symcap = 0;
+  for (int c = 0; c < nc; ++c) max_symcap = std::max<long long>(max_symcap, b->h_symcap[c]);
+  B.part_us_per_cand = std::max(1u, cdiv(max_symcap, HB2_BLOCK * 4));
+  const int adj_zc = B.L3 <= 2 ? 2 : 4;
+  B.part_v_per_cand = cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3, adj_zc);
+  B.part_x_per_cand = cdiv(B.n, HB2_BLOCK * 4);
+  CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
+  CKC(b->pool.alloc(&B.part_us, (size_t)nc * B.part_us_per_cand, true, st));
+  CKC(b->pool.alloc(&B.part_v, (size_t)nc * B.part_v_per_cand, true, st));
+  CKC(b->pool.alloc(&B.part_x, (size_t)nc * B.part_x_per_cand, true, st));
+  CKC(b->pool.alloc(&B.part_s, (size_t)3 * B.part_u_n, true, st));
+  // ---- right-hand side ---------------------------------------------------------
+  k_build_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
+  CKL();
+  // ---- symmetry rows -----------------------------------------------------------
+  CKC(b->pool.alloc(&b->d_sym_a, (size_t)so, false, st));
+  CKC(b->pool.alloc(&b->d_sym_b, (size_t)so, false, st));
+  B.sym_a = b->d_sym_a; B.sym_b = b->d_sym_b;
+  CKC(b->pool.alloc(&b->d_csc_ptr, (size_t)nc * (B.n + 1), true, st));
+  CKC(b->pool.alloc(&b->d_csc_ent, (size_t)2 * so, false, st));
+  B.csc_ptr = b->d_csc_ptr; B.csc_ent = b->d_csc_ent;
+  int max_rounds = 0;
+  for (int c = 0; c < nc; ++c) if (b->h_symcap[c] > 0) max_rounds = std::max(max_rounds, pair_count[c]);
+  if (max_rounds > 0 && so > 0) {
+    SymSetup Q{};
+    std::vector<double> pr((size_t)npairs * 6);
+    for (int i = 0; i < npairs; ++i) {
+      pr[6 * i] = pairs[i].ci; pr[6 * i + 1] = pairs[i].si; pr[6 * i + 2] = pairs[i].zi;
+      pr[6 * i + 3] = pairs[i].cj; pr[6 * i + 4] = pairs[i].sj; pr[6 * i + 5] = pairs[i].zj;
+    }
+    DevPool tmp;
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tmp.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CKT(upload(tmp, &Q.pairs, pr, st));
+    CKT(upload(tmp, &Q.pair_begin, pair_begin, st));
+    CKT(upload(tmp, &Q.pair_count, pair_count, st));
+    CKT(upload(tmp, &Q.min_pairs, min_pairs, st));
+    CKT(upload(tmp, &Q.tab_off, tab_off, st));
+    CKT(upload(tmp, &Q.tab_cap, tab_cap, st));
+    CKT(upload(tmp, &Q.symcap, b->h_symcap, st));
+    CKT(tmp.alloc(&Q.tab_key, (size_t)to, false, st));
+    CKT(tmp.alloc(&Q.tab_seq, (size_t)to, false, st));
+    CKT(cudaMemsetAsync(Q.tab_key, 0xFF, (size_t)to * 8, st));
+    CKT(cudaMemsetAsync(Q.tab_seq, 0xFF, (size_t)to * 8, st));
+    CKT(tmp.alloc(&Q.tmp_a, nv, false, st));
+    CKT(tmp.alloc(&Q.tmp_b, nv, false, st));
+    CKT(tmp.alloc(&Q.flag, nv, true, st));
+    CKT(tmp.alloc(&Q.pos, nv, true, st));
+    CKT(tmp.alloc(&Q.done, nc, false, st));
+    CKT(tmp.alloc(&Q.ndone, 1, true, st));
+    CKT(tmp.alloc(&Q.overflow, 1, true, st));
+    {
+      std::vector<int> done0(nc);
+      int nd0 = 0;
+      for (int c = 0; c < nc; ++c) { done0[c] = b->h_symcap[c] == 0; nd0 += done0[c]; }
+      CKT(cudaMemcpyAsync(Q.done, done0.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+      CKT(cudaMemcpyAsync(Q.ndone, &nd0, sizeof(int), cudaMemcpyHostToDevice, st));
+      CKT(cudaStreamSynchronize(st));
+    }
+    Q.sym_a_w = b->d_sym_a; Q.sym_b_w = b->d_sym_b;
+    Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym;
+    void* d_scan_tmp = nullptr; size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, Q.flag, Q.pos, (int)nv, st);
+    { char* p; CKT(tmp.alloc(&p, scan_bytes, false, st)); d_scan_tmp = p; }
+    dim3 gn(cdiv(B.n, 256), nc), gp(cdiv(B.npad, 256), nc);
+    for (int rnd = 0; rnd < max_rounds; ++rnd) {
+      k_sym_insert<<<gn, 256, 0, st>>>(B, Q, rnd);
+      k_sym_check<<<gp, 256, 0, st>>>(B, Q, rnd);
+      CKT(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, Q.flag, Q.pos, (int)nv, st));
+      k_sym_compact<<<gn, 256, 0, st>>>(B, Q);
+      k_sym_finalize<<<cdiv(nc, 128), 128, 0, st>>>(B, Q, rnd);
+      CKT(cudaGetLastError());
+      int nd = 0, ovf = 0;
+      CKT(cudaMemcpyAsync(&nd, Q.ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CKT(cudaMemcpyAsync(&ovf, Q.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CKT(cudaStreamSynchronize(st));
+      if (ovf) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "symmetry-row table overflow (internal error)"); }
+      if (nd >= nc) break;
+    }
+    CKT(cudaMemcpyAsync(b->h_msym.data(), B.cand_msym, sizeof(int) * nc, cudaMemcpyDeviceToHost, st));
+    CKT(cudaStreamSynchronize(st));
+    // transpose lists
+    int max_m = 0;
+    for (int c = 0; c < nc; ++c) max_m = std::max(max_m, b->h_msym[c]);
+    if (max_m > 0) {
+      size_t np1 = (size_t)nc * (B.n + 1);
+      int *d_cnt, *d_scan;
+      CKT(tmp.alloc(&d_cnt, np1, true, st));
+      CKT(tmp.alloc(&d_scan, np1, false, st));
+      dim3 gr(cdiv(max_m, 256), nc), gq(cdiv(B.n + 1, 256), nc);
+      k_csc_count<<<gr, 256, 0, st>>>(B, d_cnt);
+      size_t sb2 = 0; void* d_t2 = nullptr;
+      cub::DeviceScan::ExclusiveSum(nullptr, sb2, d_cnt, d_scan, (int)np1, st);
+      { char* p; CKT(tmp.alloc(&p, sb2, false, st)); d_t2 = p; }
+      CKT(cub::DeviceScan::ExclusiveSum(d_t2, sb2, d_cnt, d_scan, (int)np1, st));
+      k_csc_rebase2<<<gq, 256, 0, st>>>(B, d_scan, b->d_csc_ptr);
+      CKT(cudaMemsetAsync(d_cnt, 0, np1 * sizeof(int), st));
+      k_csc_fill<<<gr, 256, 0, st>>>(B, d_cnt, b->d_csc_ent);
+      k_csc_sort<<<gn, 256, 0, st>>>(B, b->d_csc_ent);
+      CKT(cudaGetLastError());
+    }
+    CKT(cudaStreamSynchronize(st));
+    tmp.free_all();
+  }
+  CKC(cudaStreamSynchronize(st));
+  b->created = true;
+  return HB2_OK;
+}
+
+extern "C" void hb2_batch_destroy(hb2_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->P->device);
+  cudaStreamSynchronize(b->stream);
+  b->pool.free_all();
+  if (b->h_nactive) cudaFreeHost(b->h_nactive);
+  delete b;
+}
+
+extern "C" int hb2_batch_sym_rows(hb2_batch* b, int32_t c, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity) {
+  if (!b || !b->created || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  int m = b->h_msym[c];
+  if (n_rows) *n_rows = m;
+  if (a_host && b_host) {
+    if (capacity < m) return fail(HB2_ERR_ARG, "capacity too small");
+    CK(cudaMemcpyAsync(a_host, b->d_sym_a + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b_host, b->d_sym_b + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+  }
+  return HB2_OK;
+}
+
+extern "C" int64_t hb2_batch_rows_padded(hb2_batch* b, int32_t c, int64_t* n_data_padded) {
+  if (!b || !b->created || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  if (n_data_padded) *n_data_padded = b->h_mdata[c];
+  return (int64_t)b->h_mdata[c] + b->h_msym[c];
+}
+
+extern "C" int hb2_batch_rhs(hb2_batch* b, int32_t c, float* out) {
+  if (!b || !b->created || !out || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  CK(cudaMemcpyAsync(out, b->B.b + b->h_uoff[c], sizeof(float) * b->h_mdata[c], cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------
+static void launch_fwd_data(hb2_batch* b, int mode) {
+  const BD& B = b->B;
+  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  unsigned grid = (unsigned)b->nviews * ntiles;
+  cudaStream_t st = b->stream;
+#define FWD(T, Z) k_fwd_data<T, Z><<<grid, HB2_BLOCK, 0, st>>>(B, mode)
+  if (b->idx16) {
+    if (B.L3 <= 4) FWD(uint16_t, 4); else if (B.L3 <= 8) FWD(uint16_t, 8); else if (B.L3 <= 12) FWD(uint16_t, 12); else FWD(uint16_t, 16);
+  } else {
+    if (B.L3 <= 4) FWD(uint32_t, 4); else if (B.L3 <= 8) FWD(uint32_t, 8); else if (B.L3 <= 12) FWD(uint32_t, 12); else FWD(uint32_t, 16);
+  }
+#undef FWD
+}
+static void launch_fwd_sym(hb2_batch* b, int mode) {
+  const BD& B = b->B;
+  dim3 g(B.part_us_per_cand, B.nc);
+  k_fwd_sym<<<g, HB2_BLOCK, 0, b->stream>>>(B, mode);
+}
+static void launch_adj(hb2_batch* b, int mode) {
+  const BD& B = b->B;
+  dim3 g(B.part_v_per_cand, B.nc);
+  cudaStream_t st = b->stream;
+  const bool z2 = B.L3 <= 2;
+#define ADJ(Z, K, M) k_adj<Z, K, M><<<g, HB2_BLOCK, 0, st>>>(B, mode)
+  if (B.MC == 1) {
+    if (z2) { if (B.K == 1) ADJ(2, 1, 1); else if (B.K == 2) ADJ(2, 2, 1); else ADJ(2, 0, 1); }
+    else { if (B.K == 1) ADJ(4, 1, 1); else if (B.K == 2) ADJ(4, 2, 1); else ADJ(4, 0, 1); }
+  } else {
+    if (z2) ADJ(2, 0, 0); else ADJ(4, 0, 0);
+  }
+#undef ADJ
+}
+static void launch_update(hb2_batch* b, int mode) {
+  const BD& B = b->B;
+  dim3 g(B.part_x_per_cand, B.nc);
+  k_update<<<g, HB2_BLOCK, 0, b->stream>>>(B, mode);
+}
+
+extern "C" int hb2_batch_apply_forward(hb2_batch* b, int32_t c, const float* x_host, float* y_host) {
+  if (!b || !b->created || !x_host || !y_host || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  BD& B = b->B;
+  cudaStream_t st = b->stream;
+  long long m = (long long)b->h_mdata[c] + b->h_msym[c];
+  CK(cudaMemcpyAsync(B.xs + (size_t)c * B.npad, x_host, sizeof(float) * B.n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(B.u + b->h_uoff[c], 0, sizeof(float) * m, st));
+  B.only_cand = c;
+  launch_fwd_data(b, MODE_PLAIN);
+  launch_fwd_sym(b, MODE_PLAIN);
+  B.only_cand = -1;
+  CKL();
+  CK(cudaMemcpyAsync(y_host, B.u + b->h_uoff[c], sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  b->solved = false;
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_apply_adjoint(hb2_batch* b, int32_t c, const float* y_host, float* x_host) {
+  if (!b || !b->created || !x_host || !y_host || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  BD& B = b->B;
+  cudaStream_t st = b->stream;
+  long long m = (long long)b->h_mdata[c] + b->h_msym[c];
+  CK(cudaMemcpyAsync(B.u + b->h_uoff[c], y_host, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+  B.only_cand = c;
+  launch_adj(b, MODE_PLAIN);
+  B.only_cand = -1;
+  CKL();
+  CK(cudaMemcpyAsync(x_host, B.xs + (size_t)c * B.npad, sizeof(float) * B.n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  b->solved = false;
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// solve + score
+// ---------------------------------------------------------------------------
+extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_result* res) {
+  if (!b || !b->created || !opt || !res) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  BD& B = b->B;
+  cudaStream_t st = b->stream;
+  const int nc = B.nc;
+  const int maxit = opt->max_iter > 0 ? opt->max_iter : 1000;
+  const int check = opt->check_every > 0 ? opt->check_every : 8;
+  B.clip_pred = opt->clip_pred;
+  B.only_cand = -1;
+  cudaEvent_t e0, e1, e2;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
+  CK(cudaEventRecord(e0, st));
+  size_t nv = (size_t)nc * B.npad;
+  CK(cudaMemsetAsync(B.x, 0, nv * sizeof(double), st));
+  CK(cudaMemsetAsync(B.hbar, 0, nv * sizeof(double), st));
+  CK(cudaMemsetAsync(B.h, 0, nv * sizeof(float), st));
+  CK(cudaMemsetAsync(B.v, 0, nv * sizeof(float), st));
+  CK(cudaMemcpyAsync(B.u, B.b, sizeof(float) * (size_t)b->u_total, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(b->d_nactive, 0, sizeof(int), st));
+  long long launches = 0;
+  k_scal_normb<<<nc, HB2_BLOCK, 0, st>>>(B);
+  launch_adj(b, MODE_INIT);
+  k_scal_init<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_nactive);
+  launch_update(b, MODE_INIT);
+  launches += 4;
+  CKL();
+  int it = 0;
+  *b->h_nactive = 1;
+  CK(cudaMemcpyAsync(b->h_nactive, b->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  while (*b->h_nactive > 0 && it < maxit) {
+    int burst = std::min(check, maxit - it);
+    for (int q = 0; q < burst; ++q) {
+      launch_fwd_data(b, MODE_LSMR);
+      launch_fwd_sym(b, MODE_LSMR);
+      k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B);
+      launch_adj(b, MODE_LSMR);
+      k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B);
+      launch_update(b, MODE_LSMR);
+      k_scal_test<<<nc, HB2_BLOCK, 0, st>>>(B, opt->atol, opt->btol, opt->conlim, maxit, opt->fixed_iters, b->d_nactive);
+      launches += 7;
+    }
+    it += burst;
+    CKL();
+    CK(cudaMemcpyAsync(b->h_nactive, b->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  CK(cudaEventRecord(e1, st));
+  // score: reprojection of float32(x) + cosine similarity
+  {
+    dim3 g(cdiv(B.n, 256), nc);
+    k_x_to_f32<<<g, 256, 0, st>>>(B);
+    launch_fwd_data(b, MODE_SCORE);
+    k_scal_score<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_score);
+    launches += 3;
+    CKL();
+  }
+  CK(cudaEventRecord(e2, st));
+  std::vector<LsmrState> hs(nc);
+  std::vector<float> sc(nc);
+  CK(cudaMemcpyAsync(hs.data(), B.st, sizeof(LsmrState) * nc, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(sc.data(), b->d_score, sizeof(float) * nc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float ms_l = 0, ms_s = 0;
+  cudaEventElapsedTime(&ms_l, e0, e1); cudaEventElapsedTime(&ms_s, e1, e2);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  b->timing[0] = ms_l; b->timing[1] = 0; b->timing[2] = ms_s; b->timing[3] = (double)launches; b->timing[4] = it;
+  for (int c = 0; c < nc; ++c) {
+    hb2_result& r = res[c];
+    r.score = sc[c]; r.itn = hs[c].itn; r.istop = hs[c].istop; r.trf_nit = 0;
+    r.flags = b->cand_flags[c];
+    r.n_data_rows = 0; r.n_sym_rows = b->h_msym[c];
+    r.normr = (float)hs[c].normr; r.normar = hs[c].normar; r.normA = (float)hs[c].normA; r.normx = (float)hs[c].normx;
+  }
+  b->solved = true;
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_get_x(hb2_batch* b, int32_t c, float* x_host) {
+  if (!b || !b->solved || !x_host || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument or batch not solved");
+  CK(cudaSetDevice(b->P->device));
+  CK(cudaMemcpyAsync(x_host, b->B.xs + (size_t)c * b->B.npad, sizeof(float) * b->B.n, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_timing(hb2_batch* b, double* out8) {
+  if (!b || !out8) return fail(HB2_ERR_ARG, "null argument");
+  memcpy(out8, b->timing, sizeof(b->timing));
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host test hook for the scalar recurrences
+// ---------------------------------------------------------------------------
+extern "C" int hb2_lsmr_scalar_step(double* state64, int phase, float alpha, float beta, double normx, double atol,
+                                    double btol, double conlim, int maxiter, float* coef_hbar, float* coef_x,
+                                    float* coef_h, double* trace8) {
+  static_assert(sizeof(LsmrState) <= 64 * sizeof(double), "state scratch too small");
+  LsmrState S;
+  memcpy(&S, state64, sizeof(S));
+  int ret = 0;
+  if (phase == 0) lsmr_init_(S, alpha, beta);
+  else if (phase == 1) lsmr_rotate_(S, alpha, beta);
+  else ret = lsmr_test_(S, normx, atol, btol, conlim, maxiter);
+  memcpy(state64, &S, sizeof(S));
+  if (coef_hbar) *coef_hbar = S.cf_hbar;
+  if (coef_x) *coef_x = S.cf_x;
+  if (coef_h) *coef_h = S.cf_h;
+  if (trace8) {
+    trace8[0] = S.rho; trace8[1] = S.rhobar; trace8[2] = S.zeta; trace8[3] = S.normr; trace8[4] = S.normA;
+    trace8[5] = S.test1; trace8[6] = S.test2; trace8[7] = S.active;
+  }
+  return ret;
+}

@@ -1,0 +1,773 @@
+// CUDA kernels of the denovo3D hot path (sm_100a).  See DESIGN.md for the
+// data layout; reference line numbers are SLR = solver_linear_regression.py.
+#pragma once
+#include "hb2_common.cuh"
+
+#define HB2_MAX_ZMC 1024   // L3*MC columns per view kept in shared memory
+#define HB2_TILE_RAYS 32   // rays per CTA of the forward projector
+#define HB2_BLOCK 256
+
+enum { MODE_LSMR = 0, MODE_PLAIN = 1, MODE_SCORE = 2, MODE_INIT = 3 };
+
+// Batch descriptor passed by value to every kernel.
+struct BD {
+  // geometry (batch-uniform)
+  int D2, L2, D3, ndisk, L3, MC, ZMC, n, npad, rows_per_view;
+  int nA, K, nc;
+  double s;
+  // in-plane maps
+  const void* fmap;            // [nA][D2][D2] disk rank or SENT
+  const uint8_t* rayvalid;     // [nA][D2]
+  const uint16_t* amap;        // [nA][K][ndisk] ray j of the k-th sample landing in voxel p, or 0xFFFF
+  // views (flat over the batch)
+  const int* view_cand;
+  const int* view_angle;
+  const int* view_colbegin;
+  const long long* view_uoff;  // absolute offset of the view's padded rows in u
+  const int* colk;
+  // candidates
+  const int* cand_view_begin;
+  const int* cand_view_count;
+  const long long* cand_uoff;    // start of the candidate's rows in u
+  const int* cand_mdata;         // padded data rows
+  const long long* cand_symoff;  // offset into sym_a/sym_b
+  const long long* cand_cscoff;  // offset into csc_ent
+  int* cand_msym;                // symmetry rows (device-updated during setup)
+  // vectors
+  float* u;        // rows: [data padded | symmetry] per candidate
+  float* b;        // same layout, data part only meaningful
+  float* v;        // [nc][npad]
+  float* h;        // [nc][npad]
+  float* xs;       // [nc][npad] float32 copy of x (score / operator tests)
+  double* x;       // [nc][npad]
+  double* hbar;    // [nc][npad]
+  // symmetry operator
+  const int* sym_a;
+  const int* sym_b;
+  const int* csc_ptr;   // [nc][n+1]
+  const int* csc_ent;   // row | sign<<31
+  // solver state
+  LsmrState* st;
+  float* part_u;   // per-CTA partial sums of squares
+  float* part_us;  // symmetry rows part
+  float* part_v;
+  double* part_x;
+  float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
+  int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
+  int only_cand;   // MODE_PLAIN: restrict to one candidate (-1 all)
+  int clip_pred;
+};
+
+template <typename T>
+struct Sent;
+template <>
+struct Sent<uint16_t> { static constexpr uint16_t v = 0xFFFFu; };
+template <>
+struct Sent<uint32_t> { static constexpr uint32_t v = 0xFFFFFFFFu; };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block reduction (blockDim.x == HB2_BLOCK), result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (HB2_BLOCK / 32) ? sh[l] : 0.f;
+    r = warp_sum(r);
+  }
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  v = warp_sum_d(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = l < (HB2_BLOCK / 32) ? sh[l] : 0.0;
+    r = warp_sum_d(r);
+  }
+  __syncthreads();
+  return r;
+}
+
+// ===========================================================================
+// setup: in-plane sample -> voxel maps (replaces SLR:1514-1557 + 1614-1620)
+// ===========================================================================
+// One thread per (angle, ray j, depth i).  Coordinates follow the reference's
+// float64 operation sequence: back_project (SLR:1712-1719, noise-free nominal
+// column), Rotation.apply(inverse=True) = fma(M10,y,M00*x) / fma(M11,y,M01*x)
+// (the order scipy executes, verified bit-exact in tests), + D2//2, rint.
+template <typename IdxT>
+__global__ void k_build_fmap(int nA, int D2, double s, const double* __restrict__ cs, const int* __restrict__ rank,
+                             IdxT* __restrict__ fmap, uint8_t* __restrict__ rayvalid, int* __restrict__ tie) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nA * D2 * D2;
+  if (t >= total) return;
+  int i = (int)(t % D2);
+  int j = (int)((t / D2) % D2);
+  int a = (int)(t / ((long long)D2 * D2));
+  const int c0 = D2 / 2;
+  double C = cs[2 * a], S = cs[2 * a + 1];
+  // x' = fma(-1, Zd, e*Xl) with Xl = 0 (nominal column): -(i - c0); y' = j - c0
+  double x0 = -(double)(i - c0), y0 = (double)(j - c0);
+  if (s != 1.0) { x0 = __dmul_rn(x0, s); y0 = __dmul_rn(y0, s); }
+  double X = __dadd_rn(__fma_rn(S, y0, __dmul_rn(C, x0)), (double)c0);
+  double Y = __dadd_rn(__fma_rn(C, y0, __dmul_rn(-S, x0)), (double)c0);
+  double xr = rint(X), yr = rint(Y);
+  IdxT out = Sent<IdxT>::v;
+  bool inb = xr >= 0.0 && xr <= (double)(D2 - 1) && yr >= 0.0 && yr <= (double)(D2 - 1);
+  if (inb) {
+    int r = rank[(int)yr * D2 + (int)xr];
+    if (r >= 0) {
+      out = (IdxT)r;
+      rayvalid[a * D2 + j] = 1;  // benign race: all writers store 1
+    }
+  }
+  fmap[t] = out;
+  // tie detector: a rounding decision within 1e-9 of a boundary
+  // may follow the reference's last-bit coordinate noise instead of ours.
+  if (X > -1.0 && X < (double)D2 && Y > -1.0 && Y < (double)D2) {
+    double fx = fabs(fabs(X - floor(X)) - 0.5), fy = fabs(fabs(Y - floor(Y)) - 0.5);
+    if (fx < 1e-9 || fy < 1e-9) atomicAdd(&tie[a], 1);
+  }
+}
+
+// Adjoint map, voxel-driven: for voxel p and angle a list the rays j of all
+// samples (j,i) with fmap[a][j][i] == p, j-major then i (deterministic).
+// pass 0: count only (max multiplicity -> *kmax); pass 1: fill amap[a][k][p].
+template <typename IdxT>
+__global__ void k_build_amap(int nA, int D2, int ndisk, double s, int K, int pass, const double* __restrict__ cs,
+                             const short2* __restrict__ disk_yx, const IdxT* __restrict__ fmap,
+                             uint16_t* __restrict__ amap, int* __restrict__ kmax) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nA * ndisk) return;
+  int p = (int)(t % ndisk), a = (int)(t / ndisk);
+  const int c0 = D2 / 2;
+  double C = cs[2 * a], S = cs[2 * a + 1];
+  short2 yx = disk_yx[p];
+  double dx = (double)(yx.y - c0), dy = (double)(yx.x - c0);  // yx.x = row y, yx.y = column x
+  // inverse rotation: x0 = C*dx - S*dy, y0 = S*dx + C*dy ; i = c0 - x0/s ; j = c0 + y0/s
+  double x0 = C * dx - S * dy, y0 = S * dx + C * dy;
+  double is = c0 - x0 / s, js = c0 + y0 / s;
+  double rad = 0.7072 / s + 0.02;
+  int i0 = max(0, (int)ceil(is - rad)), i1 = min(D2 - 1, (int)floor(is + rad));
+  int j0 = max(0, (int)ceil(js - rad)), j1 = min(D2 - 1, (int)floor(js + rad));
+  const IdxT* fm = fmap + (size_t)a * D2 * D2;
+  int cnt = 0;
+  for (int j = j0; j <= j1; ++j)
+    for (int i = i0; i <= i1; ++i)
+      if (fm[(size_t)j * D2 + i] == (IdxT)p) {
+        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * ndisk + p] = (uint16_t)j;
+        ++cnt;
+      }
+  if (pass == 0) {
+    if (cnt > 0) atomicMax(kmax, cnt);
+  } else {
+    for (int k = cnt; k < K; ++k) amap[((size_t)a * K + k) * ndisk + p] = 0xFFFFu;
+  }
+}
+
+// total samples with a hit per angle (consistency check of the adjoint map)
+template <typename IdxT>
+__global__ void k_count_hits(int nA, int D2, const IdxT* __restrict__ fmap, unsigned long long* __restrict__ hits) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nA * D2 * D2) return;
+  if (fmap[t] != Sent<IdxT>::v) atomicAdd(&hits[t / ((long long)D2 * D2)], 1ull);
+}
+__global__ void k_count_amap(int nA, int K, int ndisk, const uint16_t* __restrict__ amap,
+                             unsigned long long* __restrict__ hits) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nA * K * ndisk) return;
+  if (amap[t] != 0xFFFFu) atomicAdd(&hits[t / ((long long)K * ndisk)], 1ull);
+}
+
+// right-hand side in padded layout: b[view][z][mc][j] = pix[j][k] when the
+// column exists and the ray has data (SLR:1548), else 0.  Also max(b) per
+// candidate (upper bound of the positive constraint, SLR:248).
+__global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, float* __restrict__ bmax_bits) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nviews * B.rows_per_view;
+  if (t >= total) return;
+  int view = (int)(t / B.rows_per_view);
+  int r = (int)(t % B.rows_per_view);
+  int j = r % B.D2, zm = r / B.D2;
+  int k = B.colk[B.view_colbegin[view] + zm];
+  int a = B.view_angle[view];
+  float val = 0.f;
+  if (k >= 0 && B.rayvalid[a * B.D2 + j]) {
+    val = pix[(size_t)j * B.L2 + k];
+    // float max via ordered-int trick
+    int c = B.view_cand[view];
+    int iv = __float_as_int(val);
+    iv = iv >= 0 ? iv : iv ^ 0x7fffffff;
+    atomicMax((int*)bmax_bits + c, iv);
+  }
+  B.b[B.view_uoff[view] + r] = val;
+}
+
+// ===========================================================================
+// symmetry rows (replaces SLR:1142-1218, 1221-1287)
+// ===========================================================================
+struct SymSetup {
+  const double* pairs;          // [npairs][6] ci,si,zi,cj,sj,zj
+  const int* pair_begin;
+  const int* pair_count;
+  const long long* min_pairs;
+  const long long* tab_off;     // hash table offset per candidate
+  const long long* tab_cap;
+  unsigned long long* tab_key;
+  unsigned long long* tab_seq;
+  int* tmp_a;                   // [nc][npad]
+  int* tmp_b;
+  int* flag;                    // [nc][npad]
+  int* pos;                     // exclusive scan of flag
+  int* done;                    // [nc]
+  int* ndone;                   // [1]
+  int* sym_a_w;
+  int* sym_b_w;
+  const int* rank_sym;          // [D3*D3]
+  const short2* disk_yx_sym;    // [ndisk]
+  const long long* symcap;
+  int* overflow;
+};
+
+#define HB2_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+// image of voxel (zc,yc,xc centred) under one pair member, SLR:1225-1243:
+//   X = fma(-S,y,C*x) + D3//2 ; Y = fma(C,y,S*x) + D3//2 ; Z = (z + L3//2) + rise*h ; rint each.
+__device__ __forceinline__ int sym_image(double C, double S, double zs, int xc, int yc, int zc, int D3, int L3,
+                                         int ndisk, const int* __restrict__ rank) {
+  double x = (double)xc, y = (double)yc;
+  double X = __dadd_rn(__fma_rn(-S, y, __dmul_rn(C, x)), (double)(D3 / 2));
+  double Y = __dadd_rn(__fma_rn(C, y, __dmul_rn(S, x)), (double)(D3 / 2));
+  double Z = __dadd_rn(__dadd_rn((double)zc, (double)(L3 / 2)), zs);
+  double xr = rint(X), yr = rint(Y), zr = rint(Z);
+  if (!(zr >= 0.0 && zr <= (double)(L3 - 1) && yr >= 0.0 && yr <= (double)(D3 - 1) && xr >= 0.0 &&
+        xr <= (double)(D3 - 1)))
+    return -1;
+  int r = rank[(int)yr * D3 + (int)xr];
+  if (r < 0) return -1;
+  return (int)zr * ndisk + r;
+}
+
+// round `rnd`: every still-open candidate processes its rnd-th pair.
+// phase 0: compute (a,b) per voxel, insert unordered key with min sequence number.
+__global__ void k_sym_insert(BD B, SymSetup Q, int rnd) {
+  int c = blockIdx.y;
+  if (Q.done[c]) return;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B.n) return;
+  const double* pr = Q.pairs + (size_t)(Q.pair_begin[c] + rnd) * 6;
+  int z = g / B.ndisk, p = g % B.ndisk;
+  short2 yx = Q.disk_yx_sym[p];
+  int xc = yx.y - B.D3 / 2, yc = yx.x - B.D3 / 2, zc = z - B.L3 / 2;
+  int a = sym_image(pr[0], pr[1], pr[2], xc, yc, zc, B.D3, B.L3, B.ndisk, Q.rank_sym);
+  int b = sym_image(pr[3], pr[4], pr[5], xc, yc, zc, B.D3, B.L3, B.ndisk, Q.rank_sym);
+  size_t ti = (size_t)c * B.npad + g;
+  if (a < 0 || b < 0) {
+    Q.tmp_a[ti] = -1; Q.tmp_b[ti] = -1;
+    return;
+  }
+  Q.tmp_a[ti] = a; Q.tmp_b[ti] = b;
+  unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+  unsigned long long key = ((unsigned long long)lo << 32) | hi;
+  unsigned long long seq = (unsigned long long)rnd * (unsigned long long)B.n + (unsigned long long)g;
+  unsigned long long cap = (unsigned long long)Q.tab_cap[c];
+  unsigned long long* keys = Q.tab_key + Q.tab_off[c];
+  unsigned long long* seqs = Q.tab_seq + Q.tab_off[c];
+  unsigned long long slot = hash64(key) % cap;
+  for (unsigned long long probe = 0; probe < cap; ++probe) {
+    unsigned long long old = atomicCAS(&keys[slot], HB2_EMPTY_KEY, key);
+    if (old == HB2_EMPTY_KEY || old == key) {
+      atomicMin(&seqs[slot], seq);
+      return;
+    }
+    slot = slot + 1 == cap ? 0 : slot + 1;
+  }
+  atomicExch(Q.overflow, 1);
+}
+
+// phase 1: a candidate row survives iff its sequence number is the table minimum
+// (first-seen-wins over pairs in list order, then voxels in mask order, SLR:1197-1202).
+__global__ void k_sym_check(BD B, SymSetup Q, int rnd) {
+  int c = blockIdx.y;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B.npad) return;
+  size_t ti = (size_t)c * B.npad + g;
+  int keep = 0;
+  if (!Q.done[c] && g < B.n) {
+    int a = Q.tmp_a[ti], b = Q.tmp_b[ti];
+    if (a >= 0) {
+      unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
+      unsigned long long key = ((unsigned long long)lo << 32) | hi;
+      unsigned long long seq = (unsigned long long)rnd * (unsigned long long)B.n + (unsigned long long)g;
+      unsigned long long cap = (unsigned long long)Q.tab_cap[c];
+      const unsigned long long* keys = Q.tab_key + Q.tab_off[c];
+      const unsigned long long* seqs = Q.tab_seq + Q.tab_off[c];
+      unsigned long long slot = hash64(key) % cap;
+      for (unsigned long long probe = 0; probe < cap; ++probe) {
+        unsigned long long kk = keys[slot];
+        if (kk == key) { keep = seqs[slot] == seq; break; }
+        if (kk == HB2_EMPTY_KEY) break;
+        slot = slot + 1 == cap ? 0 : slot + 1;
+      }
+    }
+  }
+  Q.flag[ti] = keep;
+}
+
+// phase 2: ordered compaction (row order = voxel order inside the pair block)
+__global__ void k_sym_compact(BD B, SymSetup Q) {
+  int c = blockIdx.y;
+  if (Q.done[c]) return;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B.n) return;
+  size_t ti = (size_t)c * B.npad + g;
+  if (!Q.flag[ti]) return;
+  long long row = (long long)B.cand_msym[c] + (Q.pos[ti] - Q.pos[(size_t)c * B.npad]);
+  if (row >= Q.symcap[c]) { atomicExch(Q.overflow, 2); return; }
+  Q.sym_a_w[B.cand_symoff[c] + row] = Q.tmp_a[ti];
+  Q.sym_b_w[B.cand_symoff[c] + row] = Q.tmp_b[ti];
+}
+
+// phase 3: row count + early stop (SLR:1286) per candidate
+__global__ void k_sym_finalize(BD B, SymSetup Q, int rnd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B.nc || Q.done[c]) return;
+  size_t last = (size_t)c * B.npad + (B.npad - 1);
+  int cnt = Q.pos[last] + Q.flag[last] - Q.pos[(size_t)c * B.npad];
+  int tot = B.cand_msym[c] + cnt;
+  B.cand_msym[c] = tot;
+  if ((long long)tot >= Q.min_pairs[c] || rnd + 1 >= Q.pair_count[c]) {
+    Q.done[c] = 1;
+    atomicAdd(Q.ndone, 1);
+  }
+}
+
+// transpose lists of the symmetry rows: per voxel the incident rows (+ sign)
+__global__ void k_csc_count(BD B, int* __restrict__ cnt) {
+  int c = blockIdx.y;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.cand_msym[c]) return;
+  int a = B.sym_a[B.cand_symoff[c] + r], b = B.sym_b[B.cand_symoff[c] + r];
+  atomicAdd(&cnt[(size_t)c * (B.n + 1) + a], 1);
+  atomicAdd(&cnt[(size_t)c * (B.n + 1) + b], 1);
+}
+__global__ void k_csc_rebase2(BD B, const int* __restrict__ scan, int* __restrict__ ptr) {
+  int c = blockIdx.y;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > B.n) return;
+  ptr[(size_t)c * (B.n + 1) + g] = scan[(size_t)c * (B.n + 1) + g] - scan[(size_t)c * (B.n + 1)];
+}
+__global__ void k_csc_fill(BD B, int* __restrict__ cursor, int* __restrict__ ent) {
+  int c = blockIdx.y;
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B.cand_msym[c]) return;
+  int a = B.sym_a[B.cand_symoff[c] + r], b = B.sym_b[B.cand_symoff[c] + r];
+  const int* ptr = B.csc_ptr + (size_t)c * (B.n + 1);
+  int sa = atomicAdd(&cursor[(size_t)c * (B.n + 1) + a], 1);
+  ent[B.cand_cscoff[c] + ptr[a] + sa] = r;
+  int sb = atomicAdd(&cursor[(size_t)c * (B.n + 1) + b], 1);
+  ent[B.cand_cscoff[c] + ptr[b] + sb] = r | (int)0x80000000;
+}
+__global__ void k_csc_sort(BD B, int* __restrict__ ent) {  // deterministic order: by row index
+  int c = blockIdx.y;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B.n) return;
+  const int* ptr = B.csc_ptr + (size_t)c * (B.n + 1);
+  int e0 = ptr[g], e1 = ptr[g + 1];
+  int* e = ent + B.cand_cscoff[c];
+  for (int i = e0 + 1; i < e1; ++i) {
+    int key = e[i];
+    unsigned kr = ((unsigned)key & 0x7fffffffu) * 2u + ((unsigned)key >> 31);
+    int j = i - 1;
+    while (j >= e0) {
+      unsigned jr = ((unsigned)e[j] & 0x7fffffffu) * 2u + ((unsigned)e[j] >> 31);
+      if (jr <= kr) break;
+      e[j + 1] = e[j];
+      --j;
+    }
+    e[j + 1] = key;
+  }
+}
+
+// ===========================================================================
+// forward projector: data rows.  One CTA = 32 consecutive rays of one view.
+// Each warp walks a ray: lanes over depth samples, gathers the L3 slices at the
+// same in-plane voxel (the in-plane map is z-independent), warp-shuffle reduces.
+// MODE_LSMR : u~ <- A v - alpha * (u~ * inv_beta)       (lsmr.py:331-332)
+// MODE_PLAIN: u  <- A xs
+// MODE_SCORE: accumulate <pred,b>, <pred,pred>, <b,b>   (SLR:500-525)
+// ===========================================================================
+template <typename IdxT, int ZC>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
+  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
+  const int c = B.view_cand[view];
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ int s_colk[HB2_MAX_ZMC];
+  const LsmrState& S = B.st[c];
+  bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  if (!act) {
+    if (threadIdx.x == 0) {
+      if (mode == MODE_LSMR) B.part_u[blockIdx.x] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * blockIdx.x] = 0.f; B.part_s[3 * blockIdx.x + 1] = 0.f; B.part_s[3 * blockIdx.x + 2] = 0.f; }
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < B.ZMC; e += HB2_BLOCK) s_colk[e] = B.colk[B.view_colbegin[view] + e];
+  __syncthreads();
+  const float alpha = S.alpha, inv_beta = S.inv_beta;
+  const int a = B.view_angle[view];
+  const int D2 = B.D2, L3 = B.L3, MC = B.MC, ndisk = B.ndisk;
+  const IdxT* __restrict__ fm = (const IdxT*)B.fmap + (size_t)a * D2 * D2;
+  const float* __restrict__ vsrc = (mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad;
+  float* urow = B.u + B.view_uoff[view];
+  const float* brow = B.b + B.view_uoff[view];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  for (int r = warp; r < HB2_TILE_RAYS; r += HB2_BLOCK / 32) {
+    const int j = tile * HB2_TILE_RAYS + r;
+    if (j >= D2) break;
+    if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
+    const IdxT* __restrict__ fj = fm + (size_t)j * D2;
+    for (int z0 = 0; z0 < L3; z0 += ZC) {
+      unsigned zmask = 0;
+#pragma unroll
+      for (int zz = 0; zz < ZC; ++zz) {
+        int z = z0 + zz;
+        if (z < L3)
+          for (int mc = 0; mc < MC; ++mc)
+            if (s_colk[z * MC + mc] >= 0) zmask |= 1u << zz;
+      }
+      if (!zmask) continue;
+      float acc[ZC];
+#pragma unroll
+      for (int zz = 0; zz < ZC; ++zz) acc[zz] = 0.f;
+      for (int t = lane; t < D2; t += 32) {
+        IdxT id = fj[t];
+        if (id != Sent<IdxT>::v) {
+          const float* __restrict__ vp = vsrc + (size_t)z0 * ndisk + id;
+#pragma unroll
+          for (int zz = 0; zz < ZC; ++zz)
+            if (zmask & (1u << zz)) acc[zz] += __ldg(vp + (size_t)zz * ndisk);
+        }
+      }
+#pragma unroll
+      for (int zz = 0; zz < ZC; ++zz) acc[zz] = warp_sum(acc[zz]);
+      // lane e writes column (zz = e / MC, mc = e % MC)
+      for (int e = lane; e < ZC * MC; e += 32) {
+        int zz = e / MC, mc = e - zz * MC, z = z0 + zz;
+        if (z >= L3 || s_colk[z * MC + mc] < 0) continue;
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < ZC; ++q) sum = (q == zz) ? acc[q] : sum;
+        size_t ri = (size_t)(z * MC + mc) * D2 + j;
+        if (mode == MODE_LSMR) {
+          float un = fadd_(fmul_(fmul_(urow[ri], inv_beta), -alpha), sum);
+          urow[ri] = un;
+          ss += un * un;
+        } else if (mode == MODE_PLAIN) {
+          urow[ri] = sum;
+        } else {
+          float pred = B.clip_pred ? fmaxf(sum, 0.f) : sum;
+          float bv = brow[ri];
+          ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+        }
+      }
+    }
+  }
+  if (mode == MODE_LSMR) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_u[blockIdx.x] = tot;
+  } else if (mode == MODE_SCORE) {
+    float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
+    if (threadIdx.x == 0) { B.part_s[3 * blockIdx.x] = t0; B.part_s[3 * blockIdx.x + 1] = t1; B.part_s[3 * blockIdx.x + 2] = t2; }
+  }
+}
+
+// forward, symmetry rows: u~[r] <- (v[a]-v[b]) - alpha*(u~[r]*inv_beta)
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_sym(BD B, int mode) {
+  const int c = blockIdx.y;
+  __shared__ float red[HB2_BLOCK / 32];
+  const LsmrState& S = B.st[c];
+  bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  const int pi = c * B.part_us_per_cand + blockIdx.x;
+  if (!act) {
+    if (threadIdx.x == 0 && mode == MODE_LSMR) B.part_us[pi] = 0.f;
+    return;
+  }
+  const int m = B.cand_msym[c];
+  const float alpha = S.alpha, inv_beta = S.inv_beta;
+  const float* __restrict__ vsrc = (mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad;
+  float* us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
+  const int* __restrict__ sa = B.sym_a + B.cand_symoff[c];
+  const int* __restrict__ sb = B.sym_b + B.cand_symoff[c];
+  float ss = 0.f;
+  for (int r = blockIdx.x * HB2_BLOCK * 4 + threadIdx.x, q = 0; q < 4; ++q, r += HB2_BLOCK) {
+    if (r < m) {
+      float d = fadd_(__ldg(vsrc + sa[r]), -__ldg(vsrc + sb[r]));
+      if (mode == MODE_LSMR) {
+        float un = fadd_(fmul_(fmul_(us[r], inv_beta), -alpha), d);
+        us[r] = un;
+        ss += un * un;
+      } else {
+        us[r] = d;
+      }
+    }
+  }
+  if (mode == MODE_LSMR) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_us[pi] = tot;
+  }
+}
+
+// ===========================================================================
+// adjoint: voxel-driven gather.  One thread = one in-plane voxel p and a chunk
+// of ZC slices; loops over the candidate's views, reads the adjoint map once per
+// view and gathers the rays' rows for every slice of the chunk; then adds the
+// symmetry rows incident to each voxel.
+// MODE_LSMR : v~ <- A^T (u~*inv_beta) - beta * v        (lsmr.py:336-338)
+// MODE_INIT : v~ <- A^T (u~*inv_beta)                    (lsmr.py:251)
+// MODE_PLAIN: xs <- A^T u
+// ===========================================================================
+template <int ZC, int KT, int MCT>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
+  const int c = blockIdx.y;
+  __shared__ float red[HB2_BLOCK / 32];
+  const LsmrState& S = B.st[c];
+  bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
+                                 : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
+  const int pi = c * B.part_v_per_cand + blockIdx.x;
+  if (!act) {
+    if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
+    return;
+  }
+  const int L3 = B.L3, D2 = B.D2, ndisk = B.ndisk;
+  const int K = KT > 0 ? KT : B.K, MC = MCT > 0 ? MCT : B.MC;
+  const int nzch = (L3 + ZC - 1) / ZC;
+  const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
+  const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * ZC;
+  const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
+  const float beta = S.beta;
+  float ss = 0.f;
+  if (p < ndisk) {
+    float acc[ZC];
+#pragma unroll
+    for (int zz = 0; zz < ZC; ++zz) acc[zz] = 0.f;
+    const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+    for (int vi = 0; vi < nv; ++vi) {
+      const int view = vb + vi;
+      const int a = __ldg(B.view_angle + view);
+      const float* __restrict__ ub = B.u + __ldg(B.view_uoff + view) + (size_t)z0 * MC * D2;
+      const uint16_t* __restrict__ am = B.amap + (size_t)a * K * ndisk + p;
+#pragma unroll
+      for (int k = 0; k < (KT > 0 ? KT : 8); ++k) {
+        if (k >= K) break;
+        uint16_t j = am[(size_t)k * ndisk];
+        if (j != 0xFFFFu) {
+          const float* __restrict__ uj = ub + j;
+#pragma unroll
+          for (int zz = 0; zz < ZC; ++zz) {
+            if (z0 + zz < L3) {
+              for (int mc = 0; mc < MC; ++mc) acc[zz] = fmaf(__ldg(uj + (size_t)(zz * MC + mc) * D2), ib, acc[zz]);
+            }
+          }
+        }
+      }
+    }
+    // symmetry rows incident to (z,p)
+    const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.n + 1);
+    const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
+    const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
+    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad;
+#pragma unroll
+    for (int zz = 0; zz < ZC; ++zz) {
+      int z = z0 + zz;
+      if (z < L3) {
+        int g = z * ndisk + p;
+        int e0 = ptr[g], e1 = ptr[g + 1];
+        float a2 = acc[zz];
+        for (int e = e0; e < e1; ++e) {
+          int en = ent[e];
+          float val = __ldg(us + (en & 0x7fffffff));
+          a2 = fmaf(en < 0 ? -val : val, ib, a2);
+        }
+        float vn = a2;
+        if (mode == MODE_LSMR) vn = fadd_(fmul_(vdst[g], -beta), a2);
+        vdst[g] = vn;
+        ss += vn * vn;
+      }
+    }
+  }
+  if (mode != MODE_PLAIN) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_v[pi] = tot;
+  }
+}
+
+// ===========================================================================
+// vector update (lsmr.py:364-368) fused with v normalisation and ||x||^2
+// ===========================================================================
+__global__ void __launch_bounds__(HB2_BLOCK) k_update(BD B, int mode) {
+  const int c = blockIdx.y;
+  __shared__ double redd[HB2_BLOCK / 32];
+  const LsmrState& S = B.st[c];
+  const int pi = c * B.part_x_per_cand + blockIdx.x;
+  if (!S.active) {
+    if (threadIdx.x == 0) B.part_x[pi] = 0.0;
+    return;
+  }
+  const float ia = S.inv_alpha;
+  const double cfhb = (double)S.cf_hbar, cfx = (double)S.cf_x;
+  const float cfh = S.cf_h;
+  const bool normalise = !(mode == MODE_LSMR && S.skip_adj);
+  float* v = B.v + (size_t)c * B.npad;
+  float* h = B.h + (size_t)c * B.npad;
+  double* x = B.x + (size_t)c * B.npad;
+  double* hbar = B.hbar + (size_t)c * B.npad;
+  double sx = 0.0;
+  for (int i = blockIdx.x * HB2_BLOCK * 4 + threadIdx.x, q = 0; q < 4; ++q, i += HB2_BLOCK) {
+    if (i < B.n) {
+      float vn = v[i];
+      if (normalise) { vn = fmul_(vn, ia); v[i] = vn; }
+      if (mode == MODE_INIT) {
+        h[i] = vn; hbar[i] = 0.0; x[i] = 0.0;
+      } else {
+        float ho = h[i];
+        double hb = dadd_(dmul_(hbar[i], cfhb), (double)ho);
+        hbar[i] = hb;
+        double xn = dadd_(x[i], dmul_(cfx, hb));
+        x[i] = xn;
+        h[i] = fadd_(fmul_(ho, cfh), vn);
+        sx += xn * xn;
+      }
+    }
+  }
+  double tot = block_sum_d(sx, redd);
+  if (threadIdx.x == 0) B.part_x[pi] = tot;
+}
+
+// x (float64) -> xs (float32), SLR:270
+__global__ void k_x_to_f32(BD B) {
+  const int c = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n) B.xs[(size_t)c * B.npad + i] = (float)B.x[(size_t)c * B.npad + i];
+}
+
+// ===========================================================================
+// scalar kernels: one CTA per candidate reduces the per-CTA partials in a
+// fixed order (deterministic) and advances the LSMR recurrences.
+// ===========================================================================
+__device__ __forceinline__ double reduce_partials_f(const float* p, int n, double* shd) {
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += HB2_BLOCK) s += (double)p[i];
+  return block_sum_d(s, shd);
+}
+
+// phase 0 (init): normb = ||b||
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_normb(BD B) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  const float* bb = B.b + B.cand_uoff[c];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < B.cand_mdata[c]; i += HB2_BLOCK) { double t = bb[i]; s += t * t; }
+  s = block_sum_d(s, shd);
+  if (threadIdx.x == 0) {
+    LsmrState& S = B.st[c];
+    float beta = __fsqrt_rn((float)s);
+    S.beta = beta; S.normb = beta;
+    S.inv_beta = beta > 0.f ? fdiv_(1.f, beta) : 0.f;
+    S.alpha = 0.f; S.active = 1; S.skip_adj = 0; S.istop = 0; S.itn = 0;
+  }
+}
+// phase 0b: alpha = ||A^T u||, initialise recurrences
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_init(BD B, int* nactive) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  double s = reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
+  if (threadIdx.x == 0) {
+    LsmrState& S = B.st[c];
+    float alpha = __fsqrt_rn((float)s);
+    lsmr_init_(S, alpha, S.beta);
+    if (S.active) atomicAdd(nactive, 1);
+  }
+}
+// beta = ||u~||
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_beta(BD B) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  LsmrState& S = B.st[c];
+  if (!S.active) return;
+  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  double s = reduce_partials_f(B.part_u + (size_t)B.cand_view_begin[c] * ntiles, B.cand_view_count[c] * ntiles, shd);
+  s += reduce_partials_f(B.part_us + (size_t)c * B.part_us_per_cand, B.part_us_per_cand, shd);
+  if (threadIdx.x == 0) {
+    float beta = __fsqrt_rn((float)s);
+    S.beta = beta;
+    if (beta > 0.f) { S.inv_beta = fdiv_(1.f, beta); S.skip_adj = 0; }
+    else { S.skip_adj = 1; }
+  }
+}
+// alpha = ||v~||, rotations, update coefficients
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_rot(BD B) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  LsmrState& S = B.st[c];
+  if (!S.active) return;
+  double s = reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
+  if (threadIdx.x == 0) {
+    float alpha = S.skip_adj ? S.alpha : __fsqrt_rn((float)s);
+    lsmr_rotate_(S, alpha, S.beta);
+  }
+}
+// ||x||, stopping tests
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_test(BD B, double atol, double btol, double conlim, int maxiter,
+                                                         int fixed_iters, int* nactive) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  LsmrState& S = B.st[c];
+  if (!S.active) return;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < B.part_x_per_cand; i += HB2_BLOCK) s += B.part_x[(size_t)c * B.part_x_per_cand + i];
+  s = block_sum_d(s, shd);
+  if (threadIdx.x == 0) {
+    int istop = lsmr_test_(S, sqrt(s), atol, btol, conlim, maxiter);
+    if (fixed_iters > 0) { istop = S.itn >= fixed_iters ? 7 : 0; S.istop = istop; }
+    if (istop > 0) { S.active = 0; atomicSub(nactive, 1); }
+  }
+}
+// cosine score from the projector's partials (lib/analysis.py:802-821)
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_score(BD B, float* __restrict__ score) {
+  const int c = blockIdx.x;
+  __shared__ double shd[HB2_BLOCK / 32];
+  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  const int n = B.cand_view_count[c] * ntiles;
+  const float* p = B.part_s + (size_t)B.cand_view_begin[c] * ntiles * 3;
+  double d = 0, pp = 0, bb = 0;
+  for (int i = threadIdx.x; i < n; i += HB2_BLOCK) { d += p[3 * i]; pp += p[3 * i + 1]; bb += p[3 * i + 2]; }
+  d = block_sum_d(d, shd); pp = block_sum_d(pp, shd); bb = block_sum_d(bb, shd);
+  if (threadIdx.x == 0) {
+    float na = __fsqrt_rn((float)pp), nb = __fsqrt_rn((float)bb);
+    float norm = fmul_(na, nb);
+    score[c] = norm == 0.f ? 0.f : fdiv_((float)d, norm);
+  }
+}

@@ -1,0 +1,266 @@
+"""Python host objects over the C ABI: Problem (one image + in-plane geometry)
+and Batch (candidates with a common 3-D length solved together on one GPU)."""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.sparse import csr_matrix
+
+from . import _lib
+from .planner import BatchPlan, CandidateSpec
+
+DEFAULT_OPTIONS = dict(
+    max_iter=1000, atol=1e-4, btol=1e-4, conlim=1e8, check_every=8, clip_pred=0, trf_max_iter=200, trf_tol=1e-2,
+    fixed_iters=0,
+)
+
+
+def _stream_handle(stream):
+    if stream is None:
+        return None
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(int(stream.cuda_stream))  # torch.cuda.Stream
+
+
+class Problem:
+    """Image + the geometry that does not depend on (twist, rise, csym)."""
+
+    def __init__(self, image, scale2d_to_3d, D2, L2, D3, rmin, rmax, device=0, stream=None, interpolation="nn"):
+        lib = _lib.require_gpu()
+        if interpolation != "nn":
+            raise NotImplementedError(
+                f"helicon_b200: interpolation={interpolation!r} is not implemented on the CUDA path (only 'nn'); "
+                "there is no CPU fallback"
+            )
+        image = np.ascontiguousarray(image, dtype=np.float32)
+        ny, nx = image.shape
+        self.geom = _lib.Geometry(ny, nx, float(scale2d_to_3d), int(D2), int(L2), int(D3), float(rmin), int(rmax), 0)
+        self.device = int(device)
+        self.stream = _stream_handle(stream)
+        self._h = C.c_void_p()
+        _lib.check(lib.hb2_problem_create(C.byref(self._h), _lib.ptr(image), C.byref(self.geom), self.device, self.stream))
+        self.ndisk = lib.hb2_problem_ndisk(self._h)
+        self.D2, self.L2, self.D3 = int(D2), int(L2), int(D3)
+        self.s = float(scale2d_to_3d)
+
+    def rank_table(self):
+        out = np.empty(self.D2 * self.D2, dtype=np.int32)
+        _lib.check(_lib.load().hb2_problem_rank_table(self._h, _lib.ptr(out)))
+        return out.reshape(self.D2, self.D2)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.load().hb2_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Candidates (CandidateSpec) of one Problem with a common L3."""
+
+    def __init__(self, problem: Problem, L3: int, specs, need_views=True):
+        lib = _lib.require_gpu()
+        self.problem = problem
+        self.L3 = int(L3)
+        self.plan = BatchPlan(problem.s, problem.D2, problem.L2, self.L3, specs)
+        nA = len(self.plan.angles)
+        self.nvalid = np.zeros(nA, dtype=np.int32)
+        self.tie = np.zeros(nA, dtype=np.int32)
+        self._h = C.c_void_p()
+        _lib.check(
+            lib.hb2_batch_begin(
+                C.byref(self._h), problem._h, self.L3, self.plan.MC, nA, _lib.ptr(self.plan.cos_sin),
+                _lib.ptr(self.nvalid), _lib.ptr(self.tie), problem.stream,
+            )
+        )
+        self.plan.finalize(self.nvalid)
+        p = self.plan
+        _lib.check(
+            lib.hb2_batch_create(
+                self._h, len(p.cands), _lib.ptr(p.cands), len(p.views), _lib.ptr(p.views), len(p.colk),
+                _lib.ptr(p.colk), len(p.pairs), _lib.ptr(p.pairs),
+            )
+        )
+        self.n = self.L3 * problem.ndisk
+        self.nc = len(p.cands)
+        self.results = None
+
+    # -- solve -------------------------------------------------------------
+    def solve(self, **opts):
+        o = dict(DEFAULT_OPTIONS)
+        o.update(opts)
+        so = _lib.SolveOptions(**o)
+        res = np.zeros(self.nc, dtype=_lib.RESULT_DTYPE)
+        _lib.check(_lib.load().hb2_batch_solve(self._h, C.byref(so), _lib.ptr(res)))
+        for c in range(self.nc):
+            res[c]["n_data_rows"] = sum(v[4] for v in self.plan.cand_views[c])
+        self.results = res
+        return res
+
+    def timing(self):
+        out = np.zeros(8, dtype=np.float64)
+        _lib.check(_lib.load().hb2_batch_timing(self._h, _lib.ptr(out)))
+        return dict(lsmr_ms=out[0], trf_ms=out[1], score_ms=out[2], launches=int(out[3]), iterations=int(out[4]))
+
+    def x(self, c):
+        out = np.empty(self.n, dtype=np.float32)
+        _lib.check(_lib.load().hb2_batch_get_x(self._h, int(c), _lib.ptr(out)))
+        return out
+
+    def mask2d(self):
+        return self.problem_rank3d() >= 0
+
+    def problem_rank3d(self):
+        """disk rank table on the 3-D grid (D3 x D3)."""
+        D3 = self.problem.D3
+        g = self.problem.geom
+        j = np.arange(D3) - D3 // 2
+        Y, X = np.meshgrid(j, j, indexing="ij")
+        r2 = X * X + Y * Y
+        m = r2 < g.rmax * g.rmax
+        if 0 < g.rmin < g.rmax:
+            m &= r2 >= g.rmin * g.rmin
+        rank = np.full((D3, D3), -1, dtype=np.int64)
+        rank[m] = np.arange(int(m.sum()))
+        return rank
+
+    def rec3d(self, c):
+        """Scatter x into the (L3, D3, D3) volume (SLR:532-538)."""
+        D3 = self.problem.D3
+        m = self.problem_rank3d() >= 0
+        vol = np.zeros((self.L3, D3, D3), dtype=np.float32)
+        vol[:, m] = self.x(c).reshape(self.L3, -1)
+        return vol
+
+    # -- exports (drop-in builders, tests) ---------------------------------
+    def ray_valid(self):
+        out = np.empty((len(self.plan.angles), self.problem.D2), dtype=np.uint8)
+        _lib.check(_lib.load().hb2_batch_ray_valid(self._h, _lib.ptr(out)))
+        return out
+
+    def angle_map(self, a):
+        D2 = self.problem.D2
+        out = np.empty(D2 * D2, dtype=np.int32)
+        _lib.check(_lib.load().hb2_batch_angle_map(self._h, int(a), _lib.ptr(out)))
+        return out.reshape(D2, D2)
+
+    def rows_padded(self, c):
+        nd = C.c_int64()
+        tot = _lib.load().hb2_batch_rows_padded(self._h, int(c), C.byref(nd))
+        _lib.check(tot)
+        return int(nd.value), int(tot)
+
+    def rhs_padded(self, c):
+        nd, _ = self.rows_padded(c)
+        out = np.empty(nd, dtype=np.float32)
+        _lib.check(_lib.load().hb2_batch_rhs(self._h, int(c), _lib.ptr(out)))
+        return out
+
+    def data_row_index(self, c):
+        """For every real data row, in the reference's order (copy, k, j), its
+        index in the padded layout [view][z][mc][j], plus (k, j)."""
+        D2, L3, MC = self.problem.D2, self.L3, self.plan.MC
+        rv = self.ray_valid()
+        idx, kk, jj = [], [], []
+        for vi, (a, zi, h, cc, nrows) in enumerate(self.plan.cand_views[c]):
+            js = np.nonzero(rv[a])[0]
+            fill = np.zeros(L3, dtype=np.int64)
+            for k in np.nonzero(zi >= 0)[0]:
+                z = int(zi[k])
+                zm = z * MC + fill[z]
+                fill[z] += 1
+                idx.append(vi * (L3 * MC * D2) + zm * D2 + js)
+                kk.append(np.full(len(js), k))
+                jj.append(js)
+        if not idx:
+            return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64)
+        return np.concatenate(idx), np.concatenate(kk), np.concatenate(jj)
+
+    def data_csr(self, c):
+        """A_data, b, b_pid of SLR:1651-1654 assembled from the GPU-built maps."""
+        D2, L3 = self.problem.D2, self.L3
+        nd = self.problem.ndisk
+        rv = self.ray_valid()
+        rows, cols = [], []
+        r0 = 0
+        maps = {}
+        for a, zi, h, cc, nrows in self.plan.cand_views[c]:
+            if a not in maps:
+                maps[a] = self.angle_map(a)
+            fm = maps[a]
+            js = np.nonzero(rv[a])[0]
+            sub = fm[js]  # (nj, D2)
+            hit = sub >= 0
+            per_ray = hit.sum(axis=1)
+            ray_local = np.repeat(np.arange(len(js)), per_ray)
+            vox = sub[hit]
+            for k in np.nonzero(zi >= 0)[0]:
+                z = int(zi[k])
+                rows.append(r0 + ray_local)
+                cols.append(z * nd + vox)
+                r0 += len(js)
+        pidx, kk, jj = self.data_row_index(c)
+        b = self.rhs_padded(c)[pidx] if len(pidx) else np.zeros(0, np.float32)
+        if rows:
+            rows, cols = np.concatenate(rows), np.concatenate(cols)
+        else:
+            rows, cols = np.zeros(0, np.int64), np.zeros(0, np.int64)
+        A = csr_matrix((np.ones(len(rows), dtype=np.float32), (rows, cols)), shape=(r0, L3 * nd), dtype=np.float32)
+        return A, b.astype(np.float32), (kk * D2 + jj).astype(np.int32)
+
+    def sym_rows(self, c):
+        n = C.c_int32()
+        lib = _lib.load()
+        _lib.check(lib.hb2_batch_sym_rows(self._h, int(c), C.byref(n), None, None, 0))
+        a = np.empty(n.value, dtype=np.int32)
+        b = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            _lib.check(lib.hb2_batch_sym_rows(self._h, int(c), C.byref(n), _lib.ptr(a), _lib.ptr(b), n.value))
+        return a, b
+
+    def sym_csr(self, c):
+        """A_hsym, b_hsym of SLR:1289-1298 (or (None, None))."""
+        a, b = self.sym_rows(c)
+        m = len(a)
+        if m == 0:
+            return None, None
+        rows = np.repeat(np.arange(m), 2)
+        cols = np.stack([a, b], axis=1).ravel()
+        vals = np.tile(np.array([1, -1], dtype=np.float32), m)
+        A = csr_matrix((vals, (rows, cols)), shape=(m, self.n), dtype=np.float32)
+        return A, np.zeros(m, dtype=np.float32)
+
+    def apply_forward(self, c, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.shape == (self.n,)
+        _, tot = self.rows_padded(c)
+        y = np.empty(tot, dtype=np.float32)
+        _lib.check(_lib.load().hb2_batch_apply_forward(self._h, int(c), _lib.ptr(x), _lib.ptr(y)))
+        return y
+
+    def apply_adjoint(self, c, y):
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        _, tot = self.rows_padded(c)
+        assert y.shape == (tot,)
+        x = np.empty(self.n, dtype=np.float32)
+        _lib.check(_lib.load().hb2_batch_apply_adjoint(self._h, int(c), _lib.ptr(y), _lib.ptr(x)))
+        return x
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _lib.load().hb2_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

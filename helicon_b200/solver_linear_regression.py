@@ -1,0 +1,215 @@
+"""Drop-in for ``helicon.webApps.denovo3D.solver_linear_regression`` (the
+reference's denovo3D solver, "SLR") with the per-candidate work on the GPU.
+
+Same function names, argument meaning, return types and array layouts as the
+reference; see INTEGRATION.md.  What is NOT implemented on the CUDA path raises
+``NotImplementedError`` (there is no CPU fallback by design):
+interpolation other than "nn", tilt/psi/dy != 0 and ``refine_tilt_psi_dy``
+(general-orientation projector), ``fsc_test``, score metrics other than
+"cosine", and solver models other than ``{"model": "lsq"}``.
+"""
+
+from __future__ import annotations
+
+import functools
+import logging
+
+import numpy as np
+
+from . import planner
+from .engine import Batch, Problem
+from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
+from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
+
+logger = logging.getLogger(__name__)
+
+
+def _cache_compatible(func):
+    """The reference wraps its builders in ``helicon.cache`` (lib/cache.py:132-209),
+    which adds ``clear_cache``/``get_cache_info``/``__wrapped__``.  Results here
+    come from the GPU in milliseconds, so nothing is memoised on disk; the
+    attributes exist for call-site compatibility."""
+
+    @functools.wraps(func)
+    def wrapper(*args, **kwargs):
+        return func(*args, **kwargs)
+
+    wrapper.clear_cache = lambda: None
+    wrapper.get_cache_info = lambda: {"cache_dir": None, "cache_period": None, "function_name": func.__name__}
+    return wrapper
+
+
+def _unsupported(what):
+    raise NotImplementedError(f"helicon_b200 (CUDA path): {what} is not implemented; there is no CPU fallback")
+
+
+def _check_orientation(tilt_degree, psi_degree, dy_pixel):
+    if tilt_degree != 0 or psi_degree != 0 or dy_pixel != 0:
+        _unsupported("tilt/psi/dy != 0 (general-orientation projector, SURVEY section 8f rank 4)")
+
+
+def back_project_2d_coords_to_3d_coords(
+    image, scale2d_to_3d, reconstruct_diameter_2d_pixel=-1, reconstruct_length_2d_pixel=-1
+):
+    """SLR:1657-1746.  Host-only helper kept for API parity: the CUDA kernels
+    never materialise these (L2, D2, D2) float64 tables (closed form in
+    registers, see ``k_build_fmap``)."""
+    from scipy.spatial.transform import Rotation as R
+
+    ny, nx = image.shape
+    D2 = ny if reconstruct_diameter_2d_pixel <= 0 else reconstruct_diameter_2d_pixel
+    L2 = nx if reconstruct_length_2d_pixel <= 0 else reconstruct_length_2d_pixel
+    D2, L2 = int(np.rint(D2)), int(np.rint(L2))
+    depth = (np.arange(D2, dtype=np.int32) - D2 // 2).astype(np.float32)
+    across = (np.arange(D2, dtype=np.int32) - D2 // 2).astype(np.float32)
+    along = (np.arange(L2, dtype=np.int32) - L2 // 2).astype(np.float32)
+    region = image[np.ix_(across.astype(np.int32) + ny // 2, along.astype(np.int32) + nx // 2)]
+    Zg, Yg, Xg = np.meshgrid(depth, across, along, indexing="ij")
+    pts = np.stack((Xg.ravel(), Yg.ravel(), Zg.ravel()), axis=1)
+    pts = R.from_euler("y", 90, degrees=True).apply(pts, inverse=True)
+    if scale2d_to_3d != 1.0:
+        pts *= scale2d_to_3d
+    tables = tuple(np.swapaxes(pts[:, c].reshape((D2, D2, L2)), 0, 2) for c in range(3))
+    return tables, region
+
+
+def _make_problem(image, scale2d_to_3d, D2, L2, D3, D3_inner, rmax=None, interpolation="nn", device=0):
+    rmin = D3_inner / 2
+    if rmax is None:
+        rmax = D3 // 2 - 1
+    return Problem(image, scale2d_to_3d, D2, L2, D3, rmin, rmax, device=device, interpolation=interpolation)
+
+
+@_cache_compatible
+def build_A_data_matrix(
+    image,
+    scale2d_to_3d,
+    twist_degree,
+    rise_pixel,
+    csym,
+    tilt_degree,
+    psi_degree,
+    dy_pixel,
+    reconstruct_diameter_2d_pixel,
+    reconstruct_length_2d_pixel,
+    reconstruct_diameter_3d_pixel,
+    reconstruct_diameter_3d_inner_pixel,
+    reconstruct_length_3d_pixel,
+    min_projection_lines,
+    interpolation,
+    verbose=0,
+    cpu=1,
+):
+    """SLR:1301-1654 -> (csr_matrix float32, b float32, b_pid int32).
+
+    The sample->voxel maps, ray validity and right-hand side come from the CUDA
+    kernels; only the COO->CSR packing happens on the host."""
+    _check_orientation(tilt_degree, psi_degree, dy_pixel)
+    image = np.asarray(image)
+    D2 = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
+    L2 = reconstruct_length_2d_pixel if reconstruct_length_2d_pixel > 0 else image.shape[1]
+    L3 = reconstruct_length_3d_pixel if reconstruct_length_3d_pixel > 0 else L2
+    # the reference builds this mask on the (L3, D2, D2) grid with rmax from D3 (SLR:1382-1384)
+    prob = _make_problem(image, scale2d_to_3d, D2, L2, D2, reconstruct_diameter_3d_inner_pixel,
+                         rmax=reconstruct_diameter_3d_pixel // 2 - 1, interpolation=interpolation)
+    spec = CandidateSpec(twist_degree, rise_pixel, csym, min_projection_lines, -1, False)
+    batch = Batch(prob, L3, [spec])
+    try:
+        return batch.data_csr(0)
+    finally:
+        batch.close()
+        prob.close()
+
+
+@_cache_compatible
+def build_A_helical_sym_matrix(
+    nz, ny, nx, twist_degree, rise_pixel, csym, rmin, rmax, min_sym_pairs, interpolation, verbose=0
+):
+    """SLR:844-1298 -> (csr_matrix float32 | None, zeros float32 | None)."""
+    if ny != nx:
+        _unsupported("a non-square symmetry grid (ny != nx)")
+    prob = Problem(np.zeros((ny, nx), dtype=np.float32), 1.0, ny, nx, ny, rmin, rmax if rmax >= 0 else ny // 2 - 1,
+                   interpolation=interpolation)
+    spec = CandidateSpec(twist_degree, rise_pixel, csym, 1, min_sym_pairs, False)
+    batch = Batch(prob, nz, [spec])
+    try:
+        return batch.sym_csr(0)
+    finally:
+        batch.close()
+        prob.close()
+
+
+def lsq_reconstruct(
+    projection_image,
+    scale2d_to_3d,
+    twist_degree,
+    rise_pixel,
+    csym=1,
+    tilt_degree=0,
+    psi_degree=0,
+    dy_pixel=0,
+    thresh_fraction=-1,
+    positive_constraint=-1,
+    reconstruct_diameter_3d_inner_pixel=0,
+    reconstruct_diameter_2d_pixel=-1,
+    reconstruct_diameter_3d_pixel=-1,
+    reconstruct_length_2d_pixel=-1,
+    reconstruct_length_3d_pixel=-1,
+    sym_oversample=1,
+    interpolation="nn",
+    fsc_test=0,
+    score_metric="cosine",
+    target_apix2d=5.0,
+    verbose=0,
+    algorithm=dict(model="lsq"),
+    refine_tilt_psi_dy_range=None,
+    cpu=1,
+    device=0,
+    return_info=False,
+):
+    """SLR:31-547 -> ((rec3d, None, None), score) with rec3d float32 (L3, D3, D3).
+
+    One candidate through the batched GPU path (a batch of one).  ``device`` and
+    ``return_info`` are additive keyword arguments."""
+    _check_orientation(tilt_degree, psi_degree, dy_pixel)
+    if algorithm.get("model", "lsq") != "lsq":
+        _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
+    if fsc_test:
+        _unsupported("fsc_test >= 1 (half-set solves, SLR:441-482)")
+    if score_metric != "cosine":
+        _unsupported(f"score_metric {score_metric!r} (only 'cosine', SLR:500-525)")
+    if refine_tilt_psi_dy_range is not None and any(
+        refine_tilt_psi_dy_range.get(k, 0) > 0 for k in ("tilt", "psi", "dy")
+    ):
+        _unsupported("refine_tilt_psi_dy (SLR:550-841)")
+    image = np.asarray(projection_image)
+    D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
+    D2 = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
+    L2 = reconstruct_length_2d_pixel if reconstruct_length_2d_pixel > 0 else image.shape[1]
+    if D3 <= 0 or L3 <= 0:
+        raise ValueError("reconstruct_diameter_3d_pixel and reconstruct_length_3d_pixel must be given")
+    prob = _make_problem(image, scale2d_to_3d, D2, L2, D3, reconstruct_diameter_3d_inner_pixel,
+                         interpolation=interpolation, device=device)
+    try:
+        n3 = L3 * prob.ndisk
+        target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * sym_oversample))  # SLR:148-150, 168-170
+        positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
+        spec = CandidateSpec(twist_degree, rise_pixel, csym, target, target, positive)
+        batch = Batch(prob, L3, [spec])
+        try:
+            res = batch.solve(clip_pred=int(thresh_fraction >= 0))
+            rec3d = batch.rec3d(0)
+            score = np.float32(res[0]["score"])
+            info = dict(res=res[0].copy(), timing=batch.timing())
+        finally:
+            batch.close()
+    finally:
+        prob.close()
+    if return_info:
+        return (rec3d, None, None), score, info
+    return (rec3d, None, None), score
+
+
+def refine_tilt_psi_dy(*args, **kwargs):
+    """SLR:550-841 needs the general-orientation projector; not on the CUDA path yet."""
+    _unsupported("refine_tilt_psi_dy (SLR:550-841)")

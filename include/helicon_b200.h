@@ -1,0 +1,179 @@
+/* helicon_b200 -- C ABI of the B200 (sm_100a) denovo3D solve+score hot path.
+ *
+ * Drop-in boundary for jianglab/helicon's denovo3D solver.  The reference is
+ * pure Python (src/helicon/webApps/denovo3D/solver_linear_regression.py, "SLR"
+ * below); a maintainer binds this library with ctypes from
+ * the bodies of the reference functions named beside each entry point.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success or a negative hb2_status; hb2_last_error() gives the message.  All
+ * host buffers are caller-owned.  `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  Nothing here throws or calls back.
+ *
+ * Division of labour: the Python host plans the candidate exactly
+ * as the reference does (ordered symmetry copies, ordered symmetry pairs,
+ * rotation matrices from scipy, column->slice assignment); every O(pixels),
+ * O(voxels) or O(iterations) step runs in CUDA kernels behind this ABI.
+ */
+#ifndef HELICON_B200_H
+#define HELICON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HB2_OK = 0,
+  HB2_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+  HB2_ERR_ARG = -2,         /* bad argument */
+  HB2_ERR_GEOMETRY = -3,    /* geometry the path does not support (see message) */
+  HB2_ERR_NO_DEVICE = -4,   /* no CUDA device: there is no CPU fallback */
+  HB2_ERR_STATE = -5,       /* call order violated */
+  HB2_ERR_CAPACITY = -6     /* an internal table overflowed */
+} hb2_status;
+
+/* per-candidate result flags (bit mask in hb2_result.flags) */
+#define HB2_FLAG_TIE_XY 1u       /* an in-plane sample lies within 1e-9 of a rounding boundary */
+#define HB2_FLAG_TIE_Z 2u        /* a column's Z lies within 1e-9 of a rounding boundary (host planner sets it) */
+#define HB2_FLAG_BOUNDED 4u      /* the bounded (TRF) branch ran (SLR:246-270, scipy lsq_linear) */
+#define HB2_FLAG_NO_ROWS 8u      /* no data rows */
+
+typedef struct hb2_problem hb2_problem; /* one image + in-plane geometry, shared by many candidates */
+typedef struct hb2_batch hb2_batch;     /* a set of candidates solved together */
+
+/* In-plane geometry shared by all candidates of a problem.
+ * Mirrors the arguments of SLR:1304-1322 (build_A_data_matrix) and SLR:847-859
+ * (build_A_helical_sym_matrix) that do not depend on (twist, rise, csym). */
+typedef struct {
+  int32_t ny, nx;          /* image shape */
+  double scale2d_to_3d;    /* s */
+  int32_t D2, L2;          /* reconstruct_diameter_2d_pixel, reconstruct_length_2d_pixel */
+  int32_t D3;              /* reconstruct_diameter_3d_pixel */
+  double rmin;             /* reconstruct_diameter_3d_inner_pixel / 2 (SLR:116) */
+  int32_t rmax;            /* D3 // 2 - 1 (SLR:117) */
+  int32_t interpolation;   /* 0 = "nn" (SLR:1514-1557, 1142-1218) */
+} hb2_geometry;
+
+/* One candidate (twist, rise, csym).  Views/pairs are slices of the flat
+ * arrays given to hb2_batch_create, in the reference's order. */
+typedef struct {
+  int32_t view_begin, view_count;   /* data-operator symmetry copies actually used (after the row-count early stop, SLR:1647) */
+  int32_t pair_begin, pair_count;   /* symmetry pairs in sorted_hsym_csym_pairs order (SLR:1749-1791) */
+  int64_t min_sym_pairs;            /* SLR:168-170 */
+  int32_t positive;                 /* resolved positive-constraint rule (SLR:352-355) */
+  uint32_t flags_in;                /* HB2_FLAG_TIE_Z from the host planner */
+} hb2_candidate;
+
+/* One symmetry copy (h,c) of the data operator: in-plane rotation = angle
+ * table entry `angle`, and the image column k feeding each (z-slice, slot):
+ * colk[(z*MC + mc)] = k or -1, stored at col_begin in the flat colk array. */
+typedef struct {
+  int32_t angle;       /* index into the batch's unique-angle table */
+  int32_t col_begin;   /* offset into colk (L3*MC entries) */
+} hb2_view;
+
+/* One symmetry pair ((h_i,c_i),(h_j,c_j)) of the regulariser (SLR:1223-1243):
+ * rotation matrix entries (M00, M10) from scipy for each member and the z
+ * shift rise_pixel*h. */
+typedef struct {
+  double ci, si, zi;
+  double cj, sj, zj;
+} hb2_pair;
+
+typedef struct {
+  int32_t max_iter;        /* lsmr_maxiter (SLR:266) = 1000 */
+  double atol, btol;       /* 1e-2 * tol = 1e-4 (scipy lsq_linear.py:318-326) */
+  double conlim;           /* 1e8 (scipy lsmr default) */
+  int32_t check_every;     /* host polls convergence every this many iterations */
+  int32_t clip_pred;       /* thresh_fraction >= 0: clip reprojection at 0 before scoring (SLR:502-503) */
+  int32_t trf_max_iter;    /* max_iter of the bounded branch (SLR:241) = 200 */
+  double trf_tol;          /* tol (SLR:240) = 1e-2 */
+  int32_t fixed_iters;     /* >0: run exactly this many LSMR iterations, ignore stop tests (tests only) */
+} hb2_solve_options;
+
+typedef struct {
+  float score;             /* cosine similarity of A_data x vs b_data (SLR:484-525, lib/analysis.py:802-821) */
+  int32_t itn;             /* LSMR iterations of the unbounded solve */
+  int32_t istop;           /* scipy lsmr istop code */
+  int32_t trf_nit;         /* outer iterations of the bounded branch (0 if not taken) */
+  uint32_t flags;
+  int32_t n_data_rows;     /* real (unpadded) data rows */
+  int32_t n_sym_rows;
+  float normr, normar, normA, normx;
+} hb2_result;
+
+const char* hb2_last_error(void);
+int hb2_device_count(void);
+const char* hb2_build_info(void);
+
+/* ---- problem ------------------------------------------------------------- */
+/* Uploads the image, crops pixel_vals (SLR:1706-1708) and builds the disk
+ * tables of helicon.get_cylindrical_mask (lib/analysis.py:731-774). */
+int hb2_problem_create(hb2_problem** out, const float* image_host, const hb2_geometry* geom, int device, void* stream);
+void hb2_problem_destroy(hb2_problem* p);
+int hb2_problem_ndisk(const hb2_problem* p);
+/* rank table of the data grid: out[D2*D2], rank of voxel (y,x) in C order inside the disk, or -1 */
+int hb2_problem_rank_table(const hb2_problem* p, int32_t* out_host);
+
+/* ---- batch: step 1, in-plane maps for the batch's unique angles ---------- */
+/* cos_sin[2*a+0] = M00, cos_sin[2*a+1] = M10 of scipy Rotation.from_euler('z', angle_a).
+ * Builds the sample->voxel map of every angle (replaces the numba loop
+ * SLR:1514-1557 and Rotation.apply SLR:1614-1620 for tilt=psi=dy=0).
+ * Outputs (host, may be NULL): nvalid_rays[a] = rays with >=1 hit,
+ * tie_samples[a] = samples within 1e-9 of a rounding boundary. */
+int hb2_batch_begin(hb2_batch** out, hb2_problem* p, int32_t L3, int32_t MC, int32_t n_angles, const double* cos_sin,
+                    int32_t* nvalid_rays, int32_t* tie_samples, void* stream);
+/* ray validity per angle, out[n_angles*D2] (1 = the ray has projection data, SLR:1547) */
+int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out_host);
+/* sample->voxel map of one angle, out[D2*D2] int32 (disk rank or -1), row j, depth i */
+int hb2_batch_angle_map(hb2_batch* b, int32_t angle, int32_t* out_host);
+
+/* ---- batch: step 2, candidates ----------------------------------------- */
+/* Finalises the batch: adjoint maps, right-hand side, symmetry rows
+ * (replaces SLR:1142-1218 + 1221-1287 incl. the first-seen-wins de-duplication
+ * and the min_sym_pairs early stop) and their transpose lists. */
+int hb2_batch_create(hb2_batch* b, int32_t n_cand, const hb2_candidate* cands, int32_t n_views, const hb2_view* views,
+                     int32_t n_colk, const int32_t* colk, int32_t n_pairs, const hb2_pair* pairs);
+void hb2_batch_destroy(hb2_batch* b);
+
+/* number of symmetry rows of a candidate, and the rows themselves as (a,b)
+ * voxel-index pairs in the reference's row order: A[r,a]=+1, A[r,b]=-1. */
+int hb2_batch_sym_rows(hb2_batch* b, int32_t cand, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity);
+/* padded data-row count of a candidate (= view_count*L3*MC*D2) and total padded rows incl. symmetry rows */
+int64_t hb2_batch_rows_padded(hb2_batch* b, int32_t cand, int64_t* n_data_padded);
+/* right-hand side in padded layout, out[n_data_padded] */
+int hb2_batch_rhs(hb2_batch* b, int32_t cand, float* out_host);
+
+/* ---- operators (tests, drop-in exports) --------------------------------- */
+/* y = A x  (padded row layout: data rows [view][z][mc][j], then symmetry rows) */
+int hb2_batch_apply_forward(hb2_batch* b, int32_t cand, const float* x_host, float* y_host);
+/* x = A^T y */
+int hb2_batch_apply_adjoint(hb2_batch* b, int32_t cand, const float* y_host, float* x_host);
+
+/* ---- solve + score --------------------------------------------------------- */
+/* For every candidate: LSMR on [A_data; A_hsym] x = [b; 0] with scipy's stopping
+ * rules and precision map (replaces scipy lsq_linear as called at SLR:258-270),
+ * the bounded TRF branch when cand.positive and the LSMR solution violates
+ * [0, max(b)], then reprojection + cosine score (SLR:500-525).
+ * results_host[n_cand].  Candidates stay resident for hb2_batch_get_x. */
+int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_result* results_host);
+/* solution vector x of one candidate as float32 in the reference's order (SLR:270, 538) */
+int hb2_batch_get_x(hb2_batch* b, int32_t cand, float* x_host);
+/* device time (ms) of the last hb2_batch_solve, per phase; out[8]: lsmr, trf, score, total kernels launched ... */
+int hb2_batch_timing(hb2_batch* b, double* out8);
+
+/* ---- test hook: the LSMR scalar recurrences run on the HOST --------------- */
+/* Same code as the device path (compiled __host__ __device__).  state64 is an
+ * opaque 64-double scratch the caller keeps between calls.
+ * phase 0: initialise from alpha_1, beta_1 (lsmr.py:239-300);
+ * phase 1: rotations + update coefficients from alpha_{k+1}, beta_{k+1} (lsmr.py:341-414);
+ * phase 2: stopping tests given norm(x) (lsmr.py:416-457), returns istop. */
+int hb2_lsmr_scalar_step(double* state64, int phase, float alpha, float beta, double normx, double atol, double btol,
+                         double conlim, int maxiter, float* coef_hbar, float* coef_x, float* coef_h, double* trace8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELICON_B200_H */

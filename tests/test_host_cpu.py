@@ -1,0 +1,131 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, the LSMR
+scalar recurrences (compiled host+device from the same source) follow scipy's
+executed precision map, and the host planner restates the reference's ordering
+logic.  No GPU compute."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helicon_b200 import _lib, planner
+from oracle import denovo3d_oracle as O
+from tests.helpers import ROOT, load
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "helicon_b200.h")).read()
+    declared = set(re.findall(r"\b(hb2_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_sizes_match_numpy_dtypes():
+    assert _lib.CANDIDATE_DTYPE.itemsize == C.sizeof(_lib.Candidate) == 32
+    assert _lib.PAIR_DTYPE.itemsize == 48 and _lib.VIEW_DTYPE.itemsize == 8
+
+
+def test_no_gpu_means_loud_failure():
+    lib = _lib.load()
+    if lib.hb2_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.HeliconB200Error):
+        _lib.require_gpu()
+    from helicon_b200 import solver_linear_regression as solver
+
+    with pytest.raises(_lib.HeliconB200Error):
+        solver.lsq_reconstruct(np.ones((8, 8), np.float32), 1.0, 30, 2, reconstruct_diameter_3d_pixel=8,
+                               reconstruct_length_3d_pixel=4)
+
+
+def _solve_case(name):
+    from scipy.sparse import vstack
+
+    d = load(name)
+    apix, twist, rise, csym, pc, so, L3 = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    _, _, det = O.lsq_reconstruct(
+        img, 1.0, float(twist), float(rise / apix), int(csym), positive_constraint=0,
+        reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N,
+        reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so), return_details=True)
+    A = vstack((det["A_data"], det["A_hsym"])).tocsr()
+    b = np.concatenate((det["b_data"], np.zeros(det["A_hsym"].shape[0], np.float32)))
+    return A, b
+
+
+@pytest.mark.parametrize("name", ["solve_nn_unb_32", "solve_nn_unb_48_t35"])
+def test_scalar_recurrences_match_scipy_precision_map(name):
+    """Drive the library's host build of the recurrences with (alpha, beta, normx)
+    taken from the oracle's LSMR; coefficients and stop iteration must agree exactly."""
+    lib = _lib.load()
+    A, b = _solve_case(name)
+    AT = A.T.tocsr()
+    f = np.float32
+    # re-run the oracle LSMR, recording alpha/beta/normx per iteration via the vectors
+    trace = []
+    x_ref, istop_ref, itn_ref, *_ = O.lsmr_mixed(A, b, trace=trace)
+    state = np.zeros(64, dtype=np.float64)
+    cfh, cfx, cfhh = C.c_float(), C.c_float(), C.c_float()
+    tr = np.zeros(8)
+    # initial alpha, beta exactly as lsmr.py:239-262
+    u = b.astype(f).copy()
+    beta0 = f(np.linalg.norm(u))
+    u = f(1 / beta0) * u
+    v = AT.dot(u)
+    alpha0 = f(np.linalg.norm(v))
+    lib.hb2_lsmr_scalar_step(_lib.ptr(state), 0, alpha0, beta0, 0.0, 1e-4, 1e-4, 1e8, 1000, C.byref(cfh), C.byref(cfx), C.byref(cfhh), _lib.ptr(tr))
+    istop = 0
+    for t in trace:
+        lib.hb2_lsmr_scalar_step(_lib.ptr(state), 1, f(t["alpha"]), f(t["beta"]), 0.0, 1e-4, 1e-4, 1e8, 1000, C.byref(cfh), C.byref(cfx), C.byref(cfhh), _lib.ptr(tr))
+        assert tr[0] == t["rho"] and tr[1] == t["rhobar"] and tr[2] == t["zeta"], t["itn"]
+        assert tr[3] == t["normr"] and tr[4] == t["normA"], t["itn"]
+        istop = lib.hb2_lsmr_scalar_step(_lib.ptr(state), 2, 0, 0, t["normx"], 1e-4, 1e-4, 1e8, 1000, C.byref(cfh), C.byref(cfx), C.byref(cfhh), _lib.ptr(tr))
+        assert tr[5] == f(t["test1"]) and tr[6] == f(t["test2"]), t["itn"]
+        if t["itn"] < itn_ref:
+            assert istop == 0, t["itn"]
+    assert istop == istop_ref
+
+
+def test_planner_halton_and_pairs_match_reference_fixtures():
+    d = load("halton")
+    for k in d.files:
+        assert np.array_equal(np.array(planner.halton_indices(int(k))), d[k])
+    d = load("hsym_pairs")
+    for i in range(5):
+        tw, ri, cs, nz = d[f"case{i}_args"]
+        res = planner.sorted_hsym_csym_pairs(float(tw), float(ri), int(cs), int(nz))
+        arr = np.array([[e[0], e[1], e[2], e[3], e[4], e[5][0][0], e[5][0][1], e[5][1][0], e[5][1][1]] for e in res])
+        assert np.array_equal(arr, d[f"case{i}"])
+
+
+def test_planner_copies_match_oracle():
+    for rise, csym, L3, L2 in [(2.4, 1, 6, 22), (3.1, 2, 8, 24), (1.9, 1, 4, 32), (3.654, 1, 12, 256), (0.7, 3, 4, 16)]:
+        assert list(planner.data_copies(rise, csym, L3, L2)) == O.data_copies(rise, csym, L3, L2)
+
+
+def test_rotation_entries_batch_equals_single_calls():
+    from scipy.spatial.transform import Rotation as R
+
+    angles = np.array([-1.2 * h for h in range(-40, 41)] + [30.0, 60.0, 90.0, 180.0, -179.5, 33.0 * 7 + 180.0])
+    cs = planner.z_rotation_entries(angles)
+    for a, (c, s) in zip(angles, cs):
+        M = R.from_euler("z", a, degrees=True).as_matrix()
+        assert c == M[0, 0] and s == M[1, 0] and M[0, 1] == -s and M[1, 1] == c
+
+
+def test_column_slices_match_reference_tables():
+    """Z of SLR:1578-1581 from the reference's own coordinate tables vs the planner's closed form."""
+    img = np.zeros((24, 24), np.float32)
+    for s, L2, L3, rise, h in [(1.0, 24, 8, 2.4, 3), (0.5, 24, 6, 1.9, -2), (1.0, 22, 6, 3.5, 1), (2.0, 16, 12, 2.2, 0)]:
+        (X, Y, Z), _ = O.back_project_2d_coords_to_3d_coords(img, s, 12, L2)
+        zref = np.rint(Z[:, 0, 6] - h * rise + L3 // 2).astype(int)  # central depth sample
+        zi, tie = planner.column_slices(s, L2, L3, h * rise)
+        ok = (zref >= 0) & (zref <= L3 - 1)
+        if not tie:
+            assert np.array_equal(np.where(ok, zref, -1), zi)
+    zi, tie = planner.column_slices(1.0, 22, 6, 3.5)
+    assert tie
