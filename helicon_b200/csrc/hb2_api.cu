@@ -100,7 +100,11 @@ struct hb2_batch {
   float* d_score = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
-  double timing[8] = {0};
+  double timing[16] = {0};
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<std::pair<int, int>> ev_used;  // (class, index of start event)
+  size_t ev_next = 0;
+  bool profiling = false;
   bool solved = false;
 };
 
@@ -202,7 +206,7 @@ extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int3
                                int32_t* nvalid_rays, int32_t* tie_samples, void* stream) {
   if (!out || !P || !cos_sin || nA <= 0 || L3 <= 0 || MC <= 0) return fail(HB2_ERR_ARG, "bad argument");
   if ((long long)L3 * MC > HB2_MAX_ZMC) return fail(HB2_ERR_GEOMETRY, "L3*MC exceeds HB2_MAX_ZMC");
-  if ((long long)L3 * P->ndisk >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many unknowns");
+  if ((long long)(L3 + 3) * P->ndisk >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many unknowns");
   CK(cudaSetDevice(P->device));
   auto* b = new hb2_batch();
   b->P = P;
@@ -211,7 +215,8 @@ extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int3
   BD& B = b->B;
   const hb2_geometry& g = P->g;
   B.D2 = g.D2; B.L2 = g.L2; B.D3 = g.D3; B.ndisk = P->ndisk; B.L3 = L3; B.MC = MC; B.ZMC = L3 * MC;
-  B.n = L3 * P->ndisk; B.npad = (B.n + 31) / 32 * 32; B.rows_per_view = L3 * MC * g.D2;
+  B.L3P = (L3 + 3) / 4 * 4; B.ZMP = (B.ZMC + 3) / 4 * 4;
+  B.n = L3 * P->ndisk; B.nrp = (B.n + 31) / 32 * 32; B.npad = B.L3P * P->ndisk; B.rows_per_view = B.ZMP * g.D2;
   B.nA = nA; B.s = g.scale2d_to_3d; B.only_cand = -1;
   b->idx16 = P->ndisk < 65535;
   size_t ns = (size_t)nA * g.D2 * g.D2;
@@ -318,6 +323,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     b->h_mdata[c] = (int)md;
     long long cap = std::min<long long>(q.min_sym_pairs + B.n, (long long)q.pair_count * B.n);
     if (q.pair_count == 0 || q.min_sym_pairs < 0) cap = 0;
+    cap = (cap + 3) / 4 * 4;  // keeps every candidate's rows 16-byte aligned
     if (cap >= (1ll << 31) - 1) return fail(HB2_ERR_GEOMETRY, "too many symmetry rows in one candidate");
     b->h_symcap[c] = cap;
     b->h_uoff[c] = uo; b->h_symoff[c] = so; b->h_cscoff[c] = 2 * so;
@@ -337,7 +343,8 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   }
   if (expect_view != nviews) return fail(HB2_ERR_ARG, "views not fully assigned to candidates");
   if (2 * so >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "batch too large: symmetry-row lists exceed 2^31 entries; use smaller batches");
-  if ((long long)nc * B.npad >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "batch too large: nc*n exceeds 2^31; use smaller batches");
+  if ((long long)nc * (B.npad + 1) >= (1ll << 31) || (long long)nc * B.nrp >= (1ll << 31))
+    return fail(HB2_ERR_CAPACITY, "batch too large: nc*n exceeds 2^31; use smaller batches");
   b->u_total = uo;
   b->h_view_angle = view_angle;
   for (int e = 0; e < ncolk; ++e)
@@ -371,7 +378,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKC(cudaMemcpyAsync(&K, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
     CKC(cudaStreamSynchronize(st));
     if (K < 1) K = 1;
-    if (K > 8) return fail(HB2_ERR_CAPACITY, "more than 8 samples of one view land in one voxel (scale2d_to_3d too small)");
+    if (K > 64) return fail(HB2_ERR_CAPACITY, "more than 64 samples of one view land in one voxel (scale2d_to_3d too small)");
     B.K = K;
     CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.ndisk, false, st));
     if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
@@ -416,9 +423,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   int max_symcap = 0;
   for (int c = 0; c < nc; ++c) max_symcap = std::max<long long>(max_symcap, b->h_symcap[c]);
   B.part_us_per_cand = std::max(1u, cdiv(max_symcap, HB2_BLOCK * 4));
-  const int adj_zc = B.L3 <= 2 ? 2 : 4;
-  B.part_v_per_cand = cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3, adj_zc);
-  B.part_x_per_cand = cdiv(B.n, HB2_BLOCK * 4);
+  const int adj_zc = B.L3P >= 16 ? 16 : B.L3P;
+  B.part_v_per_cand = cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3P, adj_zc);
+  B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
   CKC(b->pool.alloc(&B.part_us, (size_t)nc * B.part_us_per_cand, true, st));
   CKC(b->pool.alloc(&B.part_v, (size_t)nc * B.part_v_per_cand, true, st));
@@ -431,7 +438,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(b->pool.alloc(&b->d_sym_a, (size_t)so, false, st));
   CKC(b->pool.alloc(&b->d_sym_b, (size_t)so, false, st));
   B.sym_a = b->d_sym_a; B.sym_b = b->d_sym_b;
-  CKC(b->pool.alloc(&b->d_csc_ptr, (size_t)nc * (B.n + 1), true, st));
+  CKC(b->pool.alloc(&b->d_csc_ptr, (size_t)nc * (B.npad + 1), true, st));
   CKC(b->pool.alloc(&b->d_csc_ent, (size_t)2 * so, false, st));
   B.csc_ptr = b->d_csc_ptr; B.csc_ent = b->d_csc_ent;
   int max_rounds = 0;
@@ -456,10 +463,11 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKT(tmp.alloc(&Q.tab_seq, (size_t)to, false, st));
     CKT(cudaMemsetAsync(Q.tab_key, 0xFF, (size_t)to * 8, st));
     CKT(cudaMemsetAsync(Q.tab_seq, 0xFF, (size_t)to * 8, st));
-    CKT(tmp.alloc(&Q.tmp_a, nv, false, st));
-    CKT(tmp.alloc(&Q.tmp_b, nv, false, st));
-    CKT(tmp.alloc(&Q.flag, nv, true, st));
-    CKT(tmp.alloc(&Q.pos, nv, true, st));
+    const size_t nr = (size_t)nc * B.nrp;
+    CKT(tmp.alloc(&Q.tmp_a, nr, false, st));
+    CKT(tmp.alloc(&Q.tmp_b, nr, false, st));
+    CKT(tmp.alloc(&Q.flag, nr, true, st));
+    CKT(tmp.alloc(&Q.pos, nr, true, st));
     CKT(tmp.alloc(&Q.done, nc, false, st));
     CKT(tmp.alloc(&Q.ndone, 1, true, st));
     CKT(tmp.alloc(&Q.overflow, 1, true, st));
@@ -474,13 +482,13 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     Q.sym_a_w = b->d_sym_a; Q.sym_b_w = b->d_sym_b;
     Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym;
     void* d_scan_tmp = nullptr; size_t scan_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, Q.flag, Q.pos, (int)nv, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, Q.flag, Q.pos, (int)nr, st);
     { char* p; CKT(tmp.alloc(&p, scan_bytes, false, st)); d_scan_tmp = p; }
-    dim3 gn(cdiv(B.n, 256), nc), gp(cdiv(B.npad, 256), nc);
+    dim3 gn(cdiv(B.n, 256), nc), gp(cdiv(B.nrp, 256), nc);
     for (int rnd = 0; rnd < max_rounds; ++rnd) {
       k_sym_insert<<<gn, 256, 0, st>>>(B, Q, rnd);
       k_sym_check<<<gp, 256, 0, st>>>(B, Q, rnd);
-      CKT(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, Q.flag, Q.pos, (int)nv, st));
+      CKT(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_bytes, Q.flag, Q.pos, (int)nr, st));
       k_sym_compact<<<gn, 256, 0, st>>>(B, Q);
       k_sym_finalize<<<cdiv(nc, 128), 128, 0, st>>>(B, Q, rnd);
       CKT(cudaGetLastError());
@@ -497,11 +505,11 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     int max_m = 0;
     for (int c = 0; c < nc; ++c) max_m = std::max(max_m, b->h_msym[c]);
     if (max_m > 0) {
-      size_t np1 = (size_t)nc * (B.n + 1);
+      size_t np1 = (size_t)nc * (B.npad + 1);
       int *d_cnt, *d_scan;
       CKT(tmp.alloc(&d_cnt, np1, true, st));
       CKT(tmp.alloc(&d_scan, np1, false, st));
-      dim3 gr(cdiv(max_m, 256), nc), gq(cdiv(B.n + 1, 256), nc);
+      dim3 gr(cdiv(max_m, 256), nc), gq(cdiv(B.npad + 1, 256), nc), gs(cdiv(B.npad, 256), nc);
       k_csc_count<<<gr, 256, 0, st>>>(B, d_cnt);
       size_t sb2 = 0; void* d_t2 = nullptr;
       cub::DeviceScan::ExclusiveSum(nullptr, sb2, d_cnt, d_scan, (int)np1, st);
@@ -510,7 +518,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       k_csc_rebase2<<<gq, 256, 0, st>>>(B, d_scan, b->d_csc_ptr);
       CKT(cudaMemsetAsync(d_cnt, 0, np1 * sizeof(int), st));
       k_csc_fill<<<gr, 256, 0, st>>>(B, d_cnt, b->d_csc_ent);
-      k_csc_sort<<<gn, 256, 0, st>>>(B, b->d_csc_ent);
+      k_csc_sort<<<gs, 256, 0, st>>>(B, b->d_csc_ent);
       CKT(cudaGetLastError());
     }
     CKT(cudaStreamSynchronize(st));
@@ -526,6 +534,7 @@ extern "C" void hb2_batch_destroy(hb2_batch* b) {
   cudaSetDevice(b->P->device);
   cudaStreamSynchronize(b->stream);
   b->pool.free_all();
+  for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
   if (b->h_nactive) cudaFreeHost(b->h_nactive);
   delete b;
 }
@@ -540,6 +549,11 @@ extern "C" int hb2_batch_sym_rows(hb2_batch* b, int32_t c, int32_t* n_rows, int3
     CK(cudaMemcpyAsync(a_host, b->d_sym_a + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b_host, b->d_sym_b + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
+    const int L3P = b->B.L3P, nd = b->B.ndisk;
+    for (int r = 0; r < m; ++r) {  // internal p*L3P+z -> reference z*ndisk+p
+      a_host[r] = (a_host[r] % L3P) * nd + a_host[r] / L3P;
+      b_host[r] = (b_host[r] % L3P) * nd + b_host[r] / L3P;
+    }
   }
   return HB2_OK;
 }
@@ -559,41 +573,65 @@ extern "C" int hb2_batch_rhs(hb2_batch* b, int32_t c, float* out) {
 }
 
 // ---------------------------------------------------------------------------
+// optional per-launch profiling with CUDA events on the launching stream
+// ---------------------------------------------------------------------------
+enum { KC_FWD_DATA = 0, KC_FWD_SYM = 1, KC_ADJ = 2, KC_UPDATE = 3, KC_SCALAR = 4, KC_N = 5 };
+struct ProfScope {
+  hb2_batch* b;
+  ProfScope(hb2_batch* b_, int cls) : b(b_) {
+    if (!b->profiling) return;
+    while (b->ev_pool.size() < b->ev_next + 2) { cudaEvent_t e; cudaEventCreate(&e); b->ev_pool.push_back(e); }
+    b->ev_used.push_back({cls, (int)b->ev_next});
+    cudaEventRecord(b->ev_pool[b->ev_next], b->stream);
+    b->ev_next += 2;
+  }
+  ~ProfScope() {
+    if (!b->profiling) return;
+    cudaEventRecord(b->ev_pool[b->ev_used.back().second + 1], b->stream);
+  }
+};
+
+// ---------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------
 static void launch_fwd_data(hb2_batch* b, int mode) {
+  ProfScope ps(b, KC_FWD_DATA);
   const BD& B = b->B;
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   unsigned grid = (unsigned)b->nviews * ntiles;
   cudaStream_t st = b->stream;
-#define FWD(T, Z) k_fwd_data<T, Z><<<grid, HB2_BLOCK, 0, st>>>(B, mode)
-  if (b->idx16) {
-    if (B.L3 <= 4) FWD(uint16_t, 4); else if (B.L3 <= 8) FWD(uint16_t, 8); else if (B.L3 <= 12) FWD(uint16_t, 12); else FWD(uint16_t, 16);
-  } else {
-    if (B.L3 <= 4) FWD(uint32_t, 4); else if (B.L3 <= 8) FWD(uint32_t, 8); else if (B.L3 <= 12) FWD(uint32_t, 12); else FWD(uint32_t, 16);
-  }
+  if (grid == 0) return;
+  if (b->idx16) k_fwd_data<uint16_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
+  else k_fwd_data<uint32_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
+#define FWD
 #undef FWD
 }
 static void launch_fwd_sym(hb2_batch* b, int mode) {
+  ProfScope ps(b, KC_FWD_SYM);
   const BD& B = b->B;
   dim3 g(B.part_us_per_cand, B.nc);
   k_fwd_sym<<<g, HB2_BLOCK, 0, b->stream>>>(B, mode);
 }
 static void launch_adj(hb2_batch* b, int mode) {
+  ProfScope ps(b, KC_ADJ);
   const BD& B = b->B;
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
-  const bool z2 = B.L3 <= 2;
 #define ADJ(Z, K, M) k_adj<Z, K, M><<<g, HB2_BLOCK, 0, st>>>(B, mode)
+#define ADJZ(K, M)                                                                              \
+  do {                                                                                          \
+    if (B.L3P == 4) ADJ(4, K, M); else if (B.L3P == 8) ADJ(8, K, M); else if (B.L3P == 12) ADJ(12, K, M); else ADJ(16, K, M); \
+  } while (0)
   if (B.MC == 1) {
-    if (z2) { if (B.K == 1) ADJ(2, 1, 1); else if (B.K == 2) ADJ(2, 2, 1); else ADJ(2, 0, 1); }
-    else { if (B.K == 1) ADJ(4, 1, 1); else if (B.K == 2) ADJ(4, 2, 1); else ADJ(4, 0, 1); }
+    if (B.K == 1) ADJZ(1, 1); else if (B.K == 2) ADJZ(2, 1); else ADJZ(0, 1);
   } else {
-    if (z2) ADJ(2, 0, 0); else ADJ(4, 0, 0);
+    ADJZ(0, 0);
   }
+#undef ADJZ
 #undef ADJ
 }
 static void launch_update(hb2_batch* b, int mode) {
+  ProfScope ps(b, KC_UPDATE);
   const BD& B = b->B;
   dim3 g(B.part_x_per_cand, B.nc);
   k_update<<<g, HB2_BLOCK, 0, b->stream>>>(B, mode);
@@ -605,7 +643,10 @@ extern "C" int hb2_batch_apply_forward(hb2_batch* b, int32_t c, const float* x_h
   BD& B = b->B;
   cudaStream_t st = b->stream;
   long long m = (long long)b->h_mdata[c] + b->h_msym[c];
-  CK(cudaMemcpyAsync(B.xs + (size_t)c * B.npad, x_host, sizeof(float) * B.n, cudaMemcpyHostToDevice, st));
+  std::vector<float> xi((size_t)B.npad, 0.f);  // reference order z*ndisk+p -> internal p*L3P+z
+  for (int z = 0; z < B.L3; ++z)
+    for (int pp = 0; pp < B.ndisk; ++pp) xi[(size_t)pp * B.L3P + z] = x_host[(size_t)z * B.ndisk + pp];
+  CK(cudaMemcpyAsync(B.xs + (size_t)c * B.npad, xi.data(), sizeof(float) * B.npad, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(B.u + b->h_uoff[c], 0, sizeof(float) * m, st));
   B.only_cand = c;
   launch_fwd_data(b, MODE_PLAIN);
@@ -629,8 +670,11 @@ extern "C" int hb2_batch_apply_adjoint(hb2_batch* b, int32_t c, const float* y_h
   launch_adj(b, MODE_PLAIN);
   B.only_cand = -1;
   CKL();
-  CK(cudaMemcpyAsync(x_host, B.xs + (size_t)c * B.npad, sizeof(float) * B.n, cudaMemcpyDeviceToHost, st));
+  std::vector<float> xi((size_t)B.npad);
+  CK(cudaMemcpyAsync(xi.data(), B.xs + (size_t)c * B.npad, sizeof(float) * B.npad, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  for (int z = 0; z < B.L3; ++z)
+    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + pp] = xi[(size_t)pp * B.L3P + z];
   b->solved = false;
   return HB2_OK;
 }
@@ -648,6 +692,9 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   const int check = opt->check_every > 0 ? opt->check_every : 8;
   B.clip_pred = opt->clip_pred;
   B.only_cand = -1;
+  b->profiling = opt->profile != 0;
+  b->ev_used.clear();
+  b->ev_next = 0;
   cudaEvent_t e0, e1, e2;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
   CK(cudaEventRecord(e0, st));
@@ -674,11 +721,11 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     for (int q = 0; q < burst; ++q) {
       launch_fwd_data(b, MODE_LSMR);
       launch_fwd_sym(b, MODE_LSMR);
-      k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B);
+      { ProfScope ps(b, KC_SCALAR); k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B); }
       launch_adj(b, MODE_LSMR);
-      k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B);
+      { ProfScope ps(b, KC_SCALAR); k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B); }
       launch_update(b, MODE_LSMR);
-      k_scal_test<<<nc, HB2_BLOCK, 0, st>>>(B, opt->atol, opt->btol, opt->conlim, maxit, opt->fixed_iters, b->d_nactive);
+      { ProfScope ps(b, KC_SCALAR); k_scal_test<<<nc, HB2_BLOCK, 0, st>>>(B, opt->atol, opt->btol, opt->conlim, maxit, opt->fixed_iters, b->d_nactive); }
       launches += 7;
     }
     it += burst;
@@ -689,7 +736,7 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   CK(cudaEventRecord(e1, st));
   // score: reprojection of float32(x) + cosine similarity
   {
-    dim3 g(cdiv(B.n, 256), nc);
+    dim3 g(cdiv(B.npad, 256), nc);
     k_x_to_f32<<<g, 256, 0, st>>>(B);
     launch_fwd_data(b, MODE_SCORE);
     k_scal_score<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_score);
@@ -705,7 +752,19 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   float ms_l = 0, ms_s = 0;
   cudaEventElapsedTime(&ms_l, e0, e1); cudaEventElapsedTime(&ms_s, e1, e2);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  for (double& t : b->timing) t = 0;
   b->timing[0] = ms_l; b->timing[1] = 0; b->timing[2] = ms_s; b->timing[3] = (double)launches; b->timing[4] = it;
+  if (b->profiling) {
+    for (auto& pr : b->ev_used) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, b->ev_pool[pr.second], b->ev_pool[pr.second + 1]);
+      b->timing[5 + pr.first] += ms;
+      if (pr.first == KC_FWD_DATA) b->timing[10] += 1;
+      if (pr.first == KC_ADJ) b->timing[11] += 1;
+      if (pr.first == KC_UPDATE) b->timing[12] += 1;
+    }
+    b->profiling = false;
+  }
   for (int c = 0; c < nc; ++c) {
     hb2_result& r = res[c];
     r.score = sc[c]; r.itn = hs[c].itn; r.istop = hs[c].istop; r.trf_nit = 0;
@@ -720,14 +779,18 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
 extern "C" int hb2_batch_get_x(hb2_batch* b, int32_t c, float* x_host) {
   if (!b || !b->solved || !x_host || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument or batch not solved");
   CK(cudaSetDevice(b->P->device));
-  CK(cudaMemcpyAsync(x_host, b->B.xs + (size_t)c * b->B.npad, sizeof(float) * b->B.n, cudaMemcpyDeviceToHost, b->stream));
+  const BD& B = b->B;
+  std::vector<float> xi((size_t)B.npad);
+  CK(cudaMemcpyAsync(xi.data(), B.xs + (size_t)c * B.npad, sizeof(float) * B.npad, cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
+  for (int z = 0; z < B.L3; ++z)
+    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + pp] = xi[(size_t)pp * B.L3P + z];
   return HB2_OK;
 }
 
-extern "C" int hb2_batch_timing(hb2_batch* b, double* out8) {
-  if (!b || !out8) return fail(HB2_ERR_ARG, "null argument");
-  memcpy(out8, b->timing, sizeof(b->timing));
+extern "C" int hb2_batch_timing(hb2_batch* b, double* out16) {
+  if (!b || !out16) return fail(HB2_ERR_ARG, "null argument");
+  memcpy(out16, b->timing, sizeof(b->timing));
   return HB2_OK;
 }
 

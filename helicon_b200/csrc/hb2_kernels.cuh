@@ -11,8 +11,10 @@ enum { MODE_LSMR = 0, MODE_PLAIN = 1, MODE_SCORE = 2, MODE_INIT = 3 };
 
 // Batch descriptor passed by value to every kernel.
 struct BD {
-  // geometry (batch-uniform)
-  int D2, L2, D3, ndisk, L3, MC, ZMC, n, npad, rows_per_view;
+  // geometry (batch-uniform).  Voxel space is stored z-fastest: g = p*L3P + z (p = disk rank, L3P = L3 rounded
+  // up to 4) so that one in-plane index lookup serves all slices with 128-bit loads; data rows likewise:
+  // row = view_uoff + j*ZMP + zm with zm = z*MC + mc (ZMP = ZMC rounded up to 4).
+  int D2, L2, D3, ndisk, L3, L3P, MC, ZMC, ZMP, n, nrp, npad, rows_per_view;
   int nA, K, nc;
   double s;
   // in-plane maps
@@ -203,8 +205,8 @@ __global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, flo
   if (t >= total) return;
   int view = (int)(t / B.rows_per_view);
   int r = (int)(t % B.rows_per_view);
-  int j = r % B.D2, zm = r / B.D2;
-  int k = B.colk[B.view_colbegin[view] + zm];
+  int zm = r % B.ZMP, j = r / B.ZMP;
+  int k = zm < B.ZMC ? B.colk[B.view_colbegin[view] + zm] : -1;
   int a = B.view_angle[view];
   float val = 0.f;
   if (k >= 0 && B.rayvalid[a * B.D2 + j]) {
@@ -254,7 +256,7 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
 // image of voxel (zc,yc,xc centred) under one pair member, SLR:1225-1243:
 //   X = fma(-S,y,C*x) + D3//2 ; Y = fma(C,y,S*x) + D3//2 ; Z = (z + L3//2) + rise*h ; rint each.
 __device__ __forceinline__ int sym_image(double C, double S, double zs, int xc, int yc, int zc, int D3, int L3,
-                                         int ndisk, const int* __restrict__ rank) {
+                                         int L3P, const int* __restrict__ rank) {
   double x = (double)xc, y = (double)yc;
   double X = __dadd_rn(__fma_rn(-S, y, __dmul_rn(C, x)), (double)(D3 / 2));
   double Y = __dadd_rn(__fma_rn(C, y, __dmul_rn(S, x)), (double)(D3 / 2));
@@ -265,7 +267,7 @@ __device__ __forceinline__ int sym_image(double C, double S, double zs, int xc, 
     return -1;
   int r = rank[(int)yr * D3 + (int)xr];
   if (r < 0) return -1;
-  return (int)zr * ndisk + r;
+  return r * L3P + (int)zr;  // internal (z-fastest) voxel index
 }
 
 // round `rnd`: every still-open candidate processes its rnd-th pair.
@@ -279,9 +281,9 @@ __global__ void k_sym_insert(BD B, SymSetup Q, int rnd) {
   int z = g / B.ndisk, p = g % B.ndisk;
   short2 yx = Q.disk_yx_sym[p];
   int xc = yx.y - B.D3 / 2, yc = yx.x - B.D3 / 2, zc = z - B.L3 / 2;
-  int a = sym_image(pr[0], pr[1], pr[2], xc, yc, zc, B.D3, B.L3, B.ndisk, Q.rank_sym);
-  int b = sym_image(pr[3], pr[4], pr[5], xc, yc, zc, B.D3, B.L3, B.ndisk, Q.rank_sym);
-  size_t ti = (size_t)c * B.npad + g;
+  int a = sym_image(pr[0], pr[1], pr[2], xc, yc, zc, B.D3, B.L3, B.L3P, Q.rank_sym);
+  int b = sym_image(pr[3], pr[4], pr[5], xc, yc, zc, B.D3, B.L3, B.L3P, Q.rank_sym);
+  size_t ti = (size_t)c * B.nrp + g;
   if (a < 0 || b < 0) {
     Q.tmp_a[ti] = -1; Q.tmp_b[ti] = -1;
     return;
@@ -310,8 +312,8 @@ __global__ void k_sym_insert(BD B, SymSetup Q, int rnd) {
 __global__ void k_sym_check(BD B, SymSetup Q, int rnd) {
   int c = blockIdx.y;
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B.npad) return;
-  size_t ti = (size_t)c * B.npad + g;
+  if (g >= B.nrp) return;
+  size_t ti = (size_t)c * B.nrp + g;
   int keep = 0;
   if (!Q.done[c] && g < B.n) {
     int a = Q.tmp_a[ti], b = Q.tmp_b[ti];
@@ -340,9 +342,9 @@ __global__ void k_sym_compact(BD B, SymSetup Q) {
   if (Q.done[c]) return;
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= B.n) return;
-  size_t ti = (size_t)c * B.npad + g;
+  size_t ti = (size_t)c * B.nrp + g;
   if (!Q.flag[ti]) return;
-  long long row = (long long)B.cand_msym[c] + (Q.pos[ti] - Q.pos[(size_t)c * B.npad]);
+  long long row = (long long)B.cand_msym[c] + (Q.pos[ti] - Q.pos[(size_t)c * B.nrp]);
   if (row >= Q.symcap[c]) { atomicExch(Q.overflow, 2); return; }
   Q.sym_a_w[B.cand_symoff[c] + row] = Q.tmp_a[ti];
   Q.sym_b_w[B.cand_symoff[c] + row] = Q.tmp_b[ti];
@@ -352,8 +354,8 @@ __global__ void k_sym_compact(BD B, SymSetup Q) {
 __global__ void k_sym_finalize(BD B, SymSetup Q, int rnd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= B.nc || Q.done[c]) return;
-  size_t last = (size_t)c * B.npad + (B.npad - 1);
-  int cnt = Q.pos[last] + Q.flag[last] - Q.pos[(size_t)c * B.npad];
+  size_t last = (size_t)c * B.nrp + (B.nrp - 1);
+  int cnt = Q.pos[last] + Q.flag[last] - Q.pos[(size_t)c * B.nrp];
   int tot = B.cand_msym[c] + cnt;
   B.cand_msym[c] = tot;
   if ((long long)tot >= Q.min_pairs[c] || rnd + 1 >= Q.pair_count[c]) {
@@ -368,31 +370,31 @@ __global__ void k_csc_count(BD B, int* __restrict__ cnt) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.cand_msym[c]) return;
   int a = B.sym_a[B.cand_symoff[c] + r], b = B.sym_b[B.cand_symoff[c] + r];
-  atomicAdd(&cnt[(size_t)c * (B.n + 1) + a], 1);
-  atomicAdd(&cnt[(size_t)c * (B.n + 1) + b], 1);
+  atomicAdd(&cnt[(size_t)c * (B.npad + 1) + a], 1);
+  atomicAdd(&cnt[(size_t)c * (B.npad + 1) + b], 1);
 }
 __global__ void k_csc_rebase2(BD B, const int* __restrict__ scan, int* __restrict__ ptr) {
   int c = blockIdx.y;
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g > B.n) return;
-  ptr[(size_t)c * (B.n + 1) + g] = scan[(size_t)c * (B.n + 1) + g] - scan[(size_t)c * (B.n + 1)];
+  if (g > B.npad) return;
+  ptr[(size_t)c * (B.npad + 1) + g] = scan[(size_t)c * (B.npad + 1) + g] - scan[(size_t)c * (B.npad + 1)];
 }
 __global__ void k_csc_fill(BD B, int* __restrict__ cursor, int* __restrict__ ent) {
   int c = blockIdx.y;
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B.cand_msym[c]) return;
   int a = B.sym_a[B.cand_symoff[c] + r], b = B.sym_b[B.cand_symoff[c] + r];
-  const int* ptr = B.csc_ptr + (size_t)c * (B.n + 1);
-  int sa = atomicAdd(&cursor[(size_t)c * (B.n + 1) + a], 1);
+  const int* ptr = B.csc_ptr + (size_t)c * (B.npad + 1);
+  int sa = atomicAdd(&cursor[(size_t)c * (B.npad + 1) + a], 1);
   ent[B.cand_cscoff[c] + ptr[a] + sa] = r;
-  int sb = atomicAdd(&cursor[(size_t)c * (B.n + 1) + b], 1);
+  int sb = atomicAdd(&cursor[(size_t)c * (B.npad + 1) + b], 1);
   ent[B.cand_cscoff[c] + ptr[b] + sb] = r | (int)0x80000000;
 }
 __global__ void k_csc_sort(BD B, int* __restrict__ ent) {  // deterministic order: by row index
   int c = blockIdx.y;
   int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B.n) return;
-  const int* ptr = B.csc_ptr + (size_t)c * (B.n + 1);
+  if (g >= B.npad) return;
+  const int* ptr = B.csc_ptr + (size_t)c * (B.npad + 1);
   int e0 = ptr[g], e1 = ptr[g + 1];
   int* e = ent + B.cand_cscoff[c];
   for (int i = e0 + 1; i < e1; ++i) {
@@ -410,14 +412,18 @@ __global__ void k_csc_sort(BD B, int* __restrict__ ent) {  // deterministic orde
 }
 
 // ===========================================================================
-// forward projector: data rows.  One CTA = 32 consecutive rays of one view.
-// Each warp walks a ray: lanes over depth samples, gathers the L3 slices at the
-// same in-plane voxel (the in-plane map is z-independent), warp-shuffle reduces.
+// forward projector: data rows.  One CTA = 32 consecutive rays of one view, one
+// warp per ray.  Lanes are split 8 sample groups x 4 slice quads: per step the
+// warp reads 8 map entries and, for each, one 128-bit load per quad gathers 4
+// slices of the voxel (z-fastest layout), so one index lookup serves up to 16
+// slices.  The 8 sample groups are combined with 3 shuffle steps.
 // MODE_LSMR : u~ <- A v - alpha * (u~ * inv_beta)       (lsmr.py:331-332)
 // MODE_PLAIN: u  <- A xs
 // MODE_SCORE: accumulate <pred,b>, <pred,pred>, <b,b>   (SLR:500-525)
 // ===========================================================================
-template <typename IdxT, int ZC>
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <typename IdxT>
 __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
@@ -437,60 +443,61 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   __syncthreads();
   const float alpha = S.alpha, inv_beta = S.inv_beta;
   const int a = B.view_angle[view];
-  const int D2 = B.D2, L3 = B.L3, MC = B.MC, ndisk = B.ndisk;
+  const int D2 = B.D2, L3 = B.L3, L3P = B.L3P, MC = B.MC, ZMP = B.ZMP;
   const IdxT* __restrict__ fm = (const IdxT*)B.fmap + (size_t)a * D2 * D2;
   const float* __restrict__ vsrc = (mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad;
   float* urow = B.u + B.view_uoff[view];
   const float* brow = B.b + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane & 3, sg = lane >> 2;
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   for (int r = warp; r < HB2_TILE_RAYS; r += HB2_BLOCK / 32) {
     const int j = tile * HB2_TILE_RAYS + r;
     if (j >= D2) break;
     if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
     const IdxT* __restrict__ fj = fm + (size_t)j * D2;
-    for (int z0 = 0; z0 < L3; z0 += ZC) {
-      unsigned zmask = 0;
-#pragma unroll
-      for (int zz = 0; zz < ZC; ++zz) {
-        int z = z0 + zz;
-        if (z < L3)
-          for (int mc = 0; mc < MC; ++mc)
-            if (s_colk[z * MC + mc] >= 0) zmask |= 1u << zz;
-      }
-      if (!zmask) continue;
-      float acc[ZC];
-#pragma unroll
-      for (int zz = 0; zz < ZC; ++zz) acc[zz] = 0.f;
-      for (int t = lane; t < D2; t += 32) {
-        IdxT id = fj[t];
-        if (id != Sent<IdxT>::v) {
-          const float* __restrict__ vp = vsrc + (size_t)z0 * ndisk + id;
-#pragma unroll
-          for (int zz = 0; zz < ZC; ++zz)
-            if (zmask & (1u << zz)) acc[zz] += __ldg(vp + (size_t)zz * ndisk);
+    for (int z0 = 0; z0 < L3P; z0 += 16) {
+      const int zq = z0 + 4 * q;  // this lane's 4 slices
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (zq < L3P) {
+        const float* __restrict__ vb = vsrc + zq;
+#pragma unroll 4
+        for (int i = sg; i < D2; i += 8) {
+          IdxT id = fj[i];
+          if (id != Sent<IdxT>::v) {
+            float4 t = ldg4(vb + (size_t)id * L3P);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
         }
       }
 #pragma unroll
-      for (int zz = 0; zz < ZC; ++zz) acc[zz] = warp_sum(acc[zz]);
-      // lane e writes column (zz = e / MC, mc = e % MC)
-      for (int e = lane; e < ZC * MC; e += 32) {
-        int zz = e / MC, mc = e - zz * MC, z = z0 + zz;
-        if (z >= L3 || s_colk[z * MC + mc] < 0) continue;
-        float sum = 0.f;
-#pragma unroll
-        for (int q = 0; q < ZC; ++q) sum = (q == zz) ? acc[q] : sum;
-        size_t ri = (size_t)(z * MC + mc) * D2 + j;
-        if (mode == MODE_LSMR) {
-          float un = fadd_(fmul_(fmul_(urow[ri], inv_beta), -alpha), sum);
-          urow[ri] = un;
-          ss += un * un;
-        } else if (mode == MODE_PLAIN) {
-          urow[ri] = sum;
-        } else {
-          float pred = B.clip_pred ? fmaxf(sum, 0.f) : sum;
-          float bv = brow[ri];
-          ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+      for (int o = 4; o < 32; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      }
+      // every lane of a quad now holds the quad's 4 slice sums; lane (sg = t, q) finishes slice z = zq + t
+      if (sg < 4) {
+        const int z = zq + sg;
+        if (z < L3) {
+          const float sum = sg == 0 ? acc.x : (sg == 1 ? acc.y : (sg == 2 ? acc.z : acc.w));
+          for (int mc = 0; mc < MC; ++mc) {
+            const int zm = z * MC + mc;
+            if (s_colk[zm] < 0) continue;
+            const size_t ri = (size_t)j * ZMP + zm;
+            if (mode == MODE_LSMR) {
+              float un = fadd_(fmul_(fmul_(urow[ri], inv_beta), -alpha), sum);
+              urow[ri] = un;
+              ss += un * un;
+            } else if (mode == MODE_PLAIN) {
+              urow[ri] = sum;
+            } else {
+              float pred = B.clip_pred ? fmaxf(sum, 0.f) : sum;
+              float bv = brow[ri];
+              ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+            }
+          }
         }
       }
     }
@@ -541,10 +548,11 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_sym(BD B, int mode) {
 }
 
 // ===========================================================================
-// adjoint: voxel-driven gather.  One thread = one in-plane voxel p and a chunk
-// of ZC slices; loops over the candidate's views, reads the adjoint map once per
-// view and gathers the rays' rows for every slice of the chunk; then adds the
-// symmetry rows incident to each voxel.
+// adjoint: voxel-driven gather.  One thread = one in-plane voxel p and ZC slices
+// (all of them when L3P <= 16); it loops over the candidate's views, reads the
+// adjoint map (the rays whose samples land in p) once per view and gathers the
+// rays' rows for all slices with 128-bit loads; then adds the symmetry rows
+// incident to each voxel.
 // MODE_LSMR : v~ <- A^T (u~*inv_beta) - beta * v        (lsmr.py:336-338)
 // MODE_INIT : v~ <- A^T (u~*inv_beta)                    (lsmr.py:251)
 // MODE_PLAIN: xs <- A^T u
@@ -561,9 +569,9 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
     return;
   }
-  const int L3 = B.L3, D2 = B.D2, ndisk = B.ndisk;
+  const int L3 = B.L3, L3P = B.L3P, ZMP = B.ZMP, ndisk = B.ndisk;
   const int K = KT > 0 ? KT : B.K, MC = MCT > 0 ? MCT : B.MC;
-  const int nzch = (L3 + ZC - 1) / ZC;
+  const int nzch = (L3P + ZC - 1) / ZC;
   const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
   const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * ZC;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
@@ -577,44 +585,63 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     for (int vi = 0; vi < nv; ++vi) {
       const int view = vb + vi;
       const int a = __ldg(B.view_angle + view);
-      const float* __restrict__ ub = B.u + __ldg(B.view_uoff + view) + (size_t)z0 * MC * D2;
+      const float* __restrict__ ub = B.u + __ldg(B.view_uoff + view) + z0 * MC;
       const uint16_t* __restrict__ am = B.amap + (size_t)a * K * ndisk + p;
 #pragma unroll
-      for (int k = 0; k < (KT > 0 ? KT : 8); ++k) {
-        if (k >= K) break;
+      for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
         uint16_t j = am[(size_t)k * ndisk];
         if (j != 0xFFFFu) {
-          const float* __restrict__ uj = ub + j;
+          const float* __restrict__ uj = ub + (size_t)j * ZMP;
+          if (MCT == 1) {
 #pragma unroll
-          for (int zz = 0; zz < ZC; ++zz) {
-            if (z0 + zz < L3) {
-              for (int mc = 0; mc < MC; ++mc) acc[zz] = fmaf(__ldg(uj + (size_t)(zz * MC + mc) * D2), ib, acc[zz]);
+            for (int q4 = 0; q4 < ZC / 4; ++q4) {
+              if (z0 + 4 * q4 < L3P) {
+                float4 t = ldg4(uj + 4 * q4);
+                acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]);
+                acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
+                acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]);
+                acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+              }
             }
+          } else {
+#pragma unroll
+            for (int zz = 0; zz < ZC; ++zz)
+              if (z0 + zz < L3)
+                for (int mc = 0; mc < MC; ++mc) acc[zz] = fmaf(__ldg(uj + zz * MC + mc), ib, acc[zz]);
           }
         }
       }
     }
-    // symmetry rows incident to (z,p)
-    const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.n + 1);
+    // symmetry rows incident to (p, z)
+    const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1);
     const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
     const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
-    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad;
+    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + (size_t)p * L3P + z0;
+    const int g0 = p * L3P + z0;
 #pragma unroll
-    for (int zz = 0; zz < ZC; ++zz) {
-      int z = z0 + zz;
-      if (z < L3) {
-        int g = z * ndisk + p;
-        int e0 = ptr[g], e1 = ptr[g + 1];
-        float a2 = acc[zz];
-        for (int e = e0; e < e1; ++e) {
-          int en = ent[e];
-          float val = __ldg(us + (en & 0x7fffffff));
-          a2 = fmaf(en < 0 ? -val : val, ib, a2);
+    for (int q4 = 0; q4 < ZC / 4; ++q4) {
+      if (z0 + 4 * q4 < L3P) {
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
+        float vn[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int zz = 4 * q4 + t;
+          float a2 = acc[zz];
+          if (z0 + zz < L3) {
+            const int g = g0 + zz;
+            const int e0 = ptr[g], e1 = ptr[g + 1];
+            for (int e = e0; e < e1; ++e) {
+              int en = ent[e];
+              float val = __ldg(us + (en & 0x7fffffff));
+              a2 = fmaf(en < 0 ? -val : val, ib, a2);
+            }
+          }
+          const float o = t == 0 ? old.x : (t == 1 ? old.y : (t == 2 ? old.z : old.w));
+          vn[t] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), a2) : a2;
+          ss += vn[t] * vn[t];
         }
-        float vn = a2;
-        if (mode == MODE_LSMR) vn = fadd_(fmul_(vdst[g], -beta), a2);
-        vdst[g] = vn;
-        ss += vn * vn;
+        *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
       }
     }
   }
@@ -646,7 +673,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_update(BD B, int mode) {
   double* hbar = B.hbar + (size_t)c * B.npad;
   double sx = 0.0;
   for (int i = blockIdx.x * HB2_BLOCK * 4 + threadIdx.x, q = 0; q < 4; ++q, i += HB2_BLOCK) {
-    if (i < B.n) {
+    if (i < B.npad) {
       float vn = v[i];
       if (normalise) { vn = fmul_(vn, ia); v[i] = vn; }
       if (mode == MODE_INIT) {
@@ -670,7 +697,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_update(BD B, int mode) {
 __global__ void k_x_to_f32(BD B) {
   const int c = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B.n) B.xs[(size_t)c * B.npad + i] = (float)B.x[(size_t)c * B.npad + i];
+  if (i < B.npad) B.xs[(size_t)c * B.npad + i] = (float)B.x[(size_t)c * B.npad + i];
 }
 
 // ===========================================================================

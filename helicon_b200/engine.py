@@ -13,7 +13,7 @@ from .planner import BatchPlan, CandidateSpec
 
 DEFAULT_OPTIONS = dict(
     max_iter=1000, atol=1e-4, btol=1e-4, conlim=1e8, check_every=8, clip_pred=0, trf_max_iter=200, trf_tol=1e-2,
-    fixed_iters=0,
+    fixed_iters=0, profile=0,
 )
 
 
@@ -106,9 +106,11 @@ class Batch:
         return res
 
     def timing(self):
-        out = np.zeros(8, dtype=np.float64)
+        out = np.zeros(16, dtype=np.float64)
         _lib.check(_lib.load().hb2_batch_timing(self._h, _lib.ptr(out)))
-        return dict(lsmr_ms=out[0], trf_ms=out[1], score_ms=out[2], launches=int(out[3]), iterations=int(out[4]))
+        return dict(lsmr_ms=out[0], trf_ms=out[1], score_ms=out[2], launches=int(out[3]), iterations=int(out[4]),
+                    fwd_data_ms=out[5], fwd_sym_ms=out[6], adj_ms=out[7], update_ms=out[8], scalar_ms=out[9],
+                    fwd_data_launches=int(out[10]), adj_launches=int(out[11]), update_launches=int(out[12]))
 
     def x(self, c):
         out = np.empty(self.n, dtype=np.float32)
@@ -166,8 +168,9 @@ class Batch:
 
     def data_row_index(self, c):
         """For every real data row, in the reference's order (copy, k, j), its
-        index in the padded layout [view][z][mc][j], plus (k, j)."""
+        index in the padded layout [view][j][z*MC+mc] (row stride ZMP), plus (k, j)."""
         D2, L3, MC = self.problem.D2, self.L3, self.plan.MC
+        ZMP = (L3 * MC + 3) // 4 * 4
         rv = self.ray_valid()
         idx, kk, jj = [], [], []
         for vi, (a, zi, h, cc, nrows) in enumerate(self.plan.cand_views[c]):
@@ -177,7 +180,7 @@ class Batch:
                 z = int(zi[k])
                 zm = z * MC + fill[z]
                 fill[z] += 1
-                idx.append(vi * (L3 * MC * D2) + zm * D2 + js)
+                idx.append(vi * (D2 * ZMP) + js * ZMP + zm)
                 kk.append(np.full(len(js), k))
                 jj.append(js)
         if not idx:

@@ -1,0 +1,185 @@
+"""Batched (twist x rise [x csym]) grid search -- the driver the reference runs
+as a ThreadPoolExecutor over ``process_one_task`` (webApps/denovo3D/app.py:
+2286-2523) -- with thousands of candidates resident on the GPU at once.
+
+Geometry derivation follows ``pipeline.process_one_task`` (pipeline.py:253-349)
+for the no-rescale case (target_apix2d <= apix2d_orig); the per-candidate
+semantics are those of ``lsq_reconstruct`` (solver_linear_regression.py:31-547).
+"""
+
+from __future__ import annotations
+
+import itertools
+import time
+
+import numpy as np
+
+from .engine import Batch, Problem
+from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
+
+
+def derive_geometry(ny, nx, apix2d_orig, rise, rise_max, tube_diameter, tube_diameter_inner, tube_length,
+                    reconstruct_length, target_apix2d, target_apix3d, sym_oversample, return_3d=False, tilt_max=0.0):
+    """Integer geometry of one task, pipeline.py:253-349 (image already at target_apix2d)."""
+    reconstruct_diameter = tube_diameter if 0 < tube_diameter < ny * apix2d_orig else ny * apix2d_orig
+    reconstruct_diameter_inner = tube_diameter_inner if 0 < tube_diameter_inner < reconstruct_diameter else 0
+    if reconstruct_length < rise:
+        reconstruct_length = max(min(3 * rise_max, tube_length),
+                                 round(np.tan(np.deg2rad(abs(tilt_max))) * tube_diameter * 3))
+    if target_apix2d < apix2d_orig:
+        target_apix2d = apix2d_orig
+    if target_apix2d != apix2d_orig:
+        raise NotImplementedError("helicon_b200: image down-scaling (target_apix2d > apix2d_orig, skimage rescale) "
+                                  "is outside the CUDA hot path; pass an image already at the target pixel size")
+    if target_apix3d < 0:
+        vol = reconstruct_length * (reconstruct_diameter**2 - reconstruct_diameter_inner**2) / 4 * np.pi
+        target_apix3d = max(target_apix2d, round(np.power(vol / (nx * ny), 1 / 3) + 0.5))
+    elif target_apix3d == 0:
+        target_apix3d = target_apix2d
+    D3 = int(round(reconstruct_diameter / target_apix3d))
+    D3 += D3 % 2
+    D3i = int(round(tube_diameter_inner / target_apix3d))
+    D2 = int(round(reconstruct_diameter / target_apix2d))
+    D2 += D2 % 2
+    reconstruct_length_2d = tube_length if 0 < tube_length < nx * target_apix2d else nx * target_apix2d
+    L2 = int(reconstruct_length_2d / target_apix2d)
+    L2 += L2 % 2
+    if reconstruct_length > 0:
+        L3 = max(int(np.ceil(rise / target_apix3d)), int(np.ceil(reconstruct_length / target_apix3d)))
+        L3 += L3 % 2
+    else:
+        L3 = int(L2 * target_apix2d / target_apix3d + 0.5)
+        L3 += L3 % 2
+    if sym_oversample <= 0:
+        n_voxels = L3 * (D3**2 - D3i**2)
+        ratio = 2**20 / n_voxels
+        if ratio < 10:
+            sym_oversample = max(1, int(round(ratio)))
+        elif ratio < 100:
+            sym_oversample = max(1, int(round(ratio / 10)) * 10)
+        else:
+            sym_oversample = max(1, int(round(ratio / 100)) * 100)
+        if return_3d:
+            sym_oversample *= 2
+    return dict(D2=D2, L2=L2, D3=D3, D3i=D3i, L3=L3, sym_oversample=sym_oversample, apix2d=target_apix2d,
+                apix3d=target_apix3d, s=target_apix2d / target_apix3d)
+
+
+def _periodic(v, lo=-180.0, hi=180.0):
+    """lib/angular.py:84-108 ``set_to_periodic_range``."""
+    import math
+
+    if lo <= v <= hi:
+        return v
+    tmp = math.fmod(v - lo, hi - lo)
+    return tmp + lo if tmp >= 0 else tmp + hi
+
+
+class GridTask:
+    __slots__ = ("ti", "twist", "rise", "csym", "geom", "spec")
+
+    def __init__(self, ti, twist, rise, csym, geom, spec):
+        self.ti, self.twist, self.rise, self.csym, self.geom, self.spec = ti, twist, rise, csym, geom, spec
+
+
+def build_tasks(ny, nx, apix, twists, rises, csyms=(1,), reconstruct_length_rise=3, tube_diameter=None,
+                tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
+                positive_constraint=-1, ndisk_of=None):
+    """Task list in the reference's order (twist-major, app.py:2338) with its skip rules (app.py:2389-2403)."""
+    tube_diameter = ny * apix if tube_diameter is None else tube_diameter
+    tube_length = nx * apix if tube_length is None else tube_length
+    rises = list(rises)
+    tasks = []
+    ti = 0
+    for csym in csyms:
+        for twist, rise in itertools.product(twists, rises):
+            twist = float(np.round(_periodic(float(twist)), 6))  # app.py:2360
+            this = ti
+            ti += 1
+            if abs(twist) < 0.01 or abs(rise) < 0.01 or abs(rise) >= tube_length / 2:
+                continue
+            g = derive_geometry(ny, nx, apix, rise, max(rises), tube_diameter, tube_diameter_inner, tube_length,
+                                reconstruct_length_rise * rise, apix, target_apix3d, sym_oversample)
+            tasks.append(GridTask(this, twist, float(rise), int(csym), g, None))
+    return tasks, ti
+
+
+def _bytes_per_candidate(n, md, cap):
+    return 8 * (md + cap) + 48 * n + 16 * cap + 8 * cap + 32 * (2 * cap + 17) + 16 * n + 12 * (n + 1)
+
+
+def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=3, tube_diameter=None,
+                tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
+                positive_constraint=-1, thresh_fraction=-1, top_k=10, device=0, stream=None, batch_candidates=None,
+                mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None):
+    """Solve + score every candidate of the grid on one GPU.
+
+    ``shard=(rank, world)`` keeps tasks ``rank::world`` of every twist-major
+    batch ordering so that several GPUs split the grid without communication.
+    Returns dict(scores[(n_csym,) T, R] (NaN = skipped task), itn, flags, top,
+    n_candidates, seconds).
+    """
+    image = np.ascontiguousarray(image, dtype=np.float32)
+    ny, nx = image.shape
+    twists = np.atleast_1d(np.asarray(twists, dtype=np.float64))
+    rises = np.atleast_1d(np.asarray(rises, dtype=np.float64))
+    tasks, ntot = build_tasks(ny, nx, apix, twists, rises, csyms, reconstruct_length_rise, tube_diameter,
+                              tube_diameter_inner, tube_length, target_apix3d, sym_oversample, positive_constraint)
+    rank, world = shard
+    if world > 1:
+        tasks = tasks[rank::world]
+    scores = np.full(ntot, np.nan, dtype=np.float32)
+    itn = np.zeros(ntot, dtype=np.int32)
+    flags = np.zeros(ntot, dtype=np.uint32)
+    t0 = time.perf_counter()
+    # group by everything a Problem/Batch must share
+    groups = {}
+    for t in tasks:
+        g = t.geom
+        key = (g["D2"], g["L2"], g["D3"], g["D3i"], g["s"], g["L3"])
+        groups.setdefault(key, []).append(t)
+    top = []
+    kernel_ms = 0.0
+    for (D2, L2, D3, D3i, s, L3), tl in groups.items():
+        prob = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
+        try:
+            n3 = L3 * prob.ndisk
+            for t in tl:
+                target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * t.geom["sym_oversample"]))
+                rise_px = t.rise / t.geom["apix3d"]
+                t.spec = CandidateSpec(t.twist, rise_px, t.csym, target, target,
+                                       positive_rule(positive_constraint, rise_px, t.twist, L3))
+            md_est = int((L3 + L2) / max(min(x.spec.rise_pixel for x in tl), 1e-3) + 3) * L3 * D2
+            cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
+            bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // _bytes_per_candidate(n3, md_est, cap_est))))
+            for i0 in range(0, len(tl), bs):
+                chunk = tl[i0:i0 + bs]
+                batch = Batch(prob, L3, [x.spec for x in chunk])
+                try:
+                    res = batch.solve(clip_pred=int(thresh_fraction >= 0))
+                    tm = batch.timing()
+                    kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
+                    for c, x in enumerate(chunk):
+                        scores[x.ti] = res[c]["score"]
+                        itn[x.ti] = res[c]["itn"]
+                        flags[x.ti] = res[c]["flags"]
+                    if top_k:
+                        order = np.argsort(-res["score"], kind="stable")[:top_k]
+                        for c in order:
+                            ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
+                                       rise=chunk[c].rise, csym=chunk[c].csym)
+                            if return_x_top:
+                                ent["rec3d"] = batch.rec3d(int(c))
+                            top.append(ent)
+                        top.sort(key=lambda e: (-e["score"], e["ti"]))
+                        del top[top_k:]
+                finally:
+                    batch.close()
+                if progress:
+                    progress(i0 + len(chunk), len(tl))
+        finally:
+            prob.close()
+    shape = (len(csyms), len(twists), len(rises))
+    out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
+               n_candidates=len(tasks), seconds=time.perf_counter() - t0, kernel_ms=kernel_ms)
+    return out

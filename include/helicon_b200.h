@@ -91,6 +91,7 @@ typedef struct {
   int32_t trf_max_iter;    /* max_iter of the bounded branch (SLR:241) = 200 */
   double trf_tol;          /* tol (SLR:240) = 1e-2 */
   int32_t fixed_iters;     /* >0: run exactly this many LSMR iterations, ignore stop tests (tests only) */
+  int32_t profile;         /* 1: bracket every kernel launch with CUDA events (per-kernel-class device time) */
 } hb2_solve_options;
 
 typedef struct {
@@ -141,13 +142,15 @@ void hb2_batch_destroy(hb2_batch* b);
 /* number of symmetry rows of a candidate, and the rows themselves as (a,b)
  * voxel-index pairs in the reference's row order: A[r,a]=+1, A[r,b]=-1. */
 int hb2_batch_sym_rows(hb2_batch* b, int32_t cand, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity);
-/* padded data-row count of a candidate (= view_count*L3*MC*D2) and total padded rows incl. symmetry rows */
+/* padded data-row count of a candidate (= view_count*D2*ZMP, ZMP = L3*MC rounded up to 4; row of (view v, ray j,
+ * slice z, slot mc) = v*D2*ZMP + j*ZMP + z*MC + mc) and total padded rows incl. symmetry rows */
 int64_t hb2_batch_rows_padded(hb2_batch* b, int32_t cand, int64_t* n_data_padded);
 /* right-hand side in padded layout, out[n_data_padded] */
 int hb2_batch_rhs(hb2_batch* b, int32_t cand, float* out_host);
 
 /* ---- operators (tests, drop-in exports) --------------------------------- */
-/* y = A x  (padded row layout: data rows [view][z][mc][j], then symmetry rows) */
+/* y = A x  (x in the reference's order z*ndisk + p; y in padded row layout: data rows [view][j][z*MC+mc], then
+ * symmetry rows) */
 int hb2_batch_apply_forward(hb2_batch* b, int32_t cand, const float* x_host, float* y_host);
 /* x = A^T y */
 int hb2_batch_apply_adjoint(hb2_batch* b, int32_t cand, const float* y_host, float* x_host);
@@ -161,8 +164,12 @@ int hb2_batch_apply_adjoint(hb2_batch* b, int32_t cand, const float* y_host, flo
 int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_result* results_host);
 /* solution vector x of one candidate as float32 in the reference's order (SLR:270, 538) */
 int hb2_batch_get_x(hb2_batch* b, int32_t cand, float* x_host);
-/* device time (ms) of the last hb2_batch_solve, per phase; out[8]: lsmr, trf, score, total kernels launched ... */
-int hb2_batch_timing(hb2_batch* b, double* out8);
+/* device time of the last hb2_batch_solve, out[16]:
+ * [0] lsmr phase ms, [1] trf phase ms, [2] score phase ms, [3] kernels launched, [4] lsmr iterations run,
+ * with opt.profile=1 also per kernel class, summed over launches (ms) and launch counts:
+ * [5] fwd_data ms [6] fwd_sym ms [7] adjoint ms [8] update ms [9] scalar kernels ms,
+ * [10] fwd_data launches [11] adjoint launches [12] update launches, [13..15] reserved */
+int hb2_batch_timing(hb2_batch* b, double* out16);
 
 /* ---- test hook: the LSMR scalar recurrences run on the HOST --------------- */
 /* Same code as the device path (compiled __host__ __device__).  state64 is an

@@ -221,6 +221,75 @@ def build_A_data_matrix(
     return A, b, b_pid
 
 
+def build_A_data_matrix_fast(image, scale2d_to_3d, twist_degree, rise_pixel, csym, D2, L2, D3, D3_inner, L3,
+                             min_projection_lines):
+    """nn data rows for tilt=psi=dy=0 from per-copy 2-D tables: with no tilt every
+    ray lies in one z-slice and the in-plane sample->voxel map is the same for all
+    image columns of a copy.  Identical to
+    ``build_A_data_matrix`` whenever no rounding decision sits within 1e-9 of a
+    boundary; otherwise this function defers to the literal builder.
+    Used for mid-size parity tests and as the CPU baseline's matrix builder (it is
+    faster than the reference's own numba builder, so the baseline is not
+    handicapped)."""
+    from scipy.spatial.transform import Rotation as R
+
+    s = float(scale2d_to_3d)
+    ny_i, nx_i = image.shape
+    pix = image[np.ix_(np.arange(D2) - D2 // 2 + ny_i // 2, np.arange(L2) - L2 // 2 + nx_i // 2)]
+    rmin, rmax = D3_inner / 2, D3 // 2 - 1
+    mask, idx, n_x = _disk_index(1, D2, D2, rmin, rmax)
+    rank2d = idx[0]
+    nd = n_x
+    c0 = D2 // 2
+    x0 = -(np.arange(D2, dtype=np.float64) - c0)
+    y0 = np.arange(D2, dtype=np.float64) - c0
+    kl = np.arange(L2, dtype=np.float64) - L2 // 2
+    if s != 1.0:
+        x0, y0, kl = x0 * s, y0 * s, kl * s
+    Yg, Xg = np.meshgrid(y0, x0, indexing="ij")  # (j, i)
+    pts = np.stack([Xg.ravel(), Yg.ravel(), np.zeros(D2 * D2)], axis=1)
+    near = lambda V: np.abs(np.abs(V - np.floor(V)) - 0.5) < 1e-9
+    ind_parts, cnt_parts, bs, pids = [], [], [], []
+    r0 = 0
+    for hi, ci in data_copies(rise_pixel, csym, L3, L2):
+        angle = twist_degree * hi + 360 * ci / csym
+        q = R.from_euler("z", angle, degrees=True).apply(pts, inverse=True)
+        X = q[:, 0].reshape(D2, D2) + c0
+        Y = q[:, 1].reshape(D2, D2) + c0
+        Z = (kl - hi * rise_pixel) + L3 // 2
+        inside = (X > -1) & (X < D2) & (Y > -1) & (Y < D2)
+        if np.any((near(X) | near(Y)) & inside) or np.any(near(Z) & (Z > -1) & (Z < L3)):
+            return build_A_data_matrix(image, s, twist_degree, rise_pixel, csym, 0, 0, 0, D2, L2, D3, D3_inner, L3,
+                                       min_projection_lines, "nn")
+        xi, yi, zi = np.rint(X).astype(np.int64), np.rint(Y).astype(np.int64), np.rint(Z).astype(np.int64)
+        ok = (xi >= 0) & (xi <= D2 - 1) & (yi >= 0) & (yi <= D2 - 1)
+        vox = np.full((D2, D2), -1, dtype=np.int64)
+        vox[ok] = rank2d[yi[ok], xi[ok]]
+        hit = vox >= 0
+        js = np.nonzero(hit.any(axis=1))[0]
+        ks = np.nonzero((zi >= 0) & (zi <= L3 - 1))[0]
+        nrow = len(js) * len(ks)
+        if nrow:
+            sub = vox[js]
+            h2 = sub >= 0
+            per_ray = h2.sum(axis=1).astype(np.int64)
+            v = sub[h2].astype(np.int32)  # ray-major, depth order: already CSR order within a column block
+            for k in ks:
+                ind_parts.append(v + np.int32(zi[k] * nd))
+                cnt_parts.append(per_ray)
+            bs.append(pix[np.ix_(js, ks)].T.ravel().astype(np.float32))
+            pids.append((ks[:, None] * D2 + js[None, :]).ravel().astype(np.int32))
+            r0 += nrow
+        if min_projection_lines > 0 and r0 > min_projection_lines:
+            break
+    indices = np.concatenate(ind_parts)
+    indptr = np.zeros(r0 + 1, dtype=np.int64)
+    np.cumsum(np.concatenate(cnt_parts), out=indptr[1:])
+    A = csr_matrix((np.ones(len(indices), dtype=np.float32), indices, indptr), shape=(r0, L3 * nd), dtype=np.float32)
+    A.sum_duplicates()  # the reference's COO->CSR conversion sums duplicate samples of a ray
+    return A, np.concatenate(bs), np.concatenate(pids)
+
+
 def _rows_nn(Z, Y, X, mask, idx, n_x):
     """SLR:1514-1557 (half-to-even rounding like numba's round())."""
     nz, ny, nx = Z.shape
@@ -300,7 +369,7 @@ def build_A_helical_sym_matrix(
     kz, jy, ix = np.nonzero(mask)
     xyz = np.stack([ix - nx // 2, jy - ny // 2, kz - nz // 2], axis=1).astype(np.float64)
     linear = interpolation in ["linear", "linear01", "linear11"]
-    seen = set()
+    seen = set() if linear else {}
     blocks = []
     row_count = 0
 
@@ -335,15 +404,20 @@ def _valid_index(Zr, Yr, Xr, mask, idx):
 
 
 def _dedup_first_seen(a, b, n, seen):
-    """Sequential first-seen-wins on unordered (a,b) (SLR:1197-1202)."""
-    keep = np.zeros(len(a), dtype=bool)
-    for t in range(len(a)):
-        key = int(a[t]) * n + int(b[t])
-        if key in seen:
-            continue
-        seen.add(key)
-        seen.add(int(b[t]) * n + int(a[t]))
-        keep[t] = True
+    """First-seen-wins on unordered (a,b) (SLR:1197-1202): a candidate row is kept
+    iff its unordered key was not produced by an earlier pair or an earlier voxel
+    of this pair.  ``seen`` is a dict holding one sorted int64 array of keys
+    (vectorised equivalent of the reference's Python set + sequential loop)."""
+    lo, hi = np.minimum(a, b).astype(np.int64), np.maximum(a, b).astype(np.int64)
+    key = lo * np.int64(n) + hi
+    old = seen.get("keys")
+    fresh = np.ones(len(key), dtype=bool) if old is None or len(old) == 0 else ~np.isin(key, old, assume_unique=False)
+    uniq, first = np.unique(key, return_index=True)
+    is_first = np.zeros(len(key), dtype=bool)
+    is_first[first] = True
+    keep = fresh & is_first
+    newk = key[keep]
+    seen["keys"] = newk if old is None else np.union1d(old, newk)
     return keep
 
 
@@ -468,9 +542,10 @@ def lsq_reconstruct(
     sym_oversample=1,
     interpolation="nn",
     return_details=False,
+    fast=False,
 ):
     """SLR:31-547 for algorithm={'model':'lsq'}, fsc_test=0, score_metric='cosine',
-    no tilt/psi/dy refinement."""
+    no tilt/psi/dy refinement.  ``fast=True`` uses ``build_A_data_matrix_fast``."""
     D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
     rmin = reconstruct_diameter_3d_inner_pixel / 2
     rmax = D3 // 2 - 1
@@ -478,23 +553,28 @@ def lsq_reconstruct(
     n3 = int(np.count_nonzero(mask))
     n2 = reconstruct_diameter_2d_pixel * reconstruct_length_2d_pixel
     target = min(MAX_EQUATIONS, int(max(n2, n3) * sym_oversample))
-    A_data, b_data, b_pid = build_A_data_matrix(
-        projection_image,
-        scale2d_to_3d,
-        twist_degree,
-        rise_pixel,
-        csym,
-        tilt_degree,
-        psi_degree,
-        dy_pixel,
-        reconstruct_diameter_2d_pixel,
-        reconstruct_length_2d_pixel,
-        D3,
-        reconstruct_diameter_3d_inner_pixel,
-        L3,
-        target,
-        interpolation,
-    )
+    if fast and interpolation == "nn" and tilt_degree == 0 and psi_degree == 0 and dy_pixel == 0:
+        A_data, b_data, b_pid = build_A_data_matrix_fast(
+            projection_image, scale2d_to_3d, twist_degree, rise_pixel, csym, reconstruct_diameter_2d_pixel,
+            reconstruct_length_2d_pixel, D3, reconstruct_diameter_3d_inner_pixel, L3, target)
+    else:
+        A_data, b_data, b_pid = build_A_data_matrix(
+            projection_image,
+            scale2d_to_3d,
+            twist_degree,
+            rise_pixel,
+            csym,
+            tilt_degree,
+            psi_degree,
+            dy_pixel,
+            reconstruct_diameter_2d_pixel,
+            reconstruct_length_2d_pixel,
+            D3,
+            reconstruct_diameter_3d_inner_pixel,
+            L3,
+            target,
+            interpolation,
+        )
     A_hsym, b_hsym = build_A_helical_sym_matrix(
         L3, D3, D3, twist_degree, rise_pixel, csym, rmin, rmax, target, interpolation
     )
