@@ -82,7 +82,7 @@ EXPORTS = [
     "hb2_problem_ndisk", "hb2_problem_rank_table", "hb2_batch_begin", "hb2_batch_ray_valid", "hb2_batch_angle_map",
     "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_rows_padded", "hb2_batch_rhs",
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
-    "hb2_lsmr_scalar_step",
+    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def load():
     lib.hb2_batch_solve.argtypes = [vp, P(SolveOptions), vp]
     lib.hb2_batch_get_x.argtypes = [vp, i32, vp]
     lib.hb2_batch_timing.argtypes = [vp, vp]
+    lib.hb2_batch_trf_trace.argtypes = [vp, i32, vp, i32]
     lib.hb2_lsmr_scalar_step.argtypes = [vp, C.c_int, C.c_float, C.c_float, f64, f64, f64, f64, C.c_int, P(C.c_float), P(C.c_float), P(C.c_float), vp]
     _lib = lib
     return lib

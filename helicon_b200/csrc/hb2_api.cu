@@ -1,6 +1,7 @@
 // helicon_b200: C-ABI host side (include/helicon_b200.h).  One translation unit.
 #include "../../include/helicon_b200.h"
 #include "hb2_kernels.cuh"
+#include "hb2_trf.cuh"
 
 #include <cub/cub.cuh>
 
@@ -101,6 +102,7 @@ struct hb2_batch {
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
   double timing[16] = {0};
+  std::vector<TrfState> last_trf;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<std::pair<int, int>> ev_used;  // (class, index of start event)
   size_t ev_next = 0;
@@ -679,6 +681,137 @@ extern "C" int hb2_batch_apply_adjoint(hb2_batch* b, int32_t c, const float* y_h
   return HB2_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// bounded branch driver (hb2_trf.cuh): scipy trf_linear as a batched state machine
+// ---------------------------------------------------------------------------
+static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfState>& out, long long& launches, int& outer_iters) {
+  BD& B = b->B;
+  cudaStream_t st = b->stream;
+  const int nc = B.nc;
+  bool any = false;
+  for (int c = 0; c < nc; ++c) any = any || b->cands[c].positive;
+  out.assign(nc, TrfState{});
+  if (!any) return HB2_OK;
+  DevPool tmp;
+  TD T{};
+#define CKT2(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tmp.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  const size_t nv = (size_t)nc * B.npad, nu = (size_t)b->u_total;
+  double** nvecs[] = {&T.G, &T.D, &T.DH, &T.PH, &T.RH, &T.STEP, &T.V, &T.H, &T.HBAR, &T.XIN, &T.W, &T.UN};
+  for (double** p : nvecs) CKT2(tmp.alloc(p, nv, true, st));
+  double** mvecs[] = {&T.R, &T.UM, &T.Y, &T.Y2};
+  for (double** p : mvecs) CKT2(tmp.alloc(p, nu, true, st));
+  long long max_m = 0;
+  for (int c = 0; c < nc; ++c) max_m = std::max<long long>(max_m, (long long)b->h_mdata[c] + b->h_msym[c]);
+  const unsigned gn = cdiv(B.npad, HB2_BLOCK * 4), gm = std::max(1u, cdiv(max_m, HB2_BLOCK * 4));
+  T.red_slots = (int)std::max(gn, gm);
+  CKT2(tmp.alloc(&T.red, (size_t)nc * T.red_slots * TRF_NRED, true, st));
+  CKT2(tmp.alloc(&T.st, nc, true, st));
+  CKT2(tmp.alloc(&T.nactive, 1, true, st));
+  CKT2(tmp.alloc(&T.ninner, 1, true, st));
+  {
+    std::vector<float> bmax(nc);
+    CKT2(cudaMemcpyAsync(bmax.data(), b->d_bmax, sizeof(float) * nc, cudaMemcpyDeviceToHost, st));
+    CKT2(cudaStreamSynchronize(st));
+    std::vector<TrfState> hs(nc, TrfState{});
+    for (int c = 0; c < nc; ++c) {
+      int iv;
+      memcpy(&iv, &bmax[c], 4);
+      iv = iv >= 0 ? iv : iv ^ 0x7fffffff;  // undo the ordered-int encoding of k_build_rhs
+      float ub;
+      memcpy(&ub, &iv, 4);
+      hs[c].needed = b->cands[c].positive ? 1 : 0;
+      hs[c].lb = 0.0; hs[c].ub = (double)ub;  // SLR:247-248
+      hs[c].tol = opt->trf_tol > 0 ? opt->trf_tol : 1e-2;
+      if (!(hs[c].ub > hs[c].lb)) hs[c].needed = 0;  // scipy would raise "lb >= ub"
+    }
+    CKT2(cudaMemcpyAsync(T.st, hs.data(), sizeof(TrfState) * nc, cudaMemcpyHostToDevice, st));
+    CKT2(cudaStreamSynchronize(st));
+  }
+  const double EPS = 2.220446049250313e-16;
+  const int lsmr_maxiter = opt->max_iter > 0 ? opt->max_iter : 1000;
+  const int max_iter = opt->trf_max_iter > 0 ? opt->trf_max_iter : 200;
+  const dim3 g_n(gn, nc), g_m(gm, nc), g_sym(std::max(1, B.part_us_per_cand), nc);
+  const int adj_zc = B.L3P >= 16 ? 16 : B.L3P;
+  const dim3 g_adj(cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3P, adj_zc), nc);
+  const unsigned g_fwd = (unsigned)b->nviews * ((B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS);
+  const unsigned g_sc = cdiv(nc, 128);
+  auto ew = [&](int op) { k_trf_ew<<<g_n, HB2_BLOCK, 0, st>>>(B, T, op); ++launches; };
+  auto mw = [&](int op) { k_trf_mw<<<g_m, HB2_BLOCK, 0, st>>>(B, T, op); ++launches; };
+  auto red = [&](int nslots, int add, int gate, int start = 0) { k_trf_reduce<<<nc, HB2_BLOCK, 0, st>>>(B, T, nslots, add, gate, start); ++launches; };
+  auto sc = [&](int op) { k_trf_scal<<<g_sc, 128, 0, st>>>(B, T, op, EPS, lsmr_maxiter, max_iter); ++launches; };
+  auto fwd = [&](const double* src, double* dst, int gate) {
+    if (b->idx16) k_fwd64_data<uint16_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+    else k_fwd64_data<uint32_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+    k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+    launches += 2;
+  };
+  auto adj = [&](const double* rows, double* dst, int gate) {
+    if (adj_zc == 4) k_adj64<4><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    else if (adj_zc == 8) k_adj64<8><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    else if (adj_zc == 12) k_adj64<12><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    else k_adj64<16><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    ++launches;
+  };
+  auto read_counter = [&](int* dptr, int& v) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(b->h_nactive, dptr, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    v = *b->h_nactive;
+    return e;
+  };
+  // is the unconstrained solution feasible? (lsq_linear.py:328)
+  ew(EW_START); red(gn, 0, 0, 1); sc(SC_START);
+  int nact = 0;
+  CKT2(read_counter(T.nactive, nact));
+  outer_iters = 0;
+  if (nact > 0) {
+    k_trf_start_apply<<<g_n, HB2_BLOCK, 0, st>>>(B, T); ++launches;
+    fwd(T.W, T.Y, 0); mw(MW_RESID); red(gm, 0, 0); sc(SC_RESID0);
+    adj(T.R, T.G, 0);
+    for (int it = 0; it <= max_iter && nact > 0; ++it) {
+      ew(EW_PREP); red(gn, 0, 0); sc(SC_PREP);
+      CKT2(read_counter(T.nactive, nact));
+      if (nact == 0) break;
+      ++outer_iters;
+      // inner LSMR on [A D; sqrt(diag_h)] p_h = -[r; 0]   (trf_linear.py:209-216)
+      CKT2(cudaMemsetAsync(T.ninner, 0, sizeof(int), st));
+      adj(T.UM, T.W, 0); ew(EW_INNER_INIT); red(gn, 0, 0); sc(SC_INNER_INIT);
+      ew(EW_INNER_UPD);  // itn == 0: normalise v, h = v, hbar = x = 0, W = D v
+      int ninner = 1;
+      for (int k = 0; k < lsmr_maxiter && ninner > 0; ++k) {
+        fwd(T.W, T.Y, 1); mw(MW_INNER_U); red(gm, 0, 1);
+        ew(EW_INNER_UN); red(gn, 1, 1); sc(SC_INNER_BETA);
+        adj(T.UM, T.W, 1); ew(EW_INNER_V); red(gn, 0, 1); sc(SC_INNER_ROT);
+        ew(EW_INNER_UPD); red(gn, 0, 1); sc(SC_INNER_TEST);
+        if (k % 2 == 1 || k + 1 == lsmr_maxiter) CKT2(read_counter(T.ninner, ninner));
+      }
+      // select_step (trf_linear.py:91-144)
+      ew(EW_STEP1); red(gn, 0, 0); sc(SC_STEP1);
+      ew(EW_STEP2); red(gn, 0, 2); sc(SC_STEP2);
+      fwd(T.W, T.Y, 2);
+      ew(EW_LOAD_PH); fwd(T.W, T.Y2, 2);
+      mw(MW_DOTS3); red(gm, 0, 2); sc(SC_SAVE_M);
+      ew(EW_DOTS); red(gn, 0, 2); sc(SC_QUAD);
+      ew(EW_AG); red(gn, 0, 2); sc(SC_SAVE_AG);
+      fwd(T.W, T.Y, 2); mw(MW_DOT_YY); red(gm, 0, 2); sc(SC_AG);
+      // step, predicted cost change, new point, residual, gradient (trf_linear.py:219-243)
+      ew(EW_MKSTEP); red(gn, 0, 0); sc(SC_SAVE_SG);
+      fwd(T.W, T.Y, 0); mw(MW_DOT_YY); red(gm, 0, 0); sc(SC_CC);
+      ew(EW_XUPD);
+      fwd(T.W, T.Y, 0); mw(MW_RESID); red(gm, 0, 0); sc(SC_RESID);
+      adj(T.R, T.G, 0);
+      CKT2(cudaGetLastError());
+    }
+  }
+  ew(EW_FINAL);
+  CKT2(cudaGetLastError());
+  CKT2(cudaMemcpyAsync(out.data(), T.st, sizeof(TrfState) * nc, cudaMemcpyDeviceToHost, st));
+  CKT2(cudaStreamSynchronize(st));
+  tmp.free_all();
+  return HB2_OK;
+}
+
 // ---------------------------------------------------------------------------
 // solve + score
 // ---------------------------------------------------------------------------
@@ -734,13 +867,25 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     CK(cudaStreamSynchronize(st));
   }
   CK(cudaEventRecord(e1, st));
-  // score: reprojection of float32(x) + cosine similarity
+  std::vector<TrfState> trf;
+  int trf_outer = 0;
+  cudaEvent_t e1b;
+  CK(cudaEventCreate(&e1b));
   {
     dim3 g(cdiv(B.npad, 256), nc);
     k_x_to_f32<<<g, 256, 0, st>>>(B);
+    ++launches;
+  }
+  if (opt->fixed_iters <= 0) {  // bounded branch for candidates with the positive constraint (SLR:246-270)
+    int rc = run_trf(b, opt, trf, launches, trf_outer);
+    if (rc != HB2_OK) return rc;
+  } else trf.assign(nc, TrfState{});
+  CK(cudaEventRecord(e1b, st));
+  // score: reprojection of float32(x) + cosine similarity
+  {
     launch_fwd_data(b, MODE_SCORE);
     k_scal_score<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_score);
-    launches += 3;
+    launches += 2;
     CKL();
   }
   CK(cudaEventRecord(e2, st));
@@ -749,11 +894,11 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   CK(cudaMemcpyAsync(hs.data(), B.st, sizeof(LsmrState) * nc, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(sc.data(), b->d_score, sizeof(float) * nc, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  float ms_l = 0, ms_s = 0;
-  cudaEventElapsedTime(&ms_l, e0, e1); cudaEventElapsedTime(&ms_s, e1, e2);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  float ms_l = 0, ms_s = 0, ms_t = 0;
+  cudaEventElapsedTime(&ms_l, e0, e1); cudaEventElapsedTime(&ms_t, e1, e1b); cudaEventElapsedTime(&ms_s, e1b, e2);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e1b); cudaEventDestroy(e2);
   for (double& t : b->timing) t = 0;
-  b->timing[0] = ms_l; b->timing[1] = 0; b->timing[2] = ms_s; b->timing[3] = (double)launches; b->timing[4] = it;
+  b->timing[0] = ms_l; b->timing[1] = ms_t; b->timing[2] = ms_s; b->timing[13] = trf_outer; b->timing[3] = (double)launches; b->timing[4] = it;
   if (b->profiling) {
     for (auto& pr : b->ev_used) {
       float ms = 0;
@@ -767,13 +912,23 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   }
   for (int c = 0; c < nc; ++c) {
     hb2_result& r = res[c];
-    r.score = sc[c]; r.itn = hs[c].itn; r.istop = hs[c].istop; r.trf_nit = 0;
-    r.flags = b->cand_flags[c];
+    r.score = sc[c]; r.itn = hs[c].itn; r.istop = hs[c].istop; r.trf_nit = trf[c].status == 3 ? 0 : trf[c].nit;
+    r.flags = b->cand_flags[c] | ((trf[c].needed && trf[c].status != 3) ? HB2_FLAG_BOUNDED : 0u);
     r.n_data_rows = 0; r.n_sym_rows = b->h_msym[c];
     r.normr = (float)hs[c].normr; r.normar = hs[c].normar; r.normA = (float)hs[c].normA; r.normx = (float)hs[c].normx;
   }
   b->solved = true;
+  b->last_trf = trf;
   return HB2_OK;
+}
+
+extern "C" int hb2_batch_trf_trace(hb2_batch* b, int32_t c, double* out, int32_t max_rows) {
+  if (!b || !out || c < 0 || c >= (int)b->last_trf.size()) return fail(HB2_ERR_ARG, "bad argument or no solve yet");
+  const TrfState& S = b->last_trf[c];
+  int n = std::min(std::min(S.nit, 24), (int)max_rows);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 8; ++k) out[i * 8 + k] = S.trace[i][k];
+  return S.nit * 16 + (S.status + 1);  // nit and status packed
 }
 
 extern "C" int hb2_batch_get_x(hb2_batch* b, int32_t c, float* x_host) {

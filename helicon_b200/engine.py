@@ -112,6 +112,12 @@ class Batch:
                     fwd_data_ms=out[5], fwd_sym_ms=out[6], adj_ms=out[7], update_ms=out[8], scalar_ms=out[9],
                     fwd_data_launches=int(out[10]), adj_launches=int(out[11]), update_launches=int(out[12]))
 
+    def trf_trace(self, c):
+        out = np.zeros((24, 8), dtype=np.float64)
+        rc = _lib.check(_lib.load().hb2_batch_trf_trace(self._h, int(c), _lib.ptr(out), 24))
+        nit, status = rc // 16, rc % 16 - 1
+        return out[: min(nit, 24)], nit, status
+
     def x(self, c):
         out = np.empty(self.n, dtype=np.float32)
         _lib.check(_lib.load().hb2_batch_get_x(self._h, int(c), _lib.ptr(out)))

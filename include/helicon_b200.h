@@ -171,6 +171,11 @@ int hb2_batch_get_x(hb2_batch* b, int32_t cand, float* x_host);
  * [10] fwd_data launches [11] adjoint launches [12] update launches, [13..15] reserved */
 int hb2_batch_timing(hb2_batch* b, double* out16);
 
+/* debug/test: per outer iteration of the bounded branch of the last solve, out[row*8 + k] =
+ * cost, g_norm, inner LSMR iterations, step kind (0 full Newton, 1 truncated Newton, 2 reflected, 3 anti-gradient),
+ * p_value, r_value, ag_value, cost_change.  Returns nit*16 + (status+1). */
+int hb2_batch_trf_trace(hb2_batch* b, int32_t cand, double* out, int32_t max_rows);
+
 /* ---- test hook: the LSMR scalar recurrences run on the HOST --------------- */
 /* Same code as the device path (compiled __host__ __device__).  state64 is an
  * opaque 64-double scratch the caller keeps between calls.

@@ -739,3 +739,145 @@ def lsmr_mixed(A, b, atol=1e-4, btol=1e-4, conlim=1e8, maxiter=1000, fixed_iters
             if istop > 0:
                 break
     return x, istop, itn, normr, normar, normA, condA, normx
+
+
+# ----------------------------------------------------------------------------
+# Bounded branch restated (scipy/optimize/_lsq/trf_linear.py:147-249 +
+# common.py), float64, with a per-iteration trace; checked against the real
+# scipy call in tests/test_oracle_golden.py.  Used to localise differences of
+# the CUDA state machine (hb2_trf.cuh).
+# ----------------------------------------------------------------------------
+def trf_linear_restated(A, b, x_lsq, lb, ub, tol=1e-2, max_iter=200, lsmr_maxiter=1000, trace=None):
+    from scipy.sparse.linalg import lsmr, LinearOperator
+
+    EPS = np.finfo(float).eps
+    A = A.tocsr()
+    m, n = A.shape
+    lbv, ubv = np.full(n, float(lb)), np.full(n, float(ub))
+
+    def stb(x, s):
+        steps = np.full(n, np.inf)
+        nz = s != 0
+        with np.errstate(over="ignore"):
+            steps[nz] = np.maximum((lbv - x)[nz] / s[nz], (ubv - x)[nz] / s[nz])
+        mn = steps.min()
+        return mn, (steps == mn) * np.sign(s).astype(int)
+
+    def minq(a, bq, lo, hi, c=0.0):
+        t = [lo, hi]
+        if a != 0:
+            ext = -0.5 * bq / a
+            if lo < ext < hi:
+                t.append(ext)
+        t = np.asarray(t)
+        y = t * (a * t + bq) + c
+        i = int(np.argmin(y))
+        return t[i], y[i]
+
+    d2 = ubv - lbv
+    if np.all((x_lsq >= lbv) & (x_lsq <= ubv)):
+        return x_lsq.copy(), 0, 3
+    t = np.remainder(x_lsq - lbv, 2 * d2)
+    x = lbv + np.minimum(t, 2 * d2 - t)
+    ld, ud = x - lbv, ubv - x
+    lth, uth = 0.1 * np.maximum(1, np.abs(lbv)), 0.1 * np.maximum(1, np.abs(ubv))
+    la, ua = ld <= np.minimum(ud, lth), ud <= np.minimum(ld, uth)
+    x = x.copy()
+    x[la] = lbv[la] + lth[la]
+    x[ua] = ubv[ua] - uth[ua]
+    bad = (x < lbv) | (x > ubv)
+    x[bad] = 0.5 * (lbv[bad] + ubv[bad])
+    r = A.dot(x) - b
+    g = A.T.dot(r)
+    cost = 0.5 * np.dot(r, r)
+    status = None
+    it = -1
+    for it in range(max_iter):
+        v, dv = np.ones(n), np.zeros(n)
+        mk = g < 0
+        v[mk], dv[mk] = ubv[mk] - x[mk], -1
+        mk = g > 0
+        v[mk], dv[mk] = x[mk] - lbv[mk], 1
+        g_norm = np.max(np.abs(g * v))
+        if g_norm < tol:
+            status = 1
+        if status is not None:
+            break
+        diag_h = g * dv
+        dr = diag_h**0.5
+        d = v**0.5
+        g_h = d * g
+        eta = 1e-2 * min(0.5, g_norm)
+        ltol = max(EPS, min(0.1, eta * g_norm))
+        op = LinearOperator((m + n, n), matvec=lambda z: np.hstack((A.dot(np.ravel(z) * d), dr * np.ravel(z))),
+                            rmatvec=lambda z: d * A.T.dot(z[:m]) + dr * z[m:], dtype=float)
+        sol = lsmr(op, np.hstack((r, np.zeros(n))), maxiter=lsmr_maxiter, atol=ltol, btol=ltol)
+        p_h = -sol[0]
+        p = d * p_h
+        p_dot_g = np.dot(p, g)
+        if p_dot_g > 0:
+            status = -1
+        theta = 1 - min(0.005, g_norm)
+        Ah = lambda z: A.dot(z * d)
+        kind = "full"
+        if np.all((x + p >= lbv) & (x + p <= ubv)):
+            step = p
+            pv = rv = agv = np.nan
+        else:
+            p_stride, hits = stb(x, p)
+            r_h = p_h.copy()
+            r_h[hits.astype(bool)] *= -1
+            rr = d * r_h
+            p = p * p_stride
+            p_h = p_h * p_stride
+            xb = x + p
+            rsu, _ = stb(xb, rr)
+            rsl = (1 - theta) * rsu
+            rsu *= theta
+            if rsu > 0:
+                v1, u1 = Ah(r_h), Ah(p_h)
+                a = 0.5 * (np.dot(v1, v1) + np.dot(r_h * diag_h, r_h))
+                bq = np.dot(g_h, r_h) + np.dot(u1, v1) + np.dot(p_h * diag_h, r_h)
+                c = 0.5 * np.dot(u1, u1) + np.dot(g_h, p_h) + 0.5 * np.dot(p_h * diag_h, p_h)
+                rs, rv = minq(a, bq, rsl, rsu, c)
+                r_h = p_h + r_h * rs
+                rr = d * r_h
+            else:
+                rv = np.inf
+            p_h = p_h * theta
+            p = p * theta
+            u1 = Ah(p_h)
+            pv = 0.5 * (np.dot(u1, u1) + np.dot(p_h * diag_h, p_h)) + np.dot(p_h, g_h)
+            ag_h = -g_h
+            ag = d * ag_h
+            agu, _ = stb(x, ag)
+            agu *= theta
+            v2 = Ah(ag_h)
+            a = 0.5 * (np.dot(v2, v2) + np.dot(ag_h * diag_h, ag_h))
+            bq = np.dot(g_h, ag_h)
+            ags, agv = minq(a, bq, 0, agu)
+            ag = ag * ags
+            if pv < rv and pv < agv:
+                step, kind = p, "p"
+            elif rv < pv and rv < agv:
+                step, kind = rr, "r"
+            else:
+                step, kind = ag, "ag"
+        Js = A.dot(step)
+        cost_change = -(0.5 * np.dot(Js, Js) + np.dot(step, g))
+        if cost_change >= 0:
+            xn = x + step
+            xn[xn <= lbv] = np.nextafter(lbv, ubv)[xn <= lbv]
+            xn[xn >= ubv] = np.nextafter(ubv, lbv)[xn >= ubv]
+            x = xn
+        if trace is not None:
+            trace.append(dict(it=it, cost=cost, g_norm=g_norm, inner_itn=sol[2], kind=kind, p_value=pv, r_value=rv,
+                              ag_value=agv, cost_change=cost_change, p_dot_g=p_dot_g, ltol=ltol))
+        r = A.dot(x) - b
+        g = A.T.dot(r)
+        if cost_change < tol * cost:
+            status = 2
+        cost = 0.5 * np.dot(r, r)
+    if status is None:
+        status = 0
+    return x, it + 1, status

@@ -232,3 +232,73 @@ def test_reference_test_shapes(solver):
     with pytest.raises(NotImplementedError):
         solver.lsq_reconstruct(image, 1.0, 30, 2, tilt_degree=5, reconstruct_diameter_3d_pixel=8,
                                reconstruct_length_3d_pixel=8)
+
+
+def _oracle_bounded_spread(img, kw, n_perm=4):
+    """Oracle bounded solve + the same solve with the equations permuted: the reference's own
+    reproducibility band (float32 LSMR noise is amplified by the data-dependent TRF decisions)."""
+    from scipy.optimize import lsq_linear
+
+    (rec_o, _, _), score_o, det = O.lsq_reconstruct(img, return_details=True, **kw)
+    A = vstack((det["A_data"], det["A_hsym"])).tocsr()
+    b = np.concatenate((det["b_data"], np.zeros(det["A_hsym"].shape[0], np.float32)))
+    ub = float(det["b_data"].max())
+    x0 = det["res"].x
+    sc = lambda x: float(O.cosine_similarity(det["A_data"].dot(x.astype(np.float32)), det["b_data"]))
+    nits, dsc, dx = [det["res"].nit], [0.0], [0.0]
+    for seed in range(n_perm):
+        p = np.random.default_rng(seed).permutation(A.shape[0])
+        r2 = lsq_linear(A[p].tocsr(), b[p], bounds=(0.0, ub), tol=1e-2, max_iter=200, lsmr_maxiter=1000, lsmr_tol="auto")
+        nits.append(r2.nit); dsc.append(abs(sc(r2.x) - sc(x0))); dx.append(float(np.linalg.norm(r2.x - x0) / np.linalg.norm(x0)))
+    return rec_o, float(score_o), nits, max(dsc), max(dx)
+
+
+BOUNDED_CASES = {
+    "golden_48_t35": ("solve_nn_pos_48_t35", None),
+    "golden_32": ("solve_nn_pos_32", None),
+    "fresh_40": (None, dict(N=40, L3=4, twist=-2.37, rise_px=1.31, so=4, seed=11)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BOUNDED_CASES))
+def test_bounded_solve_within_reference_reproducibility_band(solver, case):
+    """positive constraint -> scipy's bounded TRF branch (float64 outer iterations started from the float32 LSMR
+    iterate).  The reference does NOT reproduce itself to 1e-5/1e-4 on this path: permuting its equations moves the
+    score by 5e-5..2e-2 and x by 1e-3..3e-1 on these cases (the termination test and the 3-way step choice are
+    data-dependent).  The CUDA path must land inside that band (x2), respect the bounds, and take a number of outer
+    iterations the reference also takes."""
+    gname, spec = BOUNDED_CASES[case]
+    if gname:
+        d = load(gname)
+        apix, twist, rise, csym, pc, so, L3 = d["args"]
+        img = d["image"]; N = img.shape[0]
+        kw = dict(scale2d_to_3d=1.0, twist_degree=float(twist), rise_pixel=float(rise / apix), csym=int(csym),
+                  positive_constraint=int(pc), reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N,
+                  reconstruct_diameter_3d_pixel=N, reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so),
+                  interpolation="nn")
+    else:
+        rng = np.random.default_rng(spec["seed"]); N = spec["N"]
+        yy, xx = np.mgrid[0:N, 0:N]
+        img = np.zeros((N, N), np.float32)
+        for _ in range(25):
+            cy, cx = rng.uniform(0.3 * N, 0.7 * N), rng.uniform(0, N)
+            img += np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 5.0).astype(np.float32)
+        kw = dict(scale2d_to_3d=1.0, twist_degree=spec["twist"], rise_pixel=spec["rise_px"], csym=1, positive_constraint=1,
+                  reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N,
+                  reconstruct_length_3d_pixel=spec["L3"], sym_oversample=spec["so"], interpolation="nn")
+    (rec, _, _), score, info = solver.lsq_reconstruct(img, return_info=True, **kw)
+    rec_o, score_o, nits, band_s, band_x = _oracle_bounded_spread(img, kw)
+    if gname:
+        assert abs(score_o - float(load(gname)["score"])) < 1e-6  # the oracle IS the reference here
+    r = info["res"]
+    rel = float(np.linalg.norm(rec - rec_o) / np.linalg.norm(rec_o))
+    dscore = abs(float(score) - score_o)
+    print(f"{case}: gpu lsmr itn={r['itn']} trf_nit={r['trf_nit']} flags={r['flags']} score={float(score):.7f} "
+          f"oracle={score_o:.7f} |dscore|={dscore:.2e} (band {band_s:.2e}) rel-L2(x)={rel:.2e} (band {band_x:.2e}) "
+          f"oracle nits={nits}")
+    assert r["flags"] & 4 and r["trf_nit"] > 0
+    assert rec.min() >= 0.0 and rec.max() <= float(img.max()) + 1e-6  # bounds respected
+    tie = bool(r["flags"] & 3)
+    assert dscore <= max(1e-5, 2 * band_s) * (5 if tie else 1)
+    assert rel <= max(2e-3, 2 * band_x) * (5 if tie else 1)
+    assert min(nits) - 1 <= r["trf_nit"] <= max(nits) + 1
