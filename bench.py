@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--positive", type=int, default=0,
                     help="positive_constraint passed to the solver (0 = unbounded LSMR path; -1 = reference default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
+    ap.add_argument("--e2e-batches", type=int, default=3, help="batches per search_grid() call of the e2e measurement")
     ap.add_argument("--cpu-iters", type=int, default=60)
     args = ap.parse_args()
 
@@ -275,20 +277,27 @@ def main():
         dist.all_gather(out, t)
         return torch.cat(out)
 
-    def run_step(step, profile=False):
-        sel, specs = specs_for(step)
-        batch = Batch(prob, g["L3"], specs)
-        res = batch.solve(profile=int(profile))
-        tm = batch.timing()
-        md = [batch.rows_padded(c)[0] for c in range(0, batch.nc, max(1, batch.nc // 8))]
-        batch.close()
-        allsc = gather_scores(res["score"].astype(np.float32))
-        top = torch.topk(allsc, min(10, allsc.numel()))
-        return res, tm, float(np.mean(md)), top
+    from helicon_b200.grid import BatchPipeline
+
+    pipe = BatchPipeline(device=local_rank, pipelined=not args.no_pipeline)
+
+    def run_steps(steps, profile=False):
+        """Steps run back to back; the host planning + GPU setup of step s+1 (worker thread, second stream) overlaps
+        the solve of step s.  Everything -- planning, map/row builds, solve, score, NCCL gather -- is inside."""
+        out = []
+        sels = [specs_for(s) for s in steps]
+        for i, batch in pipe.run(prob, g["L3"], [sp for _, sp in sels]):
+            res = batch.solve(profile=int(profile))
+            tm = batch.timing()
+            md = [batch.rows_padded(c)[0] for c in range(0, batch.nc, max(1, batch.nc // 8))]
+            batch.close()
+            allsc = gather_scores(res["score"].astype(np.float32))
+            top = torch.topk(allsc, min(10, allsc.numel()))
+            out.append((res, tm, float(np.mean(md)), top))
+        return out
 
     # ---- kernel-path timing: image resident, candidates -> scores -------------
-    for s in range(args.warmup):
-        run_step(s)
+    run_steps(range(args.warmup))
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -297,8 +306,7 @@ def main():
     launches, itn_sum, ncand = 0, 0, 0
     fwd_ms, fwd_launches, fwd_bytes = 0.0, 0, 0.0
     adj_ms, upd_ms, sym_ms, scal_ms, lsmr_ms = 0.0, 0.0, 0.0, 0.0, 0.0
-    for s in range(args.warmup, args.warmup + args.steps):
-        res, tm, md_mean, top = run_step(s, profile=True)
+    for res, tm, md_mean, top in run_steps(range(args.warmup, args.warmup + args.steps), profile=True):
         launches += tm["launches"]
         itn_sum += int(res["itn"].sum()); ncand += len(res)
         fwd_ms += tm["fwd_data_ms"]; fwd_launches += tm["fwd_data_launches"]
@@ -307,6 +315,7 @@ def main():
         # algorithmic bytes of the forward projector: read v (4n) + read/write u (8 m_data) per
         # candidate-iteration, summed over the iterations each candidate was active
         fwd_bytes += float(res["itn"].sum()) * (4.0 * n3 + 8.0 * md_mean)
+    torch.cuda.synchronize()  # the batches run on the library's own streams
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -317,18 +326,21 @@ def main():
     t_ms = float(tt.item())
     total_cands = ncand * world
     value = total_cands / (t_ms / 1e3)
+    pipe.close()
 
     # ---- end-to-end through the public API: host image in, host scores out ----
     e2e_vals = []
     e2e_bytes_in = img.nbytes
     per_rank = args.batch
+    n_tw = max(1, per_rank // N_RISE) * args.e2e_batches  # twists per search_grid call and rank
+    launches_e2e = 0
     for s in range(2):
-        bi = ((args.warmup + args.steps + s) * world + rank) * per_rank
-        tw_idx = [(bi // N_RISE + q) % N_TWIST for q in range(max(1, per_rank // N_RISE))]
+        bi = ((args.warmup + args.steps) * world + (2 * rank + s) * args.e2e_batches) * per_rank
+        tw_idx = [(bi // N_RISE + q) % N_TWIST for q in range(n_tw)]
         barrier()
         t0 = time.perf_counter()
         out = search_grid(np.array(img, copy=True), APIX, TWISTS[tw_idx], RISES, positive_constraint=args.positive,
-                          device=local_rank, stream=stream, batch_candidates=per_rank)
+                          device=local_rank, stream=stream, batch_candidates=per_rank, pipelined=not args.no_pipeline)
         allsc = gather_scores(np.nan_to_num(out["scores"].ravel().astype(np.float32), nan=-1.0))
         best = float(allsc.max().item())  # device->host read of the step's result
         barrier()
@@ -338,6 +350,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if s > 0:
             e2e_vals.append(out["n_candidates"] * world / float(tt.item()))
+            launches_e2e = out["launches"]
     e2e_val = float(np.mean(e2e_vals))
     d2h = int(out["scores"].size * 4 + out["itn"].size * 4)
 
@@ -359,12 +372,15 @@ def main():
         steps=args.steps, warmup=args.warmup, ms_per_step=t_ms / args.steps, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="f32 (u,v,h) / f64 (x,hbar), as scipy executes LSMR", data="synthetic",
         config=dict(workload=WORKLOAD, step=f"{args.batch} consecutive grid candidates per GPU", L3=g["L3"],
+                    pipelined=not args.no_pipeline,
                     unknowns_per_candidate=n3, positive_constraint=args.positive,
                     cache="inputs of every step are new candidates; per-step working set >> L2 (126 MB)",
                     mean_lsmr_iterations=itn_sum / max(1, ncand)),
         clocks=clocks, gpu_launches=int(launches),
         e2e=dict(value=e2e_val, unit="candidates/s", h2d_bytes_per_step=int(e2e_bytes_in), d2h_bytes_per_step=d2h,
-                 note="search_grid(): host image -> Problem upload, host planning, solve, scores copied back"),
+                 candidates_per_call=int(out["n_candidates"]),
+                 note="search_grid(): host image -> Problem upload, host planning, solve, scores copied back; bytes are per "
+                      "search_grid() call"),
         roofline=dict(bound="hbm", kernel="k_fwd_data (forward projector u <- A v - alpha u)", achieved=achieved,
                       peak=peak, unit="GB/s", frac=achieved / peak if peak else None, traffic=None,
                       peak_source=peak_src,

@@ -82,7 +82,7 @@ EXPORTS = [
     "hb2_problem_ndisk", "hb2_problem_rank_table", "hb2_batch_begin", "hb2_batch_ray_valid", "hb2_batch_angle_map",
     "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_rows_padded", "hb2_batch_rhs",
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
-    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace",
+    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim",
 ]
 
 _lib = None
@@ -104,6 +104,9 @@ def load():
     lib.hb2_last_error.restype = C.c_char_p
     lib.hb2_build_info.restype = C.c_char_p
     lib.hb2_device_count.restype = C.c_int
+    lib.hb2_stream_create.argtypes = [C.c_int, P(vp)]
+    lib.hb2_stream_destroy.argtypes = [C.c_int, vp]
+    lib.hb2_device_trim.argtypes = [C.c_int]
     lib.hb2_problem_create.argtypes = [P(vp), vp, P(Geometry), C.c_int, vp]
     lib.hb2_problem_destroy.argtypes = [vp]
     lib.hb2_problem_destroy.restype = None

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -46,17 +47,24 @@ struct hb2_problem {
   int* d_rank_data = nullptr;      // [D2*D2]
   int* d_rank_sym = nullptr;       // [D3*D3]
   short2* d_yx_data = nullptr;     // [ndisk] (row y, column x) on the data grid
-  short2* d_yx_sym = nullptr;      // [ndisk] on the symmetry grid
-  std::vector<int> h_rank_data;
+  short2* d_yx_sym = nullptr;      // [ndisk] on the symmetry grid, REFERENCE voxel order (row enumeration of the symmetry rows)
+  std::vector<int> h_rank_data;    // reference disk rank (C-order np.nonzero) on the data grid, for exports
+  std::vector<int> int2ref, ref2int;  // internal (tile-major) disk rank <-> reference rank
 };
 
-struct DevPool {  // owns device allocations of a batch
+// Device allocations of a batch come from the stream-ordered allocator (cudaMallocAsync on the batch's stream) with
+// the pool's release threshold lifted in hb2_problem_create: successive batches of a grid search reuse the same
+// physical memory without cudaMalloc/cudaFree round trips, and freeing never synchronises the device, so the setup
+// of the next batch (another stream, another host thread) overlaps the solve of the current one.
+struct DevPool {
   std::vector<void*> ptrs;
   size_t bytes = 0;
+  cudaStream_t stream = nullptr;
   template <typename T>
   cudaError_t alloc(T** p, size_t count, bool zero, cudaStream_t st) {
     size_t nb = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)p, nb);
+    stream = st;
+    cudaError_t e = cudaMallocAsync((void**)p, nb, st);
     if (e != cudaSuccess) return e;
     ptrs.push_back(*p);
     bytes += nb;
@@ -65,11 +73,11 @@ struct DevPool {  // owns device allocations of a batch
   }
   void release(void* p) {
     for (auto& q : ptrs)
-      if (q == p) { cudaFree(q); q = nullptr; }
+      if (q == p) { cudaFreeAsync(q, stream); q = nullptr; }
   }
   void free_all() {
     for (void* p : ptrs)
-      if (p) cudaFree(p);
+      if (p) cudaFreeAsync(p, stream);
     ptrs.clear();
   }
 };
@@ -118,6 +126,32 @@ extern "C" int hb2_device_count(void) {
 }
 extern "C" const char* hb2_build_info(void) { return "helicon_b200 sm_100a " __DATE__ " " __TIME__; }
 
+extern "C" int hb2_stream_create(int device, void** out) {
+  if (!out) return fail(HB2_ERR_ARG, "null argument");
+  if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
+  CK(cudaSetDevice(device));
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *out = (void*)st;
+  return HB2_OK;
+}
+extern "C" int hb2_stream_destroy(int device, void* stream) {
+  if (!stream) return HB2_OK;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  CK(cudaStreamDestroy((cudaStream_t)stream));
+  return HB2_OK;
+}
+extern "C" int hb2_device_trim(int device) {
+  if (hb2_device_count() <= 0) return HB2_OK;
+  CK(cudaSetDevice(device));
+  CK(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, device));
+  CK(cudaMemPoolTrimTo(pool, 0));
+  return HB2_OK;
+}
+
 // ---------------------------------------------------------------------------
 // problem
 // ---------------------------------------------------------------------------
@@ -138,6 +172,28 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
     }
 }
 
+// Internal voxel order: the disk is cut into TH x TW tiles (relative to the mask's bounding box) and voxels are
+// numbered tile by tile, row-major inside a tile.  256 consecutive internal ranks (one adjoint CTA) then cover a
+// compact 2-D patch, whose rays form a short contiguous range in every view -- the rows a CTA gathers stay in L1
+// (profiles/r1: with row-major ranks every CTA touched (1 + 256|sin|) rows per view).  Reference order is kept for
+// everything exported and for the enumeration order of the symmetry rows.
+static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref) {
+  static int TH = -1, TW = -1;
+  if (TH < 0) {
+    const char* eh = getenv("HB2_TILE_H"); const char* ew = getenv("HB2_TILE_W");
+    TH = eh ? std::max(1, atoi(eh)) : 8; TW = ew ? std::max(1, atoi(ew)) : 32;
+  }
+  int ymin = 1 << 30, xmin = 1 << 30;
+  for (const short2& q : yx_ref) { ymin = std::min<int>(ymin, q.x); xmin = std::min<int>(xmin, q.y); }
+  int2ref.resize(yx_ref.size());
+  for (size_t i = 0; i < yx_ref.size(); ++i) int2ref[i] = (int)i;
+  auto key = [&](int r) {
+    const int y = yx_ref[r].x - ymin, x = yx_ref[r].y - xmin;
+    return std::make_pair(std::make_pair(y / TH, x / TW), r);  // reference rank is row-major already
+  };
+  std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) { return key(a) < key(b); });
+}
+
 extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const hb2_geometry* g, int device, void* stream) {
   if (!out || !image || !g) return fail(HB2_ERR_ARG, "null argument");
   if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
@@ -147,6 +203,12 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   if (g->D2 / 2 > g->ny / 2 + 0 && (g->D2 > g->ny)) return fail(HB2_ERR_ARG, "D2 larger than the image");
   if (g->L2 > g->nx) return fail(HB2_ERR_ARG, "L2 larger than the image");
   CK(cudaSetDevice(device));
+  {
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;  // keep freed blocks cached for the next batch
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   cudaStream_t st = (cudaStream_t)stream;
   auto* P = new hb2_problem();
   P->device = device;
@@ -163,6 +225,21 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   }
   P->ndisk = (int)yd.size();
   P->h_rank_data = rd;
+  {
+    std::vector<int> i2r_sym;
+    tile_order(yd, P->int2ref);
+    tile_order(ys, i2r_sym);
+    if (i2r_sym != P->int2ref) {
+      delete P;
+      return fail(HB2_ERR_GEOMETRY, "the cylinder mask is not the same voxel set on the 2-D (D2) and 3-D (D3) grids");
+    }
+    P->ref2int.resize(P->ndisk);
+    for (int i = 0; i < P->ndisk; ++i) P->ref2int[P->int2ref[i]] = i;
+  }
+  std::vector<short2> yd_int(yd.size());
+  for (int i = 0; i < P->ndisk; ++i) yd_int[i] = yd[P->int2ref[i]];
+  for (int& r : rd) if (r >= 0) r = P->ref2int[r];
+  for (int& r : rs) if (r >= 0) r = P->ref2int[r];
   // crop: SLR:1706-1708
   std::vector<float> pix((size_t)g->D2 * g->L2);
   for (int j = 0; j < g->D2; ++j)
@@ -181,7 +258,7 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   CK(cudaMemcpyAsync(P->d_pix, pix.data(), pix.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_rank_data, rd.data(), rd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_rank_sym, rs.data(), rs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(P->d_yx_data, yd.data(), yd.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_yx_data, yd_int.data(), yd_int.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_yx_sym, ys.data(), ys.size() * sizeof(short2), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));  // host vectors go out of scope
   *out = P;
@@ -267,12 +344,12 @@ extern "C" int hb2_batch_angle_map(hb2_batch* b, int32_t angle, int32_t* out) {
     std::vector<uint16_t> t(n);
     CK(cudaMemcpyAsync(t.data(), (uint16_t*)b->d_fmap + n * angle, n * 2, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFu ? -1 : (int)t[i];
+    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFu ? -1 : b->P->int2ref[t[i]];
   } else {
     std::vector<uint32_t> t(n);
     CK(cudaMemcpyAsync(t.data(), (uint32_t*)b->d_fmap + n * angle, n * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFFFFFu ? -1 : (int)t[i];
+    for (size_t i = 0; i < n; ++i) out[i] = t[i] == 0xFFFFFFFFu ? -1 : b->P->int2ref[t[i]];
   }
   return HB2_OK;
 }
@@ -372,9 +449,10 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKC(b->pool.alloc(&d_kmax, 1, true, st));
     CKC(b->pool.alloc(&d_h1, B.nA, true, st));
     CKC(b->pool.alloc(&d_h2, B.nA, true, st));
+    B.apitch = (B.ndisk + 255) / 256 * 256;
     long long na = (long long)B.nA * B.ndisk;
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
     CKL();
     int K = 0;
     CKC(cudaMemcpyAsync(&K, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -382,15 +460,16 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     if (K < 1) K = 1;
     if (K > 64) return fail(HB2_ERR_CAPACITY, "more than 64 samples of one view land in one voxel (scale2d_to_3d too small)");
     B.K = K;
-    CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.ndisk, false, st));
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
+    CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.apitch, false, st));
+    CKC(cudaMemsetAsync(b->d_amap, 0xFF, (size_t)B.nA * K * B.apitch * sizeof(uint16_t), st));
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
     CKL();
     // consistency: every hit of the forward map must appear in the adjoint map
     long long ns = (long long)B.nA * D2 * D2;
     if (b->idx16) k_count_hits<uint16_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint16_t*)b->d_fmap, d_h1);
     else k_count_hits<uint32_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint32_t*)b->d_fmap, d_h1);
-    k_count_amap<<<cdiv((long long)B.nA * K * B.ndisk, 256), 256, 0, st>>>(B.nA, K, B.ndisk, b->d_amap, d_h2);
+    k_count_amap<<<cdiv((long long)B.nA * K * B.apitch, 256), 256, 0, st>>>(B.nA, K, B.apitch, b->d_amap, d_h2);
     CKL();
     std::vector<unsigned long long> h1(B.nA), h2(B.nA);
     CKC(cudaMemcpyAsync(h1.data(), d_h1, 8 * B.nA, cudaMemcpyDeviceToHost, st));
@@ -425,8 +504,15 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   int max_symcap = 0;
   for (int c = 0; c < nc; ++c) max_symcap = std::max<long long>(max_symcap, b->h_symcap[c]);
   B.part_us_per_cand = std::max(1u, cdiv(max_symcap, HB2_BLOCK * 4));
-  const int adj_zc = B.L3P >= 16 ? 16 : B.L3P;
-  B.part_v_per_cand = cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3P, adj_zc);
+  {
+    long long max_md = 0;
+    for (int c = 0; c < nc; ++c) max_md = std::max<long long>(max_md, b->h_mdata[c]);
+    B.adj_lean = (B.MC == 1 && B.K <= 2 && max_md + (long long)B.ZMP * B.D2 < (1ll << 32) &&
+                  true) ? 1 : 0;
+    B.adj_nqt = std::min(4, B.L3P / 4);
+    B.adj_nzch = cdiv(B.L3P, 4 * B.adj_nqt);
+    B.part_v_per_cand = B.adj_lean ? cdiv(B.ndisk, HB2_BLOCK) * B.adj_nzch : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
+  }
   B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
   CKC(b->pool.alloc(&B.part_us, (size_t)nc * B.part_us_per_cand, true, st));
@@ -552,9 +638,10 @@ extern "C" int hb2_batch_sym_rows(hb2_batch* b, int32_t c, int32_t* n_rows, int3
     CK(cudaMemcpyAsync(b_host, b->d_sym_b + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     const int L3P = b->B.L3P, nd = b->B.ndisk;
-    for (int r = 0; r < m; ++r) {  // internal p*L3P+z -> reference z*ndisk+p
-      a_host[r] = (a_host[r] % L3P) * nd + a_host[r] / L3P;
-      b_host[r] = (b_host[r] % L3P) * nd + b_host[r] / L3P;
+    const std::vector<int>& i2r = b->P->int2ref;
+    for (int r = 0; r < m; ++r) {  // internal p*L3P+z -> reference z*ndisk+rank
+      a_host[r] = (a_host[r] % L3P) * nd + i2r[a_host[r] / L3P];
+      b_host[r] = (b_host[r] % L3P) * nd + i2r[b_host[r] / L3P];
     }
   }
   return HB2_OK;
@@ -619,17 +706,17 @@ static void launch_adj(hb2_batch* b, int mode) {
   const BD& B = b->B;
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
-#define ADJ(Z, K, M) k_adj<Z, K, M><<<g, HB2_BLOCK, 0, st>>>(B, mode)
-#define ADJZ(K, M)                                                                              \
-  do {                                                                                          \
-    if (B.L3P == 4) ADJ(4, K, M); else if (B.L3P == 8) ADJ(8, K, M); else if (B.L3P == 12) ADJ(12, K, M); else ADJ(16, K, M); \
-  } while (0)
-  if (B.MC == 1) {
-    if (B.K == 1) ADJZ(1, 1); else if (B.K == 2) ADJZ(2, 1); else ADJZ(0, 1);
-  } else {
-    ADJZ(0, 0);
+  if (B.adj_lean) {
+#define ADJL(Q, K) k_adj_lean<Q, K><<<g, HB2_BLOCK, 0, st>>>(B, mode)
+#define ADJLQ(K) do { if (B.adj_nqt == 1) ADJL(1, K); else if (B.adj_nqt == 2) ADJL(2, K); else if (B.adj_nqt == 3) ADJL(3, K); else ADJL(4, K); } while (0)
+    if (B.K == 1) ADJLQ(1); else ADJLQ(2);
+#undef ADJLQ
+#undef ADJL
+    return;
   }
-#undef ADJZ
+#define ADJ(K, M) k_adj<K, M><<<g, HB2_BLOCK, 0, st>>>(B, mode)
+  if (B.MC == 1) ADJ(0, 1);
+  else ADJ(0, 0);
 #undef ADJ
 }
 static void launch_update(hb2_batch* b, int mode) {
@@ -647,7 +734,7 @@ extern "C" int hb2_batch_apply_forward(hb2_batch* b, int32_t c, const float* x_h
   long long m = (long long)b->h_mdata[c] + b->h_msym[c];
   std::vector<float> xi((size_t)B.npad, 0.f);  // reference order z*ndisk+p -> internal p*L3P+z
   for (int z = 0; z < B.L3; ++z)
-    for (int pp = 0; pp < B.ndisk; ++pp) xi[(size_t)pp * B.L3P + z] = x_host[(size_t)z * B.ndisk + pp];
+    for (int pp = 0; pp < B.ndisk; ++pp) xi[(size_t)pp * B.L3P + z] = x_host[(size_t)z * B.ndisk + b->P->int2ref[pp]];
   CK(cudaMemcpyAsync(B.xs + (size_t)c * B.npad, xi.data(), sizeof(float) * B.npad, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(B.u + b->h_uoff[c], 0, sizeof(float) * m, st));
   B.only_cand = c;
@@ -676,7 +763,7 @@ extern "C" int hb2_batch_apply_adjoint(hb2_batch* b, int32_t c, const float* y_h
   CK(cudaMemcpyAsync(xi.data(), B.xs + (size_t)c * B.npad, sizeof(float) * B.npad, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int z = 0; z < B.L3; ++z)
-    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + pp] = xi[(size_t)pp * B.L3P + z];
+    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + b->P->int2ref[pp]] = xi[(size_t)pp * B.L3P + z];
   b->solved = false;
   return HB2_OK;
 }
@@ -732,8 +819,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   const int lsmr_maxiter = opt->max_iter > 0 ? opt->max_iter : 1000;
   const int max_iter = opt->trf_max_iter > 0 ? opt->trf_max_iter : 200;
   const dim3 g_n(gn, nc), g_m(gm, nc), g_sym(std::max(1, B.part_us_per_cand), nc);
-  const int adj_zc = B.L3P >= 16 ? 16 : B.L3P;
-  const dim3 g_adj(cdiv(B.ndisk, HB2_BLOCK) * cdiv(B.L3P, adj_zc), nc);
+  const dim3 g_adj(cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK), nc);
   const unsigned g_fwd = (unsigned)b->nviews * ((B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS);
   const unsigned g_sc = cdiv(nc, 128);
   auto ew = [&](int op) { k_trf_ew<<<g_n, HB2_BLOCK, 0, st>>>(B, T, op); ++launches; };
@@ -747,10 +833,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     launches += 2;
   };
   auto adj = [&](const double* rows, double* dst, int gate) {
-    if (adj_zc == 4) k_adj64<4><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
-    else if (adj_zc == 8) k_adj64<8><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
-    else if (adj_zc == 12) k_adj64<12><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
-    else k_adj64<16><<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    k_adj64<<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
     ++launches;
   };
   auto read_counter = [&](int* dptr, int& v) -> cudaError_t {
@@ -939,7 +1022,7 @@ extern "C" int hb2_batch_get_x(hb2_batch* b, int32_t c, float* x_host) {
   CK(cudaMemcpyAsync(xi.data(), B.xs + (size_t)c * B.npad, sizeof(float) * B.npad, cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   for (int z = 0; z < B.L3; ++z)
-    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + pp] = xi[(size_t)pp * B.L3P + z];
+    for (int pp = 0; pp < B.ndisk; ++pp) x_host[(size_t)z * B.ndisk + b->P->int2ref[pp]] = xi[(size_t)pp * B.L3P + z];
   return HB2_OK;
 }
 

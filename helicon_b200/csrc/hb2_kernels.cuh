@@ -6,6 +6,7 @@
 #define HB2_MAX_ZMC 1024   // L3*MC columns per view kept in shared memory
 #define HB2_TILE_RAYS 32   // rays per CTA of the forward projector
 #define HB2_BLOCK 256
+#define HB2_FWD_U 8      // samples in flight per lane of the forward projector
 
 enum { MODE_LSMR = 0, MODE_PLAIN = 1, MODE_SCORE = 2, MODE_INIT = 3 };
 
@@ -20,7 +21,8 @@ struct BD {
   // in-plane maps
   const void* fmap;            // [nA][D2][D2] disk rank or SENT
   const uint8_t* rayvalid;     // [nA][D2]
-  const uint16_t* amap;        // [nA][K][ndisk] ray j of the k-th sample landing in voxel p, or 0xFFFF
+  const uint16_t* amap;        // [nA][K][apitch] ray j of the k-th sample landing in voxel p, or 0xFFFF
+  int apitch;                  // row pitch of amap: ndisk rounded up to 256 (rows 512-byte aligned; padding = 0xFFFF)
   // views (flat over the batch)
   const int* view_cand;
   const int* view_angle;
@@ -56,6 +58,8 @@ struct BD {
   double* part_x;
   float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
   int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
+  int adj_lean;    // MC == 1, K <= 2, row offsets fit 32 bits: k_adj_lean with adj_nqt quads per thread
+  int adj_nqt, adj_nzch;
   int only_cand;   // MODE_PLAIN: restrict to one candidate (-1 all)
   int clip_pred;
 };
@@ -151,7 +155,7 @@ __global__ void k_build_fmap(int nA, int D2, double s, const double* __restrict_
 // samples (j,i) with fmap[a][j][i] == p, j-major then i (deterministic).
 // pass 0: count only (max multiplicity -> *kmax); pass 1: fill amap[a][k][p].
 template <typename IdxT>
-__global__ void k_build_amap(int nA, int D2, int ndisk, double s, int K, int pass, const double* __restrict__ cs,
+__global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, int K, int pass, const double* __restrict__ cs,
                              const short2* __restrict__ disk_yx, const IdxT* __restrict__ fmap,
                              uint16_t* __restrict__ amap, int* __restrict__ kmax) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -172,13 +176,13 @@ __global__ void k_build_amap(int nA, int D2, int ndisk, double s, int K, int pas
   for (int j = j0; j <= j1; ++j)
     for (int i = i0; i <= i1; ++i)
       if (fm[(size_t)j * D2 + i] == (IdxT)p) {
-        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * ndisk + p] = (uint16_t)j;
+        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * apitch + p] = (uint16_t)j;
         ++cnt;
       }
   if (pass == 0) {
     if (cnt > 0) atomicMax(kmax, cnt);
   } else {
-    for (int k = cnt; k < K; ++k) amap[((size_t)a * K + k) * ndisk + p] = 0xFFFFu;
+    for (int k = cnt; k < K; ++k) amap[((size_t)a * K + k) * apitch + p] = 0xFFFFu;
   }
 }
 
@@ -189,11 +193,11 @@ __global__ void k_count_hits(int nA, int D2, const IdxT* __restrict__ fmap, unsi
   if (t >= (long long)nA * D2 * D2) return;
   if (fmap[t] != Sent<IdxT>::v) atomicAdd(&hits[t / ((long long)D2 * D2)], 1ull);
 }
-__global__ void k_count_amap(int nA, int K, int ndisk, const uint16_t* __restrict__ amap,
+__global__ void k_count_amap(int nA, int K, int apitch, const uint16_t* __restrict__ amap,
                              unsigned long long* __restrict__ hits) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nA * K * ndisk) return;
-  if (amap[t] != 0xFFFFu) atomicAdd(&hits[t / ((long long)K * ndisk)], 1ull);
+  if (t >= (long long)nA * K * apitch) return;
+  if (amap[t] != 0xFFFFu) atomicAdd(&hits[t / ((long long)K * apitch)], 1ull);
 }
 
 // right-hand side in padded layout: b[view][z][mc][j] = pix[j][k] when the
@@ -461,13 +465,19 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (zq < L3P) {
         const float* __restrict__ vb = vsrc + zq;
-#pragma unroll 4
-        for (int i = sg; i < D2; i += 8) {
-          IdxT id = fj[i];
-          if (id != Sent<IdxT>::v) {
-            float4 t = ldg4(vb + (size_t)id * L3P);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-          }
+        // HB2_FWD_U map entries, then their gathers, are issued before the first add (independent loads in flight);
+        // the additions keep the sample order.
+        for (int i0 = sg; i0 < D2; i0 += 8 * HB2_FWD_U) {
+          IdxT ids[HB2_FWD_U];
+#pragma unroll
+          for (int w = 0; w < HB2_FWD_U; ++w) ids[w] = (i0 + 8 * w < D2) ? fj[i0 + 8 * w] : Sent<IdxT>::v;
+          float4 tt[HB2_FWD_U];
+#pragma unroll
+          for (int w = 0; w < HB2_FWD_U; ++w)
+            tt[w] = ids[w] != Sent<IdxT>::v ? ldg4(vb + (size_t)ids[w] * L3P) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < HB2_FWD_U; ++w)
+            if (ids[w] != Sent<IdxT>::v) { acc.x += tt[w].x; acc.y += tt[w].y; acc.z += tt[w].z; acc.w += tt[w].w; }
         }
       }
 #pragma unroll
@@ -548,19 +558,24 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_sym(BD B, int mode) {
 }
 
 // ===========================================================================
-// adjoint: voxel-driven gather.  One thread = one in-plane voxel p and ZC slices
-// (all of them when L3P <= 16); it loops over the candidate's views, reads the
-// adjoint map (the rays whose samples land in p) once per view and gathers the
-// rays' rows for all slices with 128-bit loads; then adds the symmetry rows
-// incident to each voxel.
+// adjoint: voxel-driven gather.  One thread = one in-plane voxel p and one slice
+// quad q (4 slices); the NQ = L3P/4 lanes of a voxel are adjacent, so a warp
+// covers ~32/NQ consecutive voxels of a disk row.  Per view the lanes read the
+// adjoint map (the rays whose samples land in p) and gather their 16 bytes of
+// the ray's row: neighbouring voxels map to the same or the neighbouring ray,
+// whose rows are contiguous ([view][j][z]), so one warp-wide 128-bit gather
+// touches few 128-byte lines.  Then the symmetry rows incident to each voxel.
 // MODE_LSMR : v~ <- A^T (u~*inv_beta) - beta * v        (lsmr.py:336-338)
 // MODE_INIT : v~ <- A^T (u~*inv_beta)                    (lsmr.py:251)
 // MODE_PLAIN: xs <- A^T u
 // ===========================================================================
-template <int ZC, int KT, int MCT>
+#define HB2_ADJ_VIEWS 128  // views staged in shared memory per pass
+template <int KT, int MCT>
 __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
   const int c = blockIdx.y;
   __shared__ float red[HB2_BLOCK / 32];
+  __shared__ int s_ang[HB2_ADJ_VIEWS];
+  __shared__ long long s_uoff[HB2_ADJ_VIEWS];
   const LsmrState& S = B.st[c];
   bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
                                  : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
@@ -571,78 +586,185 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
   }
   const int L3 = B.L3, L3P = B.L3P, ZMP = B.ZMP, ndisk = B.ndisk;
   const int K = KT > 0 ? KT : B.K, MC = MCT > 0 ? MCT : B.MC;
-  const int nzch = (L3P + ZC - 1) / ZC;
-  const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
-  const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * ZC;
+  const int NQ = L3P >> 2;
+  const int t = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const int p = t / NQ, q = t - p * NQ;
+  const bool live = p < ndisk;
+  const int z0 = 4 * q;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
   const float beta = S.beta;
-  float ss = 0.f;
-  if (p < ndisk) {
-    float acc[ZC];
-#pragma unroll
-    for (int zz = 0; zz < ZC; ++zz) acc[zz] = 0.f;
-    const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
-    for (int vi = 0; vi < nv; ++vi) {
-      const int view = vb + vi;
-      const int a = __ldg(B.view_angle + view);
-      const float* __restrict__ ub = B.u + __ldg(B.view_uoff + view) + z0 * MC;
-      const uint16_t* __restrict__ am = B.amap + (size_t)a * K * ndisk + p;
-#pragma unroll
-      for (int k = 0; k < (KT > 0 ? KT : K); ++k) {
-        uint16_t j = am[(size_t)k * ndisk];
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+  for (int v0 = 0; v0 < nv; v0 += HB2_ADJ_VIEWS) {
+    const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nvc; e += HB2_BLOCK) {
+      s_ang[e] = B.view_angle[vb + v0 + e];
+      s_uoff[e] = B.view_uoff[vb + v0 + e];
+    }
+    __syncthreads();
+    if (!live) continue;
+    for (int vi = 0; vi < nvc; ++vi) {
+      const float* __restrict__ ub = B.u + s_uoff[vi] + z0 * MC;
+      const uint16_t* __restrict__ am = B.amap + (size_t)s_ang[vi] * K * B.apitch + p;
+      for (int k = 0; k < K; ++k) {
+        const uint16_t j = am[(size_t)k * B.apitch];
         if (j != 0xFFFFu) {
           const float* __restrict__ uj = ub + (size_t)j * ZMP;
           if (MCT == 1) {
-#pragma unroll
-            for (int q4 = 0; q4 < ZC / 4; ++q4) {
-              if (z0 + 4 * q4 < L3P) {
-                float4 t = ldg4(uj + 4 * q4);
-                acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]);
-                acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
-                acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]);
-                acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
-              }
-            }
+            const float4 r4 = ldg4(uj);
+            acc0 = fmaf(r4.x, ib, acc0); acc1 = fmaf(r4.y, ib, acc1);
+            acc2 = fmaf(r4.z, ib, acc2); acc3 = fmaf(r4.w, ib, acc3);
           } else {
-#pragma unroll
-            for (int zz = 0; zz < ZC; ++zz)
-              if (z0 + zz < L3)
-                for (int mc = 0; mc < MC; ++mc) acc[zz] = fmaf(__ldg(uj + zz * MC + mc), ib, acc[zz]);
+            for (int mc = 0; mc < MC; ++mc) {
+              if (z0 + 0 < L3) acc0 = fmaf(__ldg(uj + 0 * MC + mc), ib, acc0);
+              if (z0 + 1 < L3) acc1 = fmaf(__ldg(uj + 1 * MC + mc), ib, acc1);
+              if (z0 + 2 < L3) acc2 = fmaf(__ldg(uj + 2 * MC + mc), ib, acc2);
+              if (z0 + 3 < L3) acc3 = fmaf(__ldg(uj + 3 * MC + mc), ib, acc3);
+            }
           }
         }
       }
     }
-    // symmetry rows incident to (p, z)
+  }
+  float ss = 0.f;
+  if (live) {
+    // symmetry rows incident to (p, z0..z0+3)
     const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1);
     const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
     const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
     float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + (size_t)p * L3P + z0;
     const int g0 = p * L3P + z0;
+    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst);
+    float vn[4] = {acc0, acc1, acc2, acc3};
+    const int nz = min(4, L3 - z0);  // real slices of this quad (padded slices stay 0)
+    int e = nz > 0 ? ptr[g0] : 0;
 #pragma unroll
-    for (int q4 = 0; q4 < ZC / 4; ++q4) {
-      if (z0 + 4 * q4 < L3P) {
-        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
-        float vn[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int zz = 4 * q4 + t;
-          float a2 = acc[zz];
-          if (z0 + zz < L3) {
-            const int g = g0 + zz;
-            const int e0 = ptr[g], e1 = ptr[g + 1];
-            for (int e = e0; e < e1; ++e) {
-              int en = ent[e];
-              float val = __ldg(us + (en & 0x7fffffff));
-              a2 = fmaf(en < 0 ? -val : val, ib, a2);
-            }
-          }
-          const float o = t == 0 ? old.x : (t == 1 ? old.y : (t == 2 ? old.z : old.w));
-          vn[t] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), a2) : a2;
-          ss += vn[t] * vn[t];
+    for (int tz = 0; tz < 4; ++tz) {
+      float a2 = vn[tz];
+      if (tz < nz) {
+        const int e1 = ptr[g0 + tz + 1];
+        for (; e < e1; ++e) {
+          const int en = ent[e];
+          const float val = __ldg(us + (en & 0x7fffffff));
+          a2 = fmaf(en < 0 ? -val : val, ib, a2);
         }
-        *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
       }
+      const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
+      vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), a2) : a2;
+      ss += vn[tz] * vn[tz];
+    }
+    *reinterpret_cast<float4*>(vdst) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+  }
+  if (mode != MODE_PLAIN) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_v[pi] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Adjoint, fast path (MC == 1, K <= 2).  One thread = one in-plane voxel p and
+// NQT slice quads (z chunk = blockIdx % nzch when L3P > 16).  Per view: one
+// 32-bit map offset from shared memory, K 16-bit map entries, and for a hit NQT
+// 128-bit loads of the ray's row.  View rows of a candidate are contiguous in u
+// (view vi starts at vi*rows_per_view), so no row-offset table is needed and
+// all offsets are 32-bit.  Addition order: views, then k, then symmetry rows.
+// (profiles/r1_summary.md: variants with (voxel, quad) lanes, with cp.async
+// staging of the map and with 4-view load batching were measured and were not
+// faster -- the kernel sits at ~50 % of the L1 wavefront rate either way.)
+// ---------------------------------------------------------------------------
+template <int NQT, int KT>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_lean(BD B, int mode) {
+  const int c = blockIdx.y;
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ unsigned s_aoff[HB2_ADJ_VIEWS];
+  const LsmrState& S = B.st[c];
+  bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
+                                 : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
+  const int nzch = B.adj_nzch;
+  const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
+  const int pi = c * B.part_v_per_cand + blockIdx.x;
+  if (!act) {
+    if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
+    return;
+  }
+  const int L3 = B.L3, L3P = B.L3P, ndisk = B.ndisk;
+  const unsigned ZMP = (unsigned)B.ZMP, rpv = (unsigned)B.rows_per_view, kstride = (unsigned)KT * (unsigned)B.apitch;
+  const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * (4 * NQT);
+  const bool live = p < ndisk;
+  const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
+  const float beta = S.beta;
+  float acc[4 * NQT];
+#pragma unroll
+  for (int i = 0; i < 4 * NQT; ++i) acc[i] = 0.f;
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+  const float* __restrict__ ucand = B.u + B.cand_uoff[c] + z0;
+  const uint16_t* __restrict__ am0 = B.amap + (live ? p : 0);
+  const uint16_t* __restrict__ am1 = am0 + B.apitch;
+  for (int v0 = 0; v0 < nv; v0 += HB2_ADJ_VIEWS) {
+    const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nvc; e += HB2_BLOCK) s_aoff[e] = (unsigned)B.view_angle[vb + v0 + e] * kstride;
+    __syncthreads();
+    if (!live) continue;
+    unsigned uo = (unsigned)v0 * rpv;
+#pragma unroll 2
+    for (int vi = 0; vi < nvc; ++vi, uo += rpv) {
+      const unsigned ao = s_aoff[vi];
+      const unsigned j0 = am0[ao];
+      unsigned j1 = 0xFFFFu;
+      if (KT == 2) j1 = am1[ao];
+      if (j0 != 0xFFFFu) {
+        const float4* __restrict__ r = reinterpret_cast<const float4*>(ucand + (uo + j0 * ZMP));
+#pragma unroll
+        for (int q4 = 0; q4 < NQT; ++q4) {
+          const float4 t = __ldg(r + q4);
+          acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
+          acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+        }
+      }
+      if (KT == 2 && j1 != 0xFFFFu) {
+        const float4* __restrict__ r = reinterpret_cast<const float4*>(ucand + (uo + j1 * ZMP));
+#pragma unroll
+        for (int q4 = 0; q4 < NQT; ++q4) {
+          const float4 t = __ldg(r + q4);
+          acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
+          acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+        }
+      }
+    }
+  }
+  float ss = 0.f;
+  if (live) {
+    const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1) + (p * L3P + z0);
+    const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
+    const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
+    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + (size_t)p * L3P + z0;
+    const int nz = min(4 * NQT, L3 - z0);  // real slices of this chunk (padded slices stay 0)
+    int e = nz > 0 ? ptr[0] : 0;
+#pragma unroll
+    for (int q4 = 0; q4 < NQT; ++q4) {
+      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
+      float vn[4];
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        const int zz = 4 * q4 + tz;
+        float a2 = acc[zz];
+        if (zz < nz) {
+          const int e1 = ptr[zz + 1];
+          for (; e < e1; ++e) {
+            const int en = ent[e];
+            const float val = __ldg(us + (en & 0x7fffffff));
+            a2 = fmaf(en < 0 ? -val : val, ib, a2);
+          }
+        }
+        const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
+        vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), a2) : a2;
+        ss += vn[tz] * vn[tz];
+      }
+      *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
     }
   }
   if (mode != MODE_PLAIN) {

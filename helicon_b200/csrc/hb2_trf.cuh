@@ -191,34 +191,39 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_sym(BD B, TD T, const doubl
     if (r < m) us[r] = __ldg(vsrc + sa[r]) - __ldg(vsrc + sb[r]);
 }
 
-template <int ZC>
+// same lane layout as k_adj: one thread = (voxel p, slice quad q)
 __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* __restrict__ rows, double* __restrict__ dst,
                                                     int inner) {
   const int c = blockIdx.y;
   const TrfState& S = T.st[c];
   if (!trf_gate(S, inner) || (inner == 1 && S.in.skip_adj)) return;
   const int L3 = B.L3, L3P = B.L3P, ZMP = B.ZMP, ndisk = B.ndisk, K = B.K, MC = B.MC;
-  const int nzch = (L3P + ZC - 1) / ZC;
-  const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
-  const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * ZC;
+  const int NQ = L3P >> 2;
+  const int t = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const int p = t / NQ, q = t - p * NQ;
   if (p >= ndisk) return;
-  double acc[ZC];
-#pragma unroll
-  for (int zz = 0; zz < ZC; ++zz) acc[zz] = 0.0;
+  const int z0 = 4 * q;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
   for (int vi = 0; vi < nv; ++vi) {
     const int view = vb + vi;
     const int a = __ldg(B.view_angle + view);
     const double* __restrict__ ub = rows + __ldg(B.view_uoff + view) + z0 * MC;
-    const uint16_t* __restrict__ am = B.amap + (size_t)a * K * ndisk + p;
+    const uint16_t* __restrict__ am = B.amap + (size_t)a * K * B.apitch + p;
     for (int k = 0; k < K; ++k) {
-      uint16_t j = am[(size_t)k * ndisk];
+      const uint16_t j = am[(size_t)k * B.apitch];
       if (j != 0xFFFFu) {
         const double* __restrict__ uj = ub + (size_t)j * ZMP;
+        if (MC == 1) {
+          const double2 r0 = __ldg(reinterpret_cast<const double2*>(uj));
+          const double2 r1 = __ldg(reinterpret_cast<const double2*>(uj) + 1);
+          acc[0] += r0.x; acc[1] += r0.y; acc[2] += r1.x; acc[3] += r1.y;
+        } else {
 #pragma unroll
-        for (int zz = 0; zz < ZC; ++zz)
-          if (z0 + zz < L3)
-            for (int mc = 0; mc < MC; ++mc) acc[zz] += __ldg(uj + zz * MC + mc);
+          for (int zz = 0; zz < 4; ++zz)
+            if (z0 + zz < L3)
+              for (int mc = 0; mc < MC; ++mc) acc[zz] += __ldg(uj + zz * MC + mc);
+        }
       }
     }
   }
@@ -227,19 +232,17 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* _
   const double* __restrict__ us = rows + B.cand_uoff[c] + B.cand_mdata[c];
   double* vdst = dst + (size_t)c * B.npad + (size_t)p * L3P + z0;
 #pragma unroll
-  for (int zz = 0; zz < ZC; ++zz) {
-    if (z0 + zz < L3P) {
-      double a2 = acc[zz];
-      if (z0 + zz < L3) {
-        const int g = p * L3P + z0 + zz;
-        for (int e = ptr[g]; e < ptr[g + 1]; ++e) {
-          int en = ent[e];
-          double val = __ldg(us + (en & 0x7fffffff));
-          a2 += en < 0 ? -val : val;
-        }
+  for (int zz = 0; zz < 4; ++zz) {
+    double a2 = acc[zz];
+    if (z0 + zz < L3) {
+      const int g = p * L3P + z0 + zz;
+      for (int e = ptr[g]; e < ptr[g + 1]; ++e) {
+        int en = ent[e];
+        double val = __ldg(us + (en & 0x7fffffff));
+        a2 += en < 0 ? -val : val;
       }
-      vdst[zz] = a2;
     }
+    vdst[zz] = a2;
   }
 }
 

@@ -22,7 +22,29 @@ def _stream_handle(stream):
         return None
     if isinstance(stream, int):
         return C.c_void_p(stream)
-    return C.c_void_p(int(stream.cuda_stream))  # torch.cuda.Stream
+    return C.c_void_p(int(stream.cuda_stream))  # torch.cuda.Stream or engine.Stream
+
+
+class Stream:
+    """A non-blocking CUDA stream owned by the library (``hb2_stream_create``)."""
+
+    def __init__(self, device=0):
+        lib = _lib.require_gpu()
+        self.device = int(device)
+        h = C.c_void_p()
+        _lib.check(lib.hb2_stream_create(self.device, C.byref(h)))
+        self.cuda_stream = int(h.value)
+
+    def close(self):
+        if getattr(self, "cuda_stream", None):
+            _lib.load().hb2_stream_destroy(self.device, C.c_void_p(self.cuda_stream))
+            self.cuda_stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Problem:
@@ -66,9 +88,11 @@ class Problem:
 class Batch:
     """Candidates (CandidateSpec) of one Problem with a common L3."""
 
-    def __init__(self, problem: Problem, L3: int, specs, need_views=True):
+    def __init__(self, problem: Problem, L3: int, specs, need_views=True, stream=None):
+        """``stream``: the stream ALL work of this batch runs on (default: the problem's)."""
         lib = _lib.require_gpu()
         self.problem = problem
+        self._stream_ref = stream  # keep the stream object alive as long as the batch
         self.L3 = int(L3)
         self.plan = BatchPlan(problem.s, problem.D2, problem.L2, self.L3, specs)
         nA = len(self.plan.angles)
@@ -78,7 +102,7 @@ class Batch:
         _lib.check(
             lib.hb2_batch_begin(
                 C.byref(self._h), problem._h, self.L3, self.plan.MC, nA, _lib.ptr(self.plan.cos_sin),
-                _lib.ptr(self.nvalid), _lib.ptr(self.tie), problem.stream,
+                _lib.ptr(self.nvalid), _lib.ptr(self.tie), problem.stream if stream is None else _stream_handle(stream),
             )
         )
         self.plan.finalize(self.nvalid)

@@ -14,8 +14,59 @@ import time
 
 import numpy as np
 
-from .engine import Batch, Problem
+from concurrent.futures import ThreadPoolExecutor
+
+from .engine import Batch, Problem, Stream
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
+
+
+class BatchPipeline:
+    """Double-buffered batch preparation.
+
+    ``for i, batch in pipe.run(prob, L3, chunks)`` yields ready ``Batch`` objects in
+    order while a worker thread plans and sets up the NEXT chunk (host planner,
+    in-plane maps, right-hand side, symmetry rows) on the other of two non-blocking
+    streams, so that it overlaps the solve of the current batch: the C calls
+    release the GIL, the GPU work of the two batches runs on different streams.
+    The caller closes each batch when it is done with it.
+    """
+
+    def __init__(self, device=0, pipelined=True):
+        self.device = int(device)
+        self.pipelined = bool(pipelined)
+        self.streams = [Stream(device), Stream(device)]
+        self._ex = ThreadPoolExecutor(max_workers=1) if pipelined else None
+
+    def run(self, prob, L3, chunks):
+        chunks = list(chunks)
+        if not chunks:
+            return
+        make = lambda i: Batch(prob, L3, chunks[i], stream=self.streams[i % 2])  # noqa: E731
+        if not self.pipelined:
+            for i in range(len(chunks)):
+                yield i, make(i)
+            return
+        fut = self._ex.submit(make, 0)
+        for i in range(len(chunks)):
+            batch = fut.result()
+            fut = self._ex.submit(make, i + 1) if i + 1 < len(chunks) else None
+            try:
+                yield i, batch
+            except GeneratorExit:
+                if fut is not None:
+                    try:
+                        fut.result().close()
+                    except Exception:
+                        pass
+                raise
+
+    def close(self):
+        if self._ex is not None:
+            self._ex.shutdown(wait=True)
+            self._ex = None
+        for st in self.streams:
+            st.close()
+        self.streams = []
 
 
 def derive_geometry(ny, nx, apix2d_orig, rise, rise_max, tube_diameter, tube_diameter_inner, tube_length,
@@ -111,7 +162,7 @@ def _bytes_per_candidate(n, md, cap):
 def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=3, tube_diameter=None,
                 tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
                 positive_constraint=-1, thresh_fraction=-1, top_k=10, device=0, stream=None, batch_candidates=None,
-                mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None):
+                mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None, pipelined=True):
     """Solve + score every candidate of the grid on one GPU.
 
     ``shard=(rank, world)`` keeps tasks ``rank::world`` of every twist-major
@@ -140,46 +191,55 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
         groups.setdefault(key, []).append(t)
     top = []
     kernel_ms = 0.0
-    for (D2, L2, D3, D3i, s, L3), tl in groups.items():
-        prob = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
-        try:
-            n3 = L3 * prob.ndisk
-            for t in tl:
-                target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * t.geom["sym_oversample"]))
-                rise_px = t.rise / t.geom["apix3d"]
-                t.spec = CandidateSpec(t.twist, rise_px, t.csym, target, target,
-                                       positive_rule(positive_constraint, rise_px, t.twist, L3))
-            md_est = int((L3 + L2) / max(min(x.spec.rise_pixel for x in tl), 1e-3) + 3) * L3 * D2
-            cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
-            bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // _bytes_per_candidate(n3, md_est, cap_est))))
-            for i0 in range(0, len(tl), bs):
-                chunk = tl[i0:i0 + bs]
-                batch = Batch(prob, L3, [x.spec for x in chunk])
-                try:
-                    res = batch.solve(clip_pred=int(thresh_fraction >= 0))
-                    tm = batch.timing()
-                    kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
-                    for c, x in enumerate(chunk):
-                        scores[x.ti] = res[c]["score"]
-                        itn[x.ti] = res[c]["itn"]
-                        flags[x.ti] = res[c]["flags"]
-                    if top_k:
-                        order = np.argsort(-res["score"], kind="stable")[:top_k]
-                        for c in order:
-                            ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
-                                       rise=chunk[c].rise, csym=chunk[c].csym)
-                            if return_x_top:
-                                ent["rec3d"] = batch.rec3d(int(c))
-                            top.append(ent)
-                        top.sort(key=lambda e: (-e["score"], e["ti"]))
-                        del top[top_k:]
-                finally:
-                    batch.close()
-                if progress:
-                    progress(i0 + len(chunk), len(tl))
-        finally:
-            prob.close()
+    launches = 0
+    pipe = BatchPipeline(device=device, pipelined=pipelined)
+    try:
+        for (D2, L2, D3, D3i, s, L3), tl in groups.items():
+            prob = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
+            try:
+                n3 = L3 * prob.ndisk
+                for t in tl:
+                    target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * t.geom["sym_oversample"]))
+                    rise_px = t.rise / t.geom["apix3d"]
+                    t.spec = CandidateSpec(t.twist, rise_px, t.csym, target, target,
+                                           positive_rule(positive_constraint, rise_px, t.twist, L3))
+                md_est = int((L3 + L2) / max(min(x.spec.rise_pixel for x in tl), 1e-3) + 3) * L3 * D2
+                cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
+                per_cand = _bytes_per_candidate(n3, md_est, cap_est) * (2 if pipelined else 1)  # two batches resident
+                bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // per_cand)))
+                chunks = [tl[i0:i0 + bs] for i0 in range(0, len(tl), bs)]
+                done = 0
+                for bi, batch in pipe.run(prob, L3, [[x.spec for x in ch] for ch in chunks]):
+                    chunk = chunks[bi]
+                    try:
+                        res = batch.solve(clip_pred=int(thresh_fraction >= 0))
+                        tm = batch.timing()
+                        kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
+                        launches += tm["launches"]
+                        for c, x in enumerate(chunk):
+                            scores[x.ti] = res[c]["score"]
+                            itn[x.ti] = res[c]["itn"]
+                            flags[x.ti] = res[c]["flags"]
+                        if top_k:
+                            order = np.argsort(-res["score"], kind="stable")[:top_k]
+                            for c in order:
+                                ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
+                                           rise=chunk[c].rise, csym=chunk[c].csym)
+                                if return_x_top:
+                                    ent["rec3d"] = batch.rec3d(int(c))
+                                top.append(ent)
+                            top.sort(key=lambda e: (-e["score"], e["ti"]))
+                            del top[top_k:]
+                    finally:
+                        batch.close()
+                    done += len(chunk)
+                    if progress:
+                        progress(done, len(tl))
+            finally:
+                prob.close()
+    finally:
+        pipe.close()
     shape = (len(csyms), len(twists), len(rises))
     out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
-               n_candidates=len(tasks), seconds=time.perf_counter() - t0, kernel_ms=kernel_ms)
+               n_candidates=len(tasks), seconds=time.perf_counter() - t0, kernel_ms=kernel_ms, launches=launches)
     return out

@@ -116,89 +116,119 @@ class BatchPlan:
     stage 1 (``__init__``): unique angles + per-copy column tables;
     stage 2 (``finalize(nvalid)``): row-count early stop (SLR:1647) once the GPU
     has reported the number of rays with data per angle, then flat tables.
+
+    Everything per candidate is a handful of numpy calls over (n_h, L2) arrays
+    (all symmetry copies at once); the arithmetic per element is the scalar
+    sequence of ``column_slices``.
     """
 
     def __init__(self, s, D2, L2, L3, specs):
         self.s, self.D2, self.L2, self.L3 = float(s), int(D2), int(L2), int(L3)
         self.specs = list(specs)
+        L2, L3 = self.L2, self.L3
+        kk = np.arange(L2, dtype=np.float64) - (L2 // 2)
+        z0 = kk * self.s if self.s != 1.0 else kk
         angle_index = {}
         angles = []
-        self.cand_copies = []  # per candidate: list of (angle_id, zi array, h, c)
+        self._cand = []  # per candidate: (copies, angle ids, index of each copy's h in hs, hs, ZI[n_h, L2])
         self.cand_tie_z = []
         mc = 1
         for sp in self.specs:
-            copies = data_copies(sp.rise_pixel, sp.csym, self.L3, self.L2)
-            lst = []
-            tie_any = False
-            col_cache = {}
-            for h, c in copies:
-                angle = sp.twist * h + 360 * c / sp.csym
+            copies = data_copies(sp.rise_pixel, sp.csym, L3, L2)
+            hs = sorted({h for h, _ in copies})
+            hpos = {h: i for i, h in enumerate(hs)}
+            zshift = np.array([h * sp.rise_pixel for h in hs], dtype=np.float64)
+            Z = (z0[None, :] - zshift[:, None]) + (L3 // 2)
+            zi = np.rint(Z).astype(np.int64)
+            ok = (zi >= 0) & (zi <= L3 - 1)
+            near = np.abs(np.abs(Z - np.floor(Z)) - 0.5) < 1e-9
+            self.cand_tie_z.append(bool(np.any(near & (Z > -1.0) & (Z < L3))))
+            ZI = np.where(ok, zi, -1)
+            if ok.any():
+                flat = (np.arange(len(hs))[:, None] * L3 + zi)[ok]
+                mc = max(mc, int(np.bincount(flat).max()))
+            aid = np.empty(len(copies), dtype=np.int64)
+            hidx = np.empty(len(copies), dtype=np.int64)
+            tw, cs = sp.twist, sp.csym
+            for i, (h, c) in enumerate(copies):
+                angle = tw * h + 360 * c / cs
                 a = angle_index.get(angle)
                 if a is None:
                     a = len(angles)
                     angle_index[angle] = a
                     angles.append(angle)
-                if h not in col_cache:
-                    zi, tie = column_slices(self.s, self.L2, self.L3, h * sp.rise_pixel)
-                    cnt = np.bincount(zi[zi >= 0], minlength=self.L3) if np.any(zi >= 0) else np.zeros(self.L3, int)
-                    col_cache[h] = (zi, tie, int(cnt.max()) if len(cnt) else 0)
-                zi, tie, cmax = col_cache[h]
-                tie_any |= tie
-                mc = max(mc, cmax)
-                lst.append((a, zi, h, c))
-            self.cand_copies.append(lst)
-            self.cand_tie_z.append(tie_any)
+                aid[i] = a
+                hidx[i] = hpos[h]
+            self._cand.append((copies, aid, hidx, hs, ZI))
         self.MC = mc
         self.angles = np.array(angles, dtype=np.float64)
         self.cos_sin = z_rotation_entries(self.angles)
         self.finalized = False
 
     def finalize(self, nvalid_rays):
-        nvalid_rays = np.asarray(nvalid_rays)
-        L3, MC = self.L3, self.MC
-        cands = np.zeros(len(self.specs), dtype=_lib.CANDIDATE_DTYPE)
-        views, colk, pairs = [], [], []
+        nvalid_rays = np.asarray(nvalid_rays, dtype=np.int64)
+        L2, L3, MC = self.L2, self.L3, self.MC
+        nc = len(self.specs)
+        cands = np.zeros(nc, dtype=_lib.CANDIDATE_DTYPE)
+        view_angle, colk = [], []
         self.cand_views = []  # per candidate: list of (angle_id, zi, h, c, n_rows_real)
+        pair_meta = []        # (candidate, angle_i, angle_j, zshift_i, zshift_j) arrays, rotated in one scipy call below
+        nviews = 0
+        npairs = 0
+        karange = np.arange(L2, dtype=np.int64)[None, :]
         for ci, sp in enumerate(self.specs):
-            used = []
-            n_b = 0
-            for a, zi, h, c in self.cand_copies[ci]:
-                ncols = int(np.count_nonzero(zi >= 0))
-                nrows = ncols * int(nvalid_rays[a])
-                n_b += nrows
-                if nrows:
-                    used.append((a, zi, h, c, nrows))
-                if sp.min_projection_lines > 0 and n_b > sp.min_projection_lines:
-                    break
-            self.cand_views.append(used)
-            cands[ci]["view_begin"] = len(views)
-            cands[ci]["view_count"] = len(used)
-            for a, zi, h, c, nrows in used:
-                tab = np.full(L3 * MC, -1, dtype=np.int32)
-                fill = np.zeros(L3, dtype=np.int64)
-                for k in np.nonzero(zi >= 0)[0]:
-                    z = int(zi[k])
-                    tab[z * MC + fill[z]] = k
-                    fill[z] += 1
-                views.append((a, len(colk) * L3 * MC))
-                colk.append(tab)
+            copies, aid, hidx, hs, ZI = self._cand[ci]
+            valid = ZI >= 0
+            ncols_h = valid.sum(axis=1)
+            nrows = ncols_h[hidx] * nvalid_rays[aid]
+            stop = len(copies)
+            if sp.min_projection_lines > 0:
+                over = np.nonzero(np.cumsum(nrows) > sp.min_projection_lines)[0]
+                if len(over):
+                    stop = int(over[0]) + 1
+            sel = np.nonzero(nrows[:stop] > 0)[0]
+            self.cand_views.append([(int(aid[i]), ZI[hidx[i]], copies[i][0], copies[i][1], int(nrows[i])) for i in sel])
+            cands[ci]["view_begin"] = nviews
+            cands[ci]["view_count"] = len(sel)
+            if len(sel):
+                # column table of every h: tab[z*MC + m] = m-th image column whose slice is z (columns ascending)
+                prev = np.concatenate([np.full((len(hs), 1), -2, dtype=np.int64), ZI[:, :-1]], axis=1)
+                run_start = np.maximum.accumulate(np.where(valid & (ZI != prev), karange, 0), axis=1)
+                tab = np.full((len(hs), L3 * MC), -1, dtype=np.int32)
+                hh, kq = np.nonzero(valid)
+                tab[hh, ZI[hh, kq] * MC + (kq - run_start[hh, kq])] = kq
+                colk.append(tab[hidx[sel]])
+                view_angle.append(aid[sel])
+                nviews += len(sel)
             # symmetry pairs (SLR:892, 1223-1243)
-            cands[ci]["pair_begin"] = len(pairs)
+            cands[ci]["pair_begin"] = npairs
             plist = sorted_hsym_csym_pairs(sp.twist, sp.rise_pixel, sp.csym, L3) if sp.min_sym_pairs >= 0 else []
             if plist:
-                ai = np.array([sp.twist * p[-1][0][0] + p[-1][0][1] * 360 / sp.csym for p in plist])
-                aj = np.array([sp.twist * p[-1][1][0] + p[-1][1][1] * 360 / sp.csym for p in plist])
-                ei, ej = z_rotation_entries(ai), z_rotation_entries(aj)
-                for t, p in enumerate(plist):
-                    (hi, _), (hj, _) = p[-1]
-                    pairs.append((ei[t, 0], ei[t, 1], sp.rise_pixel * hi, ej[t, 0], ej[t, 1], sp.rise_pixel * hj))
+                pq = np.array([(p[-1][0][0], p[-1][0][1], p[-1][1][0], p[-1][1][1]) for p in plist], dtype=np.float64)
+                ai = sp.twist * pq[:, 0] + pq[:, 1] * 360 / sp.csym
+                aj = sp.twist * pq[:, 2] + pq[:, 3] * 360 / sp.csym
+                pair_meta.append((ai, aj, sp.rise_pixel * pq[:, 0], sp.rise_pixel * pq[:, 2]))
+                npairs += len(plist)
             cands[ci]["pair_count"] = len(plist)
             cands[ci]["min_sym_pairs"] = sp.min_sym_pairs
             cands[ci]["positive"] = int(sp.positive)
             cands[ci]["flags_in"] = _lib.HB2_FLAG_TIE_Z if self.cand_tie_z[ci] else 0
         self.cands = cands
-        self.views = np.array(views, dtype=_lib.VIEW_DTYPE) if views else np.zeros(0, dtype=_lib.VIEW_DTYPE)
-        self.colk = np.concatenate(colk).astype(np.int32) if colk else np.zeros(0, dtype=np.int32)
-        self.pairs = np.array(pairs, dtype=_lib.PAIR_DTYPE) if pairs else np.zeros(0, dtype=_lib.PAIR_DTYPE)
+        views = np.zeros(nviews, dtype=_lib.VIEW_DTYPE)
+        if nviews:
+            views["angle"] = np.concatenate(view_angle)
+            views["col_begin"] = np.arange(nviews, dtype=np.int64) * (L3 * MC)
+            self.colk = np.ascontiguousarray(np.concatenate(colk).reshape(-1), dtype=np.int32)
+        else:
+            self.colk = np.zeros(0, dtype=np.int32)
+        self.views = views
+        pairs = np.zeros(npairs, dtype=_lib.PAIR_DTYPE)
+        if npairs:
+            ai = np.concatenate([m[0] for m in pair_meta])
+            aj = np.concatenate([m[1] for m in pair_meta])
+            ei, ej = z_rotation_entries(ai), z_rotation_entries(aj)
+            pairs["ci"], pairs["si"], pairs["zi"] = ei[:, 0], ei[:, 1], np.concatenate([m[2] for m in pair_meta])
+            pairs["cj"], pairs["sj"], pairs["zj"] = ej[:, 0], ej[:, 1], np.concatenate([m[3] for m in pair_meta])
+        self.pairs = pairs
         self.finalized = True
         return self

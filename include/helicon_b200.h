@@ -109,6 +109,17 @@ const char* hb2_last_error(void);
 int hb2_device_count(void);
 const char* hb2_build_info(void);
 
+/* ---- streams / memory ------------------------------------------------------
+ * Additive helpers for the batched grid driver (no reference counterpart: the
+ * reference runs one candidate per ThreadPoolExecutor worker, app.py:2455-2523).
+ * A batch does all its work on the stream given to hb2_batch_begin; batches on
+ * different non-blocking streams overlap (setup of the next batch under the
+ * solve of the current one).  Batch memory comes from the device's stream-
+ * ordered pool and is kept cached between batches; hb2_device_trim returns it. */
+int hb2_stream_create(int device, void** stream_out);
+int hb2_stream_destroy(int device, void* stream);
+int hb2_device_trim(int device);
+
 /* ---- problem ------------------------------------------------------------- */
 /* Uploads the image, crops pixel_vals (SLR:1706-1708) and builds the disk
  * tables of helicon.get_cylindrical_mask (lib/analysis.py:731-774). */
