@@ -50,6 +50,11 @@ struct hb2_problem {
   short2* d_yx_sym = nullptr;      // [ndisk] on the symmetry grid, REFERENCE voxel order (row enumeration of the symmetry rows)
   std::vector<int> h_rank_data;    // reference disk rank (C-order np.nonzero) on the data grid, for exports
   std::vector<int> int2ref, ref2int;  // internal (tile-major) disk rank <-> reference rank
+  std::vector<int> h_tile_begin;      // [ntile+1] first internal rank of every non-empty voxel tile
+  int ntile = 0;
+  bool tile_ok = false;               // tiles hold <= 256 voxels (k_adj_tile)
+  int* d_tile_begin = nullptr;
+  int* d_aslot = nullptr;             // [ndisk] tile*256 + rank inside the tile
 };
 
 // Device allocations of a batch come from the stream-ordered allocator (cudaMallocAsync on the batch's stream) with
@@ -88,6 +93,7 @@ struct hb2_batch {
   DevPool pool;
   BD B{};
   bool idx16 = true;
+  size_t adj_tile_smem = 0;
   bool created = false;
   int nviews = 0;
   // host copies
@@ -104,7 +110,7 @@ struct hb2_batch {
   uint8_t* d_rayvalid = nullptr;
   int* d_tie = nullptr;
   uint16_t* d_amap = nullptr;
-  int* d_sym_a = nullptr; int* d_sym_b = nullptr; int* d_csc_ptr = nullptr; int* d_csc_ent = nullptr;
+  int* d_sym_a = nullptr; int* d_sym_b = nullptr; int* d_csc_ptr = nullptr; int* d_csc_ent = nullptr; int* d_ell = nullptr;
   float* d_bmax = nullptr;
   float* d_score = nullptr;
   int* d_nactive = nullptr;
@@ -177,21 +183,26 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
 // compact 2-D patch, whose rays form a short contiguous range in every view -- the rows a CTA gathers stay in L1
 // (profiles/r1: with row-major ranks every CTA touched (1 + 256|sin|) rows per view).  Reference order is kept for
 // everything exported and for the enumeration order of the symmetry rows.
-static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref) {
+static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref, std::vector<int>& tile_begin,
+                       bool& tile_ok) {
   static int TH = -1, TW = -1;
   if (TH < 0) {
     const char* eh = getenv("HB2_TILE_H"); const char* ew = getenv("HB2_TILE_W");
     TH = eh ? std::max(1, atoi(eh)) : 8; TW = ew ? std::max(1, atoi(ew)) : 32;
   }
+  tile_ok = (long long)TH * TW <= HB2_BLOCK;
   int ymin = 1 << 30, xmin = 1 << 30;
   for (const short2& q : yx_ref) { ymin = std::min<int>(ymin, q.x); xmin = std::min<int>(xmin, q.y); }
   int2ref.resize(yx_ref.size());
   for (size_t i = 0; i < yx_ref.size(); ++i) int2ref[i] = (int)i;
-  auto key = [&](int r) {
-    const int y = yx_ref[r].x - ymin, x = yx_ref[r].y - xmin;
-    return std::make_pair(std::make_pair(y / TH, x / TW), r);  // reference rank is row-major already
-  };
-  std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) { return key(a) < key(b); });
+  auto tkey = [&](int r) { return std::make_pair((yx_ref[r].x - ymin) / TH, (yx_ref[r].y - xmin) / TW); };
+  std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) {
+    return std::make_pair(tkey(a), a) < std::make_pair(tkey(b), b);  // reference rank is row-major already
+  });
+  tile_begin.clear();
+  for (size_t i = 0; i < int2ref.size(); ++i)
+    if (i == 0 || tkey(int2ref[i]) != tkey(int2ref[i - 1])) tile_begin.push_back((int)i);
+  tile_begin.push_back((int)int2ref.size());
 }
 
 extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const hb2_geometry* g, int device, void* stream) {
@@ -226,9 +237,11 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   P->ndisk = (int)yd.size();
   P->h_rank_data = rd;
   {
-    std::vector<int> i2r_sym;
-    tile_order(yd, P->int2ref);
-    tile_order(ys, i2r_sym);
+    std::vector<int> i2r_sym, tb_sym;
+    bool ok_sym;
+    tile_order(yd, P->int2ref, P->h_tile_begin, P->tile_ok);
+    tile_order(ys, i2r_sym, tb_sym, ok_sym);
+    P->ntile = (int)P->h_tile_begin.size() - 1;
     if (i2r_sym != P->int2ref) {
       delete P;
       return fail(HB2_ERR_GEOMETRY, "the cylinder mask is not the same voxel set on the 2-D (D2) and 3-D (D3) grids");
@@ -255,6 +268,13 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   CK(cudaMalloc(&P->d_rank_sym, rs.size() * sizeof(int)));
   CK(cudaMalloc(&P->d_yx_data, yd.size() * sizeof(short2)));
   CK(cudaMalloc(&P->d_yx_sym, ys.size() * sizeof(short2)));
+  std::vector<int> aslot(P->ndisk);
+  for (int t = 0; t < P->ntile; ++t)
+    for (int i = P->h_tile_begin[t]; i < P->h_tile_begin[t + 1]; ++i) aslot[i] = t * HB2_BLOCK + (i - P->h_tile_begin[t]);
+  CK(cudaMalloc(&P->d_tile_begin, P->h_tile_begin.size() * sizeof(int)));
+  CK(cudaMalloc(&P->d_aslot, aslot.size() * sizeof(int)));
+  CK(cudaMemcpyAsync(P->d_tile_begin, P->h_tile_begin.data(), P->h_tile_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(P->d_aslot, aslot.data(), aslot.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_pix, pix.data(), pix.size() * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_rank_data, rd.data(), rd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(P->d_rank_sym, rs.data(), rs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -268,6 +288,7 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
 extern "C" void hb2_problem_destroy(hb2_problem* P) {
   if (!P) return;
   cudaSetDevice(P->device);
+  cudaFree(P->d_tile_begin); cudaFree(P->d_aslot);
   cudaFree(P->d_pix); cudaFree(P->d_rank_data); cudaFree(P->d_rank_sym); cudaFree(P->d_yx_data); cudaFree(P->d_yx_sym);
   delete P;
 }
@@ -449,10 +470,12 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKC(b->pool.alloc(&d_kmax, 1, true, st));
     CKC(b->pool.alloc(&d_h1, B.nA, true, st));
     CKC(b->pool.alloc(&d_h2, B.nA, true, st));
-    B.apitch = (B.ndisk + 255) / 256 * 256;
+    B.apitch = P->tile_ok ? P->ntile * HB2_BLOCK : 0;
+    B.aslot = P->d_aslot; B.tile_begin = P->d_tile_begin; B.ntile = P->ntile;
+    if (!P->tile_ok) return fail(HB2_ERR_GEOMETRY, "HB2_TILE_H*HB2_TILE_W must be <= 256");
     long long na = (long long)B.nA * B.ndisk;
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
     CKL();
     int K = 0;
     CKC(cudaMemcpyAsync(&K, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -462,8 +485,8 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     B.K = K;
     CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.apitch, false, st));
     CKC(cudaMemsetAsync(b->d_amap, 0xFF, (size_t)B.nA * K * B.apitch * sizeof(uint16_t), st));
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
     CKL();
     // consistency: every hit of the forward map must appear in the adjoint map
     long long ns = (long long)B.nA * D2 * D2;
@@ -478,6 +501,19 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     for (int a = 0; a < B.nA; ++a)
       if (h1[a] != h2[a]) return fail(HB2_ERR_CAPACITY, "adjoint map does not cover the forward map (internal error)");
     B.amap = b->d_amap;
+    {  // ray window of every (angle, tile) for the tile adjoint
+      uint16_t *d_jlo, *d_nr; int* d_rmax;
+      CKC(b->pool.alloc(&d_jlo, (size_t)B.nA * B.ntile, false, st));
+      CKC(b->pool.alloc(&d_nr, (size_t)B.nA * B.ntile, false, st));
+      CKC(b->pool.alloc(&d_rmax, 1, true, st));
+      k_tile_rays<<<dim3(B.ntile, B.nA), HB2_BLOCK, 0, st>>>(K, B.apitch, B.ntile, b->d_amap, d_jlo, d_nr, d_rmax);
+      CKL();
+      int rmax = 0;
+      CKC(cudaMemcpyAsync(&rmax, d_rmax, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CKC(cudaStreamSynchronize(st));
+      B.tile_jlo = d_jlo; B.tile_nr = d_nr; B.rmax = std::max(rmax, 1);
+      b->pool.release(d_rmax);
+    }
     b->pool.release(d_kmax); b->pool.release(d_h1); b->pool.release(d_h2);
   }
   // ---- vectors -----------------------------------------------------------------
@@ -507,11 +543,15 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   {
     long long max_md = 0;
     for (int c = 0; c < nc; ++c) max_md = std::max<long long>(max_md, b->h_mdata[c]);
-    B.adj_lean = (B.MC == 1 && B.K <= 2 && max_md + (long long)B.ZMP * B.D2 < (1ll << 32) &&
-                  true) ? 1 : 0;
-    B.adj_nqt = std::min(4, B.L3P / 4);
-    B.adj_nzch = cdiv(B.L3P, 4 * B.adj_nqt);
-    B.part_v_per_cand = B.adj_lean ? cdiv(B.ndisk, HB2_BLOCK) * B.adj_nzch : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
+    B.adj_fast = (B.MC == 1 && B.K <= 2 && max_md + (long long)B.ZMP * B.D2 < (1ll << 32)) ? 1 : 0;
+    int max_views = 0;
+    for (int c = 0; c < nc; ++c) max_views = std::max(max_views, b->h_view_count[c]);
+    b->adj_tile_smem = (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.K * HB2_BLOCK * sizeof(uint16_t) +
+                       (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.rmax * B.L3P * sizeof(float);
+    const char* no_tile = getenv("HB2_NO_ADJ_TILE");
+    B.adj_tile = (B.adj_fast && B.L3P <= 16 && max_views <= HB2_ADJT_MAXV && b->adj_tile_smem <= 96 * 1024 &&
+                  !(no_tile && atoi(no_tile))) ? 1 : 0;
+    B.part_v_per_cand = B.adj_tile ? B.ntile : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
   }
   B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
@@ -612,6 +652,11 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKT(cudaStreamSynchronize(st));
     tmp.free_all();
   }
+  // fixed-width copy of the transpose lists for the fast adjoint
+  CKC(b->pool.alloc(&b->d_ell, (size_t)nc * HB2_ELL_W * B.npad, false, st));
+  k_ell_fill<<<dim3(cdiv(B.npad, 256), nc), 256, 0, st>>>(B, b->d_ell);
+  CKL();
+  B.ell = b->d_ell;
   CKC(cudaStreamSynchronize(st));
   b->created = true;
   return HB2_OK;
@@ -706,12 +751,22 @@ static void launch_adj(hb2_batch* b, int mode) {
   const BD& B = b->B;
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
-  if (B.adj_lean) {
-#define ADJL(Q, K) k_adj_lean<Q, K><<<g, HB2_BLOCK, 0, st>>>(B, mode)
-#define ADJLQ(K) do { if (B.adj_nqt == 1) ADJL(1, K); else if (B.adj_nqt == 2) ADJL(2, K); else if (B.adj_nqt == 3) ADJL(3, K); else ADJL(4, K); } while (0)
-    if (B.K == 1) ADJLQ(1); else ADJLQ(2);
-#undef ADJLQ
-#undef ADJL
+  if (B.adj_tile) {
+    const size_t sm = b->adj_tile_smem;
+#define ADJT(Q, K)                                                                                       \
+  do {                                                                                                   \
+    cudaFuncSetAttribute(k_adj_tile<Q, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
+    k_adj_tile<Q, K><<<g, HB2_ADJT_THREADS, sm, st>>>(B, mode);                                                 \
+  } while (0)
+#define ADJTQ(K) do { if (B.L3P == 4) ADJT(1, K); else if (B.L3P == 8) ADJT(2, K); else if (B.L3P == 12) ADJT(3, K); else ADJT(4, K); } while (0)
+    if (B.K == 1) ADJTQ(1); else ADJTQ(2);
+#undef ADJTQ
+#undef ADJT
+    return;
+  }
+  if (B.adj_fast) {
+    if (B.K == 1) k_adj_pq<1><<<g, HB2_BLOCK, 0, st>>>(B, mode);
+    else k_adj_pq<2><<<g, HB2_BLOCK, 0, st>>>(B, mode);
     return;
   }
 #define ADJ(K, M) k_adj<K, M><<<g, HB2_BLOCK, 0, st>>>(B, mode)

@@ -7,6 +7,9 @@
 #define HB2_TILE_RAYS 32   // rays per CTA of the forward projector
 #define HB2_BLOCK 256
 #define HB2_FWD_U 8      // samples in flight per lane of the forward projector
+#define HB2_ELL_W 4      // fixed-width part of the symmetry transpose lists
+#define HB2_ELL_NONE 0x7FFFFFFF
+#define HB2_ELL_OVERFLOW 0x7FFFFFFE  // in plane W-1: the voxel has more than W entries, use the CSR list
 
 enum { MODE_LSMR = 0, MODE_PLAIN = 1, MODE_SCORE = 2, MODE_INIT = 3 };
 
@@ -22,7 +25,13 @@ struct BD {
   const void* fmap;            // [nA][D2][D2] disk rank or SENT
   const uint8_t* rayvalid;     // [nA][D2]
   const uint16_t* amap;        // [nA][K][apitch] ray j of the k-th sample landing in voxel p, or 0xFFFF
-  int apitch;                  // row pitch of amap: ndisk rounded up to 256 (rows 512-byte aligned; padding = 0xFFFF)
+  int apitch;                  // row pitch of amap = ntile*256: every voxel tile owns a 512-byte aligned run of 256 slots
+  const int* aslot;            // [ndisk] slot of voxel p in an amap row (tile*256 + rank inside the tile)
+  const int* tile_begin;       // [ntile+1] first internal rank of every voxel tile (tile-major voxel order)
+  int ntile;
+  const uint16_t* tile_jlo;    // [nA][ntile] first ray of the view that crosses the tile
+  const uint16_t* tile_nr;     // [nA][ntile] number of consecutive rays crossing it (0 = none)
+  int rmax;                    // max of tile_nr
   // views (flat over the batch)
   const int* view_cand;
   const int* view_angle;
@@ -50,6 +59,7 @@ struct BD {
   const int* sym_b;
   const int* csc_ptr;   // [nc][n+1]
   const int* csc_ent;   // row | sign<<31
+  const int* ell;       // [nc][HB2_ELL_W][npad]: first entries of every voxel's transpose list (z-fastest like v)
   // solver state
   LsmrState* st;
   float* part_u;   // per-CTA partial sums of squares
@@ -58,8 +68,8 @@ struct BD {
   double* part_x;
   float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
   int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
-  int adj_lean;    // MC == 1, K <= 2, row offsets fit 32 bits: k_adj_lean with adj_nqt quads per thread
-  int adj_nqt, adj_nzch;
+  int adj_fast;    // MC == 1, K <= 2, row offsets fit 32 bits: k_adj_pq
+  int adj_tile;    // additionally L3P <= 16, <= 256 views per candidate, windows fit shared memory: k_adj_tile
   int only_cand;   // MODE_PLAIN: restrict to one candidate (-1 all)
   int clip_pred;
 };
@@ -156,7 +166,7 @@ __global__ void k_build_fmap(int nA, int D2, double s, const double* __restrict_
 // pass 0: count only (max multiplicity -> *kmax); pass 1: fill amap[a][k][p].
 template <typename IdxT>
 __global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, int K, int pass, const double* __restrict__ cs,
-                             const short2* __restrict__ disk_yx, const IdxT* __restrict__ fmap,
+                             const short2* __restrict__ disk_yx, const int* __restrict__ aslot, const IdxT* __restrict__ fmap,
                              uint16_t* __restrict__ amap, int* __restrict__ kmax) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nA * ndisk) return;
@@ -176,13 +186,13 @@ __global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, in
   for (int j = j0; j <= j1; ++j)
     for (int i = i0; i <= i1; ++i)
       if (fm[(size_t)j * D2 + i] == (IdxT)p) {
-        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * apitch + p] = (uint16_t)j;
+        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * apitch + aslot[p]] = (uint16_t)j;
         ++cnt;
       }
   if (pass == 0) {
     if (cnt > 0) atomicMax(kmax, cnt);
   } else {
-    for (int k = cnt; k < K; ++k) amap[((size_t)a * K + k) * apitch + p] = 0xFFFFu;
+    for (int k = cnt; k < K; ++k) amap[((size_t)a * K + k) * apitch + aslot[p]] = 0xFFFFu;
   }
 }
 
@@ -415,6 +425,26 @@ __global__ void k_csc_sort(BD B, int* __restrict__ ent) {  // deterministic orde
   }
 }
 
+// fixed-width copy of the (sorted) transpose lists: ell[c][w][g] = w-th entry of voxel g, HB2_ELL_NONE beyond the
+// list; voxels with more than HB2_ELL_W entries get HB2_ELL_OVERFLOW in the last plane (the adjoint then walks the
+// CSR list).  Measured on cfg-like geometries: 2-3 entries per voxel, > 4 for < 0.01 % of the voxels.
+__global__ void k_ell_fill(BD B, int* __restrict__ ell) {
+  int c = blockIdx.y;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= B.npad) return;
+  const int* ptr = B.csc_ptr + (size_t)c * (B.npad + 1);
+  const int* e = B.csc_ent + B.cand_cscoff[c];
+  const int e0 = ptr[g], cnt = ptr[g + 1] - e0;
+  int* dst = ell + (size_t)c * HB2_ELL_W * B.npad + g;
+#pragma unroll
+  for (int w = 0; w < HB2_ELL_W; ++w) {
+    int val = HB2_ELL_NONE;
+    if (cnt <= HB2_ELL_W) { if (w < cnt) val = e[e0 + w]; }
+    else if (w == HB2_ELL_W - 1) val = HB2_ELL_OVERFLOW;
+    dst[(size_t)w * B.npad] = val;
+  }
+}
+
 // ===========================================================================
 // forward projector: data rows.  One CTA = 32 consecutive rays of one view, one
 // warp per ray.  Lanes are split 8 sample groups x 4 slice quads: per step the
@@ -590,6 +620,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
   const int t = blockIdx.x * HB2_BLOCK + threadIdx.x;
   const int p = t / NQ, q = t - p * NQ;
   const bool live = p < ndisk;
+  const int slot = live ? B.aslot[p] : 0;
   const int z0 = 4 * q;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
   const float beta = S.beta;
@@ -606,7 +637,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     if (!live) continue;
     for (int vi = 0; vi < nvc; ++vi) {
       const float* __restrict__ ub = B.u + s_uoff[vi] + z0 * MC;
-      const uint16_t* __restrict__ am = B.amap + (size_t)s_ang[vi] * K * B.apitch + p;
+      const uint16_t* __restrict__ am = B.amap + (size_t)s_ang[vi] * K * B.apitch + slot;
       for (int k = 0; k < K; ++k) {
         const uint16_t j = am[(size_t)k * B.apitch];
         if (j != 0xFFFFu) {
@@ -664,112 +695,362 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
 }
 
 // ---------------------------------------------------------------------------
-// Adjoint, fast path (MC == 1, K <= 2).  One thread = one in-plane voxel p and
-// NQT slice quads (z chunk = blockIdx % nzch when L3P > 16).  Per view: one
-// 32-bit map offset from shared memory, K 16-bit map entries, and for a hit NQT
-// 128-bit loads of the ray's row.  View rows of a candidate are contiguous in u
-// (view vi starts at vi*rows_per_view), so no row-offset table is needed and
-// all offsets are 32-bit.  Addition order: views, then k, then symmetry rows.
-// (profiles/r1_summary.md: variants with (voxel, quad) lanes, with cp.async
-// staging of the map and with 4-view load batching were measured and were not
-// faster -- the kernel sits at ~50 % of the L1 wavefront rate either way.)
+// Adjoint, fast path (MC == 1, K <= 2).  One thread = one in-plane voxel p and one
+// slice quad q; the NQ = L3P/4 lanes of a voxel are adjacent, so every warp-wide
+// 128-bit gather covers whole 4*NQ-float rows of ~32/NQ neighbouring voxels, which
+// map to the same or neighbouring rays (contiguous rows): ~5 L1 wavefronts per
+// gather instead of ~16 for three strided gathers (profiles/r1_summary.md: the
+// adjoint is bound by the L1 wavefront rate, 66 % of it these row gathers and
+// 27 % the 4-byte walks of the per-voxel symmetry lists).  The symmetry part
+// reads the fixed-width list copy (BD::ell) with 128-bit loads laid out like v.
+// All offsets are 32-bit (view rows of a candidate are contiguous in u).
+// Addition order: views, then k, then symmetry rows -- as k_adj.
 // ---------------------------------------------------------------------------
-template <int NQT, int KT>
-__global__ void __launch_bounds__(HB2_BLOCK) k_adj_lean(BD B, int mode) {
+#define HB2_ADJ_VU 4
+template <int KT>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
   const int c = blockIdx.y;
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ unsigned s_aoff[HB2_ADJ_VIEWS];
   const LsmrState& S = B.st[c];
   bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
                                  : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
-  const int nzch = B.adj_nzch;
-  const int ptile = blockIdx.x / nzch, zch = blockIdx.x - ptile * nzch;
   const int pi = c * B.part_v_per_cand + blockIdx.x;
   if (!act) {
     if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
     return;
   }
-  const int L3 = B.L3, L3P = B.L3P, ndisk = B.ndisk;
-  const unsigned ZMP = (unsigned)B.ZMP, rpv = (unsigned)B.rows_per_view, kstride = (unsigned)KT * (unsigned)B.apitch;
-  const int p = ptile * HB2_BLOCK + threadIdx.x, z0 = zch * (4 * NQT);
+  const int L3P = B.L3P, ndisk = B.ndisk;
+  const int NQ = L3P >> 2;
+  const unsigned rpv = (unsigned)B.rows_per_view, kstride = (unsigned)KT * (unsigned)B.apitch;
+  const int t = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const int p = t / NQ, q = t - p * NQ, z0 = 4 * q;
   const bool live = p < ndisk;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
   const float beta = S.beta;
-  float acc[4 * NQT];
-#pragma unroll
-  for (int i = 0; i < 4 * NQT; ++i) acc[i] = 0.f;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
   const float* __restrict__ ucand = B.u + B.cand_uoff[c] + z0;
-  const uint16_t* __restrict__ am0 = B.amap + (live ? p : 0);
+  const uint16_t* __restrict__ am0 = B.amap + (live ? B.aslot[p] : 0);
   const uint16_t* __restrict__ am1 = am0 + B.apitch;
   for (int v0 = 0; v0 < nv; v0 += HB2_ADJ_VIEWS) {
     const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
     __syncthreads();
-    for (int e = threadIdx.x; e < nvc; e += HB2_BLOCK) s_aoff[e] = (unsigned)B.view_angle[vb + v0 + e] * kstride;
+    for (int e = threadIdx.x; e < HB2_ADJ_VIEWS; e += HB2_BLOCK)
+      s_aoff[e] = (unsigned)B.view_angle[vb + v0 + min(e, nvc - 1)] * kstride;  // tail entries repeat the last view
     __syncthreads();
     if (!live) continue;
-    unsigned uo = (unsigned)v0 * rpv;
-#pragma unroll 2
-    for (int vi = 0; vi < nvc; ++vi, uo += rpv) {
-      const unsigned ao = s_aoff[vi];
-      const unsigned j0 = am0[ao];
-      unsigned j1 = 0xFFFFu;
-      if (KT == 2) j1 = am1[ao];
-      if (j0 != 0xFFFFu) {
-        const float4* __restrict__ r = reinterpret_cast<const float4*>(ucand + (uo + j0 * ZMP));
+    for (int vi = 0; vi < nvc; vi += HB2_ADJ_VU) {
+      unsigned j0[HB2_ADJ_VU], j1[HB2_ADJ_VU];
 #pragma unroll
-        for (int q4 = 0; q4 < NQT; ++q4) {
-          const float4 t = __ldg(r + q4);
-          acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
-          acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
-        }
+      for (int w = 0; w < HB2_ADJ_VU; ++w) {
+        const unsigned ao = s_aoff[vi + w];
+        j0[w] = am0[ao];
+        j1[w] = KT == 2 ? (unsigned)am1[ao] : 0xFFFFu;
+        if (vi + w >= nvc) { j0[w] = 0xFFFFu; j1[w] = 0xFFFFu; }
       }
-      if (KT == 2 && j1 != 0xFFFFu) {
-        const float4* __restrict__ r = reinterpret_cast<const float4*>(ucand + (uo + j1 * ZMP));
+      float4 r0[HB2_ADJ_VU];
 #pragma unroll
-        for (int q4 = 0; q4 < NQT; ++q4) {
-          const float4 t = __ldg(r + q4);
-          acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
-          acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+      for (int w = 0; w < HB2_ADJ_VU; ++w) {
+        const unsigned uo = (unsigned)(v0 + vi + w) * rpv;
+        r0[w] = j0[w] != 0xFFFFu ? ldg4(ucand + (uo + j0[w] * (unsigned)L3P)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int w = 0; w < HB2_ADJ_VU; ++w) {
+        if (j0[w] != 0xFFFFu) {
+          acc0 = fmaf(r0[w].x, ib, acc0); acc1 = fmaf(r0[w].y, ib, acc1);
+          acc2 = fmaf(r0[w].z, ib, acc2); acc3 = fmaf(r0[w].w, ib, acc3);
+        }
+        if (KT == 2 && j1[w] != 0xFFFFu) {  // second sample of the same view in this voxel (rare)
+          const float4 r1 = ldg4(ucand + ((unsigned)(v0 + vi + w) * rpv + j1[w] * (unsigned)L3P));
+          acc0 = fmaf(r1.x, ib, acc0); acc1 = fmaf(r1.y, ib, acc1);
+          acc2 = fmaf(r1.z, ib, acc2); acc3 = fmaf(r1.w, ib, acc3);
         }
       }
     }
   }
   float ss = 0.f;
   if (live) {
-    const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1) + (p * L3P + z0);
-    const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
+    const int g0 = p * L3P + z0;
     const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
-    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + (size_t)p * L3P + z0;
-    const int nz = min(4 * NQT, L3 - z0);  // real slices of this chunk (padded slices stay 0)
-    int e = nz > 0 ? ptr[0] : 0;
+    const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
+    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + g0;
+    int ev[HB2_ELL_W][4];
 #pragma unroll
-    for (int q4 = 0; q4 < NQT; ++q4) {
-      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
-      float vn[4];
+    for (int w = 0; w < HB2_ELL_W; ++w) {
+      const int4 e4 = __ldg(reinterpret_cast<const int4*>(ell + (size_t)w * B.npad));
+      ev[w][0] = e4.x; ev[w][1] = e4.y; ev[w][2] = e4.z; ev[w][3] = e4.w;
+    }
+    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst);
+    float vals[HB2_ELL_W][4];
+#pragma unroll
+    for (int w = 0; w < HB2_ELL_W; ++w)
 #pragma unroll
       for (int tz = 0; tz < 4; ++tz) {
-        const int zz = 4 * q4 + tz;
-        float a2 = acc[zz];
-        if (zz < nz) {
-          const int e1 = ptr[zz + 1];
-          for (; e < e1; ++e) {
-            const int en = ent[e];
-            const float val = __ldg(us + (en & 0x7fffffff));
-            a2 = fmaf(en < 0 ? -val : val, ib, a2);
-          }
-        }
-        const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
-        vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), a2) : a2;
-        ss += vn[tz] * vn[tz];
+        const bool ok = ev[w][tz] < 0 || ev[w][tz] < HB2_ELL_OVERFLOW;  // a real entry (either sign)
+        vals[w][tz] = ok ? __ldg(us + (ev[w][tz] & 0x7fffffff)) : 0.f;
       }
-      *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+    const float a2[4] = {acc0, acc1, acc2, acc3};
+    float vn[4];
+#pragma unroll
+    for (int tz = 0; tz < 4; ++tz) {
+      float s2 = a2[tz];
+      if (ev[HB2_ELL_W - 1][tz] == HB2_ELL_OVERFLOW) {  // long list: walk the CSR copy
+        const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1) + g0 + tz;
+        const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
+        for (int e = ptr[0]; e < ptr[1]; ++e) {
+          const int x = ent[e];
+          const float val = __ldg(us + (x & 0x7fffffff));
+          s2 = fmaf(x < 0 ? -val : val, ib, s2);
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < HB2_ELL_W; ++w)
+          if (ev[w][tz] != HB2_ELL_NONE) s2 = fmaf(ev[w][tz] < 0 ? -vals[w][tz] : vals[w][tz], ib, s2);
+      }
+      const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
+      vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), s2) : s2;
+      ss += vn[tz] * vn[tz];
     }
+    *reinterpret_cast<float4*>(vdst) = make_float4(vn[0], vn[1], vn[2], vn[3]);
   }
   if (mode != MODE_PLAIN) {
     float tot = block_sum(ss, red);
     if (threadIdx.x == 0) B.part_v[pi] = tot;
+  }
+}
+
+// rays of view angle a crossing voxel tile t: [jlo, jlo + nr).  One CTA per (tile, angle).
+__global__ void __launch_bounds__(HB2_BLOCK) k_tile_rays(int K, int apitch, int ntile, const uint16_t* __restrict__ amap,
+                                                        uint16_t* __restrict__ jlo, uint16_t* __restrict__ nr,
+                                                        int* __restrict__ rmax) {
+  const int t = blockIdx.x, a = blockIdx.y;
+  __shared__ int s_lo[HB2_BLOCK / 32], s_hi[HB2_BLOCK / 32];
+  int lo = 0x7fffffff, hi = -1;
+  for (int k = 0; k < K; ++k) {
+    const unsigned j = amap[((size_t)a * K + k) * apitch + (size_t)t * HB2_BLOCK + threadIdx.x];
+    if (j != 0xFFFFu) { lo = min(lo, (int)j); hi = max(hi, (int)j); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < HB2_BLOCK / 32; ++w) { lo = min(lo, s_lo[w]); hi = max(hi, s_hi[w]); }
+    const int n = hi >= 0 ? hi - lo + 1 : 0;
+    jlo[(size_t)a * ntile + t] = (uint16_t)(n ? lo : 0);
+    nr[(size_t)a * ntile + t] = (uint16_t)n;
+    if (n) atomicMax(rmax, n);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Adjoint, tile path (MC == 1, K <= 2, L3P <= 16): one CTA = one voxel tile
+// (8 x 32 in-plane patch, <= 256 voxels, one thread each, all slices in
+// registers).  profiles/r1_summary.md: with global gathers every view costs a
+// dependent L2 round trip (map entry -> row) and the kernel is bound by
+// loads-in-flight / latency.  Here both operands of a stage of HB2_ADJT_SV
+// views are brought to shared memory by the TMA engine (cp.async.bulk, mbarrier
+// completion, two stages in flight): the tile's 512-byte runs of the adjoint
+// map, and -- because a compact tile is crossed by a short contiguous range of
+// rays in every view -- one contiguous window [jlo, jlo+nr) x L3P of the view's
+// rows.  The inner loop then touches shared memory only.
+// Addition order: views, then k, then symmetry rows (= k_adj / k_adj_pq).
+// ---------------------------------------------------------------------------
+#define HB2_ADJT_SV 4      // views per stage
+#define HB2_ADJT_NS 4      // stages in flight
+#define HB2_ADJT_THREADS (HB2_BLOCK + 32)  // 8 consumer warps (one thread per voxel) + 1 producer warp
+#define HB2_ADJT_MAXV 256
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NQT, int KT>
+__global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ unsigned long long full_bar[HB2_ADJT_NS], empty_bar[HB2_ADJT_NS];
+  __shared__ int s_ang[HB2_ADJT_MAXV];
+  __shared__ uint16_t s_jlo[HB2_ADJT_MAXV], s_nr[HB2_ADJT_MAXV];
+  const LsmrState& S = B.st[c];
+  bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
+                                 : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
+  const int pi = c * B.part_v_per_cand + blockIdx.x;
+  if (!act) {
+    if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
+    return;
+  }
+  constexpr int L3P = 4 * NQT;
+  const int ndisk_t = B.tile_begin[tile + 1] - B.tile_begin[tile];
+  const int p = B.tile_begin[tile] + threadIdx.x;
+  const bool producer = threadIdx.x >= HB2_BLOCK;
+  const bool live = threadIdx.x < ndisk_t;
+  const unsigned rpv = (unsigned)B.rows_per_view;
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+  const int rmax = B.rmax;
+  // dynamic shared memory: [NS][SV][KT][256] map entries, then [NS][SV][rmax*L3P] row windows
+  uint16_t* s_map = reinterpret_cast<uint16_t*>(dsm);
+  float* s_u = reinterpret_cast<float*>(dsm + (size_t)HB2_ADJT_NS * HB2_ADJT_SV * KT * HB2_BLOCK * sizeof(uint16_t));
+  const int ustride = rmax * L3P;
+  for (int e = threadIdx.x; e < nv; e += HB2_ADJT_THREADS) {
+    const int a = B.view_angle[vb + e];
+    s_ang[e] = a;
+    s_jlo[e] = B.tile_jlo[(size_t)a * B.ntile + tile];
+    s_nr[e] = B.tile_nr[(size_t)a * B.ntile + tile];
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < HB2_ADJT_NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], HB2_BLOCK / 32); }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  const int nstage = (nv + HB2_ADJT_SV - 1) / HB2_ADJT_SV;
+  const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
+  const float beta = S.beta;
+  float acc[4 * NQT];
+#pragma unroll
+  for (int i = 0; i < 4 * NQT; ++i) acc[i] = 0.f;
+  if (producer) {
+    // producer warp: lane w of a stage loads view st*SV + w (K map runs of 512 bytes + the row window)
+    const float* __restrict__ ucand = B.u + B.cand_uoff[c];
+    const uint16_t* __restrict__ amt = B.amap + (size_t)tile * HB2_BLOCK;
+    const int w = threadIdx.x - HB2_BLOCK;
+    for (int st = 0; st < nstage; ++st) {
+      const int buf = st % HB2_ADJT_NS;
+      if (st >= HB2_ADJT_NS) mbar_wait(&empty_bar[buf], (unsigned)(((st / HB2_ADJT_NS) - 1) & 1));
+      const int v = st * HB2_ADJT_SV + w;
+      const bool has = w < HB2_ADJT_SV && v < nv;
+      const unsigned nr = has ? s_nr[v] : 0;
+      unsigned tot = has ? KT * HB2_BLOCK * (unsigned)sizeof(uint16_t) + nr * L3P * (unsigned)sizeof(float) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (w == 0) mbar_expect_tx(&full_bar[buf], tot);
+      __syncwarp();
+      if (has) {
+        const size_t arow = (size_t)s_ang[v] * KT * B.apitch;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          bulk_g2s(s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT + k) * HB2_BLOCK, amt + arow + (size_t)k * B.apitch,
+                   HB2_BLOCK * (unsigned)sizeof(uint16_t), &full_bar[buf]);
+        if (nr)
+          bulk_g2s(s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride, ucand + ((size_t)v * rpv + (size_t)s_jlo[v] * L3P),
+                   nr * L3P * (unsigned)sizeof(float), &full_bar[buf]);
+      }
+    }
+  } else {
+    for (int st = 0; st < nstage; ++st) {
+      const int buf = st % HB2_ADJT_NS;
+      mbar_wait(&full_bar[buf], (unsigned)((st / HB2_ADJT_NS) & 1));
+      if (live) {
+        const int nvs = min(HB2_ADJT_SV, nv - st * HB2_ADJT_SV);
+#pragma unroll
+        for (int w = 0; w < HB2_ADJT_SV; ++w) {
+          if (w < nvs) {
+            const uint16_t* mp = s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT) * HB2_BLOCK + threadIdx.x;
+            const float* uw = s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride;
+            const int jl = s_jlo[st * HB2_ADJT_SV + w];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+              const unsigned j = mp[(size_t)k * HB2_BLOCK];
+              if (j != 0xFFFFu) {
+                const float4* r = reinterpret_cast<const float4*>(uw + ((int)j - jl) * L3P);
+#pragma unroll
+                for (int q4 = 0; q4 < NQT; ++q4) {
+                  const float4 t = r[q4];
+                  acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
+                  acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[buf]);  // this warp is done with the stage's buffers
+    }
+  }
+  float ss = 0.f;
+  if (live && !producer) {
+    const int L3 = B.L3;
+    const int g0 = p * L3P;
+    const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
+    const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
+    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + g0;
+#pragma unroll
+    for (int q4 = 0; q4 < NQT; ++q4) {
+      int ev[HB2_ELL_W][4];
+#pragma unroll
+      for (int w = 0; w < HB2_ELL_W; ++w) {
+        const int4 e4 = __ldg(reinterpret_cast<const int4*>(ell + (size_t)w * B.npad) + q4);
+        ev[w][0] = e4.x; ev[w][1] = e4.y; ev[w][2] = e4.z; ev[w][3] = e4.w;
+      }
+      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
+      float vals[HB2_ELL_W][4];
+#pragma unroll
+      for (int w = 0; w < HB2_ELL_W; ++w)
+#pragma unroll
+        for (int tz = 0; tz < 4; ++tz) {
+          const bool ok = ev[w][tz] < 0 || ev[w][tz] < HB2_ELL_OVERFLOW;  // a real entry (either sign)
+          vals[w][tz] = ok ? __ldg(us + (ev[w][tz] & 0x7fffffff)) : 0.f;
+        }
+      float vn[4];
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        float s2 = acc[4 * q4 + tz];
+        if (ev[HB2_ELL_W - 1][tz] == HB2_ELL_OVERFLOW) {  // long list: walk the CSR copy
+          const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1) + g0 + 4 * q4 + tz;
+          const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
+          for (int e = ptr[0]; e < ptr[1]; ++e) {
+            const int x = ent[e];
+            const float val = __ldg(us + (x & 0x7fffffff));
+            s2 = fmaf(x < 0 ? -val : val, ib, s2);
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < HB2_ELL_W; ++w)
+            if (ev[w][tz] != HB2_ELL_NONE) s2 = fmaf(ev[w][tz] < 0 ? -vals[w][tz] : vals[w][tz], ib, s2);
+        }
+        const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
+        vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), s2) : s2;
+        ss += vn[tz] * vn[tz];
+      }
+      *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+    }
+    (void)L3;
+  }
+  if (mode != MODE_PLAIN) {  // 9 warps: the producer warp only joins the barrier
+    ss = warp_sum(ss);
+    if (!producer && (threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < HB2_BLOCK / 32; ++w) tot += red[w];
+      B.part_v[pi] = tot;
+    }
   }
 }
 

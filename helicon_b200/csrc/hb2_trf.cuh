@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* _
   const int t = blockIdx.x * HB2_BLOCK + threadIdx.x;
   const int p = t / NQ, q = t - p * NQ;
   if (p >= ndisk) return;
+  const int slot = B.aslot[p];
   const int z0 = 4 * q;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* _
     const int view = vb + vi;
     const int a = __ldg(B.view_angle + view);
     const double* __restrict__ ub = rows + __ldg(B.view_uoff + view) + z0 * MC;
-    const uint16_t* __restrict__ am = B.amap + (size_t)a * K * B.apitch + p;
+    const uint16_t* __restrict__ am = B.amap + (size_t)a * K * B.apitch + slot;
     for (int k = 0; k < K; ++k) {
       const uint16_t j = am[(size_t)k * B.apitch];
       if (j != 0xFFFFu) {
