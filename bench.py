@@ -334,23 +334,29 @@ def main():
     per_rank = args.batch
     n_tw = max(1, per_rank // N_RISE) * args.e2e_batches  # twists per search_grid call and rank
     launches_e2e = 0
+    from helicon_b200.distributed import gather_grid_results
+
     for s in range(2):
-        bi = ((args.warmup + args.steps) * world + (2 * rank + s) * args.e2e_batches) * per_rank
-        tw_idx = [(bi // N_RISE + q) % N_TWIST for q in range(n_tw)]
+        # every rank is handed the same twist list (world x the per-rank share) and solves its round-robin shard;
+        # the score tiles and local top-K are all-gathered (NCCL) inside the timed region
+        bi = (args.warmup + args.steps) * world * per_rank + s * n_tw * world * N_RISE
+        tw_idx = [(bi // N_RISE + q) % N_TWIST for q in range(n_tw * world)]
         barrier()
         t0 = time.perf_counter()
         out = search_grid(np.array(img, copy=True), APIX, TWISTS[tw_idx], RISES, positive_constraint=args.positive,
-                          device=local_rank, stream=stream, batch_candidates=per_rank, pipelined=not args.no_pipeline)
-        allsc = gather_scores(np.nan_to_num(out["scores"].ravel().astype(np.float32), nan=-1.0))
-        best = float(allsc.max().item())  # device->host read of the step's result
+                          device=local_rank, stream=stream, batch_candidates=per_rank, pipelined=not args.no_pipeline,
+                          shard=(rank, world))
+        launches_local = out["launches"]
+        out = gather_grid_results(out, top_k=10, dist=dist, device="cuda")
+        best = float(np.nanmax(out["scores"]))  # host read of the step's result
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device="cuda")
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if s > 0:
-            e2e_vals.append(out["n_candidates"] * world / float(tt.item()))
-            launches_e2e = out["launches"]
+            e2e_vals.append(out["n_candidates"] / float(tt.item()))
+            launches_e2e = launches_local
     e2e_val = float(np.mean(e2e_vals))
     d2h = int(out["scores"].size * 4 + out["itn"].size * 4)
 
@@ -378,7 +384,7 @@ def main():
                     mean_lsmr_iterations=itn_sum / max(1, ncand)),
         clocks=clocks, gpu_launches=int(launches),
         e2e=dict(value=e2e_val, unit="candidates/s", h2d_bytes_per_step=int(e2e_bytes_in), d2h_bytes_per_step=d2h,
-                 candidates_per_call=int(out["n_candidates"]),
+                 candidates_per_call=int(out["n_candidates"]), best_score=best,
                  note="search_grid(): host image -> Problem upload, host planning, solve, scores copied back; bytes are per "
                       "search_grid() call"),
         roofline=dict(bound="hbm", kernel="k_fwd_data (forward projector u <- A v - alpha u)", achieved=achieved,

@@ -1,0 +1,85 @@
+"""world_size-2 gloo test of the multi-GPU host logic (sharding + score/top-K all-gather).
+No CUDA: the per-rank solve is replaced by a deterministic fake score."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.multiprocessing as mp  # noqa: E402
+
+from helicon_b200 import distributed as D  # noqa: E402
+from helicon_b200.grid import build_tasks  # noqa: E402
+
+
+def _fake_local(rank, world, twists, rises):
+    tasks, ntot = build_tasks(64, 64, 5.0, twists, rises, csyms=(1,), reconstruct_length_rise=3)
+    mine = D.shard_tasks(tasks, rank, world)
+    scores = np.full(ntot, np.nan, np.float32)
+    itn = np.zeros(ntot, np.int32)
+    flags = np.zeros(ntot, np.uint32)
+    for t in mine:
+        scores[t.ti] = np.float32(np.cos(0.37 * t.ti) * 0.5 + 0.5)
+        itn[t.ti] = 100 + t.ti % 7
+        flags[t.ti] = t.ti % 3
+    top = sorted((dict(score=float(scores[t.ti]), ti=t.ti, twist=t.twist, rise=t.rise, csym=t.csym) for t in mine),
+                 key=lambda e: (-e["score"], e["ti"]))[:5]
+    shape = (1, len(twists), len(rises))
+    return dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
+                n_candidates=len(mine)), tasks
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    twists = np.linspace(-3.0, 3.0, 13)  # includes |twist| < 0.01 -> skipped task (NaN on every rank)
+    rises = np.linspace(4.0, 6.0, 5)
+    out, tasks = _fake_local(rank, world, twists, rises)
+    res = D.gather_grid_results(out, top_k=5, dist=dist)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, res["scores"], res["itn"], res["flags"], [(e["score"], e["ti"]) for e in res["top"]], res["n_candidates"]))
+
+
+def test_two_rank_gather_equals_single_process():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    twists = np.linspace(-3.0, 3.0, 13)
+    rises = np.linspace(4.0, 6.0, 5)
+    ref, tasks = _fake_local(0, 1, twists, rises)
+    ref = D.gather_grid_results(ref, top_k=5, dist=None)
+    for rank, scores, itn, flags, top, ncand in got:
+        assert np.array_equal(np.isnan(scores), np.isnan(ref["scores"]))
+        assert np.array_equal(np.nan_to_num(scores), np.nan_to_num(ref["scores"]))
+        assert np.array_equal(itn, ref["itn"]) and np.array_equal(flags, ref["flags"])
+        assert top == [(e["score"], e["ti"]) for e in ref["top"]]
+        assert ncand == len(tasks)
+    # the skipped tasks (|twist| < 0.01) are NaN everywhere
+    assert np.isnan(ref["scores"]).sum() == 5
+
+
+def test_shards_are_disjoint_and_cover():
+    tasks, ntot = build_tasks(64, 64, 5.0, np.linspace(-2, -1, 7), np.linspace(4, 5, 3))
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            seen += [t.ti for t in D.shard_tasks(tasks, r, world)]
+        assert sorted(seen) == [t.ti for t in tasks]
+        sizes = [len(D.shard_tasks(tasks, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
