@@ -51,6 +51,7 @@ struct hb2_problem {
   std::vector<int> h_rank_data;    // reference disk rank (C-order np.nonzero) on the data grid, for exports
   std::vector<int> int2ref, ref2int;  // internal (tile-major) disk rank <-> reference rank
   std::vector<int> h_tile_begin;      // [ntile+1] first internal rank of every non-empty voxel tile
+  std::vector<int> h_tilerow_begin;   // [ntilerow+1] first internal rank of every row of tiles
   int ntile = 0;
   bool tile_ok = false;               // tiles hold <= 256 voxels (k_adj_tile)
   int* d_tile_begin = nullptr;
@@ -94,6 +95,9 @@ struct hb2_batch {
   BD B{};
   bool idx16 = true;
   size_t adj_tile_smem = 0;
+  size_t fwd_band_smem = 0;
+  long long extra_launches = 0;  // kernels beyond one per launch_* call (band path: projector + reduce)
+  int max_views = 0;
   bool created = false;
   int nviews = 0;
   // host copies
@@ -184,7 +188,7 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
 // (profiles/r1: with row-major ranks every CTA touched (1 + 256|sin|) rows per view).  Reference order is kept for
 // everything exported and for the enumeration order of the symmetry rows.
 static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref, std::vector<int>& tile_begin,
-                       bool& tile_ok) {
+                       std::vector<int>& tilerow_begin, bool& tile_ok) {
   static int TH = -1, TW = -1;
   if (TH < 0) {
     const char* eh = getenv("HB2_TILE_H"); const char* ew = getenv("HB2_TILE_W");
@@ -203,6 +207,10 @@ static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2
   for (size_t i = 0; i < int2ref.size(); ++i)
     if (i == 0 || tkey(int2ref[i]) != tkey(int2ref[i - 1])) tile_begin.push_back((int)i);
   tile_begin.push_back((int)int2ref.size());
+  tilerow_begin.clear();
+  for (size_t i = 0; i < int2ref.size(); ++i)
+    if (i == 0 || tkey(int2ref[i]).first != tkey(int2ref[i - 1]).first) tilerow_begin.push_back((int)i);
+  tilerow_begin.push_back((int)int2ref.size());
 }
 
 extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const hb2_geometry* g, int device, void* stream) {
@@ -237,10 +245,10 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   P->ndisk = (int)yd.size();
   P->h_rank_data = rd;
   {
-    std::vector<int> i2r_sym, tb_sym;
+    std::vector<int> i2r_sym, tb_sym, tr_sym;
     bool ok_sym;
-    tile_order(yd, P->int2ref, P->h_tile_begin, P->tile_ok);
-    tile_order(ys, i2r_sym, tb_sym, ok_sym);
+    tile_order(yd, P->int2ref, P->h_tile_begin, P->h_tilerow_begin, P->tile_ok);
+    tile_order(ys, i2r_sym, tb_sym, tr_sym, ok_sym);
     P->ntile = (int)P->h_tile_begin.size() - 1;
     if (i2r_sym != P->int2ref) {
       delete P;
@@ -554,6 +562,47 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     B.part_v_per_cand = B.adj_tile ? B.ntile : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
   }
   B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
+  // ---- forward band path: bands of tile-rows that fit shared memory, ray segments per (angle, band) -------------
+  B.fwd_band = 0; B.fwd_ppv = ntiles; B.nband = 0;
+  {
+    int max_views = 0;
+    for (int c = 0; c < nc; ++c) max_views = std::max(max_views, b->h_view_count[c]);
+    b->max_views = max_views;
+    // The band path is correct (tests run it with HB2_FWD_BAND=1) but measured slower than the gather kernel on
+    // cfg2 (24 vs 18 us per candidate-pass, profiles/r1_summary.md: issue-bound on the per-ray lane reduction and
+    // +11 MB of partial-sum traffic), so it is opt-in until the lane-per-ray variant lands.
+    const char* use_band = getenv("HB2_FWD_BAND");
+    const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)sizeof(float));
+    std::vector<int> bands{0};
+    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && (use_band && atoi(use_band));
+    const std::vector<int>& tr = P->h_tilerow_begin;
+    for (size_t r = 0; ok && r + 1 < tr.size(); ++r) {
+      if (tr[r + 1] - tr[r] > cap) { ok = false; break; }
+      if (tr[r + 1] - bands.back() > cap) bands.push_back(tr[r]);
+    }
+    bands.push_back(B.ndisk);
+    const int NB = (int)bands.size() - 1;
+    if (ok && NB <= HB2_MAX_BANDS) {
+      int max_bn = 0;
+      for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
+      b->fwd_band_smem = (size_t)max_bn * B.L3P * sizeof(float);
+      CKC(upload(b->pool, &B.band_begin, bands, st));
+      ushort2 *d_seg, *d_rng;
+      CKC(b->pool.alloc(&d_seg, (size_t)B.nA * NB * D2, false, st));
+      CKC(b->pool.alloc(&d_rng, (size_t)B.nA * NB, false, st));
+      const long long nt = (long long)B.nA * NB * D2;
+      if (b->idx16) k_band_segs<uint16_t><<<cdiv(nt, 256), 256, 0, st>>>(B.nA, NB, D2, B.band_begin, (const uint16_t*)b->d_fmap, d_seg);
+      else k_band_segs<uint32_t><<<cdiv(nt, 256), 256, 0, st>>>(B.nA, NB, D2, B.band_begin, (const uint32_t*)b->d_fmap, d_seg);
+      k_band_rng<<<dim3(NB, B.nA), HB2_BLOCK, 0, st>>>(NB, D2, d_seg, d_rng);
+      CKL();
+      std::vector<long long> poff(nc);
+      long long po = 0;
+      for (int c = 0; c < nc; ++c) { poff[c] = po; po += (long long)b->h_view_count[c] * NB * D2 * B.L3P; }
+      CKC(upload(b->pool, &B.cand_poff, poff, st));
+      CKC(b->pool.alloc(&B.fwd_part, (size_t)std::max<long long>(po, 1), false, st));
+      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = 1; B.fwd_ppv = 1;
+    }
+  }
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
   CKC(b->pool.alloc(&B.part_us, (size_t)nc * B.part_us_per_cand, true, st));
   CKC(b->pool.alloc(&B.part_v, (size_t)nc * B.part_v_per_cand, true, st));
@@ -731,14 +780,28 @@ struct ProfScope {
 static void launch_fwd_data(hb2_batch* b, int mode) {
   ProfScope ps(b, KC_FWD_DATA);
   const BD& B = b->B;
+  cudaStream_t st = b->stream;
+  if (b->nviews == 0) return;
+  if (B.fwd_band) {
+    const size_t sm = b->fwd_band_smem;
+    const dim3 gb(B.nband, B.nc), gr(b->max_views, B.nc);
+#define FWB(T, Q)                                                                                         \
+  do {                                                                                                    \
+    cudaFuncSetAttribute(k_fwd_band<T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);         \
+    k_fwd_band<T, Q><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, mode);                                          \
+    k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
+  } while (0)
+#define FWBQ(T) do { if (B.L3P == 4) FWB(T, 1); else if (B.L3P == 8) FWB(T, 2); else if (B.L3P == 12) FWB(T, 3); else FWB(T, 4); } while (0)
+    if (b->idx16) FWBQ(uint16_t); else FWBQ(uint32_t);
+    b->extra_launches += 1;
+#undef FWBQ
+#undef FWB
+    return;
+  }
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   unsigned grid = (unsigned)b->nviews * ntiles;
-  cudaStream_t st = b->stream;
-  if (grid == 0) return;
   if (b->idx16) k_fwd_data<uint16_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
   else k_fwd_data<uint32_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
-#define FWD
-#undef FWD
 }
 static void launch_fwd_sym(hb2_batch* b, int mode) {
   ProfScope ps(b, KC_FWD_SYM);
@@ -977,6 +1040,7 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   CK(cudaMemcpyAsync(B.u, B.b, sizeof(float) * (size_t)b->u_total, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemsetAsync(b->d_nactive, 0, sizeof(int), st));
   long long launches = 0;
+  b->extra_launches = 0;
   k_scal_normb<<<nc, HB2_BLOCK, 0, st>>>(B);
   launch_adj(b, MODE_INIT);
   k_scal_init<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_nactive);
@@ -1036,7 +1100,7 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   cudaEventElapsedTime(&ms_l, e0, e1); cudaEventElapsedTime(&ms_t, e1, e1b); cudaEventElapsedTime(&ms_s, e1b, e2);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e1b); cudaEventDestroy(e2);
   for (double& t : b->timing) t = 0;
-  b->timing[0] = ms_l; b->timing[1] = ms_t; b->timing[2] = ms_s; b->timing[13] = trf_outer; b->timing[3] = (double)launches; b->timing[4] = it;
+  b->timing[0] = ms_l; b->timing[1] = ms_t; b->timing[2] = ms_s; b->timing[13] = trf_outer; b->timing[3] = (double)(launches + b->extra_launches); b->timing[4] = it;
   if (b->profiling) {
     for (auto& pr : b->ev_used) {
       float ms = 0;

@@ -68,6 +68,15 @@ struct BD {
   double* part_x;
   float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
   int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
+  // forward band path (k_fwd_band + k_fwd_band_reduce)
+  int fwd_band;                // 1: use it (MC == 1, bands fit shared memory)
+  int nband;
+  const int* band_begin;       // [nband+1] first internal rank of every band of voxel tile-rows
+  const ushort2* band_seg;     // [nA][nband][D2] sample range [ilo, ihi) of ray j inside the band (ilo == ihi: none)
+  const ushort2* band_rng;     // [nA][nband] rays [jlo, jhi) crossing the band
+  float* fwd_part;             // per candidate [view][band][D2][ZMP] partial ray sums
+  const long long* cand_poff;  // offset of the candidate's partials in fwd_part
+  int fwd_ppv;                 // norm/score partials per view (1 on the band path, ceil(D2/32) otherwise)
   int adj_fast;    // MC == 1, K <= 2, row offsets fit 32 bits: k_adj_pq
   int adj_tile;    // additionally L3P <= 16, <= 256 views per candidate, windows fit shared memory: k_adj_tile
   int only_cand;   // MODE_PLAIN: restrict to one candidate (-1 all)
@@ -117,6 +126,35 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
   }
   __syncthreads();
   return r;
+}
+
+// ---------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk) + mbarrier helpers (sm_90+/sm_100a PTX)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(unsigned saddr) {
+  float4 r;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ===========================================================================
@@ -551,6 +589,252 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   }
 }
 
+// ===========================================================================
+// forward projector, band path.  profiles/r1_summary.md: the gather kernel above
+// re-reads v from L2 for every view (186 MB per candidate-pass, 8.5 TB/s at the
+// L2 port) and sits at ~80 % of the L1 wavefront rate.  Here a CTA keeps a BAND
+// of the candidate's voxels -- whole tile-rows of the tile-major voxel order,
+// i.e. one contiguous block of v, <= ~200 KB -- in shared memory (TMA bulk
+// copy) and applies ALL views to it: every ray of every view that crosses the
+// band contributes one partial sum (its samples inside the band, gathered from
+// shared memory with conflict-light 128-bit loads); k_fwd_band_reduce adds a
+// ray's partials over the bands it crosses, in band order, and applies the
+// LSMR row update / the score accumulation.  v leaves L2 once per pass.
+// Lanes of a warp: SPW = 32/NQ consecutive samples of one ray x NQ slice quads.
+// ===========================================================================
+#define HB2_FWDB_THREADS 1024
+#define HB2_FWDB_RU 4        // rays processed together by a warp
+#define HB2_FWDB_SU 3        // steps of those rays whose map loads are issued together
+#define HB2_FWDB_MAXV 256
+#define HB2_MAX_BANDS 32
+
+// sample range of every ray inside every band (setup): one thread per (angle, band, ray)
+template <typename IdxT>
+__global__ void k_band_segs(int nA, int nband, int D2, const int* __restrict__ band_begin, const IdxT* __restrict__ fmap,
+                            ushort2* __restrict__ seg) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nA * nband * D2) return;
+  const int j = (int)(t % D2), b = (int)((t / D2) % nband), a = (int)(t / ((long long)D2 * nband));
+  const unsigned bb = (unsigned)band_begin[b], bn = (unsigned)band_begin[b + 1] - bb;
+  const IdxT* __restrict__ fj = fmap + ((size_t)a * D2 + j) * D2;
+  int lo = D2, hi = 0;
+  for (int i = 0; i < D2; ++i) {
+    const unsigned rel = (unsigned)fj[i] - bb;
+    if (fj[i] != Sent<IdxT>::v && rel < bn) { lo = min(lo, i); hi = i + 1; }
+  }
+  seg[t] = hi > lo ? make_ushort2((unsigned short)lo, (unsigned short)hi) : make_ushort2(0, 0);
+}
+// rays crossing every band (setup): one CTA per (band, angle)
+__global__ void __launch_bounds__(HB2_BLOCK) k_band_rng(int nband, int D2, const ushort2* __restrict__ seg,
+                                                       ushort2* __restrict__ rng) {
+  const int b = blockIdx.x, a = blockIdx.y;
+  __shared__ int s_lo, s_hi;
+  if (threadIdx.x == 0) { s_lo = D2; s_hi = 0; }
+  __syncthreads();
+  const ushort2* sg = seg + ((size_t)a * nband + b) * D2;
+  for (int j = threadIdx.x; j < D2; j += HB2_BLOCK)
+    if (sg[j].y > sg[j].x) { atomicMin(&s_lo, j); atomicMax(&s_hi, j + 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) rng[(size_t)a * nband + b] = s_hi > s_lo ? make_ushort2((unsigned short)s_lo, (unsigned short)s_hi) : make_ushort2(0, 0);
+}
+
+template <typename IdxT, int NQ>
+__global__ void __launch_bounds__(HB2_FWDB_THREADS, 1) k_fwd_band(BD B, int mode) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  float* tile = reinterpret_cast<float*>(dsm);
+  __shared__ unsigned long long bar;
+  __shared__ int s_pref[HB2_FWDB_MAXV + 1];
+  __shared__ unsigned short s_jlo[HB2_FWDB_MAXV], s_cnt[HB2_FWDB_MAXV];
+  __shared__ int s_ang[HB2_FWDB_MAXV];
+  const int c = blockIdx.y, b = blockIdx.x;
+  const LsmrState& S = B.st[c];
+  const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  if (!act) return;
+  constexpr int L3P = 4 * NQ;
+  constexpr int SPW = 32 / NQ;                       // samples per warp step
+  constexpr int P2 = SPW > 16 ? 16 : (SPW > 8 ? 8 : (SPW > 4 ? 4 : (SPW > 2 ? 2 : 1)));  // largest power of 2 < SPW
+  const int D2 = B.D2, NB = B.nband;
+  const unsigned bb = (unsigned)B.band_begin[b], bn = (unsigned)B.band_begin[b + 1] - bb;
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+  const float* __restrict__ vsrc = (mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad + (size_t)bb * L3P;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  for (int e = threadIdx.x; e < nv; e += HB2_FWDB_THREADS) {
+    const int a = B.view_angle[vb + e];
+    const ushort2 r = B.band_rng[(size_t)a * NB + b];
+    s_ang[e] = a; s_jlo[e] = r.x; s_cnt[e] = (unsigned short)(r.y - r.x); s_pref[e + 1] = ((int)r.y - (int)r.x + 31) / 32;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // warp 0: TMA bulk load of the band (32 KB pieces), then the prefix over views
+    const unsigned total = bn * L3P * (unsigned)sizeof(float);
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, total);
+    __syncwarp();
+    const unsigned piece = 32768u;
+    for (unsigned off = threadIdx.x * piece; off < total; off += 32u * piece)
+      bulk_g2s(dsm + off, reinterpret_cast<const unsigned char*>(vsrc) + off, min(piece, total - off), &bar);
+    if (threadIdx.x == 0) {
+      s_pref[0] = 0;
+      for (int e = 0; e < nv; ++e) s_pref[e + 1] += s_pref[e];
+    }
+  }
+  __syncthreads();
+  const int total_items = s_pref[nv];
+  mbar_wait(&bar, 0u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sl = lane / NQ, q = lane - sl * NQ;
+  const bool lane_on = sl < SPW;
+  float* __restrict__ part = B.fwd_part + B.cand_poff[c];
+  const unsigned tile_s = smem_u32(tile) + 16u * (unsigned)q;  // 32-bit shared address of this lane's quad in voxel 0
+  // A warp item = 32 consecutive rays of one view: their sample ranges arrive with ONE coalesced load, then the
+  // rays are processed HB2_FWDB_RU at a time (independent map loads / shared-memory gathers in flight).
+  int vcur = 0;
+  for (int it = warp; it < total_items; it += HB2_FWDB_THREADS / 32) {
+    while (it >= s_pref[vcur + 1]) ++vcur;
+    const int a = s_ang[vcur];
+    const int jbase = (int)s_jlo[vcur] + 32 * (it - s_pref[vcur]);
+    const int nray = min(32, (int)s_jlo[vcur] + s_cnt[vcur] - jbase);
+    const ushort2* __restrict__ segp = B.band_seg + ((size_t)a * NB + b) * D2 + jbase;
+    const ushort2 mysg = lane < nray ? __ldg(segp + lane) : make_ushort2(0, 0);
+    const IdxT* __restrict__ fbase = (const IdxT*)B.fmap + ((size_t)a * D2 + jbase) * D2;
+    float* __restrict__ pbase = part + (((size_t)vcur * NB + b) * D2 + jbase) * L3P + 4 * q;
+    for (int r0 = 0; r0 < nray; r0 += HB2_FWDB_RU) {
+      // per ray: 32-bit element offset of this lane's next sample in the map and the samples it still has to visit
+      const IdxT* fp[HB2_FWDB_RU];
+      int rem[HB2_FWDB_RU];
+      float4 acc[HB2_FWDB_RU];
+      int tmax = 0;
+#pragma unroll
+      for (int u = 0; u < HB2_FWDB_RU; ++u) {
+        const int src = min(r0 + u, 31);
+        const int lo = __shfl_sync(0xffffffffu, (int)mysg.x, src), hi = __shfl_sync(0xffffffffu, (int)mysg.y, src);
+        const int len = (r0 + u < nray) ? hi - lo : 0;
+        fp[u] = fbase + (unsigned)((r0 + u) * D2 + lo + sl);
+        rem[u] = lane_on ? len - sl : 0;
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tmax = max(tmax, (len + SPW - 1) / SPW);
+      }
+#pragma unroll 1
+      for (int t = 0; t < tmax; t += HB2_FWDB_SU) {
+        // HB2_FWDB_SU steps of HB2_FWDB_RU rays: RU*SU independent map loads, then their shared-memory gathers
+        unsigned rel[HB2_FWDB_SU][HB2_FWDB_RU];
+#pragma unroll
+        for (int w = 0; w < HB2_FWDB_SU; ++w)
+#pragma unroll
+          for (int u = 0; u < HB2_FWDB_RU; ++u) {
+            rel[w][u] = 0xFFFFFFFFu;
+            if (rem[u] > w * SPW) rel[w][u] = (unsigned)fp[u][w * SPW] - bb;
+          }
+#pragma unroll
+        for (int u = 0; u < HB2_FWDB_RU; ++u) { fp[u] += HB2_FWDB_SU * SPW; rem[u] -= HB2_FWDB_SU * SPW; }
+#pragma unroll
+        for (int w = 0; w < HB2_FWDB_SU; ++w)
+#pragma unroll
+          for (int u = 0; u < HB2_FWDB_RU; ++u) {
+            if (rel[w][u] < bn) {
+              const float4 tv = lds128(tile_s + rel[w][u] * (unsigned)(L3P * sizeof(float)));
+              acc[u].x += tv.x; acc[u].y += tv.y; acc[u].z += tv.z; acc[u].w += tv.w;
+            }
+          }
+      }
+      // combine the SPW sample lanes of every quad (fixed tree), one ray after the other
+#pragma unroll
+      for (int u = 0; u < HB2_FWDB_RU; ++u) {
+        int n = SPW;
+#pragma unroll
+        for (int off = P2; off >= 1; off >>= 1) {
+          const float x = __shfl_down_sync(0xffffffffu, acc[u].x, off * NQ), y = __shfl_down_sync(0xffffffffu, acc[u].y, off * NQ);
+          const float z = __shfl_down_sync(0xffffffffu, acc[u].z, off * NQ), w = __shfl_down_sync(0xffffffffu, acc[u].w, off * NQ);
+          if (sl + off < n) { acc[u].x += x; acc[u].y += y; acc[u].z += z; acc[u].w += w; }
+          n = off;
+        }
+        if (sl == 0 && r0 + u < nray) *reinterpret_cast<float4*>(pbase + (size_t)(r0 + u) * L3P) = acc[u];
+      }
+    }
+  }
+}
+
+// sum of a ray's partials over the bands it crosses (band order) + the row epilogue of k_fwd_data.
+// One CTA per (view of the candidate, candidate).
+template <int NQ>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_band_reduce(BD B, int mode) {
+  const int c = blockIdx.y, vi = blockIdx.x;
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ ushort2 s_rng[HB2_MAX_BANDS];
+  __shared__ int s_colk[16];
+  const LsmrState& S = B.st[c];
+  const int nv = B.cand_view_count[c];
+  const int view = B.cand_view_begin[c] + vi;
+  const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  const bool has = vi < nv;
+  if (!act || !has) {
+    if (threadIdx.x == 0 && has) {
+      if (mode == MODE_LSMR) B.part_u[view] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * view] = 0.f; B.part_s[3 * view + 1] = 0.f; B.part_s[3 * view + 2] = 0.f; }
+    }
+    return;
+  }
+  constexpr int L3P = 4 * NQ;
+  const int D2 = B.D2, NB = B.nband, L3 = B.L3;
+  const int a = B.view_angle[view];
+  if (threadIdx.x < NB) s_rng[threadIdx.x] = B.band_rng[(size_t)a * NB + threadIdx.x];
+  if (threadIdx.x < L3P) s_colk[threadIdx.x] = threadIdx.x < L3 ? B.colk[B.view_colbegin[view] + threadIdx.x] : -1;
+  __syncthreads();
+  const float alpha = S.alpha, inv_beta = S.inv_beta;
+  const float* __restrict__ part = B.fwd_part + B.cand_poff[c] + (size_t)vi * NB * D2 * L3P;
+  float* urow = B.u + B.view_uoff[view];
+  const float* brow = B.b + B.view_uoff[view];
+  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  for (int item = threadIdx.x; item < D2 * NQ; item += HB2_BLOCK) {
+    const int j = item / NQ, q = item - j * NQ;
+    if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int bq = 0; bq < NB; ++bq) {
+      const ushort2 r = s_rng[bq];
+      if (j >= (int)r.x && j < (int)r.y) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(part + ((size_t)bq * D2 + j) * L3P + 4 * q));
+        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+      }
+    }
+    const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+    const size_t r0 = (size_t)j * L3P + 4 * q;
+    if (mode == MODE_LSMR) {
+      float4 uo = *reinterpret_cast<const float4*>(urow + r0);
+      float un[4] = {uo.x, uo.y, uo.z, uo.w};
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        if (s_colk[4 * q + tz] >= 0) {
+          un[tz] = fadd_(fmul_(fmul_(un[tz], inv_beta), -alpha), sv[tz]);
+          ss += un[tz] * un[tz];
+        }
+      }
+      *reinterpret_cast<float4*>(urow + r0) = make_float4(un[0], un[1], un[2], un[3]);
+    } else if (mode == MODE_PLAIN) {
+      float4 uo = *reinterpret_cast<const float4*>(urow + r0);
+      float un[4] = {uo.x, uo.y, uo.z, uo.w};
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) if (s_colk[4 * q + tz] >= 0) un[tz] = sv[tz];
+      *reinterpret_cast<float4*>(urow + r0) = make_float4(un[0], un[1], un[2], un[3]);
+    } else {
+      const float4 bv4 = *reinterpret_cast<const float4*>(brow + r0);
+      const float bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        if (s_colk[4 * q + tz] >= 0) {
+          const float pred = B.clip_pred ? fmaxf(sv[tz], 0.f) : sv[tz];
+          ss += pred * pred; s_pb += pred * bv[tz]; s_bb += bv[tz] * bv[tz];
+        }
+      }
+    }
+  }
+  if (mode == MODE_LSMR) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_u[view] = tot;
+  } else if (mode == MODE_SCORE) {
+    float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
+    if (threadIdx.x == 0) { B.part_s[3 * view] = t0; B.part_s[3 * view + 1] = t1; B.part_s[3 * view + 2] = t2; }
+  }
+}
+
 // forward, symmetry rows: u~[r] <- (v[a]-v[b]) - alpha*(u~[r]*inv_beta)
 __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_sym(BD B, int mode) {
   const int c = blockIdx.y;
@@ -865,27 +1149,6 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_tile_rays(int K, int apitch, int 
 #define HB2_ADJT_NS 4      // stages in flight
 #define HB2_ADJT_THREADS (HB2_BLOCK + 32)  // 8 consumer warps (one thread per voxel) + 1 producer warp
 #define HB2_ADJT_MAXV 256
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 template <int NQT, int KT>
 __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
   extern __shared__ __align__(128) unsigned char dsm[];
@@ -1147,7 +1410,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_scal_beta(BD B) {
   __shared__ double shd[HB2_BLOCK / 32];
   LsmrState& S = B.st[c];
   if (!S.active) return;
-  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  const int ntiles = B.fwd_ppv;
   double s = reduce_partials_f(B.part_u + (size_t)B.cand_view_begin[c] * ntiles, B.cand_view_count[c] * ntiles, shd);
   s += reduce_partials_f(B.part_us + (size_t)c * B.part_us_per_cand, B.part_us_per_cand, shd);
   if (threadIdx.x == 0) {
@@ -1189,7 +1452,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_scal_test(BD B, double atol, doub
 __global__ void __launch_bounds__(HB2_BLOCK) k_scal_score(BD B, float* __restrict__ score) {
   const int c = blockIdx.x;
   __shared__ double shd[HB2_BLOCK / 32];
-  const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
+  const int ntiles = B.fwd_ppv;
   const int n = B.cand_view_count[c] * ntiles;
   const float* p = B.part_s + (size_t)B.cand_view_begin[c] * ntiles * 3;
   double d = 0, pp = 0, bb = 0;
