@@ -1321,6 +1321,9 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
 // vector update (lsmr.py:364-368) fused with v normalisation and ||x||^2
 // ===========================================================================
 __global__ void __launch_bounds__(HB2_BLOCK) k_update(BD B, int mode) {
+  // npad is a multiple of 4: every thread moves 4 consecutive elements with 128-bit accesses
+  // (v, h: one float4 each; x, hbar: two double2 each) -- the kernel is a pure HBM stream (44 n bytes);
+  // profiles/r1_summary.md: 4.5 -> 6.6 TB/s against scalar accesses.
   const int c = blockIdx.y;
   __shared__ double redd[HB2_BLOCK / 32];
   const LsmrState& S = B.st[c];
@@ -1333,26 +1336,43 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_update(BD B, int mode) {
   const double cfhb = (double)S.cf_hbar, cfx = (double)S.cf_x;
   const float cfh = S.cf_h;
   const bool normalise = !(mode == MODE_LSMR && S.skip_adj);
-  float* v = B.v + (size_t)c * B.npad;
-  float* h = B.h + (size_t)c * B.npad;
-  double* x = B.x + (size_t)c * B.npad;
-  double* hbar = B.hbar + (size_t)c * B.npad;
+  float4* v4 = reinterpret_cast<float4*>(B.v + (size_t)c * B.npad);
+  float4* h4 = reinterpret_cast<float4*>(B.h + (size_t)c * B.npad);
+  double2* x2 = reinterpret_cast<double2*>(B.x + (size_t)c * B.npad);
+  double2* hb2 = reinterpret_cast<double2*>(B.hbar + (size_t)c * B.npad);
+  const int n4 = B.npad >> 2;
   double sx = 0.0;
-  for (int i = blockIdx.x * HB2_BLOCK * 4 + threadIdx.x, q = 0; q < 4; ++q, i += HB2_BLOCK) {
-    if (i < B.npad) {
-      float vn = v[i];
-      if (normalise) { vn = fmul_(vn, ia); v[i] = vn; }
-      if (mode == MODE_INIT) {
-        h[i] = vn; hbar[i] = 0.0; x[i] = 0.0;
-      } else {
-        float ho = h[i];
-        double hb = dadd_(dmul_(hbar[i], cfhb), (double)ho);
-        hbar[i] = hb;
-        double xn = dadd_(x[i], dmul_(cfx, hb));
-        x[i] = xn;
-        h[i] = fadd_(fmul_(ho, cfh), vn);
-        sx += xn * xn;
+  const int i = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  if (i < n4) {
+    float4 vq = v4[i];
+    float vn[4] = {vq.x, vq.y, vq.z, vq.w};
+    if (normalise) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) vn[k] = fmul_(vn[k], ia);
+      v4[i] = make_float4(vn[0], vn[1], vn[2], vn[3]);
+    }
+    if (mode == MODE_INIT) {
+      h4[i] = make_float4(vn[0], vn[1], vn[2], vn[3]);
+      hb2[2 * i] = make_double2(0.0, 0.0); hb2[2 * i + 1] = make_double2(0.0, 0.0);
+      x2[2 * i] = make_double2(0.0, 0.0); x2[2 * i + 1] = make_double2(0.0, 0.0);
+    } else {
+      const float4 hq = h4[i];
+      const float ho[4] = {hq.x, hq.y, hq.z, hq.w};
+      const double2 b0 = hb2[2 * i], b1 = hb2[2 * i + 1];
+      const double2 x0 = x2[2 * i], x1 = x2[2 * i + 1];
+      double hb[4] = {b0.x, b0.y, b1.x, b1.y};
+      double xn[4] = {x0.x, x0.y, x1.x, x1.y};
+      float hn[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hb[k] = dadd_(dmul_(hb[k], cfhb), (double)ho[k]);
+        xn[k] = dadd_(xn[k], dmul_(cfx, hb[k]));
+        hn[k] = fadd_(fmul_(ho[k], cfh), vn[k]);
+        sx += xn[k] * xn[k];
       }
+      hb2[2 * i] = make_double2(hb[0], hb[1]); hb2[2 * i + 1] = make_double2(hb[2], hb[3]);
+      x2[2 * i] = make_double2(xn[0], xn[1]); x2[2 * i + 1] = make_double2(xn[2], xn[3]);
+      h4[i] = make_float4(hn[0], hn[1], hn[2], hn[3]);
     }
   }
   double tot = block_sum_d(sx, redd);
