@@ -55,6 +55,15 @@ class SolveOptions(C.Structure):
     ]
 
 
+class SymmParams(C.Structure):
+    _fields_ = [
+        ("nz0", C.c_int32), ("ny0", C.c_int32), ("nx0", C.c_int32), ("nz", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32),
+        ("oz", C.c_int32), ("oy", C.c_int32), ("ox", C.c_int32), ("nz1", C.c_int32), ("ny1", C.c_int32), ("nx1", C.c_int32),
+        ("apix", C.c_double), ("new_apix", C.c_double), ("csym", C.c_int32), ("n_ent", C.c_int32),
+        ("zs0", C.c_int32), ("zs1", C.c_int32),
+    ]
+
+
 class Result(C.Structure):
     _fields_ = [
         ("score", C.c_float), ("itn", C.c_int32), ("istop", C.c_int32), ("trf_nit", C.c_int32), ("flags", C.c_uint32),
@@ -82,7 +91,7 @@ EXPORTS = [
     "hb2_problem_ndisk", "hb2_problem_rank_table", "hb2_batch_begin", "hb2_batch_ray_valid", "hb2_batch_angle_map",
     "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_rows_padded", "hb2_batch_rhs",
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
-    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim",
+    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize",
 ]
 
 _lib = None
@@ -128,6 +137,7 @@ def load():
     lib.hb2_batch_get_x.argtypes = [vp, i32, vp]
     lib.hb2_batch_timing.argtypes = [vp, vp]
     lib.hb2_batch_trf_trace.argtypes = [vp, i32, vp, i32]
+    lib.hb2_helical_symmetrize.argtypes = [vp, P(SymmParams), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.c_int, vp]
     lib.hb2_lsmr_scalar_step.argtypes = [vp, C.c_int, C.c_float, C.c_float, f64, f64, f64, f64, C.c_int, P(C.c_float), P(C.c_float), P(C.c_float), vp]
     _lib = lib
     return lib

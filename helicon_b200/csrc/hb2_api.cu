@@ -2,6 +2,7 @@
 #include "../../include/helicon_b200.h"
 #include "hb2_kernels.cuh"
 #include "hb2_trf.cuh"
+#include "hb2_symm.cuh"
 
 #include <cub/cub.cuh>
 
@@ -1173,4 +1174,58 @@ extern "C" int hb2_lsmr_scalar_step(double* state64, int phase, float alpha, flo
     trace8[5] = S.test1; trace8[6] = S.test2; trace8[7] = S.active;
   }
   return ret;
+}
+
+// ---------------------------------------------------------------------------
+// post-solve display products (hb2_symm.cuh)
+// ---------------------------------------------------------------------------
+extern "C" int hb2_helical_symmetrize(const float* data_host, const hb2_symm_params* p, const int64_t* k_begin,
+                                      const int32_t* ent_h, const int32_t* ent_floor, const int32_t* ent_ceil,
+                                      const double* ent_wk, const double* mats, int32_t n_mats, float* vol_out_host,
+                                      float* xsum_out, float* ysum_out, float* zsum_out, int device, void* stream) {
+  if (!data_host || !p || !k_begin || !mats) return fail(HB2_ERR_ARG, "null argument");
+  if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
+  if (p->nz1 <= 0 || p->ny1 <= 0 || p->nx1 <= 0 || p->csym <= 0 || p->n_ent < 0) return fail(HB2_ERR_ARG, "bad sizes");
+  if (p->zs0 < 0 || p->zs1 > p->nz1) return fail(HB2_ERR_ARG, "z-section slab outside the output");
+  CK(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  SymmP P{};
+  P.nz0 = p->nz0; P.ny0 = p->ny0; P.nx0 = p->nx0; P.nz = p->nz; P.ny = p->ny; P.nx = p->nx;
+  P.oz = p->oz; P.oy = p->oy; P.ox = p->ox; P.nz1 = p->nz1; P.ny1 = p->ny1; P.nx1 = p->nx1;
+  P.apix = p->apix; P.new_apix = p->new_apix; P.csym = p->csym; P.zs0 = p->zs0; P.zs1 = p->zs1;
+  for (int e = 0; e < p->n_ent; ++e)
+    if (ent_floor[e] < 0 || ent_ceil[e] >= p->nz0 || ent_h[e] < 0 || (long long)(ent_h[e] + 1) * p->csym > n_mats)
+      return fail(HB2_ERR_ARG, "entry table out of range");
+  DevPool pool;
+  const size_t nd = (size_t)p->nz0 * p->ny0 * p->nx0, nv = (size_t)p->nz1 * p->ny1 * p->nx1;
+  float *d_data, *d_vol, *d_x, *d_y, *d_z;
+  long long* d_kb; int *d_h, *d_f, *d_c; double *d_w, *d_m;
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { pool.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  CKS(pool.alloc(&d_data, nd, false, st)); CKS(pool.alloc(&d_vol, nv, false, st));
+  CKS(pool.alloc(&d_x, (size_t)p->nz1 * p->ny1, false, st)); CKS(pool.alloc(&d_y, (size_t)p->nz1 * p->nx1, false, st));
+  CKS(pool.alloc(&d_z, (size_t)p->ny1 * p->nx1, false, st));
+  CKS(pool.alloc(&d_kb, (size_t)p->nz1 + 1, false, st)); CKS(pool.alloc(&d_h, (size_t)p->n_ent, false, st));
+  CKS(pool.alloc(&d_f, (size_t)p->n_ent, false, st)); CKS(pool.alloc(&d_c, (size_t)p->n_ent, false, st));
+  CKS(pool.alloc(&d_w, (size_t)p->n_ent, false, st)); CKS(pool.alloc(&d_m, (size_t)n_mats * 4, false, st));
+  CKS(cudaMemcpyAsync(d_data, data_host, nd * sizeof(float), cudaMemcpyHostToDevice, st));
+  CKS(cudaMemcpyAsync(d_kb, k_begin, ((size_t)p->nz1 + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  if (p->n_ent) {
+    CKS(cudaMemcpyAsync(d_h, ent_h, (size_t)p->n_ent * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(d_f, ent_floor, (size_t)p->n_ent * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(d_c, ent_ceil, (size_t)p->n_ent * sizeof(int), cudaMemcpyHostToDevice, st));
+    CKS(cudaMemcpyAsync(d_w, ent_wk, (size_t)p->n_ent * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  CKS(cudaMemcpyAsync(d_m, mats, (size_t)n_mats * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+  k_symm_volume<<<cdiv((long long)nv, 256), 256, 0, st>>>(P, d_data, d_kb, d_h, d_f, d_c, d_w, d_m, d_vol);
+  const long long nproj = (long long)p->nz1 * p->ny1 + (long long)p->nz1 * p->nx1 + (long long)p->ny1 * p->nx1;
+  k_symm_project<<<cdiv(nproj, 128), 128, 0, st>>>(P, d_vol, d_x, d_y, d_z);
+  CKS(cudaGetLastError());
+  if (vol_out_host) CKS(cudaMemcpyAsync(vol_out_host, d_vol, nv * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (xsum_out) CKS(cudaMemcpyAsync(xsum_out, d_x, (size_t)p->nz1 * p->ny1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (ysum_out) CKS(cudaMemcpyAsync(ysum_out, d_y, (size_t)p->nz1 * p->nx1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (zsum_out) CKS(cudaMemcpyAsync(zsum_out, d_z, (size_t)p->ny1 * p->nx1 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CKS(cudaStreamSynchronize(st));
+  pool.free_all();
+#undef CKS
+  return HB2_OK;
 }

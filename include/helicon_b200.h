@@ -196,6 +196,33 @@ int hb2_batch_trf_trace(hb2_batch* b, int32_t cand, double* out, int32_t max_row
 int hb2_lsmr_scalar_step(double* state64, int phase, float alpha, float beta, double normx, double atol, double btol,
                          double conlim, int maxiter, float* coef_hbar, float* coef_x, float* coef_h, double* trace8);
 
+/* ---- post-solve display products ------------------
+ * helicon.apply_helical_symmetry (lib/transforms.py:58-165) as called by
+ * pipeline.process_one_task (pipeline.py:405-427), plus the three sums the task
+ * keeps of the symmetrised volume (pipeline.py:435-447): np.sum(vol, axis=2),
+ * np.sum(vol, axis=1), np.sum(vol[zs0:zs1], axis=0) -- with numpy's summation
+ * order, so results are bit-identical.  The host plans the z entries exactly as
+ * the reference computes them (per OUTPUT slice k: the helical copies h whose
+ * source slice k2 lies in the unit's z window, floor/ceil(k2), k2 - floor(k2))
+ * and the 2x2 in-plane matrices of every (h, c); the kernels do the per-voxel
+ * trilinear gather in the reference's float64 operation order. */
+typedef struct {
+  int32_t nz0, ny0, nx0;   /* asymmetric unit (rec3d) */
+  int32_t nz, ny, nx;      /* working grid: max(unit, new_size) per axis (lib/transforms.py:74-80) */
+  int32_t oz, oy, ox;      /* crop offset of the output in the working grid (lib/transforms.py:157-163) */
+  int32_t nz1, ny1, nx1;   /* output size */
+  double apix, new_apix;
+  int32_t csym, n_ent;
+  int32_t zs0, zs1;        /* z-section slab in output slices (pipeline.py:443-446) */
+} hb2_symm_params;
+/* k_begin[nz1+1]: CSR over output slices into ent_*; ent_h indexes mats in blocks of csym
+ * (mats[(h*csym + c)*4 ..] = cos, sin, -sin, cos of deg2rad(twist*h + 360 c/csym)).
+ * Any of the four outputs may be NULL. */
+int hb2_helical_symmetrize(const float* data_host, const hb2_symm_params* p, const int64_t* k_begin,
+                           const int32_t* ent_h, const int32_t* ent_floor, const int32_t* ent_ceil,
+                           const double* ent_wk, const double* mats, int32_t n_mats, float* vol_out_host,
+                           float* xsum_out, float* ysum_out, float* zsum_out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
