@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
     ap.add_argument("--e2e-batches", type=int, default=3, help="batches per search_grid() call of the e2e measurement")
     ap.add_argument("--cpu-iters", type=int, default=60)
+    ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: LSMR iterations timed per sampled candidate")
+    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="--impl reference: wall-clock budget of the run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -218,10 +220,18 @@ def main():
         for _ in range(args.warmup):  # warm-up: imports, page cache, worker start-up (small problem)
             _cpu_candidate((small, -1.3, 4.75 / (APIX * 4), 4, 30000, 5))
         vals, t_steps = [], []
+        iters = args.ref_iters
+        t_budget, t_start = args.ref_budget_s, time.perf_counter()
         for s in range(args.steps):
             sel = tasks[(s * cores * 37) % (len(tasks) - cores):][:cores]
-            v, wall, outs = cpu_sample(img, sel, cores, args.cpu_iters, itn_typical)
+            v, wall, outs = cpu_sample(img, sel, cores, iters, itn_typical)
             vals.append(v); t_steps.append(wall)
+            # keep the whole run inside the budget: fewer LSMR iterations per sample for the remaining steps
+            left = t_budget - (time.perf_counter() - t_start)
+            if s + 1 < args.steps:
+                t_it = max(o[1] for o in outs)
+                t_fix = max(o[0] + o[2] for o in outs)
+                iters = int(max(4, min(args.ref_iters, (left / (args.steps - s - 1) - t_fix) / max(t_it, 1e-3))))
         value = float(np.mean(vals))
         line = dict(
             impl="reference", metric="denovo3D candidates/sec (solve+score)", value=value, unit="candidates/s",
@@ -230,7 +240,8 @@ def main():
             config=dict(workload=WORKLOAD, positive_constraint=args.positive),
             cpu_baseline=dict(value=value, unit="candidates/s", cores=cores, kind="port",
                               sample=f"{cores} grid candidates per step, one per core in parallel processes: full matrix "
-                                     f"build + {args.cpu_iters} scipy-LSMR iterations each, LSMR time scaled to "
+                                     f"build + up to {args.ref_iters} scipy-LSMR iterations each (fewer when the "
+                                     f"{args.ref_budget_s:.0f} s budget of the run runs out), LSMR time scaled to "
                                      f"{itn_typical} iterations (typical for this grid) + score"),
             e2e=dict(value=value, unit="candidates/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         )
