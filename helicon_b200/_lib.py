@@ -23,6 +23,7 @@ HB2_FLAG_TIE_XY = 1
 HB2_FLAG_TIE_Z = 2
 HB2_FLAG_BOUNDED = 4
 HB2_FLAG_NO_ROWS = 8
+HB2_FLAG_TIE_Z_EXACT = 16
 
 
 class Geometry(C.Structure):
@@ -40,7 +41,7 @@ class Candidate(C.Structure):
 
 
 class View(C.Structure):
-    _fields_ = [("angle", C.c_int32), ("col_begin", C.c_int32)]
+    _fields_ = [("angle", C.c_int32), ("col_begin", C.c_int32), ("tie", C.c_int32), ("tie_slot0", C.c_int32)]
 
 
 class Pair(C.Structure):
@@ -75,7 +76,7 @@ class Result(C.Structure):
 CANDIDATE_DTYPE = np.dtype(
     [("view_begin", "<i4"), ("view_count", "<i4"), ("pair_begin", "<i4"), ("pair_count", "<i4"),
      ("min_sym_pairs", "<i8"), ("positive", "<i4"), ("flags_in", "<u4")], align=True)
-VIEW_DTYPE = np.dtype([("angle", "<i4"), ("col_begin", "<i4")], align=True)
+VIEW_DTYPE = np.dtype([("angle", "<i4"), ("col_begin", "<i4"), ("tie", "<i4"), ("tie_slot0", "<i4")], align=True)
 PAIR_DTYPE = np.dtype([("ci", "<f8"), ("si", "<f8"), ("zi", "<f8"), ("cj", "<f8"), ("sj", "<f8"), ("zj", "<f8")], align=True)
 RESULT_DTYPE = np.dtype(
     [("score", "<f4"), ("itn", "<i4"), ("istop", "<i4"), ("trf_nit", "<i4"), ("flags", "<u4"), ("n_data_rows", "<i4"),
@@ -91,7 +92,7 @@ EXPORTS = [
     "hb2_problem_ndisk", "hb2_problem_rank_table", "hb2_batch_begin", "hb2_batch_ray_valid", "hb2_batch_angle_map",
     "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_rows_padded", "hb2_batch_rhs",
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
-    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize",
+    "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize", "hb2_batch_set_ties",
 ]
 
 _lib = None
@@ -124,6 +125,7 @@ def load():
     lib.hb2_batch_begin.argtypes = [P(vp), vp, i32, i32, i32, vp, vp, vp, vp]
     lib.hb2_batch_ray_valid.argtypes = [vp, vp]
     lib.hb2_batch_angle_map.argtypes = [vp, i32, vp]
+    lib.hb2_batch_set_ties.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.hb2_batch_create.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.hb2_batch_destroy.argtypes = [vp]
     lib.hb2_batch_destroy.restype = None

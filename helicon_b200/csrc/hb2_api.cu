@@ -3,6 +3,7 @@
 #include "hb2_kernels.cuh"
 #include "hb2_trf.cuh"
 #include "hb2_symm.cuh"
+#include "hb2_tie.cuh"
 
 #include <cub/cub.cuh>
 
@@ -97,6 +98,12 @@ struct hb2_batch {
   bool idx16 = true;
   size_t adj_tile_smem = 0;
   size_t fwd_band_smem = 0;
+  // tie views (hb2_batch_set_ties)
+  int n_tie = 0, tie_TS = 0;
+  std::vector<int8_t> h_tie_zlo;
+  std::vector<uint8_t> h_tie_up, h_tie_rv;
+  int n_tie_views = 0;
+  uint16_t* d_amap_i = nullptr;
   long long extra_launches = 0;  // kernels beyond one per launch_* call (band path: projector + reduce)
   int max_views = 0;
   bool created = false;
@@ -397,6 +404,18 @@ static cudaError_t upload(DevPool& pool, const T** dst, const std::vector<T>& sr
   return e;
 }
 
+extern "C" int hb2_batch_set_ties(hb2_batch* b, int32_t n_tie, int32_t TS, const int8_t* zlo, const uint8_t* up,
+                                  const uint8_t* rowvalid) {
+  if (!b || n_tie < 0 || (n_tie > 0 && (!zlo || !up || !rowvalid || TS <= 0))) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_set_ties must precede hb2_batch_create");
+  const int D2 = b->B.D2;
+  b->n_tie = n_tie; b->tie_TS = TS;
+  b->h_tie_zlo.assign(zlo, zlo + (size_t)n_tie * TS);
+  b->h_tie_up.assign(up, up + (size_t)n_tie * TS * D2);
+  b->h_tie_rv.assign(rowvalid, rowvalid + (size_t)n_tie * TS * D2);
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* cands, int32_t nviews, const hb2_view* views,
                                 int32_t ncolk, const int32_t* colk, int32_t npairs, const hb2_pair* pairs) {
   if (!b || !cands || nc <= 0 || !views || nviews <= 0 || !colk) return fail(HB2_ERR_ARG, "bad argument");
@@ -411,7 +430,8 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   b->cands.assign(cands, cands + nc);
   const int D2 = B.D2, ntiles = (D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   // ---- host tables ---------------------------------------------------------
-  std::vector<int> view_cand(nviews, -1), view_angle(nviews), view_colbegin(nviews);
+  std::vector<int> view_cand(nviews, -1), view_angle(nviews), view_colbegin(nviews), view_tie(nviews, -1), view_tie_slot0(nviews, 0);
+  std::vector<int> tie_views, cand_tie_begin(nc, 0), cand_tie_count(nc, 0);
   std::vector<long long> view_uoff(nviews);
   b->h_view_begin.resize(nc); b->h_view_count.resize(nc); b->h_mdata.resize(nc); b->h_msym.assign(nc, 0);
   b->h_uoff.resize(nc); b->h_symoff.resize(nc); b->h_symcap.resize(nc); b->h_cscoff.resize(nc);
@@ -441,6 +461,14 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       const hb2_view& w = views[vi];
       if (w.angle < 0 || w.angle >= B.nA || w.col_begin < 0 || w.col_begin + B.ZMC > ncolk) return fail(HB2_ERR_ARG, "bad view");
       view_cand[vi] = c; view_angle[vi] = w.angle; view_colbegin[vi] = w.col_begin;
+      if (w.tie >= 0) {
+        if (w.tie >= b->n_tie || w.tie_slot0 < 0 || w.tie_slot0 + B.ZMC > b->tie_TS) return fail(HB2_ERR_ARG, "bad tie view");
+        if (B.ZMC > HB2_TIE_MAXZMC) return fail(HB2_ERR_GEOMETRY, "tie views need L3*MC <= 16");
+        view_tie[vi] = w.tie; view_tie_slot0[vi] = w.tie_slot0;
+        if (cand_tie_count[c] == 0) cand_tie_begin[c] = (int)tie_views.size();
+        tie_views.push_back(vi);
+        cand_tie_count[c] += 1;
+      }
       view_uoff[vi] = uo + (long long)v * B.rows_per_view;
       if (b->tie_per_angle[w.angle] > 0) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
     }
@@ -463,6 +491,18 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(upload(b->pool, &B.view_cand, view_cand, st));
   CKC(upload(b->pool, &B.view_angle, view_angle, st));
   CKC(upload(b->pool, &B.view_colbegin, view_colbegin, st));
+  b->n_tie_views = (int)tie_views.size();
+  B.n_tie_views = b->n_tie_views; B.tie_TS = b->tie_TS;
+  CKC(upload(b->pool, &B.cand_tie_begin, cand_tie_begin, st));
+  CKC(upload(b->pool, &B.cand_tie_count, cand_tie_count, st));
+  if (b->n_tie_views > 0) {
+    CKC(upload(b->pool, &B.view_tie, view_tie, st));
+    CKC(upload(b->pool, &B.view_tie_slot0, view_tie_slot0, st));
+    CKC(upload(b->pool, &B.tie_views, tie_views, st));
+    CKC(upload(b->pool, (const int8_t**)&B.tie_zlo, b->h_tie_zlo, st));
+    CKC(upload(b->pool, &B.tie_up, b->h_tie_up, st));
+    CKC(upload(b->pool, &B.tie_rowvalid, b->h_tie_rv, st));
+  }
   CKC(upload(b->pool, &B.view_uoff, view_uoff, st));
   std::vector<int> colk_v(colk, colk + ncolk);
   CKC(upload(b->pool, &B.colk, colk_v, st));
@@ -483,8 +523,8 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     B.aslot = P->d_aslot; B.tile_begin = P->d_tile_begin; B.ntile = P->ntile;
     if (!P->tile_ok) return fail(HB2_ERR_GEOMETRY, "HB2_TILE_H*HB2_TILE_W must be <= 256");
     long long na = (long long)B.nA * B.ndisk;
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, nullptr, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, nullptr, d_kmax);
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, nullptr, d_kmax, nullptr);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, 0, 0, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, nullptr, d_kmax, nullptr);
     CKL();
     int K = 0;
     CKC(cudaMemcpyAsync(&K, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -494,8 +534,13 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     B.K = K;
     CKC(b->pool.alloc(&b->d_amap, (size_t)B.nA * K * B.apitch, false, st));
     CKC(cudaMemsetAsync(b->d_amap, 0xFF, (size_t)B.nA * K * B.apitch * sizeof(uint16_t), st));
-    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax);
-    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax);
+    if (b->n_tie_views > 0) {  // the tie adjoint needs the depth sample of every map entry
+      CKC(b->pool.alloc(&b->d_amap_i, (size_t)B.nA * K * B.apitch, false, st));
+      CKC(cudaMemsetAsync(b->d_amap_i, 0, (size_t)B.nA * K * B.apitch * sizeof(uint16_t), st));
+      B.amap_i = b->d_amap_i;
+    }
+    if (b->idx16) k_build_amap<uint16_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint16_t*)b->d_fmap, b->d_amap, d_kmax, b->d_amap_i);
+    else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax, b->d_amap_i);
     CKL();
     // consistency: every hit of the forward map must appear in the adjoint map
     long long ns = (long long)B.nA * D2 * D2;
@@ -534,6 +579,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(b->pool.alloc(&B.xs, nv, true, st));
   CKC(b->pool.alloc(&B.x, nv, true, st));
   CKC(b->pool.alloc(&B.hbar, nv, true, st));
+  if (b->n_tie_views > 0) CKC(b->pool.alloc(&B.vtie, nv, true, st));
   CKC(b->pool.alloc(&B.st, nc, true, st));
   CKC(b->pool.alloc(&b->d_bmax, nc, false, st));
   CKC(b->pool.alloc(&b->d_score, nc, true, st));
@@ -575,7 +621,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     const char* use_band = getenv("HB2_FWD_BAND");
     const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)sizeof(float));
     std::vector<int> bands{0};
-    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && (use_band && atoi(use_band));
+    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && (use_band && atoi(use_band)) && b->n_tie_views == 0;
     const std::vector<int>& tr = P->h_tilerow_begin;
     for (size_t r = 0; ok && r + 1 < tr.size(); ++r) {
       if (tr[r + 1] - tr[r] > cap) { ok = false; break; }
@@ -783,6 +829,12 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   const BD& B = b->B;
   cudaStream_t st = b->stream;
   if (b->nviews == 0) return;
+  if (b->n_tie_views > 0) {  // exact rows of the tie views (the projector kernels below skip them)
+    const float* src = mode == MODE_LSMR ? B.v : B.xs;
+    if (b->idx16) k_fwd_tie<uint16_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    else k_fwd_tie<uint32_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    b->extra_launches += 1;
+  }
   if (B.fwd_band) {
     const size_t sm = b->fwd_band_smem;
     const dim3 gb(B.nband, B.nc), gr(b->max_views, B.nc);
@@ -815,6 +867,10 @@ static void launch_adj(hb2_batch* b, int mode) {
   const BD& B = b->B;
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
+  if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
+    k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+    b->extra_launches += 1;
+  }
   if (B.adj_tile) {
     const size_t sm = b->adj_tile_smem;
 #define ADJT(Q, K)                                                                                       \
@@ -905,6 +961,8 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   const size_t nv = (size_t)nc * B.npad, nu = (size_t)b->u_total;
   double** nvecs[] = {&T.G, &T.D, &T.DH, &T.PH, &T.RH, &T.STEP, &T.V, &T.H, &T.HBAR, &T.XIN, &T.W, &T.UN};
   for (double** p : nvecs) CKT2(tmp.alloc(p, nv, true, st));
+  B.vtie64 = nullptr;
+  if (b->n_tie_views > 0) CKT2(tmp.alloc(&B.vtie64, nv, true, st));
   double** mvecs[] = {&T.R, &T.UM, &T.Y, &T.Y2};
   for (double** p : mvecs) CKT2(tmp.alloc(p, nu, true, st));
   long long max_m = 0;
@@ -950,8 +1008,17 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     else k_fwd64_data<uint32_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     launches += 2;
+    if (b->n_tie_views > 0) {
+      if (b->idx16) k_fwd_tie<uint16_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      else k_fwd_tie<uint32_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      ++launches;
+    }
   };
   auto adj = [&](const double* rows, double* dst, int gate) {
+    if (b->n_tie_views > 0) {
+      k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+      ++launches;
+    }
     k_adj64<<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
     ++launches;
   };
@@ -1011,6 +1078,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   CKT2(cudaMemcpyAsync(out.data(), T.st, sizeof(TrfState) * nc, cudaMemcpyDeviceToHost, st));
   CKT2(cudaStreamSynchronize(st));
   tmp.free_all();
+  B.vtie64 = nullptr;
   return HB2_OK;
 }
 

@@ -68,6 +68,19 @@ struct BD {
   double* part_x;
   float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
   int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
+  // tie views (exact per-sample slices); null / 0 when the batch has none
+  const int* view_tie;            // [nviews] tie index or -1
+  const int* view_tie_slot0;      // [nviews]
+  const signed char* tie_zlo;     // [n_tie][TS]
+  const unsigned char* tie_up;    // [n_tie][TS][D2]
+  const unsigned char* tie_rowvalid;  // [n_tie][TS][D2]
+  int tie_TS, n_tie_views;
+  const int* tie_views;           // [n_tie_views] view slots that are tie views, grouped by candidate
+  const int* cand_tie_begin;      // [nc] range into tie_views
+  const int* cand_tie_count;      // [nc]
+  const uint16_t* amap_i;         // [nA][K][apitch] depth sample i of the entry in amap (built only with ties)
+  float* vtie;                    // [nc][npad] adjoint contribution of the tie views (f32 path)
+  double* vtie64;                 // same for the float64 operators of the bounded branch
   // forward band path (k_fwd_band + k_fwd_band_reduce)
   int fwd_band;                // 1: use it (MC == 1, bands fit shared memory)
   int nband;
@@ -205,7 +218,7 @@ __global__ void k_build_fmap(int nA, int D2, double s, const double* __restrict_
 template <typename IdxT>
 __global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, int K, int pass, const double* __restrict__ cs,
                              const short2* __restrict__ disk_yx, const int* __restrict__ aslot, const IdxT* __restrict__ fmap,
-                             uint16_t* __restrict__ amap, int* __restrict__ kmax) {
+                             uint16_t* __restrict__ amap, int* __restrict__ kmax, uint16_t* __restrict__ amap_i) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nA * ndisk) return;
   int p = (int)(t % ndisk), a = (int)(t / ndisk);
@@ -224,7 +237,10 @@ __global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, in
   for (int j = j0; j <= j1; ++j)
     for (int i = i0; i <= i1; ++i)
       if (fm[(size_t)j * D2 + i] == (IdxT)p) {
-        if (pass == 1 && cnt < K) amap[((size_t)a * K + cnt) * apitch + aslot[p]] = (uint16_t)j;
+        if (pass == 1 && cnt < K) {
+          amap[((size_t)a * K + cnt) * apitch + aslot[p]] = (uint16_t)j;
+          if (amap_i) amap_i[((size_t)a * K + cnt) * apitch + aslot[p]] = (uint16_t)i;
+        }
         ++cnt;
       }
   if (pass == 0) {
@@ -261,7 +277,10 @@ __global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, flo
   int k = zm < B.ZMC ? B.colk[B.view_colbegin[view] + zm] : -1;
   int a = B.view_angle[view];
   float val = 0.f;
-  if (k >= 0 && B.rayvalid[a * B.D2 + j]) {
+  bool rowok = k >= 0 && B.rayvalid[a * B.D2 + j];
+  if (rowok && B.view_tie && B.view_tie[view] >= 0)  // tie view: the row exists iff a sample of ITS slices hits
+    rowok = B.tie_rowvalid[((size_t)B.view_tie[view] * B.tie_TS + B.view_tie_slot0[view] + zm) * B.D2 + j] != 0;
+  if (rowok) {
     val = pix[(size_t)j * B.L2 + k];
     // float max via ordered-int trick
     int c = B.view_cand[view];
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
   const int c = B.view_cand[view];
+  if (B.view_tie && B.view_tie[view] >= 0) return;  // tie views: k_fwd_tie (rows and partials)
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ int s_colk[HB2_MAX_ZMC];
   const LsmrState& S = B.st[c];
@@ -914,12 +934,13 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
     __syncthreads();
     for (int e = threadIdx.x; e < nvc; e += HB2_BLOCK) {
-      s_ang[e] = B.view_angle[vb + v0 + e];
+      s_ang[e] = (B.view_tie && B.view_tie[vb + v0 + e] >= 0) ? -1 : B.view_angle[vb + v0 + e];
       s_uoff[e] = B.view_uoff[vb + v0 + e];
     }
     __syncthreads();
     if (!live) continue;
     for (int vi = 0; vi < nvc; ++vi) {
+      if (s_ang[vi] < 0) continue;  // tie view (k_adj_tie)
       const float* __restrict__ ub = B.u + s_uoff[vi] + z0 * MC;
       const uint16_t* __restrict__ am = B.amap + (size_t)s_ang[vi] * K * B.apitch + slot;
       for (int k = 0; k < K; ++k) {
@@ -952,6 +973,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     const int g0 = p * L3P + z0;
     float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
     if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst);
+    if (B.vtie && B.cand_tie_count[c] > 0) {  // rows of the tie views (k_adj_tie)
+      const float4 t = *reinterpret_cast<const float4*>(B.vtie + (size_t)c * B.npad + g0);
+      acc0 += t.x; acc1 += t.y; acc2 += t.z; acc3 += t.w;
+    }
     float vn[4] = {acc0, acc1, acc2, acc3};
     const int nz = min(4, L3 - z0);  // real slices of this quad (padded slices stay 0)
     int e = nz > 0 ? ptr[g0] : 0;
@@ -1020,8 +1045,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
   for (int v0 = 0; v0 < nv; v0 += HB2_ADJ_VIEWS) {
     const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
     __syncthreads();
-    for (int e = threadIdx.x; e < HB2_ADJ_VIEWS; e += HB2_BLOCK)
-      s_aoff[e] = (unsigned)B.view_angle[vb + v0 + min(e, nvc - 1)] * kstride;  // tail entries repeat the last view
+    for (int e = threadIdx.x; e < HB2_ADJ_VIEWS; e += HB2_BLOCK) {
+      const int vw = vb + v0 + min(e, nvc - 1);  // tail entries repeat the last view
+      s_aoff[e] = (B.view_tie && B.view_tie[vw] >= 0) ? 0xFFFFFFFFu : (unsigned)B.view_angle[vw] * kstride;
+    }
     __syncthreads();
     if (!live) continue;
     for (int vi = 0; vi < nvc; vi += HB2_ADJ_VU) {
@@ -1029,9 +1056,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
 #pragma unroll
       for (int w = 0; w < HB2_ADJ_VU; ++w) {
         const unsigned ao = s_aoff[vi + w];
-        j0[w] = am0[ao];
-        j1[w] = KT == 2 ? (unsigned)am1[ao] : 0xFFFFu;
-        if (vi + w >= nvc) { j0[w] = 0xFFFFu; j1[w] = 0xFFFFu; }
+        const bool skip = ao == 0xFFFFFFFFu || vi + w >= nvc;  // tie view (k_adj_tie) or past the end
+        j0[w] = am0[skip ? 0u : ao];
+        j1[w] = KT == 2 ? (unsigned)am1[skip ? 0u : ao] : 0xFFFFu;
+        if (skip) { j0[w] = 0xFFFFu; j1[w] = 0xFFFFu; }
       }
       float4 r0[HB2_ADJ_VU];
 #pragma unroll
@@ -1059,6 +1087,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
     const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
     const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
     float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + g0;
+    if (B.vtie && B.cand_tie_count[c] > 0) {  // rows of the tie views (k_adj_tie)
+      const float4 t = *reinterpret_cast<const float4*>(B.vtie + (size_t)c * B.npad + g0);
+      acc0 += t.x; acc1 += t.y; acc2 += t.z; acc3 += t.w;
+    }
     int ev[HB2_ELL_W][4];
 #pragma unroll
     for (int w = 0; w < HB2_ELL_W; ++w) {
@@ -1179,9 +1211,10 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
   const int ustride = rmax * L3P;
   for (int e = threadIdx.x; e < nv; e += HB2_ADJT_THREADS) {
     const int a = B.view_angle[vb + e];
+    const bool tie = B.view_tie && B.view_tie[vb + e] >= 0;  // tie views are handled by k_adj_tie (BD::vtie)
     s_ang[e] = a;
     s_jlo[e] = B.tile_jlo[(size_t)a * B.ntile + tile];
-    s_nr[e] = B.tile_nr[(size_t)a * B.ntile + tile];
+    s_nr[e] = tie ? (uint16_t)0xFFFFu : B.tile_nr[(size_t)a * B.ntile + tile];
   }
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -1204,7 +1237,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
       const int buf = st % HB2_ADJT_NS;
       if (st >= HB2_ADJT_NS) mbar_wait(&empty_bar[buf], (unsigned)(((st / HB2_ADJT_NS) - 1) & 1));
       const int v = st * HB2_ADJT_SV + w;
-      const bool has = w < HB2_ADJT_SV && v < nv;
+      const bool has = w < HB2_ADJT_SV && v < nv && s_nr[min(v, nv - 1)] != 0xFFFFu;
       const unsigned nr = has ? s_nr[v] : 0;
       unsigned tot = has ? KT * HB2_BLOCK * (unsigned)sizeof(uint16_t) + nr * L3P * (unsigned)sizeof(float) : 0u;
 #pragma unroll
@@ -1230,7 +1263,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
         const int nvs = min(HB2_ADJT_SV, nv - st * HB2_ADJT_SV);
 #pragma unroll
         for (int w = 0; w < HB2_ADJT_SV; ++w) {
-          if (w < nvs) {
+          if (w < nvs && s_nr[st * HB2_ADJT_SV + w] != 0xFFFFu) {
             const uint16_t* mp = s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT) * HB2_BLOCK + threadIdx.x;
             const float* uw = s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride;
             const int jl = s_jlo[st * HB2_ADJT_SV + w];
@@ -1261,6 +1294,14 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
     const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
     const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
     float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + g0;
+    if (B.vtie && B.cand_tie_count[c] > 0) {  // rows of the tie views (k_adj_tie)
+      const float4* vt = reinterpret_cast<const float4*>(B.vtie + (size_t)c * B.npad + g0);
+#pragma unroll
+      for (int q4 = 0; q4 < NQT; ++q4) {
+        const float4 t = vt[q4];
+        acc[4 * q4 + 0] += t.x; acc[4 * q4 + 1] += t.y; acc[4 * q4 + 2] += t.z; acc[4 * q4 + 3] += t.w;
+      }
+    }
 #pragma unroll
     for (int q4 = 0; q4 < NQT; ++q4) {
       int ev[HB2_ELL_W][4];

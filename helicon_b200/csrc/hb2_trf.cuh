@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_data(BD B, TD T, const doub
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
   const int c = B.view_cand[view];
+  if (B.view_tie && B.view_tie[view] >= 0) return;  // tie views: k_fwd_tie<double>
   const TrfState& S = T.st[c];
   if (!trf_gate(S, inner)) return;
   __shared__ int s_colk[HB2_MAX_ZMC];
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* _
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
   for (int vi = 0; vi < nv; ++vi) {
     const int view = vb + vi;
+    if (B.view_tie && B.view_tie[view] >= 0) continue;  // tie views: k_adj_tie<double> (BD::vtie64)
     const int a = __ldg(B.view_angle + view);
     const double* __restrict__ ub = rows + __ldg(B.view_uoff + view) + z0 * MC;
     const uint16_t* __restrict__ am = B.amap + (size_t)a * K * B.apitch + slot;
@@ -232,6 +234,11 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj64(BD B, TD T, const double* _
   const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
   const double* __restrict__ us = rows + B.cand_uoff[c] + B.cand_mdata[c];
   double* vdst = dst + (size_t)c * B.npad + (size_t)p * L3P + z0;
+  if (B.vtie64 && B.cand_tie_count[c] > 0) {
+    const double* vt = B.vtie64 + (size_t)c * B.npad + (size_t)p * L3P + z0;
+#pragma unroll
+    for (int zz = 0; zz < 4; ++zz) acc[zz] += vt[zz];
+  }
 #pragma unroll
   for (int zz = 0; zz < 4; ++zz) {
     double a2 = acc[zz];

@@ -105,8 +105,12 @@ class Batch:
                 _lib.ptr(self.nvalid), _lib.ptr(self.tie), problem.stream if stream is None else _stream_handle(stream),
             )
         )
-        self.plan.finalize(self.nvalid)
+        self._amap_cache = {}
+        self.plan.finalize(self.nvalid, lambda a: self.angle_map(a) >= 0)
         p = self.plan
+        if p.n_tie:
+            _lib.check(lib.hb2_batch_set_ties(self._h, p.n_tie, p.tie_TS, _lib.ptr(p.tie_zlo), _lib.ptr(p.tie_up),
+                                              _lib.ptr(p.tie_rowvalid)))
         _lib.check(
             lib.hb2_batch_create(
                 self._h, len(p.cands), _lib.ptr(p.cands), len(p.views), _lib.ptr(p.views), len(p.colk),
@@ -179,10 +183,14 @@ class Batch:
         return out
 
     def angle_map(self, a):
-        D2 = self.problem.D2
-        out = np.empty(D2 * D2, dtype=np.int32)
-        _lib.check(_lib.load().hb2_batch_angle_map(self._h, int(a), _lib.ptr(out)))
-        return out.reshape(D2, D2)
+        """sample -> voxel map of angle a: [ray j, depth i] reference disk rank or -1 (cached)."""
+        a = int(a)
+        if a not in self._amap_cache:
+            D2 = self.problem.D2
+            out = np.empty(D2 * D2, dtype=np.int32)
+            _lib.check(_lib.load().hb2_batch_angle_map(self._h, a, _lib.ptr(out)))
+            self._amap_cache[a] = out.reshape(D2, D2)
+        return self._amap_cache[a]
 
     def rows_padded(self, c):
         nd = C.c_int64()
@@ -198,21 +206,34 @@ class Batch:
 
     def data_row_index(self, c):
         """For every real data row, in the reference's order (copy, k, j), its
-        index in the padded layout [view][j][z*MC+mc] (row stride ZMP), plus (k, j)."""
+        index in the padded layout [view slot][j][column slot] (row stride ZMP), plus (k, j)."""
         D2, L3, MC = self.problem.D2, self.L3, self.plan.MC
-        ZMP = (L3 * MC + 3) // 4 * 4
+        ZMC = L3 * MC
+        ZMP = (ZMC + 3) // 4 * 4
         rv = self.ray_valid()
+        base = int(self.plan.cands[c]["view_begin"])
         idx, kk, jj = [], [], []
-        for vi, (a, zi, h, cc, nrows) in enumerate(self.plan.cand_views[c]):
-            js = np.nonzero(rv[a])[0]
-            fill = np.zeros(L3, dtype=np.int64)
-            for k in np.nonzero(zi >= 0)[0]:
-                z = int(zi[k])
-                zm = z * MC + fill[z]
-                fill[z] += 1
-                idx.append(vi * (D2 * ZMP) + js * ZMP + zm)
-                kk.append(np.full(len(js), k))
-                jj.append(js)
+        for (a, zi, h, cc, nrows), slot in zip(self.plan.cand_views[c], self.plan.cand_view_slots[c]):
+            vi = slot - base
+            if zi.ndim == 1:
+                js = np.nonzero(rv[a])[0]
+                fill = np.zeros(L3, dtype=np.int64)
+                for k in np.nonzero(zi >= 0)[0]:
+                    z = int(zi[k])
+                    zm = z * MC + fill[z]
+                    fill[z] += 1
+                    idx.append(vi * (D2 * ZMP) + js * ZMP + zm)
+                    kk.append(np.full(len(js), k))
+                    jj.append(js)
+            else:  # tie view: column slots, per-(column, ray) validity
+                va = self.angle_map(a) >= 0
+                inside = (zi >= 0) & (zi < L3)
+                cols = np.nonzero(inside.any(axis=1))[0]
+                for t, k in enumerate(cols):
+                    js = np.nonzero((va & inside[k][None, :]).any(axis=1))[0]
+                    idx.append((vi + t // ZMC) * (D2 * ZMP) + js * ZMP + (t % ZMC))
+                    kk.append(np.full(len(js), k))
+                    jj.append(js)
         if not idx:
             return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.int64)
         return np.concatenate(idx), np.concatenate(kk), np.concatenate(jj)
@@ -224,22 +245,31 @@ class Batch:
         rv = self.ray_valid()
         rows, cols = [], []
         r0 = 0
-        maps = {}
         for a, zi, h, cc, nrows in self.plan.cand_views[c]:
-            if a not in maps:
-                maps[a] = self.angle_map(a)
-            fm = maps[a]
-            js = np.nonzero(rv[a])[0]
-            sub = fm[js]  # (nj, D2)
-            hit = sub >= 0
-            per_ray = hit.sum(axis=1)
-            ray_local = np.repeat(np.arange(len(js)), per_ray)
-            vox = sub[hit]
-            for k in np.nonzero(zi >= 0)[0]:
-                z = int(zi[k])
-                rows.append(r0 + ray_local)
-                cols.append(z * nd + vox)
-                r0 += len(js)
+            fm = self.angle_map(a)
+            if zi.ndim == 1:
+                js = np.nonzero(rv[a])[0]
+                sub = fm[js]  # (nj, D2)
+                hit = sub >= 0
+                per_ray = hit.sum(axis=1)
+                ray_local = np.repeat(np.arange(len(js)), per_ray)
+                vox = sub[hit]
+                for k in np.nonzero(zi >= 0)[0]:
+                    z = int(zi[k])
+                    rows.append(r0 + ray_local)
+                    cols.append(z * nd + vox)
+                    r0 += len(js)
+            else:  # tie view: every sample carries its own slice (zi[k, i])
+                inside = (zi >= 0) & (zi < L3)
+                for k in np.nonzero(inside.any(axis=1))[0]:
+                    hit = (fm >= 0) & inside[k][None, :]  # [j, i]
+                    js = np.nonzero(hit.any(axis=1))[0]
+                    sub = hit[js]
+                    ray_local = np.repeat(np.arange(len(js)), sub.sum(axis=1))
+                    jj_, ii_ = np.nonzero(sub)
+                    rows.append(r0 + ray_local)
+                    cols.append(zi[k][ii_] * nd + fm[js][jj_, ii_])
+                    r0 += len(js)
         pidx, kk, jj = self.data_row_index(c)
         b = self.rhs_padded(c)[pidx] if len(pidx) else np.zeros(0, np.float32)
         if rows:

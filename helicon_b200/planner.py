@@ -81,6 +81,16 @@ def z_rotation_entries(angles_deg):
     return np.ascontiguousarray(np.stack([M[:, 0, 0], M[:, 1, 0]], axis=1))
 
 
+def z_rotation_m22(angles_deg):
+    """M22 of the same scipy rotation matrices: 1.0 or 1 - 2**-53 depending on the angle."""
+    from scipy.spatial.transform import Rotation as R
+
+    angles_deg = np.atleast_1d(np.asarray(angles_deg, dtype=np.float64))
+    if len(angles_deg) == 0:
+        return np.zeros(0)
+    return np.ascontiguousarray(R.from_euler("z", angles_deg.reshape(-1, 1), degrees=True).as_matrix()[:, 2, 2])
+
+
 def column_slices(s, L2, L3, zshift):
     """z-slice of every image column k for one symmetry copy (SLR:1578-1581,
     1529 with tilt=psi=0): Z = s*(k - L2//2) - h*rise_pixel + L3//2, rint
@@ -94,6 +104,43 @@ def column_slices(s, L2, L3, zshift):
     near = np.abs(np.abs(Z - np.floor(Z)) - 0.5) < 1e-9
     tie = bool(np.any(near & (Z > -1.0) & (Z < L3)))
     return np.where(ok, zi, -1), tie
+
+
+@functools.lru_cache(maxsize=16)
+def reference_z_table(s, D2, L2):
+    """z coordinate of sample (column k, depth i) exactly as the reference's coordinate tables hold it
+    (SLR:1712-1719: ``R.from_euler('y', 90).apply(inverse=True)`` of the integer grid, then ``*= s``): the exact
+    value s*(k - L2//2) plus last-bit noise that depends on (k, i) only (not on the ray j; checked in
+    tests/test_host_cpu.py).  It decides rounding ties: returns a float64 array [L2, D2]."""
+    from scipy.spatial.transform import Rotation as R
+
+    depth = (np.arange(D2, dtype=np.int32) - D2 // 2).astype(np.float32)
+    along = (np.arange(L2, dtype=np.int32) - L2 // 2).astype(np.float32)
+    Zg, Yg, Xg = np.meshgrid(depth, np.zeros(1, np.float32), along, indexing="ij")
+    pts = np.stack((Xg.ravel(), Yg.ravel(), Zg.ravel()), axis=1)
+    pts = R.from_euler("y", 90, degrees=True).apply(pts, inverse=True)
+    if s != 1.0:
+        pts *= s
+    return np.ascontiguousarray(np.swapaxes(pts[:, 2].reshape((D2, 1, L2)), 0, 2)[:, 0, :])
+
+
+class TieView:
+    """A symmetry copy whose column -> slice rounding sits on a tie (h*rise_pixel half-integer): every sample picks
+    its slice from the reference's noisy z table.  ``cols``: image columns with at least one sample inside [0, L3);
+    ``zlo[t]``: lower slice of column t (may be -1); ``up[t, i]`` in {0, 1}: sample i of column t lands in zlo+up."""
+
+    __slots__ = ("cols", "zlo", "up", "zt")
+
+    def __init__(self, zt, L3):
+        inside = (zt >= 0) & (zt < L3)
+        self.cols = np.nonzero(inside.any(axis=1))[0]
+        sub = zt[self.cols]
+        self.zlo = sub.min(axis=1)
+        up = sub - self.zlo[:, None]
+        if up.size and up.max() > 1:
+            raise AssertionError("a tie column spans more than two slices")
+        self.up = up.astype(np.uint8)
+        self.zt = zt
 
 
 class CandidateSpec:
@@ -114,15 +161,15 @@ class BatchPlan:
     """Two-stage plan of a batch with uniform (geometry, L3).
 
     stage 1 (``__init__``): unique angles + per-copy column tables;
-    stage 2 (``finalize(nvalid)``): row-count early stop (SLR:1647) once the GPU
-    has reported the number of rays with data per angle, then flat tables.
+    stage 2 (``finalize(nvalid, angle_valid)``): row-count early stop (SLR:1647) once the GPU has reported the number
+    of rays with data per angle, then flat tables.
 
-    Everything per candidate is a handful of numpy calls over (n_h, L2) arrays
-    (all symmetry copies at once); the arithmetic per element is the scalar
-    sequence of ``column_slices``.
+    Everything per candidate is a handful of numpy calls over (n_h, L2) arrays (all symmetry copies at once); the
+    arithmetic per element is the scalar sequence of ``column_slices``.  Copies whose column -> slice rounding is a
+    tie become ``TieView``s (exact per-sample slices from the reference's z table) when ``exact_ties``.
     """
 
-    def __init__(self, s, D2, L2, L3, specs):
+    def __init__(self, s, D2, L2, L3, specs, exact_ties=True):
         self.s, self.D2, self.L2, self.L3 = float(s), int(D2), int(L2), int(L3)
         self.specs = list(specs)
         L2, L3 = self.L2, self.L3
@@ -130,7 +177,7 @@ class BatchPlan:
         z0 = kk * self.s if self.s != 1.0 else kk
         angle_index = {}
         angles = []
-        self._cand = []  # per candidate: (copies, angle ids, index of each copy's h in hs, hs, ZI[n_h, L2])
+        self._cand = []  # per candidate: (copies, angle ids, index of each copy's h in hs, hs, ZI[n_h, L2], ties {hidx: TieView})
         self.cand_tie_z = []
         mc = 1
         for sp in self.specs:
@@ -142,10 +189,14 @@ class BatchPlan:
             zi = np.rint(Z).astype(np.int64)
             ok = (zi >= 0) & (zi <= L3 - 1)
             near = np.abs(np.abs(Z - np.floor(Z)) - 0.5) < 1e-9
-            self.cand_tie_z.append(bool(np.any(near & (Z > -1.0) & (Z < L3))))
+            tie_h = np.any(near & (Z > -1.0) & (Z < L3), axis=1)
+            exact = bool(exact_ties and tie_h.any() and L3 <= 16)
+            self.cand_tie_z.append(bool(tie_h.any()) and not exact)  # approximate only when not handled exactly
             ZI = np.where(ok, zi, -1)
-            if ok.any():
-                flat = (np.arange(len(hs))[:, None] * L3 + zi)[ok]
+            reg = ~tie_h if exact else np.ones(len(hs), dtype=bool)
+            okr = ok & reg[:, None]
+            if okr.any():
+                flat = (np.arange(len(hs))[:, None] * L3 + zi)[okr]
                 mc = max(mc, int(np.bincount(flat).max()))
             aid = np.empty(len(copies), dtype=np.int64)
             hidx = np.empty(len(copies), dtype=np.int64)
@@ -159,47 +210,98 @@ class BatchPlan:
                     angles.append(angle)
                 aid[i] = a
                 hidx[i] = hpos[h]
-            self._cand.append((copies, aid, hidx, hs, ZI))
+            # tie copies: the reference's z passes through Rotation.apply of the copy's z-rotation, whose M22 is
+            # 1 or 1 - 2^-53 depending on the angle (quaternion normalisation) -- it decides the ties, so take it
+            # from the same scipy call (SLR:1576-1577)
+            ties = {}
+            if exact:
+                Zt = reference_z_table(self.s, self.D2, L2)
+                tc = [i for i in range(len(copies)) if tie_h[hidx[i]]]
+                ang = np.array([tw * copies[i][0] + 360 * copies[i][1] / cs for i in tc], dtype=np.float64)
+                m22 = z_rotation_m22(ang)
+                for i, m in zip(tc, m22):
+                    key = (int(hidx[i]), int(copies[i][1]))
+                    if key not in ties:
+                        zt = np.rint(((Zt * m) - zshift[hidx[i]]) + (L3 // 2)).astype(np.int64)
+                        ties[key] = TieView(zt, L3)
+            self._cand.append((copies, aid, hidx, hs, ZI, ties))
         self.MC = mc
         self.angles = np.array(angles, dtype=np.float64)
         self.cos_sin = z_rotation_entries(self.angles)
+        self.has_ties = any(c[5] for c in self._cand)
         self.finalized = False
 
-    def finalize(self, nvalid_rays):
+    def finalize(self, nvalid_rays, angle_valid=None):
+        """``angle_valid(a)`` -> bool [D2, D2] (sample (j, i) of angle a hits a voxel), needed only for tie views."""
         nvalid_rays = np.asarray(nvalid_rays, dtype=np.int64)
-        L2, L3, MC = self.L2, self.L3, self.MC
+        L2, L3, MC, D2 = self.L2, self.L3, self.MC, self.D2
+        ZMC = L3 * MC
         nc = len(self.specs)
         cands = np.zeros(nc, dtype=_lib.CANDIDATE_DTYPE)
-        view_angle, colk = [], []
-        self.cand_views = []  # per candidate: list of (angle_id, zi, h, c, n_rows_real)
-        pair_meta = []        # (candidate, angle_i, angle_j, zshift_i, zshift_j) arrays, rotated in one scipy call below
+        view_rows = []  # (angle, tie index or -1, first tie column slot)
+        colk = []
+        self.cand_views = []  # per candidate: list of (angle_id, zi (1-D, or 2-D [L2, D2] for a tie view), h, c, n_rows_real)
+        self.cand_view_slots = []  # per candidate: first view slot of every entry of cand_views (tie views may take several)
+        pair_meta = []
+        tie_zlo, tie_up, tie_rv = [], [], []
         nviews = 0
         npairs = 0
         karange = np.arange(L2, dtype=np.int64)[None, :]
         for ci, sp in enumerate(self.specs):
-            copies, aid, hidx, hs, ZI = self._cand[ci]
+            copies, aid, hidx, hs, ZI, ties = self._cand[ci]
             valid = ZI >= 0
             ncols_h = valid.sum(axis=1)
             nrows = ncols_h[hidx] * nvalid_rays[aid]
+            tie_rows = {}
+            for i in range(len(copies)):
+                tv = ties.get((int(hidx[i]), int(copies[i][1])))
+                if tv is not None:
+                    va = angle_valid(int(aid[i]))  # [j, i]
+                    inside = (tv.zt[tv.cols] >= 0) & (tv.zt[tv.cols] < L3)  # [t, i]
+                    rv = (va[None, :, :] & inside[:, None, :]).any(axis=2)  # [t, j]
+                    tie_rows[i] = rv
+                    nrows[i] = int(rv.sum())
             stop = len(copies)
             if sp.min_projection_lines > 0:
                 over = np.nonzero(np.cumsum(nrows) > sp.min_projection_lines)[0]
                 if len(over):
                     stop = int(over[0]) + 1
             sel = np.nonzero(nrows[:stop] > 0)[0]
-            self.cand_views.append([(int(aid[i]), ZI[hidx[i]], copies[i][0], copies[i][1], int(nrows[i])) for i in sel])
+            cv, slots = [], []
             cands[ci]["view_begin"] = nviews
-            cands[ci]["view_count"] = len(sel)
             if len(sel):
-                # column table of every h: tab[z*MC + m] = m-th image column whose slice is z (columns ascending)
                 prev = np.concatenate([np.full((len(hs), 1), -2, dtype=np.int64), ZI[:, :-1]], axis=1)
                 run_start = np.maximum.accumulate(np.where(valid & (ZI != prev), karange, 0), axis=1)
-                tab = np.full((len(hs), L3 * MC), -1, dtype=np.int32)
+                tab = np.full((len(hs), ZMC), -1, dtype=np.int32)
                 hh, kq = np.nonzero(valid)
+                tie_hs = {k[0] for k in ties}
+                keep = np.array([int(h) not in tie_hs for h in hh], dtype=bool) if ties else np.ones(len(hh), dtype=bool)
+                hh, kq = hh[keep], kq[keep]
                 tab[hh, ZI[hh, kq] * MC + (kq - run_start[hh, kq])] = kq
-                colk.append(tab[hidx[sel]])
-                view_angle.append(aid[sel])
-                nviews += len(sel)
+                for i in sel:
+                    tv = ties.get((int(hidx[i]), int(copies[i][1])))
+                    slots.append(nviews)
+                    if tv is None:
+                        cv.append((int(aid[i]), ZI[hidx[i]], copies[i][0], copies[i][1], int(nrows[i])))
+                        colk.append(tab[hidx[i]])
+                        view_rows.append((int(aid[i]), -1, 0))
+                        nviews += 1
+                    else:
+                        cv.append((int(aid[i]), tv.zt, copies[i][0], copies[i][1], int(nrows[i])))
+                        ncol = len(tv.cols)
+                        nslot = (ncol + ZMC - 1) // ZMC
+                        tid = len(tie_zlo)
+                        tie_zlo.append(tv.zlo); tie_up.append(tv.up); tie_rv.append(tie_rows[i])
+                        for q in range(nslot):
+                            t = np.full(ZMC, -1, dtype=np.int32)
+                            cc = tv.cols[q * ZMC:(q + 1) * ZMC]
+                            t[:len(cc)] = cc
+                            colk.append(t)
+                            view_rows.append((int(aid[i]), tid, q * ZMC))
+                        nviews += nslot
+            self.cand_views.append(cv)
+            self.cand_view_slots.append(slots)
+            cands[ci]["view_count"] = nviews - cands[ci]["view_begin"]
             # symmetry pairs (SLR:892, 1223-1243)
             cands[ci]["pair_begin"] = npairs
             plist = sorted_hsym_csym_pairs(sp.twist, sp.rise_pixel, sp.csym, L3) if sp.min_sym_pairs >= 0 else []
@@ -212,16 +314,35 @@ class BatchPlan:
             cands[ci]["pair_count"] = len(plist)
             cands[ci]["min_sym_pairs"] = sp.min_sym_pairs
             cands[ci]["positive"] = int(sp.positive)
-            cands[ci]["flags_in"] = _lib.HB2_FLAG_TIE_Z if self.cand_tie_z[ci] else 0
+            fl = _lib.HB2_FLAG_TIE_Z if self.cand_tie_z[ci] else 0
+            if ties:
+                fl |= _lib.HB2_FLAG_TIE_Z_EXACT
+            cands[ci]["flags_in"] = fl
         self.cands = cands
         views = np.zeros(nviews, dtype=_lib.VIEW_DTYPE)
         if nviews:
-            views["angle"] = np.concatenate(view_angle)
-            views["col_begin"] = np.arange(nviews, dtype=np.int64) * (L3 * MC)
+            vr = np.array(view_rows, dtype=np.int64)
+            views["angle"] = vr[:, 0]
+            views["tie"] = vr[:, 1]
+            views["tie_slot0"] = vr[:, 2]
+            views["col_begin"] = np.arange(nviews, dtype=np.int64) * ZMC
             self.colk = np.ascontiguousarray(np.concatenate(colk).reshape(-1), dtype=np.int32)
         else:
             self.colk = np.zeros(0, dtype=np.int32)
         self.views = views
+        # tie tables, padded to TS column slots per tie view
+        self.n_tie = len(tie_zlo)
+        if self.n_tie:
+            TS = max(len(z) for z in tie_zlo)
+            TS = (TS + ZMC - 1) // ZMC * ZMC
+            self.tie_TS = TS
+            self.tie_zlo = np.full((self.n_tie, TS), -100, dtype=np.int8)
+            self.tie_up = np.zeros((self.n_tie, TS, D2), dtype=np.uint8)
+            self.tie_rowvalid = np.zeros((self.n_tie, TS, D2), dtype=np.uint8)
+            for t, (zl, up, rv) in enumerate(zip(tie_zlo, tie_up, tie_rv)):
+                self.tie_zlo[t, :len(zl)] = zl
+                self.tie_up[t, :len(zl)] = up
+                self.tie_rowvalid[t, :len(zl)] = rv
         pairs = np.zeros(npairs, dtype=_lib.PAIR_DTYPE)
         if npairs:
             ai = np.concatenate([m[0] for m in pair_meta])

@@ -39,6 +39,7 @@ typedef enum {
 #define HB2_FLAG_TIE_Z 2u        /* a column's Z lies within 1e-9 of a rounding boundary (host planner sets it) */
 #define HB2_FLAG_BOUNDED 4u      /* the bounded (TRF) branch ran (SLR:246-270, scipy lsq_linear) */
 #define HB2_FLAG_NO_ROWS 8u      /* no data rows */
+#define HB2_FLAG_TIE_Z_EXACT 16u /* column->slice ties resolved per sample from the reference's z table (exact) */
 
 typedef struct hb2_problem hb2_problem; /* one image + in-plane geometry, shared by many candidates */
 typedef struct hb2_batch hb2_batch;     /* a set of candidates solved together */
@@ -72,6 +73,9 @@ typedef struct {
 typedef struct {
   int32_t angle;       /* index into the batch's unique-angle table */
   int32_t col_begin;   /* offset into colk (L3*MC entries) */
+  int32_t tie;         /* -1, or index of the tie view this slot belongs to (hb2_batch_set_ties): colk then lists
+                          the image COLUMNS of column slots tie_slot0 .. tie_slot0 + L3*MC - 1 */
+  int32_t tie_slot0;
 } hb2_view;
 
 /* One symmetry pair ((h_i,c_i),(h_j,c_j)) of the regulariser (SLR:1223-1243):
@@ -141,6 +145,15 @@ int hb2_batch_begin(hb2_batch** out, hb2_problem* p, int32_t L3, int32_t MC, int
 int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out_host);
 /* sample->voxel map of one angle, out[D2*D2] int32 (disk rank or -1), row j, depth i */
 int hb2_batch_angle_map(hb2_batch* b, int32_t angle, int32_t* out_host);
+
+/* Tie views: a symmetry copy whose Z = s*(k - L2//2) - h*rise + L3//2 is a half-integer for its
+ * columns lets every SAMPLE round by the last-bit noise of the reference's coordinate table (SLR:1712-1719), so a
+ * row (column k, ray j) draws from two neighbouring slices.  The host resolves it from that table:
+ * zlo[t*TS + s] = lower slice of column slot s (may be -1; <= -100 = unused slot), up[(t*TS + s)*D2 + i] in {0,1}
+ * = sample i of the slot lands in zlo + up, rowvalid[(t*TS + s)*D2 + j] = the row exists.  Call between
+ * hb2_batch_begin and hb2_batch_create; views refer to tie t through hb2_view.tie. */
+int hb2_batch_set_ties(hb2_batch* b, int32_t n_tie, int32_t TS, const int8_t* zlo, const uint8_t* up,
+                       const uint8_t* rowvalid);
 
 /* ---- batch: step 2, candidates ----------------------------------------- */
 /* Finalises the batch: adjoint maps, right-hand side, symmetry rows

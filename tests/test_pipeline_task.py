@@ -95,20 +95,27 @@ def test_display_products_exact_given_reference_volume():
 
 
 @pytest.mark.gpu
-def test_tie_geometry_is_flagged_not_silently_different():
+def test_tie_geometry_is_solved_exactly():
     """task_tiez: h*rise_pixel is a half-integer, so the reference's column->slice rounding follows the last-bit noise
-    of its coordinate tables.  The CUDA path does not reproduce that noise yet; it
-    must FLAG the candidate (HB2_FLAG_TIE_Z) so that a caller can tell, and still return a sane score."""
-    from helicon_b200 import _lib
-    from helicon_b200 import solver_linear_regression as S
+    of its coordinate tables: every sample of such a view picks one of two slices.  The CUDA path resolves
+    it from the same table (planner.reference_z_table -> TieView -> k_fwd_tie / k_adj_tie): same score as the
+    reference to 1e-5, flagged HB2_FLAG_TIE_Z_EXACT (not the approximate HB2_FLAG_TIE_Z)."""
+    from helicon_b200 import _lib, pipeline
 
     d = load("task_tiez")
+    res = pipeline.process_one_task(**_kw(d))
+    score, rd, meta = res
+    rec3d = rd[3][0]
+    assert abs(float(score) - float(d["score"])) <= 1e-5, (float(score), float(d["score"]))
+    assert np.linalg.norm(rec3d - d["rec3d"]) <= 5e-3 * np.linalg.norm(d["rec3d"])
+    from helicon_b200 import solver_linear_regression as S
+
     apix, twist, rise, csym, pc, tf = (float(v) for v in d["args"])
     D2, D3, L2, L3 = (int(v) for v in d["geom"])
     img = np.clip(d["data_orig"], 0, None)
-    (rec, _, _), score, info = S.lsq_reconstruct(img, 1.0, twist, rise / apix, int(csym), positive_constraint=0,
-                                                 reconstruct_diameter_2d_pixel=D2, reconstruct_diameter_3d_pixel=D3,
-                                                 reconstruct_length_2d_pixel=L2, reconstruct_length_3d_pixel=L3,
-                                                 sym_oversample=160, return_info=True)
-    assert int(info["res"]["flags"]) & _lib.HB2_FLAG_TIE_Z
-    assert 0.9 < float(score) <= 1.0
+    _, _, info = S.lsq_reconstruct(img, 1.0, twist, rise / apix, int(csym), positive_constraint=0,
+                                   reconstruct_diameter_2d_pixel=D2, reconstruct_diameter_3d_pixel=D3,
+                                   reconstruct_length_2d_pixel=L2, reconstruct_length_3d_pixel=L3, sym_oversample=160,
+                                   return_info=True)
+    fl = int(info["res"]["flags"])
+    assert fl & _lib.HB2_FLAG_TIE_Z_EXACT and not fl & _lib.HB2_FLAG_TIE_Z
