@@ -1213,7 +1213,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
     const int a = B.view_angle[vb + e];
     const bool tie = B.view_tie && B.view_tie[vb + e] >= 0;  // tie views are handled by k_adj_tie (BD::vtie)
     s_ang[e] = a;
-    s_jlo[e] = B.tile_jlo[(size_t)a * B.ntile + tile];
+    s_jlo[e] = tie ? (uint16_t)0xFFFFu : B.tile_jlo[(size_t)a * B.ntile + tile];  // 0xFFFF: skip the view
     s_nr[e] = tie ? (uint16_t)0xFFFFu : B.tile_nr[(size_t)a * B.ntile + tile];
   }
   if (threadIdx.x == 0) {
@@ -1263,10 +1263,10 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
         const int nvs = min(HB2_ADJT_SV, nv - st * HB2_ADJT_SV);
 #pragma unroll
         for (int w = 0; w < HB2_ADJT_SV; ++w) {
-          if (w < nvs && s_nr[st * HB2_ADJT_SV + w] != 0xFFFFu) {
+          const int jl = w < nvs ? (int)s_jlo[st * HB2_ADJT_SV + w] : 0xFFFF;
+          if (jl != 0xFFFF) {
             const uint16_t* mp = s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT) * HB2_BLOCK + threadIdx.x;
             const float* uw = s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride;
-            const int jl = s_jlo[st * HB2_ADJT_SV + w];
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
               const unsigned j = mp[(size_t)k * HB2_BLOCK];

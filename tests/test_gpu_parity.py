@@ -140,7 +140,8 @@ def test_operator_forward_adjoint_vs_oracle_csr(name):
     batch.close(); prob.close()
 
 
-@pytest.mark.parametrize("name", ["solve_nn_unb_32", "solve_nn_unb_48_t35", "solve_nn_unb_48_c2", "solve_nn_unb_64"])
+@pytest.mark.parametrize("name", ["solve_nn_unb_32", "solve_nn_unb_48_t35", "solve_nn_unb_48_c2", "solve_nn_unb_64",
+                                  "solve_nn_unb_96_tie475"])
 def test_unbounded_solve_vs_reference_golden(solver, name):
     d = load(name)
     apix, twist, rise, csym, pc, so, L3 = d["args"]
@@ -156,6 +157,8 @@ def test_unbounded_solve_vs_reference_golden(solver, name):
     print(f"{name}: itn={info['res']['itn']} istop={info['res']['istop']} score={float(score):.7f} "
           f"ref={float(d['score']):.7f} |dscore|={dscore:.2e} rel-L2(x)={rel:.2e}")
     assert rec.dtype == np.float32 and rec.shape == ref.shape and h1 is None and h2 is None
+    if name.endswith("tie475"):  # rise_pixel*13 = 47.5: tie views h = +-13, resolved exactly (oracle/make_golden_tie475.py)
+        assert info["res"]["flags"] & 16 and not info["res"]["flags"] & 2
     if info["res"]["flags"] & 3:  # tie-flagged geometry: a few samples may land in a neighbouring voxel
         assert dscore <= 2e-4
     else:
