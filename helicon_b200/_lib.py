@@ -41,7 +41,8 @@ class Candidate(C.Structure):
 
 
 class View(C.Structure):
-    _fields_ = [("angle", C.c_int32), ("col_begin", C.c_int32), ("tie", C.c_int32), ("tie_slot0", C.c_int32)]
+    _fields_ = [("angle", C.c_int32), ("col_begin", C.c_int32), ("tie", C.c_int32), ("tie_slot0", C.c_int32),
+                ("dup_of", C.c_int32), ("mult", C.c_int32)]
 
 
 class Pair(C.Structure):
@@ -76,7 +77,8 @@ class Result(C.Structure):
 CANDIDATE_DTYPE = np.dtype(
     [("view_begin", "<i4"), ("view_count", "<i4"), ("pair_begin", "<i4"), ("pair_count", "<i4"),
      ("min_sym_pairs", "<i8"), ("positive", "<i4"), ("flags_in", "<u4")], align=True)
-VIEW_DTYPE = np.dtype([("angle", "<i4"), ("col_begin", "<i4"), ("tie", "<i4"), ("tie_slot0", "<i4")], align=True)
+VIEW_DTYPE = np.dtype([("angle", "<i4"), ("col_begin", "<i4"), ("tie", "<i4"), ("tie_slot0", "<i4"), ("dup_of", "<i4"),
+                       ("mult", "<i4")], align=True)
 PAIR_DTYPE = np.dtype([("ci", "<f8"), ("si", "<f8"), ("zi", "<f8"), ("cj", "<f8"), ("sj", "<f8"), ("zj", "<f8")], align=True)
 RESULT_DTYPE = np.dtype(
     [("score", "<f4"), ("itn", "<i4"), ("istop", "<i4"), ("trf_nit", "<i4"), ("flags", "<u4"), ("n_data_rows", "<i4"),

@@ -432,6 +432,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   // ---- host tables ---------------------------------------------------------
   std::vector<int> view_cand(nviews, -1), view_angle(nviews), view_colbegin(nviews), view_tie(nviews, -1), view_tie_slot0(nviews, 0);
   std::vector<int> tie_views, cand_tie_begin(nc, 0), cand_tie_count(nc, 0);
+  std::vector<int> view_dupof(nviews, -1), view_mult(nviews, 1), view_dups((size_t)nviews * HB2_MAXDUP, -1);
   std::vector<long long> view_uoff(nviews);
   b->h_view_begin.resize(nc); b->h_view_count.resize(nc); b->h_mdata.resize(nc); b->h_msym.assign(nc, 0);
   b->h_uoff.resize(nc); b->h_symoff.resize(nc); b->h_symcap.resize(nc); b->h_cscoff.resize(nc);
@@ -461,6 +462,18 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       const hb2_view& w = views[vi];
       if (w.angle < 0 || w.angle >= B.nA || w.col_begin < 0 || w.col_begin + B.ZMC > ncolk) return fail(HB2_ERR_ARG, "bad view");
       view_cand[vi] = c; view_angle[vi] = w.angle; view_colbegin[vi] = w.col_begin;
+      static const bool no_dedupe = getenv("HB2_NO_DEDUPE") && atoi(getenv("HB2_NO_DEDUPE"));
+      if (w.dup_of >= 0 && w.tie < 0 && !no_dedupe) {  // duplicate of an earlier regular view of the same candidate
+        const int prim = q.view_begin + w.dup_of;
+        if (w.dup_of >= v || views[prim].angle != w.angle || views[prim].tie >= 0 || views[prim].dup_of >= 0)
+          return fail(HB2_ERR_ARG, "bad duplicate view");
+        int slot = 0;
+        while (slot < HB2_MAXDUP && view_dups[(size_t)prim * HB2_MAXDUP + slot] >= 0) ++slot;
+        if (slot < HB2_MAXDUP) {  // more than HB2_MAXDUP duplicates: the extra ones are computed on their own
+          view_dups[(size_t)prim * HB2_MAXDUP + slot] = vi;
+          view_dupof[vi] = prim; view_mult[vi] = 0; view_mult[prim] += 1;
+        }
+      }
       if (w.tie >= 0) {
         if (w.tie >= b->n_tie || w.tie_slot0 < 0 || w.tie_slot0 + B.ZMC > b->tie_TS) return fail(HB2_ERR_ARG, "bad tie view");
         if (B.ZMC > HB2_TIE_MAXZMC) return fail(HB2_ERR_GEOMETRY, "tie views need L3*MC <= 16");
@@ -491,6 +504,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(upload(b->pool, &B.view_cand, view_cand, st));
   CKC(upload(b->pool, &B.view_angle, view_angle, st));
   CKC(upload(b->pool, &B.view_colbegin, view_colbegin, st));
+  CKC(upload(b->pool, &B.view_dupof, view_dupof, st));
+  CKC(upload(b->pool, &B.view_mult, view_mult, st));
+  CKC(upload(b->pool, &B.view_dups, view_dups, st));
   b->n_tie_views = (int)tie_views.size();
   B.n_tie_views = b->n_tie_views; B.tie_TS = b->tie_TS;
   CKC(upload(b->pool, &B.cand_tie_begin, cand_tie_begin, st));

@@ -8,6 +8,7 @@
 #define HB2_BLOCK 256
 #define HB2_FWD_U 8      // samples in flight per lane of the forward projector
 #define HB2_ELL_W 4      // fixed-width part of the symmetry transpose lists
+#define HB2_MAXDUP 3     // duplicates of one view served by its first copy
 #define HB2_ELL_NONE 0x7FFFFFFF
 #define HB2_ELL_OVERFLOW 0x7FFFFFFE  // in plane W-1: the voxel has more than W entries, use the CSR list
 
@@ -68,6 +69,10 @@ struct BD {
   double* part_x;
   float* part_s;   // score partials: 3 per CTA (dot, pp, bb)
   int part_u_n, part_us_per_cand, part_v_per_cand, part_x_per_cand;
+  // Halton-duplicated views (SLR:1559-1571): identical rows, computed once
+  const int* view_dupof;          // [nviews] view index of the first copy, or -1
+  const int* view_mult;           // [nviews] 1 + number of duplicates (0 for a duplicate)
+  const int* view_dups;           // [nviews][HB2_MAXDUP] view indices of the duplicates of a first copy, -1 padded
   // tie views (exact per-sample slices); null / 0 when the batch has none
   const int* view_tie;            // [nviews] tie index or -1
   const int* view_tie_slot0;      // [nviews]
@@ -520,14 +525,24 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
   const int c = B.view_cand[view];
   if (B.view_tie && B.view_tie[view] >= 0) return;  // tie views: k_fwd_tie (rows and partials)
+  if (B.view_dupof[view] >= 0) return;              // duplicate of an earlier view: served by that view's CTAs
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ int s_colk[HB2_MAX_ZMC];
+  int dupv[HB2_MAXDUP];
+#pragma unroll
+  for (int d = 0; d < HB2_MAXDUP; ++d) dupv[d] = B.view_dups[view * HB2_MAXDUP + d];
   const LsmrState& S = B.st[c];
   bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
   if (!act) {
     if (threadIdx.x == 0) {
-      if (mode == MODE_LSMR) B.part_u[blockIdx.x] = 0.f;
-      if (mode == MODE_SCORE) { B.part_s[3 * blockIdx.x] = 0.f; B.part_s[3 * blockIdx.x + 1] = 0.f; B.part_s[3 * blockIdx.x + 2] = 0.f; }
+#pragma unroll
+      for (int d = -1; d < HB2_MAXDUP; ++d) {
+        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+        if (vw < 0) continue;
+        const int pb = vw * ntiles + tile;
+        if (mode == MODE_LSMR) B.part_u[pb] = 0.f;
+        if (mode == MODE_SCORE) { B.part_s[3 * pb] = 0.f; B.part_s[3 * pb + 1] = 0.f; B.part_s[3 * pb + 2] = 0.f; }
+      }
     }
     return;
   }
@@ -587,9 +602,15 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
             if (mode == MODE_LSMR) {
               float un = fadd_(fmul_(fmul_(urow[ri], inv_beta), -alpha), sum);
               urow[ri] = un;
+#pragma unroll
+              for (int d = 0; d < HB2_MAXDUP; ++d)
+                if (dupv[d] >= 0) (B.u + B.view_uoff[dupv[d]])[ri] = un;  // identical row of the duplicate view
               ss += un * un;
             } else if (mode == MODE_PLAIN) {
               urow[ri] = sum;
+#pragma unroll
+              for (int d = 0; d < HB2_MAXDUP; ++d)
+                if (dupv[d] >= 0) (B.u + B.view_uoff[dupv[d]])[ri] = sum;
             } else {
               float pred = B.clip_pred ? fmaxf(sum, 0.f) : sum;
               float bv = brow[ri];
@@ -600,12 +621,26 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
       }
     }
   }
+  // partials of the view and of the duplicates it serves (identical rows -> identical partial sums)
   if (mode == MODE_LSMR) {
     float tot = block_sum(ss, red);
-    if (threadIdx.x == 0) B.part_u[blockIdx.x] = tot;
+    if (threadIdx.x == 0) {
+      B.part_u[blockIdx.x] = tot;
+#pragma unroll
+      for (int d = 0; d < HB2_MAXDUP; ++d)
+        if (dupv[d] >= 0) B.part_u[dupv[d] * ntiles + tile] = tot;
+    }
   } else if (mode == MODE_SCORE) {
     float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
-    if (threadIdx.x == 0) { B.part_s[3 * blockIdx.x] = t0; B.part_s[3 * blockIdx.x + 1] = t1; B.part_s[3 * blockIdx.x + 2] = t2; }
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int d = -1; d < HB2_MAXDUP; ++d) {
+        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+        if (vw < 0) continue;
+        const int pb = vw * ntiles + tile;
+        B.part_s[3 * pb] = t0; B.part_s[3 * pb + 1] = t1; B.part_s[3 * pb + 2] = t2;
+      }
+    }
   }
 }
 
@@ -910,6 +945,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ int s_ang[HB2_ADJ_VIEWS];
   __shared__ long long s_uoff[HB2_ADJ_VIEWS];
+  __shared__ float s_w[HB2_ADJ_VIEWS];
   const LsmrState& S = B.st[c];
   bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
                                  : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
@@ -927,6 +963,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
   const int slot = live ? B.aslot[p] : 0;
   const int z0 = 4 * q;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
+  // Halton duplicates carry identical rows inside the solver (u starts as b and is updated row-wise), so the
+  // first copy can stand for them with its multiplicity; an arbitrary row vector (MODE_PLAIN, the API's
+  // apply_adjoint) must honour every row on its own.
+  const bool dedupe_adj = mode != MODE_PLAIN;
   const float beta = S.beta;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
@@ -934,13 +974,16 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
     const int nvc = min(HB2_ADJ_VIEWS, nv - v0);
     __syncthreads();
     for (int e = threadIdx.x; e < nvc; e += HB2_BLOCK) {
-      s_ang[e] = (B.view_tie && B.view_tie[vb + v0 + e] >= 0) ? -1 : B.view_angle[vb + v0 + e];
+      const bool skip = (B.view_tie && B.view_tie[vb + v0 + e] >= 0) || (dedupe_adj && B.view_dupof[vb + v0 + e] >= 0);
+      s_ang[e] = skip ? -1 : B.view_angle[vb + v0 + e];
       s_uoff[e] = B.view_uoff[vb + v0 + e];
+      s_w[e] = dedupe_adj ? (float)B.view_mult[vb + v0 + e] : 1.f;
     }
     __syncthreads();
     if (!live) continue;
     for (int vi = 0; vi < nvc; ++vi) {
-      if (s_ang[vi] < 0) continue;  // tie view (k_adj_tie)
+      if (s_ang[vi] < 0) continue;  // tie view (k_adj_tie) or duplicate (weight of its first copy)
+      const float ibw = ib * s_w[vi];
       const float* __restrict__ ub = B.u + s_uoff[vi] + z0 * MC;
       const uint16_t* __restrict__ am = B.amap + (size_t)s_ang[vi] * K * B.apitch + slot;
       for (int k = 0; k < K; ++k) {
@@ -949,14 +992,14 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj(BD B, int mode) {
           const float* __restrict__ uj = ub + (size_t)j * ZMP;
           if (MCT == 1) {
             const float4 r4 = ldg4(uj);
-            acc0 = fmaf(r4.x, ib, acc0); acc1 = fmaf(r4.y, ib, acc1);
-            acc2 = fmaf(r4.z, ib, acc2); acc3 = fmaf(r4.w, ib, acc3);
+            acc0 = fmaf(r4.x, ibw, acc0); acc1 = fmaf(r4.y, ibw, acc1);
+            acc2 = fmaf(r4.z, ibw, acc2); acc3 = fmaf(r4.w, ibw, acc3);
           } else {
             for (int mc = 0; mc < MC; ++mc) {
-              if (z0 + 0 < L3) acc0 = fmaf(__ldg(uj + 0 * MC + mc), ib, acc0);
-              if (z0 + 1 < L3) acc1 = fmaf(__ldg(uj + 1 * MC + mc), ib, acc1);
-              if (z0 + 2 < L3) acc2 = fmaf(__ldg(uj + 2 * MC + mc), ib, acc2);
-              if (z0 + 3 < L3) acc3 = fmaf(__ldg(uj + 3 * MC + mc), ib, acc3);
+              if (z0 + 0 < L3) acc0 = fmaf(__ldg(uj + 0 * MC + mc), ibw, acc0);
+              if (z0 + 1 < L3) acc1 = fmaf(__ldg(uj + 1 * MC + mc), ibw, acc1);
+              if (z0 + 2 < L3) acc2 = fmaf(__ldg(uj + 2 * MC + mc), ibw, acc2);
+              if (z0 + 3 < L3) acc3 = fmaf(__ldg(uj + 3 * MC + mc), ibw, acc3);
             }
           }
         }
@@ -1021,6 +1064,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
   const int c = blockIdx.y;
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ unsigned s_aoff[HB2_ADJ_VIEWS];
+  __shared__ float s_w[HB2_ADJ_VIEWS];
   const LsmrState& S = B.st[c];
   bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
                                  : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
@@ -1036,6 +1080,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
   const int p = t / NQ, q = t - p * NQ, z0 = 4 * q;
   const bool live = p < ndisk;
   const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
+  // Halton duplicates carry identical rows inside the solver (u starts as b and is updated row-wise), so the
+  // first copy can stand for them with its multiplicity; an arbitrary row vector (MODE_PLAIN, the API's
+  // apply_adjoint) must honour every row on its own.
+  const bool dedupe_adj = mode != MODE_PLAIN;
   const float beta = S.beta;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
@@ -1047,7 +1095,9 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
     __syncthreads();
     for (int e = threadIdx.x; e < HB2_ADJ_VIEWS; e += HB2_BLOCK) {
       const int vw = vb + v0 + min(e, nvc - 1);  // tail entries repeat the last view
-      s_aoff[e] = (B.view_tie && B.view_tie[vw] >= 0) ? 0xFFFFFFFFu : (unsigned)B.view_angle[vw] * kstride;
+      const bool skip = (B.view_tie && B.view_tie[vw] >= 0) || (dedupe_adj && B.view_dupof[vw] >= 0);  // k_adj_tie / weight of the first copy
+      s_aoff[e] = skip ? 0xFFFFFFFFu : (unsigned)B.view_angle[vw] * kstride;
+      s_w[e] = dedupe_adj ? (float)B.view_mult[vw] : 1.f;
     }
     __syncthreads();
     if (!live) continue;
@@ -1069,14 +1119,15 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_pq(BD B, int mode) {
       }
 #pragma unroll
       for (int w = 0; w < HB2_ADJ_VU; ++w) {
+        const float ibw = ib * s_w[vi + w];
         if (j0[w] != 0xFFFFu) {
-          acc0 = fmaf(r0[w].x, ib, acc0); acc1 = fmaf(r0[w].y, ib, acc1);
-          acc2 = fmaf(r0[w].z, ib, acc2); acc3 = fmaf(r0[w].w, ib, acc3);
+          acc0 = fmaf(r0[w].x, ibw, acc0); acc1 = fmaf(r0[w].y, ibw, acc1);
+          acc2 = fmaf(r0[w].z, ibw, acc2); acc3 = fmaf(r0[w].w, ibw, acc3);
         }
         if (KT == 2 && j1[w] != 0xFFFFu) {  // second sample of the same view in this voxel (rare)
           const float4 r1 = ldg4(ucand + ((unsigned)(v0 + vi + w) * rpv + j1[w] * (unsigned)L3P));
-          acc0 = fmaf(r1.x, ib, acc0); acc1 = fmaf(r1.y, ib, acc1);
-          acc2 = fmaf(r1.z, ib, acc2); acc3 = fmaf(r1.w, ib, acc3);
+          acc0 = fmaf(r1.x, ibw, acc0); acc1 = fmaf(r1.y, ibw, acc1);
+          acc2 = fmaf(r1.z, ibw, acc2); acc3 = fmaf(r1.w, ibw, acc3);
         }
       }
     }
@@ -1189,6 +1240,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
   __shared__ unsigned long long full_bar[HB2_ADJT_NS], empty_bar[HB2_ADJT_NS];
   __shared__ int s_ang[HB2_ADJT_MAXV];
   __shared__ uint16_t s_jlo[HB2_ADJT_MAXV], s_nr[HB2_ADJT_MAXV];
+  __shared__ float s_w[HB2_ADJT_MAXV];  // multiplicity of the view (Halton duplicates are skipped, their first copy counts twice)
   const LsmrState& S = B.st[c];
   bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
                                  : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
@@ -1211,7 +1263,10 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
   const int ustride = rmax * L3P;
   for (int e = threadIdx.x; e < nv; e += HB2_ADJT_THREADS) {
     const int a = B.view_angle[vb + e];
-    const bool tie = B.view_tie && B.view_tie[vb + e] >= 0;  // tie views are handled by k_adj_tie (BD::vtie)
+    // tie views are handled by k_adj_tie (BD::vtie); duplicates (solver modes only) by the weight of their first copy
+    const bool dedupe_adj = mode != MODE_PLAIN;
+    const bool tie = (B.view_tie && B.view_tie[vb + e] >= 0) || (dedupe_adj && B.view_dupof[vb + e] >= 0);
+    s_w[e] = dedupe_adj ? (float)B.view_mult[vb + e] : 1.f;
     s_ang[e] = a;
     s_jlo[e] = tie ? (uint16_t)0xFFFFu : B.tile_jlo[(size_t)a * B.ntile + tile];  // 0xFFFF: skip the view
     s_nr[e] = tie ? (uint16_t)0xFFFFu : B.tile_nr[(size_t)a * B.ntile + tile];
@@ -1267,6 +1322,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
           if (jl != 0xFFFF) {
             const uint16_t* mp = s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT) * HB2_BLOCK + threadIdx.x;
             const float* uw = s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride;
+            const float ibw = ib * s_w[st * HB2_ADJT_SV + w];
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
               const unsigned j = mp[(size_t)k * HB2_BLOCK];
@@ -1275,8 +1331,8 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
 #pragma unroll
                 for (int q4 = 0; q4 < NQT; ++q4) {
                   const float4 t = r[q4];
-                  acc[4 * q4 + 0] = fmaf(t.x, ib, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ib, acc[4 * q4 + 1]);
-                  acc[4 * q4 + 2] = fmaf(t.z, ib, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ib, acc[4 * q4 + 3]);
+                  acc[4 * q4 + 0] = fmaf(t.x, ibw, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ibw, acc[4 * q4 + 1]);
+                  acc[4 * q4 + 2] = fmaf(t.z, ibw, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ibw, acc[4 * q4 + 3]);
                 }
               }
             }

@@ -238,7 +238,7 @@ class BatchPlan:
         ZMC = L3 * MC
         nc = len(self.specs)
         cands = np.zeros(nc, dtype=_lib.CANDIDATE_DTYPE)
-        view_rows = []  # (angle, tie index or -1, first tie column slot)
+        view_rows = []  # [angle, tie index or -1, first tie column slot, dup_of, mult]
         colk = []
         self.cand_views = []  # per candidate: list of (angle_id, zi (1-D, or 2-D [L2, D2] for a tie view), h, c, n_rows_real)
         self.cand_view_slots = []  # per candidate: first view slot of every entry of cand_views (tie views may take several)
@@ -268,6 +268,7 @@ class BatchPlan:
                     stop = int(over[0]) + 1
             sel = np.nonzero(nrows[:stop] > 0)[0]
             cv, slots = [], []
+            first_of = {}  # (h, c) -> candidate-relative index of its first regular view
             cands[ci]["view_begin"] = nviews
             if len(sel):
                 prev = np.concatenate([np.full((len(hs), 1), -2, dtype=np.int64), ZI[:, :-1]], axis=1)
@@ -284,7 +285,14 @@ class BatchPlan:
                     if tv is None:
                         cv.append((int(aid[i]), ZI[hidx[i]], copies[i][0], copies[i][1], int(nrows[i])))
                         colk.append(tab[hidx[i]])
-                        view_rows.append((int(aid[i]), -1, 0))
+                        rel = nviews - int(cands[ci]["view_begin"])
+                        prim = first_of.get(copies[i])
+                        if prim is None:
+                            first_of[copies[i]] = rel
+                            view_rows.append([int(aid[i]), -1, 0, -1, 1])
+                        else:  # Halton duplicate of an earlier copy: identical rows
+                            view_rows[int(cands[ci]["view_begin"]) + prim][4] += 1
+                            view_rows.append([int(aid[i]), -1, 0, prim, 0])
                         nviews += 1
                     else:
                         cv.append((int(aid[i]), tv.zt, copies[i][0], copies[i][1], int(nrows[i])))
@@ -297,7 +305,7 @@ class BatchPlan:
                             cc = tv.cols[q * ZMC:(q + 1) * ZMC]
                             t[:len(cc)] = cc
                             colk.append(t)
-                            view_rows.append((int(aid[i]), tid, q * ZMC))
+                            view_rows.append([int(aid[i]), tid, q * ZMC, -1, 1])
                         nviews += nslot
             self.cand_views.append(cv)
             self.cand_view_slots.append(slots)
@@ -325,6 +333,8 @@ class BatchPlan:
             views["angle"] = vr[:, 0]
             views["tie"] = vr[:, 1]
             views["tie_slot0"] = vr[:, 2]
+            views["dup_of"] = vr[:, 3]
+            views["mult"] = vr[:, 4]
             views["col_begin"] = np.arange(nviews, dtype=np.int64) * ZMC
             self.colk = np.ascontiguousarray(np.concatenate(colk).reshape(-1), dtype=np.int32)
         else:

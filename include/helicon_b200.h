@@ -76,6 +76,10 @@ typedef struct {
   int32_t tie;         /* -1, or index of the tie view this slot belongs to (hb2_batch_set_ties): colk then lists
                           the image COLUMNS of column slots tie_slot0 .. tie_slot0 + L3*MC - 1 */
   int32_t tie_slot0;
+  int32_t dup_of;      /* -1, or the candidate-relative index of an EARLIER view with the same (h, c): the reference's
+                          Halton re-indexing repeats symmetry copies (SLR:1559-1571), their rows are identical; the
+                          projector kernels compute them once (forward: copy, adjoint: weight) */
+  int32_t mult;        /* 1 + number of later duplicates of this view (0 for a duplicate) */
 } hb2_view;
 
 /* One symmetry pair ((h_i,c_i),(h_j,c_j)) of the regulariser (SLR:1223-1243):
