@@ -4,6 +4,7 @@
 #include "hb2_trf.cuh"
 #include "hb2_symm.cuh"
 #include "hb2_tie.cuh"
+#include "hb2_adj_tile.cuh"
 
 #include <cub/cub.cuh>
 
@@ -889,10 +890,10 @@ static void launch_adj(hb2_batch* b, int mode) {
   }
   if (B.adj_tile) {
     const size_t sm = b->adj_tile_smem;
-#define ADJT(Q, K)                                                                                       \
-  do {                                                                                                   \
-    cudaFuncSetAttribute(k_adj_tile<Q, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);        \
-    k_adj_tile<Q, K><<<g, HB2_ADJT_THREADS, sm, st>>>(B, mode);                                                 \
+#define ADJT(Q, K)                                                                                                   \
+  do {                                                                                                               \
+    cudaFuncSetAttribute(k_adj_tile<Q, K, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+    k_adj_tile<Q, K, float, false><<<g, HB2_ADJT_THREADS, sm, st>>>(B, TD{}, B.u, nullptr, mode);                    \
   } while (0)
 #define ADJTQ(K) do { if (B.L3P == 4) ADJT(1, K); else if (B.L3P == 8) ADJT(2, K); else if (B.L3P == 12) ADJT(3, K); else ADJT(4, K); } while (0)
     if (B.K == 1) ADJTQ(1); else ADJTQ(2);
@@ -1013,6 +1014,8 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   const int max_iter = opt->trf_max_iter > 0 ? opt->trf_max_iter : 200;
   const dim3 g_n(gn, nc), g_m(gm, nc), g_sym(std::max(1, B.part_us_per_cand), nc);
   const dim3 g_adj(cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK), nc);
+  const size_t sm64 = (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.K * HB2_BLOCK * sizeof(uint16_t) +
+                      (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.rmax * B.L3P * sizeof(double);
   const unsigned g_fwd = (unsigned)b->nviews * ((B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS);
   const unsigned g_sc = cdiv(nc, 128);
   auto ew = [&](int op) { k_trf_ew<<<g_n, HB2_BLOCK, 0, st>>>(B, T, op); ++launches; };
@@ -1035,7 +1038,20 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
       k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;
     }
-    k_adj64<<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    if (B.adj_tile && sm64 <= 200 * 1024) {  // float64 instantiation of the TMA-staged tile adjoint
+      const dim3 gt(B.ntile, nc);
+#define ADJT64(Q, K)                                                                                                 \
+  do {                                                                                                               \
+    cudaFuncSetAttribute(k_adj_tile<Q, K, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm64);    \
+    k_adj_tile<Q, K, double, true><<<gt, HB2_ADJT_THREADS, sm64, st>>>(B, T, rows, dst, gate);                       \
+  } while (0)
+#define ADJT64Q(K) do { if (B.L3P == 4) ADJT64(1, K); else if (B.L3P == 8) ADJT64(2, K); else if (B.L3P == 12) ADJT64(3, K); else ADJT64(4, K); } while (0)
+      if (B.K == 1) ADJT64Q(1); else ADJT64Q(2);
+#undef ADJT64Q
+#undef ADJT64
+    } else {
+      k_adj64<<<g_adj, HB2_BLOCK, 0, st>>>(B, T, rows, dst, gate);
+    }
     ++launches;
   };
   auto read_counter = [&](int* dptr, int& v) -> cudaError_t {

@@ -1215,205 +1215,6 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_tile_rays(int K, int apitch, int 
   }
 }
 
-// ---------------------------------------------------------------------------
-// Adjoint, tile path (MC == 1, K <= 2, L3P <= 16): one CTA = one voxel tile
-// (8 x 32 in-plane patch, <= 256 voxels, one thread each, all slices in
-// registers).  profiles/r1_summary.md: with global gathers every view costs a
-// dependent L2 round trip (map entry -> row) and the kernel is bound by
-// loads-in-flight / latency.  Here both operands of a stage of HB2_ADJT_SV
-// views are brought to shared memory by the TMA engine (cp.async.bulk, mbarrier
-// completion, two stages in flight): the tile's 512-byte runs of the adjoint
-// map, and -- because a compact tile is crossed by a short contiguous range of
-// rays in every view -- one contiguous window [jlo, jlo+nr) x L3P of the view's
-// rows.  The inner loop then touches shared memory only.
-// Addition order: views, then k, then symmetry rows (= k_adj / k_adj_pq).
-// ---------------------------------------------------------------------------
-#define HB2_ADJT_SV 4      // views per stage
-#define HB2_ADJT_NS 4      // stages in flight
-#define HB2_ADJT_THREADS (HB2_BLOCK + 32)  // 8 consumer warps (one thread per voxel) + 1 producer warp
-#define HB2_ADJT_MAXV 256
-template <int NQT, int KT>
-__global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, int mode) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  const int c = blockIdx.y, tile = blockIdx.x;
-  __shared__ float red[HB2_BLOCK / 32];
-  __shared__ unsigned long long full_bar[HB2_ADJT_NS], empty_bar[HB2_ADJT_NS];
-  __shared__ int s_ang[HB2_ADJT_MAXV];
-  __shared__ uint16_t s_jlo[HB2_ADJT_MAXV], s_nr[HB2_ADJT_MAXV];
-  __shared__ float s_w[HB2_ADJT_MAXV];  // multiplicity of the view (Halton duplicates are skipped, their first copy counts twice)
-  const LsmrState& S = B.st[c];
-  bool act = (mode == MODE_LSMR) ? (S.active != 0 && !S.skip_adj)
-                                 : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
-  const int pi = c * B.part_v_per_cand + blockIdx.x;
-  if (!act) {
-    if (threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
-    return;
-  }
-  constexpr int L3P = 4 * NQT;
-  const int ndisk_t = B.tile_begin[tile + 1] - B.tile_begin[tile];
-  const int p = B.tile_begin[tile] + threadIdx.x;
-  const bool producer = threadIdx.x >= HB2_BLOCK;
-  const bool live = threadIdx.x < ndisk_t;
-  const unsigned rpv = (unsigned)B.rows_per_view;
-  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
-  const int rmax = B.rmax;
-  // dynamic shared memory: [NS][SV][KT][256] map entries, then [NS][SV][rmax*L3P] row windows
-  uint16_t* s_map = reinterpret_cast<uint16_t*>(dsm);
-  float* s_u = reinterpret_cast<float*>(dsm + (size_t)HB2_ADJT_NS * HB2_ADJT_SV * KT * HB2_BLOCK * sizeof(uint16_t));
-  const int ustride = rmax * L3P;
-  for (int e = threadIdx.x; e < nv; e += HB2_ADJT_THREADS) {
-    const int a = B.view_angle[vb + e];
-    // tie views are handled by k_adj_tie (BD::vtie); duplicates (solver modes only) by the weight of their first copy
-    const bool dedupe_adj = mode != MODE_PLAIN;
-    const bool tie = (B.view_tie && B.view_tie[vb + e] >= 0) || (dedupe_adj && B.view_dupof[vb + e] >= 0);
-    s_w[e] = dedupe_adj ? (float)B.view_mult[vb + e] : 1.f;
-    s_ang[e] = a;
-    s_jlo[e] = tie ? (uint16_t)0xFFFFu : B.tile_jlo[(size_t)a * B.ntile + tile];  // 0xFFFF: skip the view
-    s_nr[e] = tie ? (uint16_t)0xFFFFu : B.tile_nr[(size_t)a * B.ntile + tile];
-  }
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < HB2_ADJT_NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], HB2_BLOCK / 32); }
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  __syncthreads();
-  const int nstage = (nv + HB2_ADJT_SV - 1) / HB2_ADJT_SV;
-  const float ib = mode == MODE_PLAIN ? 1.f : S.inv_beta;
-  const float beta = S.beta;
-  float acc[4 * NQT];
-#pragma unroll
-  for (int i = 0; i < 4 * NQT; ++i) acc[i] = 0.f;
-  if (producer) {
-    // producer warp: lane w of a stage loads view st*SV + w (K map runs of 512 bytes + the row window)
-    const float* __restrict__ ucand = B.u + B.cand_uoff[c];
-    const uint16_t* __restrict__ amt = B.amap + (size_t)tile * HB2_BLOCK;
-    const int w = threadIdx.x - HB2_BLOCK;
-    for (int st = 0; st < nstage; ++st) {
-      const int buf = st % HB2_ADJT_NS;
-      if (st >= HB2_ADJT_NS) mbar_wait(&empty_bar[buf], (unsigned)(((st / HB2_ADJT_NS) - 1) & 1));
-      const int v = st * HB2_ADJT_SV + w;
-      const bool has = w < HB2_ADJT_SV && v < nv && s_nr[min(v, nv - 1)] != 0xFFFFu;
-      const unsigned nr = has ? s_nr[v] : 0;
-      unsigned tot = has ? KT * HB2_BLOCK * (unsigned)sizeof(uint16_t) + nr * L3P * (unsigned)sizeof(float) : 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-      if (w == 0) mbar_expect_tx(&full_bar[buf], tot);
-      __syncwarp();
-      if (has) {
-        const size_t arow = (size_t)s_ang[v] * KT * B.apitch;
-#pragma unroll
-        for (int k = 0; k < KT; ++k)
-          bulk_g2s(s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT + k) * HB2_BLOCK, amt + arow + (size_t)k * B.apitch,
-                   HB2_BLOCK * (unsigned)sizeof(uint16_t), &full_bar[buf]);
-        if (nr)
-          bulk_g2s(s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride, ucand + ((size_t)v * rpv + (size_t)s_jlo[v] * L3P),
-                   nr * L3P * (unsigned)sizeof(float), &full_bar[buf]);
-      }
-    }
-  } else {
-    for (int st = 0; st < nstage; ++st) {
-      const int buf = st % HB2_ADJT_NS;
-      mbar_wait(&full_bar[buf], (unsigned)((st / HB2_ADJT_NS) & 1));
-      if (live) {
-        const int nvs = min(HB2_ADJT_SV, nv - st * HB2_ADJT_SV);
-#pragma unroll
-        for (int w = 0; w < HB2_ADJT_SV; ++w) {
-          const int jl = w < nvs ? (int)s_jlo[st * HB2_ADJT_SV + w] : 0xFFFF;
-          if (jl != 0xFFFF) {
-            const uint16_t* mp = s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT) * HB2_BLOCK + threadIdx.x;
-            const float* uw = s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride;
-            const float ibw = ib * s_w[st * HB2_ADJT_SV + w];
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-              const unsigned j = mp[(size_t)k * HB2_BLOCK];
-              if (j != 0xFFFFu) {
-                const float4* r = reinterpret_cast<const float4*>(uw + ((int)j - jl) * L3P);
-#pragma unroll
-                for (int q4 = 0; q4 < NQT; ++q4) {
-                  const float4 t = r[q4];
-                  acc[4 * q4 + 0] = fmaf(t.x, ibw, acc[4 * q4 + 0]); acc[4 * q4 + 1] = fmaf(t.y, ibw, acc[4 * q4 + 1]);
-                  acc[4 * q4 + 2] = fmaf(t.z, ibw, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(t.w, ibw, acc[4 * q4 + 3]);
-                }
-              }
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[buf]);  // this warp is done with the stage's buffers
-    }
-  }
-  float ss = 0.f;
-  if (live && !producer) {
-    const int L3 = B.L3;
-    const int g0 = p * L3P;
-    const float* __restrict__ us = B.u + B.cand_uoff[c] + B.cand_mdata[c];
-    const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
-    float* vdst = (mode == MODE_PLAIN ? B.xs : B.v) + (size_t)c * B.npad + g0;
-    if (B.vtie && B.cand_tie_count[c] > 0) {  // rows of the tie views (k_adj_tie)
-      const float4* vt = reinterpret_cast<const float4*>(B.vtie + (size_t)c * B.npad + g0);
-#pragma unroll
-      for (int q4 = 0; q4 < NQT; ++q4) {
-        const float4 t = vt[q4];
-        acc[4 * q4 + 0] += t.x; acc[4 * q4 + 1] += t.y; acc[4 * q4 + 2] += t.z; acc[4 * q4 + 3] += t.w;
-      }
-    }
-#pragma unroll
-    for (int q4 = 0; q4 < NQT; ++q4) {
-      int ev[HB2_ELL_W][4];
-#pragma unroll
-      for (int w = 0; w < HB2_ELL_W; ++w) {
-        const int4 e4 = __ldg(reinterpret_cast<const int4*>(ell + (size_t)w * B.npad) + q4);
-        ev[w][0] = e4.x; ev[w][1] = e4.y; ev[w][2] = e4.z; ev[w][3] = e4.w;
-      }
-      float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mode == MODE_LSMR) old = *reinterpret_cast<const float4*>(vdst + 4 * q4);
-      float vals[HB2_ELL_W][4];
-#pragma unroll
-      for (int w = 0; w < HB2_ELL_W; ++w)
-#pragma unroll
-        for (int tz = 0; tz < 4; ++tz) {
-          const bool ok = ev[w][tz] < 0 || ev[w][tz] < HB2_ELL_OVERFLOW;  // a real entry (either sign)
-          vals[w][tz] = ok ? __ldg(us + (ev[w][tz] & 0x7fffffff)) : 0.f;
-        }
-      float vn[4];
-#pragma unroll
-      for (int tz = 0; tz < 4; ++tz) {
-        float s2 = acc[4 * q4 + tz];
-        if (ev[HB2_ELL_W - 1][tz] == HB2_ELL_OVERFLOW) {  // long list: walk the CSR copy
-          const int* __restrict__ ptr = B.csc_ptr + (size_t)c * (B.npad + 1) + g0 + 4 * q4 + tz;
-          const int* __restrict__ ent = B.csc_ent + B.cand_cscoff[c];
-          for (int e = ptr[0]; e < ptr[1]; ++e) {
-            const int x = ent[e];
-            const float val = __ldg(us + (x & 0x7fffffff));
-            s2 = fmaf(x < 0 ? -val : val, ib, s2);
-          }
-        } else {
-#pragma unroll
-          for (int w = 0; w < HB2_ELL_W; ++w)
-            if (ev[w][tz] != HB2_ELL_NONE) s2 = fmaf(ev[w][tz] < 0 ? -vals[w][tz] : vals[w][tz], ib, s2);
-        }
-        const float o = tz == 0 ? old.x : (tz == 1 ? old.y : (tz == 2 ? old.z : old.w));
-        vn[tz] = mode == MODE_LSMR ? fadd_(fmul_(o, -beta), s2) : s2;
-        ss += vn[tz] * vn[tz];
-      }
-      *reinterpret_cast<float4*>(vdst + 4 * q4) = make_float4(vn[0], vn[1], vn[2], vn[3]);
-    }
-    (void)L3;
-  }
-  if (mode != MODE_PLAIN) {  // 9 warps: the producer warp only joins the barrier
-    ss = warp_sum(ss);
-    if (!producer && (threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float tot = 0.f;
-#pragma unroll
-      for (int w = 0; w < HB2_BLOCK / 32; ++w) tot += red[w];
-      B.part_v[pi] = tot;
-    }
-  }
-}
-
 // ===========================================================================
 // vector update (lsmr.py:364-368) fused with v normalisation and ||x||^2
 // ===========================================================================
