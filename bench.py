@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--positive", type=int, default=0,
                     help="positive_constraint passed to the solver (0 = unbounded LSMR path; -1 = reference default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-positive-rule", action="store_true", help="skip the secondary positive_constraint=-1 measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
     ap.add_argument("--e2e-batches", type=int, default=3, help="batches per search_grid() call of the e2e measurement")
     ap.add_argument("--cpu-iters", type=int, default=60)
@@ -371,6 +372,27 @@ def main():
     e2e_val = float(np.mean(e2e_vals))
     d2h = int(out["scores"].size * 4 + out["itn"].size * 4)
 
+    # ---- the same call with the reference's DEFAULT positive-constraint rule (SLR:352-355): for this amyloid-like
+    # geometry every candidate then also runs the bounded TRF branch of scipy's lsq_linear (float64) --------------
+    posrule = None
+    if args.positive == 0 and not args.no_positive_rule:
+        bi = (args.warmup + args.steps) * world * per_rank + 2 * n_tw * world * N_RISE
+        tw_idx = [(bi // N_RISE + q) % N_TWIST for q in range(2 * world)]
+        barrier()
+        t0 = time.perf_counter()
+        outp = search_grid(np.array(img, copy=True), APIX, TWISTS[tw_idx], RISES, positive_constraint=-1,
+                           device=local_rank, stream=stream, batch_candidates=100, pipelined=not args.no_pipeline,
+                           shard=(rank, world))
+        outp = gather_grid_results(outp, top_k=10, dist=dist, device="cuda")
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        posrule = dict(value=outp["n_candidates"] / float(tt.item()), unit="candidates/s",
+                       candidates=int(outp["n_candidates"]),
+                       bounded_fraction=float(np.mean((outp["flags"][np.isfinite(outp["scores"])] & 4) != 0)),
+                       note="search_grid(positive_constraint=-1), host image in -> host scores out; one un-warmed call")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -425,6 +447,8 @@ def main():
         kernel_share=dict(lsmr_phase_ms=lsmr_ms, fwd_data_ms=fwd_ms, fwd_sym_ms=sym_ms, adjoint_ms=adj_ms,
                           update_ms=upd_ms, scalar_ms=scal_ms),
     )
+    if posrule is not None:
+        line["e2e_positive_rule_default"] = posrule
     if not args.no_cpu_baseline:
         sel = [tasks[(args.warmup * args.batch + 17) % len(tasks)]]
         itn_ref = int(round(itn_sum / max(1, ncand)))

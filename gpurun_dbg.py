@@ -1,19 +1,25 @@
-import sys, os; sys.path.insert(0,'.')
+import sys, os, time; sys.path.insert(0,'.')
 import numpy as np, warnings; warnings.filterwarnings("ignore")
+import torch
+import bench
 from helicon_b200.engine import Batch, Problem
-from helicon_b200.planner import CandidateSpec, MAX_EQUATIONS
-d=np.load("tests/golden/solve_nn_unb_64.npz")
-apix, twist, rise, csym, pc, so, L3 = d["args"]; img=d["image"]; N=img.shape[0]; L3=int(L3)
-prob=Problem(img,1.0,N,N,N,0.0,N//2-1)
-n3=L3*prob.ndisk; target=min(MAX_EQUATIONS,int(max(N*N,n3)*so))
-b=Batch(prob,L3,[CandidateSpec(float(twist),float(rise/apix),1,target,target,False)])
-rng=np.random.default_rng(0)
-x=rng.standard_normal(b.n).astype(np.float32)
-y=b.apply_forward(0,x)
-np.save(f"gpurun_out/y_{os.environ.get('HB2_NO_DEDUPE','0')}.npy",y)
-g=b.apply_adjoint(0,y); np.save(f"gpurun_out/g_{os.environ.get('HB2_NO_DEDUPE','0')}.npy",g)
-res=b.solve(fixed_iters=1, check_every=1)
-print(os.environ.get('HB2_NO_DEDUPE'), "fwd |y|", np.linalg.norm(y), "res", res["score"], res["normr"], res["normA"], res["normar"])
-v=b.plan.views
-c0=b.plan.cands[0]
-print([(i,int(q["dup_of"])) for i,q in enumerate(v) if q["dup_of"]>=0])
+from helicon_b200.grid import BatchPipeline
+from helicon_b200.planner import MAX_EQUATIONS, CandidateSpec
+img = bench.synthetic_filament(); tasks = bench.grid_tasks(); g = tasks[0].geom
+prob = Problem(img, g["s"], g["D2"], g["L2"], g["D3"], 0.0, g["D3"] // 2 - 1)
+n3 = g["L3"] * prob.ndisk
+target = min(MAX_EQUATIONS, int(max(g["D2"] * g["L2"], n3) * g["sym_oversample"]))
+def specs(step): return [CandidateSpec(t.twist, t.rise / g["apix3d"], 1, target, target, False) for t in tasks[step*200:(step+1)*200]]
+pipe = BatchPipeline(device=0, pipelined=True)
+chunks=[specs(s) for s in range(6)]
+torch.cuda.synchronize(); T0=time.perf_counter(); last=T0
+for i,batch in pipe.run(prob, g["L3"], chunks):
+    t1=time.perf_counter()
+    res=batch.solve(profile=int(os.environ.get("PROF","0")))
+    t2=time.perf_counter()
+    tm=batch.timing()
+    batch.close()
+    t3=time.perf_counter()
+    print(f"step {i}: wait-for-batch {1e3*(t1-last):.0f} ms | solve call {1e3*(t2-t1):.0f} ms (lsmr {tm['lsmr_ms']:.0f}) | close {1e3*(t3-t2):.0f} ms | itn max {res['itn'].max()}")
+    last=t3
+torch.cuda.synchronize(); print("total", time.perf_counter()-T0)

@@ -61,33 +61,89 @@ struct hb2_problem {
   int* d_aslot = nullptr;             // [ndisk] tile*256 + rank inside the tile
 };
 
-// Device allocations of a batch come from the stream-ordered allocator (cudaMallocAsync on the batch's stream) with
-// the pool's release threshold lifted in hb2_problem_create: successive batches of a grid search reuse the same
-// physical memory without cudaMalloc/cudaFree round trips, and freeing never synchronises the device, so the setup
-// of the next batch (another stream, another host thread) overlaps the solve of the current one.
+// Device memory of a batch: one ARENA per (device, stream), bump-allocated.  A grid search alternates two streams
+// (grid.BatchPipeline), so in steady state every batch lands in the block its stream's previous batch used and no
+// allocator call happens at all -- cudaMalloc/cudaFree synchronise the device, and growing the stream-ordered pool
+// (cudaMallocAsync) was measured to stall a concurrently running solve by up to 2 s (profiles/r1_summary.md section 4).
+// Pools nest like a stack (batch pool, then temporaries of setup / of the bounded branch); what does not fit the
+// arena yet is served by cudaMalloc and remembered, and the arena is re-sized the next time it is empty.
+#include <map>
+#include <mutex>
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, top = 0, wanted = 0, high = 0;
+  int live = 0;  // pools with allocations in this arena
+};
+static std::mutex g_arena_mu;
+static std::map<std::pair<int, cudaStream_t>, Arena*> g_arenas;
+static Arena* arena_for(cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  Arena*& a = g_arenas[{dev, st}];
+  if (!a) a = new Arena();
+  return a;
+}
+
 struct DevPool {
-  std::vector<void*> ptrs;
-  size_t bytes = 0;
+  std::vector<void*> owned;  // overflow allocations (cudaMalloc)
+  size_t bytes = 0, overflow = 0;
   cudaStream_t stream = nullptr;
+  Arena* arena = nullptr;
+  size_t first = 0, last = 0;  // arena range of this pool
+  bool in_arena = false;
   template <typename T>
   cudaError_t alloc(T** p, size_t count, bool zero, cudaStream_t st) {
-    size_t nb = std::max<size_t>(count, 1) * sizeof(T);
+    const size_t nb = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
     stream = st;
-    cudaError_t e = cudaMallocAsync((void**)p, nb, st);
-    if (e != cudaSuccess) return e;
-    ptrs.push_back(*p);
+    if (!arena) arena = arena_for(st);
+    Arena& A = *arena;
+    if (A.live == 0 && !in_arena) {  // arena idle: re-size it if earlier batches did not fit
+      A.top = 0;
+      if (A.wanted > A.cap) {
+        if (A.base) { cudaStreamSynchronize(st); cudaFree(A.base); A.base = nullptr; A.cap = 0; }
+        const size_t want = A.wanted + A.wanted / 8;
+        if (cudaMalloc((void**)&A.base, want) == cudaSuccess) A.cap = want;
+        else cudaGetLastError();
+      }
+    }
+    cudaError_t e = cudaSuccess;
+    if (A.top + nb <= A.cap) {
+      if (!in_arena) { in_arena = true; first = A.top; A.live += 1; }
+      *p = reinterpret_cast<T*>(A.base + A.top);
+      A.top += nb; last = A.top;
+      A.high = std::max(A.high, A.top);
+    } else {
+      e = cudaMalloc((void**)p, nb);
+      if (e != cudaSuccess) return e;
+      owned.push_back(*p);
+      overflow += nb;
+      A.wanted = std::max(A.wanted, std::max(A.high, A.top) + overflow_total(A) + nb);
+    }
     bytes += nb;
     if (zero) e = cudaMemsetAsync(*p, 0, nb, st);
     return e;
   }
-  void release(void* p) {
-    for (auto& q : ptrs)
-      if (q == p) { cudaFreeAsync(q, stream); q = nullptr; }
+  size_t overflow_total(Arena&) const { return overflow; }
+  void release(void* p) {  // individual frees only matter for overflow blocks
+    for (auto& q : owned)
+      if (q == p) { cudaStreamSynchronize(stream); cudaFree(q); q = nullptr; }
   }
   void free_all() {
-    for (void* p : ptrs)
-      if (p) cudaFreeAsync(p, stream);
-    ptrs.clear();
+    if (!owned.empty()) {
+      cudaStreamSynchronize(stream);
+      for (void* p : owned)
+        if (p) cudaFree(p);
+      owned.clear();
+    }
+    if (in_arena) {
+      Arena& A = *arena;
+      if (A.top == last) A.top = first;  // stack discipline: give the range back
+      A.live -= 1;
+      if (A.live == 0) A.top = 0;
+      in_arena = false;
+    }
+    bytes = 0; overflow = 0;
   }
 };
 
@@ -158,6 +214,15 @@ extern "C" int hb2_stream_destroy(int device, void* stream) {
   if (!stream) return HB2_OK;
   CK(cudaSetDevice(device));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
+  {  // the stream's arena goes with it
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    auto it = g_arenas.find({device, (cudaStream_t)stream});
+    if (it != g_arenas.end() && it->second->live == 0) {
+      if (it->second->base) cudaFree(it->second->base);
+      delete it->second;
+      g_arenas.erase(it);
+    }
+  }
   CK(cudaStreamDestroy((cudaStream_t)stream));
   return HB2_OK;
 }
@@ -165,9 +230,11 @@ extern "C" int hb2_device_trim(int device) {
   if (hb2_device_count() <= 0) return HB2_OK;
   CK(cudaSetDevice(device));
   CK(cudaDeviceSynchronize());
-  cudaMemPool_t pool;
-  CK(cudaDeviceGetDefaultMemPool(&pool, device));
-  CK(cudaMemPoolTrimTo(pool, 0));
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  for (auto& kv : g_arenas) {
+    Arena* a = kv.second;
+    if (kv.first.first == device && a->live == 0 && a->base) { cudaFree(a->base); a->base = nullptr; a->cap = 0; a->top = 0; }
+  }
   return HB2_OK;
 }
 
@@ -231,12 +298,6 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   if (g->D2 / 2 > g->ny / 2 + 0 && (g->D2 > g->ny)) return fail(HB2_ERR_ARG, "D2 larger than the image");
   if (g->L2 > g->nx) return fail(HB2_ERR_ARG, "L2 larger than the image");
   CK(cudaSetDevice(device));
-  {
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;  // keep freed blocks cached for the next batch
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
   cudaStream_t st = (cudaStream_t)stream;
   auto* P = new hb2_problem();
   P->device = device;

@@ -128,8 +128,7 @@ class Batch:
         so = _lib.SolveOptions(**o)
         res = np.zeros(self.nc, dtype=_lib.RESULT_DTYPE)
         _lib.check(_lib.load().hb2_batch_solve(self._h, C.byref(so), _lib.ptr(res)))
-        for c in range(self.nc):
-            res[c]["n_data_rows"] = sum(v[4] for v in self.plan.cand_views[c])
+        res["n_data_rows"] = self.plan.cand_n_data_rows
         self.results = res
         return res
 

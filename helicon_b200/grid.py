@@ -31,10 +31,14 @@ class BatchPipeline:
     The caller closes each batch when it is done with it.
     """
 
+    _STREAMS = {}  # device -> the two library streams, kept for the life of the process: their memory arenas stay warm
+
     def __init__(self, device=0, pipelined=True):
         self.device = int(device)
         self.pipelined = bool(pipelined)
-        self.streams = [Stream(device), Stream(device)]
+        if self.device not in BatchPipeline._STREAMS:
+            BatchPipeline._STREAMS[self.device] = [Stream(device), Stream(device)]
+        self.streams = BatchPipeline._STREAMS[self.device]
         self._ex = ThreadPoolExecutor(max_workers=1) if pipelined else None
 
     def run(self, prob, L3, chunks):
@@ -64,9 +68,6 @@ class BatchPipeline:
         if self._ex is not None:
             self._ex.shutdown(wait=True)
             self._ex = None
-        for st in self.streams:
-            st.close()
-        self.streams = []
 
 
 def derive_geometry(ny, nx, apix2d_orig, rise, rise_max, tube_diameter, tube_diameter_inner, tube_length,

@@ -238,10 +238,11 @@ class BatchPlan:
         ZMC = L3 * MC
         nc = len(self.specs)
         cands = np.zeros(nc, dtype=_lib.CANDIDATE_DTYPE)
-        view_rows = []  # [angle, tie index or -1, first tie column slot, dup_of, mult]
+        vrows = []   # per candidate: int64 array [n_slots, 5] = angle, tie index or -1, first tie column slot, dup_of, mult
         colk = []
-        self.cand_views = []  # per candidate: list of (angle_id, zi (1-D, or 2-D [L2, D2] for a tie view), h, c, n_rows_real)
-        self.cand_view_slots = []  # per candidate: first view slot of every entry of cand_views (tie views may take several)
+        self._cv_src = []            # per candidate: what cand_views / cand_view_slots are built from (lazily)
+        self._cand_views = None
+        self.cand_n_data_rows = np.zeros(nc, dtype=np.int64)
         pair_meta = []
         tie_zlo, tie_up, tie_rv = [], [], []
         nviews = 0
@@ -253,63 +254,82 @@ class BatchPlan:
             ncols_h = valid.sum(axis=1)
             nrows = ncols_h[hidx] * nvalid_rays[aid]
             tie_rows = {}
-            for i in range(len(copies)):
-                tv = ties.get((int(hidx[i]), int(copies[i][1])))
-                if tv is not None:
-                    va = angle_valid(int(aid[i]))  # [j, i]
-                    inside = (tv.zt[tv.cols] >= 0) & (tv.zt[tv.cols] < L3)  # [t, i]
-                    rv = (va[None, :, :] & inside[:, None, :]).any(axis=2)  # [t, j]
-                    tie_rows[i] = rv
-                    nrows[i] = int(rv.sum())
+            if ties:
+                for i in range(len(copies)):
+                    tv = ties.get((int(hidx[i]), int(copies[i][1])))
+                    if tv is not None:
+                        va = angle_valid(int(aid[i]))  # [j, i]
+                        inside = (tv.zt[tv.cols] >= 0) & (tv.zt[tv.cols] < L3)  # [t, i]
+                        rv = (va[None, :, :] & inside[:, None, :]).any(axis=2)  # [t, j]
+                        tie_rows[i] = rv
+                        nrows[i] = int(rv.sum())
             stop = len(copies)
             if sp.min_projection_lines > 0:
                 over = np.nonzero(np.cumsum(nrows) > sp.min_projection_lines)[0]
                 if len(over):
                     stop = int(over[0]) + 1
             sel = np.nonzero(nrows[:stop] > 0)[0]
-            cv, slots = [], []
-            first_of = {}  # (h, c) -> candidate-relative index of its first regular view
-            cands[ci]["view_begin"] = nviews
+            vbeg = nviews
+            slots = np.zeros(len(sel), dtype=np.int64)
             if len(sel):
                 prev = np.concatenate([np.full((len(hs), 1), -2, dtype=np.int64), ZI[:, :-1]], axis=1)
                 run_start = np.maximum.accumulate(np.where(valid & (ZI != prev), karange, 0), axis=1)
                 tab = np.full((len(hs), ZMC), -1, dtype=np.int32)
                 hh, kq = np.nonzero(valid)
-                tie_hs = {k[0] for k in ties}
-                keep = np.array([int(h) not in tie_hs for h in hh], dtype=bool) if ties else np.ones(len(hh), dtype=bool)
-                hh, kq = hh[keep], kq[keep]
+                if ties:
+                    tie_hs = {k[0] for k in ties}
+                    keep = np.array([int(h) not in tie_hs for h in hh], dtype=bool)
+                    hh, kq = hh[keep], kq[keep]
                 tab[hh, ZI[hh, kq] * MC + (kq - run_start[hh, kq])] = kq
-                for i in sel:
-                    tv = ties.get((int(hidx[i]), int(copies[i][1])))
-                    slots.append(nviews)
-                    if tv is None:
-                        cv.append((int(aid[i]), ZI[hidx[i]], copies[i][0], copies[i][1], int(nrows[i])))
-                        colk.append(tab[hidx[i]])
-                        rel = nviews - int(cands[ci]["view_begin"])
-                        prim = first_of.get(copies[i])
-                        if prim is None:
-                            first_of[copies[i]] = rel
-                            view_rows.append([int(aid[i]), -1, 0, -1, 1])
-                        else:  # Halton duplicate of an earlier copy: identical rows
-                            view_rows[int(cands[ci]["view_begin"]) + prim][4] += 1
-                            view_rows.append([int(aid[i]), -1, 0, prim, 0])
-                        nviews += 1
-                    else:
-                        cv.append((int(aid[i]), tv.zt, copies[i][0], copies[i][1], int(nrows[i])))
-                        ncol = len(tv.cols)
-                        nslot = (ncol + ZMC - 1) // ZMC
-                        tid = len(tie_zlo)
-                        tie_zlo.append(tv.zlo); tie_up.append(tv.up); tie_rv.append(tie_rows[i])
-                        for q in range(nslot):
-                            t = np.full(ZMC, -1, dtype=np.int32)
-                            cc = tv.cols[q * ZMC:(q + 1) * ZMC]
-                            t[:len(cc)] = cc
-                            colk.append(t)
-                            view_rows.append([int(aid[i]), tid, q * ZMC, -1, 1])
-                        nviews += nslot
-            self.cand_views.append(cv)
-            self.cand_view_slots.append(slots)
-            cands[ci]["view_count"] = nviews - cands[ci]["view_begin"]
+                if not ties:
+                    # all regular views: Halton duplicates (same (h, c)) are served by their first copy
+                    key = hidx[sel] * sp.csym + np.array([copies[i][1] for i in sel], dtype=np.int64)
+                    _, first_idx, inv = np.unique(key, return_index=True, return_inverse=True)
+                    first_pos = first_idx[inv]
+                    pos = np.arange(len(sel))
+                    is_dup = first_pos != pos
+                    vr = np.empty((len(sel), 5), dtype=np.int64)
+                    vr[:, 0] = aid[sel]; vr[:, 1] = -1; vr[:, 2] = 0
+                    vr[:, 3] = np.where(is_dup, first_pos, -1)
+                    vr[:, 4] = np.where(is_dup, 0, np.bincount(first_pos, minlength=len(sel)))
+                    vrows.append(vr)
+                    colk.append(tab[hidx[sel]])
+                    slots = vbeg + pos
+                    nviews += len(sel)
+                else:
+                    first_of = {}
+                    rows_c = []
+                    for q_, i in enumerate(sel):
+                        tv = ties.get((int(hidx[i]), int(copies[i][1])))
+                        slots[q_] = nviews
+                        if tv is None:
+                            colk.append(tab[hidx[i]][None, :])
+                            rel = nviews - vbeg
+                            prim = first_of.get(copies[i])
+                            if prim is None:
+                                first_of[copies[i]] = rel
+                                rows_c.append([int(aid[i]), -1, 0, -1, 1])
+                            else:  # Halton duplicate of an earlier copy: identical rows
+                                rows_c[prim][4] += 1
+                                rows_c.append([int(aid[i]), -1, 0, prim, 0])
+                            nviews += 1
+                        else:
+                            ncol = len(tv.cols)
+                            nslot = (ncol + ZMC - 1) // ZMC
+                            tid = len(tie_zlo)
+                            tie_zlo.append(tv.zlo); tie_up.append(tv.up); tie_rv.append(tie_rows[i])
+                            for q in range(nslot):
+                                t = np.full(ZMC, -1, dtype=np.int32)
+                                cc = tv.cols[q * ZMC:(q + 1) * ZMC]
+                                t[:len(cc)] = cc
+                                colk.append(t[None, :])
+                                rows_c.append([int(aid[i]), tid, q * ZMC, -1, 1])
+                            nviews += nslot
+                    vrows.append(np.array(rows_c, dtype=np.int64).reshape(-1, 5))
+            self._cv_src.append((sel, slots, nrows[sel] if len(sel) else np.zeros(0, np.int64)))
+            self.cand_n_data_rows[ci] = int(nrows[sel].sum()) if len(sel) else 0
+            cands[ci]["view_begin"] = vbeg
+            cands[ci]["view_count"] = nviews - vbeg
             # symmetry pairs (SLR:892, 1223-1243)
             cands[ci]["pair_begin"] = npairs
             plist = sorted_hsym_csym_pairs(sp.twist, sp.rise_pixel, sp.csym, L3) if sp.min_sym_pairs >= 0 else []
@@ -326,17 +346,18 @@ class BatchPlan:
             if ties:
                 fl |= _lib.HB2_FLAG_TIE_Z_EXACT
             cands[ci]["flags_in"] = fl
+        view_rows = np.concatenate(vrows) if vrows else np.zeros((0, 5), dtype=np.int64)
         self.cands = cands
         views = np.zeros(nviews, dtype=_lib.VIEW_DTYPE)
         if nviews:
-            vr = np.array(view_rows, dtype=np.int64)
+            vr = view_rows
             views["angle"] = vr[:, 0]
             views["tie"] = vr[:, 1]
             views["tie_slot0"] = vr[:, 2]
             views["dup_of"] = vr[:, 3]
             views["mult"] = vr[:, 4]
             views["col_begin"] = np.arange(nviews, dtype=np.int64) * ZMC
-            self.colk = np.ascontiguousarray(np.concatenate(colk).reshape(-1), dtype=np.int32)
+            self.colk = np.ascontiguousarray(np.concatenate(colk, axis=0).reshape(-1), dtype=np.int32)
         else:
             self.colk = np.zeros(0, dtype=np.int32)
         self.views = views
@@ -363,3 +384,32 @@ class BatchPlan:
         self.pairs = pairs
         self.finalized = True
         return self
+
+    def _build_views(self):
+        cvs, sls = [], []
+        for ci in range(len(self.specs)):
+            copies, aid, hidx, hs, ZI, ties = self._cand[ci]
+            sel, slots, nrows = self._cv_src[ci]
+            cv = []
+            for q, i in enumerate(sel):
+                tv = ties.get((int(hidx[i]), int(copies[i][1]))) if ties else None
+                cv.append((int(aid[i]), ZI[hidx[i]] if tv is None else tv.zt, copies[i][0], copies[i][1], int(nrows[q])))
+            cvs.append(cv)
+            sls.append([int(v) for v in slots])
+        self._cand_views, self._cand_view_slots = cvs, sls
+
+    @property
+    def cand_views(self):
+        """per candidate: list of (angle_id, zi (1-D, or 2-D [L2, D2] for a tie view), h, c, n_rows_real), in the
+        reference's copy order incl. Halton duplicates (built on demand: exports and tests only)."""
+        if self._cand_views is None:
+            self._build_views()
+        return self._cand_views
+
+    @property
+    def cand_view_slots(self):
+        """per candidate: first view slot of every entry of ``cand_views`` (tie views take several slots; note that a
+        duplicate copy has its OWN slot -- identical rows, stored twice)."""
+        if self._cand_views is None:
+            self._build_views()
+        return self._cand_view_slots
