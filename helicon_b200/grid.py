@@ -244,3 +244,46 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
                n_candidates=len(tasks), seconds=time.perf_counter() - t0, kernel_ms=kernel_ms, launches=launches)
     return out
+
+
+def search_images(images, apix, twists, rises, csyms=(1,), shard=(0, 1), dist=None, gather_device="cuda", **kw):
+    """BASELINE config 4: an independent (twist x rise [x csym]) grid search per image (e.g. 2-D class averages).
+
+    Images are dealt round-robin over ranks (``shard=(rank, world)``): every rank runs ``search_grid`` on its images
+    with the whole grid, so there is no data-path communication; with ``dist`` (an initialised ``torch.distributed``)
+    the per-image score maps are all-gathered at the end.  Returns ``dict(scores[n_img, (n_csym,) T, R], best=[(score,
+    twist, rise, csym)] per image, n_candidates, seconds)``; entries of images solved by other ranks are NaN / None
+    unless gathered.
+    """
+    rank, world = shard
+    t0 = time.perf_counter()
+    n_img = len(images)
+    shape = (len(csyms), len(np.atleast_1d(twists)), len(np.atleast_1d(rises)))
+    scores = np.full((n_img,) + shape, np.nan, dtype=np.float32)
+    best = [None] * n_img
+    ncand = 0
+    for ii in range(rank, n_img, world):
+        out = search_grid(images[ii], apix, twists, rises, csyms=csyms, **kw)
+        scores[ii] = out["scores"]
+        ncand += out["n_candidates"]
+        if out["top"]:
+            e = out["top"][0]
+            best[ii] = (e["score"], e["twist"], e["rise"], e["csym"])
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        import torch
+
+        t = torch.from_numpy(scores.reshape(n_img, -1)).to(gather_device)
+        parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, t)
+        allsc = torch.stack(parts).cpu().numpy()  # [world, n_img, grid]
+        own = np.arange(n_img) % dist.get_world_size()
+        scores = allsc[own, np.arange(n_img)].reshape((n_img,) + shape)
+        tw, ri = np.atleast_1d(twists), np.atleast_1d(rises)
+        for ii in range(n_img):
+            if best[ii] is None and np.any(np.isfinite(scores[ii])):
+                c, a, b = np.unravel_index(np.nanargmax(scores[ii]), shape)
+                best[ii] = (float(scores[ii][c, a, b]), float(tw[a]), float(ri[b]), int(csyms[c]))
+        nt = torch.tensor([ncand], device=gather_device)
+        dist.all_reduce(nt)
+        ncand = int(nt.item())
+    return dict(scores=scores, best=best, n_candidates=ncand, seconds=time.perf_counter() - t0)

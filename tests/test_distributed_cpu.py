@@ -83,3 +83,49 @@ def test_shards_are_disjoint_and_cover():
         assert sorted(seen) == [t.ti for t in tasks]
         sizes = [len(D.shard_tasks(tasks, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _img_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from helicon_b200 import grid as G
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    twists, rises = np.array([-2.0, -1.0]), np.array([4.5, 5.0, 5.5])
+
+    def fake_search_grid(image, apix, tw, ri, csyms=(1,), **kw):  # stands in for the GPU solve
+        sc = (np.float32(image.mean()) + 0.01 * np.arange(len(tw) * len(ri), dtype=np.float32)).reshape(1, len(tw), len(ri))
+        a, b = np.unravel_index(np.argmax(sc[0]), sc[0].shape)
+        return dict(scores=sc, n_candidates=sc.size,
+                    top=[dict(score=float(sc[0, a, b]), twist=float(tw[a]), rise=float(ri[b]), csym=1)])
+
+    G.search_grid, keep = fake_search_grid, G.search_grid
+    images = [np.full((8, 8), float(i), np.float32) for i in range(5)]
+    out = G.search_images(images, 5.0, twists, rises, shard=(rank, world), dist=dist, gather_device="cpu")
+    G.search_grid = keep
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, out["scores"], out["best"], out["n_candidates"]))
+
+
+def test_per_image_search_sharded_by_image_and_gathered():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_img_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, scores, best, ncand in got:
+        assert scores.shape == (5, 1, 2, 3) and np.all(np.isfinite(scores)) and ncand == 30
+        for i in range(5):
+            assert np.isclose(scores[i].max(), i + 0.05) and best[i][1:] == (-1.0, 5.5, 1)

@@ -352,3 +352,33 @@ def test_alternative_kernel_paths_agree_with_default(env, monkeypatch):
         # a different summation order moves the loosely converged LSMR iterate like a row permutation of the
         # reference does (2e-4..8e-4 at N=64, more on small cases): same bound as at the stopping point
         assert np.linalg.norm(a - b) <= 5e-3 * np.linalg.norm(a)
+
+
+def test_grid_scores_best_and_topk_vs_reference_grid():
+    """North-star criterion on a small grid: 5 twists x 4 rises on a 64x64 filament solved by the REFERENCE
+    (tests/golden/grid_64.npz, oracle/make_golden_grid.py) vs ONE batched GPU solve of the 20 candidates:
+    scores within 1e-5, identical best (twist, rise), identical top-K ordering (ties closer than 1e-5 may swap)."""
+    from helicon_b200.engine import Batch, Problem
+    from helicon_b200.planner import MAX_EQUATIONS, CandidateSpec
+
+    d = load("grid_64")
+    img, apix, L3, so = d["image"], float(d["apix"]), int(d["L3"]), int(d["sym_oversample"])
+    N = img.shape[0]
+    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+    target = min(MAX_EQUATIONS, int(max(N * N, L3 * prob.ndisk) * so))
+    specs = [CandidateSpec(float(tw), float(ri / apix), 1, target, target, False) for tw in d["twists"] for ri in d["rises"]]
+    batch = Batch(prob, L3, specs)
+    res = batch.solve()
+    batch.close(); prob.close()
+    got = res["score"].reshape(d["scores"].shape)
+    ref = d["scores"]
+    flagged = (res["flags"] & 3) != 0
+    print("max |dscore|", float(np.abs(got - ref).max()), "flagged", int(flagged.sum()))
+    assert np.abs(got - ref)[~flagged.reshape(ref.shape)].max() <= 1e-5
+    assert np.abs(got - ref).max() <= 2e-4
+    assert np.unravel_index(np.argmax(got), got.shape) == np.unravel_index(np.argmax(ref), ref.shape)
+    order_ref = np.argsort(-ref.ravel(), kind="stable")
+    order_got = np.argsort(-got.ravel(), kind="stable")
+    for k in range(10):  # top-10: same candidate unless the reference's own scores are closer than 1e-5 at that rank
+        if order_ref[k] != order_got[k]:
+            assert abs(ref.ravel()[order_ref[k]] - ref.ravel()[order_got[k]]) <= 1e-5, k
