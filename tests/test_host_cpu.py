@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_numpy_dtypes():
     assert _lib.CANDIDATE_DTYPE.itemsize == C.sizeof(_lib.Candidate) == 32
-    assert _lib.PAIR_DTYPE.itemsize == 48 and _lib.VIEW_DTYPE.itemsize == C.sizeof(_lib.View) == 16
+    assert _lib.PAIR_DTYPE.itemsize == 48 and _lib.VIEW_DTYPE.itemsize == C.sizeof(_lib.View) == 24
 
 
 def test_no_gpu_means_loud_failure():
