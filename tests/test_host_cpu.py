@@ -129,3 +129,26 @@ def test_column_slices_match_reference_tables():
             assert np.array_equal(np.where(ok, zref, -1), zi)
     zi, tie = planner.column_slices(1.0, 22, 6, 3.5)
     assert tie
+
+
+@pytest.mark.parametrize("name", ["data_nn_tiez", "data_nn_csym2"])
+def test_tie_views_reproduce_the_reference_slice_of_every_sample(name):
+    """Column->slice ties: the planner's TieView tables (from planner.reference_z_table and the M22 of the
+    copy's z-rotation) against the literal coordinate pipeline of the reference (SLR:1576-1581) for every ray j."""
+    from scipy.spatial.transform import Rotation as R
+
+    d = load(name)
+    s, twist, rise, csym, D2, L2, D3, D3i, L3, mpl = d["args"]
+    D2, L2, L3, csym = int(D2), int(L2), int(L3), int(csym)
+    s, twist, rise = float(s), float(twist), float(rise)
+    P = planner.BatchPlan(s, D2, L2, L3, [planner.CandidateSpec(twist, rise, csym, int(mpl), -1, False)])
+    copies, aid, hidx, hs, ZI, ties = P._cand[0]
+    assert P.has_ties and ties and not P.cand_tie_z[0]
+    (X0, Y0, Z0), _ = O.back_project_2d_coords_to_3d_coords(d["image"], s, D2, L2)
+    coords0 = np.vstack((X0.ravel(), Y0.ravel(), Z0.ravel())).T
+    for (hi, c), tv in ties.items():
+        h = hs[hi]
+        cc = R.from_euler("z", twist * h + 360 * c / csym, degrees=True).apply(coords0, inverse=True)
+        zi = np.rint(cc[:, 2].reshape(L2, D2, D2) - h * rise + L3 // 2).astype(np.int64)
+        assert all(np.array_equal(zi[:, j, :], tv.zt) for j in range(D2)), (h, c)
+        assert set(np.unique(tv.up)) <= {0, 1}
