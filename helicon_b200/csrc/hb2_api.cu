@@ -100,6 +100,10 @@ struct DevPool {
     Arena& A = *arena;
     if (A.live == 0 && !in_arena) {  // arena idle: re-size it if earlier batches did not fit
       A.top = 0;
+      if (A.cap == 0 && A.wanted == 0) {  // first use of this stream: start with a fifth of the free memory (<= 24 GB)
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) A.wanted = std::min<size_t>(fr / 5, (size_t)24 << 30) / 9 * 8;
+      }
       if (A.wanted > A.cap) {
         if (A.base) { cudaStreamSynchronize(st); cudaFree(A.base); A.base = nullptr; A.cap = 0; }
         const size_t want = A.wanted + A.wanted / 8;
@@ -621,10 +625,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     else k_build_amap<uint32_t><<<cdiv(na, 256), 256, 0, st>>>(B.nA, D2, B.ndisk, B.apitch, B.s, K, 1, b->d_cs, P->d_yx_data, P->d_aslot, (const uint32_t*)b->d_fmap, b->d_amap, d_kmax, b->d_amap_i);
     CKL();
     // consistency: every hit of the forward map must appear in the adjoint map
-    long long ns = (long long)B.nA * D2 * D2;
-    if (b->idx16) k_count_hits<uint16_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint16_t*)b->d_fmap, d_h1);
-    else k_count_hits<uint32_t><<<cdiv(ns, 256), 256, 0, st>>>(B.nA, D2, (const uint32_t*)b->d_fmap, d_h1);
-    k_count_amap<<<cdiv((long long)B.nA * K * B.apitch, 256), 256, 0, st>>>(B.nA, K, B.apitch, b->d_amap, d_h2);
+    if (b->idx16) k_count_hits<uint16_t><<<dim3(cdiv((long long)D2 * D2, 256), B.nA), 256, 0, st>>>(B.nA, D2, (const uint16_t*)b->d_fmap, d_h1);
+    else k_count_hits<uint32_t><<<dim3(cdiv((long long)D2 * D2, 256), B.nA), 256, 0, st>>>(B.nA, D2, (const uint32_t*)b->d_fmap, d_h1);
+    k_count_amap<<<dim3(cdiv((long long)K * B.apitch, 256), B.nA), 256, 0, st>>>(B.nA, K, B.apitch, b->d_amap, d_h2);
     CKL();
     std::vector<unsigned long long> h1(B.nA), h2(B.nA);
     CKC(cudaMemcpyAsync(h1.data(), d_h1, 8 * B.nA, cudaMemcpyDeviceToHost, st));

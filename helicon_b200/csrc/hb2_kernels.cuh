@@ -255,18 +255,26 @@ __global__ void k_build_amap(int nA, int D2, int ndisk, int apitch, double s, in
   }
 }
 
-// total samples with a hit per angle (consistency check of the adjoint map)
+// total samples with a hit per angle (consistency check of the adjoint map).  One CTA covers 256 consecutive
+// entries of ONE angle (grid.y = angle), counts with a ballot and issues a single atomic.
 template <typename IdxT>
-__global__ void k_count_hits(int nA, int D2, const IdxT* __restrict__ fmap, unsigned long long* __restrict__ hits) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nA * D2 * D2) return;
-  if (fmap[t] != Sent<IdxT>::v) atomicAdd(&hits[t / ((long long)D2 * D2)], 1ull);
+__global__ void __launch_bounds__(HB2_BLOCK) k_count_hits(int nA, int D2, const IdxT* __restrict__ fmap,
+                                                         unsigned long long* __restrict__ hits) {
+  const int a = blockIdx.y;
+  const long long per = (long long)D2 * D2;
+  const long long e = (long long)blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const bool hit = e < per && fmap[(size_t)a * per + e] != Sent<IdxT>::v;
+  const int n = __syncthreads_count(hit);
+  if (threadIdx.x == 0 && n) atomicAdd(&hits[a], (unsigned long long)n);
 }
-__global__ void k_count_amap(int nA, int K, int apitch, const uint16_t* __restrict__ amap,
-                             unsigned long long* __restrict__ hits) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nA * K * apitch) return;
-  if (amap[t] != 0xFFFFu) atomicAdd(&hits[t / ((long long)K * apitch)], 1ull);
+__global__ void __launch_bounds__(HB2_BLOCK) k_count_amap(int nA, int K, int apitch, const uint16_t* __restrict__ amap,
+                                                         unsigned long long* __restrict__ hits) {
+  const int a = blockIdx.y;
+  const long long per = (long long)K * apitch;
+  const long long e = (long long)blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const bool hit = e < per && amap[(size_t)a * per + e] != 0xFFFFu;
+  const int n = __syncthreads_count(hit);
+  if (threadIdx.x == 0 && n) atomicAdd(&hits[a], (unsigned long long)n);
 }
 
 // right-hand side in padded layout: b[view][z][mc][j] = pix[j][k] when the
@@ -275,7 +283,7 @@ __global__ void k_count_amap(int nA, int K, int apitch, const uint16_t* __restri
 __global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, float* __restrict__ bmax_bits) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)nviews * B.rows_per_view;
-  if (t >= total) return;
+  if (t >= total) return;  // rows_per_view is a multiple of 4, blocks of 256: a warp may still straddle two views
   int view = (int)(t / B.rows_per_view);
   int r = (int)(t % B.rows_per_view);
   int zm = r % B.ZMP, j = r / B.ZMP;
@@ -287,13 +295,19 @@ __global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, flo
     rowok = B.tie_rowvalid[((size_t)B.view_tie[view] * B.tie_TS + B.view_tie_slot0[view] + zm) * B.D2 + j] != 0;
   if (rowok) {
     val = pix[(size_t)j * B.L2 + k];
-    // float max via ordered-int trick
-    int c = B.view_cand[view];
-    int iv = __float_as_int(val);
-    iv = iv >= 0 ? iv : iv ^ 0x7fffffff;
-    atomicMax((int*)bmax_bits + c, iv);
   }
   B.b[B.view_uoff[view] + r] = val;
+  // max(b) per candidate: float max via the ordered-int trick, one atomic per group of lanes of the same candidate
+  // (one atomic per row serialised 224 k atomics per candidate on a single address)
+  {
+    const int c = B.view_cand[view];
+    int iv = (int)0x80000000;
+    if (rowok) { iv = __float_as_int(val); iv = iv >= 0 ? iv : iv ^ 0x7fffffff; }
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, c);  // lanes of this warp that belong to the same candidate
+    const int m = __reduce_max_sync(peers, iv);
+    if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31) && m != (int)0x80000000) atomicMax((int*)bmax_bits + c, m);
+  }
 }
 
 // ===========================================================================
