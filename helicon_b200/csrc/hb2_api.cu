@@ -839,6 +839,31 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   return HB2_OK;
 }
 
+// Half-set masks (fsc_test): upload, then rebuild the right-hand side and max(b) with the masks applied.
+extern "C" int hb2_batch_set_pixel_masks(hb2_batch* b, int32_t n_masks, const uint8_t* masks, const int32_t* cand_mask) {
+  if (!b || n_masks < 0 || (n_masks > 0 && !masks) || !cand_mask) return fail(HB2_ERR_ARG, "bad argument");
+  if (!b->created) return fail(HB2_ERR_STATE, "hb2_batch_set_pixel_masks must follow hb2_batch_create");
+  BD& B = b->B;
+  if (B.fwd_band) return fail(HB2_ERR_STATE, "pixel masks are not supported on the opt-in band path (HB2_FWD_BAND)");
+  CK(cudaSetDevice(b->P->device));
+  cudaStream_t st = b->stream;
+  const int nc = B.nc;
+  const size_t npx = (size_t)B.L2 * B.D2;
+  for (int c = 0; c < nc; ++c)
+    if (cand_mask[c] >= n_masks) return fail(HB2_ERR_ARG, "cand_mask entry out of range");
+  std::vector<uint8_t> hm(masks, masks + (size_t)n_masks * npx);
+  std::vector<int> cm(cand_mask, cand_mask + nc);
+  CK(upload(b->pool, &B.pixmask, hm, st));
+  CK(upload(b->pool, &B.cand_pixmask, cm, st));
+  if (n_masks == 0) B.pixmask = nullptr;
+  std::vector<int> neg(nc, (int)0x80000000);
+  CK(cudaMemcpyAsync(b->d_bmax, neg.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  k_build_rhs<<<cdiv((long long)b->nviews * B.rows_per_view, 256), 256, 0, st>>>(B, b->P->d_pix, b->nviews, b->d_bmax);
+  CKL();
+  CK(cudaStreamSynchronize(st));
+  return HB2_OK;
+}
+
 extern "C" void hb2_batch_destroy(hb2_batch* b) {
   if (!b) return;
   cudaSetDevice(b->P->device);

@@ -99,7 +99,18 @@ struct BD {
   int adj_tile;    // additionally L3P <= 16, <= 256 views per candidate, windows fit shared memory: k_adj_tile
   int only_cand;   // MODE_PLAIN: restrict to one candidate (-1 all)
   int clip_pred;
+  // half-set solves (fsc_test, SLR:175-203, 441-482): a candidate keeps only the data rows whose image pixel
+  // pid = k*D2 + j is set in its mask; the other rows are absent (u, b stay 0 like every other padded row)
+  const uint8_t* pixmask;       // [n_masks][L2*D2] or null
+  const int* cand_pixmask;      // [nc] mask index or -1
 };
+
+// pixel mask of candidate c (null: all rows kept)
+__device__ __forceinline__ const uint8_t* cand_mask(const BD& B, int c) {
+  if (!B.pixmask) return nullptr;
+  const int m = B.cand_pixmask[c];
+  return m < 0 ? nullptr : B.pixmask + (size_t)m * B.L2 * B.D2;
+}
 
 template <typename T>
 struct Sent;
@@ -293,6 +304,10 @@ __global__ void k_build_rhs(BD B, const float* __restrict__ pix, int nviews, flo
   bool rowok = k >= 0 && B.rayvalid[a * B.D2 + j];
   if (rowok && B.view_tie && B.view_tie[view] >= 0)  // tie view: the row exists iff a sample of ITS slices hits
     rowok = B.tie_rowvalid[((size_t)B.view_tie[view] * B.tie_TS + B.view_tie_slot0[view] + zm) * B.D2 + j] != 0;
+  if (rowok) {
+    const uint8_t* pm = cand_mask(B, B.view_cand[view]);
+    if (pm && !pm[(size_t)k * B.D2 + j]) rowok = false;  // row of the other half set
+  }
   if (rowok) {
     val = pix[(size_t)j * B.L2 + k];
   }
@@ -571,6 +586,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   const float* brow = B.b + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane & 3, sg = lane >> 2;
+  const uint8_t* __restrict__ pm = cand_mask(B, c);
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   for (int r = warp; r < HB2_TILE_RAYS; r += HB2_BLOCK / 32) {
     const int j = tile * HB2_TILE_RAYS + r;
@@ -612,6 +628,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
           for (int mc = 0; mc < MC; ++mc) {
             const int zm = z * MC + mc;
             if (s_colk[zm] < 0) continue;
+            if (pm && !pm[(size_t)s_colk[zm] * D2 + j]) continue;
             const size_t ri = (size_t)j * ZMP + zm;
             if (mode == MODE_LSMR) {
               float un = fadd_(fmul_(fmul_(urow[ri], inv_beta), -alpha), sum);

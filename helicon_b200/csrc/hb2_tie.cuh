@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
   float alpha = 0.f, inv_beta = 0.f;
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  const uint8_t* __restrict__ pm = cand_mask(B, c);
   for (int j = warp; j < D2; j += HB2_BLOCK / 32) {
     T acc[HB2_TIE_MAXZMC];
 #pragma unroll
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
     // lane t finishes column slot t
 #pragma unroll
     for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
-      if (lane == t && t < ZMC && s_colk[t] >= 0 && rv[(size_t)t * D2 + j]) {
+      if (lane == t && t < ZMC && s_colk[t] >= 0 && rv[(size_t)t * D2 + j] && !(pm && !pm[(size_t)s_colk[t] * D2 + j])) {
         const size_t ri = (size_t)j * ZMP + t;
         if (TRF) {
           urow[ri] = acc[t];

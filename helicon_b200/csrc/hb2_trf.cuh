@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_data(BD B, TD T, const doub
   double* urow = dst + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane & 3, sg = lane >> 2;
+  const uint8_t* __restrict__ pm = cand_mask(B, c);
   for (int r = warp; r < HB2_TILE_RAYS; r += HB2_BLOCK / 32) {
     const int j = tile * HB2_TILE_RAYS + r;
     if (j >= D2) break;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_data(BD B, TD T, const doub
           const double sum = sg == 0 ? acc[0] : (sg == 1 ? acc[1] : (sg == 2 ? acc[2] : acc[3]));
           for (int mc = 0; mc < MC; ++mc) {
             const int zm = z * MC + mc;
-            if (s_colk[zm] >= 0) urow[(size_t)j * ZMP + zm] = sum;
+            if (s_colk[zm] >= 0 && !(pm && !pm[(size_t)s_colk[zm] * D2 + j])) urow[(size_t)j * ZMP + zm] = sum;
           }
         }
       }

@@ -121,6 +121,14 @@ class Batch:
         self.nc = len(p.cands)
         self.results = None
 
+    # -- half sets (fsc_test) -----------------------------------------------
+    def set_pixel_masks(self, masks, cand_mask):
+        """masks: (n_masks, L2*D2) uint8 over pixel ids pid = k*D2 + j; cand_mask[c] = mask index or -1."""
+        masks = np.ascontiguousarray(masks, dtype=np.uint8).reshape(-1, self.problem.L2 * self.problem.D2)
+        cand_mask = np.ascontiguousarray(cand_mask, dtype=np.int32)
+        assert cand_mask.shape == (self.nc,)
+        _lib.check(_lib.load().hb2_batch_set_pixel_masks(self._h, len(masks), _lib.ptr(masks), _lib.ptr(cand_mask)))
+
     # -- solve -------------------------------------------------------------
     def solve(self, **opts):
         o = dict(DEFAULT_OPTIONS)

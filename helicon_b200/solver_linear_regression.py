@@ -5,7 +5,7 @@ Same function names, argument meaning, return types and array layouts as the
 reference; see INTEGRATION.md.  What is NOT implemented on the CUDA path raises
 ``NotImplementedError`` (there is no CPU fallback by design):
 interpolation other than "nn", tilt/psi/dy != 0 and ``refine_tilt_psi_dy``
-(general-orientation projector), ``fsc_test``, score metrics other than
+(general-orientation projector), score metrics other than
 "cosine", and solver models other than ``{"model": "lsq"}``.
 """
 
@@ -174,8 +174,6 @@ def lsq_reconstruct(
     _check_orientation(tilt_degree, psi_degree, dy_pixel)
     if algorithm.get("model", "lsq") != "lsq":
         _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
-    if fsc_test:
-        _unsupported("fsc_test >= 1 (half-set solves, SLR:441-482)")
     if score_metric != "cosine":
         _unsupported(f"score_metric {score_metric!r} (only 'cosine', SLR:500-525)")
     if refine_tilt_psi_dy_range is not None and any(
@@ -195,19 +193,53 @@ def lsq_reconstruct(
         target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * sym_oversample))  # SLR:148-150, 168-170
         positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
         spec = CandidateSpec(twist_degree, rise_pixel, csym, target, target, positive)
-        batch = Batch(prob, L3, [spec])
+        nsets = 3 if fsc_test >= 1 else 1
+        # fsc_test: the full set and the two half sets are three candidates of one batch that differ only in
+        # which data rows they keep (SLR:441-482); the symmetry rows are shared by construction.
+        batch = Batch(prob, L3, [spec] * nsets)
+        half1 = half2 = None
         try:
+            if nsets == 3:
+                _, kk, jj = batch.data_row_index(0)
+                set1 = split_pixel_ids((kk * D2 + jj).astype(np.int32), fsc_test)
+                m1 = np.zeros(L2 * D2, dtype=np.uint8)
+                m1[set1] = 1
+                batch.set_pixel_masks(np.stack([m1, 1 - m1]), [-1, 0, 1])
             res = batch.solve(clip_pred=int(thresh_fraction >= 0))
             rec3d = batch.rec3d(0)
-            score = np.float32(res[0]["score"])
-            info = dict(res=res[0].copy(), timing=batch.timing())
+            if nsets == 3:
+                half1, half2 = batch.rec3d(1), batch.rec3d(2)
+                s = [np.float32(r["score"]) for r in res]  # SLR:527-528
+                score = s[0] / 2 + (s[1] + s[2]) / 4
+            else:
+                score = np.float32(res[0]["score"])
+            info = dict(res=res[0].copy(), all_res=res.copy(), timing=batch.timing())
         finally:
             batch.close()
     finally:
         prob.close()
     if return_info:
-        return (rec3d, None, None), score, info
-    return (rec3d, None, None), score
+        return (rec3d, half1, half2), score, info
+    return (rec3d, half1, half2), score
+
+
+def split_pixel_ids(b_id, mode):
+    """Pixel ids of half set 1 exactly as ``split_A_b`` picks them (SLR:175-203): mode 1 random halves (the same
+    ``np.random.shuffle`` call on the same ``list(set(b_id))``, so a seeded global RNG reproduces the reference's
+    split), 2 even/odd, 3 left/right, else outer thirds vs centre."""
+    b_id_unique = sorted(set(b_id))
+    n = len(b_id_unique)
+    if mode == 1:
+        b_id_unique = list(set(b_id))
+        np.random.shuffle(b_id_unique)
+        set1 = b_id_unique[: n // 2]
+    elif mode == 2:
+        set1 = b_id_unique[::2]
+    elif mode == 3:
+        set1 = b_id_unique[: n // 2]
+    else:
+        set1 = b_id_unique[: n // 3] + b_id_unique[n * 2 // 3:]
+    return np.asarray(set1, dtype=np.int64)
 
 
 def refine_tilt_psi_dy(*args, **kwargs):

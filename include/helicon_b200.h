@@ -167,6 +167,13 @@ int hb2_batch_create(hb2_batch* b, int32_t n_cand, const hb2_candidate* cands, i
                      int32_t n_colk, const int32_t* colk, int32_t n_pairs, const hb2_pair* pairs);
 void hb2_batch_destroy(hb2_batch* b);
 
+/* Half-set solves (fsc_test, SLR:175-203 split_A_b + SLR:441-482): candidate c keeps only the data rows whose image
+ * pixel id pid = k*D2 + j (b_data_pid, SLR:1548) is set in masks[cand_mask[c]][L2*D2]; cand_mask[c] = -1 keeps all
+ * rows.  The host derives the sets from b_data_pid exactly as split_A_b does (incl. its np.random.shuffle for mode
+ * 1); the kernels drop the rows (forward rows, right-hand side, max(b) of the positive bound, score).  Call after
+ * hb2_batch_create, before hb2_batch_solve. */
+int hb2_batch_set_pixel_masks(hb2_batch* b, int32_t n_masks, const uint8_t* masks, const int32_t* cand_mask);
+
 /* number of symmetry rows of a candidate, and the rows themselves as (a,b)
  * voxel-index pairs in the reference's row order: A[r,a]=+1, A[r,b]=-1. */
 int hb2_batch_sym_rows(hb2_batch* b, int32_t cand, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity);

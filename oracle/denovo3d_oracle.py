@@ -500,6 +500,24 @@ def _hsym_rows_linear(Zi, Yi, Xi, Zj, Yj, Xj, mask, idx, n_x, seen):
 # ----------------------------------------------------------------------------
 # solve + score (SLR:31-547)
 # ----------------------------------------------------------------------------
+def split_A_b(A, b, b_id, mode):
+    """SLR:175-203: the two half sets of the data equations by image pixel id."""
+    uniq = sorted(set(b_id))
+    n = len(uniq)
+    if mode == 1:  # random halves: the reference shuffles list(set(b_id)) with the global numpy RNG
+        uniq = list(set(b_id))
+        np.random.shuffle(uniq)
+        first = uniq[: n // 2]
+    elif mode == 2:
+        first = uniq[::2]
+    elif mode == 3:
+        first = uniq[: n // 2]
+    else:
+        first = uniq[: n // 3] + uniq[n * 2 // 3:]
+    sel = np.isin(b_id, first)
+    return (A[sel], b[sel]), (A[~sel], b[~sel])
+
+
 def positive_rule(positive_constraint, rise_pixel, twist_degree, L3):
     """SLR:352-355."""
     pitch_pixel = round(rise_pixel * 360 / abs(twist_degree))
@@ -543,9 +561,11 @@ def lsq_reconstruct(
     interpolation="nn",
     return_details=False,
     fast=False,
+    fsc_test=0,
 ):
-    """SLR:31-547 for algorithm={'model':'lsq'}, fsc_test=0, score_metric='cosine',
-    no tilt/psi/dy refinement.  ``fast=True`` uses ``build_A_data_matrix_fast``."""
+    """SLR:31-547 for algorithm={'model':'lsq'}, score_metric='cosine', no tilt/psi/dy
+    refinement.  ``fast=True`` uses ``build_A_data_matrix_fast``.  ``fsc_test >= 1`` adds the
+    two half-set solves (SLR:441-482) and the combined score (SLR:527-528)."""
     D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
     rmin = reconstruct_diameter_3d_inner_pixel / 2
     rmax = D3 // 2 - 1
@@ -586,6 +606,18 @@ def lsq_reconstruct(
     score = cosine_similarity(pred, b_data)
     rec3d = np.zeros((L3, D3, D3), dtype=np.float32)
     rec3d[mask] = x
+    if fsc_test >= 1:
+        halves, scores = [], [score]
+        for A_h, b_h in split_A_b(A_data, b_data, b_pid, fsc_test):
+            x_h, _ = solve_lsq(A_h, b_h, A_hsym, b_hsym, positive)
+            pred = A_h.dot(x_h)
+            if thresh_fraction >= 0:
+                pred = np.clip(pred, 0, None)
+            scores.append(cosine_similarity(pred, b_h))
+            vol = np.zeros((L3, D3, D3), dtype=np.float32)
+            vol[mask] = x_h
+            halves.append(vol)
+        return (rec3d, halves[0], halves[1]), scores[0] / 2 + (scores[1] + scores[2]) / 4
     if return_details:
         return (rec3d, None, None), score, dict(
             A_data=A_data, b_data=b_data, b_pid=b_pid, A_hsym=A_hsym, x=x, res=res, positive=positive

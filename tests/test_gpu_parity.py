@@ -382,3 +382,30 @@ def test_grid_scores_best_and_topk_vs_reference_grid():
     for k in range(10):  # top-10: same candidate unless the reference's own scores are closer than 1e-5 at that rank
         if order_ref[k] != order_got[k]:
             assert abs(ref.ravel()[order_ref[k]] - ref.ravel()[order_got[k]]) <= 1e-5, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["fsc_mode1_48", "fsc_mode2_48", "fsc_mode3_48_c2", "fsc_mode4_32"])
+def test_half_set_solves_vs_reference_golden(solver, name):
+    """lsq_reconstruct(fsc_test=1..4): full + two half-set solves as three masked candidates of one batch."""
+    d = load(name)
+    apix, twist, rise, csym, pc, so, L3, mode, seed = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    np.random.seed(int(seed))
+    (rec, h1, h2), score, info = solver.lsq_reconstruct(
+        img, 1.0, float(twist), float(rise / apix), int(csym), positive_constraint=int(pc),
+        reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N,
+        reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so), interpolation="nn", fsc_test=int(mode),
+        return_info=True)
+    relf = lambda a, r: float(np.linalg.norm(a - r) / np.linalg.norm(r))
+    rels = [relf(rec, d["rec3d"]), relf(h1, d["half1"]), relf(h2, d["half2"])]
+    dscore = abs(float(score) - float(d["score"]))
+    print(f"{name}: itn={[int(r['itn']) for r in info['all_res']]} |dscore|={dscore:.2e} rel-L2={['%.1e' % r for r in rels]}")
+    # the halves keep disjoint, complementary row sets: zero support where the other half has its data
+    assert h1.shape == rec.shape == h2.shape and h1.dtype == np.float32
+    if info["res"]["flags"] & 3:
+        assert dscore <= 2e-4
+    else:
+        assert dscore <= 1e-5
+        assert max(rels) < 5e-3
