@@ -431,6 +431,51 @@ extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int3
   return HB2_OK;
 }
 
+// Exact per-column maps for in-plane tie views: appended to the batch's angle table as extra "angles".
+extern "C" int hb2_batch_add_exact_maps(hb2_batch* b, int32_t nE, const double* cos_sin, const double* x0rows,
+                                        int32_t* nvalid_rays) {
+  if (!b || nE <= 0 || !cos_sin || !x0rows) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_add_exact_maps must precede hb2_batch_create");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  const int D2 = B.D2, nA = B.nA, nT = nA + nE;
+  const size_t per = (size_t)D2 * D2, esz = b->idx16 ? 2 : 4;
+  double* cs2; void* fm2; uint8_t* rv2; int* tie2; double* d_x0;
+  CK(b->pool.alloc(&cs2, (size_t)2 * nT, false, st));
+  { uint8_t* p; CK(b->pool.alloc(&p, (size_t)nT * per * esz, false, st)); fm2 = p; }
+  CK(b->pool.alloc(&rv2, (size_t)nT * D2, true, st));
+  CK(b->pool.alloc(&tie2, (size_t)nT, true, st));
+  CK(b->pool.alloc(&d_x0, (size_t)nE * D2, false, st));
+  CK(cudaMemcpyAsync(cs2, b->d_cs, sizeof(double) * 2 * nA, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(cs2 + 2 * nA, cos_sin, sizeof(double) * 2 * nE, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(fm2, b->d_fmap, (size_t)nA * per * esz, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(rv2, b->d_rayvalid, (size_t)nA * D2, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(tie2, b->d_tie, sizeof(int) * nA, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(d_x0, x0rows, sizeof(double) * nE * D2, cudaMemcpyHostToDevice, st));
+  const long long ns = (long long)nE * per;
+  if (b->idx16)
+    k_build_fmap_exact<uint16_t><<<cdiv(ns, 256), 256, 0, st>>>(nE, D2, B.s, cs2 + 2 * nA, d_x0, P->d_rank_data,
+                                                                  (uint16_t*)fm2 + (size_t)nA * per, rv2 + (size_t)nA * D2);
+  else
+    k_build_fmap_exact<uint32_t><<<cdiv(ns, 256), 256, 0, st>>>(nE, D2, B.s, cs2 + 2 * nA, d_x0, P->d_rank_data,
+                                                                  (uint32_t*)fm2 + (size_t)nA * per, rv2 + (size_t)nA * D2);
+  CKL();
+  std::vector<uint8_t> rv((size_t)nE * D2);
+  CK(cudaMemcpyAsync(rv.data(), rv2 + (size_t)nA * D2, rv.size(), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int a = 0; a < nE; ++a) {
+    int cnt = 0;
+    for (int j = 0; j < D2; ++j) cnt += rv[(size_t)a * D2 + j];
+    if (nvalid_rays) nvalid_rays[a] = cnt;
+  }
+  b->d_cs = cs2; b->d_fmap = fm2; b->d_rayvalid = rv2; b->d_tie = tie2;
+  b->tie_per_angle.resize(nT, 0);
+  B.nA = nT; B.fmap = fm2; B.rayvalid = rv2;
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out) {
   if (!b || !out) return fail(HB2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->P->device));

@@ -228,6 +228,36 @@ __global__ void k_build_fmap(int nA, int D2, double s, const double* __restrict_
   }
 }
 
+// Exact maps for in-plane tie views: same arithmetic as k_build_fmap, but the depth coordinate x0 of
+// sample i comes from the reference's own coordinate table row of ONE image column (host: planner.reference_xz_tables;
+// the table's last-bit noise depends on (column, i) only and decides the half-integer roundings at 30/60/... degrees).
+template <typename IdxT>
+__global__ void k_build_fmap_exact(int nE, int D2, double s, const double* __restrict__ cs, const double* __restrict__ x0tab,
+                                   const int* __restrict__ rank, IdxT* __restrict__ fmap, uint8_t* __restrict__ rayvalid) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)nE * D2 * D2;
+  if (t >= total) return;
+  int i = (int)(t % D2);
+  int j = (int)((t / D2) % D2);
+  int a = (int)(t / ((long long)D2 * D2));
+  const int c0 = D2 / 2;
+  double C = cs[2 * a], S = cs[2 * a + 1];
+  double x0 = x0tab[(size_t)a * D2 + i], y0 = (double)(j - c0);
+  if (s != 1.0) y0 = __dmul_rn(y0, s);
+  double X = __dadd_rn(__fma_rn(S, y0, __dmul_rn(C, x0)), (double)c0);
+  double Y = __dadd_rn(__fma_rn(C, y0, __dmul_rn(-S, x0)), (double)c0);
+  double xr = rint(X), yr = rint(Y);
+  IdxT out = Sent<IdxT>::v;
+  if (xr >= 0.0 && xr <= (double)(D2 - 1) && yr >= 0.0 && yr <= (double)(D2 - 1)) {
+    int r = rank[(int)yr * D2 + (int)xr];
+    if (r >= 0) {
+      out = (IdxT)r;
+      rayvalid[a * D2 + j] = 1;
+    }
+  }
+  fmap[t] = out;
+}
+
 // Adjoint map, voxel-driven: for voxel p and angle a list the rays j of all
 // samples (j,i) with fmap[a][j][i] == p, j-major then i (deterministic).
 // pass 0: count only (max multiplicity -> *kmax); pass 1: fill amap[a][k][p].

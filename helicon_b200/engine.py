@@ -105,6 +105,12 @@ class Batch:
                 _lib.ptr(self.nvalid), _lib.ptr(self.tie), problem.stream if stream is None else _stream_handle(stream),
             )
         )
+        req = self.plan.exact_map_requests(self.tie)
+        if req is not None:  # in-plane tie views: exact per-column maps appended to the angle table
+            nv_ex = np.zeros(len(req[0]), dtype=np.int32)
+            _lib.check(lib.hb2_batch_add_exact_maps(self._h, len(req[0]), _lib.ptr(req[0]), _lib.ptr(req[1]), _lib.ptr(nv_ex)))
+            self.nvalid = np.concatenate([self.nvalid, nv_ex])
+            self.tie = np.concatenate([self.tie, np.zeros(len(nv_ex), dtype=np.int32)])
         self._amap_cache = {}
         self.plan.finalize(self.nvalid, lambda a: self.angle_map(a) >= 0)
         p = self.plan
@@ -185,7 +191,7 @@ class Batch:
 
     # -- exports (drop-in builders, tests) ---------------------------------
     def ray_valid(self):
-        out = np.empty((len(self.plan.angles), self.problem.D2), dtype=np.uint8)
+        out = np.empty((len(self.nvalid), self.problem.D2), dtype=np.uint8)  # incl. exact-map angles
         _lib.check(_lib.load().hb2_batch_ray_valid(self._h, _lib.ptr(out)))
         return out
 

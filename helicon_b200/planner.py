@@ -107,11 +107,12 @@ def column_slices(s, L2, L3, zshift):
 
 
 @functools.lru_cache(maxsize=16)
-def reference_z_table(s, D2, L2):
-    """z coordinate of sample (column k, depth i) exactly as the reference's coordinate tables hold it
+def reference_xz_tables(s, D2, L2):
+    """x and z coordinate of sample (column k, depth i) exactly as the reference's coordinate tables hold them
     (SLR:1712-1719: ``R.from_euler('y', 90).apply(inverse=True)`` of the integer grid, then ``*= s``): the exact
-    value s*(k - L2//2) plus last-bit noise that depends on (k, i) only (not on the ray j; checked in
-    tests/test_host_cpu.py).  It decides rounding ties: returns a float64 array [L2, D2]."""
+    values -s*(i - D2//2) and s*(k - L2//2) plus last-bit noise that depends on (k, i) only (not on the ray j, and
+    the y coordinate carries none; checked in tests/test_host_cpu.py).  The noise decides rounding ties.
+    Returns two float64 arrays [L2, D2]."""
     from scipy.spatial.transform import Rotation as R
 
     depth = (np.arange(D2, dtype=np.int32) - D2 // 2).astype(np.float32)
@@ -121,7 +122,12 @@ def reference_z_table(s, D2, L2):
     pts = R.from_euler("y", 90, degrees=True).apply(pts, inverse=True)
     if s != 1.0:
         pts *= s
-    return np.ascontiguousarray(np.swapaxes(pts[:, 2].reshape((D2, 1, L2)), 0, 2)[:, 0, :])
+    tab = lambda c: np.ascontiguousarray(np.swapaxes(pts[:, c].reshape((D2, 1, L2)), 0, 2)[:, 0, :])
+    return tab(0), tab(2)
+
+
+def reference_z_table(s, D2, L2):
+    return reference_xz_tables(s, D2, L2)[1]
 
 
 class TieView:
@@ -229,7 +235,42 @@ class BatchPlan:
         self.angles = np.array(angles, dtype=np.float64)
         self.cos_sin = z_rotation_entries(self.angles)
         self.has_ties = any(c[5] for c in self._cand)
+        self.exact_ties = bool(exact_ties)
+        self._xy = [None] * len(self.specs)
         self.finalized = False
+
+    def exact_map_requests(self, tie_counts):
+        """In-plane tie views.  ``tie_counts[a]`` (from ``hb2_batch_begin``) > 0 marks the angles where a
+        sample sits on a rounding boundary (twist*h = 30, 60, ... degrees); there the reference's voxel choice follows
+        the noise of its x table, which differs per image column.  Every copy with such an angle is replaced by one
+        single-column view per image column it uses, each with its own exact map (``hb2_batch_add_exact_maps``).
+        Returns ``(cos_sin [nE, 2], x0rows [nE, D2])`` or None; the new maps get angle indices len(angles) + e."""
+        tie_counts = np.asarray(tie_counts)
+        nA = len(self.angles)
+        if not self.exact_ties or not tie_counts[:nA].any():
+            return None
+        Xt = reference_xz_tables(self.s, self.D2, self.L2)[0]
+        index, cs_rows, x0_rows = {}, [], []
+        for ci in range(len(self.specs)):
+            copies, aid, hidx, hs, ZI, ties = self._cand[ci]
+            m = {}
+            for i in np.nonzero(tie_counts[aid] > 0)[0]:
+                if ties and (int(hidx[i]), int(copies[i][1])) in ties:
+                    continue  # also a column->slice tie view: keeps that path (and the in-plane flag)
+                lst = []
+                for k in np.nonzero(ZI[hidx[i]] >= 0)[0]:
+                    key = (int(aid[i]), int(k))
+                    e = index.get(key)
+                    if e is None:
+                        e = index[key] = len(cs_rows)
+                        cs_rows.append(self.cos_sin[aid[i]])
+                        x0_rows.append(Xt[k])
+                    lst.append((int(k), nA + e))
+                m[int(i)] = lst
+            self._xy[ci] = m or None
+        if not cs_rows:
+            return None
+        return np.ascontiguousarray(cs_rows, dtype=np.float64), np.ascontiguousarray(x0_rows, dtype=np.float64)
 
     def finalize(self, nvalid_rays, angle_valid=None):
         """``angle_valid(a)`` -> bool [D2, D2] (sample (j, i) of angle a hits a voxel), needed only for tie views."""
@@ -241,6 +282,7 @@ class BatchPlan:
         vrows = []   # per candidate: int64 array [n_slots, 5] = angle, tie index or -1, first tie column slot, dup_of, mult
         colk = []
         self._cv_src = []            # per candidate: what cand_views / cand_view_slots are built from (lazily)
+        self._cv_explicit = []       # per candidate with tie views: explicit [(view tuple, slot)] list, else None
         self._cand_views = None
         self.cand_n_data_rows = np.zeros(nc, dtype=np.int64)
         pair_meta = []
@@ -263,6 +305,10 @@ class BatchPlan:
                         rv = (va[None, :, :] & inside[:, None, :]).any(axis=2)  # [t, j]
                         tie_rows[i] = rv
                         nrows[i] = int(rv.sum())
+            xy = self._xy[ci]
+            if xy:
+                for i, lst in xy.items():  # one single-column view per image column, each with its own exact map
+                    nrows[i] = int(sum(nvalid_rays[a] for _, a in lst))
             stop = len(copies)
             if sp.min_projection_lines > 0:
                 over = np.nonzero(np.cumsum(nrows) > sp.min_projection_lines)[0]
@@ -281,7 +327,8 @@ class BatchPlan:
                     keep = np.array([int(h) not in tie_hs for h in hh], dtype=bool)
                     hh, kq = hh[keep], kq[keep]
                 tab[hh, ZI[hh, kq] * MC + (kq - run_start[hh, kq])] = kq
-                if not ties:
+                explicit = None
+                if not ties and not xy:
                     # all regular views: Halton duplicates (same (h, c)) are served by their first copy
                     key = hidx[sel] * sp.csym + np.array([copies[i][1] for i in sel], dtype=np.int64)
                     _, first_idx, inv = np.unique(key, return_index=True, return_inverse=True)
@@ -299,9 +346,24 @@ class BatchPlan:
                 else:
                     first_of = {}
                     rows_c = []
+                    explicit = []
                     for q_, i in enumerate(sel):
-                        tv = ties.get((int(hidx[i]), int(copies[i][1])))
+                        tv = ties.get((int(hidx[i]), int(copies[i][1]))) if ties else None
                         slots[q_] = nviews
+                        if xy and int(i) in xy:
+                            row = tab[hidx[i]]
+                            for k, a_ex in xy[int(i)]:
+                                if nvalid_rays[a_ex] == 0:
+                                    continue
+                                t = np.where(row == k, row, -1).astype(np.int32)
+                                zi_k = np.where(np.arange(L2) == k, ZI[hidx[i]], -1)
+                                explicit.append(((a_ex, zi_k, copies[i][0], copies[i][1], int(nvalid_rays[a_ex])), nviews))
+                                colk.append(t[None, :])
+                                rows_c.append([a_ex, -1, 0, -1, 1])
+                                nviews += 1
+                            continue
+                        explicit.append(((int(aid[i]), ZI[hidx[i]] if tv is None else tv.zt, copies[i][0], copies[i][1],
+                                         int(nrows[i])), nviews))
                         if tv is None:
                             colk.append(tab[hidx[i]][None, :])
                             rel = nviews - vbeg
@@ -327,6 +389,7 @@ class BatchPlan:
                             nviews += nslot
                     vrows.append(np.array(rows_c, dtype=np.int64).reshape(-1, 5))
             self._cv_src.append((sel, slots, nrows[sel] if len(sel) else np.zeros(0, np.int64)))
+            self._cv_explicit.append(explicit if len(sel) else None)
             self.cand_n_data_rows[ci] = int(nrows[sel].sum()) if len(sel) else 0
             cands[ci]["view_begin"] = vbeg
             cands[ci]["view_count"] = nviews - vbeg
@@ -390,6 +453,10 @@ class BatchPlan:
         for ci in range(len(self.specs)):
             copies, aid, hidx, hs, ZI, ties = self._cand[ci]
             sel, slots, nrows = self._cv_src[ci]
+            if self._cv_explicit[ci] is not None:
+                cvs.append([e[0] for e in self._cv_explicit[ci]])
+                sls.append([int(e[1]) for e in self._cv_explicit[ci]])
+                continue
             cv = []
             for q, i in enumerate(sel):
                 tv = ties.get((int(hidx[i]), int(copies[i][1]))) if ties else None

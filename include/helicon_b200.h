@@ -150,6 +150,16 @@ int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out_host);
 /* sample->voxel map of one angle, out[D2*D2] int32 (disk rank or -1), row j, depth i */
 int hb2_batch_angle_map(hb2_batch* b, int32_t angle, int32_t* out_host);
 
+/* In-plane tie views: at view angles where a sample coordinate cos*x0 + sin*y0 is a half-integer (30, 60,
+ * ... degrees; angle 0/90/180 when s = 0.5) the reference's rounding follows the last-bit noise of its coordinate
+ * table (SLR:1712-1719), which depends on (image column k, depth sample i).  For such a view the host requests one
+ * EXACT map per image column: cos_sin[2e..] as in hb2_batch_begin, x0rows[e*D2 + i] = the table's x coordinate of
+ * sample i in that column (taken from the same scipy call the reference makes).  The maps are appended to the angle
+ * table (indices n_angles .. n_angles + n_extra - 1) and used by single-column views.  nvalid_rays[n_extra] out.
+ * Call between hb2_batch_begin and hb2_batch_create. */
+int hb2_batch_add_exact_maps(hb2_batch* b, int32_t n_extra, const double* cos_sin, const double* x0rows,
+                             int32_t* nvalid_rays);
+
 /* Tie views: a symmetry copy whose Z = s*(k - L2//2) - h*rise + L3//2 is a half-integer for its
  * columns lets every SAMPLE round by the last-bit noise of the reference's coordinate table (SLR:1712-1719), so a
  * row (column k, ray j) draws from two neighbouring slices.  The host resolves it from that table:

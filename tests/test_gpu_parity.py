@@ -19,8 +19,9 @@ from tests.helpers import cases, csr_equal, csr_from, load
 
 pytestmark = pytest.mark.gpu
 
-# geometries with IN-PLANE rounding ties (flagged, reported only); column->slice ties (data_nn_tiez) are resolved exactly
-TIE_CASES = {"data_nn_tie30"}
+# rounding ties are resolved exactly from the reference's coordinate tables: in-plane ties (view angles of
+# 30/60/... degrees, or s = 0.5) by per-column exact maps, column->slice ties by per-sample slices
+XY_TIE_EXACT = {"data_nn_tie30", "data_nn_reftest", "data_nn_inner"}  # data_nn_s05: a view with BOTH tie kinds stays flagged
 Z_TIE_EXACT = {"data_nn_tiez", "data_nn_csym2"}
 
 
@@ -52,14 +53,15 @@ def test_data_rows_vs_reference(name):
     s, twist, rise, csym, D2, L2, D3, D3i, L3, mpl = d["args"]
     prob = Problem(d["image"], float(s), int(D2), int(L2), int(D2), D3i / 2, int(D3) // 2 - 1)
     batch = Batch(prob, int(L3), [CandidateSpec(twist, rise, int(csym), int(mpl), -1, False)])
-    flagged = int(batch.tie.sum()) > 0 or bool(batch.plan.cand_tie_z[0])
+    used = np.unique(batch.plan.views["angle"])
+    flagged = int(batch.tie[used].sum()) > 0 or bool(batch.plan.cand_tie_z[0])
     A, b, pid = batch.data_csr(0)
     ref = csr_from(d)
     ok, why = csr_equal(A, ref)
     print(f"{name}: flagged={flagged} rows gpu={A.shape[0]} ref={ref.shape[0]} identical={ok}")
     batch.close(); prob.close()
-    if name in TIE_CASES:
-        assert flagged
+    if name in XY_TIE_EXACT:
+        assert int(batch.tie.sum()) > 0 and not flagged  # tie angles present, every view on them replaced by exact maps
     if name in Z_TIE_EXACT:
         assert batch.plan.has_ties and not flagged
     if not flagged:
@@ -69,7 +71,7 @@ def test_data_rows_vs_reference(name):
 
 
 def test_data_rows_enough_unflagged_cases():
-    assert len([c for c in cases("data", "nn") if c not in TIE_CASES]) >= 3
+    assert len(cases("data", "nn")) >= 8
 
 
 @pytest.mark.parametrize("name", cases("hsym", "nn"))
@@ -159,6 +161,8 @@ def test_unbounded_solve_vs_reference_golden(solver, name):
     assert rec.dtype == np.float32 and rec.shape == ref.shape and h1 is None and h2 is None
     if name.endswith("tie475"):  # rise_pixel*13 = 47.5: tie views h = +-13, resolved exactly (oracle/make_golden_tie475.py)
         assert info["res"]["flags"] & 16 and not info["res"]["flags"] & 2
+    if name == "solve_nn_unb_32":  # twist*h = -30 deg at h = 25: in-plane tie views, resolved by exact per-column maps
+        assert not info["res"]["flags"] & 3
     if info["res"]["flags"] & 3:  # tie-flagged geometry: a few samples may land in a neighbouring voxel
         assert dscore <= 2e-4
     else:

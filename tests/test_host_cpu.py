@@ -152,3 +152,34 @@ def test_tie_views_reproduce_the_reference_slice_of_every_sample(name):
         zi = np.rint(cc[:, 2].reshape(L2, D2, D2) - h * rise + L3 // 2).astype(np.int64)
         assert all(np.array_equal(zi[:, j, :], tv.zt) for j in range(D2)), (h, c)
         assert set(np.unique(tv.up)) <= {0, 1}
+
+
+@pytest.mark.parametrize("N,s,angle", [(12, 1.0, 30.0), (16, 1.0, -60.0), (16, 0.5, 0.0), (14, 1.0, 150.0)])
+def test_exact_map_requests_reproduce_the_reference_voxel_of_every_sample(N, s, angle):
+    """In-plane ties: the x rows the planner hands to ``hb2_batch_add_exact_maps`` plus the kernel's
+    arithmetic (fma(S, y0, C*x0) + D2//2, rint; restated here with exact rationals) against the literal coordinate
+    pipeline of the reference (SLR:1576-1581) for every (column, ray, sample) -- and the x table carries no
+    dependence on the ray j, the y table no noise at all."""
+    from fractions import Fraction as F
+
+    from scipy.spatial.transform import Rotation as R
+
+    (X0, Y0, Z0), _ = O.back_project_2d_coords_to_3d_coords(np.zeros((N, N), np.float32), s, N, N)
+    Xt, Zt = planner.reference_xz_tables(s, N, N)
+    assert all(np.array_equal(X0[:, j, :], Xt) for j in range(N))
+    assert all(np.array_equal(Z0[:, j, :], Zt) for j in range(N))
+    assert np.array_equal(Y0, np.broadcast_to((s * (np.arange(N) - N // 2))[None, :, None], Y0.shape))
+    coords0 = np.vstack((X0.ravel(), Y0.ravel(), Z0.ravel())).T
+    cc = R.from_euler("z", angle, degrees=True).apply(coords0, inverse=True)
+    Xr = np.rint(cc[:, 0].reshape(N, N, N) + N // 2)
+    Yr = np.rint(cc[:, 1].reshape(N, N, N) + N // 2)
+    C, S = planner.z_rotation_entries([angle])[0]
+    fma = lambda a, b, c: float(F(a) * F(b) + F(c))
+    y0 = s * (np.arange(N) - N // 2)
+    varies = False
+    for k in range(N):
+        X = np.array([[fma(S, y0[j], C * Xt[k, i]) + N // 2 for i in range(N)] for j in range(N)])
+        Y = np.array([[fma(C, y0[j], (-S) * Xt[k, i]) + N // 2 for i in range(N)] for j in range(N)])
+        assert np.array_equal(np.rint(X), Xr[k]) and np.array_equal(np.rint(Y), Yr[k]), k
+        varies |= not (np.array_equal(Xr[k], Xr[0]) and np.array_equal(Yr[k], Yr[0]))
+    assert varies  # these are tie angles: the rounding really depends on the column
