@@ -5,6 +5,7 @@
 #include "hb2_symm.cuh"
 #include "hb2_tie.cuh"
 #include "hb2_adj_tile.cuh"
+#include "hb2_explicit.cuh"
 
 #include <cub/cub.cuh>
 
@@ -164,6 +165,12 @@ struct hb2_batch {
   std::vector<int8_t> h_tie_zlo;
   std::vector<uint8_t> h_tie_up, h_tie_rv;
   int n_tie_views = 0;
+  // explicit data rows (hb2_batch_explicit_rows)
+  bool explicit_rows = false;
+  long long exp_nnz = 0;
+  float* d_exp_b = nullptr;
+  int* d_exp_pid = nullptr;
+  float exp_bmax = 0.f;
   uint16_t* d_amap_i = nullptr;
   long long extra_launches = 0;  // kernels beyond one per launch_* call (band path: projector + reduce)
   int max_views = 0;
@@ -476,6 +483,154 @@ extern "C" int hb2_batch_add_exact_maps(hb2_batch* b, int32_t nE, const double* 
   return HB2_OK;
 }
 
+// Explicit data rows (general orientation and/or trilinear interpolation): built on the GPU, see hb2_explicit.cuh.
+extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry* eg, int32_t ncopies, const double* copy_mats,
+                                       const double* zshift, const double* xtab, const double* ztab,
+                                       int64_t min_projection_lines, int32_t* copies_used, int32_t* rows_per_copy,
+                                       int64_t* n_rows, int64_t* nnz_out) {
+  if (!b || !eg || ncopies <= 0 || !copy_mats || !zshift || !xtab || !ztab) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_explicit_rows must precede hb2_batch_create");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  ExpGeo G{};
+  G.D2 = B.D2; G.L2 = B.L2; G.L3 = B.L3; G.L3P = B.L3P; G.linear = eg->interpolation == 1 ? 1 : 0;
+  G.s = B.s; G.dy = eg->dy_pixel;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) G.Ayx[r * 3 + c] = eg->rot_yx[c * 3 + r];  // transpose: apply(inverse=True)
+  std::vector<ExpCopy> hc(ncopies);
+  for (int q = 0; q < ncopies; ++q) {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) hc[q].A[r * 3 + c] = copy_mats[(size_t)q * 9 + c * 3 + r];
+    hc[q].zshift = zshift[q];
+  }
+  const long long R = (long long)B.L2 * B.D2, NT = (long long)ncopies * R;
+  if (NT >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "too many potential rows");
+  ExpCopy* d_cp; double *d_xt, *d_zt; int *d_cnt, *d_flag, *d_off, *d_ridx;
+  CK(b->pool.alloc(&d_cp, (size_t)ncopies, false, st));
+  CK(b->pool.alloc(&d_xt, (size_t)R, false, st));
+  CK(b->pool.alloc(&d_zt, (size_t)R, false, st));
+  CK(b->pool.alloc(&d_cnt, (size_t)NT + 1, true, st));
+  CK(b->pool.alloc(&d_flag, (size_t)NT + 1, true, st));
+  CK(b->pool.alloc(&d_off, (size_t)NT + 1, false, st));
+  CK(b->pool.alloc(&d_ridx, (size_t)NT + 1, false, st));
+  CK(cudaMemcpyAsync(d_cp, hc.data(), sizeof(ExpCopy) * ncopies, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_xt, xtab, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_zt, ztab, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+  k_exp_rows<0><<<cdiv(NT, 128), 128, 0, st>>>(G, ncopies, d_cp, d_xt, d_zt, P->d_rank_data, P->d_pix, d_cnt, nullptr, nullptr,
+                                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  k_exp_flags<<<cdiv(NT, 256), 256, 0, st>>>(NT, d_cnt, d_flag);
+  CKL();
+  // row index of every potential row (exclusive scan of the flags; NT + 1 entries so the total is the last one)
+  size_t sb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, sb, d_flag, d_ridx, (int)(NT + 1), st);
+  void* d_tmp; { uint8_t* p; CK(b->pool.alloc(&p, sb, false, st)); d_tmp = p; }
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp, sb, d_flag, d_ridx, (int)(NT + 1), st));
+  std::vector<int> bound(ncopies + 1);
+  CK(cudaMemcpy2DAsync(bound.data(), sizeof(int), d_ridx, sizeof(int) * R, sizeof(int), ncopies + 1, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // SLR:1640-1647: copies are appended until the row count exceeds min_projection_lines
+  int used = ncopies;
+  for (int q = 0; q < ncopies; ++q) {
+    if (rows_per_copy) rows_per_copy[q] = bound[q + 1] - bound[q];
+    if (min_projection_lines > 0 && bound[q + 1] > min_projection_lines) { used = q + 1; break; }
+  }
+  if (rows_per_copy) for (int q = used; q < ncopies; ++q) rows_per_copy[q] = bound[q + 1] - bound[q];
+  const int m = bound[used];
+  const long long NU = (long long)used * R;
+  // entry offsets over the used copies: the count pass may exceed 2^31 entries in total, so check with a 64-bit sum
+  {
+    std::vector<int> hcnt((size_t)NU);
+    CK(cudaMemcpyAsync(hcnt.data(), d_cnt, sizeof(int) * NU, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    long long tot = 0;
+    for (long long t = 0; t < NU; ++t) tot += hcnt[t];
+    if (tot >= (1ll << 31) - 64) return fail(HB2_ERR_CAPACITY, "explicit rows exceed 2^31 matrix entries");
+    b->exp_nnz = tot;
+  }
+  CK(cudaMemsetAsync(d_cnt + NU, 0, sizeof(int), st));
+  CK(cub::DeviceScan::ExclusiveSum(d_tmp, sb, d_cnt, d_off, (int)(NU + 1), st));
+  const long long nnz = b->exp_nnz;
+  int *d_ptr, *d_col, *d_erow, *d_pid; float *d_w, *d_rb;
+  CK(b->pool.alloc(&d_ptr, (size_t)m + 1, false, st));
+  CK(b->pool.alloc(&d_col, (size_t)nnz, false, st));
+  CK(b->pool.alloc(&d_w, (size_t)nnz, false, st));
+  CK(b->pool.alloc(&d_erow, (size_t)nnz, false, st));
+  CK(b->pool.alloc(&d_rb, (size_t)m, false, st));
+  CK(b->pool.alloc(&d_pid, (size_t)m, false, st));
+  if (m > 0) {
+    k_exp_rows<1><<<cdiv(NU, 128), 128, 0, st>>>(G, used, d_cp, d_xt, d_zt, P->d_rank_data, P->d_pix, d_cnt, d_off, d_ridx, d_col,
+                                                  d_w, d_erow, d_ptr, d_rb, d_pid);
+    CKL();
+  }
+  const int nnz_i = (int)nnz;
+  CK(cudaMemcpyAsync(d_ptr + m, &nnz_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  // transpose: stable sort of the entries by voxel (deterministic adjoint order), column pointers from a histogram
+  int *d_cptr, *d_crow; float* d_cw;
+  CK(b->pool.alloc(&d_cptr, (size_t)B.npad + 2, true, st));
+  CK(b->pool.alloc(&d_crow, (size_t)nnz, false, st));
+  CK(b->pool.alloc(&d_cw, (size_t)nnz, false, st));
+  if (nnz > 0) {
+    int *d_keys2, *d_id, *d_id2, *d_cc;
+    CK(b->pool.alloc(&d_keys2, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_id, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_id2, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_cc, (size_t)B.npad + 2, true, st));
+    k_iota<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id);
+    int bits = 1;
+    while ((1ll << bits) < (long long)B.npad) ++bits;
+    size_t sb3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb3, d_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st);
+    void* d_t3; { uint8_t* p; CK(b->pool.alloc(&p, sb3, false, st)); d_t3 = p; }
+    CK(cub::DeviceRadixSort::SortPairs(d_t3, sb3, d_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st));
+    k_exp_gather<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id2, d_erow, d_w, d_crow, d_cw);
+    k_exp_colcount<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_col, d_cc);
+    CKL();
+    size_t sb4 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sb4, d_cc, d_cptr, B.npad + 1, st);
+    void* d_t4; { uint8_t* p; CK(b->pool.alloc(&p, sb4, false, st)); d_t4 = p; }
+    CK(cub::DeviceScan::ExclusiveSum(d_t4, sb4, d_cc, d_cptr, B.npad + 1, st));
+  }
+  // max(b) over the rows: upper bound of the positive constraint (SLR:248)
+  std::vector<float> hb((size_t)std::max(m, 1), 0.f);
+  if (m > 0) CK(cudaMemcpyAsync(hb.data(), d_rb, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  float bm = m > 0 ? hb[0] : 0.f;
+  for (int r = 1; r < m; ++r) bm = std::max(bm, hb[r]);
+  b->exp_bmax = bm;
+  b->explicit_rows = true;
+  b->d_exp_b = d_rb; b->d_exp_pid = d_pid;
+  B.exp_m = m; B.exp_ptr = d_ptr; B.exp_col = d_col; B.exp_w = d_w; B.exp_cptr = d_cptr; B.exp_crow = d_crow; B.exp_cw = d_cw;
+  if (copies_used) *copies_used = used;
+  if (n_rows) *n_rows = m;
+  if (nnz_out) *nnz_out = nnz;
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_explicit_export(hb2_batch* b, int64_t* indptr, int32_t* indices, float* data, float* b_out, int32_t* pid_out) {
+  if (!b || !b->explicit_rows) return fail(HB2_ERR_STATE, "no explicit rows in this batch");
+  CK(cudaSetDevice(b->P->device));
+  cudaStream_t st = b->stream;
+  const BD& B = b->B;
+  const int m = B.exp_m;
+  const long long nnz = b->exp_nnz;
+  std::vector<int> ptr((size_t)m + 1);
+  CK(cudaMemcpyAsync(ptr.data(), B.exp_ptr, sizeof(int) * (m + 1), cudaMemcpyDeviceToHost, st));
+  if (indices && nnz) CK(cudaMemcpyAsync(indices, B.exp_col, sizeof(int) * nnz, cudaMemcpyDeviceToHost, st));
+  if (data && nnz) CK(cudaMemcpyAsync(data, B.exp_w, sizeof(float) * nnz, cudaMemcpyDeviceToHost, st));
+  if (b_out && m) CK(cudaMemcpyAsync(b_out, b->d_exp_b, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+  if (pid_out && m) CK(cudaMemcpyAsync(pid_out, b->d_exp_pid, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (indptr) for (int r = 0; r <= m; ++r) indptr[r] = ptr[r];
+  if (indices) {  // internal p*L3P + z -> reference z*ndisk + rank
+    const int L3P = B.L3P, nd = B.ndisk;
+    const std::vector<int>& i2r = b->P->int2ref;
+    for (long long e = 0; e < nnz; ++e) indices[e] = (indices[e] % L3P) * nd + i2r[indices[e] / L3P];
+  }
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_ray_valid(hb2_batch* b, uint8_t* out) {
   if (!b || !out) return fail(HB2_ERR_ARG, "null argument");
   CK(cudaSetDevice(b->P->device));
@@ -585,16 +740,19 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
           view_dupof[vi] = prim; view_mult[vi] = 0; view_mult[prim] += 1;
         }
       }
+      if (b->explicit_rows && w.tie < 0) return fail(HB2_ERR_ARG, "a batch with explicit rows takes pseudo views only");
       if (w.tie >= 0) {
-        if (w.tie >= b->n_tie || w.tie_slot0 < 0 || w.tie_slot0 + B.ZMC > b->tie_TS) return fail(HB2_ERR_ARG, "bad tie view");
-        if (B.ZMC > HB2_TIE_MAXZMC) return fail(HB2_ERR_GEOMETRY, "tie views need L3*MC <= 16");
+        if (!b->explicit_rows) {
+          if (w.tie >= b->n_tie || w.tie_slot0 < 0 || w.tie_slot0 + B.ZMC > b->tie_TS) return fail(HB2_ERR_ARG, "bad tie view");
+          if (B.ZMC > HB2_TIE_MAXZMC) return fail(HB2_ERR_GEOMETRY, "tie views need L3*MC <= 16");
+        }
         view_tie[vi] = w.tie; view_tie_slot0[vi] = w.tie_slot0;
         if (cand_tie_count[c] == 0) cand_tie_begin[c] = (int)tie_views.size();
         tie_views.push_back(vi);
         cand_tie_count[c] += 1;
       }
       view_uoff[vi] = uo + (long long)v * B.rows_per_view;
-      if (b->tie_per_angle[w.angle] > 0) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
+      if (b->tie_per_angle[w.angle] > 0 && !b->explicit_rows) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
     }
     b->cand_flags[c] |= q.flags_in;
     if (q.view_count == 0) b->cand_flags[c] |= HB2_FLAG_NO_ROWS;
@@ -784,6 +942,16 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   // ---- right-hand side ---------------------------------------------------------
   k_build_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
   CKL();
+  if (b->explicit_rows) {  // the explicit rows bring their own right-hand side (pseudo views have no columns)
+    if (nc != 1) return fail(HB2_ERR_ARG, "a batch with explicit rows holds one candidate");
+    if ((long long)B.exp_m > b->h_mdata[0]) return fail(HB2_ERR_ARG, "not enough pseudo views for the explicit rows");
+    CKC(cudaMemcpyAsync(B.b + b->h_uoff[0], b->d_exp_b, sizeof(float) * B.exp_m, cudaMemcpyDeviceToDevice, st));
+    int iv;
+    memcpy(&iv, &b->exp_bmax, sizeof(int));
+    iv = iv >= 0 ? iv : iv ^ 0x7fffffff;
+    CKC(cudaMemcpyAsync(b->d_bmax, &iv, sizeof(int), cudaMemcpyHostToDevice, st));
+    CKC(cudaStreamSynchronize(st));
+  }
   // ---- symmetry rows -----------------------------------------------------------
   CKC(b->pool.alloc(&b->d_sym_a, (size_t)so, false, st));
   CKC(b->pool.alloc(&b->d_sym_b, (size_t)so, false, st));
@@ -982,7 +1150,8 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (b->nviews == 0) return;
   if (b->n_tie_views > 0) {  // exact rows of the tie views (the projector kernels below skip them)
     const float* src = mode == MODE_LSMR ? B.v : B.xs;
-    if (b->idx16) k_fwd_tie<uint16_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    if (b->explicit_rows) k_fwd_csr<float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    else if (b->idx16) k_fwd_tie<uint16_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     else k_fwd_tie<uint32_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     b->extra_launches += 1;
   }
@@ -1019,7 +1188,8 @@ static void launch_adj(hb2_batch* b, int mode) {
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
   if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
-    k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+    if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+    else k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     b->extra_launches += 1;
   }
   if (B.adj_tile) {
@@ -1162,14 +1332,16 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     launches += 2;
     if (b->n_tie_views > 0) {
-      if (b->idx16) k_fwd_tie<uint16_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      if (b->explicit_rows) k_fwd_csr<double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      else if (b->idx16) k_fwd_tie<uint16_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       else k_fwd_tie<uint32_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       ++launches;
     }
   };
   auto adj = [&](const double* rows, double* dst, int gate) {
     if (b->n_tie_views > 0) {
-      k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+      if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+      else k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;
     }
     if (B.adj_tile && sm64 <= 200 * 1024) {  // float64 instantiation of the TMA-staged tile adjoint

@@ -1,0 +1,205 @@
+// Explicit data rows: the general case of build_A_data_matrix (SLR:1301-1654) -- tilt/psi/dy != 0 and/or trilinear
+// interpolation -- where a ray is no longer one in-plane gather per slice, so the matrix-free projector kernels do not
+// apply.  The rows are BUILT ON THE GPU with the reference's float64 operation sequence (one thread per image pixel
+// (k, j) and symmetry copy, the numba loop of SLR:1403-1557) into a CSR + its transpose, and the solvers apply them
+// with k_fwd_csr / k_adj_csc.  Inside the batch these rows occupy "pseudo views": chunks of rows_per_view padded rows
+// marked as tie views, so that every other kernel (symmetry rows, LSMR/TRF state machines, norms, score) is unchanged
+// -- the fast projector kernels skip them, the adjoint kernels add BD::vtie.
+#pragma once
+#include "hb2_tie.cuh"
+
+struct ExpGeo {
+  int D2, L2, L3, L3P, linear;
+  double s, dy;
+  double Ayx[9];  // transpose of R.from_euler("yx", (tilt, psi)).as_matrix(): apply(inverse=True) multiplies by it
+};
+struct ExpCopy {
+  double A[9];    // transpose of R.from_euler("z", angle).as_matrix() (from scipy, incl. its M22 = 1 or 1 - 2^-53)
+  double zshift;  // h * rise_pixel
+};
+
+// scipy's Rotation.apply on one point: out[r] = fma(A[r][2], z, fma(A[r][1], y, A[r][0] * x)) (verified against
+// scipy 1.18 with exact rationals, tests/test_host_cpu.py)
+__device__ __forceinline__ void rot_apply(const double* A, double x, double y, double z, double& ox, double& oy, double& oz) {
+  ox = __fma_rn(A[2], z, __fma_rn(A[1], y, __dmul_rn(A[0], x)));
+  oy = __fma_rn(A[5], z, __fma_rn(A[4], y, __dmul_rn(A[3], x)));
+  oz = __fma_rn(A[8], z, __fma_rn(A[7], y, __dmul_rn(A[6], x)));
+}
+
+// One thread per potential row (copy, k, j).  FILL = 0: cnt[t] = number of matrix entries of the row (0: the row does
+// not exist, SLR:1547/1496).  FILL = 1: writes the entries at ent_off[t] (col = internal voxel index p*L3P + z,
+// weight, row index) and the row's b / pixel id.
+template <int FILL>
+__global__ void __launch_bounds__(128) k_exp_rows(ExpGeo G, int ncopies, const ExpCopy* __restrict__ copies,
+                                                  const double* __restrict__ xt, const double* __restrict__ zt,
+                                                  const int* __restrict__ rank, const float* __restrict__ pix,
+                                                  int* __restrict__ cnt, const int* __restrict__ ent_off,
+                                                  const int* __restrict__ row_idx, int* __restrict__ col,
+                                                  float* __restrict__ w, int* __restrict__ erow, int* __restrict__ rptr,
+                                                  float* __restrict__ rb, int* __restrict__ rpid) {
+  const long long R = (long long)G.L2 * G.D2;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)ncopies * R) return;
+  const int cp = (int)(t / R);
+  const int k = (int)((t % R) / G.D2), j = (int)(t % G.D2);
+  if (FILL && cnt[t] == 0) return;
+  const ExpCopy& C = copies[cp];
+  const int D2 = G.D2, c0 = D2 / 2, L3 = G.L3;
+  double y0 = (double)(j - c0);
+  if (G.s != 1.0) y0 = __dmul_rn(y0, G.s);
+  y0 = __dsub_rn(y0, G.dy);
+  int n = 0;
+  int off = 0, row = 0;
+  if (FILL) {
+    off = ent_off[t]; row = row_idx[t];
+    rptr[row] = off;
+    rb[row] = pix[(size_t)j * G.L2 + k];
+    rpid[row] = k * D2 + j;
+  }
+  for (int i = 0; i < D2; ++i) {
+    const double x0 = xt[(size_t)k * D2 + i], z0 = zt[(size_t)k * D2 + i];
+    double x1, y1, z1, x2, y2, z2;
+    rot_apply(G.Ayx, x0, y0, z0, x1, y1, z1);
+    rot_apply(C.A, x1, y1, z1, x2, y2, z2);
+    z2 = __dsub_rn(z2, C.zshift);
+    const double X = __dadd_rn(x2, (double)c0), Y = __dadd_rn(y2, (double)c0), Z = __dadd_rn(z2, (double)(L3 / 2));
+    if (!G.linear) {
+      const double zr = rint(Z), yr = rint(Y), xr = rint(X);
+      if (!(zr >= 0.0 && zr <= (double)(L3 - 1) && yr >= 0.0 && yr <= (double)(D2 - 1) && xr >= 0.0 && xr <= (double)(D2 - 1)))
+        continue;
+      const int p = rank[(int)yr * D2 + (int)xr];
+      if (p < 0) continue;
+      if (FILL) { col[off + n] = p * G.L3P + (int)zr; w[off + n] = 1.f; erow[off + n] = row; }
+      ++n;
+    } else {
+      // int() truncates toward zero (SLR:1418-1420); all eight corners must be inside the grid and the mask
+      if (!(Z > -1.0 && Z < (double)L3 && Y > -1.0 && Y < (double)D2 && X > -1.0 && X < (double)D2)) continue;
+      const int zi = (int)Z, yi = (int)Y, xi = (int)X;
+      if (zi + 1 > L3 - 1 || yi + 1 > D2 - 1 || xi + 1 > D2 - 1) continue;
+      const int p00 = rank[yi * D2 + xi], p01 = rank[yi * D2 + xi + 1];
+      const int p10 = rank[(yi + 1) * D2 + xi], p11 = rank[(yi + 1) * D2 + xi + 1];
+      if (p00 < 0 || p01 < 0 || p10 < 0 || p11 < 0) continue;
+      if (FILL) {
+        const double zf = __dsub_rn(Z, (double)zi), yf = __dsub_rn(Y, (double)yi), xf = __dsub_rn(X, (double)xi);
+        const double mz = __dsub_rn(1.0, zf), my = __dsub_rn(1.0, yf), mx = __dsub_rn(1.0, xf);
+        const int o = off + n;
+        const int L3P = G.L3P;
+        col[o + 0] = p00 * L3P + zi;     w[o + 0] = (float)__dmul_rn(__dmul_rn(mz, my), mx);
+        col[o + 1] = p01 * L3P + zi;     w[o + 1] = (float)__dmul_rn(__dmul_rn(mz, my), xf);
+        col[o + 2] = p10 * L3P + zi;     w[o + 2] = (float)__dmul_rn(__dmul_rn(mz, yf), mx);
+        col[o + 3] = p11 * L3P + zi;     w[o + 3] = (float)__dmul_rn(__dmul_rn(mz, yf), xf);
+        col[o + 4] = p00 * L3P + zi + 1; w[o + 4] = (float)__dmul_rn(__dmul_rn(zf, my), mx);
+        col[o + 5] = p01 * L3P + zi + 1; w[o + 5] = (float)__dmul_rn(__dmul_rn(zf, my), xf);
+        col[o + 6] = p10 * L3P + zi + 1; w[o + 6] = (float)__dmul_rn(__dmul_rn(zf, yf), mx);
+        col[o + 7] = p11 * L3P + zi + 1; w[o + 7] = (float)__dmul_rn(__dmul_rn(zf, yf), xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) erow[o + e] = row;
+      }
+      n += 8;
+    }
+  }
+  if (!FILL) cnt[t] = n;
+}
+
+__global__ void k_exp_flags(long long n, const int* __restrict__ cnt, int* __restrict__ flag) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) flag[t] = cnt[t] > 0;
+}
+__global__ void k_iota(int n, int* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = e;
+}
+__global__ void k_exp_colcount(int nnz, const int* __restrict__ col, int* __restrict__ cc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(&cc[col[e]], 1);
+}
+__global__ void k_exp_gather(int nnz, const int* __restrict__ order, const int* __restrict__ erow, const float* __restrict__ w,
+                             int* __restrict__ crow, float* __restrict__ cw) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) { crow[e] = erow[order[e]]; cw[e] = w[order[e]]; }
+}
+
+// Forward: rows <- A_explicit src.  One CTA per pseudo view (rows_per_view consecutive padded rows), one warp per row.
+// Epilogues and per-view partials as k_fwd_tie.
+template <typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
+  const int view = B.tie_views[blockIdx.x];
+  const int c = B.view_cand[view];
+  __shared__ float red[HB2_BLOCK / 32];
+  const int ppv = B.fwd_ppv;
+  const bool act = tie_active<TRF>(B, Tt, c, mode, false);
+  if (!act) {
+    if (!TRF && threadIdx.x < ppv) {
+      if (mode == MODE_LSMR) B.part_u[view * ppv + threadIdx.x] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + threadIdx.x)] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 1] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 2] = 0.f; }
+    }
+    return;
+  }
+  const T* __restrict__ vsrc = src + (size_t)c * B.npad;
+  const long long vo = B.view_uoff[view] - B.cand_uoff[c];  // first explicit row of this pseudo view
+  T* urow = rows + B.view_uoff[view];
+  const float* brow = B.b + B.view_uoff[view];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float alpha = 0.f, inv_beta = 0.f;
+  if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
+  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  const int nrow = (int)min((long long)B.rows_per_view, (long long)B.exp_m - vo);
+  for (int r = warp; r < nrow; r += HB2_BLOCK / 32) {
+    const int e0 = B.exp_ptr[vo + r], e1 = B.exp_ptr[vo + r + 1];
+    T acc = (T)0;
+    for (int e = e0 + lane; e < e1; e += 32) acc += (T)B.exp_w[e] * vsrc[B.exp_col[e]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (TRF) {
+        urow[r] = acc;
+      } else if (mode == MODE_LSMR) {
+        const float un = fadd_(fmul_(fmul_((float)urow[r], inv_beta), -alpha), (float)acc);
+        urow[r] = (T)un;
+        ss += un * un;
+      } else if (mode == MODE_PLAIN) {
+        urow[r] = acc;
+      } else {
+        const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
+        const float bv = brow[r];
+        ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+      }
+    }
+  }
+  if (!TRF) {
+    if (mode == MODE_LSMR) {
+      const float tot = block_sum(ss, red);
+      if (threadIdx.x < ppv) B.part_u[view * ppv + threadIdx.x] = threadIdx.x == 0 ? tot : 0.f;
+    } else if (mode == MODE_SCORE) {
+      const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
+      if (threadIdx.x < ppv) {
+        const bool f = threadIdx.x == 0;
+        B.part_s[3 * (view * ppv + threadIdx.x)] = f ? t0 : 0.f;
+        B.part_s[3 * (view * ppv + threadIdx.x) + 1] = f ? t1 : 0.f;
+        B.part_s[3 * (view * ppv + threadIdx.x) + 2] = f ? t2 : 0.f;
+      }
+    }
+  }
+}
+
+// Adjoint: vt[c][g] = sum over the transpose list of voxel g of w * rows[row] (* inv_beta in the LSMR modes, like
+// k_adj_tie); the adjoint kernels add vt to the symmetry part.  One thread per voxel entry g = p*L3P + z.
+template <typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_csc(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
+  const int c = blockIdx.y;
+  if (B.cand_tie_count[c] == 0) return;
+  if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
+  const int g = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  if (g >= B.npad) return;
+  T ib = (T)1;
+  if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
+  const T* __restrict__ ub = rows + B.cand_uoff[c];
+  T acc = (T)0;
+  const int e0 = B.exp_cptr[g], e1 = B.exp_cptr[g + 1];
+  for (int e = e0; e < e1; ++e) {
+    const T uv = ub[B.exp_crow[e]];
+    const T val = TRF ? uv : (T)fmaf((float)uv, (float)ib, 0.f);
+    acc += (T)B.exp_cw[e] * val;
+  }
+  vt[(size_t)c * B.npad + g] = acc;
+}

@@ -103,6 +103,14 @@ struct BD {
   // pid = k*D2 + j is set in its mask; the other rows are absent (u, b stay 0 like every other padded row)
   const uint8_t* pixmask;       // [n_masks][L2*D2] or null
   const int* cand_pixmask;      // [nc] mask index or -1
+  // explicit data rows (hb2_explicit.cuh): CSR of the rows (col = internal voxel index) and its transpose
+  int exp_m;                    // number of explicit rows (0: matrix-free batch)
+  const int* exp_ptr;           // [exp_m + 1]
+  const int* exp_col;
+  const float* exp_w;
+  const int* exp_cptr;          // [npad + 1]
+  const int* exp_crow;
+  const float* exp_cw;
 };
 
 // pixel mask of candidate c (null: all rows kept)

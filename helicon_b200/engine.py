@@ -340,3 +340,90 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+class ExplicitBatch(Batch):
+    """ONE candidate whose data rows are explicit (general orientation tilt/psi/dy and/or trilinear interpolation,
+    ``hb2_batch_explicit_rows``): built on the GPU with the reference's float64 operation sequence, applied by CSR
+    kernels; symmetry rows, LSMR/TRF and the score are the batch's usual kernels."""
+
+    def __init__(self, problem: Problem, L3: int, spec: CandidateSpec, tilt_degree=0.0, psi_degree=0.0, dy_pixel=0.0,
+                 interpolation="nn", stream=None):
+        from scipy.spatial.transform import Rotation as R
+
+        from . import planner
+
+        lib = _lib.require_gpu()
+        if interpolation not in ("nn", "linear"):
+            raise NotImplementedError(f"helicon_b200: interpolation={interpolation!r} (only 'nn' and 'linear')")
+        self.problem = problem
+        self._stream_ref = stream
+        self.L3 = int(L3)
+        D2, L2 = problem.D2, problem.L2
+        self.plan = BatchPlan(problem.s, D2, L2, self.L3, [spec], exact_ties=False)  # used for the symmetry pairs only
+        st = problem.stream if stream is None else _stream_handle(stream)
+        dummy = np.array([[1.0, 0.0]], dtype=np.float64)  # the in-plane maps are not used by explicit rows
+        self.nvalid = np.zeros(1, dtype=np.int32)
+        self.tie = np.zeros(1, dtype=np.int32)
+        self._h = C.c_void_p()
+        _lib.check(lib.hb2_batch_begin(C.byref(self._h), problem._h, self.L3, 1, 1, _lib.ptr(dummy), _lib.ptr(self.nvalid),
+                                       _lib.ptr(self.tie), st))
+        self.tie[:] = 0
+        copies = planner.data_copies(spec.rise_pixel, spec.csym, self.L3, L2)
+        ang = np.array([spec.twist * h + 360 * c / spec.csym for h, c in copies], dtype=np.float64)
+        mats = np.ascontiguousarray(R.from_euler("z", ang.reshape(-1, 1), degrees=True).as_matrix().reshape(-1, 9))
+        zshift = np.array([h * spec.rise_pixel for h, _ in copies], dtype=np.float64)
+        geo = _lib.ExplicitGeometry()
+        geo.interpolation = 1 if interpolation == "linear" else 0
+        geo.dy_pixel = float(dy_pixel)
+        myx = R.from_euler("yx", (tilt_degree, psi_degree), degrees=True).as_matrix().reshape(-1)
+        for q in range(9):
+            geo.rot_yx[q] = float(myx[q])
+        Xt, Zt = planner.reference_xz_tables(problem.s, D2, L2)
+        used, m, nnz = C.c_int32(), C.c_int64(), C.c_int64()
+        self.rows_per_copy = np.zeros(len(copies), dtype=np.int32)
+        _lib.check(lib.hb2_batch_explicit_rows(
+            self._h, C.byref(geo), len(copies), _lib.ptr(mats), _lib.ptr(zshift), _lib.ptr(Xt), _lib.ptr(Zt),
+            int(spec.min_projection_lines), C.byref(used), _lib.ptr(self.rows_per_copy), C.byref(m), C.byref(nnz)))
+        self.copies_used, self.m_rows, self.nnz = int(used.value), int(m.value), int(nnz.value)
+        # pairs (symmetry rows) from the planner; views replaced by pseudo views over the explicit rows
+        p = self.plan
+        p.finalize(np.zeros(len(p.angles), dtype=np.int64))
+        ZMP = (self.L3 + 3) // 4 * 4
+        rpv = D2 * ZMP
+        nv = (self.m_rows + rpv - 1) // rpv
+        views = np.zeros(nv, dtype=_lib.VIEW_DTYPE)
+        views["angle"] = 0
+        views["tie"] = 0
+        views["dup_of"] = -1
+        views["mult"] = 1
+        views["col_begin"] = 0
+        colk = np.full(self.L3, -1, dtype=np.int32)
+        p.cands[0]["view_begin"], p.cands[0]["view_count"] = 0, nv
+        p.cands[0]["flags_in"] = 0
+        p.views, p.colk = views, colk
+        p.cand_n_data_rows = np.array([self.m_rows], dtype=np.int64)
+        _lib.check(lib.hb2_batch_create(self._h, 1, _lib.ptr(p.cands), nv, _lib.ptr(views), len(colk), _lib.ptr(colk),
+                                        len(p.pairs), _lib.ptr(p.pairs)))
+        self.n = self.L3 * problem.ndisk
+        self.nc = 1
+        self.results = None
+        self._amap_cache = {}
+
+    def data_csr(self, c=0):
+        """A_data, b, b_pid (SLR:1651-1654) downloaded from the GPU-built rows (duplicates summed by scipy)."""
+        m, nnz = self.m_rows, self.nnz
+        indptr = np.zeros(m + 1, dtype=np.int64)
+        indices = np.zeros(max(nnz, 1), dtype=np.int32)
+        data = np.zeros(max(nnz, 1), dtype=np.float32)
+        b = np.zeros(max(m, 1), dtype=np.float32)
+        pid = np.zeros(max(m, 1), dtype=np.int32)
+        _lib.check(_lib.load().hb2_batch_explicit_export(self._h, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data),
+                                                         _lib.ptr(b), _lib.ptr(pid)))
+        A = csr_matrix((data[:nnz], indices[:nnz], indptr), shape=(m, self.n), dtype=np.float32)
+        return A, b[:m], pid[:m]
+
+    def data_row_index(self, c=0):
+        _, _, pid = self.data_csr(0)
+        D2 = self.problem.D2
+        return np.arange(self.m_rows, dtype=np.int64), (pid // D2).astype(np.int64), (pid % D2).astype(np.int64)

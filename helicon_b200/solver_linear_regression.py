@@ -4,8 +4,8 @@ reference's denovo3D solver, "SLR") with the per-candidate work on the GPU.
 Same function names, argument meaning, return types and array layouts as the
 reference; see INTEGRATION.md.  What is NOT implemented on the CUDA path raises
 ``NotImplementedError`` (there is no CPU fallback by design):
-interpolation other than "nn", tilt/psi/dy != 0 and ``refine_tilt_psi_dy``
-(general-orientation projector), score metrics other than
+``interpolation="linear"`` inside ``lsq_reconstruct`` (its data rows are built, its symmetry rows not yet),
+``refine_tilt_psi_dy``, score metrics other than
 "cosine", and solver models other than ``{"model": "lsq"}``.
 """
 
@@ -17,7 +17,7 @@ import logging
 import numpy as np
 
 from . import planner
-from .engine import Batch, Problem
+from .engine import Batch, ExplicitBatch, Problem
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
 
@@ -43,9 +43,15 @@ def _unsupported(what):
     raise NotImplementedError(f"helicon_b200 (CUDA path): {what} is not implemented; there is no CPU fallback")
 
 
-def _check_orientation(tilt_degree, psi_degree, dy_pixel):
-    if tilt_degree != 0 or psi_degree != 0 or dy_pixel != 0:
-        _unsupported("tilt/psi/dy != 0 (general-orientation projector, SURVEY section 8f rank 4)")
+def _interp(interpolation):
+    # SLR:1401: "linear", "linear10" and "linear11" all select the trilinear kernel, anything else nearest neighbour
+    return "linear" if interpolation in ("linear", "linear10", "linear11") else "nn"
+
+
+def _is_explicit(tilt_degree, psi_degree, dy_pixel, interpolation):
+    """The matrix-free projector covers the grid-search case (tilt = psi = dy = 0, nearest neighbour); everything
+    else runs on explicit GPU-built rows (engine.ExplicitBatch)."""
+    return bool(tilt_degree != 0 or psi_degree != 0 or dy_pixel != 0 or _interp(interpolation) == "linear")
 
 
 def back_project_2d_coords_to_3d_coords(
@@ -104,18 +110,22 @@ def build_A_data_matrix(
 
     The sample->voxel maps, ray validity and right-hand side come from the CUDA
     kernels; only the COO->CSR packing happens on the host."""
-    _check_orientation(tilt_degree, psi_degree, dy_pixel)
     image = np.asarray(image)
     D2 = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
     L2 = reconstruct_length_2d_pixel if reconstruct_length_2d_pixel > 0 else image.shape[1]
     L3 = reconstruct_length_3d_pixel if reconstruct_length_3d_pixel > 0 else L2
     # the reference builds this mask on the (L3, D2, D2) grid with rmax from D3 (SLR:1382-1384)
     prob = _make_problem(image, scale2d_to_3d, D2, L2, D2, reconstruct_diameter_3d_inner_pixel,
-                         rmax=reconstruct_diameter_3d_pixel // 2 - 1, interpolation=interpolation)
+                         rmax=reconstruct_diameter_3d_pixel // 2 - 1)
     spec = CandidateSpec(twist_degree, rise_pixel, csym, min_projection_lines, -1, False)
-    batch = Batch(prob, L3, [spec])
+    if _is_explicit(tilt_degree, psi_degree, dy_pixel, interpolation):
+        batch = ExplicitBatch(prob, L3, spec, tilt_degree, psi_degree, dy_pixel, _interp(interpolation))
+    else:
+        batch = Batch(prob, L3, [spec])
     try:
-        return batch.data_csr(0)
+        A, b, pid = batch.data_csr(0)
+        A.sum_duplicates()
+        return A, b, pid
     finally:
         batch.close()
         prob.close()
@@ -171,7 +181,12 @@ def lsq_reconstruct(
 
     One candidate through the batched GPU path (a batch of one).  ``device`` and
     ``return_info`` are additive keyword arguments."""
-    _check_orientation(tilt_degree, psi_degree, dy_pixel)
+    explicit = _is_explicit(tilt_degree, psi_degree, dy_pixel, interpolation)
+    if explicit and _interp(interpolation) == "linear":
+        _unsupported("interpolation='linear' in lsq_reconstruct (trilinear symmetry rows, SLR:910-1138; the trilinear "
+                     "data rows are available through build_A_data_matrix)")
+    if explicit and fsc_test:
+        _unsupported("fsc_test together with tilt/psi/dy != 0")
     if algorithm.get("model", "lsq") != "lsq":
         _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
     if score_metric != "cosine":
@@ -187,7 +202,7 @@ def lsq_reconstruct(
     if D3 <= 0 or L3 <= 0:
         raise ValueError("reconstruct_diameter_3d_pixel and reconstruct_length_3d_pixel must be given")
     prob = _make_problem(image, scale2d_to_3d, D2, L2, D3, reconstruct_diameter_3d_inner_pixel,
-                         interpolation=interpolation, device=device)
+                         device=device)
     try:
         n3 = L3 * prob.ndisk
         target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * sym_oversample))  # SLR:148-150, 168-170
@@ -196,7 +211,10 @@ def lsq_reconstruct(
         nsets = 3 if fsc_test >= 1 else 1
         # fsc_test: the full set and the two half sets are three candidates of one batch that differ only in
         # which data rows they keep (SLR:441-482); the symmetry rows are shared by construction.
-        batch = Batch(prob, L3, [spec] * nsets)
+        if explicit:  # general orientation: explicit GPU-built data rows (one candidate)
+            batch = ExplicitBatch(prob, L3, spec, tilt_degree, psi_degree, dy_pixel, _interp(interpolation))
+        else:
+            batch = Batch(prob, L3, [spec] * nsets)
         half1 = half2 = None
         try:
             if nsets == 3:

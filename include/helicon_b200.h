@@ -169,6 +169,29 @@ int hb2_batch_add_exact_maps(hb2_batch* b, int32_t n_extra, const double* cos_si
 int hb2_batch_set_ties(hb2_batch* b, int32_t n_tie, int32_t TS, const int8_t* zlo, const uint8_t* up,
                        const uint8_t* rowvalid);
 
+/* ---- explicit data rows: general orientation and/or trilinear interpolation ---------------------------------
+ * build_A_data_matrix (SLR:1301-1654) outside the grid-search case (tilt = psi = dy = 0, nearest neighbour), where a ray
+ * crosses slices and the matrix-free projector does not apply: the rows are built ON THE GPU by the reference's float64
+ * operation sequence (coords0[:,1] -= dy; R('yx',(tilt,psi)).apply(inverse); per copy R('z',angle).apply(inverse),
+ * z -= h*rise; + n//2 offsets; round()/int(); SLR:1390-1395, 1576-1581, numba loops 1403-1557) into a CSR and its
+ * transpose kept on the device; the solvers apply them in place of the projector kernels.  The batch then holds ONE
+ * candidate whose hb2_candidate.view_count pseudo views (hb2_view.tie = 0, colk = -1) cover ceil(n_rows /
+ * (D2 * ZMP)) chunks of the padded row space.
+ * rot_yx / copy_mats: scipy's as_matrix() entries, row-major; xtab / ztab [L2*D2]: the reference's coordinate
+ * tables (x and z of sample (column k, depth i)); copies in the reference's order (Halton re-indexed); the early stop
+ * SLR:1647 is applied here.  Call between hb2_batch_begin (one dummy angle) and hb2_batch_create. */
+typedef struct {
+  int32_t interpolation;   /* 0 = "nn", 1 = "linear" (SLR:1403-1510) */
+  double dy_pixel;
+  double rot_yx[9];        /* Rotation.from_euler("yx", (tilt, psi), degrees=True).as_matrix() */
+} hb2_explicit_geometry;
+int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry* g, int32_t n_copies, const double* copy_mats,
+                            const double* zshift, const double* xtab, const double* ztab, int64_t min_projection_lines,
+                            int32_t* copies_used, int32_t* rows_per_copy, int64_t* n_rows, int64_t* nnz);
+/* the rows as CSR in the reference's voxel order (entries unmerged: a voxel hit twice by one ray appears twice),
+ * right-hand side and pixel ids (SLR:1651-1654); any pointer may be NULL */
+int hb2_batch_explicit_export(hb2_batch* b, int64_t* indptr, int32_t* indices, float* data, float* b_out, int32_t* pid_out);
+
 /* ---- batch: step 2, candidates ----------------------------------------- */
 /* Finalises the batch: adjoint maps, right-hand side, symmetry rows
  * (replaces SLR:1142-1218 + 1221-1287 incl. the first-seen-wins de-duplication
