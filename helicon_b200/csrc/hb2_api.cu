@@ -171,6 +171,14 @@ struct hb2_batch {
   float* d_exp_b = nullptr;
   int* d_exp_pid = nullptr;
   float exp_bmax = 0.f;
+  int exp_md = 0;                 // explicit data rows
+  int *d_exp_ptr = nullptr, *d_exp_col = nullptr, *d_exp_erow = nullptr;
+  float* d_exp_w = nullptr;
+  bool exp_finished = false;
+  // trilinear symmetry rows (hb2_batch_explicit_sym_rows): 16 entries per row
+  int ls_m = 0;
+  int* d_ls_col = nullptr;
+  float* d_ls_w = nullptr;
   uint16_t* d_amap_i = nullptr;
   long long extra_launches = 0;  // kernels beyond one per launch_* call (band path: projector + reduce)
   int max_views = 0;
@@ -566,32 +574,6 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
   }
   const int nnz_i = (int)nnz;
   CK(cudaMemcpyAsync(d_ptr + m, &nnz_i, sizeof(int), cudaMemcpyHostToDevice, st));
-  // transpose: stable sort of the entries by voxel (deterministic adjoint order), column pointers from a histogram
-  int *d_cptr, *d_crow; float* d_cw;
-  CK(b->pool.alloc(&d_cptr, (size_t)B.npad + 2, true, st));
-  CK(b->pool.alloc(&d_crow, (size_t)nnz, false, st));
-  CK(b->pool.alloc(&d_cw, (size_t)nnz, false, st));
-  if (nnz > 0) {
-    int *d_keys2, *d_id, *d_id2, *d_cc;
-    CK(b->pool.alloc(&d_keys2, (size_t)nnz, false, st));
-    CK(b->pool.alloc(&d_id, (size_t)nnz, false, st));
-    CK(b->pool.alloc(&d_id2, (size_t)nnz, false, st));
-    CK(b->pool.alloc(&d_cc, (size_t)B.npad + 2, true, st));
-    k_iota<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id);
-    int bits = 1;
-    while ((1ll << bits) < (long long)B.npad) ++bits;
-    size_t sb3 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sb3, d_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st);
-    void* d_t3; { uint8_t* p; CK(b->pool.alloc(&p, sb3, false, st)); d_t3 = p; }
-    CK(cub::DeviceRadixSort::SortPairs(d_t3, sb3, d_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st));
-    k_exp_gather<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id2, d_erow, d_w, d_crow, d_cw);
-    k_exp_colcount<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_col, d_cc);
-    CKL();
-    size_t sb4 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, sb4, d_cc, d_cptr, B.npad + 1, st);
-    void* d_t4; { uint8_t* p; CK(b->pool.alloc(&p, sb4, false, st)); d_t4 = p; }
-    CK(cub::DeviceScan::ExclusiveSum(d_t4, sb4, d_cc, d_cptr, B.npad + 1, st));
-  }
   // max(b) over the rows: upper bound of the positive constraint (SLR:248)
   std::vector<float> hb((size_t)std::max(m, 1), 0.f);
   if (m > 0) CK(cudaMemcpyAsync(hb.data(), d_rb, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
@@ -601,10 +583,148 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
   b->exp_bmax = bm;
   b->explicit_rows = true;
   b->d_exp_b = d_rb; b->d_exp_pid = d_pid;
-  B.exp_m = m; B.exp_ptr = d_ptr; B.exp_col = d_col; B.exp_w = d_w; B.exp_cptr = d_cptr; B.exp_crow = d_crow; B.exp_cw = d_cw;
+  b->exp_md = m; b->d_exp_ptr = d_ptr; b->d_exp_col = d_col; b->d_exp_w = d_w; b->d_exp_erow = d_erow;
+  B.exp_m = m; B.exp_m_data = m; B.exp_ptr = d_ptr; B.exp_col = d_col; B.exp_w = d_w;
   if (copies_used) *copies_used = used;
   if (n_rows) *n_rows = m;
   if (nnz_out) *nnz_out = nnz;
+  return HB2_OK;
+}
+
+// Trilinear symmetry rows, see hb2_explicit.cuh.  pair_mats[p*12 ..] = M00, M01, M10, M11, M22, rise*h of member i,
+// then of member j (scipy's as_matrix entries).  One round per pair; stops when the row count reaches min_sym_pairs.
+extern "C" int hb2_batch_explicit_sym_rows(hb2_batch* b, int32_t npairs, const double* pair_mats, int64_t min_sym_pairs,
+                                           int64_t* n_rows) {
+  if (!b || npairs < 0 || (npairs > 0 && !pair_mats)) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_explicit_sym_rows must precede hb2_batch_create");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  b->ls_m = 0;
+  if (n_rows) *n_rows = 0;
+  if (npairs == 0 || min_sym_pairs < 0) return HB2_OK;
+  static_assert(sizeof(LsymPair) == 12 * sizeof(double), "LsymPair layout");
+  const long long cap_rows = std::min<long long>(min_sym_pairs + B.n, (long long)npairs * B.n);
+  if (cap_rows * 16 >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "too many trilinear symmetry rows");
+  LsymSetup Q{};
+  Q.n = B.n; Q.ndisk = B.ndisk; Q.D3 = B.D3; Q.L3 = B.L3; Q.L3P = B.L3P;
+  Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym;
+  Q.tab_cap = (unsigned long long)(2 * cap_rows + 17);
+  LsymPair* d_pairs; int* d_ov;
+  CK(b->pool.alloc(&d_pairs, (size_t)npairs, false, st));
+  CK(cudaMemcpyAsync(d_pairs, pair_mats, sizeof(LsymPair) * npairs, cudaMemcpyHostToDevice, st));
+  CK(b->pool.alloc(&Q.tab_key, (size_t)Q.tab_cap, false, st));
+  CK(b->pool.alloc(&Q.tab_seq, (size_t)Q.tab_cap, false, st));
+  CK(cudaMemsetAsync(Q.tab_key, 0xFF, sizeof(unsigned long long) * Q.tab_cap, st));
+  CK(cudaMemsetAsync(Q.tab_seq, 0xFF, sizeof(unsigned long long) * Q.tab_cap, st));
+  CK(b->pool.alloc(&Q.tmp_a, (size_t)B.n + 1, false, st));
+  CK(b->pool.alloc(&Q.tmp_b, (size_t)B.n + 1, false, st));
+  CK(b->pool.alloc(&Q.flag, (size_t)B.n + 1, true, st));
+  CK(b->pool.alloc(&Q.pos, (size_t)B.n + 1, true, st));
+  CK(b->pool.alloc(&d_ov, 1, true, st));
+  Q.overflow = d_ov;
+  CK(b->pool.alloc(&b->d_ls_col, (size_t)cap_rows * 16, false, st));
+  CK(b->pool.alloc(&b->d_ls_w, (size_t)cap_rows * 16, false, st));
+  size_t sb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, sb, Q.flag, Q.pos, B.n + 1, st);
+  void* d_tmp; { uint8_t* p; CK(b->pool.alloc(&p, sb, false, st)); d_tmp = p; }
+  long long rows = 0;
+  const unsigned gn = cdiv((long long)B.n + 1, 256);
+  for (int rnd = 0; rnd < npairs; ++rnd) {
+    k_lsym_insert<<<gn, 256, 0, st>>>(Q, d_pairs, rnd);
+    k_lsym_check<<<gn, 256, 0, st>>>(Q, rnd);
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, sb, Q.flag, Q.pos, B.n + 1, st));
+    k_lsym_emit<<<gn, 256, 0, st>>>(Q, d_pairs, rnd, (int)rows, (int)cap_rows, b->d_ls_col, b->d_ls_w);
+    CKL();
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(&h[0], Q.pos + B.n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h[1], d_ov, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[1]) return fail(HB2_ERR_CAPACITY, "trilinear symmetry rows: table overflow");
+    rows += h[0];
+    if (rows >= min_sym_pairs) break;  // SLR:1286
+  }
+  b->ls_m = (int)rows;
+  if (n_rows) *n_rows = rows;
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_explicit_sym_export(hb2_batch* b, int32_t* cols, float* w) {
+  if (!b) return fail(HB2_ERR_ARG, "null argument");
+  CK(cudaSetDevice(b->P->device));
+  const size_t ne = (size_t)b->ls_m * 16;
+  if (ne == 0) return HB2_OK;
+  if (cols) CK(cudaMemcpyAsync(cols, b->d_ls_col, sizeof(int) * ne, cudaMemcpyDeviceToHost, b->stream));
+  if (w) CK(cudaMemcpyAsync(w, b->d_ls_w, sizeof(float) * ne, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (cols) {
+    const int L3P = b->B.L3P, nd = b->B.ndisk;
+    const std::vector<int>& i2r = b->P->int2ref;
+    for (size_t e = 0; e < ne; ++e) cols[e] = (cols[e] % L3P) * nd + i2r[cols[e] / L3P];
+  }
+  return HB2_OK;
+}
+
+// Appends the trilinear symmetry rows (b = 0) to the explicit rows and builds the transpose (stable sort of the entries
+// by voxel -> deterministic adjoint order; column pointers from a histogram).  Called by hb2_batch_create.
+static int exp_finish(hb2_batch* b) {
+  if (b->exp_finished) return HB2_OK;
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  const int md = b->exp_md, ms = b->ls_m, m = md + ms;
+  const long long nnz_d = b->exp_nnz, nnz = nnz_d + 16ll * ms;
+  if (nnz >= (1ll << 31) - 64) return fail(HB2_ERR_CAPACITY, "explicit rows exceed 2^31 matrix entries");
+  if (ms > 0) {
+    int *ptr, *col, *erow; float *w, *rb;
+    CK(b->pool.alloc(&ptr, (size_t)m + 1, false, st));
+    CK(b->pool.alloc(&col, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&w, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&erow, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&rb, (size_t)m, true, st));
+    CK(cudaMemcpyAsync(ptr, b->d_exp_ptr, sizeof(int) * (md + 1), cudaMemcpyDeviceToDevice, st));
+    if (nnz_d) {
+      CK(cudaMemcpyAsync(col, b->d_exp_col, sizeof(int) * nnz_d, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(w, b->d_exp_w, sizeof(float) * nnz_d, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(erow, b->d_exp_erow, sizeof(int) * nnz_d, cudaMemcpyDeviceToDevice, st));
+    }
+    if (md) CK(cudaMemcpyAsync(rb, b->d_exp_b, sizeof(float) * md, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(col + nnz_d, b->d_ls_col, sizeof(int) * 16 * ms, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(w + nnz_d, b->d_ls_w, sizeof(float) * 16 * ms, cudaMemcpyDeviceToDevice, st));
+    k_lsym_ptr<<<cdiv(16ll * ms + 1, 256), 256, 0, st>>>(md, (int)nnz_d, ms, ptr, erow);
+    CKL();
+    b->d_exp_ptr = ptr; b->d_exp_col = col; b->d_exp_w = w; b->d_exp_erow = erow; b->d_exp_b = rb;
+  }
+  int *d_cptr, *d_crow; float* d_cw;
+  CK(b->pool.alloc(&d_cptr, (size_t)B.npad + 2, true, st));
+  CK(b->pool.alloc(&d_crow, (size_t)std::max<long long>(nnz, 1), false, st));
+  CK(b->pool.alloc(&d_cw, (size_t)std::max<long long>(nnz, 1), false, st));
+  if (nnz > 0) {
+    const int nnz_i = (int)nnz;
+    int *d_keys2, *d_id, *d_id2, *d_cc;
+    CK(b->pool.alloc(&d_keys2, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_id, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_id2, (size_t)nnz, false, st));
+    CK(b->pool.alloc(&d_cc, (size_t)B.npad + 2, true, st));
+    k_iota<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id);
+    int bits = 1;
+    while ((1ll << bits) < (long long)B.npad) ++bits;
+    size_t sb3 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sb3, b->d_exp_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st);
+    void* d_t3; { uint8_t* p; CK(b->pool.alloc(&p, sb3, false, st)); d_t3 = p; }
+    CK(cub::DeviceRadixSort::SortPairs(d_t3, sb3, b->d_exp_col, d_keys2, d_id, d_id2, nnz_i, 0, bits, st));
+    k_exp_gather<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, d_id2, b->d_exp_erow, b->d_exp_w, d_crow, d_cw);
+    k_exp_colcount<<<cdiv(nnz, 256), 256, 0, st>>>(nnz_i, b->d_exp_col, d_cc);
+    CKL();
+    size_t sb4 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sb4, d_cc, d_cptr, B.npad + 1, st);
+    void* d_t4; { uint8_t* p; CK(b->pool.alloc(&p, sb4, false, st)); d_t4 = p; }
+    CK(cub::DeviceScan::ExclusiveSum(d_t4, sb4, d_cc, d_cptr, B.npad + 1, st));
+  }
+  B.exp_m = m; B.exp_m_data = md;
+  B.exp_ptr = b->d_exp_ptr; B.exp_col = b->d_exp_col; B.exp_w = b->d_exp_w;
+  B.exp_cptr = d_cptr; B.exp_crow = d_crow; B.exp_cw = d_cw;
+  b->exp_finished = true;
   return HB2_OK;
 }
 
@@ -613,12 +733,12 @@ extern "C" int hb2_batch_explicit_export(hb2_batch* b, int64_t* indptr, int32_t*
   CK(cudaSetDevice(b->P->device));
   cudaStream_t st = b->stream;
   const BD& B = b->B;
-  const int m = B.exp_m;
+  const int m = b->exp_md;  // the data rows (trilinear symmetry rows: hb2_batch_explicit_sym_export)
   const long long nnz = b->exp_nnz;
   std::vector<int> ptr((size_t)m + 1);
-  CK(cudaMemcpyAsync(ptr.data(), B.exp_ptr, sizeof(int) * (m + 1), cudaMemcpyDeviceToHost, st));
-  if (indices && nnz) CK(cudaMemcpyAsync(indices, B.exp_col, sizeof(int) * nnz, cudaMemcpyDeviceToHost, st));
-  if (data && nnz) CK(cudaMemcpyAsync(data, B.exp_w, sizeof(float) * nnz, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ptr.data(), b->d_exp_ptr, sizeof(int) * (m + 1), cudaMemcpyDeviceToHost, st));
+  if (indices && nnz) CK(cudaMemcpyAsync(indices, b->d_exp_col, sizeof(int) * nnz, cudaMemcpyDeviceToHost, st));
+  if (data && nnz) CK(cudaMemcpyAsync(data, b->d_exp_w, sizeof(float) * nnz, cudaMemcpyDeviceToHost, st));
   if (b_out && m) CK(cudaMemcpyAsync(b_out, b->d_exp_b, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
   if (pid_out && m) CK(cudaMemcpyAsync(pid_out, b->d_exp_pid, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -943,6 +1063,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   k_build_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
   CKL();
   if (b->explicit_rows) {  // the explicit rows bring their own right-hand side (pseudo views have no columns)
+    { int rc_ = exp_finish(b); if (rc_ != HB2_OK) return rc_; }
     if (nc != 1) return fail(HB2_ERR_ARG, "a batch with explicit rows holds one candidate");
     if ((long long)B.exp_m > b->h_mdata[0]) return fail(HB2_ERR_ARG, "not enough pseudo views for the explicit rows");
     CKC(cudaMemcpyAsync(B.b + b->h_uoff[0], b->d_exp_b, sizeof(float) * B.exp_m, cudaMemcpyDeviceToDevice, st));

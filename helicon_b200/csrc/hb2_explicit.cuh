@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __r
         ss += un * un;
       } else if (mode == MODE_PLAIN) {
         urow[r] = acc;
-      } else {
+      } else if (vo + r < B.exp_m_data) {  // the score covers the data rows only (SLR:500-525)
         const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
         const float bv = brow[r];
         ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
@@ -202,4 +202,138 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_csc(BD B, TD Tt, const T* __r
     acc += (T)B.exp_cw[e] * val;
   }
   vt[(size_t)c * B.npad + g] = acc;
+}
+
+// ===========================================================================
+// Trilinear symmetry rows (SLR:910-1138 + the pair loop 1221-1287).  Per ordered pair of symmetry operations and per
+// mask voxel (np.nonzero order): the two images of the voxel, int() truncation corners, all 16 corners inside the grid
+// and the mask, |dz|, |dy|, |dx| >= 3 between the corner origins, first-seen-wins on the ROUNDED image pair (the
+// reference's pair_ids set), then 8 + 8 trilinear weights -- with the reference's corner-110 weight xf*yf*(1-xf)
+// (SLR:1089, 1125) reproduced.  Rounds run one pair at a time on the host (early stop SLR:1286).
+// ===========================================================================
+struct LsymPair { double mi[5]; double zi; double mj[5]; double zj; };  // M00, M01, M10, M11, M22 of scipy + rise*h
+struct LsymSetup {
+  int n, ndisk, D3, L3, L3P;
+  const int* rank_sym;            // [D3*D3] internal disk rank or -1
+  const short2* disk_yx_sym;      // [ndisk] reference order -> (y, x)
+  unsigned long long* tab_key;
+  unsigned long long* tab_seq;
+  unsigned long long tab_cap;
+  int* tmp_a;                     // rounded image i (internal voxel index or -1), -2: no row
+  int* tmp_b;
+  int* flag;
+  int* pos;
+  int* overflow;
+};
+
+struct LsymImg { double X, Y, Z; int xi, yi, zi; bool ok; };
+__device__ __forceinline__ LsymImg lsym_image(const double* M, double zs, int xc, int yc, int zc, int D3, int L3,
+                                              const int* __restrict__ rank) {
+  LsymImg r;
+  const double x = (double)xc, y = (double)yc, z = (double)zc;
+  // Rotation.apply(inverse=False): out = fma(M[r][2], z, fma(M[r][1], y, M[r][0]*x)); M02 = M12 = M20 = M21 = 0
+  r.X = __dadd_rn(__fma_rn(M[1], y, __dmul_rn(M[0], x)), (double)(D3 / 2));
+  r.Y = __dadd_rn(__fma_rn(M[3], y, __dmul_rn(M[2], x)), (double)(D3 / 2));
+  r.Z = __dadd_rn(__dadd_rn(__dmul_rn(M[4], z), (double)(L3 / 2)), zs);
+  r.ok = false;
+  if (!(r.Z > -1.0 && r.Z < (double)L3 && r.Y > -1.0 && r.Y < (double)D3 && r.X > -1.0 && r.X < (double)D3)) return r;
+  r.zi = (int)r.Z; r.yi = (int)r.Y; r.xi = (int)r.X;
+  if (r.zi + 1 > L3 - 1 || r.yi + 1 > D3 - 1 || r.xi + 1 > D3 - 1) return r;
+  if (rank[r.yi * D3 + r.xi] < 0 || rank[r.yi * D3 + r.xi + 1] < 0 || rank[(r.yi + 1) * D3 + r.xi] < 0 ||
+      rank[(r.yi + 1) * D3 + r.xi + 1] < 0)
+    return r;
+  r.ok = true;
+  return r;
+}
+// mask_nonzero_indices_matrix[round(Z), round(Y), round(X)] with numpy's negative-index wrap (Z in (-1, -0.5) rounds to
+// -1 = the last slice); -1 when the rounded voxel is outside the mask
+__device__ __forceinline__ int lsym_rounded(const LsymImg& g, int D3, int L3, int L3P, const int* __restrict__ rank) {
+  int zr = (int)rint(g.Z), yr = (int)rint(g.Y), xr = (int)rint(g.X);
+  if (zr < 0) zr += L3;
+  if (yr < 0) yr += D3;
+  if (xr < 0) xr += D3;
+  const int p = rank[yr * D3 + xr];
+  return p < 0 ? -1 : p * L3P + zr;
+}
+__device__ __forceinline__ bool lsym_eval(const LsymSetup& Q, const LsymPair& P, int g, LsymImg& a, LsymImg& b) {
+  const int z = g / Q.ndisk, p = g % Q.ndisk;
+  const short2 yx = Q.disk_yx_sym[p];
+  const int xc = yx.y - Q.D3 / 2, yc = yx.x - Q.D3 / 2, zc = z - Q.L3 / 2;
+  a = lsym_image(P.mi, P.zi, xc, yc, zc, Q.D3, Q.L3, Q.rank_sym);
+  if (!a.ok) return false;
+  b = lsym_image(P.mj, P.zj, xc, yc, zc, Q.D3, Q.L3, Q.rank_sym);
+  if (!b.ok) return false;
+  if (abs(a.zi - b.zi) < 3 || abs(a.yi - b.yi) < 3 || abs(a.xi - b.xi) < 3) return false;
+  return true;
+}
+__device__ __forceinline__ unsigned long long lsym_key(int ir, int jr) {
+  const unsigned lo = (unsigned)(min(ir, jr) + 1), hi = (unsigned)(max(ir, jr) + 1);
+  return ((unsigned long long)lo << 32) | hi;
+}
+
+__global__ void k_lsym_insert(LsymSetup Q, const LsymPair* __restrict__ pairs, int rnd) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Q.n) return;
+  LsymImg a, b;
+  if (!lsym_eval(Q, pairs[rnd], g, a, b)) { Q.tmp_a[g] = -2; Q.tmp_b[g] = -2; return; }
+  const int ir = lsym_rounded(a, Q.D3, Q.L3, Q.L3P, Q.rank_sym), jr = lsym_rounded(b, Q.D3, Q.L3, Q.L3P, Q.rank_sym);
+  Q.tmp_a[g] = ir; Q.tmp_b[g] = jr;
+  const unsigned long long key = lsym_key(ir, jr);
+  const unsigned long long seq = (unsigned long long)rnd * (unsigned long long)Q.n + (unsigned long long)g;
+  unsigned long long slot = hash64(key) % Q.tab_cap;
+  for (unsigned long long probe = 0; probe < Q.tab_cap; ++probe) {
+    const unsigned long long old = atomicCAS(&Q.tab_key[slot], HB2_EMPTY_KEY, key);
+    if (old == HB2_EMPTY_KEY || old == key) { atomicMin(&Q.tab_seq[slot], seq); return; }
+    slot = slot + 1 == Q.tab_cap ? 0 : slot + 1;
+  }
+  atomicExch(Q.overflow, 1);
+}
+__global__ void k_lsym_check(LsymSetup Q, int rnd) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > Q.n) return;
+  int keep = 0;
+  if (g < Q.n && Q.tmp_a[g] != -2) {
+    const unsigned long long key = lsym_key(Q.tmp_a[g], Q.tmp_b[g]);
+    const unsigned long long seq = (unsigned long long)rnd * (unsigned long long)Q.n + (unsigned long long)g;
+    unsigned long long slot = hash64(key) % Q.tab_cap;
+    for (unsigned long long probe = 0; probe < Q.tab_cap; ++probe) {
+      const unsigned long long kk = Q.tab_key[slot];
+      if (kk == key) { keep = Q.tab_seq[slot] == seq; break; }
+      if (kk == HB2_EMPTY_KEY) break;
+      slot = slot + 1 == Q.tab_cap ? 0 : slot + 1;
+    }
+  }
+  Q.flag[g] = keep;  // flag[n] = 0: the scan's last entry is the round's row count
+}
+__device__ __forceinline__ void lsym_weights(const LsymImg& g, double sgn, int L3P, int D3, const int* __restrict__ rank,
+                                             int* __restrict__ col, float* __restrict__ w) {
+  const double zf = __dsub_rn(g.Z, (double)g.zi), yf = __dsub_rn(g.Y, (double)g.yi), xf = __dsub_rn(g.X, (double)g.xi);
+  const double mz = __dsub_rn(1.0, zf), my = __dsub_rn(1.0, yf), mx = __dsub_rn(1.0, xf);
+  const int p00 = rank[g.yi * D3 + g.xi], p01 = rank[g.yi * D3 + g.xi + 1];
+  const int p10 = rank[(g.yi + 1) * D3 + g.xi], p11 = rank[(g.yi + 1) * D3 + g.xi + 1];
+  const double a = sgn * mz, c = sgn * zf, e = sgn * xf;  // unary minus binds first in the reference's expressions
+  col[0] = p00 * L3P + g.zi;     w[0] = (float)__dmul_rn(__dmul_rn(a, my), mx);
+  col[1] = p01 * L3P + g.zi;     w[1] = (float)__dmul_rn(__dmul_rn(a, my), xf);
+  col[2] = p10 * L3P + g.zi;     w[2] = (float)__dmul_rn(__dmul_rn(a, yf), mx);
+  col[3] = p11 * L3P + g.zi;     w[3] = (float)__dmul_rn(__dmul_rn(a, yf), xf);
+  col[4] = p00 * L3P + g.zi + 1; w[4] = (float)__dmul_rn(__dmul_rn(c, my), mx);
+  col[5] = p01 * L3P + g.zi + 1; w[5] = (float)__dmul_rn(__dmul_rn(c, my), xf);
+  col[6] = p10 * L3P + g.zi + 1; w[6] = (float)__dmul_rn(__dmul_rn(e, yf), mx);   // SLR:1089/1125: xf*yf*(1-xf)
+  col[7] = p11 * L3P + g.zi + 1; w[7] = (float)__dmul_rn(__dmul_rn(e, yf), zf);   // xf*yf*zf
+}
+__global__ void k_lsym_emit(LsymSetup Q, const LsymPair* __restrict__ pairs, int rnd, int row0, int cap_rows,
+                            int* __restrict__ col, float* __restrict__ w) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= Q.n || !Q.flag[g]) return;
+  const int row = row0 + Q.pos[g];
+  if (row >= cap_rows) { atomicExch(Q.overflow, 2); return; }
+  LsymImg a, b;
+  lsym_eval(Q, pairs[rnd], g, a, b);
+  lsym_weights(a, 1.0, Q.L3P, Q.D3, Q.rank_sym, col + (size_t)row * 16, w + (size_t)row * 16);
+  lsym_weights(b, -1.0, Q.L3P, Q.D3, Q.rank_sym, col + (size_t)row * 16 + 8, w + (size_t)row * 16 + 8);
+}
+__global__ void k_lsym_ptr(int m0, int nnz0, int ms, int* __restrict__ ptr, int* __restrict__ erow) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= ms) ptr[m0 + t] = nnz0 + 16 * t;
+  if (t < ms * 16) erow[nnz0 + t] = m0 + t / 16;
 }

@@ -105,6 +105,7 @@ struct BD {
   const int* cand_pixmask;      // [nc] mask index or -1
   // explicit data rows (hb2_explicit.cuh): CSR of the rows (col = internal voxel index) and its transpose
   int exp_m;                    // number of explicit rows (0: matrix-free batch)
+  int exp_m_data;               // the first exp_m_data of them are data rows (scored); the rest trilinear symmetry rows
   const int* exp_ptr;           // [exp_m + 1]
   const int* exp_col;
   const float* exp_w;

@@ -360,7 +360,11 @@ class ExplicitBatch(Batch):
         self._stream_ref = stream
         self.L3 = int(L3)
         D2, L2 = problem.D2, problem.L2
-        self.plan = BatchPlan(problem.s, D2, L2, self.L3, [spec], exact_ties=False)  # used for the symmetry pairs only
+        linear = interpolation == "linear"
+        # nearest neighbour: the batch's own symmetry rows (pairs from the planner); trilinear: explicit rows as well
+        plan_spec = CandidateSpec(spec.twist, spec.rise_pixel, spec.csym, spec.min_projection_lines,
+                                  -1 if linear else spec.min_sym_pairs, spec.positive)
+        self.plan = BatchPlan(problem.s, D2, L2, self.L3, [plan_spec], exact_ties=False)
         st = problem.stream if stream is None else _stream_handle(stream)
         dummy = np.array([[1.0, 0.0]], dtype=np.float64)  # the in-plane maps are not used by explicit rows
         self.nvalid = np.zeros(1, dtype=np.int32)
@@ -386,12 +390,21 @@ class ExplicitBatch(Batch):
             self._h, C.byref(geo), len(copies), _lib.ptr(mats), _lib.ptr(zshift), _lib.ptr(Xt), _lib.ptr(Zt),
             int(spec.min_projection_lines), C.byref(used), _lib.ptr(self.rows_per_copy), C.byref(m), C.byref(nnz)))
         self.copies_used, self.m_rows, self.nnz = int(used.value), int(m.value), int(nnz.value)
+        self.m_sym_explicit = 0
+        if linear and spec.min_sym_pairs >= 0:
+            if problem.D3 != D2:
+                raise NotImplementedError("helicon_b200: trilinear rows need reconstruct_diameter_3d == 2d diameter")
+            tab = planner.trilinear_pair_table(spec.twist, spec.rise_pixel, spec.csym, self.L3)
+            ms = C.c_int64()
+            _lib.check(lib.hb2_batch_explicit_sym_rows(self._h, len(tab), _lib.ptr(tab), int(spec.min_sym_pairs),
+                                                       C.byref(ms)))
+            self.m_sym_explicit = int(ms.value)
         # pairs (symmetry rows) from the planner; views replaced by pseudo views over the explicit rows
         p = self.plan
         p.finalize(np.zeros(len(p.angles), dtype=np.int64))
         ZMP = (self.L3 + 3) // 4 * 4
         rpv = D2 * ZMP
-        nv = (self.m_rows + rpv - 1) // rpv
+        nv = (self.m_rows + self.m_sym_explicit + rpv - 1) // rpv
         views = np.zeros(nv, dtype=_lib.VIEW_DTYPE)
         views["angle"] = 0
         views["tie"] = 0
@@ -423,7 +436,43 @@ class ExplicitBatch(Batch):
         A = csr_matrix((data[:nnz], indices[:nnz], indptr), shape=(m, self.n), dtype=np.float32)
         return A, b[:m], pid[:m]
 
+    def sym_csr(self, c=0):
+        if not self.m_sym_explicit:
+            return super().sym_csr(c)
+        return trilinear_sym_csr(self._h, self.m_sym_explicit, self.n)
+
     def data_row_index(self, c=0):
         _, _, pid = self.data_csr(0)
         D2 = self.problem.D2
         return np.arange(self.m_rows, dtype=np.int64), (pid // D2).astype(np.int64), (pid % D2).astype(np.int64)
+
+
+def trilinear_sym_csr(handle, m, n):
+    """A_hsym, b_hsym (SLR:1289-1298) from the GPU-built trilinear symmetry rows (duplicates summed by scipy)."""
+    if m == 0:
+        return None, None
+    cols = np.zeros(16 * m, dtype=np.int32)
+    w = np.zeros(16 * m, dtype=np.float32)
+    _lib.check(_lib.load().hb2_batch_explicit_sym_export(handle, _lib.ptr(cols), _lib.ptr(w)))
+    A = csr_matrix((w, cols, np.arange(m + 1, dtype=np.int64) * 16), shape=(m, n), dtype=np.float32)
+    A.sum_duplicates()
+    return A, np.zeros(m, dtype=np.float32)
+
+
+def build_trilinear_sym_rows(problem: Problem, nz, twist, rise_pixel, csym, min_sym_pairs):
+    """build_A_helical_sym_matrix with interpolation "linear": rows built on the GPU, nothing else of a batch."""
+    from . import planner
+
+    lib = _lib.require_gpu()
+    h = C.c_void_p()
+    dummy = np.array([[1.0, 0.0]], dtype=np.float64)
+    nvalid, tie = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    _lib.check(lib.hb2_batch_begin(C.byref(h), problem._h, int(nz), 1, 1, _lib.ptr(dummy), _lib.ptr(nvalid), _lib.ptr(tie),
+                                   problem.stream))
+    try:
+        tab = planner.trilinear_pair_table(twist, rise_pixel, csym, int(nz))
+        ms = C.c_int64()
+        _lib.check(lib.hb2_batch_explicit_sym_rows(h, len(tab), _lib.ptr(tab), int(min_sym_pairs), C.byref(ms)))
+        return trilinear_sym_csr(h, int(ms.value), int(nz) * problem.ndisk)
+    finally:
+        lib.hb2_batch_destroy(h)

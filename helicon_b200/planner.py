@@ -81,6 +81,21 @@ def z_rotation_entries(angles_deg):
     return np.ascontiguousarray(np.stack([M[:, 0, 0], M[:, 1, 0]], axis=1))
 
 
+def trilinear_pair_table(twist, rise_pixel, csym, nz):
+    """Rows of ``hb2_batch_explicit_sym_rows``: for every pair of ``sorted_hsym_csym_pairs`` (SLR:892) the entries
+    M00, M01, M10, M11, M22 of ``Rotation.from_euler('z', twist*h + 360*c/csym)`` (SLR:1225, 1235) and the z shift
+    rise_pixel*h (SLR:1231, 1243) of both members -> float64 [n_pairs, 12]."""
+    from scipy.spatial.transform import Rotation as R
+
+    plist = sorted_hsym_csym_pairs(twist, rise_pixel, csym, nz)
+    out = np.zeros((len(plist), 12), dtype=np.float64)
+    for q, p in enumerate(plist):
+        for m, (h, c) in enumerate(p[-1]):
+            M = R.from_euler("z", twist * h + c * 360 / csym, degrees=True).as_matrix()
+            out[q, 6 * m:6 * m + 6] = (M[0, 0], M[0, 1], M[1, 0], M[1, 1], M[2, 2], rise_pixel * h)
+    return out
+
+
 def z_rotation_m22(angles_deg):
     """M22 of the same scipy rotation matrices: 1.0 or 1 - 2**-53 depending on the angle."""
     from scipy.spatial.transform import Rotation as R

@@ -4,7 +4,6 @@ reference's denovo3D solver, "SLR") with the per-candidate work on the GPU.
 Same function names, argument meaning, return types and array layouts as the
 reference; see INTEGRATION.md.  What is NOT implemented on the CUDA path raises
 ``NotImplementedError`` (there is no CPU fallback by design):
-``interpolation="linear"`` inside ``lsq_reconstruct`` (its data rows are built, its symmetry rows not yet),
 ``refine_tilt_psi_dy``, score metrics other than
 "cosine", and solver models other than ``{"model": "lsq"}``.
 """
@@ -17,7 +16,7 @@ import logging
 import numpy as np
 
 from . import planner
-from .engine import Batch, ExplicitBatch, Problem
+from .engine import Batch, ExplicitBatch, Problem, build_trilinear_sym_rows
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
 
@@ -138,8 +137,12 @@ def build_A_helical_sym_matrix(
     """SLR:844-1298 -> (csr_matrix float32 | None, zeros float32 | None)."""
     if ny != nx:
         _unsupported("a non-square symmetry grid (ny != nx)")
-    prob = Problem(np.zeros((ny, nx), dtype=np.float32), 1.0, ny, nx, ny, rmin, rmax if rmax >= 0 else ny // 2 - 1,
-                   interpolation=interpolation)
+    prob = Problem(np.zeros((ny, nx), dtype=np.float32), 1.0, ny, nx, ny, rmin, rmax if rmax >= 0 else ny // 2 - 1)
+    if interpolation in ("linear", "linear01", "linear11"):  # SLR:907 (this list differs from the data builder's)
+        try:
+            return build_trilinear_sym_rows(prob, nz, twist_degree, rise_pixel, csym, min_sym_pairs)
+        finally:
+            prob.close()
     spec = CandidateSpec(twist_degree, rise_pixel, csym, 1, min_sym_pairs, False)
     batch = Batch(prob, nz, [spec])
     try:
@@ -182,9 +185,9 @@ def lsq_reconstruct(
     One candidate through the batched GPU path (a batch of one).  ``device`` and
     ``return_info`` are additive keyword arguments."""
     explicit = _is_explicit(tilt_degree, psi_degree, dy_pixel, interpolation)
-    if explicit and _interp(interpolation) == "linear":
-        _unsupported("interpolation='linear' in lsq_reconstruct (trilinear symmetry rows, SLR:910-1138; the trilinear "
-                     "data rows are available through build_A_data_matrix)")
+    if interpolation in ("linear10", "linear01"):
+        _unsupported(f"interpolation={interpolation!r} (the reference's data and symmetry builders disagree on it, "
+                     "SLR:907 vs 1401)")
     if explicit and fsc_test:
         _unsupported("fsc_test together with tilt/psi/dy != 0")
     if algorithm.get("model", "lsq") != "lsq":

@@ -192,6 +192,18 @@ int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry* g, int32_
  * right-hand side and pixel ids (SLR:1651-1654); any pointer may be NULL */
 int hb2_batch_explicit_export(hb2_batch* b, int64_t* indptr, int32_t* indices, float* data, float* b_out, int32_t* pid_out);
 
+/* Trilinear symmetry rows (build_A_helical_sym_matrix with interpolation "linear", SLR:910-1138 + pair loop
+ * 1221-1287), built on the GPU: per ordered pair and mask voxel the two images (scipy Rotation.apply arithmetic),
+ * int() corners, all 16 corners valid, corner origins >= 3 apart on every axis, first-seen-wins on the rounded image
+ * pair, 8 + 8 weights (incl. the reference's corner-110 expression xf*yf*(1-xf)).  pair_mats[p*12..] = M00, M01, M10,
+ * M11, M22 of scipy's matrix and rise*h for member i, then the same for member j; pairs in sorted_hsym_csym_pairs
+ * order; stops when the row count reaches min_sym_pairs.  In a batch with explicit data rows they are appended to
+ * them (b = 0, not scored) and the candidate is created with pair_count = 0.  Call before hb2_batch_create. */
+int hb2_batch_explicit_sym_rows(hb2_batch* b, int32_t n_pairs, const double* pair_mats, int64_t min_sym_pairs,
+                                int64_t* n_rows);
+/* the rows as 16 (column, weight) entries each, columns in the reference's voxel order; either may be NULL */
+int hb2_batch_explicit_sym_export(hb2_batch* b, int32_t* cols, float* weights);
+
 /* ---- batch: step 2, candidates ----------------------------------------- */
 /* Finalises the batch: adjoint maps, right-hand side, symmetry rows
  * (replaces SLR:1142-1218 + 1221-1287 incl. the first-seen-wins de-duplication

@@ -55,3 +55,36 @@ for name, N, apix, twist, rise, csym, pc, so, L3, tilt, psi, dy in SOLVE:
                         args=np.array([apix, twist, rise, csym, pc, so, L3, tilt, psi, dy], dtype=np.float64), rec3d=rec,
                         score=np.float64(score))
     print(name, rec.shape, float(score))
+
+# trilinear full solves: (name, N, apix, twist, rise_A, csym, positive_constraint, sym_oversample, L3, tilt, psi, dy)
+SOLVE_LIN = [
+    ("gen_solve_lin_48", 48, 5.4, -3.5, 9.5, 1, 0, 2, 8, 0.0, 0.0, 0.0),
+    ("gen_solve_lin_48_pos", 48, 5.4, -3.5, 9.5, 1, 1, 2, 8, 0.0, 0.0, 0.0),
+    ("gen_solve_lin_40_c2_tilt", 40, 6.5, 27.0, 12.0, 2, 0, 2, 10, 2.0, -1.0, 0.5),
+]
+for name, N, apix, twist, rise, csym, pc, so, L3, tilt, psi, dy in SOLVE_LIN:
+    img = synth_image(N, apix, twist=twist, rise=rise, csym=csym)
+    S.build_A_data_matrix.clear_cache()
+    S.build_A_helical_sym_matrix.clear_cache()
+    (rec, _, _), score = S.lsq_reconstruct(
+        projection_image=img, scale2d_to_3d=1.0, twist_degree=twist, rise_pixel=rise / apix, csym=csym, tilt_degree=tilt,
+        psi_degree=psi, dy_pixel=dy, positive_constraint=pc, reconstruct_diameter_2d_pixel=N,
+        reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N, reconstruct_length_3d_pixel=L3,
+        sym_oversample=so, interpolation="linear", algorithm=dict(model="lsq"), cpu=1)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), image=img,
+                        args=np.array([apix, twist, rise, csym, pc, so, L3, tilt, psi, dy], dtype=np.float64), rec3d=rec,
+                        score=np.float64(score))
+    print(name, rec.shape, float(score))
+
+# trilinear symmetry rows: (name, nz, ny, nx, twist, rise_px, csym, rmin, rmax, min_pairs)
+HSYM_LIN = [
+    ("gen_hsym_lin_c2_stop", 10, 24, 24, 41.0, 1.43, 2, 0, 11, 2500),
+    ("gen_hsym_lin_inner", 12, 20, 20, -7.3, 2.37, 1, 3, 9, 10**7),
+    ("gen_hsym_lin_tie", 10, 20, 20, 30.0, 2.5, 1, 0, 9, 10**7),
+]
+for name, nz, ny, nx, twist, rise, csym, rmin, rmax, msp in HSYM_LIN:
+    A, b = S.build_A_helical_sym_matrix.__wrapped__(nz, ny, nx, twist, rise, csym, rmin, rmax, msp, "linear", verbose=0)
+    d = dict(args=np.array([nz, ny, nx, twist, rise, csym, rmin, rmax, msp], dtype=np.float64))
+    d.update(csr_parts(A, "A"))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(name, A.shape, A.nnz)
