@@ -1271,7 +1271,7 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (b->nviews == 0) return;
   if (b->n_tie_views > 0) {  // exact rows of the tie views (the projector kernels below skip them)
     const float* src = mode == MODE_LSMR ? B.v : B.xs;
-    if (b->explicit_rows) k_fwd_csr<float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    if (b->explicit_rows) k_fwd_csr<float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     else if (b->idx16) k_fwd_tie<uint16_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     else k_fwd_tie<uint32_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     b->extra_launches += 1;
@@ -1309,7 +1309,7 @@ static void launch_adj(hb2_batch* b, int mode) {
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
   if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
-    if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+    if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     else k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     b->extra_launches += 1;
   }
@@ -1453,7 +1453,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     launches += 2;
     if (b->n_tie_views > 0) {
-      if (b->explicit_rows) k_fwd_csr<double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      if (b->explicit_rows) k_fwd_csr<double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       else if (b->idx16) k_fwd_tie<uint16_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       else k_fwd_tie<uint32_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       ++launches;
@@ -1461,7 +1461,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   };
   auto adj = [&](const double* rows, double* dst, int gate) {
     if (b->n_tie_views > 0) {
-      if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+      if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       else k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;
     }

@@ -126,12 +126,13 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __r
   const int view = B.tie_views[blockIdx.x];
   const int c = B.view_cand[view];
   __shared__ float red[HB2_BLOCK / 32];
-  const int ppv = B.fwd_ppv;
+  const int ppv = B.fwd_ppv;       // partial-sum slots per view = gridDim.y sub-CTAs per pseudo view
+  const int sub = blockIdx.y;
   const bool act = tie_active<TRF>(B, Tt, c, mode, false);
   if (!act) {
-    if (!TRF && threadIdx.x < ppv) {
-      if (mode == MODE_LSMR) B.part_u[view * ppv + threadIdx.x] = 0.f;
-      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + threadIdx.x)] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 1] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 2] = 0.f; }
+    if (!TRF && threadIdx.x == 0) {
+      if (mode == MODE_LSMR) B.part_u[view * ppv + sub] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + sub)] = 0.f; B.part_s[3 * (view * ppv + sub) + 1] = 0.f; B.part_s[3 * (view * ppv + sub) + 2] = 0.f; }
     }
     return;
   }
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __r
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   const int nrow = (int)min((long long)B.rows_per_view, (long long)B.exp_m - vo);
-  for (int r = warp; r < nrow; r += HB2_BLOCK / 32) {
+  for (int r = sub * (HB2_BLOCK / 32) + warp; r < nrow; r += ppv * (HB2_BLOCK / 32)) {
     const int e0 = B.exp_ptr[vo + r], e1 = B.exp_ptr[vo + r + 1];
     T acc = (T)0;
     for (int e = e0 + lane; e < e1; e += 32) acc += (T)B.exp_w[e] * vsrc[B.exp_col[e]];
@@ -169,39 +170,41 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __r
   if (!TRF) {
     if (mode == MODE_LSMR) {
       const float tot = block_sum(ss, red);
-      if (threadIdx.x < ppv) B.part_u[view * ppv + threadIdx.x] = threadIdx.x == 0 ? tot : 0.f;
+      if (threadIdx.x == 0) B.part_u[view * ppv + sub] = tot;
     } else if (mode == MODE_SCORE) {
       const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
-      if (threadIdx.x < ppv) {
-        const bool f = threadIdx.x == 0;
-        B.part_s[3 * (view * ppv + threadIdx.x)] = f ? t0 : 0.f;
-        B.part_s[3 * (view * ppv + threadIdx.x) + 1] = f ? t1 : 0.f;
-        B.part_s[3 * (view * ppv + threadIdx.x) + 2] = f ? t2 : 0.f;
+      if (threadIdx.x == 0) {
+        B.part_s[3 * (view * ppv + sub)] = t0;
+        B.part_s[3 * (view * ppv + sub) + 1] = t1;
+        B.part_s[3 * (view * ppv + sub) + 2] = t2;
       }
     }
   }
 }
 
 // Adjoint: vt[c][g] = sum over the transpose list of voxel g of w * rows[row] (* inv_beta in the LSMR modes, like
-// k_adj_tie); the adjoint kernels add vt to the symmetry part.  One thread per voxel entry g = p*L3P + z.
+// k_adj_tie); the adjoint kernels add vt to the symmetry part.  One warp per voxel entry g = p*L3P + z (fixed
+// lane-strided order + xor tree: deterministic).
 template <typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BLOCK) k_adj_csc(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
   const int c = blockIdx.y;
   if (B.cand_tie_count[c] == 0) return;
   if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
-  const int g = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const int g = blockIdx.x * (HB2_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;  // one warp per voxel
   if (g >= B.npad) return;
   T ib = (T)1;
   if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
   const T* __restrict__ ub = rows + B.cand_uoff[c];
   T acc = (T)0;
   const int e0 = B.exp_cptr[g], e1 = B.exp_cptr[g + 1];
-  for (int e = e0; e < e1; ++e) {
+  for (int e = e0 + lane; e < e1; e += 32) {
     const T uv = ub[B.exp_crow[e]];
     const T val = TRF ? uv : (T)fmaf((float)uv, (float)ib, 0.f);
     acc += (T)B.exp_cw[e] * val;
   }
-  vt[(size_t)c * B.npad + g] = acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) vt[(size_t)c * B.npad + g] = acc;
 }
 
 // ===========================================================================

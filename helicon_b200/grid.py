@@ -16,7 +16,7 @@ import numpy as np
 
 from concurrent.futures import ThreadPoolExecutor
 
-from .engine import Batch, Problem, Stream
+from .engine import Batch, ExplicitBatch, Problem, Stream
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 
 
@@ -163,8 +163,13 @@ def _bytes_per_candidate(n, md, cap):
 def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=3, tube_diameter=None,
                 tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
                 positive_constraint=-1, thresh_fraction=-1, top_k=10, device=0, stream=None, batch_candidates=None,
-                mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None, pipelined=True):
+                mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None, pipelined=True,
+                interpolation="nn"):
     """Solve + score every candidate of the grid on one GPU.
+
+    ``interpolation="nn"`` runs batches of candidates through the matrix-free projector; ``"linear"`` (trilinear rows,
+    SLR:1403-1510 / 910-1138) runs one candidate at a time on explicit GPU-built rows (engine.ExplicitBatch) -- same
+    results contract, lower throughput.
 
     ``shard=(rank, world)`` keeps tasks ``rank::world`` of every twist-major
     batch ordering so that several GPUs split the grid without communication.
@@ -208,9 +213,16 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                 cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
                 per_cand = _bytes_per_candidate(n3, md_est, cap_est) * (2 if pipelined else 1)  # two batches resident
                 bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // per_cand)))
+                if interpolation != "nn":
+                    bs = 1
                 chunks = [tl[i0:i0 + bs] for i0 in range(0, len(tl), bs)]
                 done = 0
-                for bi, batch in pipe.run(prob, L3, [[x.spec for x in ch] for ch in chunks]):
+                if interpolation == "nn":
+                    batches = pipe.run(prob, L3, [[x.spec for x in ch] for ch in chunks])
+                else:
+                    batches = ((bi, ExplicitBatch(prob, L3, ch[0].spec, interpolation=interpolation))
+                               for bi, ch in enumerate(chunks))
+                for bi, batch in batches:
                     chunk = chunks[bi]
                     try:
                         res = batch.solve(clip_pred=int(thresh_fraction >= 0))

@@ -179,6 +179,11 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
             sym_oversample = max(1, int(round(ratio / 100)) * 100)
         if return_3d:
             sym_oversample *= 2
+    if tilt != 0 or psi != 0 or dy != 0:
+        # the solve itself handles a tilted candidate (explicit rows), but the display products then go through
+        # helicon.transform_map (pipeline.py:436-438, scipy.ndimage affine resampling), which is not on the CUDA path
+        _unsupported("tilt/psi/dy != 0 in process_one_task (transform_map of the display volume); "
+                     "solver_linear_regression.lsq_reconstruct accepts them")
     # ---- solve + score (pipeline.py:351-404) on the GPU -------------------------------------------------------------
     refine_range = None
     if algorithm.get("model", "lsq") in ("lsq", "elasticnet", "lasso", "ridge"):
@@ -206,7 +211,7 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
     else:
         pitch_pixel = int(np.ceil(2 * rise / apix2d_orig))
     new_length = max(nx_orig, int(pitch_pixel * 1.2))
-    # tilt = psi = dy = 0 here (anything else was refused by lsq_reconstruct): transform_map is the identity
+    # tilt = psi = dy = 0 here (refused above otherwise): transform_map is the identity
     rec3d_x_proj, rec3d_y_proj, rec3d_z_sections = transforms.symmetrize_and_project(
         rec3d, target_apix3d, twist, rise, csym, (new_length, ny_orig, ny_orig), apix2d_orig, rise, apix2d_orig)
     nz, ny, nx = rec3d.shape
