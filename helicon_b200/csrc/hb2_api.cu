@@ -1025,7 +1025,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     const char* use_band = getenv("HB2_FWD_BAND");
     const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)sizeof(float));
     std::vector<int> bands{0};
-    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && (use_band && atoi(use_band)) && b->n_tie_views == 0;
+    const int band_mode = use_band ? atoi(use_band) : 0;  // 1: sample-lane kernel, 2: (ray, quad)-lane kernel
+    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->n_tie_views == 0;
+    if (band_mode == 2 && !(b->idx16 && D2 % 8 == 0)) ok = false;
     const std::vector<int>& tr = P->h_tilerow_begin;
     for (size_t r = 0; ok && r + 1 < tr.size(); ++r) {
       if (tr[r + 1] - tr[r] > cap) { ok = false; break; }
@@ -1036,7 +1038,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     if (ok && NB <= HB2_MAX_BANDS) {
       int max_bn = 0;
       for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
-      b->fwd_band_smem = (size_t)max_bn * B.L3P * sizeof(float);
+      b->fwd_band_smem = (size_t)(band_mode == 2 ? max_bn + HB2_FWDB2_PAD * ((max_bn + 31) / 32) : max_bn) * B.L3P * sizeof(float);
       CKC(upload(b->pool, &B.band_begin, bands, st));
       ushort2 *d_seg, *d_rng;
       CKC(b->pool.alloc(&d_seg, (size_t)B.nA * NB * D2, false, st));
@@ -1051,7 +1053,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       for (int c = 0; c < nc; ++c) { poff[c] = po; po += (long long)b->h_view_count[c] * NB * D2 * B.L3P; }
       CKC(upload(b->pool, &B.cand_poff, poff, st));
       CKC(b->pool.alloc(&B.fwd_part, (size_t)std::max<long long>(po, 1), false, st));
-      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = 1; B.fwd_ppv = 1;
+      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = band_mode == 2 ? 2 : 1; B.fwd_ppv = 1;
     }
   }
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
@@ -1286,7 +1288,15 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
     k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
   } while (0)
 #define FWBQ(T) do { if (B.L3P == 4) FWB(T, 1); else if (B.L3P == 8) FWB(T, 2); else if (B.L3P == 12) FWB(T, 3); else FWB(T, 4); } while (0)
-    if (b->idx16) FWBQ(uint16_t); else FWBQ(uint32_t);
+#define FWB2(Q)                                                                                           \
+  do {                                                                                                    \
+    cudaFuncSetAttribute(k_fwd_band2<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);           \
+    k_fwd_band2<Q><<<gb, HB2_FWDB2_THREADS, sm, st>>>(B, mode);                                           \
+    k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
+  } while (0)
+    if (B.fwd_band == 2) { if (B.L3P == 4) FWB2(1); else if (B.L3P == 8) FWB2(2); else if (B.L3P == 12) FWB2(3); else FWB2(4); }
+    else if (b->idx16) FWBQ(uint16_t); else FWBQ(uint32_t);
+#undef FWB2
     b->extra_launches += 1;
 #undef FWBQ
 #undef FWB

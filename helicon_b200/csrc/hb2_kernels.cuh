@@ -878,6 +878,101 @@ __global__ void __launch_bounds__(HB2_FWDB_THREADS, 1) k_fwd_band(BD B, int mode
   }
 }
 
+// Band path, second layout: a lane owns one (ray, slice quad) and walks the ray's samples inside the band -- no
+// cross-lane reduction, one 128-bit store per (ray, quad) partial.  The map entries of a ray arrive 8 at a time
+// (one aligned 128-bit load per lane and 8 samples; all samples of the ray that lie in the band are contiguous, so
+// "rank inside the band" is the only test).  The band sits in shared memory with one spare record after every 32
+// voxels (HB2_FWDB2_PAD), so that adjacent rays -- one voxel row apart at shallow view angles -- fall into different
+// bank groups.
+#define HB2_FWDB2_THREADS 512
+#define HB2_FWDB2_PAD 1u   // spare records after every 32 voxels (measured: 1 -> 563 us, quad-major lanes + common sample
+                          // origin with 1 / 3 -> 807 / 773 us per 32 candidate-passes; profiles/r1_summary.md)
+template <int NQ>
+__global__ void __launch_bounds__(HB2_FWDB2_THREADS, 1) k_fwd_band2(BD B, int mode) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ unsigned long long bar;
+  __shared__ int s_pref[HB2_FWDB_MAXV + 1];
+  __shared__ unsigned short s_jlo[HB2_FWDB_MAXV], s_cnt[HB2_FWDB_MAXV];
+  __shared__ int s_ang[HB2_FWDB_MAXV];
+  const int c = blockIdx.y, b = blockIdx.x;
+  const LsmrState& S = B.st[c];
+  const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  if (!act) return;
+  constexpr int L3P = 4 * NQ;
+  constexpr int RPW = 32 / NQ;                       // rays per warp item
+  constexpr unsigned REC = L3P * (unsigned)sizeof(float);
+  const int D2 = B.D2, NB = B.nband;
+  const unsigned bb = (unsigned)B.band_begin[b], bn = (unsigned)B.band_begin[b + 1] - bb;
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
+  const unsigned char* __restrict__ vsrc =
+      reinterpret_cast<const unsigned char*>((mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad + (size_t)bb * L3P);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  for (int e = threadIdx.x; e < nv; e += HB2_FWDB2_THREADS) {
+    const int a = B.view_angle[vb + e];
+    const ushort2 r = B.band_rng[(size_t)a * NB + b];
+    s_ang[e] = a; s_jlo[e] = r.x; s_cnt[e] = (unsigned short)(r.y - r.x); s_pref[e + 1] = ((int)r.y - (int)r.x + RPW - 1) / RPW;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // warp 0: TMA bulk loads, 32 voxel records per copy with one spare record after each group
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, bn * REC);
+    __syncwarp();
+    const unsigned ngrp = (bn + 31u) / 32u;
+    for (unsigned g = threadIdx.x; g < ngrp; g += 32u)
+      bulk_g2s(dsm + (size_t)g * (32u + HB2_FWDB2_PAD) * REC, vsrc + (size_t)g * 32u * REC, min(32u, bn - g * 32u) * REC, &bar);
+    if (threadIdx.x == 0) {
+      s_pref[0] = 0;
+      for (int e = 0; e < nv; ++e) s_pref[e + 1] += s_pref[e];
+    }
+  }
+  __syncthreads();
+  const int total_items = s_pref[nv];
+  mbar_wait(&bar, 0u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rl = lane / NQ, q = lane - rl * NQ;
+  const bool lane_on = rl < RPW;
+  float* __restrict__ part = B.fwd_part + B.cand_poff[c];
+  const unsigned tile_s = smem_u32(dsm) + 16u * (unsigned)q;
+  const uint16_t* __restrict__ fmap = (const uint16_t*)B.fmap;
+  int vcur = 0;
+  for (int it = warp; it < total_items; it += HB2_FWDB2_THREADS / 32) {
+    while (it >= s_pref[vcur + 1]) ++vcur;
+    const int a = s_ang[vcur];
+    const int j = (int)s_jlo[vcur] + RPW * (it - s_pref[vcur]) + rl;
+    const bool ray_on = lane_on && j < (int)s_jlo[vcur] + (int)s_cnt[vcur];
+    ushort2 sg = make_ushort2(0, 0);
+    if (ray_on) sg = __ldg(B.band_seg + ((size_t)a * NB + b) * D2 + j);
+    const int lo = sg.x, hi = sg.y;
+    const int ib = lo & ~7;
+    const int nblk = hi > lo ? (hi - ib + 7) >> 3 : 0;
+    const int tmax = __reduce_max_sync(0xffffffffu, nblk);
+    const uint4* __restrict__ fp = reinterpret_cast<const uint4*>(fmap + ((size_t)a * D2 + (ray_on ? j : 0)) * D2 + ib);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 nxt = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    if (nblk > 0) nxt = __ldg(fp);
+    for (int t = 0; t < tmax; ++t) {
+      const uint4 pk = nxt;
+      nxt = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (t + 1 < nblk) nxt = __ldg(fp + t + 1);
+      const unsigned wds[4] = {pk.x, pk.y, pk.z, pk.w};
+      float4 tv[8];
+      bool ok[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const unsigned id = (e & 1) ? (wds[e >> 1] >> 16) : (wds[e >> 1] & 0xFFFFu);
+        const unsigned rel = id - bb;
+        ok[e] = rel < bn;
+        tv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[e]) tv[e] = lds128(tile_s + (rel + HB2_FWDB2_PAD * (rel >> 5)) * REC);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (ok[e]) { acc.x += tv[e].x; acc.y += tv[e].y; acc.z += tv[e].z; acc.w += tv[e].w; }
+    }
+    if (ray_on) *reinterpret_cast<float4*>(part + (((size_t)vcur * NB + b) * D2 + j) * L3P + 4 * q) = acc;
+  }
+}
+
 // sum of a ray's partials over the bands it crosses (band order) + the row epilogue of k_fwd_data.
 // One CTA per (view of the candidate, candidate).
 template <int NQ>

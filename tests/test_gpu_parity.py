@@ -321,7 +321,7 @@ def test_bounded_solve_within_reference_reproducibility_band(solver, case):
     assert min(nits) - 1 <= r["trf_nit"] <= max(nits) + 1
 
 
-@pytest.mark.parametrize("env", [dict(HB2_FWD_BAND="1"), dict(HB2_NO_ADJ_TILE="1")])
+@pytest.mark.parametrize("env", [dict(HB2_FWD_BAND="1"), dict(HB2_FWD_BAND="2"), dict(HB2_NO_ADJ_TILE="1")])
 def test_alternative_kernel_paths_agree_with_default(env, monkeypatch):
     """The opt-in forward band path (TMA-staged voxel bands + partial ray sums) and the (voxel, quad) adjoint
     fallback are checked against the default kernels on the same batch: operator applies to float32 round-off,
