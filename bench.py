@@ -202,6 +202,7 @@ def main():
                     help="positive_constraint passed to the solver (0 = unbounded LSMR path; -1 = reference default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-positive-rule", action="store_true", help="skip the secondary positive_constraint=-1 measurement")
+    ap.add_argument("--no-trilinear", action="store_true", help="skip the secondary interpolation='linear' measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
     ap.add_argument("--e2e-batches", type=int, default=3, help="batches per search_grid() call of the e2e measurement")
     ap.add_argument("--cpu-iters", type=int, default=60)
@@ -396,6 +397,19 @@ def main():
                        bounded_fraction=float(np.mean((outp["flags"][np.isfinite(outp["scores"])] & 4) != 0)),
                        note="search_grid(positive_constraint=-1), host image in -> host scores out; one un-warmed call")
 
+    # ---- secondary: trilinear interpolation (the app's default mode) through the same call: explicit GPU-built rows,
+    # one candidate at a time; a few candidates on rank 0 only, un-warmed -------------------
+    trilinear = None
+    if rank == 0 and not args.no_trilinear:
+        t0 = time.perf_counter()
+        outl = search_grid(np.array(img, copy=True), APIX, TWISTS[[398, 402]], RISES[[24, 26]], positive_constraint=0,
+                           device=local_rank, stream=stream, interpolation="linear")
+        dtl = time.perf_counter() - t0
+        trilinear = dict(value=outl["n_candidates"] / dtl, unit="candidates/s", candidates=int(outl["n_candidates"]),
+                         n_gpus=1, mean_lsmr_iterations=float(outl["itn"].mean()), best_score=float(np.nanmax(outl["scores"])),
+                         note="search_grid(interpolation='linear', positive_constraint=0) on one GPU: row build on the GPU "
+                              "+ LSMR on the explicit CSR (345 M entries per candidate at this shape), one un-warmed call")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -452,6 +466,8 @@ def main():
     )
     if posrule is not None:
         line["e2e_positive_rule_default"] = posrule
+    if trilinear is not None:
+        line["e2e_trilinear"] = trilinear
     if not args.no_cpu_baseline:
         sel = [tasks[(args.warmup * args.batch + 17) % len(tasks)]]
         itn_ref = int(round(itn_sum / max(1, ncand)))

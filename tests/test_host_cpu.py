@@ -183,3 +183,20 @@ def test_exact_map_requests_reproduce_the_reference_voxel_of_every_sample(N, s, 
         assert np.array_equal(np.rint(X), Xr[k]) and np.array_equal(np.rint(Y), Yr[k]), k
         varies |= not (np.array_equal(Xr[k], Xr[0]) and np.array_equal(Yr[k], Yr[0]))
     assert varies  # these are tie angles: the rounding really depends on the column
+
+
+def test_mrc_writer_reader_round_trip(tmp_path):
+    """denovo3DBatch.write_mrc <-> pipeline._read_mrc (the reference uses the mrcfile package for both)."""
+    from helicon_b200 import pipeline
+    from helicon_b200.denovo3DBatch import _axis, write_mrc
+
+    vol = np.random.default_rng(0).random((3, 5, 7)).astype(np.float32)
+    path = str(tmp_path / "v.mrc")
+    write_mrc(path, vol, 1.3)
+    data, apix = pipeline.get_images_from_file(path)
+    assert np.array_equal(data, vol) and apix == 1.3
+    assert np.array_equal(pipeline.read_image_2d(path, 1), vol[1])
+    write_mrc(path, vol[0], 2.0)
+    data, apix = pipeline.get_images_from_file(path)
+    assert data.shape == (5, 7) and apix == 2.0
+    assert np.allclose(_axis("-3:-1:5", "twist"), np.linspace(-3, -1, 5)) and list(_axis("4.7,4.8", "rise")) == [4.7, 4.8]

@@ -119,3 +119,32 @@ def test_tie_geometry_is_solved_exactly():
                                    return_info=True)
     fl = int(info["res"]["flags"])
     assert fl & _lib.HB2_FLAG_TIE_Z_EXACT and not fl & _lib.HB2_FLAG_TIE_Z
+
+
+@pytest.mark.gpu
+def test_denovo3dbatch_cli_end_to_end(tmp_path):
+    """The command line driver: MRC in -> grid search on the GPU -> score table, top-K list, best map (MRC out); same
+    scores as a direct search_grid() call on the same image."""
+    import json
+
+    from helicon_b200 import denovo3DBatch as cli
+    from helicon_b200 import pipeline
+    from helicon_b200.grid import search_grid
+
+    d = load("grid_64")
+    img, apix = d["image"], float(d["apix"])
+    path = str(tmp_path / "img.mrc")
+    cli.write_mrc(path, img, apix)
+    out = str(tmp_path / "run")
+    rc = cli.main([path, "--twist=-2.13,-1.37,-0.67", "--rise", "4.31:5.13:3", "--positive-constraint", "0", "--output", out,
+                   "--save-map", "--top-k", "5"])
+    assert rc == 0
+    s = np.load(out + "_img0_scores.npz")
+    ref = search_grid(img, round(apix, 4), np.array([-2.13, -1.37, -0.67]), np.linspace(4.31, 5.13, 3), positive_constraint=0)
+    assert s["scores"].shape == ref["scores"].shape == (1, 3, 3) and np.array_equal(s["scores"], ref["scores"])
+    top = json.load(open(out + "_top.json"))[0]["top"]
+    bi = np.unravel_index(np.argmax(ref["scores"]), ref["scores"].shape)
+    assert len(top) == 5 and abs(top[0]["twist"] - [-2.13, -1.37, -0.67][bi[1]]) < 1e-9
+    vol, apix_out = pipeline.get_images_from_file(out + "_img0_best_map.mrc")
+    assert vol.ndim == 3 and vol.shape[1:] == (img.shape[0], img.shape[0]) and np.isfinite(vol).all()
+    assert apix_out == round(apix, 4) and float(vol.max()) > 0
