@@ -148,7 +148,14 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_csr(BD B, TD Tt, const T* __r
   for (int r = sub * (HB2_BLOCK / 32) + warp; r < nrow; r += ppv * (HB2_BLOCK / 32)) {
     const int e0 = B.exp_ptr[vo + r], e1 = B.exp_ptr[vo + r + 1];
     T acc = (T)0;
-    for (int e = e0 + lane; e < e1; e += 32) acc += (T)B.exp_w[e] * vsrc[B.exp_col[e]];
+    int e = e0 + lane;
+    for (; e + 96 < e1; e += 128) {  // four independent (column, weight, gather) chains in flight per lane
+      const int c0 = B.exp_col[e], c1 = B.exp_col[e + 32], c2 = B.exp_col[e + 64], c3 = B.exp_col[e + 96];
+      const float w0 = B.exp_w[e], w1 = B.exp_w[e + 32], w2 = B.exp_w[e + 64], w3 = B.exp_w[e + 96];
+      const T v0 = vsrc[c0], v1 = vsrc[c1], v2 = vsrc[c2], v3 = vsrc[c3];
+      acc += (T)w0 * v0; acc += (T)w1 * v1; acc += (T)w2 * v2; acc += (T)w3 * v3;
+    }
+    for (; e < e1; e += 32) acc += (T)B.exp_w[e] * vsrc[B.exp_col[e]];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
