@@ -22,7 +22,10 @@
 #define HB2_ADJT_MAXV 256
 // T = float : the LSMR adjoint (modes of k_adj: LSMR / INIT / PLAIN) on B.u -> B.v / B.xs
 // T = double: the bounded branch's plain adjoint dst <- A^T rows (gate semantics of k_adj64)
-template <int NQT, int KT, typename T, bool TRF>
+// CHUNKED (more than 16 slices): grid.z = chunks of 4*NQT = 16 slices; a CTA handles one chunk of its tile's voxels.  The
+// rows of a view are then no longer one contiguous window: every ray row contributes one 64-byte piece (its slices of
+// the chunk), copied by its own bulk copy -- the producer warp spreads the rows of a stage over its 32 lanes.
+template <int NQT, int KT, typename T, bool TRF, bool CHUNKED = false>
 __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ dst_all, int mode) {
   extern __shared__ __align__(128) unsigned char dsm[];
   const int c = blockIdx.y, tile = blockIdx.x;
@@ -33,12 +36,15 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, cons
   __shared__ float s_w[HB2_ADJT_MAXV];  // multiplicity of the view (Halton duplicates are skipped, their first copy counts twice)
   const LsmrState& S = B.st[c];
   const bool act = tie_active<TRF>(B, Tt, c, mode, true);
-  const int pi = c * B.part_v_per_cand + blockIdx.x;
+  const int pi = c * B.part_v_per_cand + (CHUNKED ? (int)blockIdx.z * B.ntile : 0) + blockIdx.x;
   if (!act) {
     if (!TRF && threadIdx.x == 0 && mode != MODE_PLAIN) B.part_v[pi] = 0.f;
     return;
   }
-  constexpr int L3P = 4 * NQT;
+  constexpr int L3P = 4 * NQT;  // slices handled by this CTA (= all of them unless CHUNKED)
+  const int zc0 = CHUNKED ? (int)blockIdx.z * L3P : 0;                 // first slice of the chunk
+  const int cw = CHUNKED ? min(L3P, B.L3P - zc0) : L3P;                // slices of the chunk (multiple of 4)
+  const int vstride = CHUNKED ? B.L3P : L3P;                           // voxel / ray-row stride in global memory
   const int ndisk_t = B.tile_begin[tile + 1] - B.tile_begin[tile];
   const int p = B.tile_begin[tile] + threadIdx.x;
   const bool producer = threadIdx.x >= HB2_BLOCK;
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, cons
       const int v = st * HB2_ADJT_SV + w;
       const bool has = w < HB2_ADJT_SV && v < nv && s_nr[min(v, nv - 1)] != 0xFFFFu;
       const unsigned nr = has ? s_nr[v] : 0;
-      unsigned tot = has ? KT * HB2_BLOCK * (unsigned)sizeof(uint16_t) + nr * L3P * (unsigned)sizeof(T) : 0u;
+      unsigned tot = has ? KT * HB2_BLOCK * (unsigned)sizeof(uint16_t) + nr * (unsigned)cw * (unsigned)sizeof(T) : 0u;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       if (w == 0) mbar_expect_tx(&full_bar[buf], tot);
@@ -94,9 +100,21 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, cons
         for (int k = 0; k < KT; ++k)
           bulk_g2s(s_map + ((size_t)(buf * HB2_ADJT_SV + w) * KT + k) * HB2_BLOCK, amt + arow + (size_t)k * B.apitch,
                    HB2_BLOCK * (unsigned)sizeof(uint16_t), &full_bar[buf]);
-        if (nr)
+        if (!CHUNKED && nr)
           bulk_g2s(s_u + (size_t)(buf * HB2_ADJT_SV + w) * ustride, ucand + ((size_t)v * rpv + (size_t)s_jlo[v] * L3P),
                    nr * L3P * (unsigned)sizeof(T), &full_bar[buf]);
+      }
+      if (CHUNKED) {  // one piece per ray row: rows of the stage's views spread over the lanes
+#pragma unroll
+        for (int ws = 0; ws < HB2_ADJT_SV; ++ws) {
+          const int vs = st * HB2_ADJT_SV + ws;
+          if (vs >= nv || s_nr[vs] == 0xFFFFu) continue;
+          const unsigned nrs = s_nr[vs];
+          const T* src = ucand + ((size_t)vs * rpv + (size_t)s_jlo[vs] * vstride + zc0);
+          T* dstw = s_u + (size_t)(buf * HB2_ADJT_SV + ws) * ustride;
+          for (unsigned r = (unsigned)w; r < nrs; r += 32u)
+            bulk_g2s(dstw + (size_t)r * L3P, src + (size_t)r * vstride, (unsigned)cw * (unsigned)sizeof(T), &full_bar[buf]);
+        }
       }
     }
   } else {
@@ -142,7 +160,7 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, cons
   }
   float ss = 0.f;
   if (live && !producer) {
-    const int g0 = p * L3P;
+    const int g0 = p * vstride + zc0;
     const T* __restrict__ us = rows + B.cand_uoff[c] + B.cand_mdata[c];
     const int* __restrict__ ell = B.ell + (size_t)c * HB2_ELL_W * B.npad + g0;
     T* vdst = (TRF ? dst_all : (T*)(mode == MODE_PLAIN ? (void*)B.xs : (void*)B.v)) + (size_t)c * B.npad + g0;
@@ -150,10 +168,12 @@ __global__ void __launch_bounds__(HB2_ADJT_THREADS) k_adj_tile(BD B, TD Tt, cons
     if (vtie && B.cand_tie_count[c] > 0) {  // rows of the tie views (k_adj_tie)
       const T* vt = vtie + (size_t)c * B.npad + g0;
 #pragma unroll
-      for (int z = 0; z < 4 * NQT; ++z) acc[z] += vt[z];
+      for (int z = 0; z < 4 * NQT; ++z)
+        if (z < cw) acc[z] += vt[z];
     }
 #pragma unroll
     for (int q4 = 0; q4 < NQT; ++q4) {
+      if (4 * q4 >= cw) break;  // partial last chunk
       int ev[HB2_ELL_W][4];
 #pragma unroll
       for (int w = 0; w < HB2_ELL_W; ++w) {

@@ -159,6 +159,7 @@ struct hb2_batch {
   BD B{};
   bool idx16 = true;
   size_t adj_tile_smem = 0;
+  int adj_chunks = 1;  // adj_tile == 2: chunks of 16 slices
   size_t fwd_band_smem = 0;
   // tie views (hb2_batch_set_ties)
   int n_tie = 0, tie_TS = 0;
@@ -1010,7 +1011,17 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     const char* no_tile = getenv("HB2_NO_ADJ_TILE");
     B.adj_tile = (B.adj_fast && B.L3P <= 16 && max_views <= HB2_ADJT_MAXV && b->adj_tile_smem <= 96 * 1024 &&
                   !(no_tile && atoi(no_tile))) ? 1 : 0;
-    B.part_v_per_cand = B.adj_tile ? B.ntile : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
+    b->adj_chunks = 1;
+    // More than 16 slices: the tile adjoint in chunks of 16 slices (grid.z), one 64-byte piece per ray row.  Measured
+    // (profiles/r1_summary.md section 7) 35 % SLOWER than the (voxel, quad) fallback at L3 = 44...104 -- ~40 small bulk
+    // copies per view and chunk instead of one -- so it is opt-in (HB2_ADJ_CHUNKED=1).
+    static const bool use_chunked = getenv("HB2_ADJ_CHUNKED") && atoi(getenv("HB2_ADJ_CHUNKED"));
+    if (use_chunked && !B.adj_tile && B.adj_fast && B.L3P > 16 && max_views <= HB2_ADJT_MAXV) {
+      const size_t sm = (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.K * HB2_BLOCK * sizeof(uint16_t) +
+                        (size_t)HB2_ADJT_NS * HB2_ADJT_SV * B.rmax * 16 * sizeof(float);
+      if (sm <= 160 * 1024) { B.adj_tile = 2; b->adj_tile_smem = sm; b->adj_chunks = (B.L3P + 15) / 16; }
+    }
+    B.part_v_per_cand = B.adj_tile ? B.ntile * b->adj_chunks : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
   }
   B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
   // ---- forward band path: bands of tile-rows that fit shared memory, ray segments per (angle, band) -------------
@@ -1274,8 +1285,8 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (b->n_tie_views > 0) {  // exact rows of the tie views (the projector kernels below skip them)
     const float* src = mode == MODE_LSMR ? B.v : B.xs;
     if (b->explicit_rows) k_fwd_csr<float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
-    else if (b->idx16) k_fwd_tie<uint16_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
-    else k_fwd_tie<uint32_t, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    else if (b->idx16) k_fwd_tie<uint16_t, float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    else k_fwd_tie<uint32_t, float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     b->extra_launches += 1;
   }
   if (B.fwd_band) {
@@ -1322,6 +1333,18 @@ static void launch_adj(hb2_batch* b, int mode) {
     if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     else k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     b->extra_launches += 1;
+  }
+  if (B.adj_tile == 2) {
+    const size_t sm = b->adj_tile_smem;
+    const dim3 gc(B.ntile, B.nc, b->adj_chunks);
+#define ADJTC(K)                                                                                                        \
+  do {                                                                                                                  \
+    cudaFuncSetAttribute(k_adj_tile<4, K, float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+    k_adj_tile<4, K, float, false, true><<<gc, HB2_ADJT_THREADS, sm, st>>>(B, TD{}, B.u, nullptr, mode);                \
+  } while (0)
+    if (B.K == 1) ADJTC(1); else ADJTC(2);
+#undef ADJTC
+    return;
   }
   if (B.adj_tile) {
     const size_t sm = b->adj_tile_smem;
@@ -1464,8 +1487,8 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     launches += 2;
     if (b->n_tie_views > 0) {
       if (b->explicit_rows) k_fwd_csr<double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
-      else if (b->idx16) k_fwd_tie<uint16_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
-      else k_fwd_tie<uint32_t, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      else if (b->idx16) k_fwd_tie<uint16_t, double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      else k_fwd_tie<uint32_t, double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       ++launches;
     }
   };
@@ -1475,7 +1498,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
       else k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;
     }
-    if (B.adj_tile && sm64 <= 200 * 1024) {  // float64 instantiation of the TMA-staged tile adjoint
+    if (B.adj_tile == 1 && sm64 <= 200 * 1024) {  // float64 instantiation of the TMA-staged tile adjoint
       const dim3 gt(B.ntile, nc);
 #define ADJT64(Q, K)                                                                                                 \
   do {                                                                                                               \

@@ -23,7 +23,10 @@ __device__ __forceinline__ bool tie_active(const BD& B, const TD& T, int c, int 
                              : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
 }
 
-// One CTA per tie view slot (ZMC column slots of one tie view), one warp per ray, lanes over the depth samples.
+// Grid (tie view slots, ray groups): a CTA takes the rays j = blockIdx.y, blockIdx.y + gridDim.y, ... of one tie view slot
+// (ZMC column slots of one tie view), one warp per ray, lanes over the depth samples; gridDim.y = the view's partial-sum
+// slots (BD::fwd_ppv).  (One CTA per view slot cost 2.2 ms per pass at 512 x 512 -- a handful of CTAs walking 512 x 512
+// samples each -- and dominated small batches, profiles/r1_summary.md section 7.)
 //   f32 (TRF = false): src = v or xs, rows = u, LSMR / PLAIN / SCORE epilogue of k_fwd_data incl. the view's partials;
 //   f64 (TRF = true) : rows <- A w plain.
 template <typename IdxT, typename T, bool TRF>
@@ -32,12 +35,12 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
   const int c = B.view_cand[view];
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ int s_colk[HB2_TIE_MAXZMC], s_zlo[HB2_TIE_MAXZMC];
-  const int ppv = B.fwd_ppv;
+  const int ppv = B.fwd_ppv, sub = blockIdx.y;
   const bool act = tie_active<TRF>(B, Tt, c, mode, false);
   if (!act) {
-    if (!TRF && threadIdx.x < ppv) {
-      if (mode == MODE_LSMR) B.part_u[view * ppv + threadIdx.x] = 0.f;
-      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + threadIdx.x)] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 1] = 0.f; B.part_s[3 * (view * ppv + threadIdx.x) + 2] = 0.f; }
+    if (!TRF && threadIdx.x == 0) {
+      if (mode == MODE_LSMR) B.part_u[view * ppv + sub] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + sub)] = 0.f; B.part_s[3 * (view * ppv + sub) + 1] = 0.f; B.part_s[3 * (view * ppv + sub) + 2] = 0.f; }
     }
     return;
   }
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   const uint8_t* __restrict__ pm = cand_mask(B, c);
-  for (int j = warp; j < D2; j += HB2_BLOCK / 32) {
+  for (int j = sub * (HB2_BLOCK / 32) + warp; j < D2; j += ppv * (HB2_BLOCK / 32)) {
     T acc[HB2_TIE_MAXZMC];
 #pragma unroll
     for (int t = 0; t < HB2_TIE_MAXZMC; ++t) acc[t] = (T)0;
@@ -105,14 +108,13 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
   if (!TRF) {
     if (mode == MODE_LSMR) {
       const float tot = block_sum(ss, red);
-      if (threadIdx.x < ppv) B.part_u[view * ppv + threadIdx.x] = threadIdx.x == 0 ? tot : 0.f;
+      if (threadIdx.x == 0) B.part_u[view * ppv + sub] = tot;
     } else if (mode == MODE_SCORE) {
       const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
-      if (threadIdx.x < ppv) {
-        const bool f = threadIdx.x == 0;
-        B.part_s[3 * (view * ppv + threadIdx.x)] = f ? t0 : 0.f;
-        B.part_s[3 * (view * ppv + threadIdx.x) + 1] = f ? t1 : 0.f;
-        B.part_s[3 * (view * ppv + threadIdx.x) + 2] = f ? t2 : 0.f;
+      if (threadIdx.x == 0) {
+        B.part_s[3 * (view * ppv + sub)] = t0;
+        B.part_s[3 * (view * ppv + sub) + 1] = t1;
+        B.part_s[3 * (view * ppv + sub) + 2] = t2;
       }
     }
   }

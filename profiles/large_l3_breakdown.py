@@ -18,6 +18,7 @@ for name, N, tw, rises in (("cfg5 384 rise 21", 384, -170.0, [21.0, 21.5]), ("cf
     n3 = g["L3"] * prob.ndisk
     target = min(MAX_EQUATIONS, int(max(g["D2"] * g["L2"], n3) * g["sym_oversample"]))
     batch = Batch(prob, g["L3"], [CandidateSpec(t.twist, t.rise / g["apix3d"], 1, target, target, False) for t in tl])
+    batch.solve(fixed_iters=2, check_every=2)  # warm-up (lazy kernel loading would land in the first timed launch)
     res = batch.solve(fixed_iters=10, check_every=10, profile=1)
     tm = batch.timing()
     nc = len(tl)
