@@ -320,7 +320,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     launches, itn_sum, ncand = 0, 0, 0
-    fwd_ms, fwd_launches, fwd_bytes = 0.0, 0, 0.0
+    fwd_ms, fwd_launches, fwd_bytes, iter_bytes = 0.0, 0, 0.0, 0.0
     adj_ms, upd_ms, sym_ms, scal_ms, lsmr_ms = 0.0, 0.0, 0.0, 0.0, 0.0
     for res, tm, md_mean, top in run_steps(range(args.warmup, args.warmup + args.steps), profile=True):
         launches += tm["launches"]
@@ -331,6 +331,8 @@ def main():
         # algorithmic bytes of the forward projector: read v (4n) + read/write u (8 m_data) per
         # candidate-iteration, summed over the iterations each candidate was active
         fwd_bytes += float(res["itn"].sum()) * (4.0 * n3 + 8.0 * md_mean)
+        # whole LSMR iteration: B_iter = 56 n + 12 m bytes with m = data + symmetry rows
+        iter_bytes += float(np.sum(res["itn"].astype(np.float64) * (56.0 * n3 + 12.0 * (md_mean + res["n_sym_rows"]))))
     torch.cuda.synchronize()  # the batches run on the library's own streams
     e1.record(stream)
     barrier()
@@ -461,6 +463,11 @@ def main():
                       avg_launch_ms=fwd_ms / max(1, fwd_launches),
                       note="achieved = algorithmic bytes (4n + 8 m_data per active candidate-iteration) / summed "
                            "CUDA-event time of the kernel's launches inside the timed region"),
+        roofline_iteration=dict(
+            bound="hbm", achieved=iter_bytes / (lsmr_ms / 1e3) / 1e9 if lsmr_ms > 0 else 0.0, peak=peak, unit="GB/s",
+            frac=(iter_bytes / (lsmr_ms / 1e3) / 1e9 / peak) if lsmr_ms > 0 and peak else None,
+            note="all kernels of the LSMR phase together: algorithmic bytes B_iter = 56 n + 12 m per active "
+                 "candidate-iteration (SURVEY 8d) / device time of the LSMR phase"),
         kernel_share=dict(lsmr_phase_ms=lsmr_ms, fwd_data_ms=fwd_ms, fwd_sym_ms=sym_ms, adjoint_ms=adj_ms,
                           update_ms=upd_ms, scalar_ms=scal_ms),
     )
