@@ -148,3 +148,29 @@ def test_denovo3dbatch_cli_end_to_end(tmp_path):
     vol, apix_out = pipeline.get_images_from_file(out + "_img0_best_map.mrc")
     assert vol.ndim == 3 and vol.shape[1:] == (img.shape[0], img.shape[0]) and np.isfinite(vol).all()
     assert apix_out == round(apix, 4) and float(vol.max()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["task_linear", "task_fsc2"])
+def test_process_one_task_trilinear_and_half_sets_vs_reference(name):
+    """The whole task wrapper with interpolation="linear" (the app's default mode; explicit GPU-built rows) and with
+    fsc_test=2 (three masked candidates): score, reconstruction(s) and display products vs the reference's outputs
+    (oracle/make_golden_task_more.py)."""
+    from helicon_b200 import pipeline
+
+    d = load(name)
+    linear, fsc = bool(int(d["interpolation"])), int(d["fsc_test"])
+    res = pipeline.process_one_task(**_kw(d, interpolation="linear" if linear else "nn", fsc_test=fsc))
+    score, rd, meta = res
+    xp, yp, zs, (rec3d, h1, h2), D2, D3, L2, L3 = rd
+    assert (D2, D3, L2, L3) == tuple(int(v) for v in d["geom"])
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    tol_s, tol_x = (2e-4, 3e-2) if linear else (1e-5, 5e-3)  # trilinear systems: the reference's own permutation band
+    print(f"{name}: score {float(score):.7f} vs {float(d['score']):.7f}; rel-L2 rec3d {rel(rec3d, d['rec3d']):.2e} "
+          f"x_proj {rel(xp, d['x_proj']):.2e}")
+    assert abs(float(score) - float(d["score"])) <= tol_s
+    assert rel(rec3d, d["rec3d"]) <= tol_x and rel(xp, d["x_proj"]) <= tol_x and rel(zs, d["z_sections"]) <= tol_x
+    if fsc:
+        assert rel(h1, d["half1"]) <= 5e-3 and rel(h2, d["half2"]) <= 5e-3
+    else:
+        assert h1 is None and h2 is None
