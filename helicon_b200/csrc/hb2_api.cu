@@ -907,6 +907,14 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKC(upload(b->pool, &B.tie_views, tie_views, st));
     CKC(upload(b->pool, (const int8_t**)&B.tie_zlo, b->h_tie_zlo, st));
     CKC(upload(b->pool, &B.tie_up, b->h_tie_up, st));
+    B.tie_upmask = nullptr;
+    if (!b->explicit_rows && b->n_tie > 0 && b->tie_TS % B.ZMC == 0 && B.ZMC <= 16) {
+      uint16_t* d_mask;
+      const long long nm = (long long)b->n_tie * (b->tie_TS / B.ZMC) * D2;
+      CKC(b->pool.alloc(&d_mask, (size_t)nm, false, st));
+      k_tie_pack<<<cdiv(nm, 256), 256, 0, st>>>(b->n_tie, b->tie_TS, B.ZMC, D2, B.tie_up, d_mask);
+      B.tie_upmask = d_mask;
+    }
     CKC(upload(b->pool, &B.tie_rowvalid, b->h_tie_rv, st));
   }
   CKC(upload(b->pool, &B.view_uoff, view_uoff, st));

@@ -78,6 +78,7 @@ struct BD {
   const int* view_tie_slot0;      // [nviews]
   const signed char* tie_zlo;     // [n_tie][TS]
   const unsigned char* tie_up;    // [n_tie][TS][D2]
+  const uint16_t* tie_upmask;     // [n_tie][TS/ZMC][D2]: bit t = tie_up of column slot g*ZMC + t (built at create)
   const unsigned char* tie_rowvalid;  // [n_tie][TS][D2]
   int tie_TS, n_tie_views;
   const int* tie_views;           // [n_tie_views] view slots that are tie views, grouped by candidate

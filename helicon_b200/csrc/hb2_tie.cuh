@@ -23,6 +23,17 @@ __device__ __forceinline__ bool tie_active(const BD& B, const TD& T, int c, int 
                              : (mode == MODE_INIT ? (S.beta > 0.f) : (B.only_cand < 0 || B.only_cand == c));
 }
 
+// bit t of upmask[(tv*G + g)*D2 + i] = up[(tv*TS + g*ZMC + t)*D2 + i]: one 16-bit load per sample instead of ZMC byte loads
+__global__ void k_tie_pack(int n_tie, int TS, int ZMC, int D2, const unsigned char* __restrict__ up, uint16_t* __restrict__ mask) {
+  const int G = TS / ZMC;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_tie * G * D2) return;
+  const int i = (int)(t % D2), g = (int)((t / D2) % G), tv = (int)(t / ((long long)D2 * G));
+  unsigned m = 0;
+  for (int q = 0; q < ZMC; ++q) m |= (unsigned)(up[((size_t)tv * TS + (size_t)g * ZMC + q) * D2 + i] & 1u) << q;
+  mask[t] = (uint16_t)m;
+}
+
 // Grid (tie view slots, ray groups): a CTA takes the rays j = blockIdx.y, blockIdx.y + gridDim.y, ... of one tie view slot
 // (ZMC column slots of one tie view), one warp per ray, lanes over the depth samples; gridDim.y = the view's partial-sum
 // slots (BD::fwd_ppv).  (One CTA per view slot cost 2.2 ms per pass at 512 x 512 -- a handful of CTAs walking 512 x 512
@@ -55,6 +66,15 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
   const T* __restrict__ vsrc = src + (size_t)c * B.npad;
   const unsigned char* __restrict__ up = B.tie_up + ((size_t)tv * B.tie_TS + s0) * D2;
   const unsigned char* __restrict__ rv = B.tie_rowvalid + ((size_t)tv * B.tie_TS + s0) * D2;
+  // fast path: used slots on consecutive slices starting at zb = -1 or 0 (CTA-uniform), packed masks available
+  int fast_zb = 99;
+  if (B.tie_upmask && s0 % ZMC == 0 && B.tie_TS % ZMC == 0) {
+    const int zb = s_zlo[0];
+    bool ok = zb == -1 || zb == 0;
+    for (int t = 0; t < ZMC && ok; ++t)
+      if (s_colk[t] >= 0 && s_zlo[t] != zb + t) ok = false;
+    if (ok) fast_zb = zb;
+  }
   T* urow = rows + B.view_uoff[view];
   const float* brow = B.b + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,6 +87,43 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
 #pragma unroll
     for (int t = 0; t < HB2_TIE_MAXZMC; ++t) acc[t] = (T)0;
     const IdxT* __restrict__ fj = fm + (size_t)j * D2;
+    if (fast_zb != 99) {
+      // consecutive column slots sit on consecutive slices (zlo[t] = zb + t, zb = -1 or 0): the voxel record comes in
+      // with 128-bit loads and slot t takes slice zb + t or zb + t + 1 by its bit of the packed mask
+      const uint16_t* __restrict__ um = B.tie_upmask + ((size_t)tv * (B.tie_TS / ZMC) + s0 / ZMC) * D2;
+      for (int i = lane; i < D2; i += 32) {
+        const IdxT id = fj[i];
+        if (id == Sent<IdxT>::v) continue;
+        const T* __restrict__ vb = vsrc + (size_t)id * L3P;
+        const unsigned m = um[i];
+        T rec[HB2_TIE_MAXZMC];
+#pragma unroll
+        for (int z4 = 0; z4 < HB2_TIE_MAXZMC; z4 += 4) {
+          if (z4 < L3P) {
+            if constexpr (sizeof(T) == 4) {
+              const float4 q4 = *reinterpret_cast<const float4*>(vb + z4);
+              rec[z4] = q4.x; rec[z4 + 1] = q4.y; rec[z4 + 2] = q4.z; rec[z4 + 3] = q4.w;
+            } else {
+              const double2 a2 = *reinterpret_cast<const double2*>(vb + z4), b2 = *reinterpret_cast<const double2*>(vb + z4 + 2);
+              rec[z4] = a2.x; rec[z4 + 1] = a2.y; rec[z4 + 2] = b2.x; rec[z4 + 3] = b2.y;
+            }
+          } else {
+            rec[z4] = rec[z4 + 1] = rec[z4 + 2] = rec[z4 + 3] = (T)0;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
+          if (t < ZMC && s_colk[t] >= 0) {
+            // slice index zb + t + bit, zb in {-1, 0}: static register picks
+            const bool hi = (m >> t) & 1u;
+            T lo_v, hi_v;
+            if (fast_zb == 0) { lo_v = t < L3 ? rec[t] : (T)0; hi_v = (t + 1 < L3 && t + 1 < HB2_TIE_MAXZMC) ? rec[(t + 1) % HB2_TIE_MAXZMC] : (T)0; }
+            else { lo_v = (t >= 1 && t - 1 < L3) ? rec[(t + HB2_TIE_MAXZMC - 1) % HB2_TIE_MAXZMC] : (T)0; hi_v = t < L3 ? rec[t] : (T)0; }
+            acc[t] += hi ? hi_v : lo_v;
+          }
+        }
+      }
+    } else
     for (int i = lane; i < D2; i += 32) {
       const IdxT id = fj[i];
       if (id == Sent<IdxT>::v) continue;
@@ -146,12 +203,41 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_tie(BD B, TD Tt, const T* __r
     const signed char* __restrict__ zl = B.tie_zlo + (size_t)tv * B.tie_TS + s0;
     const unsigned char* __restrict__ up = B.tie_up + ((size_t)tv * B.tie_TS + s0) * D2;
     const T* __restrict__ ub = rows + B.view_uoff[view];
+    // fast path (see k_fwd_tie): used slots on consecutive slices from zb = -1 or 0, packed masks
+    int fast_zb = 99;
+    if (B.tie_upmask && s0 % ZMC == 0 && B.tie_TS % ZMC == 0) {
+      const int zb = zl[0];
+      bool ok = zb == -1 || zb == 0;
+      for (int t = 0; t < ZMC && ok; ++t)
+        if (ck[t] >= 0 && zl[t] != zb + t) ok = false;
+      if (ok) fast_zb = zb;
+    }
+    const uint16_t* __restrict__ um = B.tie_upmask ? B.tie_upmask + ((size_t)tv * (B.tie_TS / ZMC) + s0 / ZMC) * D2 : nullptr;
     for (int k = 0; k < K; ++k) {
       const size_t mi = ((size_t)a * K + k) * B.apitch + slot;
       const unsigned j = B.amap[mi];
       if (j == 0xFFFFu) continue;
       const unsigned i = B.amap_i[mi];
       const T* __restrict__ uj = ub + (size_t)j * ZMP;
+      if (fast_zb != 99) {
+        const unsigned m = um[i];
+#pragma unroll
+        for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
+          if (t < ZMC && ck[t] >= 0) {
+            const T val = TRF ? uj[t] : (T)fmaf((float)uj[t], (float)ib, 0.f);
+            const bool hi = (m >> t) & 1u;
+            // target slice zb + t + bit: static accumulator picks, slices outside [0, L3) are dropped
+            if (fast_zb == 0) {
+              if (!hi) { if (t < L3) acc[t] += val; }
+              else if (t + 1 < L3 && t + 1 < HB2_TIE_MAXZMC) acc[(t + 1) % HB2_TIE_MAXZMC] += val;
+            } else {
+              if (hi) { if (t < L3) acc[t] += val; }
+              else if (t >= 1 && t - 1 < L3) acc[(t + HB2_TIE_MAXZMC - 1) % HB2_TIE_MAXZMC] += val;
+            }
+          }
+        }
+        continue;
+      }
       for (int t = 0; t < ZMC; ++t) {
         if (ck[t] < 0) continue;
         const int z = (int)zl[t] + (int)up[(size_t)t * D2 + i];
