@@ -100,7 +100,7 @@ EXPORTS = [
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
     "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize", "hb2_batch_set_ties",
     "hb2_batch_set_pixel_masks", "hb2_batch_add_exact_maps", "hb2_batch_explicit_rows", "hb2_batch_explicit_export", "hb2_batch_explicit_sym_rows",
-    "hb2_batch_explicit_sym_export",
+    "hb2_batch_explicit_sym_export", "hb2_batch_explicit_pixel_mask",
 ]
 
 _lib = None
@@ -138,6 +138,7 @@ def load():
     lib.hb2_batch_explicit_rows.argtypes = [vp, P(ExplicitGeometry), i32, vp, vp, vp, vp, i64, P(i32), vp, P(i64), P(i64)]
     lib.hb2_batch_explicit_sym_rows.argtypes = [vp, i32, vp, i64, P(i64)]
     lib.hb2_batch_explicit_sym_export.argtypes = [vp, vp, vp]
+    lib.hb2_batch_explicit_pixel_mask.argtypes = [vp, vp]
     lib.hb2_batch_explicit_export.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.hb2_batch_set_pixel_masks.argtypes = [vp, i32, vp, vp]
     lib.hb2_batch_create.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp]

@@ -176,6 +176,7 @@ struct hb2_batch {
   int *d_exp_ptr = nullptr, *d_exp_col = nullptr, *d_exp_erow = nullptr;
   float* d_exp_w = nullptr;
   bool exp_finished = false;
+  std::vector<uint8_t> h_exp_pixmask;  // half-set mask over pixel ids k*D2 + j (empty: all rows kept)
   // trilinear symmetry rows (hb2_batch_explicit_sym_rows): 16 entries per row
   int ls_m = 0;
   int* d_ls_col = nullptr;
@@ -492,6 +493,16 @@ extern "C" int hb2_batch_add_exact_maps(hb2_batch* b, int32_t nE, const double* 
   return HB2_OK;
 }
 
+// Half-set mask for explicit rows (fsc_test): rows whose pixel id is not set are dropped AFTER the early stop
+// (the reference splits the finished matrix, SLR:441-444).  Call before hb2_batch_explicit_rows.
+extern "C" int hb2_batch_explicit_pixel_mask(hb2_batch* b, const uint8_t* mask) {
+  if (!b) return fail(HB2_ERR_ARG, "null argument");
+  if (b->explicit_rows) return fail(HB2_ERR_STATE, "hb2_batch_explicit_pixel_mask must precede hb2_batch_explicit_rows");
+  if (mask) b->h_exp_pixmask.assign(mask, mask + (size_t)b->B.L2 * b->B.D2);
+  else b->h_exp_pixmask.clear();
+  return HB2_OK;
+}
+
 // Explicit data rows (general orientation and/or trilinear interpolation): built on the GPU, see hb2_explicit.cuh.
 extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry* eg, int32_t ncopies, const double* copy_mats,
                                        const double* zshift, const double* xtab, const double* ztab,
@@ -546,8 +557,19 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
     if (min_projection_lines > 0 && bound[q + 1] > min_projection_lines) { used = q + 1; break; }
   }
   if (rows_per_copy) for (int q = used; q < ncopies; ++q) rows_per_copy[q] = bound[q + 1] - bound[q];
-  const int m = bound[used];
   const long long NU = (long long)used * R;
+  int m = bound[used];
+  if (!b->h_exp_pixmask.empty()) {  // half set: drop the other half's rows, keep the order
+    uint8_t* d_pm;
+    CK(b->pool.alloc(&d_pm, (size_t)R, false, st));
+    CK(cudaMemcpyAsync(d_pm, b->h_exp_pixmask.data(), (size_t)R, cudaMemcpyHostToDevice, st));
+    k_exp_maskrows<<<cdiv(NU, 256), 256, 0, st>>>(NU, R, B.D2, d_pm, d_cnt);
+    k_exp_flags<<<cdiv(NT, 256), 256, 0, st>>>(NT, d_cnt, d_flag);
+    CKL();
+    CK(cub::DeviceScan::ExclusiveSum(d_tmp, sb, d_flag, d_ridx, (int)(NT + 1), st));
+    CK(cudaMemcpyAsync(&m, d_ridx + NU, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
   // entry offsets over the used copies: the count pass may exceed 2^31 entries in total, so check with a 64-bit sum
   {
     std::vector<int> hcnt((size_t)NU);

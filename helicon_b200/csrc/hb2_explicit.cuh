@@ -105,6 +105,13 @@ __global__ void k_exp_flags(long long n, const int* __restrict__ cnt, int* __res
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) flag[t] = cnt[t] > 0;
 }
+// half sets: potential row t = (copy, k, j) survives iff its pixel id k*D2 + j is set in the mask
+__global__ void k_exp_maskrows(long long n, long long R, int D2, const uint8_t* __restrict__ mask, int* __restrict__ cnt) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long kj = t % R;  // = k*D2 + j: the potential rows of a copy are laid out [k][j]
+  if (!mask[kj]) cnt[t] = 0;
+}
 __global__ void k_iota(int n, int* __restrict__ out) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n) out[e] = e;

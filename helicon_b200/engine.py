@@ -348,7 +348,7 @@ class ExplicitBatch(Batch):
     kernels; symmetry rows, LSMR/TRF and the score are the batch's usual kernels."""
 
     def __init__(self, problem: Problem, L3: int, spec: CandidateSpec, tilt_degree=0.0, psi_degree=0.0, dy_pixel=0.0,
-                 interpolation="nn", stream=None):
+                 interpolation="nn", stream=None, pixel_mask=None):
         from scipy.spatial.transform import Rotation as R
 
         from . import planner
@@ -384,6 +384,9 @@ class ExplicitBatch(Batch):
         for q in range(9):
             geo.rot_yx[q] = float(myx[q])
         Xt, Zt = planner.reference_xz_tables(problem.s, D2, L2)
+        if pixel_mask is not None:  # half set (fsc_test): rows of the other half are dropped after the early stop
+            pm = np.ascontiguousarray(pixel_mask, dtype=np.uint8).reshape(L2 * D2)
+            _lib.check(lib.hb2_batch_explicit_pixel_mask(self._h, _lib.ptr(pm)))
         used, m, nnz = C.c_int32(), C.c_int64(), C.c_int64()
         self.rows_per_copy = np.zeros(len(copies), dtype=np.int32)
         _lib.check(lib.hb2_batch_explicit_rows(

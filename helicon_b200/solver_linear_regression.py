@@ -188,8 +188,6 @@ def lsq_reconstruct(
     if interpolation in ("linear10", "linear01"):
         _unsupported(f"interpolation={interpolation!r} (the reference's data and symmetry builders disagree on it, "
                      "SLR:907 vs 1401)")
-    if explicit and fsc_test:
-        _unsupported("fsc_test together with tilt/psi/dy != 0")
     if algorithm.get("model", "lsq") != "lsq":
         _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
     if score_metric != "cosine":
@@ -214,10 +212,34 @@ def lsq_reconstruct(
         nsets = 3 if fsc_test >= 1 else 1
         # fsc_test: the full set and the two half sets are three candidates of one batch that differ only in
         # which data rows they keep (SLR:441-482); the symmetry rows are shared by construction.
-        if explicit:  # general orientation: explicit GPU-built data rows (one candidate)
-            batch = ExplicitBatch(prob, L3, spec, tilt_degree, psi_degree, dy_pixel, _interp(interpolation))
-        else:
-            batch = Batch(prob, L3, [spec] * nsets)
+        if explicit:
+            # explicit GPU-built data rows (general orientation / trilinear): one candidate per batch; the half sets of
+            # fsc_test are two more batches whose builder drops the other half's rows
+            xs, scs, infos = [], [], []
+            masks = [None]
+            for hs in range(nsets):
+                batch = ExplicitBatch(prob, L3, spec, tilt_degree, psi_degree, dy_pixel, _interp(interpolation),
+                                      pixel_mask=masks[hs])
+                try:
+                    if hs == 0 and nsets == 3:
+                        _, kk, jj = batch.data_row_index(0)
+                        set1 = split_pixel_ids((kk * D2 + jj).astype(np.int32), fsc_test)
+                        m1 = np.zeros(L2 * D2, dtype=np.uint8)
+                        m1[set1] = 1
+                        masks += [m1, 1 - m1]
+                    r = batch.solve(clip_pred=int(thresh_fraction >= 0))
+                    xs.append(batch.rec3d(0)); scs.append(np.float32(r[0]["score"]))
+                    infos.append((r[0].copy(), batch.timing()))
+                finally:
+                    batch.close()
+            rec3d = xs[0]
+            half1, half2 = (xs[1], xs[2]) if nsets == 3 else (None, None)
+            score = scs[0] / 2 + (scs[1] + scs[2]) / 4 if nsets == 3 else scs[0]
+            info = dict(res=infos[0][0], all_res=np.array([i[0] for i in infos]), timing=infos[0][1])
+            if return_info:
+                return (rec3d, half1, half2), score, info
+            return (rec3d, half1, half2), score
+        batch = Batch(prob, L3, [spec] * nsets)
         half1 = half2 = None
         try:
             if nsets == 3:
@@ -264,5 +286,7 @@ def split_pixel_ids(b_id, mode):
 
 
 def refine_tilt_psi_dy(*args, **kwargs):
-    """SLR:550-841 needs the general-orientation projector; not on the CUDA path yet."""
+    """SLR:550-841: Gauss-Newton around ``lsqr(atol=btol=1e-6)`` / ``lsq_linear`` at its default tolerance.  Its
+    building blocks (tilted rows, solves) run on the GPU through ``lsq_reconstruct(tilt_degree=..., ...)``; the
+    refinement loop itself is not implemented."""
     _unsupported("refine_tilt_psi_dy (SLR:550-841)")

@@ -188,6 +188,10 @@ typedef struct {
 int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry* g, int32_t n_copies, const double* copy_mats,
                             const double* zshift, const double* xtab, const double* ztab, int64_t min_projection_lines,
                             int32_t* copies_used, int32_t* rows_per_copy, int64_t* n_rows, int64_t* nnz);
+/* Half sets for explicit rows (fsc_test): keep only the rows whose pixel id k*D2 + j is set in mask[L2*D2] (NULL: all);
+ * applied after the early stop, as the reference splits the finished matrix (SLR:441-444).  Call before
+ * hb2_batch_explicit_rows. */
+int hb2_batch_explicit_pixel_mask(hb2_batch* b, const uint8_t* mask);
 /* the rows as CSR in the reference's voxel order (entries unmerged: a voxel hit twice by one ray appears twice),
  * right-hand side and pixel ids (SLR:1651-1654); any pointer may be NULL */
 int hb2_batch_explicit_export(hb2_batch* b, int64_t* indptr, int32_t* indices, float* data, float* b_out, int32_t* pid_out);
