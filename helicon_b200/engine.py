@@ -439,6 +439,16 @@ class ExplicitBatch(Batch):
         A = csr_matrix((data[:nnz], indices[:nnz], indptr), shape=(m, self.n), dtype=np.float32)
         return A, b[:m], pid[:m]
 
+    def data_b(self):
+        """b_data of the explicit rows (SLR:1548) without downloading the matrix."""
+        b = np.zeros(max(self.m_rows, 1), dtype=np.float32)
+        _lib.check(_lib.load().hb2_batch_explicit_export(self._h, None, None, None, _lib.ptr(b), None))
+        return b[:self.m_rows]
+
+    def predict(self, x):
+        """A_data @ x on the GPU (x in the reference's voxel order)."""
+        return self.apply_forward(0, x)[:self.m_rows]
+
     def sym_csr(self, c=0):
         if not self.m_sym_explicit:
             return super().sym_csr(c)

@@ -4,7 +4,7 @@ reference's denovo3D solver, "SLR") with the per-candidate work on the GPU.
 Same function names, argument meaning, return types and array layouts as the
 reference; see INTEGRATION.md.  What is NOT implemented on the CUDA path raises
 ``NotImplementedError`` (there is no CPU fallback by design):
-``refine_tilt_psi_dy``, score metrics other than
+score metrics other than
 "cosine", and solver models other than ``{"model": "lsq"}``.
 """
 
@@ -76,6 +76,17 @@ def back_project_2d_coords_to_3d_coords(
         pts *= scale2d_to_3d
     tables = tuple(np.swapaxes(pts[:, c].reshape((D2, D2, L2)), 0, 2) for c in range(3))
     return tables, region
+
+
+def _disk_mask(D3, rmin, rmax):
+    """In-plane support of helicon.get_cylindrical_mask (lib/analysis.py:731-774): rmin^2 <= x^2 + y^2 < rmax^2."""
+    j = np.arange(D3) - D3 // 2
+    Y, X = np.meshgrid(j, j, indexing="ij")
+    r2 = X * X + Y * Y
+    m = r2 < rmax * rmax
+    if 0 < rmin < rmax:
+        m &= r2 >= rmin * rmin
+    return m
 
 
 def _make_problem(image, scale2d_to_3d, D2, L2, D3, D3_inner, rmax=None, interpolation="nn", device=0):
@@ -192,10 +203,46 @@ def lsq_reconstruct(
         _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
     if score_metric != "cosine":
         _unsupported(f"score_metric {score_metric!r} (only 'cosine', SLR:500-525)")
-    if refine_tilt_psi_dy_range is not None and any(
-        refine_tilt_psi_dy_range.get(k, 0) > 0 for k in ("tilt", "psi", "dy")
-    ):
-        _unsupported("refine_tilt_psi_dy (SLR:550-841)")
+    want_refine = refine_tilt_psi_dy_range is not None and any(
+        refine_tilt_psi_dy_range.get(k, 0) > 0 for k in ("tilt", "psi", "dy"))
+    if want_refine and fsc_test:
+        _unsupported("refine_tilt_psi_dy_range together with fsc_test")
+    if want_refine:
+        # SLR:372-437: solve at the given orientation, then the local Gauss-Newton refinement; keep whichever scores higher
+        kw = dict(csym=csym, tilt_degree=tilt_degree, psi_degree=psi_degree, dy_pixel=dy_pixel,
+                  thresh_fraction=thresh_fraction, positive_constraint=positive_constraint,
+                  reconstruct_diameter_3d_inner_pixel=reconstruct_diameter_3d_inner_pixel,
+                  reconstruct_diameter_2d_pixel=reconstruct_diameter_2d_pixel,
+                  reconstruct_diameter_3d_pixel=reconstruct_diameter_3d_pixel,
+                  reconstruct_length_2d_pixel=reconstruct_length_2d_pixel,
+                  reconstruct_length_3d_pixel=reconstruct_length_3d_pixel, sym_oversample=sym_oversample,
+                  interpolation=interpolation, fsc_test=0, score_metric=score_metric, target_apix2d=target_apix2d,
+                  verbose=verbose, algorithm=algorithm, refine_tilt_psi_dy_range=None, cpu=cpu, device=device)
+        (rec3d, _, _), score = lsq_reconstruct(projection_image, scale2d_to_3d, twist_degree, rise_pixel, **kw)
+        r = refine_tilt_psi_dy_range
+        image = np.asarray(projection_image)
+        D2r = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
+        L2r = reconstruct_length_2d_pixel if reconstruct_length_2d_pixel > 0 else image.shape[1]
+        tilt_o, psi_o, dy_o, x_ref, score_ref = refine_tilt_psi_dy(
+            projection_image, scale2d_to_3d, twist_degree, rise_pixel, csym, D2r, L2r, reconstruct_diameter_3d_pixel,
+            reconstruct_diameter_3d_inner_pixel, reconstruct_length_3d_pixel, sym_oversample, interpolation, None,
+            tilt_0=0.0, psi_0=0.0, dy_0=0.0, delta_tilt=r.get("delta_tilt", 0.5), delta_psi=r.get("delta_psi", 1.0),
+            delta_dy=r.get("delta_dy", 0.2), max_iter=r.get("max_iter", 5),
+            bounds_tilt=(-r.get("tilt", 30.0), r.get("tilt", 30.0)), bounds_psi=(-r.get("psi", 45.0), r.get("psi", 45.0)),
+            bounds_dy=(-r.get("dy", 5.0), r.get("dy", 5.0)), positive_constraint=positive_constraint,
+            algorithm=algorithm, verbose=verbose, cpu=cpu, device=device)
+        if score_ref is not None and (score is None or score_ref > score):
+            D3r, L3r = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
+            m2 = _disk_mask(D3r, reconstruct_diameter_3d_inner_pixel / 2, D3r // 2 - 1)
+            rec3d = np.zeros((L3r, D3r, D3r), dtype=np.float32)
+            rec3d[:, m2] = np.asarray(x_ref, dtype=np.float32).reshape(L3r, -1)
+            score = score_ref
+            if not hasattr(lsq_reconstruct, "_refined_params"):  # SLR:431-435 (consumed by pipeline.py:429-434)
+                lsq_reconstruct._refined_params = {}
+            lsq_reconstruct._refined_params.update(tilt=tilt_o, psi=psi_o, dy=dy_o)
+        if return_info:
+            return (rec3d, None, None), score, dict(refined=(tilt_o, psi_o, dy_o, score_ref))
+        return (rec3d, None, None), score
     image = np.asarray(projection_image)
     D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
     D2 = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
@@ -285,8 +332,138 @@ def split_pixel_ids(b_id, mode):
     return np.asarray(set1, dtype=np.int64)
 
 
-def refine_tilt_psi_dy(*args, **kwargs):
-    """SLR:550-841: Gauss-Newton around ``lsqr(atol=btol=1e-6)`` / ``lsq_linear`` at its default tolerance.  Its
-    building blocks (tilted rows, solves) run on the GPU through ``lsq_reconstruct(tilt_degree=..., ...)``; the
-    refinement loop itself is not implemented."""
-    _unsupported("refine_tilt_psi_dy (SLR:550-841)")
+def refine_tilt_psi_dy(
+    projection_image,
+    scale2d_to_3d,
+    twist_degree,
+    rise_pixel,
+    csym,
+    reconstruct_diameter_2d_pixel,
+    reconstruct_length_2d_pixel,
+    reconstruct_diameter_3d_pixel,
+    reconstruct_diameter_3d_inner_pixel,
+    reconstruct_length_3d_pixel,
+    sym_oversample,
+    interpolation,
+    x_init,
+    tilt_0=0.0,
+    psi_0=0.0,
+    dy_0=0.0,
+    delta_tilt=0.5,
+    delta_psi=1.0,
+    delta_dy=0.2,
+    max_iter=5,
+    tol_tilt=0.05,
+    tol_psi=0.1,
+    tol_dy=0.05,
+    bounds_tilt=(-30.0, 30.0),
+    bounds_psi=(-45.0, 45.0),
+    bounds_dy=(-5.0, 5.0),
+    positive_constraint=-1,
+    algorithm=None,
+    verbose=0,
+    cpu=1,
+    device=0,
+):
+    """SLR:550-841: Gauss-Newton refinement of (tilt, psi, dy) with a finite-difference Jacobian -> ``(tilt, psi, dy,
+    x, score)``.  The loop (perturb, 3x3 normal equations, projected step, convergence test, re-solve) is the
+    reference's, on the host with scalars; every matrix build, prediction ``A_data @ x`` and solve runs on the GPU
+    (explicit rows, ``engine.ExplicitBatch``).
+
+    Solver note: the reference solves with ``scipy.sparse.linalg.lsqr(atol=btol=1e-6)`` (or ``lsq_linear`` at its default
+    tolerance when the positive rule fires); here the same systems are solved by the batch's LSMR at the same
+    tolerances (atol = btol = 1e-6, iteration limit 2n; bounded branch with tol = 1e-10).  LSQR and LSMR run the same
+    Golub-Kahan process and converge to the same minimiser; the iterates at the stopping point differ at the level of
+    the tolerance (measured against the reference in tests/test_gpu_parity.py).  ``x_init`` is unused, as in the
+    reference."""
+    image = np.asarray(projection_image)
+    D2, L2 = int(reconstruct_diameter_2d_pixel), int(reconstruct_length_2d_pixel)
+    D3, L3 = int(reconstruct_diameter_3d_pixel), int(reconstruct_length_3d_pixel)
+    t = np.array([tilt_0, psi_0, dy_0], dtype=np.float64)
+    deltas = np.array([delta_tilt, delta_psi, delta_dy], dtype=np.float64)
+    lo = np.array([bounds_tilt[0], bounds_psi[0], bounds_dy[0]], dtype=np.float64)
+    hi = np.array([bounds_tilt[1], bounds_psi[1], bounds_dy[1]], dtype=np.float64)
+    # SLR:634-638: the row targets use the FULL grid size D3*D3*L3 here (not the mask count as lsq_reconstruct does)
+    target = min(MAX_EQUATIONS, int(max(D2 * L2, D3 * D3 * L3) * sym_oversample))
+    positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
+    interp = _interp(interpolation)
+    prob = _make_problem(image, scale2d_to_3d, D2, L2, D3, reconstruct_diameter_3d_inner_pixel, device=device)
+    spec = CandidateSpec(twist_degree, rise_pixel, csym, target, target, positive)
+    n = L3 * prob.ndisk
+
+    def build(tv):
+        return ExplicitBatch(prob, L3, spec, float(tv[0]), float(tv[1]), float(tv[2]), interp)
+
+    def solve(batch):
+        m = batch.rows_padded(0)[1]  # data + symmetry rows (padded count: an upper bound is enough for the limit)
+        if positive:  # lsq_linear(A, b, bounds, max_iter=200): tol = 1e-10, lsmr_tol = 1e-2 * tol, lsmr_maxiter = min(m, n)
+            batch.solve(atol=1e-12, btol=1e-12, max_iter=int(min(max(m, 1), n)), trf_tol=1e-10, trf_max_iter=200)
+        else:         # lsqr(A, b, atol=1e-6, btol=1e-6): iter_lim = 2 n
+            batch.solve(atol=1e-6, btol=1e-6, max_iter=2 * n)
+        return batch.x(0)
+
+    try:
+        base = build(t)
+        try:
+            b_data = base.data_b()
+            x_cur = solve(base)
+            p_0 = base.predict(x_cur)
+        finally:
+            base.close()
+        n_base = len(b_data)
+        for iteration in range(max_iter):
+            J = np.zeros((n_base, 3), dtype=np.float64)
+            for i in range(3):
+                tp = t.copy()
+                tp[i] = np.clip(tp[i] + deltas[i], lo[i], hi[i])
+                pert = build(tp)
+                try:
+                    p_pert = pert.predict(x_cur)
+                finally:
+                    pert.close()
+                actual = tp[i] - t[i]
+                if abs(actual) > 1e-12:
+                    nc = min(n_base, len(p_pert))  # SLR:776-779: row sets may differ in size
+                    J[:nc, i] = (p_pert[:nc].astype(np.float64) - p_0[:nc]) / actual
+            r_0 = p_0.astype(np.float64) - b_data
+            G = J.T @ J
+            g = J.T @ r_0
+            cond = np.linalg.cond(G) if np.linalg.det(G) != 0 else float("inf")
+            if cond > 1e10:
+                G = G + 1e-6 * np.diag(np.diag(G))
+            try:
+                delta_t = np.linalg.solve(G, -g)
+            except np.linalg.LinAlgError:
+                logger.warning(f"  Refine iter {iteration}: singular system, stopping")
+                break
+            t_new = np.clip(t + delta_t, lo, hi)
+            step = t_new - t
+            converged = abs(step[0]) < tol_tilt and abs(step[1]) < tol_psi and abs(step[2]) < tol_dy
+            t = t_new
+            if converged:
+                break
+            cur = build(t)
+            try:
+                if cur.m_rows != n_base:
+                    # the reference concatenates the NEW rows with the BASE right-hand side here (SLR:826) and fails on
+                    # a size mismatch; keep the last consistent solution instead of raising from inside the loop
+                    logger.warning("  Refine: the row set changed size at t=%s; stopping", t)
+                    break
+                x_cur = solve(cur)
+                p_0 = cur.predict(x_cur)
+            finally:
+                cur.close()
+    finally:
+        prob.close()
+    score = float(planner_cosine(p_0, b_data))
+    return float(t[0]), float(t[1]), float(t[2]), x_cur, score
+
+
+def planner_cosine(a, b):
+    """helicon.cosine_similarity (lib/analysis.py:802-821) for the refinement's final score (host, two vectors)."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    na, nb = np.linalg.norm(a), np.linalg.norm(b)
+    if na == 0 or nb == 0:
+        return 0.0
+    return float(np.sum(a * b) / (na * nb))

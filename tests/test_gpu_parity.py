@@ -547,3 +547,45 @@ def test_half_sets_on_explicit_rows_vs_reference_golden(solver, name):
     # trilinear systems carry the reference's own permutation band (see test_trilinear_solve_vs_reference_golden)
     assert dscore <= (1e-4 if linear else 1e-5)
     assert max(rels) <= (3e-2 if linear else 5e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["refine_dy_40", "refine_dy_32_pos"])
+def test_refine_tilt_psi_dy_vs_reference_golden(solver, name):
+    """refine_tilt_psi_dy (SLR:550-841): the reference's Gauss-Newton loop with every build / prediction / solve on the
+    GPU.  The reference solves with LSQR(1e-6) (bounded: lsq_linear at 1e-10), the GPU path with LSMR at the same
+    tolerances, so the comparison is at the level of those tolerances and of the refinement's own convergence
+    thresholds (tol_tilt = 0.05 deg, tol_psi = 0.1 deg, tol_dy = 0.05 px)."""
+    d = load(name)
+    apix, twist, rise, csym, L3, so, pc, mi = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    tilt, psi, dy, x, score = solver.refine_tilt_psi_dy(
+        projection_image=img, scale2d_to_3d=1.0, twist_degree=float(twist), rise_pixel=float(rise / apix), csym=int(csym),
+        reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N,
+        reconstruct_diameter_3d_inner_pixel=0, reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so),
+        interpolation="nn", x_init=None, max_iter=int(mi), positive_constraint=int(pc), verbose=0)
+    rt, rp, rdy, rs = d["out"]
+    relx = float(np.linalg.norm(x - d["x"]) / np.linalg.norm(d["x"]))
+    print(f"{name}: tilt {tilt:.5f} ({rt:.5f}) psi {psi:.5f} ({rp:.5f}) dy {dy:.5f} ({rdy:.5f}) score {score:.6f} ({rs:.6f}) "
+          f"rel-L2(x) {relx:.2e}")
+    assert isinstance(tilt, float) and isinstance(psi, float) and isinstance(dy, float) and isinstance(score, float)
+    assert isinstance(x, np.ndarray) and np.all(np.isfinite(x))
+    assert abs(tilt - rt) <= 0.05 and abs(psi - rp) <= 0.1 and abs(dy - rdy) <= 0.05
+    assert abs(score - rs) <= 2e-3 and relx <= 5e-2
+
+
+@pytest.mark.gpu
+def test_lsq_reconstruct_with_refine_range(solver):
+    """lsq_reconstruct(refine_tilt_psi_dy_range=...) (SLR:372-437): base solve, refinement, the better of the two."""
+    d = load("refine_dy_40")
+    apix, twist, rise, csym, L3, so, pc, mi = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    kw = dict(positive_constraint=int(pc), reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N,
+              reconstruct_diameter_3d_pixel=N, reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so), interpolation="nn")
+    (rec0, _, _), s0 = solver.lsq_reconstruct(img, 1.0, float(twist), float(rise / apix), int(csym), **kw)
+    (rec1, h1, h2), s1 = solver.lsq_reconstruct(img, 1.0, float(twist), float(rise / apix), int(csym),
+                                               refine_tilt_psi_dy_range=dict(tilt=5.0, psi=5.0, dy=2.0, max_iter=2), **kw)
+    assert rec1.shape == rec0.shape and h1 is None and h2 is None and np.isfinite(rec1).all()
+    assert float(s1) >= float(s0) - 1e-7
