@@ -196,6 +196,12 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
             r_dict["dy"] = dy_range
         if r_dict:
             refine_range = r_dict
+    if refine_range is not None:
+        # solver_linear_regression.lsq_reconstruct(refine_tilt_psi_dy_range=...) runs the refinement on the GPU, but the
+        # task wrapper then rotates the display volume by the refined angles with helicon.transform_map (pipeline.py:
+        # 428-438, cubic-spline resampling), which is not on the CUDA path
+        _unsupported("tilt/psi/dy refinement ranges in process_one_task (transform_map of the display volume); "
+                     "solver_linear_regression.lsq_reconstruct / refine_tilt_psi_dy accept them")
     (rec3d, rec3d_set_1, rec3d_set_2), score = lsq_reconstruct(
         projection_image=data, scale2d_to_3d=target_apix2d / target_apix3d, twist_degree=twist,
         rise_pixel=rise / target_apix3d, csym=csym, tilt_degree=tilt, psi_degree=psi, dy_pixel=dy / target_apix2d,
