@@ -205,7 +205,8 @@ def main():
     ap.add_argument("--no-trilinear", action="store_true", help="skip the secondary interpolation='linear' measurement")
     ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
     ap.add_argument("--e2e-batches", type=int, default=3, help="batches per search_grid() call of the e2e measurement")
-    ap.add_argument("--cpu-iters", type=int, default=60)
+    ap.add_argument("--cpu-iters", type=int, default=200,
+                    help="scipy-LSMR iterations timed in the cpu_baseline sample (200 -> ~15-20 s of CPU work)")
     ap.add_argument("--ref-iters", type=int, default=16, help="--impl reference: LSMR iterations timed per sampled candidate")
     ap.add_argument("--ref-budget-s", type=float, default=200.0, help="--impl reference: wall-clock budget of the run")
     args = ap.parse_args()
