@@ -411,7 +411,7 @@ def main():
         trilinear = dict(value=outl["n_candidates"] / dtl, unit="candidates/s", candidates=int(outl["n_candidates"]),
                          n_gpus=1, mean_lsmr_iterations=float(outl["itn"].mean()), best_score=float(np.nanmax(outl["scores"])),
                          note="search_grid(interpolation='linear', positive_constraint=0) on one GPU: row build on the GPU "
-                              "+ LSMR on the explicit CSR (345 M entries per candidate at this shape), one un-warmed call")
+                              "+ LSMR on the explicit CSR (192 M entries per candidate at this shape), one un-warmed call")
 
     if rank != 0:
         if dist is not None:

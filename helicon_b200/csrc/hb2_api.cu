@@ -595,8 +595,38 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
                                                   d_w, d_erow, d_ptr, d_rb, d_pid);
     CKL();
   }
-  const int nnz_i = (int)nnz;
-  CK(cudaMemcpyAsync(d_ptr + m, &nnz_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  {
+    const int nnz_i = (int)nnz;
+    CK(cudaMemcpyAsync(d_ptr + m, &nnz_i, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  // trilinear rows: merge the duplicate entries of every row (k_exp_merge); rows of at most 8*D2 entries fit shared memory
+  static const bool no_merge = getenv("HB2_NO_MERGE") && atoi(getenv("HB2_NO_MERGE"));
+  int maxe = 1;
+  while (maxe < 8 * B.D2) maxe <<= 1;  // a row has at most 8*D2 entries; the sort works on the next power of two
+  const size_t msm = (size_t)maxe * (sizeof(unsigned long long) + sizeof(float));
+  if (G.linear && m > 0 && nnz > 0 && !no_merge && msm <= 160 * 1024) {
+    int *d_ucnt, *d_nptr;
+    CK(b->pool.alloc(&d_ucnt, (size_t)m + 1, true, st));
+    CK(b->pool.alloc(&d_nptr, (size_t)m + 1, false, st));
+    cudaFuncSetAttribute(k_exp_merge<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+    k_exp_merge<0><<<m, HB2_MERGE_THREADS, msm, st>>>(m, maxe, d_ptr, d_col, d_w, d_ucnt, nullptr, nullptr, nullptr, nullptr);
+    CKL();
+    size_t sb6 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sb6, d_ucnt, d_nptr, m + 1, st);
+    void* d_t6; { uint8_t* p; CK(b->pool.alloc(&p, sb6, false, st)); d_t6 = p; }
+    CK(cub::DeviceScan::ExclusiveSum(d_t6, sb6, d_ucnt, d_nptr, m + 1, st));
+    int nnz_m = 0;
+    CK(cudaMemcpyAsync(&nnz_m, d_nptr + m, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int *d_ncol, *d_nerow; float* d_nw;
+    CK(b->pool.alloc(&d_ncol, (size_t)std::max(nnz_m, 1), false, st));
+    CK(b->pool.alloc(&d_nw, (size_t)std::max(nnz_m, 1), false, st));
+    CK(b->pool.alloc(&d_nerow, (size_t)std::max(nnz_m, 1), false, st));
+    k_exp_merge<1><<<m, HB2_MERGE_THREADS, 0, st>>>(m, maxe, d_ptr, d_col, d_w, nullptr, d_nptr, d_ncol, d_nw, d_nerow);
+    CKL();
+    d_ptr = d_nptr; d_col = d_ncol; d_w = d_nw; d_erow = d_nerow;
+    b->exp_nnz = nnz_m;
+  }
   // max(b) over the rows: upper bound of the positive constraint (SLR:248)
   std::vector<float> hb((size_t)std::max(m, 1), 0.f);
   if (m > 0) CK(cudaMemcpyAsync(hb.data(), d_rb, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
@@ -610,7 +640,7 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
   B.exp_m = m; B.exp_m_data = m; B.exp_ptr = d_ptr; B.exp_col = d_col; B.exp_w = d_w;
   if (copies_used) *copies_used = used;
   if (n_rows) *n_rows = m;
-  if (nnz_out) *nnz_out = nnz;
+  if (nnz_out) *nnz_out = b->exp_nnz;
   return HB2_OK;
 }
 
