@@ -1,4 +1,6 @@
-import sys, os, time; sys.path.insert(0,'.')
+"""Per-step wall-clock trace of the double-buffered batch pipeline (six 200-candidate steps of cfg2): when each batch
+becomes ready, how long its solve takes.  usage: python profiles/pipeline_step_trace.py"""
+import sys, os, time; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, warnings; warnings.filterwarnings("ignore")
 import torch
 import bench
