@@ -151,14 +151,29 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_data(BD B, TD T, const doub
     if (!B.rayvalid[a * D2 + j]) continue;
     const IdxT* __restrict__ fj = fm + (size_t)j * D2;
     for (int z0 = 0; z0 < L3P; z0 += 16) {
-      double acc[4] = {0, 0, 0, 0};  // slices z0 + q + 4t
-      for (int i = sg; i < D2; i += 8) {
-        IdxT id = fj[i];
-        if (id != Sent<IdxT>::v) {
-          const double* vp = vsrc + (size_t)id * L3P + z0 + q;
+      // lane (sg, q): the 4 consecutive slices z0 + 4q ... + 3 of every 8th sample, two 128-bit loads per sample and
+      // four samples in flight (same lane layout as the float32 kernel)
+      double acc[4] = {0, 0, 0, 0};
+      const int zq = z0 + 4 * q;
+      if (zq < L3P) {
+        const double* __restrict__ vb = vsrc + zq;
+        for (int i0 = sg; i0 < D2; i0 += 32) {
+          IdxT ids[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (z0 + q + 4 * t < L3P) acc[t] += __ldg(vp + 4 * t);
+          for (int w = 0; w < 4; ++w) ids[w] = (i0 + 8 * w < D2) ? fj[i0 + 8 * w] : Sent<IdxT>::v;
+          double2 ta[4], tb[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (ids[w] != Sent<IdxT>::v) {
+              const double2* vp = reinterpret_cast<const double2*>(vb + (size_t)ids[w] * L3P);
+              ta[w] = __ldg(vp); tb[w] = __ldg(vp + 1);
+            } else {
+              ta[w] = make_double2(0.0, 0.0); tb[w] = make_double2(0.0, 0.0);
+            }
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (ids[w] != Sent<IdxT>::v) { acc[0] += ta[w].x; acc[1] += ta[w].y; acc[2] += tb[w].x; acc[3] += tb[w].y; }
         }
       }
 #pragma unroll
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd64_data(BD B, TD T, const doub
 #pragma unroll
         for (int t = 0; t < 4; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
       if (sg < 4) {
-        const int z = z0 + q + 4 * sg;
+        const int z = zq + sg;
         if (z < L3) {
           const double sum = sg == 0 ? acc[0] : (sg == 1 ? acc[1] : (sg == 2 ? acc[2] : acc[3]));
           for (int mc = 0; mc < MC; ++mc) {
