@@ -16,6 +16,7 @@ n3 = g["L3"] * prob.ndisk
 target = min(MAX_EQUATIONS, int(max(g["D2"] * g["L2"], n3) * g["sym_oversample"]))
 tw = np.linspace(-3.0, -0.2, 100)
 cases = {"regular (rise 4.73)": [(t, 4.73) for t in tw], "z ties (rise 4.75)": [(t, 4.75) for t in tw],
+         "z ties on every odd h (rise 4.55 = 3.5 px)": [(t, 4.55) for t in tw[::4]],
          "xy ties (twist -1.2, -1.5, -2.0, -2.5, -3.0)": [(t, r) for t in (-1.2, -1.5, -2.0, -2.5, -3.0) for r in np.linspace(4.41, 5.09, 20)]}
 for name, cl in cases.items():
     batch = Batch(prob, g["L3"], [CandidateSpec(t, r / g["apix3d"], 1, target, target, False) for t, r in cl])
