@@ -160,6 +160,7 @@ struct hb2_batch {
   bool idx16 = true;
   size_t adj_tile_smem = 0;
   int adj_chunks = 1;  // adj_tile == 2: chunks of 16 slices
+  bool want_tie_info = false;
   size_t fwd_band_smem = 0;
   // tie views (hb2_batch_set_ties)
   int n_tie = 0, tie_TS = 0;
@@ -966,12 +967,21 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       CKC(b->pool.alloc(&d_mask, (size_t)nm, false, st));
       k_tie_pack<<<cdiv(nm, 256), 256, 0, st>>>(b->n_tie, b->tie_TS, B.ZMC, D2, B.tie_up, d_mask);
       B.tie_upmask = d_mask;
+      b->want_tie_info = true;  // filled once colk is on the device (below)
     }
     CKC(upload(b->pool, &B.tie_rowvalid, b->h_tie_rv, st));
   }
   CKC(upload(b->pool, &B.view_uoff, view_uoff, st));
   std::vector<int> colk_v(colk, colk + ncolk);
   CKC(upload(b->pool, &B.colk, colk_v, st));
+  B.tie_info = nullptr;
+  if (b->want_tie_info && b->n_tie_views > 0) {
+    int* d_info;
+    CKC(b->pool.alloc(&d_info, (size_t)nviews, true, st));
+    k_tie_info<<<cdiv(b->n_tie_views, 128), 128, 0, st>>>(b->n_tie_views, B.tie_views, B.ZMC, b->tie_TS, B.view_tie, B.view_tie_slot0,
+                                                        B.view_colbegin, B.colk, B.tie_zlo, d_info);
+    B.tie_info = d_info;
+  }
   CKC(upload(b->pool, &B.cand_view_begin, b->h_view_begin, st));
   CKC(upload(b->pool, &B.cand_view_count, b->h_view_count, st));
   CKC(upload(b->pool, &B.cand_uoff, b->h_uoff, st));

@@ -79,6 +79,8 @@ struct BD {
   const signed char* tie_zlo;     // [n_tie][TS]
   const unsigned char* tie_up;    // [n_tie][TS][D2]
   const uint16_t* tie_upmask;     // [n_tie][TS/ZMC][D2]: bit t = tie_up of column slot g*ZMC + t (built at create)
+  const int* tie_info;            // [nviews]: used-slot mask (low 16 bits) | (zb + 2) << 16 when the used slots sit on
+                                  // consecutive slices from zb = -1 or 0 (fast path of the tie kernels), else high half 0
   const unsigned char* tie_rowvalid;  // [n_tie][TS][D2]
   int tie_TS, n_tie_views;
   const int* tie_views;           // [n_tie_views] view slots that are tie views, grouped by candidate

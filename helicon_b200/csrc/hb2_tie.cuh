@@ -34,6 +34,25 @@ __global__ void k_tie_pack(int n_tie, int TS, int ZMC, int D2, const unsigned ch
   mask[t] = (uint16_t)m;
 }
 
+// per tie view slot: which column slots are used and whether they sit on consecutive slices from zb = -1 or 0
+__global__ void k_tie_info(int n_tie_views, const int* __restrict__ tie_views, int ZMC, int tie_TS, const int* __restrict__ view_tie,
+                           const int* __restrict__ view_tie_slot0, const int* __restrict__ view_colbegin,
+                           const int* __restrict__ colk, const signed char* __restrict__ tie_zlo, int* __restrict__ info) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_tie_views) return;
+  const int view = tie_views[e];
+  const int tv = view_tie[view], s0 = view_tie_slot0[view];
+  const int* ck = colk + view_colbegin[view];
+  const signed char* zl = tie_zlo + (size_t)tv * tie_TS + s0;
+  unsigned used = 0;
+  for (int t = 0; t < ZMC && t < 16; ++t) used |= (ck[t] >= 0 ? 1u : 0u) << t;
+  const int zb = zl[0];
+  bool ok = (zb == -1 || zb == 0) && s0 % ZMC == 0 && tie_TS % ZMC == 0 && ZMC <= 16;
+  for (int t = 0; t < ZMC && ok; ++t)
+    if (ck[t] >= 0 && zl[t] != zb + t) ok = false;
+  info[view] = (int)(used | (ok ? (unsigned)(zb + 2) << 16 : 0u));
+}
+
 // Grid (tie view slots, ray groups): a CTA takes the rays j = blockIdx.y, blockIdx.y + gridDim.y, ... of one tie view slot
 // (ZMC column slots of one tie view), one warp per ray, lanes over the depth samples; gridDim.y = the view's partial-sum
 // slots (BD::fwd_ppv).  (One CTA per view slot cost 2.2 ms per pass at 512 x 512 -- a handful of CTAs walking 512 x 512
@@ -41,7 +60,7 @@ __global__ void k_tie_pack(int n_tie, int TS, int ZMC, int D2, const unsigned ch
 //   f32 (TRF = false): src = v or xs, rows = u, LSMR / PLAIN / SCORE epilogue of k_fwd_data incl. the view's partials;
 //   f64 (TRF = true) : rows <- A w plain.
 template <typename IdxT, typename T, bool TRF>
-__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
+__global__ void __launch_bounds__(HB2_BLOCK, 6) k_fwd_tie(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
   const int view = B.tie_views[blockIdx.x];
   const int c = B.view_cand[view];
   __shared__ float red[HB2_BLOCK / 32];
@@ -138,8 +157,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_tie(BD B, TD Tt, const T* __r
     }
 #pragma unroll
     for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
+      if (t < ZMC && s_colk[t] >= 0) {  // warp-uniform: unused column slots (11 of 12 in a view's second slot group) cost nothing
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+      }
     }
     // lane t finishes column slot t
 #pragma unroll
@@ -203,15 +224,11 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_tie(BD B, TD Tt, const T* __r
     const signed char* __restrict__ zl = B.tie_zlo + (size_t)tv * B.tie_TS + s0;
     const unsigned char* __restrict__ up = B.tie_up + ((size_t)tv * B.tie_TS + s0) * D2;
     const T* __restrict__ ub = rows + B.view_uoff[view];
-    // fast path (see k_fwd_tie): used slots on consecutive slices from zb = -1 or 0, packed masks
-    int fast_zb = 99;
-    if (B.tie_upmask && s0 % ZMC == 0 && B.tie_TS % ZMC == 0) {
-      const int zb = zl[0];
-      bool ok = zb == -1 || zb == 0;
-      for (int t = 0; t < ZMC && ok; ++t)
-        if (ck[t] >= 0 && zl[t] != zb + t) ok = false;
-      if (ok) fast_zb = zb;
-    }
+    // fast path (see k_fwd_tie): used slots on consecutive slices from zb = -1 or 0, packed masks; the per-slot facts
+    // come precomputed (BD::tie_info), not re-derived by every voxel
+    const int inf = B.tie_info ? B.tie_info[view] : 0;
+    const unsigned used = (unsigned)inf & 0xFFFFu;
+    const int fast_zb = (B.tie_upmask && (inf >> 16)) ? (inf >> 16) - 2 : 99;
     const uint16_t* __restrict__ um = B.tie_upmask ? B.tie_upmask + ((size_t)tv * (B.tie_TS / ZMC) + s0 / ZMC) * D2 : nullptr;
     for (int k = 0; k < K; ++k) {
       const size_t mi = ((size_t)a * K + k) * B.apitch + slot;
@@ -221,18 +238,23 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_tie(BD B, TD Tt, const T* __r
       const T* __restrict__ uj = ub + (size_t)j * ZMP;
       if (fast_zb != 99) {
         const unsigned m = um[i];
+        const unsigned lo_m = used & ~m, hi_m = used & m;  // slots whose sample falls into the lower / the upper slice
+        if (fast_zb == 0) {  // slot t -> slice t (lower) or t + 1 (upper)
 #pragma unroll
-        for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
-          if (t < ZMC && ck[t] >= 0) {
-            const T val = TRF ? uj[t] : (T)fmaf((float)uj[t], (float)ib, 0.f);
-            const bool hi = (m >> t) & 1u;
-            // target slice zb + t + bit: static accumulator picks, slices outside [0, L3) are dropped
-            if (fast_zb == 0) {
-              if (!hi) { if (t < L3) acc[t] += val; }
-              else if (t + 1 < L3 && t + 1 < HB2_TIE_MAXZMC) acc[(t + 1) % HB2_TIE_MAXZMC] += val;
-            } else {
-              if (hi) { if (t < L3) acc[t] += val; }
-              else if (t >= 1 && t - 1 < L3) acc[(t + HB2_TIE_MAXZMC - 1) % HB2_TIE_MAXZMC] += val;
+          for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
+            if (t < ZMC) {
+              const T val = TRF ? uj[t] : (T)fmaf((float)uj[t], (float)ib, 0.f);
+              if (((lo_m >> t) & 1u) && t < L3) acc[t] += val;
+              if (t + 1 < HB2_TIE_MAXZMC) { if (((hi_m >> t) & 1u) && t + 1 < L3) acc[(t + 1) % HB2_TIE_MAXZMC] += val; }
+            }
+          }
+        } else {             // slot t -> slice t - 1 (lower) or t (upper)
+#pragma unroll
+          for (int t = 0; t < HB2_TIE_MAXZMC; ++t) {
+            if (t < ZMC) {
+              const T val = TRF ? uj[t] : (T)fmaf((float)uj[t], (float)ib, 0.f);
+              if (((hi_m >> t) & 1u) && t < L3) acc[t] += val;
+              if (t >= 1) { if (((lo_m >> t) & 1u) && t - 1 < L3) acc[(t + HB2_TIE_MAXZMC - 1) % HB2_TIE_MAXZMC] += val; }
             }
           }
         }
