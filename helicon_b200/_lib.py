@@ -53,7 +53,7 @@ class SolveOptions(C.Structure):
     _fields_ = [
         ("max_iter", C.c_int32), ("atol", C.c_double), ("btol", C.c_double), ("conlim", C.c_double),
         ("check_every", C.c_int32), ("clip_pred", C.c_int32), ("trf_max_iter", C.c_int32), ("trf_tol", C.c_double),
-        ("fixed_iters", C.c_int32), ("profile", C.c_int32),
+        ("fixed_iters", C.c_int32), ("profile", C.c_int32), ("norm_mode", C.c_int32),
     ]
 
 

@@ -42,6 +42,38 @@ static int fail(int code, const std::string& msg) {
 
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
+// Opt-in dynamic shared memory limit of the current device.  Every kernel that needs more than 48 KB gets its
+// cudaFuncAttributeMaxDynamicSharedMemorySize set to THIS constant (not to the size of the launch at hand): the
+// attribute is per function and process-wide, so two host threads setting their own sizes would race -- the thread
+// with the larger request could launch after the other thread lowered the limit ("too many resources requested").
+static int hb2_max_smem() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) { cudaGetLastError(); v = 48 << 10; }
+    cached = v; cached_dev = dev;
+  }
+  return cached;
+}
+// Raise the kernel's dynamic shared memory limit to everything the device allows next to the kernel's own static
+// shared memory -- once per (device, kernel); the value never changes afterwards, so concurrent callers cannot race.
+#include <set>
+static void hb2_allow_big_smem(const void* func) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({dev, func})) return;
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, func) != cudaSuccess) { cudaGetLastError(); return; }
+  const int lim = hb2_max_smem() - (int)fa.sharedSizeBytes;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) != cudaSuccess) cudaGetLastError();
+  done.insert({dev, func});
+}
+
 // ---------------------------------------------------------------------------
 struct hb2_problem {
   int device = 0;
@@ -66,21 +98,26 @@ struct hb2_problem {
 // (grid.BatchPipeline), so in steady state every batch lands in the block its stream's previous batch used and no
 // allocator call happens at all -- cudaMalloc/cudaFree synchronise the device, and growing the stream-ordered pool
 // (cudaMallocAsync) was measured to stall a concurrently running solve by up to 2 s (profiles/r1_summary.md section 4).
-// Pools nest like a stack (batch pool, then temporaries of setup / of the bounded branch); what does not fit the
-// arena yet is served by cudaMalloc and remembered, and the arena is re-sized the next time it is empty.
+// An arena has ONE owner at a time (the batch whose pool allocated first while the arena was idle; the temporaries
+// of that batch's setup / bounded branch carry the same owner token and nest like a stack).  Pools of any other
+// owner that is alive at the same time -- e.g. lsq_reconstruct called from several threads of a ThreadPoolExecutor
+// on the default stream (app.py:2473) -- never touch the arena: they are served by cudaMalloc, so two live batches
+// can not be handed the same range and interleaved allocations can not break the stack rule.  All arena state is
+// guarded by g_arena_mu.  What does not fit the arena yet is served by cudaMalloc and remembered, and the arena is
+// re-sized the next time it is idle.
 #include <map>
 #include <mutex>
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, top = 0, wanted = 0, high = 0;
-  int live = 0;  // pools with allocations in this arena
+  int live = 0;                  // pools (of the owner) with allocations in this arena
+  const void* owner = nullptr;   // owner token while live > 0
 };
 static std::mutex g_arena_mu;
 static std::map<std::pair<int, cudaStream_t>, Arena*> g_arenas;
-static Arena* arena_for(cudaStream_t st) {
+static Arena* arena_for_locked(cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
-  std::lock_guard<std::mutex> lk(g_arena_mu);
   Arena*& a = g_arenas[{dev, st}];
   if (!a) a = new Arena();
   return a;
@@ -91,45 +128,50 @@ struct DevPool {
   size_t bytes = 0, overflow = 0;
   cudaStream_t stream = nullptr;
   Arena* arena = nullptr;
-  size_t first = 0, last = 0;  // arena range of this pool
+  const void* owner = nullptr;  // owner token (the batch); null: the pool itself
+  size_t first = 0, last = 0;   // arena range of this pool
   bool in_arena = false;
   template <typename T>
   cudaError_t alloc(T** p, size_t count, bool zero, cudaStream_t st) {
     const size_t nb = (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256;
     stream = st;
-    if (!arena) arena = arena_for(st);
-    Arena& A = *arena;
-    if (A.live == 0 && !in_arena) {  // arena idle: re-size it if earlier batches did not fit
-      A.top = 0;
-      if (A.cap == 0 && A.wanted == 0) {  // first use of this stream: start with a fifth of the free memory (<= 24 GB)
-        size_t fr = 0, tot = 0;
-        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) A.wanted = std::min<size_t>(fr / 5, (size_t)24 << 30) / 9 * 8;
-      }
-      if (A.wanted > A.cap) {
-        if (A.base) { cudaStreamSynchronize(st); cudaFree(A.base); A.base = nullptr; A.cap = 0; }
-        const size_t want = A.wanted + A.wanted / 8;
-        if (cudaMalloc((void**)&A.base, want) == cudaSuccess) A.cap = want;
-        else cudaGetLastError();
-      }
-    }
+    const void* me = owner ? owner : (const void*)this;
     cudaError_t e = cudaSuccess;
-    if (A.top + nb <= A.cap) {
-      if (!in_arena) { in_arena = true; first = A.top; A.live += 1; }
-      *p = reinterpret_cast<T*>(A.base + A.top);
-      A.top += nb; last = A.top;
-      A.high = std::max(A.high, A.top);
-    } else {
-      e = cudaMalloc((void**)p, nb);
-      if (e != cudaSuccess) return e;
-      owned.push_back(*p);
-      overflow += nb;
-      A.wanted = std::max(A.wanted, std::max(A.high, A.top) + overflow_total(A) + nb);
+    {
+      std::lock_guard<std::mutex> lk(g_arena_mu);
+      if (!arena) arena = arena_for_locked(st);
+      Arena& A = *arena;
+      if (A.live == 0) {  // arena idle: re-size it if earlier batches did not fit, then claim it
+        A.top = 0; A.owner = nullptr;
+        if (A.cap == 0 && A.wanted == 0) {  // first use of this stream: start with a fifth of the free memory (<= 24 GB)
+          size_t fr = 0, tot = 0;
+          if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) A.wanted = std::min<size_t>(fr / 5, (size_t)24 << 30) / 9 * 8;
+        }
+        if (A.wanted > A.cap) {
+          if (A.base) { cudaStreamSynchronize(st); cudaFree(A.base); A.base = nullptr; A.cap = 0; }
+          const size_t want = A.wanted + A.wanted / 8;
+          if (cudaMalloc((void**)&A.base, want) == cudaSuccess) A.cap = want;
+          else cudaGetLastError();
+        }
+      }
+      const bool mine = A.live == 0 || A.owner == me;
+      if (mine && A.top + nb <= A.cap) {
+        if (!in_arena) { in_arena = true; first = A.top; A.live += 1; A.owner = me; }
+        *p = reinterpret_cast<T*>(A.base + A.top);
+        A.top += nb; last = A.top;
+        A.high = std::max(A.high, A.top);
+      } else {
+        e = cudaMalloc((void**)p, nb);
+        if (e != cudaSuccess) return e;
+        owned.push_back(*p);
+        overflow += nb;
+        if (mine) A.wanted = std::max(A.wanted, std::max(A.high, A.top) + overflow + nb);
+      }
     }
     bytes += nb;
     if (zero) e = cudaMemsetAsync(*p, 0, nb, st);
     return e;
   }
-  size_t overflow_total(Arena&) const { return overflow; }
   void release(void* p) {  // individual frees only matter for overflow blocks
     for (auto& q : owned)
       if (q == p) { cudaStreamSynchronize(stream); cudaFree(q); q = nullptr; }
@@ -142,10 +184,11 @@ struct DevPool {
       owned.clear();
     }
     if (in_arena) {
+      std::lock_guard<std::mutex> lk(g_arena_mu);
       Arena& A = *arena;
-      if (A.top == last) A.top = first;  // stack discipline: give the range back
+      if (A.top == last) A.top = first;  // stack discipline inside one owner: give the range back
       A.live -= 1;
-      if (A.live == 0) A.top = 0;
+      if (A.live == 0) { A.top = 0; A.owner = nullptr; }
       in_arena = false;
     }
     bytes = 0; overflow = 0;
@@ -204,6 +247,7 @@ struct hb2_batch {
   int* d_sym_a = nullptr; int* d_sym_b = nullptr; int* d_csc_ptr = nullptr; int* d_csc_ent = nullptr; int* d_ell = nullptr;
   float* d_bmax = nullptr;
   float* d_score = nullptr;
+  float* d_chain = nullptr;  // [2][nc]: sums of squares of u~ and v~ as the reference's BLAS accumulates them
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
   double timing[16] = {0};
@@ -287,11 +331,8 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
 // everything exported and for the enumeration order of the symmetry rows.
 static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref, std::vector<int>& tile_begin,
                        std::vector<int>& tilerow_begin, bool& tile_ok) {
-  static int TH = -1, TW = -1;
-  if (TH < 0) {
-    const char* eh = getenv("HB2_TILE_H"); const char* ew = getenv("HB2_TILE_W");
-    TH = eh ? std::max(1, atoi(eh)) : 8; TW = ew ? std::max(1, atoi(ew)) : 32;
-  }
+  static const int TH = [] { const char* e = getenv("HB2_TILE_H"); return e ? std::max(1, atoi(e)) : 8; }();
+  static const int TW = [] { const char* e = getenv("HB2_TILE_W"); return e ? std::max(1, atoi(e)) : 32; }();
   tile_ok = (long long)TH * TW <= HB2_BLOCK;
   int ymin = 1 << 30, xmin = 1 << 30;
   for (const short2& q : yx_ref) { ymin = std::min<int>(ymin, q.x); xmin = std::min<int>(xmin, q.y); }
@@ -409,6 +450,7 @@ extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int3
   if ((long long)(L3 + 3) * P->ndisk >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many unknowns");
   CK(cudaSetDevice(P->device));
   auto* b = new hb2_batch();
+  b->pool.owner = b;
   b->P = P;
   b->stream = (cudaStream_t)stream;
   cudaStream_t st = b->stream;
@@ -609,7 +651,7 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
     int *d_ucnt, *d_nptr;
     CK(b->pool.alloc(&d_ucnt, (size_t)m + 1, true, st));
     CK(b->pool.alloc(&d_nptr, (size_t)m + 1, false, st));
-    cudaFuncSetAttribute(k_exp_merge<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+    hb2_allow_big_smem((const void*)k_exp_merge<0>);
     k_exp_merge<0><<<m, HB2_MERGE_THREADS, msm, st>>>(m, maxe, d_ptr, d_col, d_w, d_ucnt, nullptr, nullptr, nullptr, nullptr);
     CKL();
     size_t sb6 = 0;
@@ -1058,6 +1100,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(b->pool.alloc(&B.st, nc, true, st));
   CKC(b->pool.alloc(&b->d_bmax, nc, false, st));
   CKC(b->pool.alloc(&b->d_score, nc, true, st));
+  CKC(b->pool.alloc(&b->d_chain, (size_t)2 * nc, true, st));
   CKC(b->pool.alloc(&b->d_nactive, 1, true, st));
   CKC(cudaMallocHost(&b->h_nactive, sizeof(int)));
   {
@@ -1173,6 +1216,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       pr[6 * i + 3] = pairs[i].cj; pr[6 * i + 4] = pairs[i].sj; pr[6 * i + 5] = pairs[i].zj;
     }
     DevPool tmp;
+    tmp.owner = b;
 #define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tmp.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
     CKT(upload(tmp, &Q.pairs, pr, st));
     CKT(upload(tmp, &Q.pair_begin, pair_begin, st));
@@ -1328,7 +1372,7 @@ extern "C" int hb2_batch_rhs(hb2_batch* b, int32_t c, float* out) {
 // ---------------------------------------------------------------------------
 // optional per-launch profiling with CUDA events on the launching stream
 // ---------------------------------------------------------------------------
-enum { KC_FWD_DATA = 0, KC_FWD_SYM = 1, KC_ADJ = 2, KC_UPDATE = 3, KC_SCALAR = 4, KC_N = 5 };
+enum { KC_FWD_DATA = 0, KC_FWD_SYM = 1, KC_ADJ = 2, KC_UPDATE = 3, KC_SCALAR = 4, KC_NORM = 5, KC_N = 6 };
 struct ProfScope {
   hb2_batch* b;
   ProfScope(hb2_batch* b_, int cls) : b(b_) {
@@ -1364,14 +1408,14 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
     const dim3 gb(B.nband, B.nc), gr(b->max_views, B.nc);
 #define FWB(T, Q)                                                                                         \
   do {                                                                                                    \
-    cudaFuncSetAttribute(k_fwd_band<T, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);         \
+    hb2_allow_big_smem((const void*)k_fwd_band<T, Q>);         \
     k_fwd_band<T, Q><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, mode);                                          \
     k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
   } while (0)
 #define FWBQ(T) do { if (B.L3P == 4) FWB(T, 1); else if (B.L3P == 8) FWB(T, 2); else if (B.L3P == 12) FWB(T, 3); else FWB(T, 4); } while (0)
 #define FWB2(Q)                                                                                           \
   do {                                                                                                    \
-    cudaFuncSetAttribute(k_fwd_band2<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);           \
+    hb2_allow_big_smem((const void*)k_fwd_band2<Q>);           \
     k_fwd_band2<Q><<<gb, HB2_FWDB2_THREADS, sm, st>>>(B, mode);                                           \
     k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
   } while (0)
@@ -1409,7 +1453,7 @@ static void launch_adj(hb2_batch* b, int mode) {
     const dim3 gc(B.ntile, B.nc, b->adj_chunks);
 #define ADJTC(K)                                                                                                        \
   do {                                                                                                                  \
-    cudaFuncSetAttribute(k_adj_tile<4, K, float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+    hb2_allow_big_smem((const void*)k_adj_tile<4, K, float, false, true>);   \
     k_adj_tile<4, K, float, false, true><<<gc, HB2_ADJT_THREADS, sm, st>>>(B, TD{}, B.u, nullptr, mode);                \
   } while (0)
     if (B.K == 1) ADJTC(1); else ADJTC(2);
@@ -1420,7 +1464,7 @@ static void launch_adj(hb2_batch* b, int mode) {
     const size_t sm = b->adj_tile_smem;
 #define ADJT(Q, K)                                                                                                   \
   do {                                                                                                               \
-    cudaFuncSetAttribute(k_adj_tile<Q, K, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
+    hb2_allow_big_smem((const void*)k_adj_tile<Q, K, float, false>);      \
     k_adj_tile<Q, K, float, false><<<g, HB2_ADJT_THREADS, sm, st>>>(B, TD{}, B.u, nullptr, mode);                    \
   } while (0)
 #define ADJTQ(K) do { if (B.L3P == 4) ADJT(1, K); else if (B.L3P == 8) ADJT(2, K); else if (B.L3P == 12) ADJT(3, K); else ADJT(4, K); } while (0)
@@ -1501,6 +1545,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   out.assign(nc, TrfState{});
   if (!any) return HB2_OK;
   DevPool tmp;
+  tmp.owner = b;
   TD T{};
 #define CKT2(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tmp.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
   const size_t nv = (size_t)nc * B.npad, nu = (size_t)b->u_total;
@@ -1572,7 +1617,7 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
       const dim3 gt(B.ntile, nc);
 #define ADJT64(Q, K)                                                                                                 \
   do {                                                                                                               \
-    cudaFuncSetAttribute(k_adj_tile<Q, K, double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm64);    \
+    hb2_allow_big_smem((const void*)k_adj_tile<Q, K, double, true>);    \
     k_adj_tile<Q, K, double, true><<<gt, HB2_ADJT_THREADS, sm64, st>>>(B, T, rows, dst, gate);                       \
   } while (0)
 #define ADJT64Q(K) do { if (B.L3P == 4) ADJT64(1, K); else if (B.L3P == 8) ADJT64(2, K); else if (B.L3P == 12) ADJT64(3, K); else ADJT64(4, K); } while (0)
@@ -1672,9 +1717,17 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   CK(cudaMemsetAsync(b->d_nactive, 0, sizeof(int), st));
   long long launches = 0;
   b->extra_launches = 0;
-  k_scal_normb<<<nc, HB2_BLOCK, 0, st>>>(B);
+  // norm_mode 1 (default): ||u||, ||v|| as numpy/OpenBLAS compute them for the reference (k_chain_sumsq); 0: exactly
+  // rounded norms from the kernels' partial sums.  HB2_NORM_MODE overrides (experiments).
+  static const int env_norm = [] { const char* e = getenv("HB2_NORM_MODE"); return e ? atoi(e) : -1; }();
+  const bool chain = (env_norm >= 0 ? env_norm : opt->norm_mode) != 0;
+  float* ch_u = chain ? b->d_chain : nullptr;
+  float* ch_v = chain ? b->d_chain + nc : nullptr;
+  if (chain) { k_chain_sumsq<CHAIN_B><<<nc, 64, 0, st>>>(B, ch_u, MODE_INIT); ++launches; }
+  k_scal_normb<<<nc, HB2_BLOCK, 0, st>>>(B, ch_u);
   launch_adj(b, MODE_INIT);
-  k_scal_init<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_nactive);
+  if (chain) { k_chain_sumsq<CHAIN_V><<<nc, 64, 0, st>>>(B, ch_v, MODE_INIT); ++launches; }
+  k_scal_init<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_nactive, ch_v);
   launch_update(b, MODE_INIT);
   launches += 4;
   CKL();
@@ -1687,9 +1740,11 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     for (int q = 0; q < burst; ++q) {
       launch_fwd_data(b, MODE_LSMR);
       launch_fwd_sym(b, MODE_LSMR);
-      { ProfScope ps(b, KC_SCALAR); k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B); }
+      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_U><<<nc, 64, 0, st>>>(B, ch_u, MODE_LSMR); ++launches; }
+      { ProfScope ps(b, KC_SCALAR); k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B, ch_u); }
       launch_adj(b, MODE_LSMR);
-      { ProfScope ps(b, KC_SCALAR); k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B); }
+      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_V><<<nc, 64, 0, st>>>(B, ch_v, MODE_LSMR); ++launches; }
+      { ProfScope ps(b, KC_SCALAR); k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B, ch_v); }
       launch_update(b, MODE_LSMR);
       { ProfScope ps(b, KC_SCALAR); k_scal_test<<<nc, HB2_BLOCK, 0, st>>>(B, opt->atol, opt->btol, opt->conlim, maxit, opt->fixed_iters, b->d_nactive); }
       launches += 7;
@@ -1736,7 +1791,8 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     for (auto& pr : b->ev_used) {
       float ms = 0;
       cudaEventElapsedTime(&ms, b->ev_pool[pr.second], b->ev_pool[pr.second + 1]);
-      b->timing[5 + pr.first] += ms;
+      if (pr.first == KC_NORM) b->timing[14] += ms;
+      else b->timing[5 + pr.first] += ms;
       if (pr.first == KC_FWD_DATA) b->timing[10] += 1;
       if (pr.first == KC_ADJ) b->timing[11] += 1;
       if (pr.first == KC_UPDATE) b->timing[12] += 1;

@@ -1462,59 +1462,130 @@ __device__ __forceinline__ double reduce_partials_f(const float* p, int n, doubl
   return block_sum_d(s, shd);
 }
 
+// ---------------------------------------------------------------------------
+// numpy.linalg.norm of a float32 vector AS THE REFERENCE EXECUTES IT.  scipy's LSMR calls numpy.linalg.norm(u) /
+// norm(v) on float32 vectors (lsmr.py:239-340); numpy computes sqrt(dot(x, x)) with OpenBLAS sdot, whose x86 AVX-512
+// kernel (OpenBLAS 0.3.30 SkylakeX, fitted bit for bit against numpy in this container, oracle/blas_sdot.py) keeps
+// 64 float32 accumulators: accumulator l adds elements l, l + 64, l + 128, ... one after the other with a fused
+// multiply-add, then folds 64 -> 32 -> 8 -> 4 -> 1.  Sequentially accumulating ~n/64 positive terms in float32 loses
+// the low bits of every late term: the result is BIASED low (measured: -7.6e-6 relative at 6 M elements, -2.2e-5 at
+// 12 M), and LSMR amplifies a 1e-5 error of alpha/beta to ~6e-3 in x within ten iterations.  An exactly rounded norm
+// is therefore NOT what the reference computes at the BASELINE sizes.  What matters is the chain structure (64
+// accumulators, sequential float32 FMA, chain length n/64), not which element sits in which accumulator (measured
+// with the oracle: the same chains over another element order move x by 1e-5...3e-5, an exact norm by 5.8e-3).
+// One CTA of 64 threads per candidate: thread l owns accumulator l and consumes 4 consecutive floats per step
+// (128-bit loads, HB2_CHAIN_U of them in flight per thread); zero padding adds nothing.  All candidates of the batch
+// run concurrently, so the sequential chain costs latency, not throughput.
+// ---------------------------------------------------------------------------
+#define HB2_CHAIN_U 16
+enum { CHAIN_U = 0, CHAIN_V = 1, CHAIN_B = 2 };
+template <int WHICH>
+__global__ void __launch_bounds__(64) k_chain_sumsq(BD B, float* __restrict__ out, int mode) {
+  const int c = blockIdx.x;
+  if (mode == MODE_LSMR && !B.st[c].active) return;
+  const float* p;
+  long long n;
+  if (WHICH == CHAIN_U) { p = B.u + B.cand_uoff[c]; n = (long long)B.cand_mdata[c] + ((B.cand_msym[c] + 3) & ~3); }
+  else if (WHICH == CHAIN_V) { p = B.v + (size_t)c * B.npad; n = B.npad; }
+  else { p = B.b + B.cand_uoff[c]; n = B.cand_mdata[c]; }
+  const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
+  const long long n4 = n >> 2;  // every vector here is a multiple of 4 floats and 16-byte aligned
+  const int lane = threadIdx.x;
+  float acc = 0.f;
+  long long i = lane;
+  for (; i + (long long)64 * (HB2_CHAIN_U - 1) < n4; i += (long long)64 * HB2_CHAIN_U) {
+    float4 t[HB2_CHAIN_U];
+#pragma unroll
+    for (int w = 0; w < HB2_CHAIN_U; ++w) t[w] = __ldcs(p4 + i + 64 * w);
+#pragma unroll
+    for (int w = 0; w < HB2_CHAIN_U; ++w) {
+      acc = __fmaf_rn(t[w].x, t[w].x, acc); acc = __fmaf_rn(t[w].y, t[w].y, acc);
+      acc = __fmaf_rn(t[w].z, t[w].z, acc); acc = __fmaf_rn(t[w].w, t[w].w, acc);
+    }
+  }
+  for (; i < n4; i += 64) {
+    const float4 t = __ldcs(p4 + i);
+    acc = __fmaf_rn(t.x, t.x, acc); acc = __fmaf_rn(t.y, t.y, acc);
+    acc = __fmaf_rn(t.z, t.z, acc); acc = __fmaf_rn(t.w, t.w, acc);
+  }
+  // fold like the sdot kernel: 4 vectors of 16 lanes -> 4 x 8 -> 8 -> 4 -> 1
+  __shared__ float a[64];
+  a[lane] = acc;
+  __syncthreads();
+  if (lane == 0) {
+    float a8[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      float q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) q[k] = fadd_(a[16 * k + l], a[16 * k + l + 8]);
+      a8[l] = fadd_(fadd_(fadd_(q[0], q[1]), q[2]), q[3]);
+    }
+    float h[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) h[l] = fadd_(a8[l], a8[l + 4]);
+    out[c] = fadd_(fadd_(h[0], h[1]), fadd_(h[2], h[3]));
+  }
+}
+
 // phase 0 (init): normb = ||b||
-__global__ void __launch_bounds__(HB2_BLOCK) k_scal_normb(BD B) {
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_normb(BD B, const float* __restrict__ chain) {
   const int c = blockIdx.x;
   __shared__ double shd[HB2_BLOCK / 32];
   const float* bb = B.b + B.cand_uoff[c];
   double s = 0.0;
-  for (int i = threadIdx.x; i < B.cand_mdata[c]; i += HB2_BLOCK) { double t = bb[i]; s += t * t; }
-  s = block_sum_d(s, shd);
+  if (!chain) {
+    for (int i = threadIdx.x; i < B.cand_mdata[c]; i += HB2_BLOCK) { double t = bb[i]; s += t * t; }
+    s = block_sum_d(s, shd);
+  }
   if (threadIdx.x == 0) {
     LsmrState& S = B.st[c];
-    float beta = __fsqrt_rn((float)s);
+    float beta = __fsqrt_rn(chain ? chain[c] : (float)s);
     S.beta = beta; S.normb = beta;
     S.inv_beta = beta > 0.f ? fdiv_(1.f, beta) : 0.f;
     S.alpha = 0.f; S.active = 1; S.skip_adj = 0; S.istop = 0; S.itn = 0;
   }
 }
 // phase 0b: alpha = ||A^T u||, initialise recurrences
-__global__ void __launch_bounds__(HB2_BLOCK) k_scal_init(BD B, int* nactive) {
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_init(BD B, int* nactive, const float* __restrict__ chain) {
   const int c = blockIdx.x;
   __shared__ double shd[HB2_BLOCK / 32];
-  double s = reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
+  double s = chain ? 0.0 : reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
   if (threadIdx.x == 0) {
     LsmrState& S = B.st[c];
-    float alpha = __fsqrt_rn((float)s);
+    float alpha = __fsqrt_rn(chain ? chain[c] : (float)s);
     lsmr_init_(S, alpha, S.beta);
     if (S.active) atomicAdd(nactive, 1);
   }
 }
 // beta = ||u~||
-__global__ void __launch_bounds__(HB2_BLOCK) k_scal_beta(BD B) {
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_beta(BD B, const float* __restrict__ chain) {
   const int c = blockIdx.x;
   __shared__ double shd[HB2_BLOCK / 32];
   LsmrState& S = B.st[c];
   if (!S.active) return;
   const int ntiles = B.fwd_ppv;
-  double s = reduce_partials_f(B.part_u + (size_t)B.cand_view_begin[c] * ntiles, B.cand_view_count[c] * ntiles, shd);
-  s += reduce_partials_f(B.part_us + (size_t)c * B.part_us_per_cand, B.part_us_per_cand, shd);
+  double s = 0.0;
+  if (!chain) {
+    s = reduce_partials_f(B.part_u + (size_t)B.cand_view_begin[c] * ntiles, B.cand_view_count[c] * ntiles, shd);
+    s += reduce_partials_f(B.part_us + (size_t)c * B.part_us_per_cand, B.part_us_per_cand, shd);
+  }
   if (threadIdx.x == 0) {
-    float beta = __fsqrt_rn((float)s);
+    float beta = __fsqrt_rn(chain ? chain[c] : (float)s);
     S.beta = beta;
     if (beta > 0.f) { S.inv_beta = fdiv_(1.f, beta); S.skip_adj = 0; }
     else { S.skip_adj = 1; }
   }
 }
 // alpha = ||v~||, rotations, update coefficients
-__global__ void __launch_bounds__(HB2_BLOCK) k_scal_rot(BD B) {
+__global__ void __launch_bounds__(HB2_BLOCK) k_scal_rot(BD B, const float* __restrict__ chain) {
   const int c = blockIdx.x;
   __shared__ double shd[HB2_BLOCK / 32];
   LsmrState& S = B.st[c];
   if (!S.active) return;
-  double s = reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
+  double s = chain ? 0.0 : reduce_partials_f(B.part_v + (size_t)c * B.part_v_per_cand, B.part_v_per_cand, shd);
   if (threadIdx.x == 0) {
-    float alpha = S.skip_adj ? S.alpha : __fsqrt_rn((float)s);
+    float alpha = S.skip_adj ? S.alpha : __fsqrt_rn(chain ? chain[c] : (float)s);
     lsmr_rotate_(S, alpha, S.beta);
   }
 }

@@ -13,7 +13,7 @@ from .planner import BatchPlan, CandidateSpec
 
 DEFAULT_OPTIONS = dict(
     max_iter=1000, atol=1e-4, btol=1e-4, conlim=1e8, check_every=8, clip_pred=0, trf_max_iter=200, trf_tol=1e-2,
-    fixed_iters=0, profile=0,
+    fixed_iters=0, profile=0, norm_mode=1,
 )
 
 
@@ -151,7 +151,7 @@ class Batch:
         _lib.check(_lib.load().hb2_batch_timing(self._h, _lib.ptr(out)))
         return dict(lsmr_ms=out[0], trf_ms=out[1], score_ms=out[2], launches=int(out[3]), iterations=int(out[4]),
                     fwd_data_ms=out[5], fwd_sym_ms=out[6], adj_ms=out[7], update_ms=out[8], scalar_ms=out[9],
-                    fwd_data_launches=int(out[10]), adj_launches=int(out[11]), update_launches=int(out[12]))
+                    fwd_data_launches=int(out[10]), adj_launches=int(out[11]), update_launches=int(out[12]), norm_ms=out[14])
 
     def trf_trace(self, c):
         out = np.zeros((24, 8), dtype=np.float64)

@@ -42,26 +42,48 @@ class BatchPipeline:
         self._ex = ThreadPoolExecutor(max_workers=1) if pipelined else None
 
     def run(self, prob, L3, chunks):
-        chunks = list(chunks)
-        if not chunks:
-            return
-        make = lambda i: Batch(prob, L3, chunks[i], stream=self.streams[i % 2])  # noqa: E731
-        if not self.pipelined:
-            for i in range(len(chunks)):
-                yield i, make(i)
-            return
-        fut = self._ex.submit(make, 0)
-        for i in range(len(chunks)):
-            batch = fut.result()
-            fut = self._ex.submit(make, i + 1) if i + 1 < len(chunks) else None
+        """Batches of one Problem: ``chunks`` is a list of spec lists."""
+        for i, (_, batch) in enumerate(self.run_items((prob, L3, ch, None) for ch in chunks)):
+            yield i, batch
+
+    def run_items(self, items):
+        """``items`` yields ``(prob, L3, specs, tag)`` lazily -- e.g. pulled from a ``ChunkQueue`` shared by several
+        ranks: the NEXT item is fetched (and its batch built) by the worker thread while the current batch is being
+        solved by the caller.  Yields ``(tag, batch)`` in order."""
+        it = iter(items)
+        streams = self.streams
+        count = [0]
+
+        def make_next():
             try:
-                yield i, batch
+                prob, L3, specs, tag = next(it)
+            except StopIteration:
+                return None
+            i = count[0]
+            count[0] += 1
+            return tag, Batch(prob, L3, specs, stream=streams[i % 2])
+
+        if not self.pipelined:
+            while True:
+                nb = make_next()
+                if nb is None:
+                    return
+                yield nb
+        fut = self._ex.submit(make_next)
+        while True:
+            cur = fut.result()
+            if cur is None:
+                return
+            fut = self._ex.submit(make_next)
+            try:
+                yield cur
             except GeneratorExit:
-                if fut is not None:
-                    try:
-                        fut.result().close()
-                    except Exception:
-                        pass
+                try:
+                    pend = fut.result()
+                    if pend is not None:
+                        pend[1].close()
+                except Exception:
+                    pass
                 raise
 
     def close(self):
@@ -127,6 +149,62 @@ def _periodic(v, lo=-180.0, hi=180.0):
     return tmp + lo if tmp >= 0 else tmp + hi
 
 
+class ChunkQueue:
+    """Dealer of work chunks to ranks (cost-sorted deal / dynamic chunk queue per GPU).
+
+    With an initialised ``torch.distributed`` of world size > 1 the chunks are dealt DYNAMICALLY: one atomic counter in
+    the process group's key-value store (``store.add``; rank 0's TCPStore, host side, a few hundred microseconds per
+    pull) hands out chunk indices in cost-sorted order, so a rank that drew cheap candidates simply takes more of them
+    and no rank waits for another inside a search -- there is NO data-path collective.  Without a process group the
+    deal is static: chunk i of the cost-sorted list goes to rank ``i % world`` (``shard=(rank, world)``).
+    Every rank must create its queues in the same order (the counter key is derived from a per-process sequence)."""
+
+    _seq = 0
+
+    def __init__(self, n_chunks, shard=(0, 1), dist=None):
+        self.n = int(n_chunks)
+        self.rank, self.world = int(shard[0]), int(shard[1])
+        self.store = None
+        self._next = self.rank
+        if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from torch.distributed import distributed_c10d
+
+            self.store = distributed_c10d._get_default_store()
+            self.key = f"hb2_chunk_queue_{ChunkQueue._seq}"
+            ChunkQueue._seq += 1
+
+    def next(self):
+        """Index of the next chunk for this rank, or None when the list is exhausted."""
+        if self.store is not None:
+            i = int(self.store.add(self.key, 1)) - 1
+        else:
+            i = self._next
+            self._next += self.world
+        return i if i < self.n else None
+
+    def __iter__(self):
+        while True:
+            i = self.next()
+            if i is None:
+                return
+            yield i
+
+
+def prepare_image(image, thresh_fraction, reconstruct_diameter, apix):
+    """pipeline.py:276-284: with ``thresh_fraction >= 0`` the background (median of the two image rows just outside the
+    reconstruction diameter) is set to 0, values below ``thresh_fraction * max`` are cut and the maximum is scaled to 1.
+    Returns a new float32 array (the reference mutates its argument)."""
+    data = np.array(image, dtype=np.float32, copy=True)
+    if thresh_fraction >= 0:
+        ny = data.shape[0]
+        nr = min(ny // 2 - 1, int(np.ceil(reconstruct_diameter / 2 / apix) + 1))
+        data -= np.median(data[(ny // 2 - nr, ny // 2 + nr), :])
+        thresh = data.max() * thresh_fraction
+        data = np.clip(data, thresh, None) - thresh
+        data /= np.max(data)
+    return np.ascontiguousarray(data, dtype=np.float32)
+
+
 class GridTask:
     __slots__ = ("ti", "twist", "rise", "csym", "geom", "spec")
 
@@ -160,101 +238,130 @@ def _bytes_per_candidate(n, md, cap):
     return 8 * (md + cap) + 48 * n + 16 * cap + 8 * cap + 32 * (2 * cap + 17) + 16 * n + 12 * (n + 1)
 
 
+def make_chunks(tasks, ndisk_of, batch_candidates=None, mem_budget_bytes=48 << 30, pipelined=True, positive_constraint=-1,
+                interpolation="nn"):
+    """Cut the (twist-major) task list into the chunks that are solved as one batch each, most expensive first.
+
+    Tasks that share a Problem/Batch shape (D2, L2, D3, D3i, s, L3) are grouped; every group is cut into runs of
+    consecutive tasks (whole twist rows: the candidates of a run share most view angles, so their in-plane maps are
+    built once).  Chunks are sorted by an a-priori cost -- unknowns x candidates, i.e. larger L3 (larger rise) first --
+    so that a static round-robin deal is balanced and a dynamic deal ends with the cheap chunks (LPT rule)."""
+    groups = {}
+    for t in tasks:
+        g = t.geom
+        groups.setdefault((g["D2"], g["L2"], g["D3"], g["D3i"], g["s"], g["L3"]), []).append(t)
+    chunks = []
+    for key, tl in groups.items():
+        D2, L2, D3, D3i, s, L3 = key
+        n3 = L3 * ndisk_of(key)
+        for t in tl:
+            target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * t.geom["sym_oversample"]))
+            rise_px = t.rise / t.geom["apix3d"]
+            t.spec = CandidateSpec(t.twist, rise_px, t.csym, target, target,
+                                   positive_rule(positive_constraint, rise_px, t.twist, L3))
+        md_est = int((L3 + L2) / max(min(x.spec.rise_pixel for x in tl), 1e-3) + 3) * L3 * D2
+        cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
+        per_cand = _bytes_per_candidate(n3, md_est, cap_est) * (2 if pipelined else 1)  # two batches resident
+        bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // per_cand)))
+        if interpolation != "nn":
+            bs = 1
+        for i0 in range(0, len(tl), bs):
+            ch = tl[i0:i0 + bs]
+            chunks.append((key, ch, float(n3) * len(ch)))
+    chunks.sort(key=lambda c: -c[2])  # stable: equal-cost chunks keep the grid order
+    return chunks
+
+
 def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=3, tube_diameter=None,
                 tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
                 positive_constraint=-1, thresh_fraction=-1, top_k=10, device=0, stream=None, batch_candidates=None,
                 mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None, pipelined=True,
-                interpolation="nn"):
-    """Solve + score every candidate of the grid on one GPU.
+                interpolation="nn", dist=None):
+    """Solve + score every candidate of the grid on one GPU (or this rank's share of it).
 
     ``interpolation="nn"`` runs batches of candidates through the matrix-free projector; ``"linear"`` (trilinear rows,
     SLR:1403-1510 / 910-1138) runs one candidate at a time on explicit GPU-built rows (engine.ExplicitBatch) -- same
     results contract, lower throughput.
 
-    ``shard=(rank, world)`` keeps tasks ``rank::world`` of every twist-major
-    batch ordering so that several GPUs split the grid without communication.
-    Returns dict(scores[(n_csym,) T, R] (NaN = skipped task), itn, flags, top,
+    Several GPUs split the grid by CHUNKS (batches of consecutive candidates) without any data-path communication:
+    ``shard=(rank, world)`` deals the cost-sorted chunk list round-robin; with ``dist`` (an initialised
+    ``torch.distributed``) the deal is dynamic through ``ChunkQueue`` (an atomic counter).  ``thresh_fraction >= 0``
+    applies the image preparation of ``process_one_task`` (pipeline.py:276-284) and clips the predictions at 0
+    (SLR:502-503).  Returns dict(scores[(n_csym,) T, R] (NaN = not solved here / skipped task), itn, flags, top,
     n_candidates, seconds).
     """
-    image = np.ascontiguousarray(image, dtype=np.float32)
-    ny, nx = image.shape
+    ny, nx = np.asarray(image).shape
+    tube_d = ny * apix if tube_diameter is None else tube_diameter
+    image = prepare_image(image, thresh_fraction, tube_d if 0 < tube_d < ny * apix else ny * apix, apix)
     twists = np.atleast_1d(np.asarray(twists, dtype=np.float64))
     rises = np.atleast_1d(np.asarray(rises, dtype=np.float64))
     tasks, ntot = build_tasks(ny, nx, apix, twists, rises, csyms, reconstruct_length_rise, tube_diameter,
                               tube_diameter_inner, tube_length, target_apix3d, sym_oversample, positive_constraint)
-    rank, world = shard
-    if world > 1:
-        tasks = tasks[rank::world]
     scores = np.full(ntot, np.nan, dtype=np.float32)
     itn = np.zeros(ntot, dtype=np.int32)
     flags = np.zeros(ntot, dtype=np.uint32)
     t0 = time.perf_counter()
-    # group by everything a Problem/Batch must share
-    groups = {}
-    for t in tasks:
-        g = t.geom
-        key = (g["D2"], g["L2"], g["D3"], g["D3i"], g["s"], g["L3"])
-        groups.setdefault(key, []).append(t)
+    probs = {}
+
+    def problem(key):
+        if key not in probs:
+            D2, L2, D3, D3i, s, L3 = key
+            probs[key] = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
+        return probs[key]
+
+    chunks = make_chunks(tasks, lambda key: problem(key).ndisk, batch_candidates, mem_budget_bytes, pipelined,
+                         positive_constraint, interpolation)
+    queue = ChunkQueue(len(chunks), shard=shard, dist=dist)
     top = []
     kernel_ms = 0.0
     launches = 0
-    pipe = BatchPipeline(device=device, pipelined=pipelined)
+    n_mine = 0
+    total = len(tasks)
+    pipe = BatchPipeline(device=device, pipelined=pipelined and interpolation == "nn")
+    batches = None
     try:
-        for (D2, L2, D3, D3i, s, L3), tl in groups.items():
-            prob = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
+        if interpolation == "nn":
+            batches = pipe.run_items((problem(chunks[ci][0]), chunks[ci][0][5], [x.spec for x in chunks[ci][1]], ci)
+                                     for ci in queue)
+        else:
+            batches = ((ci, ExplicitBatch(problem(chunks[ci][0]), chunks[ci][0][5], chunks[ci][1][0].spec,
+                                          interpolation=interpolation)) for ci in queue)
+        for ci, batch in batches:
+            chunk = chunks[ci][1]
             try:
-                n3 = L3 * prob.ndisk
-                for t in tl:
-                    target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * t.geom["sym_oversample"]))
-                    rise_px = t.rise / t.geom["apix3d"]
-                    t.spec = CandidateSpec(t.twist, rise_px, t.csym, target, target,
-                                           positive_rule(positive_constraint, rise_px, t.twist, L3))
-                md_est = int((L3 + L2) / max(min(x.spec.rise_pixel for x in tl), 1e-3) + 3) * L3 * D2
-                cap_est = min(max(x.spec.min_sym_pairs for x in tl) + n3, 64 * n3)
-                per_cand = _bytes_per_candidate(n3, md_est, cap_est) * (2 if pipelined else 1)  # two batches resident
-                bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // per_cand)))
-                if interpolation != "nn":
-                    bs = 1
-                chunks = [tl[i0:i0 + bs] for i0 in range(0, len(tl), bs)]
-                done = 0
-                if interpolation == "nn":
-                    batches = pipe.run(prob, L3, [[x.spec for x in ch] for ch in chunks])
-                else:
-                    batches = ((bi, ExplicitBatch(prob, L3, ch[0].spec, interpolation=interpolation))
-                               for bi, ch in enumerate(chunks))
-                for bi, batch in batches:
-                    chunk = chunks[bi]
-                    try:
-                        res = batch.solve(clip_pred=int(thresh_fraction >= 0))
-                        tm = batch.timing()
-                        kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
-                        launches += tm["launches"]
-                        for c, x in enumerate(chunk):
-                            scores[x.ti] = res[c]["score"]
-                            itn[x.ti] = res[c]["itn"]
-                            flags[x.ti] = res[c]["flags"]
-                        if top_k:
-                            order = np.argsort(-res["score"], kind="stable")[:top_k]
-                            for c in order:
-                                ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
-                                           rise=chunk[c].rise, csym=chunk[c].csym)
-                                if return_x_top:
-                                    ent["rec3d"] = batch.rec3d(int(c))
-                                top.append(ent)
-                            top.sort(key=lambda e: (-e["score"], e["ti"]))
-                            del top[top_k:]
-                    finally:
-                        batch.close()
-                    done += len(chunk)
-                    if progress:
-                        progress(done, len(tl))
+                res = batch.solve(clip_pred=int(thresh_fraction >= 0))
+                tm = batch.timing()
+                kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
+                launches += tm["launches"]
+                for c, x in enumerate(chunk):
+                    scores[x.ti] = res[c]["score"]
+                    itn[x.ti] = res[c]["itn"]
+                    flags[x.ti] = res[c]["flags"]
+                if top_k:
+                    order = np.argsort(-res["score"], kind="stable")[:top_k]
+                    for c in order:
+                        ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
+                                   rise=chunk[c].rise, csym=chunk[c].csym)
+                        if return_x_top:
+                            ent["rec3d"] = batch.rec3d(int(c))
+                        top.append(ent)
+                    top.sort(key=lambda e: (-e["score"], e["ti"]))
+                    del top[top_k:]
             finally:
-                prob.close()
+                batch.close()
+            n_mine += len(chunk)
+            if progress:
+                progress(n_mine, total)
     finally:
+        if batches is not None and hasattr(batches, "close"):
+            batches.close()  # closes a batch the worker thread may still be building, BEFORE the problems go away
         pipe.close()
+        for pr in probs.values():
+            pr.close()
     shape = (len(csyms), len(twists), len(rises))
     out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
-               n_candidates=len(tasks), seconds=time.perf_counter() - t0, kernel_ms=kernel_ms, launches=launches)
+               n_candidates=n_mine, seconds=time.perf_counter() - t0, kernel_ms=kernel_ms, launches=launches,
+               axes=(tuple(int(c) for c in csyms), twists, rises))
     return out
 
 

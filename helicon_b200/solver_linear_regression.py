@@ -208,7 +208,9 @@ def lsq_reconstruct(
     if want_refine and fsc_test:
         _unsupported("refine_tilt_psi_dy_range together with fsc_test")
     if want_refine:
-        # SLR:372-437: solve at the given orientation, then the local Gauss-Newton refinement; keep whichever scores higher
+        # SLR:372-437: solve at the given orientation, then the local Gauss-Newton refinement.  For model "lsq" the
+        # reference's solve_equations returns score=None (SLR:270), so its test `score is None or score_refined > score`
+        # (SLR:424) is always true: the refined solution, its score and _refined_params are ALWAYS adopted.
         kw = dict(csym=csym, tilt_degree=tilt_degree, psi_degree=psi_degree, dy_pixel=dy_pixel,
                   thresh_fraction=thresh_fraction, positive_constraint=positive_constraint,
                   reconstruct_diameter_3d_inner_pixel=reconstruct_diameter_3d_inner_pixel,
@@ -220,18 +222,16 @@ def lsq_reconstruct(
                   verbose=verbose, algorithm=algorithm, refine_tilt_psi_dy_range=None, cpu=cpu, device=device)
         (rec3d, _, _), score = lsq_reconstruct(projection_image, scale2d_to_3d, twist_degree, rise_pixel, **kw)
         r = refine_tilt_psi_dy_range
-        image = np.asarray(projection_image)
-        D2r = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
-        L2r = reconstruct_length_2d_pixel if reconstruct_length_2d_pixel > 0 else image.shape[1]
         tilt_o, psi_o, dy_o, x_ref, score_ref = refine_tilt_psi_dy(
-            projection_image, scale2d_to_3d, twist_degree, rise_pixel, csym, D2r, L2r, reconstruct_diameter_3d_pixel,
+            projection_image, scale2d_to_3d, twist_degree, rise_pixel, csym, reconstruct_diameter_2d_pixel,
+            reconstruct_length_2d_pixel, reconstruct_diameter_3d_pixel,
             reconstruct_diameter_3d_inner_pixel, reconstruct_length_3d_pixel, sym_oversample, interpolation, None,
             tilt_0=0.0, psi_0=0.0, dy_0=0.0, delta_tilt=r.get("delta_tilt", 0.5), delta_psi=r.get("delta_psi", 1.0),
             delta_dy=r.get("delta_dy", 0.2), max_iter=r.get("max_iter", 5),
             bounds_tilt=(-r.get("tilt", 30.0), r.get("tilt", 30.0)), bounds_psi=(-r.get("psi", 45.0), r.get("psi", 45.0)),
             bounds_dy=(-r.get("dy", 5.0), r.get("dy", 5.0)), positive_constraint=positive_constraint,
             algorithm=algorithm, verbose=verbose, cpu=cpu, device=device)
-        if score_ref is not None and (score is None or score_ref > score):
+        if score_ref is not None:
             D3r, L3r = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
             m2 = _disk_mask(D3r, reconstruct_diameter_3d_inner_pixel / 2, D3r // 2 - 1)
             rec3d = np.zeros((L3r, D3r, D3r), dtype=np.float32)
@@ -253,7 +253,9 @@ def lsq_reconstruct(
                          device=device)
     try:
         n3 = L3 * prob.ndisk
-        target = min(MAX_EQUATIONS, int(max(D2 * L2, n3) * sym_oversample))  # SLR:148-150, 168-170
+        # SLR:130, 148-150, 168-170: the reference multiplies the RAW arguments (-1 * -1 = 1 with the defaults)
+        n2 = int(reconstruct_diameter_2d_pixel) * int(reconstruct_length_2d_pixel)
+        target = min(MAX_EQUATIONS, int(max(n2, n3) * sym_oversample))
         positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
         spec = CandidateSpec(twist_degree, rise_pixel, csym, target, target, positive)
         nsets = 3 if fsc_test >= 1 else 1
@@ -377,14 +379,16 @@ def refine_tilt_psi_dy(
     the tolerance (measured against the reference in tests/test_gpu_parity.py).  ``x_init`` is unused, as in the
     reference."""
     image = np.asarray(projection_image)
-    D2, L2 = int(reconstruct_diameter_2d_pixel), int(reconstruct_length_2d_pixel)
+    n2 = int(reconstruct_diameter_2d_pixel) * int(reconstruct_length_2d_pixel)  # SLR:639: raw product (1 with the -1 defaults)
+    D2 = int(reconstruct_diameter_2d_pixel) if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
+    L2 = int(reconstruct_length_2d_pixel) if reconstruct_length_2d_pixel > 0 else image.shape[1]
     D3, L3 = int(reconstruct_diameter_3d_pixel), int(reconstruct_length_3d_pixel)
     t = np.array([tilt_0, psi_0, dy_0], dtype=np.float64)
     deltas = np.array([delta_tilt, delta_psi, delta_dy], dtype=np.float64)
     lo = np.array([bounds_tilt[0], bounds_psi[0], bounds_dy[0]], dtype=np.float64)
     hi = np.array([bounds_tilt[1], bounds_psi[1], bounds_dy[1]], dtype=np.float64)
     # SLR:634-638: the row targets use the FULL grid size D3*D3*L3 here (not the mask count as lsq_reconstruct does)
-    target = min(MAX_EQUATIONS, int(max(D2 * L2, D3 * D3 * L3) * sym_oversample))
+    target = min(MAX_EQUATIONS, int(max(n2, D3 * D3 * L3) * sym_oversample))
     positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
     interp = _interp(interpolation)
     prob = _make_problem(image, scale2d_to_3d, D2, L2, D3, reconstruct_diameter_3d_inner_pixel, device=device)

@@ -100,6 +100,10 @@ typedef struct {
   double trf_tol;          /* tol (SLR:240) = 1e-2 */
   int32_t fixed_iters;     /* >0: run exactly this many LSMR iterations, ignore stop tests (tests only) */
   int32_t profile;         /* 1: bracket every kernel launch with CUDA events (per-kernel-class device time) */
+  int32_t norm_mode;       /* how LSMR's float32 norms ||u||, ||v|| (lsmr.py:239-340, numpy.linalg.norm) are formed:
+                              1 (default) = as the reference EXECUTES them: numpy -> OpenBLAS sdot with 64 sequential
+                              float32 FMA accumulators (biased low by ~1e-5 at 1e7 elements; LSMR amplifies that to
+                              ~6e-3 in x), 0 = exactly rounded */
 } hb2_solve_options;
 
 typedef struct {

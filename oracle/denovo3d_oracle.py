@@ -649,23 +649,39 @@ def _sym_ortho32(a, b):
     return c, s, r
 
 
-def lsmr_mixed(A, b, atol=1e-4, btol=1e-4, conlim=1e8, maxiter=1000, fixed_iters=None, trace=None):
+def lsmr_mixed(A, b, atol=1e-4, btol=1e-4, conlim=1e8, maxiter=1000, fixed_iters=None, trace=None, norm="blas"):
     """scipy ``lsmr`` (lsmr.py:197-480) for float32 CSR ``A`` and float32 ``b``,
     damp=0, x0=None: u,v,h float32; x,hbar float64; scalars float32.  Calls the
     real scipy on the same input give the same iterates up to summation order.
-    ``fixed_iters`` runs exactly that many iterations ignoring stop tests."""
+    ``fixed_iters`` runs exactly that many iterations ignoring stop tests.
+
+    ``norm="blas"`` is what scipy executes: ``numpy.linalg.norm`` of a float32 vector = OpenBLAS ``sdot`` with float32
+    accumulators, whose rounding grows with the vector length (measured here: -7.6e-6 relative at 6 M elements, -2.2e-5
+    at 12 M) and depends on the CPU kernel OpenBLAS dispatches and on its thread count.  ``norm="exact"`` rounds the
+    exactly accumulated (float64) norm to float32 once -- the value scipy's formula MEANS; the difference between the two
+    variants is the reference's own host-dependent float32 BLAS noise, amplified by the Lanczos process."""
     f = np.float32
+    if callable(norm):
+        nrm = norm
+    elif norm == "chain":  # the CUDA kernel's accumulation (oracle/blas_sdot.py:chain_sumsq), for CPU-side checks
+        from oracle.blas_sdot import chain_sumsq
+
+        nrm = lambda q: math.sqrt(float(chain_sumsq(q)))
+    elif norm == "exact":
+        nrm = lambda q: math.sqrt(float(np.dot(q.astype(np.float64), q.astype(np.float64))))
+    else:
+        nrm = np.linalg.norm
     A = A.tocsr()
     AT = A.T.tocsr()
     m, n = A.shape
     u = b.astype(f).copy()
-    normb = f(np.linalg.norm(u))
+    normb = f(nrm(u))
     x = np.zeros(n, np.float64)
     beta = f(normb)
     if beta > 0:
         u = f(1 / beta) * u
         v = AT.dot(u)
-        alpha = f(np.linalg.norm(v))
+        alpha = f(nrm(v))
     else:
         v = np.zeros(n, f)
         alpha = f(0)
@@ -696,12 +712,12 @@ def lsmr_mixed(A, b, atol=1e-4, btol=1e-4, conlim=1e8, maxiter=1000, fixed_iters
             itn += 1
             u *= -alpha
             u += A.dot(v)
-            beta = f(np.linalg.norm(u))
+            beta = f(nrm(u))
             if beta > 0:
                 u *= f(1 / beta)
                 v *= -beta
                 v += AT.dot(u)
-                alpha = f(np.linalg.norm(v))
+                alpha = f(nrm(v))
                 if alpha > 0:
                     v *= f(1 / alpha)
             chat, shat, alphahat = _sym_ortho32(alphabar, 0.0)

@@ -27,7 +27,7 @@ def _fake_local(rank, world, twists, rises):
                  key=lambda e: (-e["score"], e["ti"]))[:5]
     shape = (1, len(twists), len(rises))
     return dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
-                n_candidates=len(mine)), tasks
+                n_candidates=len(mine), axes=((1,), twists, rises)), tasks
 
 
 def _worker(rank, world, port, q):
@@ -42,7 +42,8 @@ def _worker(rank, world, port, q):
     res = D.gather_grid_results(out, top_k=5, dist=dist)
     dist.barrier()
     dist.destroy_process_group()
-    q.put((rank, res["scores"], res["itn"], res["flags"], [(e["score"], e["ti"]) for e in res["top"]], res["n_candidates"]))
+    q.put((rank, res["scores"], res["itn"], res["flags"],
+           [(e["score"], e["ti"], e["twist"], e["rise"], e["csym"]) for e in res["top"]], res["n_candidates"]))
 
 
 def test_two_rank_gather_equals_single_process():
@@ -68,7 +69,8 @@ def test_two_rank_gather_equals_single_process():
         assert np.array_equal(np.isnan(scores), np.isnan(ref["scores"]))
         assert np.array_equal(np.nan_to_num(scores), np.nan_to_num(ref["scores"]))
         assert np.array_equal(itn, ref["itn"]) and np.array_equal(flags, ref["flags"])
-        assert top == [(e["score"], e["ti"]) for e in ref["top"]]
+        # every merged entry carries its parameters (denovo3DBatch reads twist / rise / csym on rank 0)
+        assert top == [(e["score"], e["ti"], e["twist"], e["rise"], e["csym"]) for e in ref["top"]]
         assert ncand == len(tasks)
     # the skipped tasks (|twist| < 0.01) are NaN everywhere
     assert np.isnan(ref["scores"]).sum() == 5
@@ -129,3 +131,70 @@ def test_per_image_search_sharded_by_image_and_gathered():
         assert scores.shape == (5, 1, 2, 3) and np.all(np.isfinite(scores)) and ncand == 30
         for i in range(5):
             assert np.isclose(scores[i].max(), i + 0.05) and best[i][1:] == (-1.0, 5.5, 1)
+
+
+def _queue_worker(rank, world, port, q):
+    import time
+
+    import torch.distributed as dist
+
+    from helicon_b200.grid import ChunkQueue
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    got = []
+    for n in (23, 5):  # two queues in a row (one per search): the counter keys follow the creation order
+        mine = []
+        for i in ChunkQueue(n, shard=(rank, world), dist=dist):
+            mine.append(i)
+            time.sleep(0.002 * (1 + 3 * rank))  # rank 1 is the slow one: it must end up with fewer chunks
+        got.append(mine)
+        dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, got))
+
+
+def test_dynamic_chunk_queue_deals_every_chunk_once():
+    """grid.ChunkQueue under gloo, world size 2: the atomic counter of the process group's store hands every chunk to
+    exactly one rank, in order, and the faster rank takes more of them (SURVEY 8e dynamic deal)."""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_queue_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for qi, n in enumerate((23, 5)):
+        a, b = got[0][qi], got[1][qi]
+        assert sorted(a + b) == list(range(n)) and a == sorted(a) and b == sorted(b)
+    assert len(got[0][0]) > len(got[1][0])
+
+
+def test_static_chunk_deal_without_process_group():
+    from helicon_b200.grid import ChunkQueue
+
+    for world in (1, 2, 3):
+        seen = []
+        for r in range(world):
+            seen += list(ChunkQueue(10, shard=(r, world)))
+        assert sorted(seen) == list(range(10))
+
+
+def test_make_chunks_cost_sorted_and_complete():
+    from helicon_b200.grid import make_chunks
+
+    tasks, ntot = build_tasks(384, 384, 1.3, np.linspace(-30, 30, 5), np.array([21.0, 33.0, 47.0]), csyms=(1, 2))
+    chunks = make_chunks(tasks, lambda key: 1000, batch_candidates=4, positive_constraint=0)
+    assert sorted(t.ti for _, ch, _ in chunks for t in ch) == sorted(t.ti for t in tasks)
+    costs = [c for _, _, c in chunks]
+    assert costs == sorted(costs, reverse=True)
+    for key, ch, _ in chunks:  # one chunk = one batch shape
+        assert len({(t.geom["L3"], t.geom["D3"]) for t in ch}) == 1 and len(ch) <= 4
