@@ -8,3 +8,10 @@ solve+score hot path behind the reference's own Python signatures.
 __version__ = "0.1.0"
 
 from ._lib import HeliconB200Error  # noqa: F401
+
+
+def search_grid(*args, **kwargs):
+    """``helicon_b200.grid.search_grid`` (imported on first use: the grid driver pulls in the CUDA library binding)."""
+    from .grid import search_grid as _search_grid
+
+    return _search_grid(*args, **kwargs)

@@ -101,6 +101,8 @@ EXPORTS = [
     "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize", "hb2_batch_set_ties",
     "hb2_batch_set_pixel_masks", "hb2_batch_add_exact_maps", "hb2_batch_explicit_rows", "hb2_batch_explicit_export", "hb2_batch_explicit_sym_rows",
     "hb2_batch_explicit_sym_export", "hb2_batch_explicit_pixel_mask",
+    "hb2_scoremap_create", "hb2_scoremap_destroy", "hb2_scoremap_device_ptr", "hb2_batch_scatter_scores",
+    "hb2_scoremap_merge", "hb2_scoremap_topk", "hb2_scoremap_read",
 ]
 
 _lib = None
@@ -156,6 +158,15 @@ def load():
     lib.hb2_batch_trf_trace.argtypes = [vp, i32, vp, i32]
     lib.hb2_helical_symmetrize.argtypes = [vp, P(SymmParams), vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, C.c_int, vp]
     lib.hb2_lsmr_scalar_step.argtypes = [vp, C.c_int, C.c_float, C.c_float, f64, f64, f64, f64, C.c_int, P(C.c_float), P(C.c_float), P(C.c_float), vp]
+    lib.hb2_scoremap_create.argtypes = [P(vp), i64, C.c_int]
+    lib.hb2_scoremap_destroy.argtypes = [vp]
+    lib.hb2_scoremap_destroy.restype = None
+    lib.hb2_scoremap_device_ptr.argtypes = [vp]
+    lib.hb2_scoremap_device_ptr.restype = vp
+    lib.hb2_batch_scatter_scores.argtypes = [vp, vp, vp, vp]
+    lib.hb2_scoremap_merge.argtypes = [vp, vp, i32, vp]
+    lib.hb2_scoremap_topk.argtypes = [vp, i32, vp, vp, vp]
+    lib.hb2_scoremap_read.argtypes = [vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 

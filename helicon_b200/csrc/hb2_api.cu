@@ -1721,12 +1721,17 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   // rounded norms from the kernels' partial sums.  HB2_NORM_MODE overrides (experiments).
   static const int env_norm = [] { const char* e = getenv("HB2_NORM_MODE"); return e ? atoi(e) : -1; }();
   const bool chain = (env_norm >= 0 ? env_norm : opt->norm_mode) != 0;
+  if (chain) {
+    hb2_allow_big_smem((const void*)k_chain_sumsq<CHAIN_U>);
+    hb2_allow_big_smem((const void*)k_chain_sumsq<CHAIN_V>);
+    hb2_allow_big_smem((const void*)k_chain_sumsq<CHAIN_B>);
+  }
   float* ch_u = chain ? b->d_chain : nullptr;
   float* ch_v = chain ? b->d_chain + nc : nullptr;
-  if (chain) { k_chain_sumsq<CHAIN_B><<<nc, 64, 0, st>>>(B, ch_u, MODE_INIT); ++launches; }
+  if (chain) { k_chain_sumsq<CHAIN_B><<<nc, 64, HB2_CHAIN_SMEM, st>>>(B, ch_u, MODE_INIT); ++launches; }
   k_scal_normb<<<nc, HB2_BLOCK, 0, st>>>(B, ch_u);
   launch_adj(b, MODE_INIT);
-  if (chain) { k_chain_sumsq<CHAIN_V><<<nc, 64, 0, st>>>(B, ch_v, MODE_INIT); ++launches; }
+  if (chain) { k_chain_sumsq<CHAIN_V><<<nc, 64, HB2_CHAIN_SMEM, st>>>(B, ch_v, MODE_INIT); ++launches; }
   k_scal_init<<<nc, HB2_BLOCK, 0, st>>>(B, b->d_nactive, ch_v);
   launch_update(b, MODE_INIT);
   launches += 4;
@@ -1740,10 +1745,10 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     for (int q = 0; q < burst; ++q) {
       launch_fwd_data(b, MODE_LSMR);
       launch_fwd_sym(b, MODE_LSMR);
-      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_U><<<nc, 64, 0, st>>>(B, ch_u, MODE_LSMR); ++launches; }
+      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_U><<<nc, 64, HB2_CHAIN_SMEM, st>>>(B, ch_u, MODE_LSMR); ++launches; }
       { ProfScope ps(b, KC_SCALAR); k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B, ch_u); }
       launch_adj(b, MODE_LSMR);
-      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_V><<<nc, 64, 0, st>>>(B, ch_v, MODE_LSMR); ++launches; }
+      if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_V><<<nc, 64, HB2_CHAIN_SMEM, st>>>(B, ch_v, MODE_LSMR); ++launches; }
       { ProfScope ps(b, KC_SCALAR); k_scal_rot<<<nc, HB2_BLOCK, 0, st>>>(B, ch_v); }
       launch_update(b, MODE_LSMR);
       { ProfScope ps(b, KC_SCALAR); k_scal_test<<<nc, HB2_BLOCK, 0, st>>>(B, opt->atol, opt->btol, opt->conlim, maxit, opt->fixed_iters, b->d_nactive); }
@@ -1913,5 +1918,182 @@ extern "C" int hb2_helical_symmetrize(const float* data_host, const hb2_symm_par
   CKS(cudaStreamSynchronize(st));
   pool.free_all();
 #undef CKS
+  return HB2_OK;
+}
+
+// ---------------------------------------------------------------------------
+// device-resident score map + top-K of a search (include/helicon_b200.h)
+// ---------------------------------------------------------------------------
+struct hb2_scoremap {
+  int device = 0;
+  long long n = 0;
+  float* d_score = nullptr;  // [n] float32 scores, then [n] int32 iterations, then [n] uint32 flags
+  int* d_itn = nullptr;
+  unsigned* d_flags = nullptr;
+  long long* d_idx = nullptr;  // staging of a batch's task indices (+ flags behind them)
+  size_t idx_cap = 0;
+  float* d_top = nullptr;      // [k] scores + [k] indices (as long long)
+  long long* d_topi = nullptr;
+  int top_cap = 0;
+};
+
+__global__ void k_scoremap_fill(float* __restrict__ sc, int* __restrict__ it, unsigned* __restrict__ fl, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { sc[i] = __int_as_float(0x7fc00000); it[i] = 0; fl[i] = 0u; }
+}
+__global__ void k_scoremap_scatter(const float* __restrict__ score, const LsmrState* __restrict__ st,
+                                   const long long* __restrict__ idx, int nc, long long n, float* __restrict__ sc,
+                                   int* __restrict__ it, unsigned* __restrict__ fl) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const long long t = idx[c];
+  if (t < 0 || t >= n) return;
+  sc[t] = score[c];
+  it[t] = st[c].itn;
+  fl[t] = (unsigned)idx[nc + c];
+}
+// other ranks' maps (an all-gathered buffer of n_maps x [scores | iterations]): a task is owned by at most one rank
+__global__ void k_scoremap_merge(float* __restrict__ sc, int* __restrict__ it, unsigned* __restrict__ fl,
+                                 const float* __restrict__ g, int n_maps, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = sc[i];
+  int q = it[i];
+  unsigned f = fl[i];
+  for (int r = 0; r < n_maps; ++r) {
+    const float v = g[(size_t)r * 3 * n + i];
+    if (v == v && !(s == s)) {
+      s = v;
+      q = reinterpret_cast<const int*>(g)[(size_t)r * 3 * n + n + i];
+      f = reinterpret_cast<const unsigned*>(g)[(size_t)r * 3 * n + 2 * n + i];
+    }
+  }
+  sc[i] = s; it[i] = q; fl[i] = f;
+}
+// K rounds of a CTA-wide arg-max (score descending, lower index wins ties, NaN skipped); entries already selected are
+// excluded by comparing with the previous winner in (score, index) order, so the map itself stays untouched.
+__global__ void __launch_bounds__(1024) k_scoremap_topk(const float* __restrict__ sc, long long n, int k,
+                                                        float* __restrict__ top, long long* __restrict__ topi) {
+  __shared__ float s_v[32];
+  __shared__ long long s_i[32];
+  __shared__ float prev_v;
+  __shared__ long long prev_i;
+  if (threadIdx.x == 0) { prev_v = INFINITY; prev_i = -1; }
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    const float pv = prev_v;
+    const long long pi = prev_i;
+    float bv = -INFINITY;
+    long long bi = -1;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = sc[i];
+      if (!(v == v)) continue;
+      const bool after_prev = pi < 0 || v < pv || (v == pv && i > pi);  // strictly after the previous winner
+      if (!after_prev) continue;
+      if (bi < 0 || v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = bv; s_i[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      bv = threadIdx.x < (blockDim.x >> 5) ? s_v[threadIdx.x] : -INFINITY;
+      bi = threadIdx.x < (blockDim.x >> 5) ? s_i[threadIdx.x] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+      }
+      if (threadIdx.x == 0) { top[r] = bi >= 0 ? bv : __int_as_float(0x7fc00000); topi[r] = bi; prev_v = bv; prev_i = bi >= 0 ? bi : (long long)n; }
+    }
+    __syncthreads();
+  }
+}
+
+extern "C" int hb2_scoremap_create(hb2_scoremap** out, int64_t n, int device) {
+  if (!out || n <= 0) return fail(HB2_ERR_ARG, "bad argument");
+  if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
+  CK(cudaSetDevice(device));
+  auto* m = new hb2_scoremap();
+  m->device = device; m->n = n;
+  if (cudaMalloc((void**)&m->d_score, (size_t)n * 12) != cudaSuccess) { delete m; return fail(HB2_ERR_CUDA, "cudaMalloc of the score map failed"); }
+  m->d_itn = reinterpret_cast<int*>(m->d_score + n);
+  m->d_flags = reinterpret_cast<unsigned*>(m->d_score + 2 * n);
+  k_scoremap_fill<<<cdiv(n, 256), 256>>>(m->d_score, m->d_itn, m->d_flags, n);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = m;
+  return HB2_OK;
+}
+extern "C" void hb2_scoremap_destroy(hb2_scoremap* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  if (m->d_score) cudaFree(m->d_score);
+  if (m->d_idx) cudaFree(m->d_idx);
+  if (m->d_top) cudaFree(m->d_top);
+  if (m->d_topi) cudaFree(m->d_topi);
+  delete m;
+}
+extern "C" void* hb2_scoremap_device_ptr(hb2_scoremap* m) { return m ? (void*)m->d_score : nullptr; }
+extern "C" int hb2_batch_scatter_scores(hb2_batch* b, hb2_scoremap* m, const int64_t* task_index_host,
+                                        const uint32_t* flags_host) {
+  if (!b || !b->solved || !m || !task_index_host || !flags_host) return fail(HB2_ERR_ARG, "bad argument or batch not solved");
+  if (m->device != b->P->device) return fail(HB2_ERR_ARG, "score map and batch live on different devices");
+  CK(cudaSetDevice(m->device));
+  const int nc = b->B.nc;
+  cudaStream_t st = b->stream;
+  if (m->idx_cap < (size_t)2 * nc) {
+    CK(cudaStreamSynchronize(st));
+    if (m->d_idx) cudaFree(m->d_idx);
+    m->idx_cap = std::max<size_t>(2048, (size_t)nc * 4);
+    CK(cudaMalloc((void**)&m->d_idx, m->idx_cap * sizeof(long long)));
+  }
+  std::vector<long long> stage((size_t)2 * nc);
+  for (int c = 0; c < nc; ++c) { stage[c] = task_index_host[c]; stage[nc + c] = flags_host[c]; }
+  CK(cudaMemcpyAsync(m->d_idx, stage.data(), sizeof(long long) * 2 * nc, cudaMemcpyHostToDevice, st));
+  k_scoremap_scatter<<<cdiv(nc, 128), 128, 0, st>>>(b->d_score, b->B.st, m->d_idx, nc, m->n, m->d_score, m->d_itn, m->d_flags);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));  // task_index_host may go away; the staging buffer is shared by the search's batches
+  return HB2_OK;
+}
+extern "C" int hb2_scoremap_merge(hb2_scoremap* m, const void* gathered_dev, int32_t n_maps, void* stream) {
+  if (!m || !gathered_dev || n_maps <= 0) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(m->device));
+  k_scoremap_merge<<<cdiv(m->n, 256), 256, 0, (cudaStream_t)stream>>>(m->d_score, m->d_itn, m->d_flags, (const float*)gathered_dev, n_maps, m->n);
+  CK(cudaGetLastError());
+  return HB2_OK;
+}
+extern "C" int hb2_scoremap_topk(hb2_scoremap* m, int32_t k, float* top_scores_host, int64_t* top_index_host, void* stream) {
+  if (!m || k <= 0 || !top_scores_host || !top_index_host) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->top_cap < k) {
+    if (m->d_top) cudaFree(m->d_top);
+    if (m->d_topi) cudaFree(m->d_topi);
+    CK(cudaMalloc((void**)&m->d_top, sizeof(float) * k));
+    CK(cudaMalloc((void**)&m->d_topi, sizeof(long long) * k));
+    m->top_cap = k;
+  }
+  k_scoremap_topk<<<1, 1024, 0, st>>>(m->d_score, m->n, k, m->d_top, m->d_topi);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(top_scores_host, m->d_top, sizeof(float) * k, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(top_index_host, m->d_topi, sizeof(long long) * k, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return HB2_OK;
+}
+extern "C" int hb2_scoremap_read(hb2_scoremap* m, float* scores_host, int32_t* itn_host, uint32_t* flags_host, void* stream) {
+  if (!m) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(m->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (scores_host) CK(cudaMemcpyAsync(scores_host, m->d_score, sizeof(float) * m->n, cudaMemcpyDeviceToHost, st));
+  if (itn_host) CK(cudaMemcpyAsync(itn_host, m->d_itn, sizeof(int) * m->n, cudaMemcpyDeviceToHost, st));
+  if (flags_host) CK(cudaMemcpyAsync(flags_host, m->d_flags, sizeof(unsigned) * m->n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return HB2_OK;
 }

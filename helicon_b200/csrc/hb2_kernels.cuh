@@ -1473,11 +1473,13 @@ __device__ __forceinline__ double reduce_partials_f(const float* p, int n, doubl
 // is therefore NOT what the reference computes at the BASELINE sizes.  What matters is the chain structure (64
 // accumulators, sequential float32 FMA, chain length n/64), not which element sits in which accumulator (measured
 // with the oracle: the same chains over another element order move x by 1e-5...3e-5, an exact norm by 5.8e-3).
-// One CTA of 64 threads per candidate: thread l owns accumulator l and consumes 4 consecutive floats per step
-// (128-bit loads, HB2_CHAIN_U of them in flight per thread); zero padding adds nothing.  All candidates of the batch
-// run concurrently, so the sequential chain costs latency, not throughput.
+// One CTA of 64 threads per candidate: thread l owns accumulator l and consumes 4 consecutive floats per step; zero
+// padding adds nothing.  All candidates of the batch run concurrently, so the sequential chain costs latency, not
+// throughput; the kernel is a pure HBM stream (TMA bulk copies into a shared-memory ring).
 // ---------------------------------------------------------------------------
-#define HB2_CHAIN_U 16
+#define HB2_CHAIN_STAGES 6
+#define HB2_CHAIN_STAGE_F4 1024   // float4 per stage = 16 KB = 16 steps of the 64 accumulators
+#define HB2_CHAIN_SMEM (HB2_CHAIN_STAGES * HB2_CHAIN_STAGE_F4 * 16)
 enum { CHAIN_U = 0, CHAIN_V = 1, CHAIN_B = 2 };
 template <int WHICH>
 __global__ void __launch_bounds__(64) k_chain_sumsq(BD B, float* __restrict__ out, int mode) {
@@ -1490,26 +1492,53 @@ __global__ void __launch_bounds__(64) k_chain_sumsq(BD B, float* __restrict__ ou
   else { p = B.b + B.cand_uoff[c]; n = B.cand_mdata[c]; }
   const float4* __restrict__ p4 = reinterpret_cast<const float4*>(p);
   const long long n4 = n >> 2;  // every vector here is a multiple of 4 floats and 16-byte aligned
+  // The vector streams through a ring of shared-memory stages filled by TMA bulk copies (one elected thread issues
+  // them, mbarrier transaction counts signal arrival): 5 x 16 KB in flight per CTA keep HBM busy although only two
+  // warps per candidate consume (the chains are sequential by definition).
+  extern __shared__ __align__(128) unsigned char chain_smem[];  // HB2_CHAIN_STAGES x 16 KB (dynamic: > 48 KB)
+  float4 (*ring)[HB2_CHAIN_STAGE_F4] = reinterpret_cast<float4 (*)[HB2_CHAIN_STAGE_F4]>(chain_smem);
+  __shared__ unsigned long long full_bar[HB2_CHAIN_STAGES];
+  __shared__ float a[64];
   const int lane = threadIdx.x;
-  float acc = 0.f;
-  long long i = lane;
-  for (; i + (long long)64 * (HB2_CHAIN_U - 1) < n4; i += (long long)64 * HB2_CHAIN_U) {
-    float4 t[HB2_CHAIN_U];
+  const long long nstage = (n4 + HB2_CHAIN_STAGE_F4 - 1) / HB2_CHAIN_STAGE_F4;
+  if (lane == 0) {
 #pragma unroll
-    for (int w = 0; w < HB2_CHAIN_U; ++w) t[w] = __ldcs(p4 + i + 64 * w);
-#pragma unroll
-    for (int w = 0; w < HB2_CHAIN_U; ++w) {
-      acc = __fmaf_rn(t[w].x, t[w].x, acc); acc = __fmaf_rn(t[w].y, t[w].y, acc);
-      acc = __fmaf_rn(t[w].z, t[w].z, acc); acc = __fmaf_rn(t[w].w, t[w].w, acc);
-    }
+    for (int i = 0; i < HB2_CHAIN_STAGES; ++i) mbar_init(&full_bar[i], 1);
   }
-  for (; i < n4; i += 64) {
-    const float4 t = __ldcs(p4 + i);
-    acc = __fmaf_rn(t.x, t.x, acc); acc = __fmaf_rn(t.y, t.y, acc);
-    acc = __fmaf_rn(t.z, t.z, acc); acc = __fmaf_rn(t.w, t.w, acc);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  auto issue = [&](long long st) {
+    const int buf = (int)(st % HB2_CHAIN_STAGES);
+    const long long lo = st * HB2_CHAIN_STAGE_F4;
+    const unsigned bytes = (unsigned)(min((long long)HB2_CHAIN_STAGE_F4, n4 - lo) * 16);
+    mbar_expect_tx(&full_bar[buf], bytes);
+    bulk_g2s(&ring[buf][0], p4 + lo, bytes, &full_bar[buf]);
+  };
+  if (lane == 0)
+    for (long long st = 0; st < min((long long)HB2_CHAIN_STAGES - 1, nstage); ++st) issue(st);
+  float acc = 0.f;
+  for (long long st = 0; st < nstage; ++st) {
+    const int buf = (int)(st % HB2_CHAIN_STAGES);
+    // refill the stage consumed in the previous round (every thread passed the barrier at its end)
+    if (lane == 0 && st + HB2_CHAIN_STAGES - 1 < nstage) issue(st + HB2_CHAIN_STAGES - 1);
+    mbar_wait(&full_bar[buf], (unsigned)((st / HB2_CHAIN_STAGES) & 1));
+    const int cnt = (int)min((long long)HB2_CHAIN_STAGE_F4, n4 - st * HB2_CHAIN_STAGE_F4);
+    const float4* __restrict__ rb = ring[buf];
+    int i = lane;
+    for (; i + 64 * 3 < cnt; i += 64 * 4) {
+      const float4 t0 = rb[i], t1 = rb[i + 64], t2 = rb[i + 128], t3 = rb[i + 192];
+      acc = __fmaf_rn(t0.x, t0.x, acc); acc = __fmaf_rn(t0.y, t0.y, acc); acc = __fmaf_rn(t0.z, t0.z, acc); acc = __fmaf_rn(t0.w, t0.w, acc);
+      acc = __fmaf_rn(t1.x, t1.x, acc); acc = __fmaf_rn(t1.y, t1.y, acc); acc = __fmaf_rn(t1.z, t1.z, acc); acc = __fmaf_rn(t1.w, t1.w, acc);
+      acc = __fmaf_rn(t2.x, t2.x, acc); acc = __fmaf_rn(t2.y, t2.y, acc); acc = __fmaf_rn(t2.z, t2.z, acc); acc = __fmaf_rn(t2.w, t2.w, acc);
+      acc = __fmaf_rn(t3.x, t3.x, acc); acc = __fmaf_rn(t3.y, t3.y, acc); acc = __fmaf_rn(t3.z, t3.z, acc); acc = __fmaf_rn(t3.w, t3.w, acc);
+    }
+    for (; i < cnt; i += 64) {
+      const float4 t = rb[i];
+      acc = __fmaf_rn(t.x, t.x, acc); acc = __fmaf_rn(t.y, t.y, acc); acc = __fmaf_rn(t.z, t.z, acc); acc = __fmaf_rn(t.w, t.w, acc);
+    }
+    __syncthreads();  // the stage may be overwritten from the next round on
   }
   // fold like the sdot kernel: 4 vectors of 16 lanes -> 4 x 8 -> 8 -> 4 -> 1
-  __shared__ float a[64];
   a[lane] = acc;
   __syncthreads();
   if (lane == 0) {

@@ -105,9 +105,8 @@ def main(argv=None):
                           tube_diameter=args.tube_diameter, tube_diameter_inner=args.tube_diameter_inner,
                           tube_length=args.tube_length, sym_oversample=args.sym_oversample,
                           positive_constraint=args.positive_constraint, top_k=args.top_k, device=local_rank,
-                          shard=(rank, world), return_x_top=args.save_map and world == 1,
-                          interpolation=args.interpolation)
-        out = distributed.gather_grid_results(out, top_k=args.top_k, dist=dist, device="cuda" if dist is not None else "cpu")
+                          shard=(rank, world), return_x_top=args.save_map, interpolation=args.interpolation, dist=dist)
+        # with more than one process the per-rank score maps were all-gathered inside search_grid (one NCCL call)
         if rank != 0:
             continue
         prefix = f"{args.output}_img{i}"
@@ -119,6 +118,22 @@ def main(argv=None):
         if best is not None:
             print(f"image {i}: best twist={best['twist']:.4f} rise={best['rise']:.4f} csym={best['csym']} "
                   f"score={best['score']:.6f} ({report[-1]['n_candidates']} candidates, {out['seconds']:.1f} s)", flush=True)
+        if args.save_map and best is not None and "rec3d" not in best:
+            # the best candidate was solved by another rank: solve it again here (one candidate) for its volume
+            from .grid import build_tasks
+            from .solver_linear_regression import lsq_reconstruct
+
+            t, _ = build_tasks(img.shape[0], img.shape[1], apix, [best["twist"]], [best["rise"]], csyms=(best["csym"],),
+                               reconstruct_length_rise=args.reconstruct_length_rise, tube_diameter=args.tube_diameter,
+                               tube_diameter_inner=args.tube_diameter_inner, tube_length=args.tube_length,
+                               sym_oversample=args.sym_oversample)
+            g = t[0].geom
+            (best["rec3d"], _, _), _ = lsq_reconstruct(
+                img, g["s"], best["twist"], best["rise"] / g["apix3d"], best["csym"],
+                positive_constraint=args.positive_constraint, reconstruct_diameter_3d_inner_pixel=g["D3i"],
+                reconstruct_diameter_2d_pixel=g["D2"], reconstruct_length_2d_pixel=g["L2"],
+                reconstruct_diameter_3d_pixel=g["D3"], reconstruct_length_3d_pixel=g["L3"],
+                sym_oversample=g["sym_oversample"], interpolation=args.interpolation, device=local_rank)
         if args.save_map and best is not None and "rec3d" in best:
             ny, nx = img.shape
             vol = transforms.apply_helical_symmetry(best["rec3d"], apix, best["twist"], best["rise"], csym=best["csym"],

@@ -47,6 +47,57 @@ class Stream:
             pass
 
 
+class ScoreMap:
+    """Device-resident score map + iteration map of one search over ``n`` flat task indices, with the top-K selected
+    by a CUDA kernel (include/helicon_b200.h: hb2_scoremap_*; the reference's host-side collect / sort / top-N of
+    app.py:2482-2539).  ``scatter(batch, task_indices)`` after ``batch.solve()``; ``topk(k)``; ``read()``.
+    ``__cuda_array_interface__`` exposes the 3*n int32 words (float32 scores, int32 iterations, uint32 flags) so that
+    ``torch.as_tensor(score_map, device="cuda")`` is a zero-copy view NCCL can all-gather."""
+
+    def __init__(self, n, device=0):
+        lib = _lib.require_gpu()
+        self.n, self.device = int(n), int(device)
+        self._h = C.c_void_p()
+        _lib.check(lib.hb2_scoremap_create(C.byref(self._h), self.n, self.device))
+        ptr = lib.hb2_scoremap_device_ptr(self._h)
+        self.__cuda_array_interface__ = dict(shape=(3 * self.n,), typestr="<i4", data=(int(ptr), False), version=3)
+
+    def scatter(self, batch, task_indices, flags):
+        idx = np.ascontiguousarray(task_indices, dtype=np.int64)
+        fl = np.ascontiguousarray(flags, dtype=np.uint32)
+        assert len(idx) == batch.nc == len(fl)
+        _lib.check(_lib.load().hb2_batch_scatter_scores(batch._h, self._h, _lib.ptr(idx), _lib.ptr(fl)))
+
+    def merge(self, gathered_ptr, n_maps, stream=None):
+        """Fold ``n_maps`` maps of other ranks (device buffer of n_maps x 3n words, e.g. filled by an all-gather) in."""
+        _lib.check(_lib.load().hb2_scoremap_merge(self._h, C.c_void_p(int(gathered_ptr)), int(n_maps), _stream_handle(stream)))
+
+    def topk(self, k, stream=None):
+        sc = np.zeros(int(k), dtype=np.float32)
+        ix = np.zeros(int(k), dtype=np.int64)
+        _lib.check(_lib.load().hb2_scoremap_topk(self._h, int(k), _lib.ptr(sc), _lib.ptr(ix), _stream_handle(stream)))
+        keep = ix >= 0
+        return sc[keep], ix[keep]
+
+    def read(self, stream=None):
+        sc = np.empty(self.n, dtype=np.float32)
+        it = np.empty(self.n, dtype=np.int32)
+        fl = np.empty(self.n, dtype=np.uint32)
+        _lib.check(_lib.load().hb2_scoremap_read(self._h, _lib.ptr(sc), _lib.ptr(it), _lib.ptr(fl), _stream_handle(stream)))
+        return sc, it, fl
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.load().hb2_scoremap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Problem:
     """Image + the geometry that does not depend on (twist, rise, csym)."""
 

@@ -16,7 +16,7 @@ import numpy as np
 
 from concurrent.futures import ThreadPoolExecutor
 
-from .engine import Batch, ExplicitBatch, Problem, Stream
+from .engine import Batch, ExplicitBatch, Problem, ScoreMap, Stream
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 
 
@@ -285,7 +285,10 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
 
     Several GPUs split the grid by CHUNKS (batches of consecutive candidates) without any data-path communication:
     ``shard=(rank, world)`` deals the cost-sorted chunk list round-robin; with ``dist`` (an initialised
-    ``torch.distributed``) the deal is dynamic through ``ChunkQueue`` (an atomic counter).  ``thresh_fraction >= 0``
+    ``torch.distributed``, NCCL) the deal is dynamic through ``ChunkQueue`` (an atomic counter) and the per-rank score
+    maps are all-gathered ONCE at the end, so every rank returns the whole grid and the global top-K.  The score map,
+    iteration map and top-K selection are device-resident (``engine.ScoreMap``: one scatter kernel per solved batch,
+    one top-K kernel per search).  ``thresh_fraction >= 0``
     applies the image preparation of ``process_one_task`` (pipeline.py:276-284) and clips the predictions at 0
     (SLR:502-503).  Returns dict(scores[(n_csym,) T, R] (NaN = not solved here / skipped task), itn, flags, top,
     n_candidates, seconds).
@@ -297,9 +300,6 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     rises = np.atleast_1d(np.asarray(rises, dtype=np.float64))
     tasks, ntot = build_tasks(ny, nx, apix, twists, rises, csyms, reconstruct_length_rise, tube_diameter,
                               tube_diameter_inner, tube_length, target_apix3d, sym_oversample, positive_constraint)
-    scores = np.full(ntot, np.nan, dtype=np.float32)
-    itn = np.zeros(ntot, dtype=np.int32)
-    flags = np.zeros(ntot, dtype=np.uint32)
     t0 = time.perf_counter()
     probs = {}
 
@@ -312,57 +312,109 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     chunks = make_chunks(tasks, lambda key: problem(key).ndisk, batch_candidates, mem_budget_bytes, pipelined,
                          positive_constraint, interpolation)
     queue = ChunkQueue(len(chunks), shard=shard, dist=dist)
-    top = []
-    kernel_ms = 0.0
-    launches = 0
-    n_mine = 0
-    total = len(tasks)
-    pipe = BatchPipeline(device=device, pipelined=pipelined and interpolation == "nn")
-    batches = None
+    smap = ScoreMap(ntot, device=device)  # score / iteration / flag maps + top-K live on the device
+    top_x = {}
+    done = [0]
+
+    def on_result(chunk, res, batch):
+        done[0] += len(chunk)
+        smap.scatter(batch, [x.ti for x in chunk], res["flags"])
+        if return_x_top and top_k:  # keep the volumes of this batch's best candidates while the batch is alive
+            for c in np.argsort(-res["score"], kind="stable")[:top_k]:
+                top_x[chunk[c].ti] = (float(res[c]["score"]), batch.rec3d(int(c)))
+            if len(top_x) > top_k:
+                for ti in sorted(top_x, key=lambda t: (-top_x[t][0], t))[top_k:]:
+                    del top_x[ti]
+        if progress:
+            progress(done[0], len(tasks))
+
     try:
-        if interpolation == "nn":
-            batches = pipe.run_items((problem(chunks[ci][0]), chunks[ci][0][5], [x.spec for x in chunks[ci][1]], ci)
-                                     for ci in queue)
-        else:
-            batches = ((ci, ExplicitBatch(problem(chunks[ci][0]), chunks[ci][0][5], chunks[ci][1][0].spec,
-                                          interpolation=interpolation)) for ci in queue)
-        for ci, batch in batches:
-            chunk = chunks[ci][1]
-            try:
-                res = batch.solve(clip_pred=int(thresh_fraction >= 0))
-                tm = batch.timing()
-                kernel_ms += tm["lsmr_ms"] + tm["trf_ms"] + tm["score_ms"]
-                launches += tm["launches"]
-                for c, x in enumerate(chunk):
-                    scores[x.ti] = res[c]["score"]
-                    itn[x.ti] = res[c]["itn"]
-                    flags[x.ti] = res[c]["flags"]
-                if top_k:
-                    order = np.argsort(-res["score"], kind="stable")[:top_k]
-                    for c in order:
-                        ent = dict(score=float(res[c]["score"]), ti=chunk[c].ti, twist=chunk[c].twist,
-                                   rise=chunk[c].rise, csym=chunk[c].csym)
-                        if return_x_top:
-                            ent["rec3d"] = batch.rec3d(int(c))
-                        top.append(ent)
-                    top.sort(key=lambda e: (-e["score"], e["ti"]))
-                    del top[top_k:]
-            finally:
-                batch.close()
-            n_mine += len(chunk)
-            if progress:
-                progress(n_mine, total)
+        stats = solve_chunks(chunks, queue, problem, device=device, pipelined=pipelined, interpolation=interpolation,
+                             clip_pred=int(thresh_fraction >= 0), on_result=on_result)
+        n_solved = stats["n_candidates"]
+        if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # the ONLY collective of a search: every rank's maps all-gathered (NCCL), folded and ranked on the device
+            import torch
+
+            world = dist.get_world_size()
+            with torch.cuda.device(device):
+                mine = torch.as_tensor(smap, device=f"cuda:{device}")
+                buf = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+                dist.all_gather_into_tensor(buf, mine)
+                cur = torch.cuda.current_stream()
+                smap.merge(buf.data_ptr(), world, stream=cur)
+                cur.synchronize()
+        scores, itn, flags = smap.read()
+        if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            n_solved = int(np.isfinite(scores).sum())
+        top = []
+        if top_k:
+            axes = (tuple(int(c) for c in csyms), twists, rises)
+            from .distributed import entry_from_index
+
+            tsc, tix = smap.topk(top_k)
+            for sc_, ti in zip(tsc.tolist(), tix.tolist()):
+                ent = entry_from_index(ti, sc_, axes)
+                if ti in top_x:
+                    ent["rec3d"] = top_x[ti][1]
+                top.append(ent)
     finally:
-        if batches is not None and hasattr(batches, "close"):
-            batches.close()  # closes a batch the worker thread may still be building, BEFORE the problems go away
-        pipe.close()
+        smap.close()
         for pr in probs.values():
             pr.close()
     shape = (len(csyms), len(twists), len(rises))
     out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
-               n_candidates=n_mine, seconds=time.perf_counter() - t0, kernel_ms=kernel_ms, launches=launches,
+               n_candidates=n_solved, n_solved_here=stats["n_candidates"], seconds=time.perf_counter() - t0,
+               kernel_ms=stats["kernel_ms"], launches=stats["launches"] + 2 * stats["n_chunks"] + 2,
                axes=(tuple(int(c) for c in csyms), twists, rises))
     return out
+
+
+TIMING_KEYS = ("lsmr_ms", "trf_ms", "score_ms", "fwd_data_ms", "fwd_sym_ms", "adj_ms", "update_ms", "scalar_ms", "norm_ms",
+               "launches", "fwd_data_launches", "adj_launches", "update_launches")
+
+
+def solve_chunks(chunks, queue, problem_of, device=0, pipelined=True, interpolation="nn", clip_pred=0, profile=0,
+                 on_result=None, solve_options=None):
+    """Solve the chunks ``queue`` deals to this rank: ``chunks[i] = (problem key, [GridTask], cost)`` (make_chunks).
+
+    The batch of chunk i+1 is planned and set up by a worker thread (second stream) while chunk i is being solved
+    (BatchPipeline).  ``on_result(chunk_tasks, results, batch)`` is called per solved batch, before it is closed.
+    Returns the summed library timings (``profile=1`` adds the per-kernel-class device times)."""
+    pipe = BatchPipeline(device=device, pipelined=pipelined and interpolation == "nn")
+    stats = dict.fromkeys(TIMING_KEYS, 0.0)
+    stats.update(n_candidates=0, n_chunks=0, itn_sum=0, chunk_ids=[])
+    opts = dict(solve_options or {})
+    batches = None
+    try:
+        if interpolation == "nn":
+            batches = pipe.run_items((problem_of(chunks[ci][0]), chunks[ci][0][5], [x.spec for x in chunks[ci][1]], ci)
+                                     for ci in queue)
+        else:
+            batches = ((ci, ExplicitBatch(problem_of(chunks[ci][0]), chunks[ci][0][5], chunks[ci][1][0].spec,
+                                          interpolation=interpolation)) for ci in queue)
+        for ci, batch in batches:
+            chunk = chunks[ci][1]
+            try:
+                res = batch.solve(clip_pred=clip_pred, profile=int(profile), **opts)
+                tm = batch.timing()
+                for k in TIMING_KEYS:
+                    stats[k] += tm.get(k, 0.0)
+                stats["itn_sum"] += int(res["itn"].sum())
+                if on_result is not None:
+                    on_result(chunk, res, batch)
+            finally:
+                batch.close()
+            stats["n_candidates"] += len(chunk)
+            stats["n_chunks"] += 1
+            stats["chunk_ids"].append(ci)
+    finally:
+        if batches is not None and hasattr(batches, "close"):
+            batches.close()  # closes a batch the worker thread may still be building, BEFORE the problems go away
+        pipe.close()
+    stats["kernel_ms"] = stats["lsmr_ms"] + stats["trf_ms"] + stats["score_ms"]
+    stats["launches"] = int(stats["launches"])
+    return stats
 
 
 def search_images(images, apix, twists, rises, csyms=(1,), shard=(0, 1), dist=None, gather_device="cuda", **kw):

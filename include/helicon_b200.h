@@ -300,6 +300,26 @@ int hb2_helical_symmetrize(const float* data_host, const hb2_symm_params* p, con
                            const double* ent_wk, const double* mats, int32_t n_mats, float* vol_out_host,
                            float* xsum_out, float* ysum_out, float* zsum_out, int device, void* stream);
 
+/* ---- score map + top-K on the device (north-star item 3) -------------------
+ * The grid driver the reference runs on the host (app.py:2482-2539: collect the task results, sort by score, keep the
+ * top N, Z[twist, rise] = score) as device-resident state of ONE search: a float32 score map, an int32 iteration map
+ * and a uint32 flag map over the flat task index (csym, twist, rise), NaN / 0 where a task was skipped or is solved by
+ * another rank.
+ * hb2_batch_scatter_scores writes the scores of a SOLVED batch into the map (one kernel on the batch's stream, no host
+ * round trip per batch); hb2_scoremap_merge folds the maps of other ranks in (the buffer an NCCL all-gather filled:
+ * n_maps maps of 3*n words back to back, device memory); hb2_scoremap_topk selects the K best (score descending, ties by
+ * the lower task index = the reference's stable sort over its twist-major task list; NaN never selected). */
+typedef struct hb2_scoremap hb2_scoremap;
+int hb2_scoremap_create(hb2_scoremap** out, int64_t n, int device);
+void hb2_scoremap_destroy(hb2_scoremap* m);
+/* device pointer of the maps (float32[n] scores, int32[n] iterations, uint32[n] flags, contiguous: 3*n 4-byte words) */
+void* hb2_scoremap_device_ptr(hb2_scoremap* m);
+/* task_index_host[n_cand], flags_host[n_cand] (hb2_result.flags of the batch's solve) */
+int hb2_batch_scatter_scores(hb2_batch* b, hb2_scoremap* m, const int64_t* task_index_host, const uint32_t* flags_host);
+int hb2_scoremap_merge(hb2_scoremap* m, const void* gathered_dev, int32_t n_maps, void* stream);
+int hb2_scoremap_topk(hb2_scoremap* m, int32_t k, float* top_scores_host, int64_t* top_index_host, void* stream);
+int hb2_scoremap_read(hb2_scoremap* m, float* scores_host, int32_t* itn_host, uint32_t* flags_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,34 @@
+"""Copy recipe for the real reference as the CPU arm (test / bench infrastructure only).
+
+helicon is pure Python, so "building" the reference for this path means making its package importable where
+/root/reference does not exist (the GPU box): this script copies the UNMODIFIED package tree
+/root/reference/src/helicon -> oracle/_ref/helicon.  oracle/_ref/ is git-ignored (no reference source enters the
+history) but NOT gpurun-ignored, so it travels with the snapshot like the built .so files.  bench.py --impl reference and
+bench.py's cpu_baseline leg import it from there (kind "reference"); when it is absent they fall back to the oracle port
+(kind "port").  Nothing under helicon_b200/ imports it.
+
+Usage: python oracle/build_ref.py        (run by __graft_entry__.build() when /root/reference is present)
+"""
+import os
+import shutil
+import sys
+
+SRC = "/root/reference/src/helicon"
+DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "helicon")
+
+
+def build_ref(force=False):
+    if not os.path.isdir(SRC):
+        return os.path.isdir(DST)
+    if os.path.isdir(DST) and not force:
+        return True
+    if os.path.isdir(DST):
+        shutil.rmtree(DST)
+    os.makedirs(os.path.dirname(DST), exist_ok=True)
+    shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+    return True
+
+
+if __name__ == "__main__":
+    ok = build_ref(force="--force" in sys.argv)
+    print("oracle/_ref/helicon", "present" if ok else "absent (no /root/reference here)")

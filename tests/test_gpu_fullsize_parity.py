@@ -115,3 +115,44 @@ def test_full_size_fixed_iterations_vs_oracle(name, norm_mode):
     finally:
         batch.close()
         prob.close()
+
+
+def test_bounded_path_statistics_vs_reference_band():
+    """The reference-default (bounded TRF) path over a seeded sample of 16 cfg2 grid candidates
+    (oracle/make_golden_bounded_band.py: the unmodified reference's builders + its scipy call, once in its own row order
+    = run 0, once with the rows permuted = run 1).  The LSMR stage must stop where the reference stops (+-2); the final
+    scores are compared as a DISTRIBUTION: the CUDA path may leave run 0 no more often / no further than the
+    reference's own run 1 does (its TRF exit is a discontinuous decision, see the golden script's docstring)."""
+    from helicon_b200.engine import Batch, Problem
+    from helicon_b200.grid import derive_geometry
+    from helicon_b200.planner import MAX_EQUATIONS, CandidateSpec
+    import bench
+
+    d = load("bounded_band_cfg2")
+    cand, rows = d["cand"], d["rows"]          # rows[i, run] = [lsmr itn, trf nit, score]
+    N, apix = 256, 1.3
+    img = bench.synthetic_filament(n=N)
+    g = derive_geometry(N, N, apix, 4.75, 4.75, N * apix, 0.0, N * apix, 3 * 4.75, apix, 0, -1)
+    prob = Problem(img, 1.0, g["D2"], g["L2"], g["D3"], 0.0, g["D3"] // 2 - 1)
+    n3 = g["L3"] * prob.ndisk
+    target = min(MAX_EQUATIONS, int(max(g["D2"] * g["L2"], n3) * g["sym_oversample"]))
+    batch = Batch(prob, g["L3"], [CandidateSpec(float(t), float(r) / apix, 1, target, target, True) for t, r in cand])
+    try:
+        res = batch.solve()
+    finally:
+        batch.close()
+        prob.close()
+    d_gpu = np.abs(res["score"].astype(np.float64) - rows[:, 0, 2])
+    d_ref = np.abs(rows[:, 1, 2] - rows[:, 0, 2])
+    ditn = np.abs(res["itn"] - rows[:, 0, 0])
+    for i in range(len(cand)):
+        print(f"twist {cand[i][0]:8.4f} rise {cand[i][1]:.4f}: itn gpu {int(res['itn'][i])} ref {int(rows[i, 0, 0])}/{int(rows[i, 1, 0])} "
+              f"trf gpu {int(res['trf_nit'][i])} ref {int(rows[i, 0, 1])}/{int(rows[i, 1, 1])} |dscore| gpu {d_gpu[i]:.2e} "
+              f"reference's own {d_ref[i]:.2e}")
+    print(f"median |dscore|: gpu {np.median(d_gpu):.2e}, reference's own {np.median(d_ref):.2e}; "
+          f"within 1e-5: gpu {int((d_gpu <= 1e-5).sum())}/16, reference {int((d_ref <= 1e-5).sum())}/16; "
+          f"max: gpu {d_gpu.max():.2e}, reference {d_ref.max():.2e}")
+    assert np.all(ditn <= 2)
+    assert np.median(d_gpu) <= max(1e-5, 2 * np.median(d_ref))
+    assert (d_gpu <= 1e-5).sum() >= (d_ref <= 1e-5).sum() - 3
+    assert d_gpu.max() <= max(5e-2, 2 * d_ref.max())
