@@ -236,6 +236,7 @@ struct hb2_batch {
   std::vector<long long> h_uoff, h_symoff, h_symcap, h_cscoff;
   std::vector<int> tie_per_angle;
   std::vector<int> h_view_angle;
+  std::vector<double> h_cs;  // (cos, sin) of every unique angle (incl. the exact per-column maps)
   std::vector<uint32_t> cand_flags;
   long long u_total = 0;
   // device (non-const views of BD members)
@@ -466,6 +467,7 @@ extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int3
 #define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_); b->pool.free_all(); delete b; return fail(HB2_ERR_CUDA, m_); } } while (0)
   CKB(b->pool.alloc(&b->d_cs, (size_t)2 * nA, false, st));
   CKB(cudaMemcpyAsync(b->d_cs, cos_sin, sizeof(double) * 2 * nA, cudaMemcpyHostToDevice, st));
+  b->h_cs.assign(cos_sin, cos_sin + 2 * (size_t)nA);
   if (b->idx16) { uint16_t* p; CKB(b->pool.alloc(&p, ns, false, st)); b->d_fmap = p; }
   else { uint32_t* p; CKB(b->pool.alloc(&p, ns, false, st)); b->d_fmap = p; }
   CKB(b->pool.alloc(&b->d_rayvalid, (size_t)nA * g.D2, true, st));
@@ -510,6 +512,7 @@ extern "C" int hb2_batch_add_exact_maps(hb2_batch* b, int32_t nE, const double* 
   CK(b->pool.alloc(&d_x0, (size_t)nE * D2, false, st));
   CK(cudaMemcpyAsync(cs2, b->d_cs, sizeof(double) * 2 * nA, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(cs2 + 2 * nA, cos_sin, sizeof(double) * 2 * nE, cudaMemcpyHostToDevice, st));
+  b->h_cs.insert(b->h_cs.end(), cos_sin, cos_sin + 2 * (size_t)nE);
   CK(cudaMemcpyAsync(fm2, b->d_fmap, (size_t)nA * per * esz, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(rv2, b->d_rayvalid, (size_t)nA * D2, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(tie2, b->d_tie, sizeof(int) * nA, cudaMemcpyDeviceToDevice, st));
@@ -1031,6 +1034,14 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   CKC(upload(b->pool, &B.cand_symoff, b->h_symoff, st));
   CKC(upload(b->pool, &B.cand_cscoff, b->h_cscoff, st));
   CKC(b->pool.alloc(&B.cand_msym, nc, true, st));
+  {  // depth-sample range of every ray (all maps incl. the exact per-column ones are final here)
+    ushort2* rr;
+    CKC(b->pool.alloc(&rr, (size_t)B.nA * B.D2, false, st));
+    const unsigned gr = cdiv((long long)B.nA * B.D2 * 32, HB2_BLOCK);
+    if (b->idx16) k_ray_range<uint16_t><<<gr, HB2_BLOCK, 0, st>>>(B.nA, B.D2, (const uint16_t*)B.fmap, rr);
+    else k_ray_range<uint32_t><<<gr, HB2_BLOCK, 0, st>>>(B.nA, B.D2, (const uint32_t*)B.fmap, rr);
+    B.rayrange = rr;
+  }
   // ---- adjoint maps --------------------------------------------------------
   {
     int* d_kmax; unsigned long long *d_h1, *d_h2;
@@ -1429,8 +1440,15 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   }
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   unsigned grid = (unsigned)b->nviews * ntiles;
-  if (b->idx16) k_fwd_data<uint16_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
-  else k_fwd_data<uint32_t><<<grid, HB2_BLOCK, 0, st>>>(B, mode);
+#define FWD(T)                                                                              \
+  do {                                                                                      \
+    if (B.L3P == 4) k_fwd_data<T, 1><<<grid, HB2_BLOCK, 0, st>>>(B, mode);                  \
+    else if (B.L3P == 8) k_fwd_data<T, 2><<<grid, HB2_BLOCK, 0, st>>>(B, mode);             \
+    else if (B.L3P == 12) k_fwd_data<T, 3><<<grid, HB2_BLOCK, 0, st>>>(B, mode);            \
+    else k_fwd_data<T, 4><<<grid, HB2_BLOCK, 0, st>>>(B, mode);                             \
+  } while (0)
+  if (b->idx16) FWD(uint16_t); else FWD(uint32_t);
+#undef FWD
 }
 static void launch_fwd_sym(hb2_batch* b, int mode) {
   ProfScope ps(b, KC_FWD_SYM);

@@ -25,6 +25,7 @@ struct BD {
   // in-plane maps
   const void* fmap;            // [nA][D2][D2] disk rank or SENT
   const uint8_t* rayvalid;     // [nA][D2]
+  const ushort2* rayrange;     // [nA][D2] depth samples [ilo, ihi) of ray j that land inside the disk
   const uint16_t* amap;        // [nA][K][apitch] ray j of the k-th sample landing in voxel p, or 0xFFFF
   int apitch;                  // row pitch of amap = ntile*256: every voxel tile owns a 512-byte aligned run of 256 slots
   const int* aslot;            // [ndisk] slot of voxel p in an amap row (tile*256 + rank inside the tile)
@@ -590,8 +591,35 @@ __global__ void k_ell_fill(BD B, int* __restrict__ ell) {
 // ===========================================================================
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// Sample range of every ray: [ilo, ihi) bounds the depth samples of ray j that land inside the disk (the map row is
+// SENT outside).  One warp per (angle, ray).
 template <typename IdxT>
+__global__ void __launch_bounds__(HB2_BLOCK) k_ray_range(int nA, int D2, const IdxT* __restrict__ fmap, ushort2* __restrict__ rr) {
+  const long long w = ((long long)blockIdx.x * HB2_BLOCK + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)nA * D2) return;
+  const IdxT* __restrict__ fj = fmap + (size_t)w * D2;
+  int lo = D2, hi = 0;
+  for (int i = lane; i < D2; i += 32)
+    if (fj[i] != Sent<IdxT>::v) { lo = min(lo, i); hi = max(hi, i + 1); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) rr[w] = make_ushort2((unsigned short)min(lo, hi), (unsigned short)hi);
+}
+
+// Lanes of a warp = SG sample groups x NQL slice quads (lane = sg * NQL + q): the NQL lanes of a sample read the
+// 16 * NQL contiguous bytes of its voxel record, consecutive sample groups read consecutive samples of the ray, i.e.
+// mostly neighbouring voxels of a tile row.  NQL = L3P / 4 for L3P <= 16, so no lane idles on a slice quad that does
+// not exist (L3P = 12: 10 x 3 lanes busy instead of 8 x 3 of 8 x 4; profiles/r2_summary.md); larger L3P run in
+// passes of 4 quads.
+template <typename IdxT, int NQL>
 __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
+  constexpr int SG = 32 / NQL;      // sample groups: 32, 16, 10, 8
+  constexpr int NACT = SG * NQL;    // busy lanes
+  constexpr int UN = NQL >= 3 ? HB2_FWD_U : (NQL == 2 ? 6 : 4);  // samples in flight per lane
   const int ntiles = (B.D2 + HB2_TILE_RAYS - 1) / HB2_TILE_RAYS;
   const int view = blockIdx.x / ntiles, tile = blockIdx.x % ntiles;
   const int c = B.view_cand[view];
@@ -627,7 +655,8 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
   float* urow = B.u + B.view_uoff[view];
   const float* brow = B.b + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = lane & 3, sg = lane >> 2;
+  const int sg = lane / NQL, q = lane - sg * NQL;
+  const bool lane_on = lane < NACT;
   const uint8_t* __restrict__ pm = cand_mask(B, c);
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   for (int r = warp; r < HB2_TILE_RAYS; r += HB2_BLOCK / 32) {
@@ -635,38 +664,44 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
     if (j >= D2) break;
     if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
     const IdxT* __restrict__ fj = fm + (size_t)j * D2;
-    for (int z0 = 0; z0 < L3P; z0 += 16) {
+    const ushort2 rng = B.rayrange[(size_t)a * D2 + j];
+    const int ilo = rng.x, ihi = rng.y;
+    for (int z0 = 0; z0 < L3P; z0 += 4 * NQL) {
       const int zq = z0 + 4 * q;  // this lane's 4 slices
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (zq < L3P) {
+      if (lane_on && zq < L3P) {
         const float* __restrict__ vb = vsrc + zq;
-        // HB2_FWD_U map entries, then their gathers, are issued before the first add (independent loads in flight);
+        // UN map entries, then their gathers, are issued before the first add (independent loads in flight);
         // the additions keep the sample order.
-        for (int i0 = sg; i0 < D2; i0 += 8 * HB2_FWD_U) {
-          IdxT ids[HB2_FWD_U];
+        for (int i0 = ilo + sg; i0 < ihi; i0 += SG * UN) {
+          IdxT ids[UN];
 #pragma unroll
-          for (int w = 0; w < HB2_FWD_U; ++w) ids[w] = (i0 + 8 * w < D2) ? fj[i0 + 8 * w] : Sent<IdxT>::v;
-          float4 tt[HB2_FWD_U];
+          for (int w = 0; w < UN; ++w) ids[w] = (i0 + SG * w < ihi) ? fj[i0 + SG * w] : Sent<IdxT>::v;
+          float4 tt[UN];
 #pragma unroll
-          for (int w = 0; w < HB2_FWD_U; ++w)
+          for (int w = 0; w < UN; ++w)
             tt[w] = ids[w] != Sent<IdxT>::v ? ldg4(vb + (size_t)ids[w] * L3P) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int w = 0; w < HB2_FWD_U; ++w)
+          for (int w = 0; w < UN; ++w)
             if (ids[w] != Sent<IdxT>::v) { acc.x += tt[w].x; acc.y += tt[w].y; acc.z += tt[w].z; acc.w += tt[w].w; }
         }
       }
+      // fold the sample groups (fixed tree: deterministic): after the loop lane q (sg = 0) holds quad q's 4 sums
 #pragma unroll
-      for (int o = 4; o < 32; o <<= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+      for (int s2 = (SG > 16 ? 16 : (SG > 8 ? 8 : (SG > 4 ? 4 : 2))); s2 >= 1; s2 >>= 1) {
+        const float4 o = make_float4(__shfl_down_sync(0xffffffffu, acc.x, s2 * NQL), __shfl_down_sync(0xffffffffu, acc.y, s2 * NQL),
+                                     __shfl_down_sync(0xffffffffu, acc.z, s2 * NQL), __shfl_down_sync(0xffffffffu, acc.w, s2 * NQL));
+        if (sg < s2 && sg + s2 < SG && lane_on) { acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
       }
-      // every lane of a quad now holds the quad's 4 slice sums; lane (sg = t, q) finishes slice z = zq + t
-      if (sg < 4) {
-        const int z = zq + sg;
+      // lane t < 4 * NQL finishes slice z0 + t: component t & 3 of lane t >> 2
+      const int src_lane = (lane >> 2) < NQL ? (lane >> 2) : 0;
+      const float c0 = __shfl_sync(0xffffffffu, acc.x, src_lane), c1 = __shfl_sync(0xffffffffu, acc.y, src_lane);
+      const float c2 = __shfl_sync(0xffffffffu, acc.z, src_lane), c3 = __shfl_sync(0xffffffffu, acc.w, src_lane);
+      if (lane < 4 * NQL) {
+        const int z = z0 + lane;
         if (z < L3) {
-          const float sum = sg == 0 ? acc.x : (sg == 1 ? acc.y : (sg == 2 ? acc.z : acc.w));
+          const int t = lane & 3;
+          const float sum = t == 0 ? c0 : (t == 1 ? c1 : (t == 2 ? c2 : c3));
           for (int mc = 0; mc < MC; ++mc) {
             const int zm = z * MC + mc;
             if (s_colk[zm] < 0) continue;

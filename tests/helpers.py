@@ -55,3 +55,21 @@ def cases(kind, interpolation=None):
         if v["kind"] == kind and (interpolation is None or v["interpolation"] == interpolation):
             out.append(k)
     return sorted(out)
+
+
+def oracle_permutation_floor(details, nperm=3):
+    """The oracle's (= the reference's scipy call's) own reproducibility at its stopping point: the same equations in
+    permuted row order (same maths, other float32 summation order) -> max rel-L2 change of x."""
+    from scipy.optimize import lsq_linear
+    from scipy.sparse import vstack
+
+    A_d, b_d, A_s, x0 = details["A_data"], details["b_data"], details["A_hsym"], details["x"]
+    A = vstack((A_d, A_s)).tocsr() if A_s is not None else A_d.tocsr()
+    b = np.concatenate((b_d, np.zeros(A.shape[0] - len(b_d), np.float32)))
+    lb, ub = (0.0, float(np.max(b_d))) if details["positive"] else (-np.inf, np.inf)
+    floor = 0.0
+    for seed in range(nperm):
+        p = np.random.default_rng(seed).permutation(A.shape[0])
+        x = lsq_linear(A[p].tocsr(), b[p], bounds=(lb, ub), tol=1e-2, max_iter=200, lsmr_maxiter=1000, lsmr_tol="auto").x
+        floor = max(floor, float(np.linalg.norm(x.astype(np.float32) - x0) / np.linalg.norm(x0)))
+    return floor

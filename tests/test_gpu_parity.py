@@ -15,7 +15,7 @@ import pytest
 from scipy.sparse import vstack
 
 from oracle import denovo3d_oracle as O
-from tests.helpers import cases, csr_equal, csr_from, load
+from tests.helpers import cases, csr_equal, csr_from, load, oracle_permutation_floor  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -166,8 +166,17 @@ def test_unbounded_solve_vs_reference_golden(solver, name):
     if info["res"]["flags"] & 3:  # tie-flagged geometry: a few samples may land in a neighbouring voxel
         assert dscore <= 2e-4
     else:
+        # the bound on x is tied to the reference's OWN reproducibility at its stopping point, measured here: the same
+        # equations in permuted row order through the same scipy call (north star 1e-4 where it allows)
+        _, _, det = O.lsq_reconstruct(
+            img, 1.0, float(twist), float(rise / apix), int(csym), positive_constraint=int(pc),
+            reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N, reconstruct_diameter_3d_pixel=N,
+            reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so), interpolation="nn", return_details=True,
+            fast=not name.endswith("tie475"))
+        floor = oracle_permutation_floor(det)
+        print(f"{name}: the reference's own row-permutation floor at the stopping point: {floor:.2e}")
         assert dscore <= 1e-5
-        assert rel < 5e-3
+        assert rel <= max(1e-4, 4 * floor)
 
 
 @pytest.mark.parametrize("name", ["solve_nn_unb_48_t35"])
@@ -612,11 +621,15 @@ def test_nonsquare_image_with_cropped_region_vs_oracle(solver, interp, tilt):
         skw = dict(scale2d_to_3d=1.0, twist_degree=17.3, rise_pixel=2.9, csym=2, positive_constraint=0,
                    reconstruct_diameter_3d_inner_pixel=6, reconstruct_diameter_2d_pixel=32, reconstruct_length_2d_pixel=48,
                    reconstruct_diameter_3d_pixel=32, reconstruct_length_3d_pixel=8, sym_oversample=2, interpolation="nn")
+        from tests.helpers import oracle_permutation_floor
+
         (rec, _, _), score = solver.lsq_reconstruct(img, **skw)
-        (rec_o, _, _), score_o = O.lsq_reconstruct(img, **skw)
+        (rec_o, _, _), score_o, det = O.lsq_reconstruct(img, return_details=True, **skw)
         rel = float(np.linalg.norm(rec - rec_o) / np.linalg.norm(rec_o))
-        print(f"non-square solve: score {float(score):.7f} vs {float(score_o):.7f}, rel-L2 {rel:.2e}")
-        assert abs(float(score) - float(score_o)) <= 1e-5 and rel < 5e-3
+        floor = oracle_permutation_floor(det)
+        print(f"non-square solve: score {float(score):.7f} vs {float(score_o):.7f}, rel-L2 {rel:.2e} "
+              f"(the oracle's own row-permutation floor {floor:.2e})")
+        assert abs(float(score) - float(score_o)) <= 1e-5 and rel <= max(1e-4, 4 * floor)
 
 
 def test_threaded_lsq_reconstruct_equals_serial(solver):
