@@ -7,9 +7,9 @@ products through ``helicon_b200.transforms`` -- both on the GPU.
 Host side (once per task, not per voxel): image preparation and the integer geometry
 (pipeline.py:180-349), restated line for line.  What needs packages the reference
 itself imports lazily and that are outside the hot path raises ``NotImplementedError``
-with the option's name: ``denoise`` / ``horizontalize`` / automatic tube diameter /
-``target_apix2d > apix2d_orig`` (scikit-image), and -- like the solver drop-in --
-tilt/psi/dy other than 0 and their refinement ranges.
+with the option's name: ``denoise`` / ``horizontalize`` / automatic tube diameter (scikit-image
+restoration / radon based).  ``target_apix2d > apix2d_orig`` is served by a restatement of the scikit-image rescale
+call (``imageprep.down_scale``); tilted / refined tasks resample the display volume with ``transforms.transform_map``.
 """
 
 from __future__ import annotations
@@ -136,9 +136,10 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
                                  round(np.tan(np.deg2rad(np.max(np.abs(tilt_range)))) * tube_diameter * 3))
     if target_apix2d < apix2d_orig:
         target_apix2d = apix2d_orig
-    if target_apix2d != apix2d_orig:
-        _unsupported("image down-scaling (target_apix2d > apix2d_orig, scikit-image rescale); pass an image already at "
-                     "the target pixel size")
+    if target_apix2d != apix2d_orig:  # pipeline.py:268-275
+        from .imageprep import down_scale
+
+        data = np.ascontiguousarray(down_scale(data, target_apix=target_apix2d, apix_orig=apix2d_orig), dtype=np.float32)
     ny, nx = data.shape
     if thresh_fraction >= 0:  # pipeline.py:276-284 (modifies the caller's array in place, as the reference does)
         data_orig = data
@@ -179,11 +180,6 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
             sym_oversample = max(1, int(round(ratio / 100)) * 100)
         if return_3d:
             sym_oversample *= 2
-    if tilt != 0 or psi != 0 or dy != 0:
-        # the solve itself handles a tilted candidate (explicit rows), but the display products then go through
-        # helicon.transform_map (pipeline.py:436-438, scipy.ndimage affine resampling), which is not on the CUDA path
-        _unsupported("tilt/psi/dy != 0 in process_one_task (transform_map of the display volume); "
-                     "solver_linear_regression.lsq_reconstruct accepts them")
     # ---- solve + score (pipeline.py:351-404) on the GPU -------------------------------------------------------------
     refine_range = None
     if algorithm.get("model", "lsq") in ("lsq", "elasticnet", "lasso", "ridge"):
@@ -196,12 +192,6 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
             r_dict["dy"] = dy_range
         if r_dict:
             refine_range = r_dict
-    if refine_range is not None:
-        # solver_linear_regression.lsq_reconstruct(refine_tilt_psi_dy_range=...) runs the refinement on the GPU, but the
-        # task wrapper then rotates the display volume by the refined angles with helicon.transform_map (pipeline.py:
-        # 428-438, cubic-spline resampling), which is not on the CUDA path
-        _unsupported("tilt/psi/dy refinement ranges in process_one_task (transform_map of the display volume); "
-                     "solver_linear_regression.lsq_reconstruct / refine_tilt_psi_dy accept them")
     (rec3d, rec3d_set_1, rec3d_set_2), score = lsq_reconstruct(
         projection_image=data, scale2d_to_3d=target_apix2d / target_apix3d, twist_degree=twist,
         rise_pixel=rise / target_apix3d, csym=csym, tilt_degree=tilt, psi_degree=psi, dy_pixel=dy / target_apix2d,
@@ -217,9 +207,32 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
     else:
         pitch_pixel = int(np.ceil(2 * rise / apix2d_orig))
     new_length = max(nx_orig, int(pitch_pixel * 1.2))
-    # tilt = psi = dy = 0 here (refused above otherwise): transform_map is the identity
-    rec3d_x_proj, rec3d_y_proj, rec3d_z_sections = transforms.symmetrize_and_project(
-        rec3d, target_apix3d, twist, rise, csym, (new_length, ny_orig, ny_orig), apix2d_orig, rise, apix2d_orig)
+    # refined tilt/psi/dy replace the given ones for the display (pipeline.py:428-436; consumed once)
+    tilt_viz, psi_viz, dy_viz = tilt, psi, dy
+    rp = getattr(lsq_reconstruct, "_refined_params", None)
+    if rp:
+        tilt_viz, psi_viz, dy_viz = rp.get("tilt", tilt), rp.get("psi", psi), rp.get("dy", dy)
+        lsq_reconstruct._refined_params = {}
+    if tilt_viz == 0 and psi_viz == 0 and dy_viz == 0:
+        # transform_map is the identity: symmetrise and reduce on the device, the (pitch-long) volume never leaves it
+        rec3d_x_proj, rec3d_y_proj, rec3d_z_sections = transforms.symmetrize_and_project(
+            rec3d, target_apix3d, twist, rise, csym, (new_length, ny_orig, ny_orig), apix2d_orig, rise, apix2d_orig)
+    else:
+        rec3d_xform = transforms.apply_helical_symmetry(rec3d, target_apix3d, twist, rise, csym=csym,
+                                                        new_size=(new_length, ny_orig, ny_orig), new_apix=apix2d_orig)
+        rec3d_xform_2 = transforms.transform_map(rec3d_xform, scale=1.0, tilt=tilt_viz, psi=psi_viz, dy=dy_viz / apix2d_orig)
+        rec3d_x_proj = np.sum(rec3d_xform_2, axis=2).T
+        rec3d_y_proj = np.sum(rec3d_xform_2, axis=1).T
+        y_max = rec3d_y_proj.max()
+        if y_max > 0:
+            rec3d_y_proj *= rec3d_x_proj.max() / y_max
+        nz_per_rise = max(1, int(np.ceil(rise / apix2d_orig)))
+        z0 = rec3d_xform.shape[0] // 2 - nz_per_rise // 2
+        rec3d_z_sections = np.sum(rec3d_xform[z0:z0 + nz_per_rise, :, :], axis=0)
+        vmin, vmax = rec3d_z_sections.min(), rec3d_z_sections.max()
+        if vmax > vmin:
+            t0, t1 = rec3d_x_proj.min(), rec3d_x_proj.max()
+            rec3d_z_sections = (rec3d_z_sections - vmin) * (t1 - t0) / (vmax - vmin) + t0
     nz, ny, nx = rec3d.shape
     logger.info(f"Task {ti+1}/{ntasks}: {imageFile}-{imageIndex}:\\tpitch={round(pitch, 1)}A/twist={round(twist, 3)} "
                 f"rise={round(rise, 3)}A csym={csym} => reconstruction size={nx}x{ny}x{nz}voxels "

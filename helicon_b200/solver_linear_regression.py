@@ -201,8 +201,12 @@ def lsq_reconstruct(
                      "SLR:907 vs 1401)")
     if algorithm.get("model", "lsq") != "lsq":
         _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
-    if score_metric != "cosine":
-        _unsupported(f"score_metric {score_metric!r} (only 'cosine', SLR:500-525)")
+    if score_metric not in ("cosine", "ssim", "ms_ssim", "mutual_information", "composite"):
+        raise ValueError(f"unknown score_metric {score_metric!r}")
+    if score_metric != "cosine" and fsc_test:
+        # the reference itself cannot do this: it scatters a half set's prediction with the FULL set's pixel ids
+        # (SLR:507-519, `pred_2d.ravel()[b_data_pid] = pred`) and numpy raises on the length mismatch
+        _unsupported(f"score_metric {score_metric!r} together with fsc_test (fails in the reference as well, SLR:507-519)")
     want_refine = refine_tilt_psi_dy_range is not None and any(
         refine_tilt_psi_dy_range.get(k, 0) > 0 for k in ("tilt", "psi", "dy"))
     if want_refine and fsc_test:
@@ -277,6 +281,10 @@ def lsq_reconstruct(
                         m1[set1] = 1
                         masks += [m1, 1 - m1]
                     r = batch.solve(clip_pred=int(thresh_fraction >= 0))
+                    if score_metric != "cosine":
+                        _, kk, jj = batch.data_row_index(0)
+                        r[0]["score"] = _metric_2d(score_metric, batch.predict(batch.x(0)), batch.data_b(),
+                                                   (kk * D2 + jj), image, D2, L2, thresh_fraction)
                     xs.append(batch.rec3d(0)); scs.append(np.float32(r[0]["score"]))
                     infos.append((r[0].copy(), batch.timing()))
                 finally:
@@ -299,6 +307,11 @@ def lsq_reconstruct(
                 batch.set_pixel_masks(np.stack([m1, 1 - m1]), [-1, 0, 1])
             res = batch.solve(clip_pred=int(thresh_fraction >= 0))
             rec3d = batch.rec3d(0)
+            if score_metric != "cosine":
+                pidx, kk, jj = batch.data_row_index(0)
+                pred = batch.apply_forward(0, batch.x(0))[: batch.rows_padded(0)[0]][pidx]
+                b_ref = batch.rhs_padded(0)[pidx]
+                res[0]["score"] = _metric_2d(score_metric, pred, b_ref, (kk * D2 + jj), image, D2, L2, thresh_fraction)
             if nsets == 3:
                 half1, half2 = batch.rec3d(1), batch.rec3d(2)
                 s = [np.float32(r["score"]) for r in res]  # SLR:527-528
@@ -313,6 +326,30 @@ def lsq_reconstruct(
     if return_info:
         return (rec3d, half1, half2), score, info
     return (rec3d, half1, half2), score
+
+
+def _metric_2d(score_metric, pred, b_data, pid, image, D2, L2, thresh_fraction):
+    """SLR:484-525 for the 2-D metrics: the reprojection scattered back to the (L2, D2) image by pixel id (a later row
+    of the same pixel overwrites an earlier one, as numpy's fancy assignment does) against the transposed input region."""
+    from . import imageprep as M
+
+    pred = np.asarray(pred, dtype=np.float32)
+    if thresh_fraction >= 0:
+        pred = np.clip(pred, 0, None)
+    ny, nx = image.shape
+    region = image[ny // 2 - D2 // 2: ny // 2 + D2 // 2, nx // 2 - L2 // 2: nx // 2 + L2 // 2]
+    pred_2d = np.zeros((L2, D2), dtype=np.float32)
+    pred_2d.ravel()[np.asarray(pid, dtype=np.int64)] = pred
+    ref_2d = region.T
+    if score_metric == "ssim":
+        return M.ssim_score(pred_2d, ref_2d)
+    if score_metric == "ms_ssim":
+        return M.ms_ssim_score(pred_2d, ref_2d)
+    if score_metric == "mutual_information":
+        return M.mutual_information_score(pred_2d, ref_2d)
+    parts = [planner_cosine(pred, b_data), M.ssim_score(pred_2d, ref_2d), M.ms_ssim_score(pred_2d, ref_2d),
+             M.mutual_information_score(pred_2d, ref_2d)]
+    return float(np.mean(parts))
 
 
 def split_pixel_ids(b_id, mode):

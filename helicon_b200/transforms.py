@@ -119,3 +119,42 @@ def symmetrize_and_project(data, apix, twist_degree, rise_angstrom, csym, new_si
         tmin, tmax = x_proj.min(), x_proj.max()
         z_sec = (z_sec - vmin) * (tmax - tmin) / (vmax - vmin) + tmin
     return (x_proj, y_proj, z_sec, vol) if return_volume else (x_proj, y_proj, z_sec)
+
+
+def pad_to_size(data, shape):
+    """lib/transforms.py:441-479: zero-pad a 2-D / 3-D array, centred, to ``shape`` (no cropping)."""
+    assert data.ndim in [2, 3]
+    if data.shape == tuple(shape):
+        return data
+    pads = []
+    for n, m in zip(data.shape, shape):
+        before = max(0, (m - n) // 2)
+        pads.append((before, max(0, m - before - n)))
+    return np.pad(data, pad_width=tuple(pads), mode="constant")
+
+
+def transform_map(data, scale=1.0, rot=0, tilt=0, psi=0, dx=0, dy=0, dz=0):
+    """lib/transforms.py:168-235: resample a volume under a ZYZ rotation + shift with cubic splines.
+
+    Host side, like the reference: the arithmetic is scipy's (``Rotation.apply`` + ``ndimage.map_coordinates(order=3)``,
+    third-party code the reference calls as well), applied to the display volume of a tilted / refined task only
+    (pipeline.py:436-438; the identity for the untilted grid search, where nothing is computed).  Pinned to outputs of
+    the reference in tests/golden/transform_map.npz."""
+    if scale == 1 and rot == 0 and tilt == 0 and psi == 0 and dx == 0 and dy == 0 and dz == 0:
+        return data
+    from scipy.ndimage import map_coordinates
+    from scipy.spatial.transform import Rotation as R
+
+    nz, ny, nx = data.shape
+    k = np.arange(0, nz, dtype=np.int32) - nz // 2
+    j = np.arange(0, ny, dtype=np.int32) - ny // 2
+    i = np.arange(0, nx, dtype=np.int32) - nx // 2
+    Z, Y, X = np.meshgrid(k, j, i, indexing="ij")
+    if scale != 1.0:
+        Z, Y, X = Z * scale, Y * scale, X * scale
+    xyz = R.from_euler("ZYZ", (rot, tilt, psi), degrees=True).apply(
+        np.vstack((X.ravel(), Y.ravel(), Z.ravel())).transpose(), inverse=False)
+    xyz[:, 0] += nx // 2 - dx
+    xyz[:, 1] += ny // 2 - dy
+    xyz[:, 2] += nz // 2 - dz
+    return map_coordinates(data, xyz[:, [2, 1, 0]].T, order=3).reshape((nz, ny, nx))

@@ -257,7 +257,46 @@ def test_reference_test_shapes(solver):
         assert rec3d.shape == (8, 8, 8) and np.all(np.isfinite(rec3d))
     with pytest.raises(NotImplementedError):  # what is still outside the CUDA path fails loudly
         solver.lsq_reconstruct(image, 1.0, 30, 2, reconstruct_diameter_3d_pixel=8, reconstruct_length_3d_pixel=8,
-                               score_metric="ssim")
+                               algorithm=dict(model="no_such_model"))
+    with pytest.raises(ValueError):
+        solver.lsq_reconstruct(image, 1.0, 30, 2, reconstruct_diameter_3d_pixel=8, reconstruct_length_3d_pixel=8,
+                               score_metric="no_such_metric")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("interp", ["nn", "linear"])
+def test_2d_score_metrics_on_the_reprojection(solver, interp):
+    """score_metric ssim / ms_ssim / mutual_information / composite (SLR:494-525): the reprojection is scattered back to
+    the image by pixel id and compared in 2-D.  The metric implementations restate scikit-image (absent here and in
+    the reference's environment of this container -> parity unpinned); pinned here: the scatter equals the oracle's
+    prediction image, composite = mean of the four, and the metrics see a near-perfect reprojection."""
+    from helicon_b200 import imageprep as M
+
+    d = load("solve_nn_unb_48_t35")
+    apix, twist, rise, csym, pc, so, L3 = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    kw = dict(scale2d_to_3d=1.0, twist_degree=float(twist), rise_pixel=float(rise / apix), csym=int(csym),
+              positive_constraint=0, reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N,
+              reconstruct_diameter_3d_pixel=N, reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so),
+              interpolation=interp)
+    (rec_c, _, _), s_cos = solver.lsq_reconstruct(img, **kw)
+    vals = {}
+    for m in ("ssim", "ms_ssim", "mutual_information", "composite"):
+        (rec, _, _), vals[m] = solver.lsq_reconstruct(img, score_metric=m, **kw)
+        assert np.array_equal(rec, rec_c)
+        assert np.isfinite(vals[m])
+    assert 0.5 < vals["ssim"] <= 1 and 0.5 < vals["ms_ssim"] <= 1 and 0 < vals["mutual_information"] <= 1
+    assert abs(vals["composite"] - np.mean([float(s_cos), vals["ssim"], vals["ms_ssim"], vals["mutual_information"]])) < 1e-6
+    # the oracle's reprojection image through the same metric: inherits only the solve's reproducibility floor
+    (rec_o, _, _), _, det = O.lsq_reconstruct(img, return_details=True, **kw)
+    pred = det["A_data"].dot(det["res"].x.astype(np.float32))
+    D2, L2 = kw["reconstruct_diameter_2d_pixel"], kw["reconstruct_length_2d_pixel"]
+    ny, nx = img.shape
+    p2 = np.zeros((L2, D2), np.float32)
+    p2.ravel()[det["b_pid"]] = pred
+    ref2 = img[ny // 2 - D2 // 2: ny // 2 + D2 // 2, nx // 2 - L2 // 2: nx // 2 + L2 // 2].T
+    assert abs(M.ssim_score(p2, ref2) - vals["ssim"]) < 2e-3
 
 
 def _oracle_bounded_spread(img, kw, n_perm=4):

@@ -200,3 +200,69 @@ def test_mrc_writer_reader_round_trip(tmp_path):
     data, apix = pipeline.get_images_from_file(path)
     assert data.shape == (5, 7) and apix == 2.0
     assert np.allclose(_axis("-3:-1:5", "twist"), np.linspace(-3, -1, 5)) and list(_axis("4.7,4.8", "rise")) == [4.7, 4.8]
+
+
+def test_transform_map_matches_reference_outputs():
+    """helicon.transform_map (lib/transforms.py:168-235) on a small random volume: four argument sets generated by the
+    unmodified reference (oracle/make_golden_task_tilt.py); same scipy calls -> identical to float32 round-off."""
+    from helicon_b200 import transforms as T
+
+    d = load("transform_map")
+    for i in range(4):
+        scale, rot, tilt, psi, dx, dy, dz = (float(v) for v in d[f"case{i}_args"])
+        got = T.transform_map(d["vol"], scale=scale, rot=rot, tilt=tilt, psi=psi, dx=dx, dy=dy, dz=dz)
+        ref = d[f"case{i}"]
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert np.allclose(got, ref, rtol=0, atol=1e-6), (i, float(np.abs(got - ref).max()))
+    vol = d["vol"]
+    assert T.transform_map(vol) is vol  # the identity returns its argument (lib/transforms.py:177-187)
+
+
+def test_pad_to_size_centres_and_keeps_values():
+    from helicon_b200 import transforms as T
+
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    p = T.pad_to_size(a, (4, 4))
+    assert p.shape == (4, 4) and np.array_equal(p[0:3], a) and not p[3].any()
+    assert T.pad_to_size(a, (3, 4)) is a
+
+
+def test_down_scale_properties():
+    """imageprep.down_scale restates skimage.transform.rescale(order=3, anti_aliasing=True) (parity unpinned: skimage is
+    not installed): even output size of round(n * apix_orig / target), a constant image stays constant, the mean of a
+    smooth image is kept, the value range is never exceeded, no change when the target is not coarser."""
+    from helicon_b200 import imageprep as M
+
+    yy, xx = np.mgrid[0:100, 0:140]
+    img = (np.exp(-((yy - 50.0) ** 2) / 200.0) * (1 + 0.3 * np.cos(xx / 9.0))).astype(np.float32)
+    out = M.down_scale(img, target_apix=5.0, apix_orig=1.3)
+    assert out.shape == (26, 36) and out.shape[0] % 2 == 0 and out.shape[1] % 2 == 0
+    assert out.min() >= img.min() - 1e-6 and out.max() <= img.max() + 1e-6
+    assert abs(out[:, :36].mean() - img.mean()) < 0.02 * img.mean()
+    c = M.down_scale(np.full((64, 64), 3.5, np.float32), 4.0, 1.0)
+    assert c.shape == (16, 16) and np.allclose(c, 3.5)
+    assert M.down_scale(img, 1.3, 1.3) is img and M.down_scale(img, 1.0, 1.3) is img
+    odd = M.down_scale(np.ones((50, 50), np.float32), 2.0, 1.0)  # 25 -> padded to 26 with zeros (filters.py:408-411)
+    assert odd.shape == (26, 26) and odd[:25, :25].min() > 0.99 or odd[1:, 1:].min() > 0.99
+
+
+def test_2d_metrics_defining_properties():
+    """SSIM = 1 / MS-SSIM = 1 for identical images, lower for a degraded copy, symmetric; MI of identical images = 1
+    (normalised MI 2, minus 1) and ~0 for independent noise; constant images score 0 (lib/analysis.py:487-613)."""
+    from helicon_b200 import imageprep as M
+
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:96, 0:96]
+    a = (np.sin(xx / 5.0) * np.cos(yy / 7.0) + 1).astype(np.float32)
+    noisy = (a + 0.4 * rng.standard_normal(a.shape)).astype(np.float32)
+    assert abs(M.ssim_score(a, a) - 1) < 1e-9 and abs(M.ms_ssim_score(a, a) - 1) < 1e-9
+    s = M.ssim_score(a, noisy)
+    assert 0 < s < 0.9 and abs(s - M.ssim_score(noisy, a)) < 1e-12
+    assert 0 < M.ms_ssim_score(a, noisy) < 1
+    assert abs(M.mutual_information_score(a, a) - 1) < 1e-9
+    ind = M.mutual_information_score(rng.random((96, 96)), rng.random((96, 96)))
+    assert 0 <= ind < 0.2
+    z = np.zeros((32, 32), np.float32)
+    assert M.ssim_score(z, z) == 0.0 and M.ms_ssim_score(z, z) == 0.0
+    with pytest.raises(ValueError):
+        M.ssim_score(a, a[:10])
