@@ -96,7 +96,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(Result)
 EXPORTS = [
     "hb2_last_error", "hb2_device_count", "hb2_build_info", "hb2_problem_create", "hb2_problem_destroy",
     "hb2_problem_ndisk", "hb2_problem_rank_table", "hb2_batch_begin", "hb2_batch_ray_valid", "hb2_batch_angle_map",
-    "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_rows_padded", "hb2_batch_rhs",
+    "hb2_batch_create", "hb2_batch_destroy", "hb2_batch_sym_rows", "hb2_batch_sym_order", "hb2_batch_rows_padded", "hb2_batch_rhs",
     "hb2_batch_apply_forward", "hb2_batch_apply_adjoint", "hb2_batch_solve", "hb2_batch_get_x", "hb2_batch_timing",
     "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize", "hb2_batch_set_ties",
     "hb2_batch_set_pixel_masks", "hb2_batch_add_exact_maps", "hb2_batch_explicit_rows", "hb2_batch_explicit_export", "hb2_batch_explicit_sym_rows",
@@ -147,6 +147,7 @@ def load():
     lib.hb2_batch_destroy.argtypes = [vp]
     lib.hb2_batch_destroy.restype = None
     lib.hb2_batch_sym_rows.argtypes = [vp, i32, P(i32), vp, vp, i64]
+    lib.hb2_batch_sym_order.argtypes = [vp, i32, vp, i64]
     lib.hb2_batch_rows_padded.argtypes = [vp, i32, P(i64)]
     lib.hb2_batch_rows_padded.restype = i64
     lib.hb2_batch_rhs.argtypes = [vp, i32, vp]

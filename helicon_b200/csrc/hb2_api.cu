@@ -82,6 +82,7 @@ struct hb2_problem {
   float* d_pix = nullptr;          // [D2][L2]  pix[j][k] = image[j - D2//2 + ny//2, k - L2//2 + nx//2]
   int* d_rank_data = nullptr;      // [D2*D2]
   int* d_rank_sym = nullptr;       // [D3*D3]
+  int* d_int2ref = nullptr;        // [ndisk] internal disk rank -> reference rank
   short2* d_yx_data = nullptr;     // [ndisk] (row y, column x) on the data grid
   short2* d_yx_sym = nullptr;      // [ndisk] on the symmetry grid, REFERENCE voxel order (row enumeration of the symmetry rows)
   std::vector<int> h_rank_data;    // reference disk rank (C-order np.nonzero) on the data grid, for exports
@@ -245,6 +246,8 @@ struct hb2_batch {
   uint8_t* d_rayvalid = nullptr;
   int* d_tie = nullptr;
   uint16_t* d_amap = nullptr;
+  int* d_sym_g = nullptr;                        // per symmetry row: reference index of its generating voxel
+  std::vector<std::vector<int>> h_sym_round_end;  // [round][nc] rows of the candidate after that pair round
   int* d_sym_a = nullptr; int* d_sym_b = nullptr; int* d_csc_ptr = nullptr; int* d_csc_ent = nullptr; int* d_ell = nullptr;
   float* d_bmax = nullptr;
   float* d_score = nullptr;
@@ -325,24 +328,42 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
     }
 }
 
-// Internal voxel order: the disk is cut into TH x TW tiles (relative to the mask's bounding box) and voxels are
-// numbered tile by tile, row-major inside a tile.  256 consecutive internal ranks (one adjoint CTA) then cover a
-// compact 2-D patch, whose rays form a short contiguous range in every view -- the rows a CTA gathers stay in L1
-// (profiles/r1: with row-major ranks every CTA touched (1 + 256|sin|) rows per view).  Reference order is kept for
+// Internal voxel order ("band-column-major"): the disk is cut into BANDS of TH = 16 voxel rows (relative to the mask's
+// bounding box); inside a band voxels are numbered column by column (x-major, then y).  Consequences:
+//  * a band is ONE contiguous run of ranks -> one TMA bulk copy stages it in shared memory (forward band kernel), and
+//    rank - band_begin is the shared-memory slot;
+//  * neighbouring rows of a column are neighbouring records, and a full column is 16 records = a multiple of 8: the
+//    bank group of a 16-byte chunk depends on the ROW only, so lanes that sit on adjacent rays at the same depth sample
+//    (one row apart at view angles below 45 degrees) read distinct bank groups -- conflict-free 128-bit shared loads;
+//  * TW = 16 consecutive columns of a band (<= 256 consecutive ranks) form a compact 16 x 16 patch: the adjoint tile,
+//    whose rays are a short contiguous range in every view.
+// HB2_VOXEL_ORDER=0 restores round 1's row-major 8 x 32 tiles (tile by tile).  The reference order is kept for
 // everything exported and for the enumeration order of the symmetry rows.
 static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref, std::vector<int>& tile_begin,
                        std::vector<int>& tilerow_begin, bool& tile_ok) {
-  static const int TH = [] { const char* e = getenv("HB2_TILE_H"); return e ? std::max(1, atoi(e)) : 8; }();
-  static const int TW = [] { const char* e = getenv("HB2_TILE_W"); return e ? std::max(1, atoi(e)) : 32; }();
+  // read per problem (not latched), so that tests can compare the orders inside one process
+  const char* e_o = getenv("HB2_VOXEL_ORDER"); const char* e_h = getenv("HB2_TILE_H"); const char* e_w = getenv("HB2_TILE_W");
+  const int ORDER = e_o ? atoi(e_o) : 1;
+  const int TH = e_h ? std::max(1, atoi(e_h)) : (ORDER ? 16 : 8);
+  const int TW = e_w ? std::max(1, atoi(e_w)) : (ORDER ? 16 : 32);
   tile_ok = (long long)TH * TW <= HB2_BLOCK;
   int ymin = 1 << 30, xmin = 1 << 30;
   for (const short2& q : yx_ref) { ymin = std::min<int>(ymin, q.x); xmin = std::min<int>(xmin, q.y); }
   int2ref.resize(yx_ref.size());
   for (size_t i = 0; i < yx_ref.size(); ++i) int2ref[i] = (int)i;
   auto tkey = [&](int r) { return std::make_pair((yx_ref[r].x - ymin) / TH, (yx_ref[r].y - xmin) / TW); };
-  std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) {
-    return std::make_pair(tkey(a), a) < std::make_pair(tkey(b), b);  // reference rank is row-major already
-  });
+  if (ORDER) {
+    std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) {
+      const int ba = (yx_ref[a].x - ymin) / TH, bb = (yx_ref[b].x - ymin) / TH;
+      if (ba != bb) return ba < bb;
+      if (yx_ref[a].y != yx_ref[b].y) return yx_ref[a].y < yx_ref[b].y;
+      return yx_ref[a].x < yx_ref[b].x;
+    });
+  } else {
+    std::sort(int2ref.begin(), int2ref.end(), [&](int a, int b) {
+      return std::make_pair(tkey(a), a) < std::make_pair(tkey(b), b);  // reference rank is row-major already
+    });
+  }
   tile_begin.clear();
   for (size_t i = 0; i < int2ref.size(); ++i)
     if (i == 0 || tkey(int2ref[i]) != tkey(int2ref[i - 1])) tile_begin.push_back((int)i);
@@ -413,6 +434,8 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   std::vector<int> aslot(P->ndisk);
   for (int t = 0; t < P->ntile; ++t)
     for (int i = P->h_tile_begin[t]; i < P->h_tile_begin[t + 1]; ++i) aslot[i] = t * HB2_BLOCK + (i - P->h_tile_begin[t]);
+  CK(cudaMalloc(&P->d_int2ref, P->int2ref.size() * sizeof(int)));
+  CK(cudaMemcpyAsync(P->d_int2ref, P->int2ref.data(), P->int2ref.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMalloc(&P->d_tile_begin, P->h_tile_begin.size() * sizeof(int)));
   CK(cudaMalloc(&P->d_aslot, aslot.size() * sizeof(int)));
   CK(cudaMemcpyAsync(P->d_tile_begin, P->h_tile_begin.data(), P->h_tile_begin.size() * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -430,7 +453,7 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
 extern "C" void hb2_problem_destroy(hb2_problem* P) {
   if (!P) return;
   cudaSetDevice(P->device);
-  cudaFree(P->d_tile_begin); cudaFree(P->d_aslot);
+  cudaFree(P->d_tile_begin); cudaFree(P->d_aslot); cudaFree(P->d_int2ref);
   cudaFree(P->d_pix); cudaFree(P->d_rank_data); cudaFree(P->d_rank_sym); cudaFree(P->d_yx_data); cudaFree(P->d_yx_sym);
   delete P;
 }
@@ -1154,15 +1177,14 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     int max_views = 0;
     for (int c = 0; c < nc; ++c) max_views = std::max(max_views, b->h_view_count[c]);
     b->max_views = max_views;
-    // The band path is correct (tests run it with HB2_FWD_BAND=1) but measured slower than the gather kernel on
-    // cfg2 (24 vs 18 us per candidate-pass, profiles/r1_summary.md: issue-bound on the per-ray lane reduction and
-    // +11 MB of partial-sum traffic), so it is opt-in until the lane-per-ray variant lands.
+    // Default whenever it applies (one column slot per slice, <= 16 slices, 16-bit maps, a band of 16 voxel rows fits
+    // shared memory); HB2_FWD_BAND=0 forces the gather kernel (tests compare the two).
     const char* use_band = getenv("HB2_FWD_BAND");
     const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)sizeof(float));
     std::vector<int> bands{0};
-    const int band_mode = use_band ? atoi(use_band) : 0;  // 1: sample-lane kernel, 2: (ray, quad)-lane kernel
-    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->n_tie_views == 0;
-    if (band_mode == 2 && !(b->idx16 && D2 % 8 == 0)) ok = false;
+    const int band_mode = use_band ? atoi(use_band) : 1;
+    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->idx16 && D2 % 8 == 0 &&
+              !b->explicit_rows;
     const std::vector<int>& tr = P->h_tilerow_begin;
     for (size_t r = 0; ok && r + 1 < tr.size(); ++r) {
       if (tr[r + 1] - tr[r] > cap) { ok = false; break; }
@@ -1173,7 +1195,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     if (ok && NB <= HB2_MAX_BANDS) {
       int max_bn = 0;
       for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
-      b->fwd_band_smem = (size_t)(band_mode == 2 ? max_bn + HB2_FWDB2_PAD * ((max_bn + 31) / 32) : max_bn) * B.L3P * sizeof(float);
+      b->fwd_band_smem = (size_t)max_bn * B.L3P * sizeof(float);
       CKC(upload(b->pool, &B.band_begin, bands, st));
       ushort2 *d_seg, *d_rng;
       CKC(b->pool.alloc(&d_seg, (size_t)B.nA * NB * D2, false, st));
@@ -1188,7 +1210,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       for (int c = 0; c < nc; ++c) { poff[c] = po; po += (long long)b->h_view_count[c] * NB * D2 * B.L3P; }
       CKC(upload(b->pool, &B.cand_poff, poff, st));
       CKC(b->pool.alloc(&B.fwd_part, (size_t)std::max<long long>(po, 1), false, st));
-      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = band_mode == 2 ? 2 : 1; B.fwd_ppv = 1;
+      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = 1; B.fwd_ppv = 1;
     }
   }
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
@@ -1213,6 +1235,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   // ---- symmetry rows -----------------------------------------------------------
   CKC(b->pool.alloc(&b->d_sym_a, (size_t)so, false, st));
   CKC(b->pool.alloc(&b->d_sym_b, (size_t)so, false, st));
+  CKC(b->pool.alloc(&b->d_sym_g, (size_t)so, false, st));
   B.sym_a = b->d_sym_a; B.sym_b = b->d_sym_b;
   CKC(b->pool.alloc(&b->d_csc_ptr, (size_t)nc * (B.npad + 1), true, st));
   CKC(b->pool.alloc(&b->d_csc_ent, (size_t)2 * so, false, st));
@@ -1256,8 +1279,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       CKT(cudaMemcpyAsync(Q.ndone, &nd0, sizeof(int), cudaMemcpyHostToDevice, st));
       CKT(cudaStreamSynchronize(st));
     }
-    Q.sym_a_w = b->d_sym_a; Q.sym_b_w = b->d_sym_b;
-    Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym;
+    Q.sym_a_w = b->d_sym_a; Q.sym_b_w = b->d_sym_b; Q.sym_g_w = b->d_sym_g;
+    Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym; Q.int2ref = P->d_int2ref;
+    b->h_sym_round_end.clear();
     void* d_scan_tmp = nullptr; size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, Q.flag, Q.pos, (int)nr, st);
     { char* p; CKT(tmp.alloc(&p, scan_bytes, false, st)); d_scan_tmp = p; }
@@ -1272,6 +1296,8 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       int nd = 0, ovf = 0;
       CKT(cudaMemcpyAsync(&nd, Q.ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
       CKT(cudaMemcpyAsync(&ovf, Q.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+      b->h_sym_round_end.emplace_back(nc);
+      CKT(cudaMemcpyAsync(b->h_sym_round_end.back().data(), B.cand_msym, sizeof(int) * nc, cudaMemcpyDeviceToHost, st));
       CKT(cudaStreamSynchronize(st));
       if (ovf) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "symmetry-row table overflow (internal error)"); }
       if (nd >= nc) break;
@@ -1316,7 +1342,6 @@ extern "C" int hb2_batch_set_pixel_masks(hb2_batch* b, int32_t n_masks, const ui
   if (!b || n_masks < 0 || (n_masks > 0 && !masks) || !cand_mask) return fail(HB2_ERR_ARG, "bad argument");
   if (!b->created) return fail(HB2_ERR_STATE, "hb2_batch_set_pixel_masks must follow hb2_batch_create");
   BD& B = b->B;
-  if (B.fwd_band) return fail(HB2_ERR_STATE, "pixel masks are not supported on the opt-in band path (HB2_FWD_BAND)");
   CK(cudaSetDevice(b->P->device));
   cudaStream_t st = b->stream;
   const int nc = B.nc;
@@ -1346,6 +1371,36 @@ extern "C" void hb2_batch_destroy(hb2_batch* b) {
   delete b;
 }
 
+// Stored position of every symmetry row in the reference's order.  The rows of one pair round are stored in internal
+// voxel order (k_sym_insert); the reference enumerates them in mask order (SLR:1197-1202): ord[r] = stored index of the
+// reference's r-th row, recovered per round from the generating voxel's reference index.
+static int sym_ref_order(hb2_batch* b, int c, std::vector<int>& ord) {
+  const int m = b->h_msym[c];
+  ord.resize(m);
+  for (int r = 0; r < m; ++r) ord[r] = r;
+  if (m == 0 || !b->d_sym_g) return HB2_OK;
+  std::vector<int> gref(m);
+  CK(cudaMemcpyAsync(gref.data(), b->d_sym_g + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  int start = 0;
+  for (size_t rd = 0; rd < b->h_sym_round_end.size() && start < m; ++rd) {
+    const int end = std::min(m, b->h_sym_round_end[rd][c]);
+    if (end > start) std::sort(ord.begin() + start, ord.begin() + end, [&](int x, int y) { return gref[x] < gref[y]; });
+    start = std::max(start, end);
+  }
+  return HB2_OK;
+}
+
+extern "C" int hb2_batch_sym_order(hb2_batch* b, int32_t c, int32_t* ord_host, int64_t capacity) {
+  if (!b || !b->created || !ord_host || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
+  if (capacity < b->h_msym[c]) return fail(HB2_ERR_ARG, "capacity too small");
+  CK(cudaSetDevice(b->P->device));
+  std::vector<int> ord;
+  if (int e = sym_ref_order(b, c, ord)) return e;
+  memcpy(ord_host, ord.data(), sizeof(int) * ord.size());
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_sym_rows(hb2_batch* b, int32_t c, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity) {
   if (!b || !b->created || c < 0 || c >= b->B.nc) return fail(HB2_ERR_ARG, "bad argument");
   CK(cudaSetDevice(b->P->device));
@@ -1355,12 +1410,14 @@ extern "C" int hb2_batch_sym_rows(hb2_batch* b, int32_t c, int32_t* n_rows, int3
     if (capacity < m) return fail(HB2_ERR_ARG, "capacity too small");
     CK(cudaMemcpyAsync(a_host, b->d_sym_a + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b_host, b->d_sym_b + b->h_symoff[c], sizeof(int) * m, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
     const int L3P = b->B.L3P, nd = b->B.ndisk;
     const std::vector<int>& i2r = b->P->int2ref;
+    std::vector<int> ord;
+    if (int e = sym_ref_order(b, c, ord)) return e;
+    std::vector<int> ta(a_host, a_host + m), tb(b_host, b_host + m);
     for (int r = 0; r < m; ++r) {  // internal p*L3P+z -> reference z*ndisk+rank
-      a_host[r] = (a_host[r] % L3P) * nd + i2r[a_host[r] / L3P];
-      b_host[r] = (b_host[r] % L3P) * nd + i2r[b_host[r] / L3P];
+      a_host[r] = (ta[ord[r]] % L3P) * nd + i2r[ta[ord[r]] / L3P];
+      b_host[r] = (tb[ord[r]] % L3P) * nd + i2r[tb[ord[r]] / L3P];
     }
   }
   return HB2_OK;
@@ -1417,24 +1474,14 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (B.fwd_band) {
     const size_t sm = b->fwd_band_smem;
     const dim3 gb(B.nband, B.nc), gr(b->max_views, B.nc);
-#define FWB(T, Q)                                                                                         \
+#define FWB(Q)                                                                                            \
   do {                                                                                                    \
-    hb2_allow_big_smem((const void*)k_fwd_band<T, Q>);         \
-    k_fwd_band<T, Q><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, mode);                                          \
+    hb2_allow_big_smem((const void*)k_fwd_band<Q>);                                                       \
+    k_fwd_band<Q><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, mode);                                             \
     k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
   } while (0)
-#define FWBQ(T) do { if (B.L3P == 4) FWB(T, 1); else if (B.L3P == 8) FWB(T, 2); else if (B.L3P == 12) FWB(T, 3); else FWB(T, 4); } while (0)
-#define FWB2(Q)                                                                                           \
-  do {                                                                                                    \
-    hb2_allow_big_smem((const void*)k_fwd_band2<Q>);           \
-    k_fwd_band2<Q><<<gb, HB2_FWDB2_THREADS, sm, st>>>(B, mode);                                           \
-    k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
-  } while (0)
-    if (B.fwd_band == 2) { if (B.L3P == 4) FWB2(1); else if (B.L3P == 8) FWB2(2); else if (B.L3P == 12) FWB2(3); else FWB2(4); }
-    else if (b->idx16) FWBQ(uint16_t); else FWBQ(uint32_t);
-#undef FWB2
+    if (B.L3P == 4) FWB(1); else if (B.L3P == 8) FWB(2); else if (B.L3P == 12) FWB(3); else FWB(4);
     b->extra_launches += 1;
-#undef FWBQ
 #undef FWB
     return;
   }

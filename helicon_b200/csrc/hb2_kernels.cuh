@@ -390,6 +390,8 @@ struct SymSetup {
   int* sym_b_w;
   const int* rank_sym;          // [D3*D3]
   const short2* disk_yx_sym;    // [ndisk]
+  const int* int2ref;           // [ndisk] internal disk rank -> reference rank
+  int* sym_g_w;                 // per kept row: reference index g of the voxel that generated it (export order)
   const long long* symcap;
   int* overflow;
 };
@@ -423,15 +425,20 @@ __device__ __forceinline__ int sym_image(double C, double S, double zs, int xc, 
 __global__ void k_sym_insert(BD B, SymSetup Q, int rnd) {
   int c = blockIdx.y;
   if (Q.done[c]) return;
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B.n) return;
+  // Threads (and with them the kept rows of a pair block) enumerate the voxels in INTERNAL order, z fastest: the rows
+  // generated by one voxel column are consecutive and their images a, b are runs of consecutive floats of v, so the
+  // gathers of k_fwd_sym and the row reads of the adjoint lists are (nearly) sequential.  The reference's enumeration
+  // index g (z slowest, mask order) still decides which duplicate survives (seq) and is kept per row for the exports.
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B.n) return;
   const double* pr = Q.pairs + (size_t)(Q.pair_begin[c] + rnd) * 6;
-  int z = g / B.ndisk, p = g % B.ndisk;
+  int z = t % B.L3, p = Q.int2ref[t / B.L3];
+  int g = z * B.ndisk + p;
   short2 yx = Q.disk_yx_sym[p];
   int xc = yx.y - B.D3 / 2, yc = yx.x - B.D3 / 2, zc = z - B.L3 / 2;
   int a = sym_image(pr[0], pr[1], pr[2], xc, yc, zc, B.D3, B.L3, B.L3P, Q.rank_sym);
   int b = sym_image(pr[3], pr[4], pr[5], xc, yc, zc, B.D3, B.L3, B.L3P, Q.rank_sym);
-  size_t ti = (size_t)c * B.nrp + g;
+  size_t ti = (size_t)c * B.nrp + t;
   if (a < 0 || b < 0) {
     Q.tmp_a[ti] = -1; Q.tmp_b[ti] = -1;
     return;
@@ -459,11 +466,12 @@ __global__ void k_sym_insert(BD B, SymSetup Q, int rnd) {
 // (first-seen-wins over pairs in list order, then voxels in mask order, SLR:1197-1202).
 __global__ void k_sym_check(BD B, SymSetup Q, int rnd) {
   int c = blockIdx.y;
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B.nrp) return;
-  size_t ti = (size_t)c * B.nrp + g;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B.nrp) return;
+  size_t ti = (size_t)c * B.nrp + t;
   int keep = 0;
-  if (!Q.done[c] && g < B.n) {
+  if (!Q.done[c] && t < B.n) {
+    const int g = (t % B.L3) * B.ndisk + Q.int2ref[t / B.L3];
     int a = Q.tmp_a[ti], b = Q.tmp_b[ti];
     if (a >= 0) {
       unsigned lo = (unsigned)min(a, b), hi = (unsigned)max(a, b);
@@ -488,14 +496,15 @@ __global__ void k_sym_check(BD B, SymSetup Q, int rnd) {
 __global__ void k_sym_compact(BD B, SymSetup Q) {
   int c = blockIdx.y;
   if (Q.done[c]) return;
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= B.n) return;
-  size_t ti = (size_t)c * B.nrp + g;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B.n) return;
+  size_t ti = (size_t)c * B.nrp + t;
   if (!Q.flag[ti]) return;
   long long row = (long long)B.cand_msym[c] + (Q.pos[ti] - Q.pos[(size_t)c * B.nrp]);
   if (row >= Q.symcap[c]) { atomicExch(Q.overflow, 2); return; }
   Q.sym_a_w[B.cand_symoff[c] + row] = Q.tmp_a[ti];
   Q.sym_b_w[B.cand_symoff[c] + row] = Q.tmp_b[ti];
+  Q.sym_g_w[B.cand_symoff[c] + row] = (t % B.L3) * B.ndisk + Q.int2ref[t / B.L3];
 }
 
 // phase 3: row count + early stop (SLR:1286) per candidate
@@ -753,23 +762,29 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
 }
 
 // ===========================================================================
-// forward projector, band path.  profiles/r1_summary.md: the gather kernel above
-// re-reads v from L2 for every view (186 MB per candidate-pass, 8.5 TB/s at the
-// L2 port) and sits at ~80 % of the L1 wavefront rate.  Here a CTA keeps a BAND
-// of the candidate's voxels -- whole tile-rows of the tile-major voxel order,
-// i.e. one contiguous block of v, <= ~200 KB -- in shared memory (TMA bulk
-// copy) and applies ALL views to it: every ray of every view that crosses the
-// band contributes one partial sum (its samples inside the band, gathered from
-// shared memory with conflict-light 128-bit loads); k_fwd_band_reduce adds a
-// ray's partials over the bands it crosses, in band order, and applies the
-// LSMR row update / the score accumulation.  v leaves L2 once per pass.
-// Lanes of a warp: SPW = 32/NQ consecutive samples of one ray x NQ slice quads.
+// forward projector, band path (the default when it applies).  The gather kernel
+// above re-reads v from L2 for every view (157 MB per candidate-pass at cfg2,
+// ~9 TB/s at the L2 port: that port, not HBM, bounds it).  Here a CTA keeps one
+// BAND of the candidate's voxels -- 16 voxel rows of the disk, one contiguous run
+// of v in the band-column-major voxel order, <= ~196 KB -- in shared memory (TMA
+// bulk copies) and applies ALL views of the candidate to it: every ray of every
+// view that crosses the band contributes one partial sum (its samples inside
+// the band); k_fwd_band_reduce adds a ray's partials over the bands it crosses,
+// in band order, and applies the LSMR row update / the score accumulation.
+// v leaves L2 once per pass.
+// Lanes: a warp item is RPW = 32/NQ adjacent rays of one view x NQ slice quads;
+// a lane owns one (ray, quad), walks the ray's samples inside the band and keeps
+// its 4 sums in registers -- no cross-lane reduction.  All lanes of the warp sit
+// on the SAME depth sample at any time: adjacent rays are then one voxel row
+// apart (view angles below 45 degrees), rows of a column are adjacent records
+// and a column is 16 records, so the 8 lanes of a quarter-warp read 8 distinct
+// 16-byte bank groups (see tile_order in hb2_api.cu).  Map entries arrive 8 at
+// a time (one aligned 128-bit load per lane and 8 samples, next block
+// prefetched); "rank inside the band" is the only test per sample.
 // ===========================================================================
-#define HB2_FWDB_THREADS 1024
-#define HB2_FWDB_RU 4        // rays processed together by a warp
-#define HB2_FWDB_SU 3        // steps of those rays whose map loads are issued together
+#define HB2_FWDB_THREADS 512
 #define HB2_FWDB_MAXV 256
-#define HB2_MAX_BANDS 32
+#define HB2_MAX_BANDS 64
 
 // sample range of every ray inside every band (setup): one thread per (angle, band, ray)
 template <typename IdxT>
@@ -801,163 +816,168 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_band_rng(int nband, int D2, const
   if (threadIdx.x == 0) rng[(size_t)a * nband + b] = s_hi > s_lo ? make_ushort2((unsigned short)s_lo, (unsigned short)s_hi) : make_ushort2(0, 0);
 }
 
-template <typename IdxT, int NQ>
-__global__ void __launch_bounds__(HB2_FWDB_THREADS, 1) k_fwd_band(BD B, int mode) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  float* tile = reinterpret_cast<float*>(dsm);
-  __shared__ unsigned long long bar;
-  __shared__ int s_pref[HB2_FWDB_MAXV + 1];
-  __shared__ unsigned short s_jlo[HB2_FWDB_MAXV], s_cnt[HB2_FWDB_MAXV];
-  __shared__ int s_ang[HB2_FWDB_MAXV];
-  const int c = blockIdx.y, b = blockIdx.x;
+// Row epilogue of the band path: a ray's partials are added over the bands it crosses, in band order, then the LSMR
+// row update / plain store / score accumulation of k_fwd_data follows (duplicate views get the rows and partial sums of
+// their first copy; half-set masks drop rows).  One CTA per (view of the candidate, candidate); a pure stream over the
+// partials (8 independent 128-bit loads in flight per thread).
+// (Tried: the last band CTA of a candidate doing this for the whole candidate while the partials are L2-resident --
+// one SM cannot keep enough loads in flight, 140-270 us per candidate, forward 15.2 -> 18.5 us per candidate-pass.)
+template <int NQ>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_band_reduce(BD B, int mode) {
+  const int c = blockIdx.y, vi = blockIdx.x;
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ ushort2 s_rng[HB2_MAX_BANDS];
+  __shared__ int s_colk[16];
   const LsmrState& S = B.st[c];
+  const int nv = B.cand_view_count[c];
+  if (vi >= nv) return;
+  const int view = B.cand_view_begin[c] + vi;
+  if (B.view_tie && B.view_tie[view] >= 0) return;  // tie views: k_fwd_tie (rows and partials)
+  if (B.view_dupof[view] >= 0) return;              // duplicate of an earlier view: written by that view's CTA
+  int dupv[HB2_MAXDUP];
+#pragma unroll
+  for (int d = 0; d < HB2_MAXDUP; ++d) dupv[d] = B.view_dups[view * HB2_MAXDUP + d];
   const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
-  if (!act) return;
-  constexpr int L3P = 4 * NQ;
-  constexpr int SPW = 32 / NQ;                       // samples per warp step
-  constexpr int P2 = SPW > 16 ? 16 : (SPW > 8 ? 8 : (SPW > 4 ? 4 : (SPW > 2 ? 2 : 1)));  // largest power of 2 < SPW
-  const int D2 = B.D2, NB = B.nband;
-  const unsigned bb = (unsigned)B.band_begin[b], bn = (unsigned)B.band_begin[b + 1] - bb;
-  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
-  const float* __restrict__ vsrc = (mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad + (size_t)bb * L3P;
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  for (int e = threadIdx.x; e < nv; e += HB2_FWDB_THREADS) {
-    const int a = B.view_angle[vb + e];
-    const ushort2 r = B.band_rng[(size_t)a * NB + b];
-    s_ang[e] = a; s_jlo[e] = r.x; s_cnt[e] = (unsigned short)(r.y - r.x); s_pref[e + 1] = ((int)r.y - (int)r.x + 31) / 32;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {  // warp 0: TMA bulk load of the band (32 KB pieces), then the prefix over views
-    const unsigned total = bn * L3P * (unsigned)sizeof(float);
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, total);
-    __syncwarp();
-    const unsigned piece = 32768u;
-    for (unsigned off = threadIdx.x * piece; off < total; off += 32u * piece)
-      bulk_g2s(dsm + off, reinterpret_cast<const unsigned char*>(vsrc) + off, min(piece, total - off), &bar);
+  if (!act) {
     if (threadIdx.x == 0) {
-      s_pref[0] = 0;
-      for (int e = 0; e < nv; ++e) s_pref[e + 1] += s_pref[e];
+#pragma unroll
+      for (int d = -1; d < HB2_MAXDUP; ++d) {
+        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+        if (vw < 0) continue;
+        if (mode == MODE_LSMR) B.part_u[vw] = 0.f;
+        if (mode == MODE_SCORE) { B.part_s[3 * vw] = 0.f; B.part_s[3 * vw + 1] = 0.f; B.part_s[3 * vw + 2] = 0.f; }
+      }
+    }
+    return;
+  }
+  constexpr int L3P = 4 * NQ;
+  const int D2 = B.D2, NB = B.nband, L3 = B.L3;
+  const int a = B.view_angle[view];
+  for (int e = threadIdx.x; e < NB; e += HB2_BLOCK) s_rng[e] = B.band_rng[(size_t)a * NB + e];
+  if (threadIdx.x < 16) s_colk[threadIdx.x] = threadIdx.x < L3 ? B.colk[B.view_colbegin[view] + threadIdx.x] : -1;
+  __syncthreads();
+  const float alpha = S.alpha, inv_beta = S.inv_beta;
+  const float* __restrict__ part = B.fwd_part + B.cand_poff[c] + (size_t)vi * NB * D2 * L3P;
+  float* urow = B.u + B.view_uoff[view];
+  const float* brow = B.b + B.view_uoff[view];
+  const uint8_t* __restrict__ pm = cand_mask(B, c);
+  const size_t bstride = (size_t)D2 * L3P / 4;  // float4 between the bands of one (ray, quad)
+  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  for (int item = threadIdx.x; item < D2 * NQ; item += HB2_BLOCK) {
+    const int j = item / NQ, q = item - j * NQ;
+    if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
+    const float4* __restrict__ pv = reinterpret_cast<const float4*>(part + (size_t)j * L3P + 4 * q);
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b0 = 0; b0 < NB; b0 += 8) {  // 8 independent loads in flight, added in band order
+      float4 t[8];
+      bool on[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        on[w] = false;
+        if (b0 + w < NB) { const ushort2 r = s_rng[b0 + w]; on[w] = j >= (int)r.x && j < (int)r.y; }
+        t[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on[w]) t[w] = __ldcs(pv + (size_t)(b0 + w) * bstride);
+      }
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (on[w]) { sum.x += t[w].x; sum.y += t[w].y; sum.z += t[w].z; sum.w += t[w].w; }
+    }
+    const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
+    const size_t r0 = (size_t)j * L3P + 4 * q;
+    bool keep[4];
+#pragma unroll
+    for (int tz = 0; tz < 4; ++tz) {
+      const int k = s_colk[4 * q + tz];
+      keep[tz] = k >= 0 && !(pm && !pm[(size_t)k * D2 + j]);
+    }
+    if (mode == MODE_LSMR || mode == MODE_PLAIN) {
+      const float4 uo = *reinterpret_cast<const float4*>(urow + r0);
+      float un[4] = {uo.x, uo.y, uo.z, uo.w};
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        if (!keep[tz]) continue;
+        if (mode == MODE_LSMR) {
+          un[tz] = fadd_(fmul_(fmul_(un[tz], inv_beta), -alpha), sv[tz]);
+          ss += un[tz] * un[tz];
+        } else {
+          un[tz] = sv[tz];
+        }
+      }
+      const float4 uw = make_float4(un[0], un[1], un[2], un[3]);
+      *reinterpret_cast<float4*>(urow + r0) = uw;
+#pragma unroll
+      for (int d = 0; d < HB2_MAXDUP; ++d)
+        if (dupv[d] >= 0) *reinterpret_cast<float4*>(B.u + B.view_uoff[dupv[d]] + r0) = uw;  // identical rows of the duplicate
+    } else {
+      const float4 bv4 = *reinterpret_cast<const float4*>(brow + r0);
+      const float bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+      for (int tz = 0; tz < 4; ++tz) {
+        if (!keep[tz]) continue;
+        const float pred = B.clip_pred ? fmaxf(sv[tz], 0.f) : sv[tz];
+        ss += pred * pred; s_pb += pred * bv[tz]; s_bb += bv[tz] * bv[tz];
+      }
     }
   }
-  __syncthreads();
-  const int total_items = s_pref[nv];
-  mbar_wait(&bar, 0u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int sl = lane / NQ, q = lane - sl * NQ;
-  const bool lane_on = sl < SPW;
-  float* __restrict__ part = B.fwd_part + B.cand_poff[c];
-  const unsigned tile_s = smem_u32(tile) + 16u * (unsigned)q;  // 32-bit shared address of this lane's quad in voxel 0
-  // A warp item = 32 consecutive rays of one view: their sample ranges arrive with ONE coalesced load, then the
-  // rays are processed HB2_FWDB_RU at a time (independent map loads / shared-memory gathers in flight).
-  int vcur = 0;
-  for (int it = warp; it < total_items; it += HB2_FWDB_THREADS / 32) {
-    while (it >= s_pref[vcur + 1]) ++vcur;
-    const int a = s_ang[vcur];
-    const int jbase = (int)s_jlo[vcur] + 32 * (it - s_pref[vcur]);
-    const int nray = min(32, (int)s_jlo[vcur] + s_cnt[vcur] - jbase);
-    const ushort2* __restrict__ segp = B.band_seg + ((size_t)a * NB + b) * D2 + jbase;
-    const ushort2 mysg = lane < nray ? __ldg(segp + lane) : make_ushort2(0, 0);
-    const IdxT* __restrict__ fbase = (const IdxT*)B.fmap + ((size_t)a * D2 + jbase) * D2;
-    float* __restrict__ pbase = part + (((size_t)vcur * NB + b) * D2 + jbase) * L3P + 4 * q;
-    for (int r0 = 0; r0 < nray; r0 += HB2_FWDB_RU) {
-      // per ray: 32-bit element offset of this lane's next sample in the map and the samples it still has to visit
-      const IdxT* fp[HB2_FWDB_RU];
-      int rem[HB2_FWDB_RU];
-      float4 acc[HB2_FWDB_RU];
-      int tmax = 0;
+  if (mode == MODE_LSMR) {
+    float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) {
+      B.part_u[view] = tot;
 #pragma unroll
-      for (int u = 0; u < HB2_FWDB_RU; ++u) {
-        const int src = min(r0 + u, 31);
-        const int lo = __shfl_sync(0xffffffffu, (int)mysg.x, src), hi = __shfl_sync(0xffffffffu, (int)mysg.y, src);
-        const int len = (r0 + u < nray) ? hi - lo : 0;
-        fp[u] = fbase + (unsigned)((r0 + u) * D2 + lo + sl);
-        rem[u] = lane_on ? len - sl : 0;
-        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        tmax = max(tmax, (len + SPW - 1) / SPW);
-      }
-#pragma unroll 1
-      for (int t = 0; t < tmax; t += HB2_FWDB_SU) {
-        // HB2_FWDB_SU steps of HB2_FWDB_RU rays: RU*SU independent map loads, then their shared-memory gathers
-        unsigned rel[HB2_FWDB_SU][HB2_FWDB_RU];
+      for (int d = 0; d < HB2_MAXDUP; ++d)
+        if (dupv[d] >= 0) B.part_u[dupv[d]] = tot;
+    }
+  } else if (mode == MODE_SCORE) {
+    float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
+    if (threadIdx.x == 0) {
 #pragma unroll
-        for (int w = 0; w < HB2_FWDB_SU; ++w)
-#pragma unroll
-          for (int u = 0; u < HB2_FWDB_RU; ++u) {
-            rel[w][u] = 0xFFFFFFFFu;
-            if (rem[u] > w * SPW) rel[w][u] = (unsigned)fp[u][w * SPW] - bb;
-          }
-#pragma unroll
-        for (int u = 0; u < HB2_FWDB_RU; ++u) { fp[u] += HB2_FWDB_SU * SPW; rem[u] -= HB2_FWDB_SU * SPW; }
-#pragma unroll
-        for (int w = 0; w < HB2_FWDB_SU; ++w)
-#pragma unroll
-          for (int u = 0; u < HB2_FWDB_RU; ++u) {
-            if (rel[w][u] < bn) {
-              const float4 tv = lds128(tile_s + rel[w][u] * (unsigned)(L3P * sizeof(float)));
-              acc[u].x += tv.x; acc[u].y += tv.y; acc[u].z += tv.z; acc[u].w += tv.w;
-            }
-          }
-      }
-      // combine the SPW sample lanes of every quad (fixed tree), one ray after the other
-#pragma unroll
-      for (int u = 0; u < HB2_FWDB_RU; ++u) {
-        int n = SPW;
-#pragma unroll
-        for (int off = P2; off >= 1; off >>= 1) {
-          const float x = __shfl_down_sync(0xffffffffu, acc[u].x, off * NQ), y = __shfl_down_sync(0xffffffffu, acc[u].y, off * NQ);
-          const float z = __shfl_down_sync(0xffffffffu, acc[u].z, off * NQ), w = __shfl_down_sync(0xffffffffu, acc[u].w, off * NQ);
-          if (sl + off < n) { acc[u].x += x; acc[u].y += y; acc[u].z += z; acc[u].w += w; }
-          n = off;
-        }
-        if (sl == 0 && r0 + u < nray) *reinterpret_cast<float4*>(pbase + (size_t)(r0 + u) * L3P) = acc[u];
+      for (int d = -1; d < HB2_MAXDUP; ++d) {
+        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+        if (vw < 0) continue;
+        B.part_s[3 * vw] = t0; B.part_s[3 * vw + 1] = t1; B.part_s[3 * vw + 2] = t2;
       }
     }
   }
 }
 
-// Band path, second layout: a lane owns one (ray, slice quad) and walks the ray's samples inside the band -- no
-// cross-lane reduction, one 128-bit store per (ray, quad) partial.  The map entries of a ray arrive 8 at a time
-// (one aligned 128-bit load per lane and 8 samples; all samples of the ray that lie in the band are contiguous, so
-// "rank inside the band" is the only test).  The band sits in shared memory with one spare record after every 32
-// voxels (HB2_FWDB2_PAD), so that adjacent rays -- one voxel row apart at shallow view angles -- fall into different
-// bank groups.
-#define HB2_FWDB2_THREADS 512
-#define HB2_FWDB2_PAD 1u   // spare records after every 32 voxels (measured: 1 -> 563 us, quad-major lanes + common sample
-                          // origin with 1 / 3 -> 807 / 773 us per 32 candidate-passes; profiles/r1_summary.md)
 template <int NQ>
-__global__ void __launch_bounds__(HB2_FWDB2_THREADS, 1) k_fwd_band2(BD B, int mode) {
+__global__ void __launch_bounds__(HB2_FWDB_THREADS, 1) k_fwd_band(BD B, int mode) {
   extern __shared__ __align__(128) unsigned char dsm[];
   __shared__ unsigned long long bar;
   __shared__ int s_pref[HB2_FWDB_MAXV + 1];
   __shared__ unsigned short s_jlo[HB2_FWDB_MAXV], s_cnt[HB2_FWDB_MAXV];
   __shared__ int s_ang[HB2_FWDB_MAXV];
+  __shared__ int s_next;
   const int c = blockIdx.y, b = blockIdx.x;
   const LsmrState& S = B.st[c];
   const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
+  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
   if (!act) return;
   constexpr int L3P = 4 * NQ;
   constexpr int RPW = 32 / NQ;                       // rays per warp item
   constexpr unsigned REC = L3P * (unsigned)sizeof(float);
   const int D2 = B.D2, NB = B.nband;
   const unsigned bb = (unsigned)B.band_begin[b], bn = (unsigned)B.band_begin[b + 1] - bb;
-  const int vb = B.cand_view_begin[c], nv = B.cand_view_count[c];
   const unsigned char* __restrict__ vsrc =
       reinterpret_cast<const unsigned char*>((mode == MODE_LSMR ? B.v : B.xs) + (size_t)c * B.npad + (size_t)bb * L3P);
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); s_next = HB2_FWDB_THREADS / 32; }
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  for (int e = threadIdx.x; e < nv; e += HB2_FWDB2_THREADS) {
-    const int a = B.view_angle[vb + e];
-    const ushort2 r = B.band_rng[(size_t)a * NB + b];
+  for (int e = threadIdx.x; e < nv; e += HB2_FWDB_THREADS) {
+    const int view = vb + e;
+    const int a = B.view_angle[view];
+    ushort2 r = B.band_rng[(size_t)a * NB + b];
+    // tie views: k_fwd_tie; duplicates of an earlier view: served by that view (the epilogue copies the rows)
+    if ((B.view_tie && B.view_tie[view] >= 0) || B.view_dupof[view] >= 0) r = make_ushort2(0, 0);
     s_ang[e] = a; s_jlo[e] = r.x; s_cnt[e] = (unsigned short)(r.y - r.x); s_pref[e + 1] = ((int)r.y - (int)r.x + RPW - 1) / RPW;
   }
   __syncthreads();
-  if (threadIdx.x < 32) {  // warp 0: TMA bulk loads, 32 voxel records per copy with one spare record after each group
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, bn * REC);
+  if (threadIdx.x < 32) {  // warp 0: TMA bulk load of the band (32 KB pieces), then the prefix over views
+    const unsigned total = bn * REC;
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, total);
     __syncwarp();
-    const unsigned ngrp = (bn + 31u) / 32u;
-    for (unsigned g = threadIdx.x; g < ngrp; g += 32u)
-      bulk_g2s(dsm + (size_t)g * (32u + HB2_FWDB2_PAD) * REC, vsrc + (size_t)g * 32u * REC, min(32u, bn - g * 32u) * REC, &bar);
+    const unsigned piece = 32768u;
+    for (unsigned off = threadIdx.x * piece; off < total; off += 32u * piece)
+      bulk_g2s(dsm + off, vsrc + off, min(piece, total - off), &bar);
     if (threadIdx.x == 0) {
       s_pref[0] = 0;
       for (int e = 0; e < nv; ++e) s_pref[e + 1] += s_pref[e];
@@ -969,11 +989,14 @@ __global__ void __launch_bounds__(HB2_FWDB2_THREADS, 1) k_fwd_band2(BD B, int mo
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rl = lane / NQ, q = lane - rl * NQ;
   const bool lane_on = rl < RPW;
+  const int lane0 = lane_on ? lane - q : lane;        // first lane of this ray's quad group
   float* __restrict__ part = B.fwd_part + B.cand_poff[c];
   const unsigned tile_s = smem_u32(dsm) + 16u * (unsigned)q;
   const uint16_t* __restrict__ fmap = (const uint16_t*)B.fmap;
+  const uint4 none = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
   int vcur = 0;
-  for (int it = warp; it < total_items; it += HB2_FWDB2_THREADS / 32) {
+  // items are handed out through a shared counter (their lengths differ with the chord of the band)
+  for (int it = warp; it < total_items;) {
     while (it >= s_pref[vcur + 1]) ++vcur;
     const int a = s_ang[vcur];
     const int j = (int)s_jlo[vcur] + RPW * (it - s_pref[vcur]) + rl;
@@ -981,115 +1004,52 @@ __global__ void __launch_bounds__(HB2_FWDB2_THREADS, 1) k_fwd_band2(BD B, int mo
     ushort2 sg = make_ushort2(0, 0);
     if (ray_on) sg = __ldg(B.band_seg + ((size_t)a * NB + b) * D2 + j);
     const int lo = sg.x, hi = sg.y;
-    const int ib = lo & ~7;
-    const int nblk = hi > lo ? (hi - ib + 7) >> 3 : 0;
-    const int tmax = __reduce_max_sync(0xffffffffu, nblk);
-    const uint4* __restrict__ fp = reinterpret_cast<const uint4*>(fmap + ((size_t)a * D2 + (ray_on ? j : 0)) * D2 + ib);
+    const bool has = hi > lo;
+    // common origin of the warp: in step g every lane is on depth samples ib + 8 g ... ib + 8 g + 7
+    const int ib = __reduce_min_sync(0xffffffffu, has ? (lo & ~7) : 0x7fffffff);
+    const int gmax = __reduce_max_sync(0xffffffffu, has ? ((hi - ib + 7) >> 3) : 0);
+    const int g_lo = has ? ((lo & ~7) - ib) >> 3 : 0x7fffffff;  // first / past-last 8-sample chunk holding samples of this ray
+    const int g_hi = has ? ((hi - ib + 7) >> 3) : 0;
+    const uint4* __restrict__ fp = reinterpret_cast<const uint4*>(fmap + ((size_t)a * D2 + (ray_on ? j : 0)) * D2 + (has ? ib : 0));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint4 nxt = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-    if (nblk > 0) nxt = __ldg(fp);
-    for (int t = 0; t < tmax; ++t) {
-      const uint4 pk = nxt;
-      nxt = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-      if (t + 1 < nblk) nxt = __ldg(fp + t + 1);
-      const unsigned wds[4] = {pk.x, pk.y, pk.z, pk.w};
-      float4 tv[8];
-      bool ok[8];
+    // the NQ lanes of a ray fetch NQ consecutive chunks of its map row (one 128-bit load each) and pass them around
+    // with shuffles: one map load per lane and 8 NQ samples
+    uint4 nxt = none;
+    if (q >= g_lo && q < g_hi) nxt = __ldg(fp + q);
+    for (int g0 = 0; g0 < gmax; g0 += NQ) {
+      const uint4 mine = nxt;
+      nxt = none;
+      if (g0 + NQ + q >= g_lo && g0 + NQ + q < g_hi) nxt = __ldg(fp + g0 + NQ + q);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const unsigned id = (e & 1) ? (wds[e >> 1] >> 16) : (wds[e >> 1] & 0xFFFFu);
-        const unsigned rel = id - bb;
-        ok[e] = rel < bn;
-        tv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok[e]) tv[e] = lds128(tile_s + (rel + HB2_FWDB2_PAD * (rel >> 5)) * REC);
+      for (int sgi = 0; sgi < NQ; ++sgi) {
+        uint4 pk;
+        if (NQ == 1) pk = mine;
+        else {
+          pk.x = __shfl_sync(0xffffffffu, mine.x, lane0 + sgi); pk.y = __shfl_sync(0xffffffffu, mine.y, lane0 + sgi);
+          pk.z = __shfl_sync(0xffffffffu, mine.z, lane0 + sgi); pk.w = __shfl_sync(0xffffffffu, mine.w, lane0 + sgi);
+        }
+        if (g0 + sgi >= gmax) break;  // warp-uniform
+        if (!lane_on) pk = none;      // spare lanes (32 is not a multiple of NQ) must not gather
+        const unsigned wds[4] = {pk.x, pk.y, pk.z, pk.w};
+        float4 tv[8];
+        bool ok[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned id = (e & 1) ? (wds[e >> 1] >> 16) : (wds[e >> 1] & 0xFFFFu);
+          const unsigned rel = id - bb;
+          ok[e] = rel < bn;
+          tv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[e]) tv[e] = lds128(tile_s + rel * REC);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (ok[e]) { acc.x += tv[e].x; acc.y += tv[e].y; acc.z += tv[e].z; acc.w += tv[e].w; }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ok[e]) { acc.x += tv[e].x; acc.y += tv[e].y; acc.z += tv[e].z; acc.w += tv[e].w; }
     }
     if (ray_on) *reinterpret_cast<float4*>(part + (((size_t)vcur * NB + b) * D2 + j) * L3P + 4 * q) = acc;
-  }
-}
-
-// sum of a ray's partials over the bands it crosses (band order) + the row epilogue of k_fwd_data.
-// One CTA per (view of the candidate, candidate).
-template <int NQ>
-__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_band_reduce(BD B, int mode) {
-  const int c = blockIdx.y, vi = blockIdx.x;
-  __shared__ float red[HB2_BLOCK / 32];
-  __shared__ ushort2 s_rng[HB2_MAX_BANDS];
-  __shared__ int s_colk[16];
-  const LsmrState& S = B.st[c];
-  const int nv = B.cand_view_count[c];
-  const int view = B.cand_view_begin[c] + vi;
-  const bool act = mode == MODE_LSMR ? (S.active != 0) : (B.only_cand < 0 || B.only_cand == c);
-  const bool has = vi < nv;
-  if (!act || !has) {
-    if (threadIdx.x == 0 && has) {
-      if (mode == MODE_LSMR) B.part_u[view] = 0.f;
-      if (mode == MODE_SCORE) { B.part_s[3 * view] = 0.f; B.part_s[3 * view + 1] = 0.f; B.part_s[3 * view + 2] = 0.f; }
-    }
-    return;
-  }
-  constexpr int L3P = 4 * NQ;
-  const int D2 = B.D2, NB = B.nband, L3 = B.L3;
-  const int a = B.view_angle[view];
-  if (threadIdx.x < NB) s_rng[threadIdx.x] = B.band_rng[(size_t)a * NB + threadIdx.x];
-  if (threadIdx.x < L3P) s_colk[threadIdx.x] = threadIdx.x < L3 ? B.colk[B.view_colbegin[view] + threadIdx.x] : -1;
-  __syncthreads();
-  const float alpha = S.alpha, inv_beta = S.inv_beta;
-  const float* __restrict__ part = B.fwd_part + B.cand_poff[c] + (size_t)vi * NB * D2 * L3P;
-  float* urow = B.u + B.view_uoff[view];
-  const float* brow = B.b + B.view_uoff[view];
-  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
-  for (int item = threadIdx.x; item < D2 * NQ; item += HB2_BLOCK) {
-    const int j = item / NQ, q = item - j * NQ;
-    if (!B.rayvalid[a * D2 + j]) continue;  // no projection data: the padded rows stay 0 (SLR:1547)
-    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int bq = 0; bq < NB; ++bq) {
-      const ushort2 r = s_rng[bq];
-      if (j >= (int)r.x && j < (int)r.y) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(part + ((size_t)bq * D2 + j) * L3P + 4 * q));
-        sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
-      }
-    }
-    const float sv[4] = {sum.x, sum.y, sum.z, sum.w};
-    const size_t r0 = (size_t)j * L3P + 4 * q;
-    if (mode == MODE_LSMR) {
-      float4 uo = *reinterpret_cast<const float4*>(urow + r0);
-      float un[4] = {uo.x, uo.y, uo.z, uo.w};
-#pragma unroll
-      for (int tz = 0; tz < 4; ++tz) {
-        if (s_colk[4 * q + tz] >= 0) {
-          un[tz] = fadd_(fmul_(fmul_(un[tz], inv_beta), -alpha), sv[tz]);
-          ss += un[tz] * un[tz];
-        }
-      }
-      *reinterpret_cast<float4*>(urow + r0) = make_float4(un[0], un[1], un[2], un[3]);
-    } else if (mode == MODE_PLAIN) {
-      float4 uo = *reinterpret_cast<const float4*>(urow + r0);
-      float un[4] = {uo.x, uo.y, uo.z, uo.w};
-#pragma unroll
-      for (int tz = 0; tz < 4; ++tz) if (s_colk[4 * q + tz] >= 0) un[tz] = sv[tz];
-      *reinterpret_cast<float4*>(urow + r0) = make_float4(un[0], un[1], un[2], un[3]);
-    } else {
-      const float4 bv4 = *reinterpret_cast<const float4*>(brow + r0);
-      const float bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
-#pragma unroll
-      for (int tz = 0; tz < 4; ++tz) {
-        if (s_colk[4 * q + tz] >= 0) {
-          const float pred = B.clip_pred ? fmaxf(sv[tz], 0.f) : sv[tz];
-          ss += pred * pred; s_pb += pred * bv[tz]; s_bb += bv[tz] * bv[tz];
-        }
-      }
-    }
-  }
-  if (mode == MODE_LSMR) {
-    float tot = block_sum(ss, red);
-    if (threadIdx.x == 0) B.part_u[view] = tot;
-  } else if (mode == MODE_SCORE) {
-    float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
-    if (threadIdx.x == 0) { B.part_s[3 * view] = t0; B.part_s[3 * view + 1] = t1; B.part_s[3 * view + 2] = t2; }
+    int nx = 0;
+    if (lane == 0) nx = atomicAdd(&s_next, 1);
+    it = __shfl_sync(0xffffffffu, nx, 0);
   }
 }
 

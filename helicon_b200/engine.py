@@ -353,6 +353,16 @@ class Batch:
             _lib.check(lib.hb2_batch_sym_rows(self._h, int(c), C.byref(n), _lib.ptr(a), _lib.ptr(b), n.value))
         return a, b
 
+    def sym_row_order(self, c):
+        """Position, inside the symmetry block of the padded row vectors, of the reference's r-th symmetry row."""
+        n = C.c_int32()
+        lib = _lib.load()
+        _lib.check(lib.hb2_batch_sym_rows(self._h, int(c), C.byref(n), None, None, 0))
+        order = np.zeros(max(n.value, 1), dtype=np.int32)
+        if n.value:
+            _lib.check(lib.hb2_batch_sym_order(self._h, int(c), _lib.ptr(order), n.value))
+        return order[: n.value]
+
     def sym_csr(self, c):
         """A_hsym, b_hsym of SLR:1289-1298 (or (None, None))."""
         a, b = self.sym_rows(c)

@@ -281,11 +281,13 @@ def lsq_reconstruct(
                         m1[set1] = 1
                         masks += [m1, 1 - m1]
                     r = batch.solve(clip_pred=int(thresh_fraction >= 0))
-                    if score_metric != "cosine":
+                    xs.append(batch.rec3d(0))
+                    if score_metric != "cosine":  # after rec3d: the operator calls below reuse the solver's work vectors
+                        x_sol = batch.x(0)
                         _, kk, jj = batch.data_row_index(0)
-                        r[0]["score"] = _metric_2d(score_metric, batch.predict(batch.x(0)), batch.data_b(),
+                        r[0]["score"] = _metric_2d(score_metric, batch.predict(x_sol), batch.data_b(),
                                                    (kk * D2 + jj), image, D2, L2, thresh_fraction)
-                    xs.append(batch.rec3d(0)); scs.append(np.float32(r[0]["score"]))
+                    scs.append(np.float32(r[0]["score"]))
                     infos.append((r[0].copy(), batch.timing()))
                 finally:
                     batch.close()

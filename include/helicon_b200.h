@@ -230,6 +230,9 @@ int hb2_batch_set_pixel_masks(hb2_batch* b, int32_t n_masks, const uint8_t* mask
 /* number of symmetry rows of a candidate, and the rows themselves as (a,b)
  * voxel-index pairs in the reference's row order: A[r,a]=+1, A[r,b]=-1. */
 int hb2_batch_sym_rows(hb2_batch* b, int32_t cand, int32_t* n_rows, int32_t* a_host, int32_t* b_host, int64_t capacity);
+/* Stored position (inside the candidate's symmetry block of the row vectors) of the reference's r-th symmetry row:
+ * the rows of one pair round are kept in the internal voxel order, SLR:1197-1202 enumerates them in mask order. */
+int hb2_batch_sym_order(hb2_batch* b, int32_t cand, int32_t* order, int64_t capacity);
 /* padded data-row count of a candidate (= view_count*D2*ZMP, ZMP = L3*MC rounded up to 4; row of (view v, ray j,
  * slice z, slot mc) = v*D2*ZMP + j*ZMP + z*MC + mc) and total padded rows incl. symmetry rows */
 int64_t hb2_batch_rows_padded(hb2_batch* b, int32_t cand, int64_t* n_data_padded);
