@@ -8,6 +8,7 @@
 #include "hb2_explicit.cuh"
 
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -15,6 +16,16 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+
+// NVTX ranges named after the reference's helicon.Timer stages (lib/logging.py:169-220; SLR:100, 131, 360 and
+// pipeline.py:405), so that a timeline of the CUDA path reads like the reference's own timing log.  Header-only NVTX3: a
+// no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
@@ -470,6 +481,7 @@ extern "C" int hb2_problem_rank_table(const hb2_problem* P, int32_t* out) {
 extern "C" int hb2_batch_begin(hb2_batch** out, hb2_problem* P, int32_t L3, int32_t MC, int32_t nA, const double* cos_sin,
                                int32_t* nvalid_rays, int32_t* tie_samples, void* stream) {
   if (!out || !P || !cos_sin || nA <= 0 || L3 <= 0 || MC <= 0) return fail(HB2_ERR_ARG, "bad argument");
+  NvtxRange nvtx_("build_A_data_matrix - nn: in-plane maps");
   if ((long long)L3 * MC > HB2_MAX_ZMC) return fail(HB2_ERR_GEOMETRY, "L3*MC exceeds HB2_MAX_ZMC");
   if ((long long)(L3 + 3) * P->ndisk >= (1ll << 31)) return fail(HB2_ERR_GEOMETRY, "too many unknowns");
   CK(cudaSetDevice(P->device));
@@ -577,6 +589,7 @@ extern "C" int hb2_batch_explicit_rows(hb2_batch* b, const hb2_explicit_geometry
                                        const double* zshift, const double* xtab, const double* ztab,
                                        int64_t min_projection_lines, int32_t* copies_used, int32_t* rows_per_copy,
                                        int64_t* n_rows, int64_t* nnz_out) {
+  NvtxRange nvtx_("build csr matrix (explicit rows: linear / tilted)");
   if (!b || !eg || ncopies <= 0 || !copy_mats || !zshift || !xtab || !ztab) return fail(HB2_ERR_ARG, "bad argument");
   if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_explicit_rows must precede hb2_batch_create");
   hb2_problem* P = b->P;
@@ -929,6 +942,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
   if (!b || !cands || nc <= 0 || !views || nviews <= 0 || !colk) return fail(HB2_ERR_ARG, "bad argument");
   if (b->created) return fail(HB2_ERR_STATE, "batch already created");
   if (nc > 65535) return fail(HB2_ERR_ARG, "at most 65535 candidates per batch");
+  NvtxRange nvtx_("build_A_data_matrix + build_A_helical_sym_matrix (batch)");
   hb2_problem* P = b->P;
   CK(cudaSetDevice(P->device));
   cudaStream_t st = b->stream;
@@ -1233,6 +1247,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     CKC(cudaStreamSynchronize(st));
   }
   // ---- symmetry rows -----------------------------------------------------------
+  NvtxRange nvtx_sym_("build_A_helical_sym_matrix - nn");
   CKC(b->pool.alloc(&b->d_sym_a, (size_t)so, false, st));
   CKC(b->pool.alloc(&b->d_sym_b, (size_t)so, false, st));
   CKC(b->pool.alloc(&b->d_sym_g, (size_t)so, false, st));
@@ -1760,6 +1775,9 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
 extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_result* res) {
   if (!b || !b->created || !opt || !res) return fail(HB2_ERR_ARG, "bad argument");
   CK(cudaSetDevice(b->P->device));
+  NvtxRange nvtx_("solve_equations + score (batch)");
+  nvtxRangePushA("solve_equations: LSMR");
+  struct PopGuard { int n = 1; ~PopGuard() { while (n-- > 0) nvtxRangePop(); } } nvtx_stage_;  // closes the open stage on every return
   BD& B = b->B;
   cudaStream_t st = b->stream;
   const int nc = B.nc;
@@ -1834,11 +1852,13 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
     k_x_to_f32<<<g, 256, 0, st>>>(B);
     ++launches;
   }
+  nvtxRangePop(); nvtxRangePushA("solve_equations: bounded TRF");
   if (opt->fixed_iters <= 0) {  // bounded branch for candidates with the positive constraint (SLR:246-270)
     int rc = run_trf(b, opt, trf, launches, trf_outer);
     if (rc != HB2_OK) return rc;
   } else trf.assign(nc, TrfState{});
   CK(cudaEventRecord(e1b, st));
+  nvtxRangePop(); nvtxRangePushA("cosine_similarity (reprojection + score)");
   // score: reprojection of float32(x) + cosine similarity
   {
     launch_fwd_data(b, MODE_SCORE);
@@ -1939,6 +1959,7 @@ extern "C" int hb2_helical_symmetrize(const float* data_host, const hb2_symm_par
                                       const int32_t* ent_h, const int32_t* ent_floor, const int32_t* ent_ceil,
                                       const double* ent_wk, const double* mats, int32_t n_mats, float* vol_out_host,
                                       float* xsum_out, float* ysum_out, float* zsum_out, int device, void* stream) {
+  NvtxRange nvtx_("apply_helical_symmetry");
   if (!data_host || !p || !k_begin || !mats) return fail(HB2_ERR_ARG, "null argument");
   if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
   if (p->nz1 <= 0 || p->ny1 <= 0 || p->nx1 <= 0 || p->csym <= 0 || p->n_ent < 0) return fail(HB2_ERR_ARG, "bad sizes");

@@ -782,7 +782,9 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_data(BD B, int mode) {
 // a time (one aligned 128-bit load per lane and 8 samples, next block
 // prefetched); "rank inside the band" is the only test per sample.
 // ===========================================================================
-#define HB2_FWDB_THREADS 512
+#ifndef HB2_FWDB_THREADS
+#define HB2_FWDB_THREADS 768
+#endif
 #define HB2_FWDB_MAXV 256
 #define HB2_MAX_BANDS 64
 

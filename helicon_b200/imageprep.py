@@ -134,3 +134,156 @@ def mutual_information_score(img1, img2):
         return float(nmi - 1.0)
     except Exception:
         return 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# prepare_data (pipeline.py:146-178) and the automatic tube diameter (pipeline.py:233-240): rotation / centring / size of
+# the filament in the image.  scipy.ndimage stands in for the scikit-image calls (parity unpinned, see the header);
+# rotate_shift_image is scipy in the reference as well.
+# ---------------------------------------------------------------------------------------------------------------------
+def _closing_ignore(bw):
+    """skimage.morphology.closing(bw, mode="ignore") with the default footprint (3 x 3 cross): dilation then erosion,
+    pixels beyond the border never decide (0 for the dilation, 1 for the erosion)."""
+    from scipy import ndimage as ndi
+
+    st = ndi.generate_binary_structure(2, 1)
+    return ndi.binary_erosion(ndi.binary_dilation(bw, st, border_value=0), st, border_value=1)
+
+
+def transform_image(image, scale=1.0, rotation=0.0, rotation_center=None, pre_translation=(0.0, 0.0),
+                    post_translation=(0.0, 0.0), mode="constant", order=1):
+    """lib/transforms.py:238-312: the affine map skimage composes there -- pre-translation, rotation / scale about
+    ``rotation_center`` (default (ny/2, nx/2)), post-translation, all in (x, y) -- applied with
+    ``scipy.ndimage.affine_transform`` (output pixel <- inverse-mapped input position, spline ``order``)."""
+    from scipy.ndimage import affine_transform
+
+    image = np.asarray(image, dtype=np.float64)
+    cy, cx = (np.array(image.shape[:2]) / 2.0) if rotation_center is None else np.asarray(rotation_center, dtype=np.float64)
+    sy, sx = (scale, scale) if np.isscalar(scale) else scale
+
+    def T(tx, ty):
+        return np.array([[1, 0, tx], [0, 1, ty], [0, 0, 1]], dtype=np.float64)
+
+    a = np.deg2rad(rotation)
+    RS = np.array([[sx * np.cos(a), -sy * np.sin(a), 0], [sx * np.sin(a), sy * np.cos(a), 0], [0, 0, 1]], dtype=np.float64)
+    fwd = T(post_translation[1], post_translation[0]) @ T(cx, cy) @ RS @ T(-cx, -cy) @ T(pre_translation[1], pre_translation[0])
+    inv = np.linalg.inv(fwd)  # (x, y) of the input for every (x, y) of the output
+    M = np.array([[inv[1, 1], inv[1, 0]], [inv[0, 1], inv[0, 0]]])  # the same map in (row, column)
+    off = np.array([inv[1, 2], inv[0, 2]])
+    nd_mode = {"constant": "constant", "edge": "nearest", "symmetric": "reflect", "reflect": "mirror", "wrap": "grid-wrap"}[mode]
+    return affine_transform(image, M, offset=off, order=order, mode=nd_mode, cval=0.0)
+
+
+def rotate_shift_image(data, angle=0, pre_shift=(0, 0), post_shift=(0, 0), rotation_center=None, order=1):
+    """lib/transforms.py:315-367 (scipy.ndimage.affine_transform in the reference as well; float32 matrix / offset)."""
+    from scipy.ndimage import affine_transform
+
+    if angle == 0 and pre_shift == [0, 0] and post_shift == [0, 0]:
+        return data * 1.0
+    ny, nx = data.shape
+    if rotation_center is None:
+        rotation_center = np.array((ny // 2, nx // 2), dtype=np.float32)
+    ang = np.deg2rad(angle)
+    m = np.array([[np.cos(ang), np.sin(ang)], [-np.sin(ang), np.cos(ang)]], dtype=np.float32)
+    offset = -np.dot(m, np.array(post_shift, dtype=np.float32).T)
+    offset += np.array(rotation_center, dtype=np.float32).T - np.dot(m, np.array(rotation_center, dtype=np.float32).T)
+    offset += -np.array(pre_shift, dtype=np.float32).T
+    return affine_transform(data, matrix=m, offset=offset, order=order, mode="constant")
+
+
+def _periodic(v, lo=-180.0, hi=180.0):
+    """lib/angular.py:84-108."""
+    import math
+
+    if lo <= v <= hi:
+        return v
+    t = math.fmod(v - lo, hi - lo)
+    return t + lo if t >= 0 else t + hi
+
+
+def estimate_helix_rotation_center_diameter(data, estimate_rotation=True, estimate_center=True, threshold=0):
+    """lib/analysis.py:645-728: intensity-weighted second moments of the (morphologically closed) support -> rotation to
+    horizontal (degrees), vertical shift to the box centre (pixels), diameter = vertical extent after the rotation."""
+    data = np.asarray(data)
+    ny, nx = data.shape
+
+    def weighted(mask, inten):
+        ys, xs = np.where(mask)
+        if len(ys) < 2:
+            return 0.0, 0.0, ny
+        w = inten[ys, xs].astype(np.float64)
+        w = w - w.min() + 1e-8
+        cw = w.sum()
+        cy, cx = (ys * w).sum() / cw, (xs * w).sum() / cw
+        uy, ux = ys - cy, xs - cx
+        i_yy, i_xx, i_xy = (uy * uy * w).sum() / cw, (ux * ux * w).sum() / cw, (uy * ux * w).sum() / cw
+        angle = np.rad2deg(0.5 * np.arctan2(2.0 * i_xy, i_yy - i_xx)) + 90.0
+        if abs(angle) > 90.0:
+            angle -= 180.0
+        return angle, (ny // 2 - cy) if estimate_center else 0.0, int(ys.max() - ys.min() + 1)
+
+    mask = _closing_ignore(data > threshold)
+    if not mask.any():
+        return 0.0, 0.0, ny
+    if estimate_rotation:
+        rotation = _periodic(weighted(mask, data)[0])
+        rotated = transform_image(data, rotation=rotation)
+    else:
+        rotation, rotated = 0.0, data
+    mask_rot = _closing_ignore(rotated > threshold)
+    if not mask_rot.any():
+        return rotation, 0.0, ny
+    _, shift_y, diameter = weighted(mask_rot, rotated)
+    return rotation, shift_y, diameter
+
+
+def auto_horizontalize(data, refine=False):
+    """webApps/denovo3D/utils.py:383-426: rotate / shift the image so that the filament is horizontal and centred; with
+    ``refine`` a Nelder-Mead search (scipy ``fmin``, xtol 1e-2) maximises the spread of the mirrored row-sum profile."""
+    data_work = np.clip(data, 0, None)
+    theta, shift_y, _ = estimate_helix_rotation_center_diameter(data)
+    if refine:
+        from scipy.optimize import fmin
+
+        def score(x):
+            tmp = rotate_shift_image(data_work, angle=x[0], post_shift=(x[1], 0))
+            y = np.sum(tmp, axis=1)[1:]
+            y = y + y[::-1]
+            return -np.std(y)
+
+        theta, shift_y = fmin(score, x0=(theta, shift_y), xtol=1e-2, disp=0)
+    return rotate_shift_image(data, angle=theta, post_shift=(shift_y, 0), order=3), theta, shift_y
+
+
+def denoise_tv_chambolle(image, weight=0.1, eps=2.0e-4, max_num_iter=200):
+    """skimage.restoration.denoise_tv_chambolle with its defaults for one 2-D image (Chambolle 2004: projected
+    gradient on the dual of the ROF model; same update, same stopping rule |dE| < eps * E0)."""
+    image = np.asarray(image, dtype=np.float64)
+    p = np.zeros((2,) + image.shape)
+    g = np.zeros_like(p)
+    d = np.zeros_like(image)
+    out, E_prev, E0 = image, 0.0, None
+    for i in range(max_num_iter):
+        if i > 0:
+            d = -p.sum(0)
+            d[1:, :] += p[0, :-1, :]
+            d[:, 1:] += p[1, :, :-1]
+            out = image + d
+        else:
+            out = image
+        E = float((d**2).sum())
+        g[0, :-1, :] = np.diff(out, axis=0)
+        g[1, :, :-1] = np.diff(out, axis=1)
+        norm = np.sqrt((g**2).sum(axis=0))[np.newaxis, ...]
+        E += weight * float(norm.sum())
+        tau = 1.0 / (2.0 * image.ndim)
+        norm = norm * (tau / weight) + 1.0
+        p = (p - tau * g) / norm
+        E /= float(image.size)
+        if i == 0:
+            E0, E_prev = E, E
+        else:
+            if abs(E_prev - E) < eps * E0:
+                break
+            E_prev = E
+    return out

@@ -5,11 +5,10 @@ reference's signature and return tuple; the solve + score runs through
 products through ``helicon_b200.transforms`` -- both on the GPU.
 
 Host side (once per task, not per voxel): image preparation and the integer geometry
-(pipeline.py:180-349), restated line for line.  What needs packages the reference
-itself imports lazily and that are outside the hot path raises ``NotImplementedError``
-with the option's name: ``denoise`` / ``horizontalize`` / automatic tube diameter (scikit-image
-restoration / radon based).  ``target_apix2d > apix2d_orig`` is served by a restatement of the scikit-image rescale
-call (``imageprep.down_scale``); tilted / refined tasks resample the display volume with ``transforms.transform_map``.
+(pipeline.py:180-349), restated line for line; the scikit-image calls of that preparation (rescale, closing, affine
+warp, TV denoising) are restated with numpy / scipy.ndimage in ``helicon_b200.imageprep`` (parity unpinned: scikit-image
+is not installed where this was built).  Still refused with ``NotImplementedError``: ``denoise`` "nl_mean" / "wavelet".
+Tilted / refined tasks resample the display volume with ``transforms.transform_map``.
 """
 
 from __future__ import annotations
@@ -48,9 +47,26 @@ def _read_mrc(path):
 
 
 def get_images_from_file(imageFile):
-    """pipeline.py:37-43."""
-    data, apix = _read_mrc(imageFile)
+    """pipeline.py:37-43: through ``mrcfile`` where it is installed (the reference's reader), else the MRC2014 reader of
+    this module."""
+    try:
+        import mrcfile
+    except ImportError:
+        data, apix = _read_mrc(imageFile)
+        return data, round(apix, 4)
+    with mrcfile.open(imageFile) as mrc:
+        apix = float(mrc.voxel_size.x)
+        data = mrc.data
     return data, round(apix, 4)
+
+
+def _image_reader():
+    """``helicon.read_image_2d`` when this module is mounted inside the helicon package (the reference's
+    tests patch that name, tests/test_denovo3D_pipeline.py:151), else the reader of this module."""
+    import sys
+
+    h = sys.modules.get("helicon")
+    return getattr(h, "read_image_2d", None) or read_image_2d
 
 
 def read_image_2d(imageFile, i):
@@ -105,7 +121,7 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
     ``(score, (x_proj, y_proj, z_sections, (rec3d, h1, h2) | None, D2, D3, L2, L3), (data_orig, imageFile, imageIndex,
     target_apix3d, target_apix2d, twist, rise, csym, tilt, psi, dy))`` or ``None`` for a blank image."""
     if data is None:
-        data = read_image_2d(imageFile, imageIndex - 1)
+        data = _image_reader()(imageFile, imageIndex - 1)
     if not np.std(data):  # pipeline.py:183-187
         logger.warning(f"WARNING: the input image {imageFile}:{imageIndex} is a blank image")
         return None
@@ -114,15 +130,28 @@ def process_one_task(ti, ntasks, data, imageFile, imageIndex, twist, rise, rise_
         data = low_high_pass_filter(data, low_pass_fraction=2 * apix2d_orig / low_pass,
                                     high_pass_fraction=2.0 / np.max(data.shape))
     if denoise:
-        _unsupported(f"denoise={denoise!r} (scikit-image restoration)")
+        if denoise == "tv":
+            from .imageprep import denoise_tv_chambolle
+
+            data = denoise_tv_chambolle(data)
+        elif denoise in ("nl_mean", "wavelet"):
+            _unsupported(f"denoise={denoise!r} (scikit-image non-local means / PyWavelets shrinkage; 'tv' is implemented)")
     if transpose > 0 or (transpose < 0 and is_vertical(data)):
         data = data.T
     if horizontalize:
-        _unsupported("horizontalize (scikit-image based auto_horizontalize)")
+        from .imageprep import auto_horizontalize
+
+        data, theta_best, shift_best = auto_horizontalize(data, refine=True)
+        logger.debug(f"Image {imageFile}-{imageIndex}: rotation={round(theta_best, 2)} deg shift={round(shift_best * apix2d_orig, 1)} A")
+    data = np.ascontiguousarray(data, dtype=np.float32)
     ny, nx = data.shape
     ny_orig, nx_orig = ny, nx
-    if tube_diameter < 0:
-        _unsupported("automatic tube diameter (tube_diameter < 0, estimate_helix_rotation_center_diameter)")
+    if tube_diameter < 0:  # pipeline.py:233-240
+        from .imageprep import estimate_helix_rotation_center_diameter
+
+        _, _, diameter = estimate_helix_rotation_center_diameter(data)
+        tube_diameter = int(min(ny, diameter) * apix2d_orig * 2.5)
+        logger.debug(f"Image {imageFile}-{imageIndex}: estimated tube diameter={tube_diameter} A")
     if tube_length < 0:  # pipeline.py:211-221
         if tube_diameter > ny * apix2d_orig / 2:
             tube_length = int(nx * apix2d_orig)

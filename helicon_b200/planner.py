@@ -495,3 +495,19 @@ class BatchPlan:
         if self._cand_views is None:
             self._build_views()
         return self._cand_view_slots
+
+
+def get_cylindrical_mask(nz, ny, nx, rmin=0, rmax=-1, return_xyz=False):
+    """lib/analysis.py:731-774: boolean (nz, ny, nx) mask of the voxels with rmin^2 <= x^2 + y^2 < rmax^2 (rmax < 0:
+    ny // 2 - 1); the order of its True entries is the reference's unknown order."""
+    k = np.arange(0, nz, dtype=np.int32) - nz // 2
+    j = np.arange(0, ny, dtype=np.int32) - ny // 2
+    i = np.arange(0, nx, dtype=np.int32) - nx // 2
+    Z, Y, X = np.meshgrid(k, j, i, indexing="ij")
+    if rmax < 0:
+        rmax = ny // 2 - 1
+    r2 = X * X + Y * Y
+    mask = r2 < rmax * rmax
+    if 0 < rmin < rmax:
+        mask &= r2 >= rmin * rmin
+    return (mask, (Z, Y, X)) if return_xyz else mask

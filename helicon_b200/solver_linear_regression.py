@@ -19,6 +19,7 @@ from . import planner
 from .engine import Batch, ExplicitBatch, Problem, build_trilinear_sym_rows
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
+from .regularized import MODELS, solve_model
 
 logger = logging.getLogger(__name__)
 
@@ -199,8 +200,10 @@ def lsq_reconstruct(
     if interpolation in ("linear10", "linear01"):
         _unsupported(f"interpolation={interpolation!r} (the reference's data and symmetry builders disagree on it, "
                      "SLR:907 vs 1401)")
-    if algorithm.get("model", "lsq") != "lsq":
-        _unsupported(f"algorithm model {algorithm.get('model')!r} (only 'lsq', SLR:243-270)")
+    model = algorithm.get("model", "lsq")
+    if model not in ("lsq", "_reproject") + MODELS:
+        _unsupported(f"algorithm model {model!r} ('lsq', SLR:243-270, and 'elasticnet' / 'lasso' / 'ridge', SLR:293-322, are "
+                     "implemented; 'lreg' / 'ard' densify the matrix)")
     if score_metric not in ("cosine", "ssim", "ms_ssim", "mutual_information", "composite"):
         raise ValueError(f"unknown score_metric {score_metric!r}")
     if score_metric != "cosine" and fsc_test:
@@ -209,8 +212,6 @@ def lsq_reconstruct(
         _unsupported(f"score_metric {score_metric!r} together with fsc_test (fails in the reference as well, SLR:507-519)")
     want_refine = refine_tilt_psi_dy_range is not None and any(
         refine_tilt_psi_dy_range.get(k, 0) > 0 for k in ("tilt", "psi", "dy"))
-    if want_refine and fsc_test:
-        _unsupported("refine_tilt_psi_dy_range together with fsc_test")
     if want_refine:
         # SLR:372-437: solve at the given orientation, then the local Gauss-Newton refinement.  For model "lsq" the
         # reference's solve_equations returns score=None (SLR:270), so its test `score is None or score_refined > score`
@@ -222,9 +223,10 @@ def lsq_reconstruct(
                   reconstruct_diameter_3d_pixel=reconstruct_diameter_3d_pixel,
                   reconstruct_length_2d_pixel=reconstruct_length_2d_pixel,
                   reconstruct_length_3d_pixel=reconstruct_length_3d_pixel, sym_oversample=sym_oversample,
-                  interpolation=interpolation, fsc_test=0, score_metric=score_metric, target_apix2d=target_apix2d,
+                  interpolation=interpolation, fsc_test=fsc_test, score_metric=score_metric, target_apix2d=target_apix2d,
                   verbose=verbose, algorithm=algorithm, refine_tilt_psi_dy_range=None, cpu=cpu, device=device)
-        (rec3d, _, _), score = lsq_reconstruct(projection_image, scale2d_to_3d, twist_degree, rise_pixel, **kw)
+        (rec3d, half1, half2), score, info0 = lsq_reconstruct(projection_image, scale2d_to_3d, twist_degree, rise_pixel,
+                                                               return_info=True, **kw)
         r = refine_tilt_psi_dy_range
         tilt_o, psi_o, dy_o, x_ref, score_ref = refine_tilt_psi_dy(
             projection_image, scale2d_to_3d, twist_degree, rise_pixel, csym, reconstruct_diameter_2d_pixel,
@@ -241,12 +243,19 @@ def lsq_reconstruct(
             rec3d = np.zeros((L3r, D3r, D3r), dtype=np.float32)
             rec3d[:, m2] = np.asarray(x_ref, dtype=np.float32).reshape(L3r, -1)
             score = score_ref
+            if fsc_test:
+                # SLR:441-528: the half sets were solved at the GIVEN orientation; every score is then recomputed, the
+                # full set's as cosine(A_data(given orientation) @ x_refined, b_data), and combined 1/2, 1/4, 1/4
+                kw0 = dict(kw, fsc_test=0, algorithm=dict(model="_reproject", x=np.asarray(x_ref, dtype=np.float32)))
+                _, s0 = lsq_reconstruct(projection_image, scale2d_to_3d, twist_degree, rise_pixel, **kw0)
+                s = info0["scores"]
+                score = np.float32(s0) / 2 + (np.float32(s[1]) + np.float32(s[2])) / 4
             if not hasattr(lsq_reconstruct, "_refined_params"):  # SLR:431-435 (consumed by pipeline.py:429-434)
                 lsq_reconstruct._refined_params = {}
             lsq_reconstruct._refined_params.update(tilt=tilt_o, psi=psi_o, dy=dy_o)
         if return_info:
-            return (rec3d, None, None), score, dict(refined=(tilt_o, psi_o, dy_o, score_ref))
-        return (rec3d, None, None), score
+            return (rec3d, half1, half2), score, dict(refined=(tilt_o, psi_o, dy_o, score_ref))
+        return (rec3d, half1, half2), score
     image = np.asarray(projection_image)
     D3, L3 = reconstruct_diameter_3d_pixel, reconstruct_length_3d_pixel
     D2 = reconstruct_diameter_2d_pixel if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
@@ -280,6 +289,15 @@ def lsq_reconstruct(
                         m1 = np.zeros(L2 * D2, dtype=np.uint8)
                         m1[set1] = 1
                         masks += [m1, 1 - m1]
+                    if model != "lsq":  # SLR:293-342 on the explicit rows (the builder already dropped a half set's rows)
+                        minfo = {}
+                        w = algorithm["x"] if model == "_reproject" else solve_model(batch, 0, algorithm, positive, info=minfo)
+                        _, kk, jj = batch.data_row_index(0)
+                        sc = _score_of(score_metric, batch.predict(w), batch.data_b(), kk * D2 + jj, image, D2, L2,
+                                       thresh_fraction)
+                        xs.append(_embed(w, L3, D3, reconstruct_diameter_3d_inner_pixel)); scs.append(np.float32(sc))
+                        infos.append((dict(model=minfo), batch.timing()))
+                        continue
                     r = batch.solve(clip_pred=int(thresh_fraction >= 0))
                     xs.append(batch.rec3d(0))
                     if score_metric != "cosine":  # after rec3d: the operator calls below reuse the solver's work vectors
@@ -294,7 +312,8 @@ def lsq_reconstruct(
             rec3d = xs[0]
             half1, half2 = (xs[1], xs[2]) if nsets == 3 else (None, None)
             score = scs[0] / 2 + (scs[1] + scs[2]) / 4 if nsets == 3 else scs[0]
-            info = dict(res=infos[0][0], all_res=np.array([i[0] for i in infos]), timing=infos[0][1])
+            info = dict(res=infos[0][0], all_res=[i[0] for i in infos] if model != "lsq" else np.array([i[0] for i in infos]),
+                        timing=infos[0][1], scores=list(scs))
             if return_info:
                 return (rec3d, half1, half2), score, info
             return (rec3d, half1, half2), score
@@ -307,6 +326,35 @@ def lsq_reconstruct(
                 m1 = np.zeros(L2 * D2, dtype=np.uint8)
                 m1[set1] = 1
                 batch.set_pixel_masks(np.stack([m1, 1 - m1]), [-1, 0, 1])
+            if model != "lsq":
+                # SLR:293-342: ElasticNet / Lasso / Ridge on the same equations, minimised with the matrix-free operator
+                # (regularized.py); the half sets of fsc_test are the masked candidates 1 and 2 of the batch
+                keeps = [None] + ([m1, 1 - m1] if nsets == 3 else [])
+                vols, scs, minfos = [], [], []
+                nd_pad = batch.rows_padded(0)[0]
+                for c in range(nsets):
+                    minfo = {}
+                    w = (algorithm["x"] if model == "_reproject"
+                         else solve_model(batch, c, algorithm, positive, row_keep=keeps[c], info=minfo))
+                    pidx, kk, jj = batch.data_row_index(c)
+                    if keeps[c] is not None:
+                        sel = keeps[c][kk * D2 + jj].astype(bool)
+                        pidx, kk, jj = pidx[sel], kk[sel], jj[sel]
+                    pred = batch.apply_forward(c, w)[:nd_pad][pidx]
+                    scs.append(np.float32(_score_of(score_metric, pred, batch.rhs_padded(c)[pidx], kk * D2 + jj, image, D2,
+                                                    L2, thresh_fraction)))
+                    vols.append(_embed(w, L3, D3, reconstruct_diameter_3d_inner_pixel))
+                    minfos.append(minfo)
+                rec3d = vols[0]
+                if nsets == 3:
+                    half1, half2 = vols[1], vols[2]
+                    score = scs[0] / 2 + (scs[1] + scs[2]) / 4  # SLR:527-528
+                else:
+                    score = scs[0]
+                if return_info:
+                    return (rec3d, half1, half2), score, dict(model=minfos[0], all_models=minfos, timing=batch.timing(),
+                                                              scores=list(scs))
+                return (rec3d, half1, half2), score
             res = batch.solve(clip_pred=int(thresh_fraction >= 0))
             rec3d = batch.rec3d(0)
             if score_metric != "cosine":
@@ -320,7 +368,8 @@ def lsq_reconstruct(
                 score = s[0] / 2 + (s[1] + s[2]) / 4
             else:
                 score = np.float32(res[0]["score"])
-            info = dict(res=res[0].copy(), all_res=res.copy(), timing=batch.timing())
+            info = dict(res=res[0].copy(), all_res=res.copy(), timing=batch.timing(),
+                        scores=[np.float32(r["score"]) for r in res])
         finally:
             batch.close()
     finally:
@@ -328,6 +377,23 @@ def lsq_reconstruct(
     if return_info:
         return (rec3d, half1, half2), score, info
     return (rec3d, half1, half2), score
+
+
+def _embed(x, L3, D3, D3_inner):
+    """SLR:536-540: the unknowns scattered into the (L3, D3, D3) volume through the cylinder mask."""
+    vol = np.zeros((L3, D3, D3), dtype=np.float32)
+    vol[:, _disk_mask(D3, D3_inner / 2, D3 // 2 - 1)] = np.asarray(x, dtype=np.float32).reshape(L3, -1)
+    return vol
+
+
+def _score_of(score_metric, pred, b_data, pid, image, D2, L2, thresh_fraction):
+    """SLR:484-525 for a prediction already on the host (model branch: the reprojection is one operator apply)."""
+    if score_metric != "cosine":
+        return _metric_2d(score_metric, pred, b_data, pid, image, D2, L2, thresh_fraction)
+    pred = np.asarray(pred, dtype=np.float32)
+    if thresh_fraction >= 0:
+        pred = np.clip(pred, 0, None)
+    return planner_cosine(pred, np.asarray(b_data, dtype=np.float32))
 
 
 def _metric_2d(score_metric, pred, b_data, pid, image, D2, L2, thresh_fraction):

@@ -15,9 +15,18 @@ import sys
 
 SRC = "/root/reference/src/helicon"
 DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "helicon")
+# the reference's own tests of the path: run against helicon_b200 through the module alias of
+# INTEGRATION.md by tests/test_reference_contract.py; copied next to the package, git-ignored like it
+TESTS = ("test_denovo3D_solver.py", "test_denovo3D_pipeline.py")
+TSRC = "/root/reference/tests"
+TDST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_tests")
 
 
 def build_ref(force=False):
+    if os.path.isdir(TSRC) and (force or not os.path.isdir(TDST)):
+        os.makedirs(TDST, exist_ok=True)
+        for t in TESTS:
+            shutil.copyfile(os.path.join(TSRC, t), os.path.join(TDST, t))
     if not os.path.isdir(SRC):
         return os.path.isdir(DST)
     if os.path.isdir(DST) and not force:

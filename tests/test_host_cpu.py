@@ -266,3 +266,38 @@ def test_2d_metrics_defining_properties():
     assert M.ssim_score(z, z) == 0.0 and M.ms_ssim_score(z, z) == 0.0
     with pytest.raises(ValueError):
         M.ssim_score(a, a[:10])
+
+
+def test_horizontalize_and_diameter_estimate_on_a_synthetic_filament():
+    """imageprep.estimate_helix_rotation_center_diameter / auto_horizontalize (lib/analysis.py:645-728,
+    webApps/denovo3D/utils.py:383-426; scipy.ndimage restatement of the scikit-image calls, parity unpinned): a band of
+    known width, rotated by a known angle and shifted, is brought back to horizontal and to the box centre."""
+    from helicon_b200 import imageprep as M
+
+    ny = nx = 128
+    yy, xx = np.mgrid[0:ny, 0:nx].astype(np.float64)
+    band = np.exp(-((yy - ny // 2) ** 2) / (2 * 6.0**2)) * (1 + 0.2 * np.cos(xx / 4.0))
+    band[band < 0.05] = 0
+    rot, sh, diam = M.estimate_helix_rotation_center_diameter(band)
+    assert abs(rot) < 0.5 and abs(sh) < 0.5 and 25 <= diam <= 40
+    tilted = M.rotate_shift_image(band, angle=12.0, post_shift=(5.0, 0.0), order=1)
+    rot, sh, diam = M.estimate_helix_rotation_center_diameter(tilted)
+    fixed, theta, shift = M.auto_horizontalize(tilted, refine=True)
+    prof = fixed.sum(axis=1)
+    assert abs(float((np.arange(ny) * prof).sum() / prof.sum()) - ny // 2) < 1.0      # centred
+    r2, _, d2 = M.estimate_helix_rotation_center_diameter(np.where(fixed > 0.05, fixed, 0))  # cubic ripples off
+    assert abs(r2) < 1.0 and abs(abs(theta) - 12.0) < 1.0 and 25 <= d2 <= 45            # horizontal again
+    # transform_image: identity, and a pure rotation about the centre keeps the centre pixel's neighbourhood mass
+    assert np.allclose(M.transform_image(band), band)
+    assert abs(M.transform_image(band, rotation=90.0).sum() - band[:, 1:].sum()) < 0.05 * band.sum()
+
+
+def test_tv_denoise_reduces_noise_and_keeps_the_mean():
+    from helicon_b200 import imageprep as M
+
+    rng = np.random.default_rng(0)
+    clean = np.zeros((64, 64)); clean[20:44, 16:48] = 1.0
+    noisy = clean + 0.3 * rng.standard_normal(clean.shape)
+    out = M.denoise_tv_chambolle(noisy)
+    assert np.abs(out - clean).mean() < 0.6 * np.abs(noisy - clean).mean()
+    assert abs(out.mean() - noisy.mean()) < 1e-6

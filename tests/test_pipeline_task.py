@@ -31,7 +31,7 @@ def test_unsupported_options_fail_loudly():
     from helicon_b200 import pipeline
 
     d = load("task_a")
-    for over in (dict(denoise="tv"), dict(horizontalize=1), dict(tube_diameter=-1)):
+    for over in (dict(denoise="nl_mean"), dict(denoise="wavelet")):
         with pytest.raises(NotImplementedError):
             pipeline.process_one_task(**_kw(d, **over))
 
