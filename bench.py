@@ -569,7 +569,7 @@ def main():
     traffic, traffic_note = None, "no capture"
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-        per_cand = tj["dram_bytes_per_launch"]["k_fwd_data"] / tj["candidates_per_launch"]
+        per_cand = sum(tj["dram_bytes_per_launch"][k] for k in ("k_fwd_band", "k_fwd_band_reduce")) / tj["candidates_per_launch"]
         traffic = per_cand * itn_rank / fwd_launches
         traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of the kernel from " + tj["source"] +
                         f": {per_cand / 1e6:.2f} MB per candidate-pass x {itn_rank / fwd_launches:.1f} active candidates per "
@@ -600,22 +600,27 @@ def main():
                  launches_per_call=int(launches_e2e),
                  note="search_grid(): host image -> Problem upload, host planning, solve, device score map + top-K, ONE "
                       "all-gather at N > 1, maps copied back; bytes are per search_grid() call"),
-        roofline=dict(bound="hbm", kernel="k_fwd_data (forward projector u <- A v - alpha u)", achieved=achieved,
+        roofline=dict(bound="hbm", kernel="k_fwd_band + k_fwd_band_reduce (forward projector u <- A v - alpha u: voxel bands "
+                                         "staged in shared memory by TMA, partial ray sums, streaming row epilogue)",
+                      achieved=achieved,
                       peak=peak, unit="GB/s", frac=achieved / peak if peak else None, traffic=traffic,
                       traffic_source=traffic_note,
                       algorithmic_bytes_per_launch=fwd_bytes / fwd_launches,
-                      on_chip="the kernel is bound on chip, not by HBM (see roofline_onchip and profiles/): DRAM traffic = "
-                              "algorithmic bytes, the time goes into moving the gathered slices through the L1 data pipe",
+                      on_chip="the kernel is bound on chip, not by HBM (see roofline_onchip and profiles/r2_summary.md): the "
+                              "time goes into moving the gathered slices through the shared-memory data pipe (82 % busy); "
+                              "DRAM traffic above the algorithmic bytes = the partial ray sums of the band decomposition "
+                              "(written once, read once)",
                       peak_source=peak_src, avg_launch_ms=fwd_ms / fwd_launches,
                       note="achieved = algorithmic bytes (4n + 8 m_data per active candidate-iteration) / summed "
-                           "CUDA-event time of the kernel's launches inside the timed region (rank 0)"),
-        roofline_onchip=dict(kernel="k_fwd_data", bytes_gathered_per_pass=gather_bytes / max(1.0, itn_rank),
+                           "CUDA-event time of the two kernels' launches inside the timed region (rank 0)"),
+        roofline_onchip=dict(kernel="k_fwd_band + k_fwd_band_reduce", bytes_gathered_per_pass=gather_bytes / max(1.0, itn_rank),
                              lsu_wavefronts_per_pass=gather_bytes / max(1.0, itn_rank) / 128.0,
                              floor_us=floor_us, achieved_us=pass_us, frac=floor_us / pass_us if pass_us > 0 else None,
                              note="floor = (non-duplicate views x in-disk samples x L3P slices x 4 B) / (148 SMs x 128 B/clk "
-                                  "x SM clock): every gathered slice value crosses the L1/shared-memory data pipe once, "
-                                  "whichever memory serves it; achieved = device time of the kernel per active "
-                                  "candidate-pass"),
+                                  "x SM clock): every gathered slice value crosses the shared-memory data pipe once; achieved "
+                                  "= device time of the two kernels per active candidate-pass (ncu, profiles/r2_summary.md: "
+                                  "2.8 M wavefronts per pass = 2.3x the floor -- ragged ray segments, pure-column steps, map "
+                                  "shuffles)"),
         roofline_iteration=dict(
             bound="hbm", achieved=iter_bytes / (stats["lsmr_ms"] / 1e3) / 1e9 if stats["lsmr_ms"] > 0 else 0.0, peak=peak,
             unit="GB/s", frac=(iter_bytes / (stats["lsmr_ms"] / 1e3) / 1e9 / peak) if stats["lsmr_ms"] > 0 and peak else None,

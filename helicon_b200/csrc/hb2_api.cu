@@ -4,6 +4,7 @@
 #include "hb2_trf.cuh"
 #include "hb2_symm.cuh"
 #include "hb2_tie.cuh"
+#include "hb2_fwd_band.cuh"
 #include "hb2_adj_tile.cuh"
 #include "hb2_explicit.cuh"
 
@@ -216,7 +217,7 @@ struct hb2_batch {
   size_t adj_tile_smem = 0;
   int adj_chunks = 1;  // adj_tile == 2: chunks of 16 slices
   bool want_tie_info = false;
-  size_t fwd_band_smem = 0;
+  size_t fwd_band_smem = 0, fwd_band_smem64 = 0;
   // tie views (hb2_batch_set_ties)
   int n_tie = 0, tie_TS = 0;
   std::vector<int8_t> h_tie_zlo;
@@ -937,6 +938,67 @@ extern "C" int hb2_batch_set_ties(hb2_batch* b, int32_t n_tie, int32_t TS, const
   return HB2_OK;
 }
 
+// Band tables of the forward band path for one element size (hb2_fwd_band.cuh).  Bands = contiguous runs of the
+// band-column-major voxel order: whole 16-row bands of the disk merged while they fit ~200 KB of shared memory, a band
+// that does not fit is cut at column boundaries (multiples of 16 ranks).  Partial rows are compact: view_poff[view] +
+// band_off[angle][band] + (j - jlo).  On any limit (too many bands) the table stays empty and the gather kernel runs.
+static int build_band_tab(hb2_batch* b, size_t elem, BandTab& out, size_t& smem_out) {
+  BD& B = b->B;
+  hb2_problem* P = b->P;
+  cudaStream_t st = b->stream;
+  const int D2 = B.D2;
+  out = BandTab{};
+  const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)elem);
+  const long long cap16 = cap / 16 * 16;
+  if (cap16 < 16) return HB2_OK;
+  std::vector<int> bands{0};
+  const std::vector<int>& tr = P->h_tilerow_begin;
+  for (size_t r = 0; r + 1 < tr.size(); ++r) {
+    const int lo = tr[r], hi = tr[r + 1];
+    if (hi - bands.back() <= cap) continue;            // the 16-row band joins the open band
+    if (lo > bands.back()) bands.push_back(lo);        // close the open band in front of it
+    while (hi - bands.back() > cap) bands.push_back(bands.back() + (int)cap16);  // cut at column boundaries
+  }
+  bands.push_back(B.ndisk);
+  const int NB = (int)bands.size() - 1;
+  if (NB > HB2_MAX_BANDS) return HB2_OK;
+  int max_bn = 0;
+  for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
+  smem_out = (size_t)max_bn * B.L3P * elem;
+#define CKB2(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+  CKB2(upload(b->pool, &out.band_begin, bands, st));
+  ushort2 *d_seg, *d_rng;
+  CKB2(b->pool.alloc(&d_seg, (size_t)B.nA * NB * D2, false, st));
+  CKB2(b->pool.alloc(&d_rng, (size_t)B.nA * NB, false, st));
+  const long long nt = (long long)B.nA * NB * D2;
+  k_band_segs<uint16_t><<<cdiv(nt, 256), 256, 0, st>>>(B.nA, NB, D2, out.band_begin, (const uint16_t*)b->d_fmap, d_seg);
+  k_band_rng<<<dim3(NB, B.nA), HB2_BLOCK, 0, st>>>(NB, D2, d_seg, d_rng);
+  CKB2(cudaGetLastError());
+  std::vector<ushort2> h_rng((size_t)B.nA * NB);
+  CKB2(cudaMemcpyAsync(h_rng.data(), d_rng, sizeof(ushort2) * h_rng.size(), cudaMemcpyDeviceToHost, st));
+  CKB2(cudaStreamSynchronize(st));
+  std::vector<int> band_off((size_t)B.nA * NB), rows_of_angle(B.nA, 0);
+  for (int a = 0; a < B.nA; ++a) {
+    int acc = 0;
+    for (int q = 0; q < NB; ++q) {
+      band_off[(size_t)a * NB + q] = acc;
+      acc += (int)h_rng[(size_t)a * NB + q].y - (int)h_rng[(size_t)a * NB + q].x;
+    }
+    rows_of_angle[a] = acc;
+  }
+  const int nviews = (int)b->h_view_angle.size();
+  std::vector<long long> view_poff(std::max(nviews, 1), 0);
+  long long total = 0;
+  for (int v = 0; v < nviews; ++v) { view_poff[v] = total; total += rows_of_angle[b->h_view_angle[v]]; }
+  CKB2(upload(b->pool, &out.band_off, band_off, st));
+  CKB2(upload(b->pool, &out.view_poff, view_poff, st));
+  uint8_t* part;
+  CKB2(b->pool.alloc(&part, (size_t)std::max<long long>(total, 1) * B.L3P * elem, false, st));
+#undef CKB2
+  out.part = part; out.seg = d_seg; out.rng = d_rng; out.nband = NB;
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* cands, int32_t nviews, const hb2_view* views,
                                 int32_t ncolk, const int32_t* colk, int32_t npairs, const hb2_pair* pairs) {
   if (!b || !cands || nc <= 0 || !views || nviews <= 0 || !colk) return fail(HB2_ERR_ARG, "bad argument");
@@ -1185,46 +1247,28 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     B.part_v_per_cand = B.adj_tile ? B.ntile * b->adj_chunks : cdiv((long long)B.ndisk * (B.L3P / 4), HB2_BLOCK);
   }
   B.part_x_per_cand = cdiv(B.npad, HB2_BLOCK * 4);
-  // ---- forward band path: bands of tile-rows that fit shared memory, ray segments per (angle, band) -------------
-  B.fwd_band = 0; B.fwd_ppv = ntiles; B.nband = 0;
+  // ---- forward band path: bands that fit shared memory, ray segments per (angle, band), compact partial rows -------
+  B.fwd_band = 0; B.fwd_ppv = ntiles; B.bt32 = BandTab{}; B.bt64 = BandTab{};
   {
     int max_views = 0;
     for (int c = 0; c < nc; ++c) max_views = std::max(max_views, b->h_view_count[c]);
     b->max_views = max_views;
-    // Default whenever it applies (one column slot per slice, <= 16 slices, 16-bit maps, a band of 16 voxel rows fits
-    // shared memory); HB2_FWD_BAND=0 forces the gather kernel (tests compare the two).
+    // Default whenever it applies (one column slot per slice, <= 16 slices, 16-bit maps); HB2_FWD_BAND=0 forces the
+    // gather kernels (tests compare the two), HB2_FWD_BAND=1 keeps the float64 operator of the bounded branch on them.
     const char* use_band = getenv("HB2_FWD_BAND");
-    const long long cap = (long long)(200 * 1024) / (B.L3P * (long long)sizeof(float));
-    std::vector<int> bands{0};
-    const int band_mode = use_band ? atoi(use_band) : 1;
-    bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->idx16 && D2 % 8 == 0 &&
-              !b->explicit_rows;
-    const std::vector<int>& tr = P->h_tilerow_begin;
-    for (size_t r = 0; ok && r + 1 < tr.size(); ++r) {
-      if (tr[r + 1] - tr[r] > cap) { ok = false; break; }
-      if (tr[r + 1] - bands.back() > cap) bands.push_back(tr[r]);
-    }
-    bands.push_back(B.ndisk);
-    const int NB = (int)bands.size() - 1;
-    if (ok && NB <= HB2_MAX_BANDS) {
-      int max_bn = 0;
-      for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
-      b->fwd_band_smem = (size_t)max_bn * B.L3P * sizeof(float);
-      CKC(upload(b->pool, &B.band_begin, bands, st));
-      ushort2 *d_seg, *d_rng;
-      CKC(b->pool.alloc(&d_seg, (size_t)B.nA * NB * D2, false, st));
-      CKC(b->pool.alloc(&d_rng, (size_t)B.nA * NB, false, st));
-      const long long nt = (long long)B.nA * NB * D2;
-      if (b->idx16) k_band_segs<uint16_t><<<cdiv(nt, 256), 256, 0, st>>>(B.nA, NB, D2, B.band_begin, (const uint16_t*)b->d_fmap, d_seg);
-      else k_band_segs<uint32_t><<<cdiv(nt, 256), 256, 0, st>>>(B.nA, NB, D2, B.band_begin, (const uint32_t*)b->d_fmap, d_seg);
-      k_band_rng<<<dim3(NB, B.nA), HB2_BLOCK, 0, st>>>(NB, D2, d_seg, d_rng);
-      CKL();
-      std::vector<long long> poff(nc);
-      long long po = 0;
-      for (int c = 0; c < nc; ++c) { poff[c] = po; po += (long long)b->h_view_count[c] * NB * D2 * B.L3P; }
-      CKC(upload(b->pool, &B.cand_poff, poff, st));
-      CKC(b->pool.alloc(&B.fwd_part, (size_t)std::max<long long>(po, 1), false, st));
-      B.band_seg = d_seg; B.band_rng = d_rng; B.nband = NB; B.fwd_band = 1; B.fwd_ppv = 1;
+    const int band_mode = use_band ? atoi(use_band) : 2;
+    const bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->idx16 && D2 % 8 == 0 &&
+                    !b->explicit_rows;
+    bool any_positive = false;
+    for (int c = 0; c < nc; ++c) any_positive = any_positive || cands[c].positive != 0;
+    if (ok) {
+      int rc = build_band_tab(b, sizeof(float), B.bt32, b->fwd_band_smem);
+      if (rc != HB2_OK) { b->pool.free_all(); return rc; }
+      if (B.bt32.nband > 0) { B.fwd_band = 1; B.fwd_ppv = 1; }
+      if (B.fwd_band && band_mode > 1 && any_positive) {
+        rc = build_band_tab(b, sizeof(double), B.bt64, b->fwd_band_smem64);
+        if (rc != HB2_OK) { b->pool.free_all(); return rc; }
+      }
     }
   }
   CKC(b->pool.alloc(&B.part_u, (size_t)B.part_u_n, true, st));
@@ -1488,12 +1532,12 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   }
   if (B.fwd_band) {
     const size_t sm = b->fwd_band_smem;
-    const dim3 gb(B.nband, B.nc), gr(b->max_views, B.nc);
+    const dim3 gb(B.bt32.nband, B.nc), gr(b->max_views, B.nc);
 #define FWB(Q)                                                                                            \
   do {                                                                                                    \
-    hb2_allow_big_smem((const void*)k_fwd_band<Q>);                                                       \
-    k_fwd_band<Q><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, mode);                                             \
-    k_fwd_band_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                              \
+    hb2_allow_big_smem((const void*)k_fwd_band<Q, float, false>);                                         \
+    k_fwd_band<Q, float, false><<<gb, HB2_FWDB_THREADS, sm, st>>>(B, TD{}, nullptr, mode);                \
+    k_fwd_band_reduce<Q, float, false><<<gr, HB2_BLOCK, 0, st>>>(B, TD{}, nullptr, mode);                 \
   } while (0)
     if (B.L3P == 4) FWB(1); else if (B.L3P == 8) FWB(2); else if (B.L3P == 12) FWB(3); else FWB(4);
     b->extra_launches += 1;
@@ -1676,7 +1720,18 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   auto red = [&](int nslots, int add, int gate, int start = 0) { k_trf_reduce<<<nc, HB2_BLOCK, 0, st>>>(B, T, nslots, add, gate, start); ++launches; };
   auto sc = [&](int op) { k_trf_scal<<<g_sc, 128, 0, st>>>(B, T, op, EPS, lsmr_maxiter, max_iter); ++launches; };
   auto fwd = [&](const double* src, double* dst, int gate) {
-    if (b->idx16) k_fwd64_data<uint16_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+    if (B.bt64.nband > 0) {  // float64 instantiation of the band path (bands of half the voxels)
+      const dim3 gb(B.bt64.nband, nc), gr(b->max_views, nc);
+#define FWB64(Q)                                                                                          \
+  do {                                                                                                    \
+    hb2_allow_big_smem((const void*)k_fwd_band<Q, double, true>);                                         \
+    k_fwd_band<Q, double, true><<<gb, HB2_FWDB_THREADS, b->fwd_band_smem64, st>>>(B, T, src, gate);       \
+    k_fwd_band_reduce<Q, double, true><<<gr, HB2_BLOCK, 0, st>>>(B, T, dst, gate);                        \
+  } while (0)
+      if (B.L3P == 4) FWB64(2); else if (B.L3P == 8) FWB64(4); else if (B.L3P == 12) FWB64(6); else FWB64(8);
+#undef FWB64
+      ++launches;
+    } else if (b->idx16) k_fwd64_data<uint16_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     else k_fwd64_data<uint32_t><<<g_fwd, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     launches += 2;

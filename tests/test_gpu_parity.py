@@ -419,6 +419,22 @@ def test_alternative_kernel_paths_agree_with_default(env, monkeypatch):
         assert np.linalg.norm(a - b) <= 5e-3 * np.linalg.norm(a)
 
 
+def test_float64_band_forward_agrees_with_the_gather_kernel(solver, monkeypatch):
+    """Bounded branch: the float64 instantiation of the forward band kernel (default) against the float64 gather kernel
+    (HB2_FWD_BAND=1) on the same bounded solve -- float64 sums in another order: same TRF iteration count, x to 1e-9."""
+    d = load("solve_nn_unb_64")
+    apix, twist, rise, csym, pc, so, L3 = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    kw = dict(positive_constraint=1, reconstruct_diameter_2d_pixel=N, reconstruct_length_2d_pixel=N,
+              reconstruct_diameter_3d_pixel=N, reconstruct_length_3d_pixel=int(L3), sym_oversample=int(so), return_info=True)
+    (r0, _, _), s0, i0 = solver.lsq_reconstruct(img, 1.0, float(twist), float(rise / apix), int(csym), **kw)
+    monkeypatch.setenv("HB2_FWD_BAND", "1")
+    (r1, _, _), s1, i1 = solver.lsq_reconstruct(img, 1.0, float(twist), float(rise / apix), int(csym), **kw)
+    assert i0["res"]["trf_nit"] > 0 and i0["res"]["trf_nit"] == i1["res"]["trf_nit"]
+    assert np.linalg.norm(r0 - r1) <= 1e-6 * np.linalg.norm(r1) and abs(float(s0) - float(s1)) <= 1e-6
+
+
 def test_grid_scores_best_and_topk_vs_reference_grid():
     """North-star criterion on a small grid: 5 twists x 4 rises on a 64x64 filament solved by the REFERENCE
     (tests/golden/grid_64.npz, oracle/make_golden_grid.py) vs ONE batched GPU solve of the 20 candidates:
