@@ -101,6 +101,8 @@ EXPORTS = [
     "hb2_lsmr_scalar_step", "hb2_batch_trf_trace", "hb2_stream_create", "hb2_stream_destroy", "hb2_device_trim", "hb2_helical_symmetrize", "hb2_batch_set_ties",
     "hb2_batch_set_pixel_masks", "hb2_batch_add_exact_maps", "hb2_batch_explicit_rows", "hb2_batch_explicit_export", "hb2_batch_explicit_sym_rows",
     "hb2_batch_explicit_sym_export", "hb2_batch_explicit_pixel_mask",
+    "hb2_batch_bilinear_maps", "hb2_batch_bilinear_ray_valid", "hb2_batch_bilinear_views", "hb2_batch_bilinear_sym_rows",
+    "hb2_batch_bilinear_sym_export",
     "hb2_scoremap_create", "hb2_scoremap_destroy", "hb2_scoremap_device_ptr", "hb2_batch_scatter_scores",
     "hb2_scoremap_merge", "hb2_scoremap_topk", "hb2_scoremap_read",
 ]
@@ -143,6 +145,11 @@ def load():
     lib.hb2_batch_explicit_pixel_mask.argtypes = [vp, vp]
     lib.hb2_batch_explicit_export.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.hb2_batch_set_pixel_masks.argtypes = [vp, i32, vp, vp]
+    lib.hb2_batch_bilinear_maps.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp]
+    lib.hb2_batch_bilinear_ray_valid.argtypes = [vp, vp]
+    lib.hb2_batch_bilinear_views.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.hb2_batch_bilinear_sym_rows.argtypes = [vp, i32, i32, vp, i64, P(i64)]
+    lib.hb2_batch_bilinear_sym_export.argtypes = [vp, i32, vp, vp]
     lib.hb2_batch_create.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp]
     lib.hb2_batch_destroy.argtypes = [vp]
     lib.hb2_batch_destroy.restype = None

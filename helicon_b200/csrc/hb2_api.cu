@@ -7,6 +7,7 @@
 #include "hb2_fwd_band.cuh"
 #include "hb2_adj_tile.cuh"
 #include "hb2_explicit.cuh"
+#include "hb2_bilinear.cuh"
 
 #include <cub/cub.cuh>
 #include <nvtx3/nvToolsExt.h>
@@ -239,6 +240,25 @@ struct hb2_batch {
   int* d_ls_col = nullptr;
   float* d_ls_w = nullptr;
   uint16_t* d_amap_i = nullptr;
+  // matrix-free trilinear rows (hb2_batch_bilinear_*)
+  bool bilinear = false;
+  int bil_nM = 0;
+  std::vector<uint8_t> h_bil_rv;                 // [nM][D2]
+  std::vector<int> h_bil_view_map, h_bil_colk, h_bil_cand_nview;
+  std::vector<double> h_bil_ab;
+  std::vector<int2*> ls_ent_c;                   // per candidate: trilinear symmetry rows, 16 entries each
+  std::vector<int> ls_m_c;
+  struct LsScratch {
+    long long cap_rows = 0, sort_cap = 0;
+    int pairs_cap = 0;
+    LsymPair* pairs = nullptr;
+    unsigned long long *tab_key = nullptr, *tab_seq = nullptr;
+    int *tmp_a = nullptr, *tmp_b = nullptr, *flag = nullptr, *pos = nullptr, *ov = nullptr;
+    void* scan_tmp = nullptr; size_t scan_bytes = 0;
+    int *col = nullptr; float* w = nullptr;      // unpacked rows of the candidate being built
+    int *key = nullptr, *key2 = nullptr, *id = nullptr, *id2 = nullptr, *cc = nullptr;
+    void* sort_tmp = nullptr; size_t sort_bytes = 0;
+  } ls_scr;
   long long extra_launches = 0;  // kernels beyond one per launch_* call (band path: projector + reduce)
   int max_views = 0;
   bool created = false;
@@ -926,6 +946,314 @@ static cudaError_t upload(DevPool& pool, const T** dst, const std::vector<T>& sr
   return e;
 }
 
+// ---------------------------------------------------------------------------
+// Matrix-free trilinear rows (hb2_bilinear.cuh)
+// ---------------------------------------------------------------------------
+// In-plane bilinear footprint maps.  build_tables = 0: only ray validity and tie counts (the host decides from them which
+// views need exact per-column maps); 1: also the transposed maps and the forward lists the kernels use (call once, with
+// ALL maps of the batch).  xrows / zrows [n_tab_rows][D2]: rows of the reference's coordinate tables (SLR:1712-1719)
+// that maps[].xrow / zrow index.
+extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilinear_map* maps, int32_t n_tab_rows,
+                                       const double* xrows, const double* zrows, int32_t build_tables,
+                                       int32_t* nvalid_rays, int32_t* tie_samples) {
+  if (!b || nM <= 0 || !maps || n_tab_rows < 0 || (n_tab_rows > 0 && (!xrows || !zrows))) return fail(HB2_ERR_ARG, "bad argument");
+  if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_bilinear_maps must precede hb2_batch_create");
+  static_assert(sizeof(BilMap) == sizeof(hb2_bilinear_map), "hb2_bilinear_map layout");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  NvtxRange nvtx_("build_A_data_matrix - linear: in-plane bilinear maps");
+  if (B.s != 1.0 || B.MC != 1) return fail(HB2_ERR_GEOMETRY, "matrix-free trilinear rows need scale2d_to_3d == 1");
+  if (B.L3P > 16) return fail(HB2_ERR_GEOMETRY, "matrix-free trilinear rows need L3 <= 16");
+  if (!P->tile_ok) return fail(HB2_ERR_GEOMETRY, "HB2_TILE_H*HB2_TILE_W must be <= 256");
+  const int D2 = B.D2;
+  for (int m = 0; m < nM; ++m)
+    if (maps[m].xrow >= n_tab_rows || maps[m].zrow >= n_tab_rows) return fail(HB2_ERR_ARG, "bad table row index");
+  DevPool tmp;
+  tmp.owner = b;
+  DevPool& keep = build_tables ? b->pool : tmp;  // probe calls keep nothing
+#define CKM(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { tmp.free_all(); return fail(HB2_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } } while (0)
+  BilMap* d_maps; double *d_x = nullptr, *d_z = nullptr; uint8_t* d_rv; int* d_tie;
+  CKM(keep.alloc(&d_maps, (size_t)nM, false, st));
+  CKM(cudaMemcpyAsync(d_maps, maps, sizeof(BilMap) * nM, cudaMemcpyHostToDevice, st));
+  CKM(keep.alloc(&d_x, (size_t)std::max(n_tab_rows, 1) * D2, false, st));
+  CKM(keep.alloc(&d_z, (size_t)std::max(n_tab_rows, 1) * D2, false, st));
+  if (n_tab_rows > 0) {
+    CKM(cudaMemcpyAsync(d_x, xrows, sizeof(double) * n_tab_rows * D2, cudaMemcpyHostToDevice, st));
+    CKM(cudaMemcpyAsync(d_z, zrows, sizeof(double) * n_tab_rows * D2, cudaMemcpyHostToDevice, st));
+  }
+  CKM(keep.alloc(&d_rv, (size_t)nM * D2, true, st));
+  CKM(keep.alloc(&d_tie, (size_t)nM, true, st));
+  k_bil_rayvalid<<<cdiv((long long)nM * D2 * D2, 256), 256, 0, st>>>(nM, D2, B.L3, d_maps, d_x, d_z, P->d_rank_data, d_rv, d_tie);
+  CKM(cudaGetLastError());
+  std::vector<uint8_t> rv((size_t)nM * D2);
+  std::vector<int> tie(nM);
+  CKM(cudaMemcpyAsync(rv.data(), d_rv, rv.size(), cudaMemcpyDeviceToHost, st));
+  CKM(cudaMemcpyAsync(tie.data(), d_tie, sizeof(int) * nM, cudaMemcpyDeviceToHost, st));
+  CKM(cudaStreamSynchronize(st));
+  for (int m = 0; m < nM; ++m) {
+    int cnt = 0;
+    for (int j = 0; j < D2; ++j) cnt += rv[(size_t)m * D2 + j];
+    if (nvalid_rays) nvalid_rays[m] = cnt;
+    if (tie_samples) tie_samples[m] = tie[m];
+  }
+  if (!build_tables) { tmp.free_all(); return HB2_OK; }
+  b->h_bil_rv = rv;
+  // transposed maps (voxel-driven): count pass, then fill
+  const int apitch = P->ntile * HB2_BLOCK;
+  // (everything the batch keeps is allocated before the big sort temporaries, so that those nest like a stack in the arena)
+  int *d_kmax, *d_fcount, *d_fptr, *d_cursor;
+  CKM(b->pool.alloc(&d_kmax, 1, true, st));
+  CKM(b->pool.alloc(&d_fcount, (size_t)nM * D2 + 1, true, st));
+  const long long nmp = (long long)nM * P->ndisk;
+  k_bil_T<0><<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, B.L3, P->ndisk, apitch, 0, d_maps, d_x, d_z, P->d_rank_data, P->d_yx_data,
+                                             P->d_aslot, nullptr, nullptr, d_kmax, d_fcount);
+  CKM(cudaGetLastError());
+  int KB = 0;
+  CKM(cudaMemcpyAsync(&KB, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CKM(cudaStreamSynchronize(st));
+  KB = std::max(KB, 1);
+  if (KB > 8) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "more than 8 rays of one view touch one voxel (internal error)"); }
+  CKM(b->pool.alloc(&d_fptr, (size_t)nM * D2 + 1, false, st));
+  uint16_t* d_Tj; float* d_Tw;
+  CKM(b->pool.alloc(&d_Tj, (size_t)nM * KB * apitch, false, st));
+  CKM(b->pool.alloc(&d_Tw, (size_t)nM * KB * apitch, true, st));
+  CKM(cudaMemsetAsync(d_Tj, 0xFF, sizeof(uint16_t) * (size_t)nM * KB * apitch, st));
+  size_t sb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, sb, d_fcount, d_fptr, nM * D2 + 1, st);
+  void* d_scan; { uint8_t* p; CKM(b->pool.alloc(&p, sb, false, st)); d_scan = p; }
+  CKM(cub::DeviceScan::ExclusiveSum(d_scan, sb, d_fcount, d_fptr, nM * D2 + 1, st));
+  int nent = 0;
+  CKM(cudaMemcpyAsync(&nent, d_fptr + (size_t)nM * D2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  k_bil_T<1><<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, B.L3, P->ndisk, apitch, KB, d_maps, d_x, d_z, P->d_rank_data, P->d_yx_data,
+                                             P->d_aslot, d_Tj, d_Tw, d_kmax, nullptr);
+  CKM(cudaGetLastError());
+  CKM(cudaStreamSynchronize(st));
+  if (nent < 0) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "bilinear maps exceed 2^31 entries"); }
+  // forward lists = the transpose, every ray sorted by voxel rank (deterministic summation order)
+  float* d_Fw; void* d_Fp;
+  CKM(b->pool.alloc(&d_Fw, (size_t)std::max(nent, 1), false, st));
+  { uint8_t* p; CKM(b->pool.alloc(&p, (size_t)std::max(nent, 1) * (b->idx16 ? 2 : 4), false, st)); d_Fp = p; }
+  if (nent > 0) {
+    unsigned *d_key, *d_key2; float* d_val;
+    CKM(tmp.alloc(&d_cursor, (size_t)nM * D2, true, st));
+    CKM(tmp.alloc(&d_key, (size_t)nent, false, st));
+    CKM(tmp.alloc(&d_key2, (size_t)nent, false, st));
+    CKM(tmp.alloc(&d_val, (size_t)nent, false, st));
+    k_bil_F_fill<<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, P->ndisk, apitch, KB, P->d_aslot, d_Tj, d_Tw, d_fptr, d_cursor, d_key, d_val);
+    CKM(cudaGetLastError());
+    size_t sb2 = 0;
+    cub::DeviceSegmentedSort::SortPairs(nullptr, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * D2, d_fptr, d_fptr + 1, st);
+    void* d_s2; { uint8_t* p; CKM(tmp.alloc(&p, sb2, false, st)); d_s2 = p; }
+    CKM(cub::DeviceSegmentedSort::SortPairs(d_s2, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * D2, d_fptr, d_fptr + 1, st));
+    if (b->idx16) k_bil_pack<uint16_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint16_t*)d_Fp);
+    else k_bil_pack<uint32_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint32_t*)d_Fp);
+    CKM(cudaGetLastError());
+  }
+  CKM(cudaStreamSynchronize(st));
+  tmp.free_all();
+#undef CKM
+  b->bilinear = true;
+  b->bil_nM = nM;
+  B.bil = 1; B.bil_KB = KB;
+  B.bilF_p = d_Fp; B.bilF_w = d_Fw; B.bilF_ptr = d_fptr;
+  B.bilT_j = d_Tj; B.bilT_w = d_Tw; B.bil_rayvalid = d_rv;
+  return HB2_OK;
+}
+
+/* ray validity of every bilinear map, out[n_maps*D2] */
+extern "C" int hb2_batch_bilinear_ray_valid(hb2_batch* b, uint8_t* out) {
+  if (!b || !out || !b->bilinear) return fail(HB2_ERR_ARG, "bad argument or no bilinear maps");
+  memcpy(out, b->h_bil_rv.data(), b->h_bil_rv.size());
+  return HB2_OK;
+}
+
+// Views of a matrix-free trilinear batch, indexed like the views of hb2_batch_create: view_map[v] >= 0 (bilinear view
+// of that map) or -1 (pseudo view of the candidate's trilinear symmetry rows); colk[v*ZMP + t], ab[(v*ZMP + t)*2 ..].
+extern "C" int hb2_batch_bilinear_views(hb2_batch* b, int32_t nviews, const int32_t* view_map, const int32_t* colk,
+                                        const double* ab, int32_t nc, const int32_t* cand_nview) {
+  if (!b || nviews <= 0 || !view_map || !colk || !ab || nc <= 0 || !cand_nview) return fail(HB2_ERR_ARG, "bad argument");
+  if (!b->bilinear || b->created) return fail(HB2_ERR_STATE, "hb2_batch_bilinear_views: after hb2_batch_bilinear_maps, before hb2_batch_create");
+  const int ZMP = b->B.ZMP;
+  for (int v = 0; v < nviews; ++v) {
+    if (view_map[v] >= b->bil_nM) return fail(HB2_ERR_ARG, "bad map index");
+    for (int t = 0; t < ZMP; ++t)
+      if (colk[(size_t)v * ZMP + t] >= b->B.L2 || (t >= b->B.L3 && colk[(size_t)v * ZMP + t] >= 0)) return fail(HB2_ERR_ARG, "bad column slot");
+  }
+  b->h_bil_view_map.assign(view_map, view_map + nviews);
+  b->h_bil_colk.assign(colk, colk + (size_t)nviews * ZMP);
+  b->h_bil_ab.assign(ab, ab + (size_t)nviews * ZMP * 2);
+  b->h_bil_cand_nview.assign(cand_nview, cand_nview + nc);
+  return HB2_OK;
+}
+
+// Trilinear symmetry rows of candidate c of a matrix-free trilinear batch (same rows as hb2_batch_explicit_sym_rows; call
+// for c = 0, 1, ... in order, before hb2_batch_create).  Two passes over the pair rounds: count (insert / check / scan),
+// then emit into an exactly sized array; the scratch is shared by the candidates of the batch.
+extern "C" int hb2_batch_bilinear_sym_rows(hb2_batch* b, int32_t c, int32_t npairs, const double* pair_mats,
+                                           int64_t min_sym_pairs, int64_t* n_rows) {
+  if (!b || c < 0 || npairs < 0 || (npairs > 0 && !pair_mats)) return fail(HB2_ERR_ARG, "bad argument");
+  if (!b->bilinear || b->created) return fail(HB2_ERR_STATE, "hb2_batch_bilinear_sym_rows: after hb2_batch_bilinear_maps, before hb2_batch_create");
+  if (c != (int)b->ls_ent_c.size()) return fail(HB2_ERR_ARG, "candidates must be given in order");
+  hb2_problem* P = b->P;
+  CK(cudaSetDevice(P->device));
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  NvtxRange nvtx_("build_A_helical_sym_matrix - linear");
+  if (n_rows) *n_rows = 0;
+  b->ls_ent_c.push_back(nullptr);
+  b->ls_m_c.push_back(0);
+  if (npairs == 0 || min_sym_pairs < 0) return HB2_OK;
+  const long long cap_rows = std::min<long long>(min_sym_pairs + B.n, (long long)npairs * B.n);
+  if (cap_rows * 16 >= (1ll << 31)) return fail(HB2_ERR_CAPACITY, "too many trilinear symmetry rows");
+  hb2_batch::LsScratch& S = b->ls_scr;
+  if (cap_rows > S.cap_rows) {  // grow the scratch (the old one stays in the batch's arena until it is destroyed)
+    const unsigned long long tc = (unsigned long long)(2 * cap_rows + 17);
+    CK(b->pool.alloc(&S.tab_key, (size_t)tc, false, st));
+    CK(b->pool.alloc(&S.tab_seq, (size_t)tc, false, st));
+    CK(b->pool.alloc(&S.col, (size_t)cap_rows * 16, false, st));
+    CK(b->pool.alloc(&S.w, (size_t)cap_rows * 16, false, st));
+    S.cap_rows = cap_rows;
+    if (!S.tmp_a) {
+      CK(b->pool.alloc(&S.tmp_a, (size_t)B.n + 1, false, st));
+      CK(b->pool.alloc(&S.tmp_b, (size_t)B.n + 1, false, st));
+      CK(b->pool.alloc(&S.flag, (size_t)B.n + 1, true, st));
+      CK(b->pool.alloc(&S.pos, (size_t)B.n + 1, true, st));
+      CK(b->pool.alloc(&S.ov, 1, true, st));
+      cub::DeviceScan::ExclusiveSum(nullptr, S.scan_bytes, S.flag, S.pos, B.n + 1, st);
+      { uint8_t* p; CK(b->pool.alloc(&p, S.scan_bytes, false, st)); S.scan_tmp = p; }
+      CK(b->pool.alloc(&S.cc, (size_t)B.npad + 2, false, st));
+    }
+  }
+  if (npairs > S.pairs_cap) { CK(b->pool.alloc(&S.pairs, (size_t)npairs, false, st)); S.pairs_cap = npairs; }
+  CK(cudaMemcpyAsync(S.pairs, pair_mats, sizeof(LsymPair) * npairs, cudaMemcpyHostToDevice, st));
+  LsymSetup Q{};
+  Q.n = B.n; Q.ndisk = B.ndisk; Q.D3 = B.D3; Q.L3 = B.L3; Q.L3P = B.L3P;
+  Q.rank_sym = P->d_rank_sym; Q.disk_yx_sym = P->d_yx_sym;
+  Q.tab_cap = (unsigned long long)(2 * cap_rows + 17);
+  Q.tab_key = S.tab_key; Q.tab_seq = S.tab_seq; Q.tmp_a = S.tmp_a; Q.tmp_b = S.tmp_b; Q.flag = S.flag; Q.pos = S.pos;
+  Q.overflow = S.ov;
+  CK(cudaMemsetAsync(Q.tab_key, 0xFF, sizeof(unsigned long long) * Q.tab_cap, st));
+  CK(cudaMemsetAsync(Q.tab_seq, 0xFF, sizeof(unsigned long long) * Q.tab_cap, st));
+  CK(cudaMemsetAsync(S.ov, 0, sizeof(int), st));
+  long long rows = 0;
+  const unsigned gn = cdiv((long long)B.n + 1, 256);
+  for (int rnd = 0; rnd < npairs; ++rnd) {
+    k_lsym_insert<<<gn, 256, 0, st>>>(Q, S.pairs, rnd);
+    k_lsym_check<<<gn, 256, 0, st>>>(Q, rnd);
+    CK(cub::DeviceScan::ExclusiveSum(S.scan_tmp, S.scan_bytes, Q.flag, Q.pos, B.n + 1, st));
+    k_lsym_emit<<<gn, 256, 0, st>>>(Q, S.pairs, rnd, (int)rows, (int)cap_rows, S.col, S.w);
+    CKL();
+    int h[2] = {0, 0};
+    CK(cudaMemcpyAsync(&h[0], Q.pos + B.n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h[1], S.ov, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[1]) return fail(HB2_ERR_CAPACITY, "trilinear symmetry rows: table overflow");
+    rows += h[0];
+    if (rows >= min_sym_pairs) break;  // SLR:1286
+  }
+  if (rows > 0) {
+    int2* ent;
+    CK(b->pool.alloc(&ent, (size_t)rows * 16, false, st));
+    k_ls_pack<<<cdiv(rows * 16, 256), 256, 0, st>>>(rows * 16, S.col, S.w, ent);
+    CKL();
+    b->ls_ent_c.back() = ent;
+  }
+  b->ls_m_c.back() = (int)rows;
+  if (n_rows) *n_rows = rows;
+  return HB2_OK;
+}
+
+/* the trilinear symmetry rows of candidate c as 16 (column, weight) entries each, columns in the reference's voxel order */
+extern "C" int hb2_batch_bilinear_sym_export(hb2_batch* b, int32_t c, int32_t* cols, float* w) {
+  if (!b || !b->bilinear || c < 0 || c >= (int)b->ls_ent_c.size()) return fail(HB2_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(b->P->device));
+  const size_t ne = (size_t)b->ls_m_c[c] * 16;
+  if (ne == 0) return HB2_OK;
+  std::vector<int2> ent(ne);
+  CK(cudaMemcpyAsync(ent.data(), b->ls_ent_c[c], sizeof(int2) * ne, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  const int L3P = b->B.L3P, nd = b->B.ndisk;
+  const std::vector<int>& i2r = b->P->int2ref;
+  for (size_t e = 0; e < ne; ++e) {
+    if (cols) cols[e] = (ent[e].x % L3P) * nd + i2r[ent[e].x / L3P];
+    if (w) memcpy(&w[e], &ent[e].y, 4);
+  }
+  return HB2_OK;
+}
+
+// Called by hb2_batch_create for a matrix-free trilinear batch: uploads the view tables, right-hand side, transpose
+// lists of the trilinear symmetry rows.
+static int bil_finish(hb2_batch* b, int nviews) {
+  hb2_problem* P = b->P;
+  cudaStream_t st = b->stream;
+  BD& B = b->B;
+  const int nc = B.nc;
+  if ((int)b->h_bil_view_map.size() != nviews || (int)b->h_bil_cand_nview.size() != nc)
+    return fail(HB2_ERR_ARG, "hb2_batch_bilinear_views does not match the views of hb2_batch_create");
+  while ((int)b->ls_ent_c.size() < nc) { b->ls_ent_c.push_back(nullptr); b->ls_m_c.push_back(0); }
+  for (int c = 0; c < nc; ++c) {
+    const int nvw = b->h_bil_cand_nview[c], vc = b->h_view_count[c];
+    const long long need = ((long long)b->ls_m_c[c] + B.rows_per_view - 1) / B.rows_per_view;
+    if (nvw < 0 || nvw > vc || vc - nvw < need) return fail(HB2_ERR_ARG, "not enough pseudo views for the trilinear symmetry rows");
+    for (int v = 0; v < vc; ++v)
+      if ((b->h_bil_view_map[b->h_view_begin[c] + v] >= 0) != (v < nvw)) return fail(HB2_ERR_ARG, "bilinear views must come first");
+  }
+  CK(upload(b->pool, &B.bil_view_map, b->h_bil_view_map, st));
+  CK(upload(b->pool, &B.bil_colk, b->h_bil_colk, st));
+  CK(upload(b->pool, &B.bil_ab, b->h_bil_ab, st));
+  CK(upload(b->pool, &B.bil_cand_nview, b->h_bil_cand_nview, st));
+  k_bil_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
+  CKL();
+  // transpose lists of the trilinear symmetry rows, candidate by candidate (stable radix sort of the entries by voxel)
+  std::vector<long long> eoff(nc, 0), ceoff(nc, 0);
+  std::vector<int2*> cent(nc, nullptr);
+  int* d_cptr;
+  CK(b->pool.alloc(&d_cptr, (size_t)nc * (B.npad + 1), true, st));
+  hb2_batch::LsScratch& S = b->ls_scr;
+  long long max_ne = 0;
+  for (int c = 0; c < nc; ++c) max_ne = std::max<long long>(max_ne, 16ll * b->ls_m_c[c]);
+  if (max_ne > 0) {
+    int bits = 1;
+    while ((1ll << bits) < (long long)B.npad) ++bits;
+    for (int c = 0; c < nc; ++c) CK(b->pool.alloc(&cent[c], (size_t)std::max(16ll * b->ls_m_c[c], 1ll), false, st));
+    CK(b->pool.alloc(&S.key, (size_t)max_ne, false, st));
+    CK(b->pool.alloc(&S.key2, (size_t)max_ne, false, st));
+    CK(b->pool.alloc(&S.id, (size_t)max_ne, false, st));
+    CK(b->pool.alloc(&S.id2, (size_t)max_ne, false, st));
+    cub::DeviceRadixSort::SortPairs(nullptr, S.sort_bytes, S.key, S.key2, S.id, S.id2, (int)max_ne, 0, bits, st);
+    { uint8_t* p; CK(b->pool.alloc(&p, S.sort_bytes, false, st)); S.sort_tmp = p; }
+    size_t sbc = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, sbc, S.cc, d_cptr, B.npad + 1, st);
+    void* d_sc; { uint8_t* p; CK(b->pool.alloc(&p, sbc, false, st)); d_sc = p; }
+    for (int c = 0; c < nc; ++c) {
+      const long long ne = 16ll * b->ls_m_c[c];
+      if (ne == 0) continue;
+      CK(cudaMemsetAsync(S.cc, 0, sizeof(int) * ((size_t)B.npad + 2), st));
+      k_ls_keys<<<cdiv(ne, 256), 256, 0, st>>>(ne, b->ls_ent_c[c], S.key, S.id, S.cc);
+      size_t sbytes = S.sort_bytes;
+      CK(cub::DeviceRadixSort::SortPairs(S.sort_tmp, sbytes, S.key, S.key2, S.id, S.id2, (int)ne, 0, bits, st));
+      k_ls_gather<<<cdiv(ne, 256), 256, 0, st>>>(ne, S.id2, b->ls_ent_c[c], cent[c]);
+      CK(cub::DeviceScan::ExclusiveSum(d_sc, sbc, S.cc, d_cptr + (size_t)c * (B.npad + 1), B.npad + 1, st));
+      CKL();
+    }
+  }
+  const int2* base_e = nullptr; const int2* base_c = nullptr;
+  for (int c = 0; c < nc; ++c) {
+    if (b->ls_m_c[c] == 0) continue;
+    if (!base_e) { base_e = b->ls_ent_c[c]; base_c = cent[c]; }
+    eoff[c] = ((intptr_t)b->ls_ent_c[c] - (intptr_t)base_e) / (intptr_t)sizeof(int2);
+    ceoff[c] = ((intptr_t)cent[c] - (intptr_t)base_c) / (intptr_t)sizeof(int2);
+  }
+  B.ls_ent = base_e; B.ls_cent = base_c; B.ls_cptr = d_cptr;
+  CK(upload(b->pool, &B.ls_eoff, eoff, st));
+  CK(upload(b->pool, &B.ls_ceoff, ceoff, st));
+  CK(upload(b->pool, &B.ls_m, b->ls_m_c, st));
+  CK(cudaStreamSynchronize(st));
+  return HB2_OK;
+}
+
 extern "C" int hb2_batch_set_ties(hb2_batch* b, int32_t n_tie, int32_t TS, const int8_t* zlo, const uint8_t* up,
                                   const uint8_t* rowvalid) {
   if (!b || n_tie < 0 || (n_tie > 0 && (!zlo || !up || !rowvalid || TS <= 0))) return fail(HB2_ERR_ARG, "bad argument");
@@ -1058,9 +1386,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
           view_dupof[vi] = prim; view_mult[vi] = 0; view_mult[prim] += 1;
         }
       }
-      if (b->explicit_rows && w.tie < 0) return fail(HB2_ERR_ARG, "a batch with explicit rows takes pseudo views only");
+      if ((b->explicit_rows || b->bilinear) && w.tie < 0) return fail(HB2_ERR_ARG, "a batch with explicit / trilinear rows takes pseudo views only");
       if (w.tie >= 0) {
-        if (!b->explicit_rows) {
+        if (!b->explicit_rows && !b->bilinear) {
           if (w.tie >= b->n_tie || w.tie_slot0 < 0 || w.tie_slot0 + B.ZMC > b->tie_TS) return fail(HB2_ERR_ARG, "bad tie view");
           if (B.ZMC > HB2_TIE_MAXZMC) return fail(HB2_ERR_GEOMETRY, "tie views need L3*MC <= 16");
         }
@@ -1070,7 +1398,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
         cand_tie_count[c] += 1;
       }
       view_uoff[vi] = uo + (long long)v * B.rows_per_view;
-      if (b->tie_per_angle[w.angle] > 0 && !b->explicit_rows) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
+      if (b->tie_per_angle[w.angle] > 0 && !b->explicit_rows && !b->bilinear) b->cand_flags[c] |= HB2_FLAG_TIE_XY;
     }
     b->cand_flags[c] |= q.flags_in;
     if (q.view_count == 0) b->cand_flags[c] |= HB2_FLAG_NO_ROWS;
@@ -1258,7 +1586,7 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     const char* use_band = getenv("HB2_FWD_BAND");
     const int band_mode = use_band ? atoi(use_band) : 2;
     const bool ok = B.MC == 1 && B.L3P <= 16 && max_views <= HB2_FWDB_MAXV && band_mode > 0 && b->idx16 && D2 % 8 == 0 &&
-                    !b->explicit_rows;
+                    !b->explicit_rows && !b->bilinear;
     bool any_positive = false;
     for (int c = 0; c < nc; ++c) any_positive = any_positive || cands[c].positive != 0;
     if (ok) {
@@ -1289,6 +1617,10 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
     iv = iv >= 0 ? iv : iv ^ 0x7fffffff;
     CKC(cudaMemcpyAsync(b->d_bmax, &iv, sizeof(int), cudaMemcpyHostToDevice, st));
     CKC(cudaStreamSynchronize(st));
+  }
+  if (b->bilinear) {  // matrix-free trilinear rows: view tables, right-hand side, symmetry-row transposes
+    int rc_ = bil_finish(b, nviews);
+    if (rc_ != HB2_OK) return rc_;
   }
   // ---- symmetry rows -----------------------------------------------------------
   NvtxRange nvtx_sym_("build_A_helical_sym_matrix - nn");
@@ -1415,6 +1747,7 @@ extern "C" int hb2_batch_set_pixel_masks(hb2_batch* b, int32_t n_masks, const ui
   std::vector<int> neg(nc, (int)0x80000000);
   CK(cudaMemcpyAsync(b->d_bmax, neg.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
   k_build_rhs<<<cdiv((long long)b->nviews * B.rows_per_view, 256), 256, 0, st>>>(B, b->P->d_pix, b->nviews, b->d_bmax);
+  if (b->bilinear) k_bil_rhs<<<cdiv((long long)b->nviews * B.rows_per_view, 256), 256, 0, st>>>(B, b->P->d_pix, b->nviews, b->d_bmax);
   CKL();
   CK(cudaStreamSynchronize(st));
   return HB2_OK;
@@ -1525,7 +1858,16 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (b->nviews == 0) return;
   if (b->n_tie_views > 0) {  // exact rows of the tie views (the projector kernels below skip them)
     const float* src = mode == MODE_LSMR ? B.v : B.xs;
-    if (b->explicit_rows) k_fwd_csr<float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+    if (b->bilinear) {
+      const dim3 gv(b->n_tie_views, B.fwd_ppv);
+#define FBIL(I, Q) k_fwd_bil<I, Q, float, false><<<gv, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode)
+#define FBILQ(I) do { if (B.L3P == 4) FBIL(I, 1); else if (B.L3P == 8) FBIL(I, 2); else if (B.L3P == 12) FBIL(I, 3); else FBIL(I, 4); } while (0)
+      if (b->idx16) FBILQ(uint16_t); else FBILQ(uint32_t);
+#undef FBILQ
+#undef FBIL
+      k_fwd_lsym<float, false><<<gv, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
+      b->extra_launches += 1;
+    } else if (b->explicit_rows) k_fwd_csr<float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     else if (b->idx16) k_fwd_tie<uint16_t, float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     else k_fwd_tie<uint32_t, float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
     b->extra_launches += 1;
@@ -1568,7 +1910,15 @@ static void launch_adj(hb2_batch* b, int mode) {
   dim3 g(B.part_v_per_cand, B.nc);
   cudaStream_t st = b->stream;
   if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
-    if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+    if (b->bilinear) {
+      const dim3 ga(cdiv(B.ndisk, HB2_BLOCK), B.nc);
+      if (B.L3P == 4) k_adj_bil<1, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      else if (B.L3P == 8) k_adj_bil<2, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      else if (B.L3P == 12) k_adj_bil<3, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      else k_adj_bil<4, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      k_adj_lsym<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      b->extra_launches += 1;
+    } else if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     else k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     b->extra_launches += 1;
   }
@@ -1736,7 +2086,16 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     k_fwd64_sym<<<g_sym, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
     launches += 2;
     if (b->n_tie_views > 0) {
-      if (b->explicit_rows) k_fwd_csr<double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+      if (b->bilinear) {
+        const dim3 gv(b->n_tie_views, B.fwd_ppv);
+#define FBIL(I, Q) k_fwd_bil<I, Q, double, true><<<gv, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate)
+#define FBILQ(I) do { if (B.L3P == 4) FBIL(I, 1); else if (B.L3P == 8) FBIL(I, 2); else if (B.L3P == 12) FBIL(I, 3); else FBIL(I, 4); } while (0)
+        if (b->idx16) FBILQ(uint16_t); else FBILQ(uint32_t);
+#undef FBILQ
+#undef FBIL
+        k_fwd_lsym<double, true><<<gv, HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
+        ++launches;
+      } else if (b->explicit_rows) k_fwd_csr<double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       else if (b->idx16) k_fwd_tie<uint16_t, double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       else k_fwd_tie<uint32_t, double, true><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, T, src, dst, gate);
       ++launches;
@@ -1744,7 +2103,15 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   };
   auto adj = [&](const double* rows, double* dst, int gate) {
     if (b->n_tie_views > 0) {
-      if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+      if (b->bilinear) {
+        const dim3 ga(cdiv(B.ndisk, HB2_BLOCK), nc);
+        if (B.L3P == 4) k_adj_bil<1, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        else if (B.L3P == 8) k_adj_bil<2, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        else if (B.L3P == 12) k_adj_bil<3, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        else k_adj_bil<4, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        k_adj_lsym<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        ++launches;
+      } else if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       else k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;
     }

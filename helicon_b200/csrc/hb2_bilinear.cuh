@@ -1,0 +1,464 @@
+// Matrix-free trilinear data rows (build_A_data_matrix with interpolation "linear", SLR:1403-1510, in the grid-search
+// case tilt = psi = dy = 0, scale2d_to_3d = 1).  The reference's row of (symmetry copy, image column k, ray j) is
+//     sum_i  [(1 - zf) x[zi] + zf x[zi + 1]]  (x)  [(1 - yf)(1 - xf), (1 - yf) xf, yf (1 - xf), yf xf] at (yi, xi)
+// over the depth samples i whose 8 corners lie inside the mask.  With tilt = psi = dy = 0 the slice pair (zi, zf)
+// depends on the column k only and the in-plane footprint on (view angle, j, i) only, so the row factors into
+//     row(k, j) = a_k P[zi_k][j] + b_k P[zi_k + 1][j],     P[z][j] = sum_e w_e x[z][p_e]
+// with the MERGED in-plane footprint of the ray (p_e, w_e): a voxel met by several consecutive samples carries the
+// float64 sum of their (1 - yf)(1 - xf)-type products, accumulated in sample order like the reference's row dict
+// (SLR:1478-1496).  The footprints depend on the view angle only and are shared by all candidates of a batch, like the
+// nearest-neighbour maps: the explicit matrix (192 M entries per candidate at 256 x 256) never exists.
+//
+//   * maps: k_bil_T builds, per (map, voxel), the <= KB rays that touch the voxel and their weights (voxel-driven, the
+//     reference's float64 coordinate arithmetic: bil_sample == k_exp_rows); the forward lists are their transpose,
+//     sorted by voxel rank per ray (deterministic).
+//   * EXACT maps: where a sample coordinate is integer-valued (angle 0 / 90 / 180 / 270; integer h * rise) the int()
+//     truncation follows the last-bit noise of the reference's coordinate tables (SLR:1712-1719), which depends on
+//     (image column k, sample i).  Bilinear weights are continuous across that flip, but the 8-corner validity test is
+//     not, so such columns get their own map built from the table rows of THAT column (hb2_bilinear_map.xrow / zrow);
+//     the host turns them into single-column views.
+//   * views: slot t of a view holds the rows of one image column; canonical form
+//         t = 0 : row = a_0 P[0] + b_0 P[1]          (columns with Z in (-1, 0): int() truncates toward zero, zf < 0)
+//         t >= 1: row = a_t P[t - 1] + b_t P[t]
+//     so every slice index is static in the kernels.
+//   * trilinear symmetry rows (k_lsym_*, hb2_explicit.cuh) stay explicit: 16 (column, weight) entries per row, per
+//     candidate, plus their transpose lists.
+// Inside the batch all of these are "pseudo views" (BD::view_tie >= 0): the nearest-neighbour projector kernels skip
+// them, k_fwd_bil / k_fwd_lsym produce their rows and partial sums, k_adj_bil / k_adj_lsym their contribution to
+// A^T u (BD::vtie / vtie64), which the adjoint kernels add -- LSMR / TRF state machines, norms and score are unchanged.
+#pragma once
+#include "hb2_explicit.cuh"
+
+struct BilMap {  // == hb2_bilinear_map (include/helicon_b200.h)
+  double m00, m01, m10, m11, m22, zshift;
+  int32_t xrow, zrow;
+};
+
+struct BilS { int xi, yi; double xf, yf; bool ok, near; };
+
+// One depth sample of ray j exactly as k_exp_rows computes it (rot_yx = identity, dy = 0, s = 1).
+__device__ __forceinline__ BilS bil_sample(const BilMap& M, const double* __restrict__ xrows, const double* __restrict__ zrows,
+                                           int D2, int L3, const int* __restrict__ rank, int j, int i) {
+  BilS r;
+  r.ok = false; r.near = false; r.xi = r.yi = 0; r.xf = r.yf = 0.0;
+  const int c0 = D2 / 2;
+  const double x0 = M.xrow >= 0 ? xrows[(size_t)M.xrow * D2 + i] : -(double)(i - c0);
+  const double y0 = (double)(j - c0);
+  const double X = __dadd_rn(__fma_rn(M.m10, y0, __dmul_rn(M.m00, x0)), (double)c0);
+  const double Y = __dadd_rn(__fma_rn(M.m11, y0, __dmul_rn(M.m01, x0)), (double)c0);
+  if (!(Y > -1.0 && Y < (double)D2 && X > -1.0 && X < (double)D2)) return r;
+  r.near = fabs(X - rint(X)) < 1e-9 || fabs(Y - rint(Y)) < 1e-9;
+  if (M.zrow >= 0) {  // per-sample slice validity from the reference's z table (integer h * rise)
+    const double z2 = __dmul_rn(M.m22, zrows[(size_t)M.zrow * D2 + i]);
+    const double Z = __dadd_rn(__dsub_rn(z2, M.zshift), (double)(L3 / 2));
+    if (!(Z > -1.0 && Z < (double)L3)) return r;
+    if ((int)Z + 1 > L3 - 1) return r;
+  }
+  const int xi = (int)X, yi = (int)Y;
+  if (yi + 1 > D2 - 1 || xi + 1 > D2 - 1) return r;
+  if (rank[yi * D2 + xi] < 0 || rank[yi * D2 + xi + 1] < 0 || rank[(yi + 1) * D2 + xi] < 0 || rank[(yi + 1) * D2 + xi + 1] < 0)
+    return r;
+  r.xi = xi; r.yi = yi;
+  r.xf = __dsub_rn(X, (double)xi); r.yf = __dsub_rn(Y, (double)yi);
+  r.ok = true;
+  return r;
+}
+
+// rayvalid[m][j] = the ray has a valid sample (SLR:1496 has_projection_data); tie[m] = samples within 1e-9 of an integer
+// coordinate (the host replaces such views by exact per-column maps).
+__global__ void k_bil_rayvalid(int nM, int D2, int L3, const BilMap* __restrict__ maps, const double* __restrict__ xrows,
+                               const double* __restrict__ zrows, const int* __restrict__ rank, uint8_t* __restrict__ rayvalid,
+                               int* __restrict__ tie) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nM * D2 * D2) return;
+  const int i = (int)(t % D2), j = (int)((t / D2) % D2), m = (int)(t / ((long long)D2 * D2));
+  const BilS s = bil_sample(maps[m], xrows, zrows, D2, L3, rank, j, i);
+  if (s.ok) rayvalid[(size_t)m * D2 + j] = 1;  // benign race: all writers store 1
+  if (s.near) atomicAdd(&tie[m], 1);
+}
+
+// Transposed maps, voxel-driven.  PASS 0: kmax = max rays per (map, voxel), fcount[m][j] += 1 per entry;
+// PASS 1: Tj / Tw[(m*KB + k)*apitch + aslot[p]] (0xFFFF = empty).  Rays ascending, samples ascending inside a ray.
+template <int PASS>
+__global__ void k_bil_T(int nM, int D2, int L3, int ndisk, int apitch, int KB, const BilMap* __restrict__ maps,
+                        const double* __restrict__ xrows, const double* __restrict__ zrows, const int* __restrict__ rank,
+                        const short2* __restrict__ disk_yx, const int* __restrict__ aslot, uint16_t* __restrict__ Tj,
+                        float* __restrict__ Tw, int* __restrict__ kmax, int* __restrict__ fcount) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nM * ndisk) return;
+  const int p = (int)(t % ndisk), m = (int)(t / ndisk);
+  const BilMap M = maps[m];
+  const int c0 = D2 / 2;
+  const short2 yx = disk_yx[p];
+  const int vx = yx.y, vy = yx.x;
+  const double dx = (double)(vx - c0), dy = (double)(vy - c0);
+  // inverse of (X - c0, Y - c0) = (m00 x0 + m10 y0, m01 x0 + m11 y0): the transpose (a rotation)
+  const double x0 = M.m00 * dx + M.m01 * dy, y0 = M.m10 * dx + M.m11 * dy;
+  const double is = c0 - x0, js = c0 + y0, rad = 1.4143 + 0.02;
+  const int i0 = max(0, (int)ceil(is - rad)), i1 = min(D2 - 1, (int)floor(is + rad));
+  const int j0 = max(0, (int)ceil(js - rad)), j1 = min(D2 - 1, (int)floor(js + rad));
+  int cnt = 0;
+  for (int j = j0; j <= j1; ++j) {
+    double w = 0.0;
+    bool hit = false;
+    for (int i = i0; i <= i1; ++i) {
+      const BilS s = bil_sample(M, xrows, zrows, D2, L3, rank, j, i);
+      if (!s.ok) continue;
+      const int cx = vx - s.xi, cy = vy - s.yi;
+      if (cx < 0 || cx > 1 || cy < 0 || cy > 1) continue;
+      const double wy = cy ? s.yf : __dsub_rn(1.0, s.yf), wx = cx ? s.xf : __dsub_rn(1.0, s.xf);
+      w = __dadd_rn(w, __dmul_rn(wy, wx));
+      hit = true;
+    }
+    if (hit && w != 0.0) {
+      if (PASS == 0) atomicAdd(&fcount[(size_t)m * D2 + j], 1);
+      else if (cnt < KB) {
+        Tj[((size_t)m * KB + cnt) * apitch + aslot[p]] = (uint16_t)j;
+        Tw[((size_t)m * KB + cnt) * apitch + aslot[p]] = (float)w;
+      }
+      ++cnt;
+    }
+  }
+  if (PASS == 0) {
+    if (cnt > 0) atomicMax(kmax, cnt);
+  } else {
+    for (int k = cnt; k < KB; ++k) Tj[((size_t)m * KB + k) * apitch + aslot[p]] = 0xFFFFu;
+  }
+}
+
+// forward lists: entry (voxel p, weight) of ray (m, j) at fptr[m*D2 + j] + cursor; sorted by p afterwards
+__global__ void k_bil_F_fill(int nM, int D2, int ndisk, int apitch, int KB, const int* __restrict__ aslot,
+                             const uint16_t* __restrict__ Tj, const float* __restrict__ Tw, const int* __restrict__ fptr,
+                             int* __restrict__ cursor, unsigned* __restrict__ key, float* __restrict__ val) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nM * ndisk) return;
+  const int p = (int)(t % ndisk), m = (int)(t / ndisk);
+  for (int k = 0; k < KB; ++k) {
+    const size_t mi = ((size_t)m * KB + k) * apitch + aslot[p];
+    const unsigned j = Tj[mi];
+    if (j == 0xFFFFu) continue;
+    const int e = fptr[(size_t)m * D2 + j] + atomicAdd(&cursor[(size_t)m * D2 + j], 1);
+    key[e] = (unsigned)p; val[e] = Tw[mi];
+  }
+}
+template <typename IdxT>
+__global__ void k_bil_pack(long long n, const unsigned* __restrict__ key, IdxT* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[e] = (IdxT)key[e];
+}
+
+// right-hand side of the bilinear views (the pseudo views were zeroed by k_build_rhs) + max(b) per candidate
+__global__ void k_bil_rhs(BD B, const float* __restrict__ pix, int nviews, float* __restrict__ bmax_bits) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)nviews * B.rows_per_view) return;
+  const int view = (int)(t / B.rows_per_view), r = (int)(t % B.rows_per_view);
+  const int map = B.bil_view_map[view];
+  const int zm = r % B.ZMP, j = r / B.ZMP;
+  const int c = B.view_cand[view];
+  bool rowok = false;
+  float val = 0.f;
+  if (map >= 0) {
+    const int k = B.bil_colk[(size_t)view * B.ZMP + zm];
+    rowok = k >= 0 && B.bil_rayvalid[(size_t)map * B.D2 + j];
+    if (rowok) {
+      const uint8_t* pm = cand_mask(B, c);
+      if (pm && !pm[(size_t)k * B.D2 + j]) rowok = false;
+    }
+    if (rowok) val = pix[(size_t)j * B.L2 + k];
+    B.b[B.view_uoff[view] + r] = val;
+  }
+  int iv = (int)0x80000000;
+  if (rowok) { iv = __float_as_int(val); iv = iv >= 0 ? iv : iv ^ 0x7fffffff; }
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, c);
+  const int mx = __reduce_max_sync(peers, iv);
+  if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31) && mx != (int)0x80000000) atomicMax((int*)bmax_bits + c, mx);
+}
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* __restrict__ p, T& a, T& b, T& c, T& d);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* __restrict__ p, float& a, float& b, float& c, float& d) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  a = q.x; b = q.y; c = q.z; d = q.w;
+}
+template <>
+__device__ __forceinline__ void ld4<double>(const double* __restrict__ p, double& a, double& b, double& c, double& d) {
+  const double2 q0 = *reinterpret_cast<const double2*>(p), q1 = *reinterpret_cast<const double2*>(p + 2);
+  a = q0.x; b = q0.y; c = q1.x; d = q1.y;
+}
+
+// Forward of the bilinear views.  Grid (pseudo views, fwd_ppv); one warp per ray j; lane = (slice quad q, entry group
+// g): lanes q*G .. q*G + G - 1 walk the ray's footprint list G entries at a time, 128-bit gathers of 4 slices x weight;
+// a shuffle tree over g leaves P[4q .. 4q+3]; lane t < ZMP then blends and finishes column slot t.
+template <typename IdxT, int Q, typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
+  const int view = B.tie_views[blockIdx.x];
+  const int map = B.bil_view_map[view];
+  if (map < 0) return;  // trilinear symmetry rows: k_fwd_lsym
+  const int c = B.view_cand[view];
+  __shared__ float red[HB2_BLOCK / 32];
+  __shared__ T s_P[HB2_BLOCK / 32][16];
+  __shared__ T s_a[16], s_b[16];
+  __shared__ int s_colk[16];
+  const int ppv = B.fwd_ppv, sub = blockIdx.y;
+  if (!tie_active<TRF>(B, Tt, c, mode, false)) {
+    if (!TRF && threadIdx.x == 0) {
+      if (mode == MODE_LSMR) B.part_u[view * ppv + sub] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + sub)] = 0.f; B.part_s[3 * (view * ppv + sub) + 1] = 0.f; B.part_s[3 * (view * ppv + sub) + 2] = 0.f; }
+    }
+    return;
+  }
+  constexpr int L3P = 4 * Q, G = 32 / Q;
+  constexpr int P2 = G >= 32 ? 32 : (G >= 16 ? 16 : (G >= 8 ? 8 : 4));
+  const int D2 = B.D2, ZMP = B.ZMP;
+  if (threadIdx.x < 16) {
+    const bool in = (int)threadIdx.x < ZMP;
+    s_colk[threadIdx.x] = in ? B.bil_colk[(size_t)view * ZMP + threadIdx.x] : -1;
+    s_a[threadIdx.x] = in ? (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2] : (T)0;
+    s_b[threadIdx.x] = in ? (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2 + 1] : (T)0;
+  }
+  __syncthreads();
+  const IdxT* __restrict__ Fp = (const IdxT*)B.bilF_p;
+  const float* __restrict__ Fw = B.bilF_w;
+  const int* __restrict__ ptr = B.bilF_ptr + (size_t)map * D2;
+  const uint8_t* __restrict__ rv = B.bil_rayvalid + (size_t)map * D2;
+  const T* __restrict__ vsrc = src + (size_t)c * B.npad;
+  T* urow = rows + B.view_uoff[view];
+  const float* brow = B.b + B.view_uoff[view];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane / G, g = lane % G;
+  const bool lane_on = q < Q;
+  float alpha = 0.f, inv_beta = 0.f;
+  if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
+  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
+  const uint8_t* __restrict__ pm = cand_mask(B, c);
+  for (int j = sub * (HB2_BLOCK / 32) + warp; j < D2; j += ppv * (HB2_BLOCK / 32)) {
+    if (!rv[j]) continue;  // warp-uniform
+    const int e0 = ptr[j], e1 = ptr[j + 1];
+    T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
+    if (lane_on) {
+      int e = e0 + g;
+      for (; e + 3 * G < e1; e += 4 * G) {  // four independent (rank, weight, gather) chains in flight
+        const size_t p0 = Fp[e], p1 = Fp[e + G], p2 = Fp[e + 2 * G], p3 = Fp[e + 3 * G];
+        const T w0 = (T)Fw[e], w1 = (T)Fw[e + G], w2 = (T)Fw[e + 2 * G], w3 = (T)Fw[e + 3 * G];
+        T x0, x1, x2, x3, y0, y1, y2, y3, z0, z1, z2, z3, t0, t1, t2, t3;
+        ld4<T>(vsrc + p0 * L3P + 4 * q, x0, x1, x2, x3);
+        ld4<T>(vsrc + p1 * L3P + 4 * q, y0, y1, y2, y3);
+        ld4<T>(vsrc + p2 * L3P + 4 * q, z0, z1, z2, z3);
+        ld4<T>(vsrc + p3 * L3P + 4 * q, t0, t1, t2, t3);
+        a0 += w0 * x0; a1 += w0 * x1; a2 += w0 * x2; a3 += w0 * x3;
+        a0 += w1 * y0; a1 += w1 * y1; a2 += w1 * y2; a3 += w1 * y3;
+        a0 += w2 * z0; a1 += w2 * z1; a2 += w2 * z2; a3 += w2 * z3;
+        a0 += w3 * t0; a1 += w3 * t1; a2 += w3 * t2; a3 += w3 * t3;
+      }
+      for (; e < e1; e += G) {
+        const size_t p0 = Fp[e];
+        const T w0 = (T)Fw[e];
+        T x0, x1, x2, x3;
+        ld4<T>(vsrc + p0 * L3P + 4 * q, x0, x1, x2, x3);
+        a0 += w0 * x0; a1 += w0 * x1; a2 += w0 * x2; a3 += w0 * x3;
+      }
+    }
+    // sum over the entry groups of a quad: lanes q*G + g, g < G (G = 32, 16, 10, 8); fixed tree -> deterministic
+    if (G > P2) {
+      const T b0 = __shfl_down_sync(0xffffffffu, a0, P2), b1 = __shfl_down_sync(0xffffffffu, a1, P2);
+      const T b2 = __shfl_down_sync(0xffffffffu, a2, P2), b3 = __shfl_down_sync(0xffffffffu, a3, P2);
+      if (lane_on && g + P2 < G) { a0 += b0; a1 += b1; a2 += b2; a3 += b3; }
+    }
+#pragma unroll
+    for (int o = P2 / 2; o > 0; o >>= 1) {
+      a0 += __shfl_down_sync(0xffffffffu, a0, o); a1 += __shfl_down_sync(0xffffffffu, a1, o);
+      a2 += __shfl_down_sync(0xffffffffu, a2, o); a3 += __shfl_down_sync(0xffffffffu, a3, o);
+    }
+    if (lane_on && g == 0) { s_P[warp][4 * q] = a0; s_P[warp][4 * q + 1] = a1; s_P[warp][4 * q + 2] = a2; s_P[warp][4 * q + 3] = a3; }
+    __syncwarp();
+    if (lane < ZMP && s_colk[lane] >= 0 && !(pm && !pm[(size_t)s_colk[lane] * D2 + j])) {
+      const T lo = lane == 0 ? s_P[warp][0] : s_P[warp][lane - 1];
+      const T hi = lane == 0 ? s_P[warp][1] : s_P[warp][lane];
+      const T acc = s_a[lane] * lo + s_b[lane] * hi;
+      const size_t ri = (size_t)j * ZMP + lane;
+      if (TRF) {
+        urow[ri] = acc;
+      } else if (mode == MODE_LSMR) {
+        const float un = fadd_(fmul_(fmul_((float)urow[ri], inv_beta), -alpha), (float)acc);
+        urow[ri] = (T)un;
+        ss += un * un;
+      } else if (mode == MODE_PLAIN) {
+        urow[ri] = acc;
+      } else {
+        const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
+        const float bv = brow[ri];
+        ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+      }
+    }
+    __syncwarp();
+  }
+  if (!TRF) {
+    if (mode == MODE_LSMR) {
+      const float tot = block_sum(ss, red);
+      if (threadIdx.x == 0) B.part_u[view * ppv + sub] = tot;
+    } else if (mode == MODE_SCORE) {
+      const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
+      if (threadIdx.x == 0) {
+        B.part_s[3 * (view * ppv + sub)] = t0;
+        B.part_s[3 * (view * ppv + sub) + 1] = t1;
+        B.part_s[3 * (view * ppv + sub) + 2] = t2;
+      }
+    }
+  }
+}
+
+// Forward of the trilinear symmetry rows: one thread per row (16 entries, 128-bit loads of columns and weights).
+// The rows of candidate c occupy its pseudo views after the bilinear ones; never scored.
+template <typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_lsym(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
+  const int view = B.tie_views[blockIdx.x];
+  if (B.bil_view_map[view] >= 0) return;
+  const int c = B.view_cand[view];
+  __shared__ float red[HB2_BLOCK / 32];
+  const int ppv = B.fwd_ppv, sub = blockIdx.y;
+  const bool act = tie_active<TRF>(B, Tt, c, mode, false);
+  if (!act || (!TRF && mode == MODE_SCORE)) {
+    if (!TRF && threadIdx.x == 0) {
+      if (mode == MODE_LSMR) B.part_u[view * ppv + sub] = 0.f;
+      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + sub)] = 0.f; B.part_s[3 * (view * ppv + sub) + 1] = 0.f; B.part_s[3 * (view * ppv + sub) + 2] = 0.f; }
+    }
+    return;
+  }
+  const int first = B.cand_view_begin[c] + B.bil_cand_nview[c];  // first symmetry pseudo view of the candidate
+  const long long r_lo = (long long)(view - first) * B.rows_per_view;
+  const int nrow = (int)max(0ll, min((long long)B.rows_per_view, (long long)B.ls_m[c] - r_lo));
+  const T* __restrict__ vsrc = src + (size_t)c * B.npad;
+  T* urow = rows + B.view_uoff[view];
+  const int4* __restrict__ ent4 = reinterpret_cast<const int4*>(B.ls_ent + B.ls_eoff[c] + r_lo * 16);
+  float alpha = 0.f, inv_beta = 0.f;
+  if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
+  float ss = 0.f;
+  for (int r = sub * HB2_BLOCK + threadIdx.x; r < nrow; r += ppv * HB2_BLOCK) {
+    T acc = (T)0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int4 cc = ent4[(size_t)r * 8 + e];  // two (column, weight) entries
+      acc += (T)__int_as_float(cc.y) * vsrc[cc.x];
+      acc += (T)__int_as_float(cc.w) * vsrc[cc.z];
+    }
+    if (TRF || mode == MODE_PLAIN) {
+      urow[r] = acc;
+    } else {
+      const float un = fadd_(fmul_(fmul_((float)urow[r], inv_beta), -alpha), (float)acc);
+      urow[r] = (T)un;
+      ss += un * un;
+    }
+  }
+  if (!TRF && mode == MODE_LSMR) {
+    const float tot = block_sum(ss, red);
+    if (threadIdx.x == 0) B.part_u[view * ppv + sub] = tot;
+  }
+}
+
+// Adjoint of the bilinear views: one thread per in-plane voxel, all slices; grid (ceil(ndisk/256), nc).
+// vt[c][p*L3P + z] = sum over the candidate's bilinear views and the (ray, weight) entries of voxel p of
+// weight * (un-blended row of the ray)[z].
+template <int Q, typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
+  const int c = blockIdx.y;
+  if (B.cand_tie_count[c] == 0) return;
+  if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
+  constexpr int L3P = 4 * Q, NV = 32;
+  __shared__ T s_a[NV][16], s_b[NV][16];
+  __shared__ int s_map[NV];
+  __shared__ long long s_uoff[NV];
+  const int p = blockIdx.x * HB2_BLOCK + threadIdx.x;
+  const bool on = p < B.ndisk;
+  const int ZMP = B.ZMP, KB = B.bil_KB;
+  T ib = (T)1;
+  if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
+  T acc[L3P];
+#pragma unroll
+  for (int z = 0; z < L3P; ++z) acc[z] = (T)0;
+  const int slot = on ? B.aslot[p] : 0;
+  const int vb = B.cand_view_begin[c], nvw = B.bil_cand_nview[c];
+  for (int v0 = 0; v0 < nvw; v0 += NV) {
+    const int nv = min(NV, nvw - v0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nv * 16; e += HB2_BLOCK) {
+      const int v = e >> 4, t = e & 15;
+      const bool in = t < ZMP;
+      s_a[v][t] = in ? (T)B.bil_ab[((size_t)(vb + v0 + v) * ZMP + t) * 2] : (T)0;
+      s_b[v][t] = in ? (T)B.bil_ab[((size_t)(vb + v0 + v) * ZMP + t) * 2 + 1] : (T)0;
+    }
+    if (threadIdx.x < nv) { s_map[threadIdx.x] = B.bil_view_map[vb + v0 + threadIdx.x]; s_uoff[threadIdx.x] = B.view_uoff[vb + v0 + threadIdx.x]; }
+    __syncthreads();
+    if (!on) continue;
+    for (int v = 0; v < nv; ++v) {
+      const int map = s_map[v];
+      const T* __restrict__ ub = rows + s_uoff[v];
+      for (int k = 0; k < KB; ++k) {
+        const size_t mi = ((size_t)map * KB + k) * B.apitch + slot;
+        const unsigned j = B.bilT_j[mi];
+        if (j == 0xFFFFu) break;  // entries are packed from k = 0
+        const T w = (T)B.bilT_w[mi];
+        const T* __restrict__ uj = ub + (size_t)j * ZMP;
+        T r[L3P];
+#pragma unroll
+        for (int z4 = 0; z4 < L3P; z4 += 4) ld4<T>(uj + z4, r[z4], r[z4 + 1], r[z4 + 2], r[z4 + 3]);
+#pragma unroll
+        for (int t = 0; t < L3P; ++t) {
+          const T val = w * (TRF ? r[t] : (T)fmaf((float)r[t], (float)ib, 0.f));
+          if (t == 0) { acc[0] += s_a[v][0] * val; if (L3P > 1) acc[1] += s_b[v][0] * val; }
+          else { acc[t - 1] += s_a[v][t] * val; acc[t] += s_b[v][t] * val; }
+        }
+      }
+    }
+  }
+  if (!on) return;
+  T* dst = vt + (size_t)c * B.npad + (size_t)p * L3P;
+#pragma unroll
+  for (int z = 0; z < L3P; ++z) dst[z] = z < B.L3 ? acc[z] : (T)0;
+}
+
+// Adjoint of the trilinear symmetry rows, ADDED to vt (run after k_adj_bil): one warp per voxel entry g = p*L3P + z,
+// fixed lane-strided order + xor tree (deterministic).
+template <typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_lsym(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
+  const int c = blockIdx.y;
+  if (B.cand_tie_count[c] == 0) return;
+  if (B.ls_m[c] == 0) return;
+  if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
+  const int g = blockIdx.x * (HB2_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= B.npad) return;
+  T ib = (T)1;
+  if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
+  const T* __restrict__ ub = rows + B.cand_uoff[c] + (long long)B.bil_cand_nview[c] * B.rows_per_view;
+  const int* __restrict__ cp = B.ls_cptr + (size_t)c * (B.npad + 1);
+  const int2* __restrict__ ce = B.ls_cent + B.ls_ceoff[c];
+  T acc = (T)0;
+  const int e0 = cp[g], e1 = cp[g + 1];
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int2 en = ce[e];
+    const T uv = ub[en.x];
+    const T val = TRF ? uv : (T)fmaf((float)uv, (float)ib, 0.f);
+    acc += (T)__int_as_float(en.y) * val;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && e1 > e0) vt[(size_t)c * B.npad + g] += acc;
+}
+
+// trilinear symmetry rows of one candidate: pack (column, weight) pairs; transpose helpers
+__global__ void k_ls_pack(long long n, const int* __restrict__ col, const float* __restrict__ w, int2* __restrict__ ent) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) ent[e] = make_int2(col[e], __float_as_int(w[e]));
+}
+__global__ void k_ls_keys(long long n, const int2* __restrict__ ent, int* __restrict__ key, int* __restrict__ id, int* __restrict__ cc) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int c = ent[e].x;
+  key[e] = c; id[e] = (int)e;
+  atomicAdd(&cc[c], 1);
+}
+__global__ void k_ls_gather(long long n, const int* __restrict__ order, const int2* __restrict__ ent, int2* __restrict__ cent) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) { const int o = order[e]; cent[e] = make_int2(o >> 4, ent[o].y); }
+}

@@ -122,6 +122,25 @@ struct BD {
   const int* exp_cptr;          // [npad + 1]
   const int* exp_crow;
   const float* exp_cw;
+  // matrix-free trilinear rows (hb2_bilinear.cuh): bilinear in-plane footprints per map + per-column slice blends
+  int bil;                      // 1: every data view of the batch is a bilinear view (all views are pseudo views)
+  int bil_KB;                   // (ray, weight) slots per (map, voxel) of the transposed maps
+  const void* bilF_p;           // forward lists: voxel rank per entry (uint16 while the disk has < 65535 voxels, else uint32)
+  const float* bilF_w;          //                weight per entry
+  const int* bilF_ptr;          // [nM*D2 + 1] entries of ray (map, j)
+  const uint16_t* bilT_j;       // [nM][KB][apitch] transposed maps: ray of the k-th entry of voxel p, 0xFFFF = none
+  const float* bilT_w;          // [nM][KB][apitch]
+  const uint8_t* bil_rayvalid;  // [nM][D2]
+  const int* bil_view_map;      // [nviews] map of a bilinear view, -1 for the pseudo views of the trilinear symmetry rows
+  const int* bil_colk;          // [nviews][ZMP] image column of slot t or -1
+  const double* bil_ab;         // [nviews][ZMP][2] blend of slot t: a P[t-1] + b P[t] (t = 0: a P[0] + b P[1])
+  const int* bil_cand_nview;    // [nc] bilinear views of the candidate (first in its view range)
+  const int2* ls_ent;           // trilinear symmetry rows: 16 (internal voxel index, float weight bits) entries per row
+  const long long* ls_eoff;     // [nc] first entry of candidate c relative to ls_ent (the candidates' arrays are separate allocations)
+  const int* ls_m;              // [nc] rows
+  const int* ls_cptr;           // [nc][npad + 1] transpose lists of candidate c: entry offsets relative to ls_ceoff[c]
+  const int2* ls_cent;          // (row inside the candidate's symmetry block, float weight bits), sorted by voxel
+  const long long* ls_ceoff;    // [nc]
 };
 
 // pixel mask of candidate c (null: all rows kept)

@@ -212,6 +212,44 @@ int hb2_batch_explicit_sym_rows(hb2_batch* b, int32_t n_pairs, const double* pai
 /* the rows as 16 (column, weight) entries each, columns in the reference's voxel order; either may be NULL */
 int hb2_batch_explicit_sym_export(hb2_batch* b, int32_t* cols, float* weights);
 
+/* ---- matrix-free trilinear rows (interpolation "linear" in the grid-search case) -----------------------------
+ * build_A_data_matrix with interpolation "linear" (numba loop SLR:1403-1510) at tilt = psi = dy = 0 and
+ * scale2d_to_3d = 1: the row of (symmetry copy, image column k, ray j) factors into an in-plane bilinear footprint of
+ * the ray -- a function of the view angle only, shared by the candidates of a batch -- times a two-slice blend
+ * a_k P[zi_k] + b_k P[zi_k + 1] that depends on the column only (csrc/hb2_bilinear.cuh).  A batch of this kind holds
+ * MANY candidates; the explicit matrix of hb2_batch_explicit_rows is never built.
+ *
+ * hb2_bilinear_map: m00..m22 = entries of Rotation.from_euler("z", angle, degrees=True).as_matrix() (SLR:1576); xrow /
+ * zrow = -1 for a regular map, or the row of the coordinate tables passed along (xrows / zrows [n_tab_rows][D2] =
+ * rows of the reference's x / z tables, SLR:1712-1719, for ONE image column) for an EXACT map: where sample
+ * coordinates are integer-valued (angles 0 / 90 / 180 / 270, integer h * rise) the reference's int() truncation
+ * follows the last-bit noise of those tables per (column, sample); zrow >= 0 additionally applies the reference's
+ * slice-range test per sample with zshift = h * rise_pixel (SLR:1578, 1421-1428).
+ * build_tables = 0 only reports, per map, the number of rays with data (SLR:1496) and the number of samples within 1e-9
+ * of an integer coordinate (the host then replaces such views by single-column views with exact maps); 1 builds the
+ * maps the kernels use (call once with all maps).  Call between hb2_batch_begin (one dummy angle) and hb2_batch_create. */
+typedef struct {
+  double m00, m01, m10, m11, m22, zshift;
+  int32_t xrow, zrow;
+} hb2_bilinear_map;
+int hb2_batch_bilinear_maps(hb2_batch* b, int32_t n_maps, const hb2_bilinear_map* maps, int32_t n_tab_rows,
+                            const double* xrows, const double* zrows, int32_t build_tables, int32_t* nvalid_rays,
+                            int32_t* tie_samples);
+/* ray validity of the maps built by hb2_batch_bilinear_maps(build_tables = 1), out[n_maps*D2] */
+int hb2_batch_bilinear_ray_valid(hb2_batch* b, uint8_t* out_host);
+/* Views of the batch, indexed like the views handed to hb2_batch_create (all of them pseudo views: hb2_view.tie = 0,
+ * colk = -1): view_map[v] >= 0 -> bilinear view of that map, colk[v*ZMP + t] = image column of slot t (-1: unused),
+ * ab[(v*ZMP + t)*2 ..] = (a, b) of its slice blend: row = a P[t-1] + b P[t] for t >= 1, a P[0] + b P[1] for t = 0
+ * (a column with Z in (-1, 0): int() truncates toward zero, SLR:1418); view_map[v] = -1 -> pseudo view that holds
+ * rows_per_view of the candidate's trilinear symmetry rows.  cand_nview[c] = bilinear views of candidate c (they come
+ * first in its view range). */
+int hb2_batch_bilinear_views(hb2_batch* b, int32_t n_views, const int32_t* view_map, const int32_t* colk,
+                             const double* ab, int32_t n_cand, const int32_t* cand_nview);
+/* Trilinear symmetry rows of candidate c (arguments as hb2_batch_explicit_sym_rows); call for c = 0, 1, ... in order. */
+int hb2_batch_bilinear_sym_rows(hb2_batch* b, int32_t cand, int32_t n_pairs, const double* pair_mats,
+                                int64_t min_sym_pairs, int64_t* n_rows);
+int hb2_batch_bilinear_sym_export(hb2_batch* b, int32_t cand, int32_t* cols, float* weights);
+
 /* ---- batch: step 2, candidates ----------------------------------------- */
 /* Finalises the batch: adjoint maps, right-hand side, symmetry rows
  * (replaces SLR:1142-1218 + 1221-1287 incl. the first-seen-wins de-duplication
