@@ -184,7 +184,7 @@ class BilinearBatch(Batch):
         self.maps, self.nvalid_maps, self.n_regular_maps = maps, nvalid, nR
 
         # ---- views per candidate with the reference's early stop (SLR:1640-1647) ----------------------------------------
-        view_map, colk, ab = [], [], []
+        view_map, colk, ab, dup_of = [], [], [], []
         cand_nview = np.zeros(self.nc, dtype=np.int32)
         n_data_rows = np.zeros(self.nc, dtype=np.int64)
         self._row_src = []   # per candidate: [(copy index, [(view index in the candidate, map, k, slot)])] of the used copies
@@ -192,10 +192,13 @@ class BilinearBatch(Batch):
             total = 0
             used = []
             nv = 0
+            first_views = {}   # (h, c) -> first view of the first occurrence of the copy (Halton duplicates, SLR:1559-1571)
+            copies_ci = cand_copies[ci][0]
             for i, ent in enumerate(cand_slots[ci]):
                 rows_i = sum(int(nvalid[e[0]]) for e in ent)
                 if rows_i > 0:
                     src = []
+                    nv_copy0 = nv
                     regular = [e for e in ent if not e[5]]
                     if regular:
                         t_colk = np.full(ZMP, -1, dtype=np.int32)
@@ -218,6 +221,9 @@ class BilinearBatch(Batch):
                         view_map.append(mp); colk.append(t_colk); ab.append(t_ab)
                         src.append((nv, mp, k, slot))
                         nv += 1
+                    # identical rows of a repeated copy: served by the first occurrence's views (same order, same count)
+                    prim = first_views.setdefault(copies_ci[i], nv_copy0)
+                    dup_of.extend([-1] * (nv - nv_copy0) if prim == nv_copy0 else [prim + q for q in range(nv - nv_copy0)])
                     used.append((i, src))
                 total += rows_i
                 if sp.min_projection_lines > 0 and total > sp.min_projection_lines:
@@ -236,7 +242,7 @@ class BilinearBatch(Batch):
                 _lib.check(lib.hb2_batch_bilinear_sym_rows(self._h, ci, 0, None, -1, C.byref(ms)))
             self.m_sym[ci] = int(ms.value)
         # interleave: candidate c = its bilinear views, then ceil(m_sym / rpv) pseudo views
-        vm_all, colk_all, ab_all = [], [], []
+        vm_all, colk_all, ab_all, dup_all = [], [], [], []
         cands = np.zeros(self.nc, dtype=_lib.CANDIDATE_DTYPE)
         pos = 0
         vbeg = 0
@@ -245,8 +251,10 @@ class BilinearBatch(Batch):
             nvd = int(cand_nview[ci])
             nps = int((self.m_sym[ci] + rpv - 1) // rpv)
             vm_all.extend(view_map[pos:pos + nvd]); colk_all.extend(colk[pos:pos + nvd]); ab_all.extend(ab[pos:pos + nvd])
+            dup_all.extend(dup_of[pos:pos + nvd])
             for _ in range(nps):
                 vm_all.append(-1); colk_all.append(np.full(ZMP, -1, dtype=np.int32)); ab_all.append(np.zeros((ZMP, 2)))
+                dup_all.append(-1)
             pos += nvd
             cands[ci]["view_begin"], cands[ci]["view_count"] = vbeg, nvd + nps
             cands[ci]["pair_begin"], cands[ci]["pair_count"] = 0, 0
@@ -264,7 +272,7 @@ class BilinearBatch(Batch):
         _lib.check(lib.hb2_batch_bilinear_views(self._h, nviews, _lib.ptr(vm_arr), _lib.ptr(colk_arr), _lib.ptr(ab_arr),
                                                 self.nc, _lib.ptr(cand_nview)))
         views = np.zeros(nviews, dtype=_lib.VIEW_DTYPE)
-        views["dup_of"] = -1
+        views["dup_of"] = np.asarray(dup_all, dtype=np.int32)   # relative to the candidate's first view
         views["mult"] = 1
         dcolk = np.full(L3, -1, dtype=np.int32)
         pairs = np.zeros(0, dtype=_lib.PAIR_DTYPE)

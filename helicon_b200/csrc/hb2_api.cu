@@ -1014,7 +1014,7 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
   CKM(cudaMemcpyAsync(&KB, d_kmax, sizeof(int), cudaMemcpyDeviceToHost, st));
   CKM(cudaStreamSynchronize(st));
   KB = std::max(KB, 1);
-  if (KB > 8) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "more than 8 rays of one view touch one voxel (internal error)"); }
+  if (KB > 4) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "more than 4 rays of one view touch one voxel (internal error)"); }
   CKM(b->pool.alloc(&d_fptr, (size_t)nM * D2 + 1, false, st));
   uint16_t* d_Tj; float* d_Tw;
   CKM(b->pool.alloc(&d_Tj, (size_t)nM * KB * apitch, false, st));
@@ -1204,6 +1204,7 @@ static int bil_finish(hb2_batch* b, int nviews) {
   CK(upload(b->pool, &B.bil_colk, b->h_bil_colk, st));
   CK(upload(b->pool, &B.bil_ab, b->h_bil_ab, st));
   CK(upload(b->pool, &B.bil_cand_nview, b->h_bil_cand_nview, st));
+  CK(b->pool.alloc(&B.bil_ub, (size_t)b->u_total, true, st));
   k_bil_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
   CKL();
   // transpose lists of the trilinear symmetry rows, candidate by candidate (stable radix sort of the entries by voxel)
@@ -1375,9 +1376,9 @@ extern "C" int hb2_batch_create(hb2_batch* b, int32_t nc, const hb2_candidate* c
       if (w.angle < 0 || w.angle >= B.nA || w.col_begin < 0 || w.col_begin + B.ZMC > ncolk) return fail(HB2_ERR_ARG, "bad view");
       view_cand[vi] = c; view_angle[vi] = w.angle; view_colbegin[vi] = w.col_begin;
       static const bool no_dedupe = getenv("HB2_NO_DEDUPE") && atoi(getenv("HB2_NO_DEDUPE"));
-      if (w.dup_of >= 0 && w.tie < 0 && !no_dedupe) {  // duplicate of an earlier regular view of the same candidate
+      if (w.dup_of >= 0 && (w.tie < 0 || b->bilinear) && !no_dedupe) {  // duplicate of an earlier regular view of the same candidate
         const int prim = q.view_begin + w.dup_of;
-        if (w.dup_of >= v || views[prim].angle != w.angle || views[prim].tie >= 0 || views[prim].dup_of >= 0)
+        if (w.dup_of >= v || views[prim].angle != w.angle || (views[prim].tie >= 0 && !b->bilinear) || views[prim].dup_of >= 0)
           return fail(HB2_ERR_ARG, "bad duplicate view");
         int slot = 0;
         while (slot < HB2_MAXDUP && view_dups[(size_t)prim * HB2_MAXDUP + slot] >= 0) ++slot;
@@ -1911,13 +1912,16 @@ static void launch_adj(hb2_batch* b, int mode) {
   cudaStream_t st = b->stream;
   if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
     if (b->bilinear) {
-      const dim3 ga(cdiv(B.ndisk, HB2_BLOCK), B.nc);
-      if (B.L3P == 4) k_adj_bil<1, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
-      else if (B.L3P == 8) k_adj_bil<2, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
-      else if (B.L3P == 12) k_adj_bil<3, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
-      else k_adj_bil<4, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
-      k_adj_lsym<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
-      b->extra_launches += 1;
+      const dim3 ga(cdiv(B.ndisk, (HB2_BLOCK / 32) * (32 / (B.L3P / 4))), B.nc);  // (voxel, quad) lanes
+#define ABIL(Q)                                                                                      \
+  do {                                                                                               \
+    k_bil_unblend<Q, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.bil_ub, mode); \
+    k_adj_bil<Q, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.bil_ub, B.vtie, mode);          \
+  } while (0)
+      if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);
+#undef ABIL
+      k_adj_lsym<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
+      b->extra_launches += 2;
     } else if (b->explicit_rows) k_adj_csc<float, false><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     else k_adj_tie<float, false><<<dim3(cdiv(B.ndisk, HB2_BLOCK), B.nc), HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.vtie, mode);
     b->extra_launches += 1;
@@ -2027,6 +2031,8 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   for (double** p : nvecs) CKT2(tmp.alloc(p, nv, true, st));
   B.vtie64 = nullptr;
   if (b->n_tie_views > 0) CKT2(tmp.alloc(&B.vtie64, nv, true, st));
+  B.bil_ub64 = nullptr;
+  if (b->bilinear) CKT2(tmp.alloc(&B.bil_ub64, nu, true, st));
   double** mvecs[] = {&T.R, &T.UM, &T.Y, &T.Y2};
   for (double** p : mvecs) CKT2(tmp.alloc(p, nu, true, st));
   long long max_m = 0;
@@ -2104,13 +2110,16 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   auto adj = [&](const double* rows, double* dst, int gate) {
     if (b->n_tie_views > 0) {
       if (b->bilinear) {
-        const dim3 ga(cdiv(B.ndisk, HB2_BLOCK), nc);
-        if (B.L3P == 4) k_adj_bil<1, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
-        else if (B.L3P == 8) k_adj_bil<2, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
-        else if (B.L3P == 12) k_adj_bil<3, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
-        else k_adj_bil<4, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
-        k_adj_lsym<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
-        ++launches;
+        const dim3 ga(cdiv(B.ndisk, (HB2_BLOCK / 32) * (32 / (B.L3P / 4))), nc);
+#define ABIL(Q)                                                                                        \
+  do {                                                                                                 \
+    k_bil_unblend<Q, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, rows, B.bil_ub64, gate); \
+    k_adj_bil<Q, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, B.bil_ub64, B.vtie64, gate);           \
+  } while (0)
+        if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);
+#undef ABIL
+        k_adj_lsym<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
+        launches += 2;
       } else if (b->explicit_rows) k_adj_csc<double, true><<<dim3(cdiv(B.npad, HB2_BLOCK / 32), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       else k_adj_tie<double, true><<<dim3(cdiv(B.ndisk, HB2_BLOCK), nc), HB2_BLOCK, 0, st>>>(B, T, rows, B.vtie64, gate);
       ++launches;

@@ -34,20 +34,21 @@ struct BilMap {  // == hb2_bilinear_map (include/helicon_b200.h)
   int32_t xrow, zrow;
 };
 
-struct BilS { int xi, yi; double xf, yf; bool ok, near; };
+struct BilS { int xi, yi; double xf, yf, X, Y; bool ok, nearx, neary; };
 
 // One depth sample of ray j exactly as k_exp_rows computes it (rot_yx = identity, dy = 0, s = 1).
 __device__ __forceinline__ BilS bil_sample(const BilMap& M, const double* __restrict__ xrows, const double* __restrict__ zrows,
                                            int D2, int L3, const int* __restrict__ rank, int j, int i) {
   BilS r;
-  r.ok = false; r.near = false; r.xi = r.yi = 0; r.xf = r.yf = 0.0;
+  r.ok = false; r.nearx = r.neary = false; r.xi = r.yi = 0; r.xf = r.yf = 0.0;
   const int c0 = D2 / 2;
   const double x0 = M.xrow >= 0 ? xrows[(size_t)M.xrow * D2 + i] : -(double)(i - c0);
   const double y0 = (double)(j - c0);
   const double X = __dadd_rn(__fma_rn(M.m10, y0, __dmul_rn(M.m00, x0)), (double)c0);
   const double Y = __dadd_rn(__fma_rn(M.m11, y0, __dmul_rn(M.m01, x0)), (double)c0);
+  r.X = X; r.Y = Y;
   if (!(Y > -1.0 && Y < (double)D2 && X > -1.0 && X < (double)D2)) return r;
-  r.near = fabs(X - rint(X)) < 1e-9 || fabs(Y - rint(Y)) < 1e-9;
+  r.nearx = fabs(X - rint(X)) < 1e-9; r.neary = fabs(Y - rint(Y)) < 1e-9;
   if (M.zrow >= 0) {  // per-sample slice validity from the reference's z table (integer h * rise)
     const double z2 = __dmul_rn(M.m22, zrows[(size_t)M.zrow * D2 + i]);
     const double Z = __dadd_rn(__dsub_rn(z2, M.zshift), (double)(L3 / 2));
@@ -64,8 +65,11 @@ __device__ __forceinline__ BilS bil_sample(const BilMap& M, const double* __rest
   return r;
 }
 
-// rayvalid[m][j] = the ray has a valid sample (SLR:1496 has_projection_data); tie[m] = samples within 1e-9 of an integer
-// coordinate (the host replaces such views by exact per-column maps).
+// rayvalid[m][j] = the ray has a valid sample (SLR:1496 has_projection_data); tie[m] = samples with a coordinate within
+// 1e-9 of an integer WHOSE VALIDITY DEPENDS ON THE int() DECISION (the four corners of one choice lie inside the mask,
+// those of the other do not): there the reference follows the last-bit noise of its coordinate tables and the host
+// replaces the view by exact per-column maps.  Everywhere else the flip is invisible -- bilinear weights are continuous
+// across an integer coordinate (e.g. the sample at the rotation centre, integer-valued at every angle).
 __global__ void k_bil_rayvalid(int nM, int D2, int L3, const BilMap* __restrict__ maps, const double* __restrict__ xrows,
                                const double* __restrict__ zrows, const int* __restrict__ rank, uint8_t* __restrict__ rayvalid,
                                int* __restrict__ tie) {
@@ -74,7 +78,19 @@ __global__ void k_bil_rayvalid(int nM, int D2, int L3, const BilMap* __restrict_
   const int i = (int)(t % D2), j = (int)((t / D2) % D2), m = (int)(t / ((long long)D2 * D2));
   const BilS s = bil_sample(maps[m], xrows, zrows, D2, L3, rank, j, i);
   if (s.ok) rayvalid[(size_t)m * D2 + j] = 1;  // benign race: all writers store 1
-  if (s.near) atomicAdd(&tie[m], 1);
+  if (s.nearx || s.neary) {
+    const int xr = (int)rint(s.X), yr = (int)rint(s.Y);
+    const int xa0 = s.nearx ? max(xr - 1, 0) : (int)s.X, xa1 = s.nearx ? max(xr, 0) : (int)s.X;
+    const int ya0 = s.neary ? max(yr - 1, 0) : (int)s.Y, ya1 = s.neary ? max(yr, 0) : (int)s.Y;
+    bool any = false, all = true;
+    for (int yy = ya0; yy <= ya1; ++yy)
+      for (int xx = xa0; xx <= xa1; ++xx) {
+        const bool v = yy + 1 <= D2 - 1 && xx + 1 <= D2 - 1 && rank[yy * D2 + xx] >= 0 && rank[yy * D2 + xx + 1] >= 0 &&
+                       rank[(yy + 1) * D2 + xx] >= 0 && rank[(yy + 1) * D2 + xx + 1] >= 0;
+        any = any || v; all = all && v;
+      }
+    if (any && !all) atomicAdd(&tie[m], 1);
+  }
 }
 
 // Transposed maps, voxel-driven.  PASS 0: kmax = max rays per (map, voxel), fcount[m][j] += 1 per entry;
@@ -190,22 +206,34 @@ __device__ __forceinline__ void ld4<double>(const double* __restrict__ p, double
 
 // Forward of the bilinear views.  Grid (pseudo views, fwd_ppv); one warp per ray j; lane = (slice quad q, entry group
 // g): lanes q*G .. q*G + G - 1 walk the ray's footprint list G entries at a time, 128-bit gathers of 4 slices x weight;
-// a shuffle tree over g leaves P[4q .. 4q+3]; lane t < ZMP then blends and finishes column slot t.
+// a shuffle tree over g leaves P[4q .. 4q+3]; lane t < ZMP then blends and finishes column slot t.  Quads whose slices
+// no used slot of the view needs (single-column views of the exact maps) issue no gathers.  Halton duplicates of a copy
+// (identical rows, SLR:1559-1571) are served by the first copy's CTAs in the float32 modes (BD::view_dups).
 template <typename IdxT, int Q, typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
   const int view = B.tie_views[blockIdx.x];
   const int map = B.bil_view_map[view];
   if (map < 0) return;  // trilinear symmetry rows: k_fwd_lsym
+  if (!TRF && B.view_dupof[view] >= 0) return;  // duplicate of an earlier view: written by that view's CTAs
   const int c = B.view_cand[view];
   __shared__ float red[HB2_BLOCK / 32];
   __shared__ T s_P[HB2_BLOCK / 32][16];
   __shared__ T s_a[16], s_b[16];
   __shared__ int s_colk[16];
+  __shared__ unsigned s_qmask;
   const int ppv = B.fwd_ppv, sub = blockIdx.y;
+  int dupv[HB2_MAXDUP];
+#pragma unroll
+  for (int d = 0; d < HB2_MAXDUP; ++d) dupv[d] = TRF ? -1 : B.view_dups[view * HB2_MAXDUP + d];
   if (!tie_active<TRF>(B, Tt, c, mode, false)) {
     if (!TRF && threadIdx.x == 0) {
-      if (mode == MODE_LSMR) B.part_u[view * ppv + sub] = 0.f;
-      if (mode == MODE_SCORE) { B.part_s[3 * (view * ppv + sub)] = 0.f; B.part_s[3 * (view * ppv + sub) + 1] = 0.f; B.part_s[3 * (view * ppv + sub) + 2] = 0.f; }
+#pragma unroll
+      for (int d = -1; d < HB2_MAXDUP; ++d) {
+        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+        if (vw < 0) continue;
+        if (mode == MODE_LSMR) B.part_u[vw * ppv + sub] = 0.f;
+        if (mode == MODE_SCORE) { B.part_s[3 * (vw * ppv + sub)] = 0.f; B.part_s[3 * (vw * ppv + sub) + 1] = 0.f; B.part_s[3 * (vw * ppv + sub) + 2] = 0.f; }
+      }
     }
     return;
   }
@@ -214,9 +242,21 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   const int D2 = B.D2, ZMP = B.ZMP;
   if (threadIdx.x < 16) {
     const bool in = (int)threadIdx.x < ZMP;
-    s_colk[threadIdx.x] = in ? B.bil_colk[(size_t)view * ZMP + threadIdx.x] : -1;
+    const int ck = in ? B.bil_colk[(size_t)view * ZMP + threadIdx.x] : -1;
+    s_colk[threadIdx.x] = ck;
     s_a[threadIdx.x] = in ? (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2] : (T)0;
     s_b[threadIdx.x] = in ? (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2 + 1] : (T)0;
+    // slices the used slots read: t = 0 -> {0, 1}, t >= 1 -> {t - 1, t}
+    const int t = threadIdx.x;
+    unsigned need = 0;
+    if (ck >= 0) need = t == 0 ? 3u : (3u << (t - 1));
+    need |= __shfl_xor_sync(0xffffu, need, 8); need |= __shfl_xor_sync(0xffffu, need, 4);
+    need |= __shfl_xor_sync(0xffffu, need, 2); need |= __shfl_xor_sync(0xffffu, need, 1);
+    if (t == 0) {
+      unsigned qm = 0;
+      for (int qq = 0; qq < Q; ++qq) qm |= ((need >> (4 * qq)) & 15u) ? (1u << qq) : 0u;
+      s_qmask = qm;
+    }
   }
   __syncthreads();
   const IdxT* __restrict__ Fp = (const IdxT*)B.bilF_p;
@@ -228,7 +268,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   const float* brow = B.b + B.view_uoff[view];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane / G, g = lane % G;
-  const bool lane_on = q < Q;
+  const bool lane_on = q < Q && ((s_qmask >> q) & 1u);
   float alpha = 0.f, inv_beta = 0.f;
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
@@ -264,14 +304,14 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
     if (G > P2) {
       const T b0 = __shfl_down_sync(0xffffffffu, a0, P2), b1 = __shfl_down_sync(0xffffffffu, a1, P2);
       const T b2 = __shfl_down_sync(0xffffffffu, a2, P2), b3 = __shfl_down_sync(0xffffffffu, a3, P2);
-      if (lane_on && g + P2 < G) { a0 += b0; a1 += b1; a2 += b2; a3 += b3; }
+      if (q < Q && g + P2 < G) { a0 += b0; a1 += b1; a2 += b2; a3 += b3; }
     }
 #pragma unroll
     for (int o = P2 / 2; o > 0; o >>= 1) {
       a0 += __shfl_down_sync(0xffffffffu, a0, o); a1 += __shfl_down_sync(0xffffffffu, a1, o);
       a2 += __shfl_down_sync(0xffffffffu, a2, o); a3 += __shfl_down_sync(0xffffffffu, a3, o);
     }
-    if (lane_on && g == 0) { s_P[warp][4 * q] = a0; s_P[warp][4 * q + 1] = a1; s_P[warp][4 * q + 2] = a2; s_P[warp][4 * q + 3] = a3; }
+    if (q < Q && g == 0) { s_P[warp][4 * q] = a0; s_P[warp][4 * q + 1] = a1; s_P[warp][4 * q + 2] = a2; s_P[warp][4 * q + 3] = a3; }
     __syncwarp();
     if (lane < ZMP && s_colk[lane] >= 0 && !(pm && !pm[(size_t)s_colk[lane] * D2 + j])) {
       const T lo = lane == 0 ? s_P[warp][0] : s_P[warp][lane - 1];
@@ -283,9 +323,15 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
       } else if (mode == MODE_LSMR) {
         const float un = fadd_(fmul_(fmul_((float)urow[ri], inv_beta), -alpha), (float)acc);
         urow[ri] = (T)un;
+#pragma unroll
+        for (int d = 0; d < HB2_MAXDUP; ++d)
+          if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = (T)un;  // identical row of the duplicate view
         ss += un * un;
       } else if (mode == MODE_PLAIN) {
         urow[ri] = acc;
+#pragma unroll
+        for (int d = 0; d < HB2_MAXDUP; ++d)
+          if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = acc;
       } else {
         const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
         const float bv = brow[ri];
@@ -294,16 +340,26 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
     }
     __syncwarp();
   }
-  if (!TRF) {
+  if (!TRF) {  // partials of the view and of the duplicates it serves (identical rows -> identical partial sums)
     if (mode == MODE_LSMR) {
       const float tot = block_sum(ss, red);
-      if (threadIdx.x == 0) B.part_u[view * ppv + sub] = tot;
+      if (threadIdx.x == 0) {
+        B.part_u[view * ppv + sub] = tot;
+#pragma unroll
+        for (int d = 0; d < HB2_MAXDUP; ++d)
+          if (dupv[d] >= 0) B.part_u[dupv[d] * ppv + sub] = tot;
+      }
     } else if (mode == MODE_SCORE) {
       const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
       if (threadIdx.x == 0) {
-        B.part_s[3 * (view * ppv + sub)] = t0;
-        B.part_s[3 * (view * ppv + sub) + 1] = t1;
-        B.part_s[3 * (view * ppv + sub) + 2] = t2;
+#pragma unroll
+        for (int d = -1; d < HB2_MAXDUP; ++d) {
+          const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
+          if (vw < 0) continue;
+          B.part_s[3 * (vw * ppv + sub)] = t0;
+          B.part_s[3 * (vw * ppv + sub) + 1] = t1;
+          B.part_s[3 * (vw * ppv + sub) + 2] = t2;
+        }
       }
     }
   }
@@ -357,93 +413,141 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_lsym(BD B, TD Tt, const T* __
   }
 }
 
-// Adjoint of the bilinear views: one thread per in-plane voxel, all slices; grid (ceil(ndisk/256), nc).
-// vt[c][p*L3P + z] = sum over the candidate's bilinear views and the (ray, weight) entries of voxel p of
-// weight * (un-blended row of the ray)[z].
+// Adjoint of the bilinear views, step 1: un-blend the rows of every (view, ray) into slice space,
+//     ub[view][j][z] = scale * (b_z r[z] + a_{z+1} r[z+1])   (+ the slot-0 terms a_0 r[0] on slice 0, b_0 r[0] on slice 1),
+// scale = 1/beta in the LSMR modes (x the multiplicity of a view that serves Halton duplicates; the duplicates are
+// skipped -- float32 solver modes only).  One thread per ray; 2 x rows traffic, ~2 us per candidate-pass.
 template <int Q, typename T, bool TRF>
-__global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
+__global__ void __launch_bounds__(HB2_BLOCK) k_bil_unblend(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ ub, int mode) {
+  const int view = B.tie_views[blockIdx.x];
+  const int map = B.bil_view_map[view];
+  if (map < 0) return;
+  const int c = B.view_cand[view];
+  if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
+  const bool dedupe = !TRF && mode != MODE_PLAIN;
+  if (dedupe && B.view_dupof[view] >= 0) return;
+  constexpr int L3P = 4 * Q;
+  __shared__ T s_a[20], s_b[20];
+  const int ZMP = B.ZMP, D2 = B.D2;
+  T scale = (T)1;
+  if (!TRF && mode != MODE_PLAIN) scale = (T)B.st[c].inv_beta;
+  if (dedupe) scale *= (T)B.view_mult[view];
+  if (threadIdx.x < 20) {
+    const bool in = (int)threadIdx.x < ZMP;
+    s_a[threadIdx.x] = in ? scale * (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2] : (T)0;
+    s_b[threadIdx.x] = in ? scale * (T)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2 + 1] : (T)0;
+  }
+  __syncthreads();
+  const uint8_t* __restrict__ rv = B.bil_rayvalid + (size_t)map * D2;
+  const T* __restrict__ src = rows + B.view_uoff[view];
+  T* dst = ub + B.view_uoff[view];
+  for (int j = threadIdx.x; j < D2; j += HB2_BLOCK) {
+    if (!rv[j]) continue;  // rays without data appear in no transposed map
+    T r[L3P + 1], o[L3P];
+#pragma unroll
+    for (int z4 = 0; z4 < L3P; z4 += 4) ld4<T>(src + (size_t)j * ZMP + z4, r[z4], r[z4 + 1], r[z4 + 2], r[z4 + 3]);
+    r[L3P] = (T)0;
+#pragma unroll
+    for (int z = 0; z < L3P; ++z) o[z] = s_b[z] * r[z] + s_a[z + 1] * r[z + 1];
+    o[0] = s_a[0] * r[0] + s_a[1] * r[1];  // slot 0 blends slices (0, 1): a_0 r[0] -> slice 0, b_0 r[0] -> slice 1
+    o[1] += s_b[0] * r[0];
+#pragma unroll
+    for (int z4 = 0; z4 < L3P; z4 += 4) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(dst + (size_t)j * ZMP + z4) = make_float4(o[z4], o[z4 + 1], o[z4 + 2], o[z4 + 3]);
+      } else {
+        *reinterpret_cast<double2*>(dst + (size_t)j * ZMP + z4) = make_double2(o[z4], o[z4 + 1]);
+        *reinterpret_cast<double2*>(dst + (size_t)j * ZMP + z4 + 2) = make_double2(o[z4 + 2], o[z4 + 3]);
+      }
+    }
+  }
+}
+
+// Adjoint of the bilinear views, step 2: weighted gather of the un-blended rows.  Lane = (in-plane voxel p, slice quad
+// q), 32 / Q voxels per warp; grid (ceil(ndisk / voxels per CTA), nc):
+//     vt[c][p*L3P + 4q ..] = sum over the candidate's views and the <= KB (ray, weight) entries of voxel p of w * ub[view][ray][4q ..]
+// The entries of a (view, voxel) are loaded together (independent 128-bit row loads in flight).
+template <int Q, typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __restrict__ ub, T* __restrict__ vt, int mode) {
   const int c = blockIdx.y;
   if (B.cand_tie_count[c] == 0) return;
   if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
-  constexpr int L3P = 4 * Q, NV = 32;
-  __shared__ T s_a[NV][16], s_b[NV][16];
+  constexpr int L3P = 4 * Q, NV = 64, VPW = 32 / Q, KMAX = 4;
   __shared__ int s_map[NV];
   __shared__ long long s_uoff[NV];
-  const int p = blockIdx.x * HB2_BLOCK + threadIdx.x;
-  const bool on = p < B.ndisk;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vl = lane / Q, q = lane % Q;
+  const int p = (blockIdx.x * (HB2_BLOCK / 32) + warp) * VPW + vl;
+  const bool on = vl < VPW && p < B.ndisk;
   const int ZMP = B.ZMP, KB = B.bil_KB;
-  T ib = (T)1;
-  if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
-  T acc[L3P];
-#pragma unroll
-  for (int z = 0; z < L3P; ++z) acc[z] = (T)0;
+  const bool dedupe = !TRF && mode != MODE_PLAIN;
+  T acc0 = (T)0, acc1 = (T)0, acc2 = (T)0, acc3 = (T)0;
   const int slot = on ? B.aslot[p] : 0;
   const int vb = B.cand_view_begin[c], nvw = B.bil_cand_nview[c];
+  const size_t kstride = (size_t)B.apitch;
   for (int v0 = 0; v0 < nvw; v0 += NV) {
     const int nv = min(NV, nvw - v0);
     __syncthreads();
-    for (int e = threadIdx.x; e < nv * 16; e += HB2_BLOCK) {
-      const int v = e >> 4, t = e & 15;
-      const bool in = t < ZMP;
-      s_a[v][t] = in ? (T)B.bil_ab[((size_t)(vb + v0 + v) * ZMP + t) * 2] : (T)0;
-      s_b[v][t] = in ? (T)B.bil_ab[((size_t)(vb + v0 + v) * ZMP + t) * 2 + 1] : (T)0;
+    if (threadIdx.x < nv) {
+      const int view = vb + v0 + threadIdx.x;
+      s_map[threadIdx.x] = (dedupe && B.view_dupof[view] >= 0) ? -1 : B.bil_view_map[view];
+      s_uoff[threadIdx.x] = B.view_uoff[view];
     }
-    if (threadIdx.x < nv) { s_map[threadIdx.x] = B.bil_view_map[vb + v0 + threadIdx.x]; s_uoff[threadIdx.x] = B.view_uoff[vb + v0 + threadIdx.x]; }
     __syncthreads();
     if (!on) continue;
     for (int v = 0; v < nv; ++v) {
       const int map = s_map[v];
-      const T* __restrict__ ub = rows + s_uoff[v];
-      for (int k = 0; k < KB; ++k) {
-        const size_t mi = ((size_t)map * KB + k) * B.apitch + slot;
-        const unsigned j = B.bilT_j[mi];
-        if (j == 0xFFFFu) break;  // entries are packed from k = 0
-        const T w = (T)B.bilT_w[mi];
-        const T* __restrict__ uj = ub + (size_t)j * ZMP;
-        T r[L3P];
+      if (map < 0) continue;  // block-uniform
+      const T* __restrict__ ubv = ub + s_uoff[v] + 4 * q;
+      const uint16_t* __restrict__ tj = B.bilT_j + (size_t)map * KB * kstride + slot;
+      const float* __restrict__ tw = B.bilT_w + (size_t)map * KB * kstride + slot;
+      unsigned jj[KMAX];
+      float ww[KMAX];
 #pragma unroll
-        for (int z4 = 0; z4 < L3P; z4 += 4) ld4<T>(uj + z4, r[z4], r[z4 + 1], r[z4 + 2], r[z4 + 3]);
+      for (int k = 0; k < KMAX; ++k)
+        if (k < KB) { jj[k] = tj[(size_t)k * kstride]; ww[k] = tw[(size_t)k * kstride]; }
+      T r0[KMAX], r1[KMAX], r2[KMAX], r3[KMAX];
 #pragma unroll
-        for (int t = 0; t < L3P; ++t) {
-          const T val = w * (TRF ? r[t] : (T)fmaf((float)r[t], (float)ib, 0.f));
-          if (t == 0) { acc[0] += s_a[v][0] * val; if (L3P > 1) acc[1] += s_b[v][0] * val; }
-          else { acc[t - 1] += s_a[v][t] * val; acc[t] += s_b[v][t] * val; }
+      for (int k = 0; k < KMAX; ++k)
+        if (k < KB) {
+          r0[k] = r1[k] = r2[k] = r3[k] = (T)0;
+          if (jj[k] != 0xFFFFu) ld4<T>(ubv + (size_t)jj[k] * ZMP, r0[k], r1[k], r2[k], r3[k]);
         }
-      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < KB) { const T w = (T)ww[k]; acc0 += w * r0[k]; acc1 += w * r1[k]; acc2 += w * r2[k]; acc3 += w * r3[k]; }
     }
   }
   if (!on) return;
-  T* dst = vt + (size_t)c * B.npad + (size_t)p * L3P;
-#pragma unroll
-  for (int z = 0; z < L3P; ++z) dst[z] = z < B.L3 ? acc[z] : (T)0;
+  T* dst = vt + (size_t)c * B.npad + (size_t)p * L3P + 4 * q;
+  const int z = 4 * q;
+  dst[0] = z < B.L3 ? acc0 : (T)0; dst[1] = z + 1 < B.L3 ? acc1 : (T)0;
+  dst[2] = z + 2 < B.L3 ? acc2 : (T)0; dst[3] = z + 3 < B.L3 ? acc3 : (T)0;
 }
 
-// Adjoint of the trilinear symmetry rows, ADDED to vt (run after k_adj_bil): one warp per voxel entry g = p*L3P + z,
-// fixed lane-strided order + xor tree (deterministic).
+// Adjoint of the trilinear symmetry rows, ADDED to vt (run after k_adj_bil): one thread per voxel entry g = p*L3P + z
+// walking its transpose list (~6 entries, sorted by row: deterministic).
 template <typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BLOCK) k_adj_lsym(BD B, TD Tt, const T* __restrict__ rows, T* __restrict__ vt, int mode) {
   const int c = blockIdx.y;
   if (B.cand_tie_count[c] == 0) return;
   if (B.ls_m[c] == 0) return;
   if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
-  const int g = blockIdx.x * (HB2_BLOCK / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int g = blockIdx.x * HB2_BLOCK + threadIdx.x;
   if (g >= B.npad) return;
   T ib = (T)1;
   if (!TRF && mode != MODE_PLAIN) ib = (T)B.st[c].inv_beta;
   const T* __restrict__ ub = rows + B.cand_uoff[c] + (long long)B.bil_cand_nview[c] * B.rows_per_view;
   const int* __restrict__ cp = B.ls_cptr + (size_t)c * (B.npad + 1);
   const int2* __restrict__ ce = B.ls_cent + B.ls_ceoff[c];
-  T acc = (T)0;
   const int e0 = cp[g], e1 = cp[g + 1];
-  for (int e = e0 + lane; e < e1; e += 32) {
+  if (e1 <= e0) return;
+  T acc = (T)0;
+  for (int e = e0; e < e1; ++e) {
     const int2 en = ce[e];
-    const T uv = ub[en.x];
-    const T val = TRF ? uv : (T)fmaf((float)uv, (float)ib, 0.f);
-    acc += (T)__int_as_float(en.y) * val;
+    acc += (T)__int_as_float(en.y) * ub[en.x];
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0 && e1 > e0) vt[(size_t)c * B.npad + g] += acc;
+  vt[(size_t)c * B.npad + g] += acc * ib;
 }
 
 // trilinear symmetry rows of one candidate: pack (column, weight) pairs; transpose helpers

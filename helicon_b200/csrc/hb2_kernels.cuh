@@ -135,6 +135,8 @@ struct BD {
   const int* bil_colk;          // [nviews][ZMP] image column of slot t or -1
   const double* bil_ab;         // [nviews][ZMP][2] blend of slot t: a P[t-1] + b P[t] (t = 0: a P[0] + b P[1])
   const int* bil_cand_nview;    // [nc] bilinear views of the candidate (first in its view range)
+  float* bil_ub;                // rows layout of u: the un-blended (slice-space) rows the adjoint gathers (k_bil_unblend)
+  double* bil_ub64;             // same for the float64 operators of the bounded branch
   const int2* ls_ent;           // trilinear symmetry rows: 16 (internal voxel index, float weight bits) entries per row
   const long long* ls_eoff;     // [nc] first entry of candidate c relative to ls_ent (the candidates' arrays are separate allocations)
   const int* ls_m;              // [nc] rows

@@ -46,11 +46,14 @@ class BatchPipeline:
         for i, (_, batch) in enumerate(self.run_items((prob, L3, ch, None) for ch in chunks)):
             yield i, batch
 
-    def run_items(self, items):
+    def run_items(self, items, factory=None):
         """``items`` yields ``(prob, L3, specs, tag)`` lazily -- e.g. pulled from a ``ChunkQueue`` shared by several
         ranks: the NEXT item is fetched (and its batch built) by the worker thread while the current batch is being
-        solved by the caller.  Yields ``(tag, batch)`` in order."""
+        solved by the caller.  Yields ``(tag, batch)`` in order.  ``factory(prob, L3, specs, stream)`` builds the batch
+        (default: the nearest-neighbour ``Batch``)."""
         it = iter(items)
+        if factory is None:
+            factory = lambda prob, L3, specs, stream: Batch(prob, L3, specs, stream=stream)
         streams = self.streams
         count = [0]
 
@@ -61,7 +64,7 @@ class BatchPipeline:
                 return None
             i = count[0]
             count[0] += 1
-            return tag, Batch(prob, L3, specs, stream=streams[i % 2])
+            return tag, factory(prob, L3, specs, streams[i % 2])
 
         if not self.pipelined:
             while True:
@@ -264,7 +267,10 @@ def make_chunks(tasks, ndisk_of, batch_candidates=None, mem_budget_bytes=48 << 3
         per_cand = _bytes_per_candidate(n3, md_est, cap_est) * (2 if pipelined else 1)  # two batches resident
         bs = batch_candidates or max(1, min(512, int(mem_budget_bytes // per_cand)))
         if interpolation != "nn":
-            bs = 1
+            # trilinear rows: matrix-free batches where the factorisation applies (bilinear.py; ~0.3 GB per candidate:
+            # 16-entry symmetry rows + their transpose), else one candidate at a time on explicit rows
+            mf = s == 1.0 and D3 == D2 and L3 <= 16
+            bs = max(1, min(batch_candidates or 50, int(mem_budget_bytes // (per_cand + 40 * 16 * cap_est)))) if mf else 1
         for i0 in range(0, len(tl), bs):
             ch = tl[i0:i0 + bs]
             chunks.append((key, ch, float(n3) * len(ch)))
@@ -280,8 +286,8 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     """Solve + score every candidate of the grid on one GPU (or this rank's share of it).
 
     ``interpolation="nn"`` runs batches of candidates through the matrix-free projector; ``"linear"`` (trilinear rows,
-    SLR:1403-1510 / 910-1138) runs one candidate at a time on explicit GPU-built rows (engine.ExplicitBatch) -- same
-    results contract, lower throughput.
+    SLR:1403-1510 / 910-1138) through the matrix-free bilinear-footprint x slice-blend operator (bilinear.py) when
+    scale2d_to_3d = 1 and L3 <= 16, else one candidate at a time on explicit GPU-built rows (engine.ExplicitBatch).
 
     Several GPUs split the grid by CHUNKS (batches of consecutive candidates) without any data-path communication:
     ``shard=(rank, world)`` deals the cost-sorted chunk list round-robin; with ``dist`` (an initialised
@@ -381,18 +387,25 @@ def solve_chunks(chunks, queue, problem_of, device=0, pipelined=True, interpolat
     The batch of chunk i+1 is planned and set up by a worker thread (second stream) while chunk i is being solved
     (BatchPipeline).  ``on_result(chunk_tasks, results, batch)`` is called per solved batch, before it is closed.
     Returns the summed library timings (``profile=1`` adds the per-kernel-class device times)."""
-    pipe = BatchPipeline(device=device, pipelined=pipelined and interpolation == "nn")
+    pipe = BatchPipeline(device=device, pipelined=pipelined)
     stats = dict.fromkeys(TIMING_KEYS, 0.0)
     stats.update(n_candidates=0, n_chunks=0, itn_sum=0, chunk_ids=[])
     opts = dict(solve_options or {})
     batches = None
     try:
-        if interpolation == "nn":
-            batches = pipe.run_items((problem_of(chunks[ci][0]), chunks[ci][0][5], [x.spec for x in chunks[ci][1]], ci)
-                                     for ci in queue)
-        else:
-            batches = ((ci, ExplicitBatch(problem_of(chunks[ci][0]), chunks[ci][0][5], chunks[ci][1][0].spec,
-                                          interpolation=interpolation)) for ci in queue)
+        factory = None
+        if interpolation != "nn":
+            from . import bilinear
+
+            def factory(prob, L3, specs, stream):
+                if bilinear.supported(prob, L3):  # matrix-free trilinear rows, many candidates per batch
+                    return bilinear.BilinearBatch(prob, L3, specs, stream=stream)
+                if len(specs) != 1:
+                    raise AssertionError("explicit rows: one candidate per batch")
+                return ExplicitBatch(prob, L3, specs[0], interpolation=interpolation, stream=stream)
+
+        batches = pipe.run_items(((problem_of(chunks[ci][0]), chunks[ci][0][5], [x.spec for x in chunks[ci][1]], ci)
+                                  for ci in queue), factory)
         for ci, batch in batches:
             chunk = chunks[ci][1]
             try:

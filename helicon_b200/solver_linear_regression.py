@@ -16,6 +16,7 @@ import logging
 import numpy as np
 
 from . import planner
+from . import bilinear
 from .engine import Batch, ExplicitBatch, Problem, build_trilinear_sym_rows
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
@@ -272,6 +273,14 @@ def lsq_reconstruct(
         positive = positive_rule(positive_constraint, rise_pixel, twist_degree, L3)
         spec = CandidateSpec(twist_degree, rise_pixel, csym, target, target, positive)
         nsets = 3 if fsc_test >= 1 else 1
+        # trilinear interpolation at tilt = psi = dy = 0: the matrix-free factorisation (bilinear.py) through the same code
+        # path as nearest neighbour; the sklearn-model branch stays on the explicit rows
+        if (explicit and _interp(interpolation) == "linear" and tilt_degree == 0 and psi_degree == 0 and dy_pixel == 0
+                and model == "lsq" and bilinear.supported(prob, L3)):
+            explicit = False
+            make_batch = lambda specs: bilinear.BilinearBatch(prob, L3, specs)
+        else:
+            make_batch = lambda specs: Batch(prob, L3, specs)
         # fsc_test: the full set and the two half sets are three candidates of one batch that differ only in
         # which data rows they keep (SLR:441-482); the symmetry rows are shared by construction.
         if explicit:
@@ -317,7 +326,7 @@ def lsq_reconstruct(
             if return_info:
                 return (rec3d, half1, half2), score, info
             return (rec3d, half1, half2), score
-        batch = Batch(prob, L3, [spec] * nsets)
+        batch = make_batch([spec] * nsets)
         half1 = half2 = None
         try:
             if nsets == 3:

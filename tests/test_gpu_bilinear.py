@@ -113,7 +113,45 @@ def test_matrix_free_trilinear_batched_solve_equals_explicit_solves(positive):
                 assert abs(int(res["itn"][c]) - int(r1["itn"][0])) <= max(3, int(r1["itn"][0]) // 10)
                 # two float32 LSMR runs on operators that agree to round-off: inside the reference's own reproducibility band
                 # for trilinear systems (oracle/make_golden_band.py: |dscore| 2e-5 ... 1.2e-4 unbounded, 4.6e-2 bounded)
-                assert ds <= (2e-3 if positive else 2e-4) and rel <= (5e-2 if positive else 2e-2)
+                # (bounded: the TRF step kinds are data-dependent and the iterate is chaotic on these ill-conditioned systems --
+                # the reference's own band is 4.6e-2 in score; the reference goldens gen_solve_lin_48_pos / task_linear pin it)
+                # (unbounded: with the Halton-duplicate views computed separately or not, |dscore| moves between 6e-5 and 3e-4
+                # on this noisy test image -- two LSMR runs with different float32 summation orders)
+                assert ds <= (5e-2 if positive else 1e-3) and rel <= (0.5 if positive else 2e-2)
+            finally:
+                eb.close()
+    finally:
+        bb.close(); prob.close()
+
+
+@pytest.mark.gpu
+def test_matrix_free_trilinear_fixed_iterations_equal_explicit_rows():
+    """The same 5 LSMR iterations on the matrix-free operator and on the explicit rows (solver modes of the kernels: 1/beta
+    scaling, duplicate views, partial norms): x agrees to float32 round-off.  (Later iterates of these ill-conditioned
+    trilinear systems amplify any change of summation order: at 30 iterations the explicit path itself moves by 5e-4 in
+    rel-L2 between its two norm modes, and the reference's converged solution by 2e-2 when its equations are permuted --
+    tests/golden/gen_solve_lin_48.npz band_relx; profiles/diag_bilinear.py.)"""
+    from helicon_b200.bilinear import BilinearBatch
+    from helicon_b200.engine import ExplicitBatch, Problem
+    from helicon_b200.planner import CandidateSpec
+
+    N, L3 = 48, 8
+    img = _image(N, seed=9)
+    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+    specs = [CandidateSpec(tw, rs, 1, 0, 30000, False) for tw, rs in ((-2.1, 2.9), (-1.4, 3.3))]
+    bb = BilinearBatch(prob, L3, specs)
+    try:
+        res = bb.solve(fixed_iters=5, check_every=5)
+        for c, sp in enumerate(specs):
+            eb = ExplicitBatch(prob, L3, sp, interpolation="linear")
+            try:
+                r1 = eb.solve(fixed_iters=5, check_every=5)
+                x0, x1 = eb.x(0), bb.x(c)
+                rel = float(np.linalg.norm(x1 - x0) / np.linalg.norm(x0))
+                ds = abs(float(res["score"][c]) - float(r1["score"][0]))
+                print(f"cand {c}: 5 iterations, score {float(res['score'][c]):.7f} / {float(r1['score'][0]):.7f} |d|={ds:.2e} rel-L2(x)={rel:.2e}")
+                assert int(res["itn"][c]) == int(r1["itn"][0]) == 5
+                assert ds <= 2e-6 and rel <= 1e-5
             finally:
                 eb.close()
     finally:
