@@ -145,7 +145,7 @@ def load():
     lib.hb2_batch_explicit_pixel_mask.argtypes = [vp, vp]
     lib.hb2_batch_explicit_export.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.hb2_batch_set_pixel_masks.argtypes = [vp, i32, vp, vp]
-    lib.hb2_batch_bilinear_maps.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp]
+    lib.hb2_batch_bilinear_maps.argtypes = [vp, i32, vp, i32, vp, vp, i32, vp, vp, vp]
     lib.hb2_batch_bilinear_ray_valid.argtypes = [vp, vp]
     lib.hb2_batch_bilinear_views.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.hb2_batch_bilinear_sym_rows.argtypes = [vp, i32, i32, vp, i64, P(i64)]

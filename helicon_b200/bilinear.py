@@ -99,7 +99,7 @@ class BilinearBatch(Batch):
         reg["zrow"] = -1
         nvalid_reg = np.zeros(nR, dtype=np.int32)
         tie_reg = np.zeros(nR, dtype=np.int32)
-        _lib.check(lib.hb2_batch_bilinear_maps(self._h, nR, _lib.ptr(reg), 0, None, None, 0, _lib.ptr(nvalid_reg), _lib.ptr(tie_reg)))
+        _lib.check(lib.hb2_batch_bilinear_maps(self._h, nR, _lib.ptr(reg), 0, None, None, 0, _lib.ptr(nvalid_reg), _lib.ptr(tie_reg), None))
 
         # ---- column slots per copy; exact maps ------------------------------------------------------------------
         exact_id = {}      # (angle id, k, zshift or None) -> map index
@@ -179,9 +179,16 @@ class BilinearBatch(Batch):
             zrows = np.ascontiguousarray(Zt[ks], dtype=np.float64)
         nvalid = np.zeros(nR + nE, dtype=np.int32)
         tie_all = np.zeros(nR + nE, dtype=np.int32)
+        mhash = np.zeros(nR + nE, dtype=np.uint64)
         _lib.check(lib.hb2_batch_bilinear_maps(self._h, nR + nE, _lib.ptr(maps), ntab, _lib.ptr(xrows) if ntab else None,
-                                               _lib.ptr(zrows) if ntab else None, 1, _lib.ptr(nvalid), _lib.ptr(tie_all)))
+                                               _lib.ptr(zrows) if ntab else None, 1, _lib.ptr(nvalid), _lib.ptr(tie_all),
+                                               _lib.ptr(mhash)))
         self.maps, self.nvalid_maps, self.n_regular_maps = maps, nvalid, nR
+        # exact maps with identical content (same angle by construction of the key below) share one representative
+        canon = {}
+        rep_of = np.arange(nR + nE)
+        for q in range(nR, nR + nE):
+            rep_of[q] = canon.setdefault((exact_rows[q - nR][0], int(mhash[q]), int(nvalid[q])), q)
 
         # ---- views per candidate with the reference's early stop (SLR:1640-1647) ----------------------------------------
         view_map, colk, ab, dup_of = [], [], [], []
@@ -211,15 +218,20 @@ class BilinearBatch(Batch):
                             src.append((nv, mp, k, slot))
                         view_map.append(regular[0][0]); colk.append(t_colk); ab.append(t_ab)
                         nv += 1
+                    groups = {}   # representative exact map -> the copy's columns that use it (one view per group)
                     for (mp, k, slot, a, b, ex) in ent:
-                        if not ex or nvalid[mp] == 0:
-                            continue
+                        if ex and nvalid[mp] > 0:
+                            groups.setdefault(int(rep_of[mp]), []).append((k, slot, a, b))
+                    for mp, cols in groups.items():
                         t_colk = np.full(ZMP, -1, dtype=np.int32)
                         t_ab = np.zeros((ZMP, 2), dtype=np.float64)
-                        t_colk[slot] = k
-                        t_ab[slot] = (a, b)
+                        for (k, slot, a, b) in cols:
+                            if t_colk[slot] >= 0:
+                                raise AssertionError("two columns of one copy in the same slice slot")
+                            t_colk[slot] = k
+                            t_ab[slot] = (a, b)
+                            src.append((nv, mp, k, slot))
                         view_map.append(mp); colk.append(t_colk); ab.append(t_ab)
-                        src.append((nv, mp, k, slot))
                         nv += 1
                     # identical rows of a repeated copy: served by the first occurrence's views (same order, same count)
                     prim = first_views.setdefault(copies_ci[i], nv_copy0)

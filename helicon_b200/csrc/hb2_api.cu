@@ -955,7 +955,7 @@ static cudaError_t upload(DevPool& pool, const T** dst, const std::vector<T>& sr
 // that maps[].xrow / zrow index.
 extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilinear_map* maps, int32_t n_tab_rows,
                                        const double* xrows, const double* zrows, int32_t build_tables,
-                                       int32_t* nvalid_rays, int32_t* tie_samples) {
+                                       int32_t* nvalid_rays, int32_t* tie_samples, uint64_t* content_hash) {
   if (!b || nM <= 0 || !maps || n_tab_rows < 0 || (n_tab_rows > 0 && (!xrows || !zrows))) return fail(HB2_ERR_ARG, "bad argument");
   if (b->created) return fail(HB2_ERR_STATE, "hb2_batch_bilinear_maps must precede hb2_batch_create");
   static_assert(sizeof(BilMap) == sizeof(hb2_bilinear_map), "hb2_bilinear_map layout");
@@ -1031,6 +1031,14 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
   CKM(cudaGetLastError());
   CKM(cudaStreamSynchronize(st));
   if (nent < 0) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "bilinear maps exceed 2^31 entries"); }
+  if (content_hash) {
+    unsigned long long* d_hash;
+    CKM(b->pool.alloc(&d_hash, (size_t)nM, true, st));
+    k_bil_hash<<<dim3(cdiv(std::max<long long>((long long)KB * apitch, D2), 256), nM), 256, 0, st>>>(nM, D2, apitch, KB, d_Tj, d_Tw, d_rv, d_hash);
+    CKM(cudaGetLastError());
+    CKM(cudaMemcpyAsync(content_hash, d_hash, sizeof(unsigned long long) * nM, cudaMemcpyDeviceToHost, st));
+    CKM(cudaStreamSynchronize(st));
+  }
   // forward lists = the transpose, every ray sorted by voxel rank (deterministic summation order)
   float* d_Fw; void* d_Fp;
   CKM(b->pool.alloc(&d_Fw, (size_t)std::max(nent, 1), false, st));

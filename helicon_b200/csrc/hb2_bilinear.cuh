@@ -142,6 +142,25 @@ __global__ void k_bil_T(int nM, int D2, int L3, int ndisk, int apitch, int KB, c
   }
 }
 
+// content hash of every map (transposed entries + ray validity), order-independent: the host merges exact per-column
+// maps that came out identical (the table noise has one sign per side of the image centre) into one multi-column view
+__global__ void k_bil_hash(int nM, int D2, int apitch, int KB, const uint16_t* __restrict__ Tj, const float* __restrict__ Tw,
+                           const uint8_t* __restrict__ rayvalid, unsigned long long* __restrict__ out) {
+  const int m = blockIdx.y;
+  const long long per = (long long)KB * apitch;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long h = 0;
+  if (e < per) {
+    const unsigned j = Tj[(size_t)m * per + e];
+    if (j != 0xFFFFu)
+      h = hash64(((unsigned long long)e << 32) ^ ((unsigned long long)j << 48) ^ (unsigned long long)__float_as_uint(Tw[(size_t)m * per + e]));
+  }
+  if (e < D2 && rayvalid[(size_t)m * D2 + e]) h += hash64(0x9E3779B97F4A7C15ull + (unsigned long long)e);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(&out[m], h);
+}
+
 // forward lists: entry (voxel p, weight) of ray (m, j) at fptr[m*D2 + j] + cursor; sorted by p afterwards
 __global__ void k_bil_F_fill(int nM, int D2, int ndisk, int apitch, int KB, const int* __restrict__ aslot,
                              const uint16_t* __restrict__ Tj, const float* __restrict__ Tw, const int* __restrict__ fptr,
@@ -494,8 +513,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __r
       s_uoff[threadIdx.x] = B.view_uoff[view];
     }
     __syncthreads();
-    if (!on) continue;
-    for (int v = 0; v < nv; ++v) {
+    for (int v = 0; v < nv; ++v) {  // lanes without a voxel stay in the loop (warp votes below) with slot 0 and discard
       const int map = s_map[v];
       if (map < 0) continue;  // block-uniform
       const T* __restrict__ ubv = ub + s_uoff[v] + 4 * q;
@@ -504,18 +522,24 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __r
       unsigned jj[KMAX];
       float ww[KMAX];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
+      for (int k = 0; k < KMAX; ++k) {
+        jj[k] = 0xFFFFu; ww[k] = 0.f;
         if (k < KB) { jj[k] = tj[(size_t)k * kstride]; ww[k] = tw[(size_t)k * kstride]; }
+      }
+      // entries are packed from k = 0: slots no voxel of the warp uses are skipped by a uniform branch
+      bool use[KMAX];
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) use[k] = k < KB && (k < 2 || __any_sync(0xffffffffu, jj[k] != 0xFFFFu));
       T r0[KMAX], r1[KMAX], r2[KMAX], r3[KMAX];
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < KB) {
+        if (use[k]) {
           r0[k] = r1[k] = r2[k] = r3[k] = (T)0;
           if (jj[k] != 0xFFFFu) ld4<T>(ubv + (size_t)jj[k] * ZMP, r0[k], r1[k], r2[k], r3[k]);
         }
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < KB) { const T w = (T)ww[k]; acc0 += w * r0[k]; acc1 += w * r1[k]; acc2 += w * r2[k]; acc3 += w * r3[k]; }
+        if (use[k]) { const T w = (T)ww[k]; acc0 += w * r0[k]; acc1 += w * r1[k]; acc2 += w * r2[k]; acc3 += w * r3[k]; }
     }
   }
   if (!on) return;

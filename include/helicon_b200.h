@@ -227,14 +227,17 @@ int hb2_batch_explicit_sym_export(hb2_batch* b, int32_t* cols, float* weights);
  * slice-range test per sample with zshift = h * rise_pixel (SLR:1578, 1421-1428).
  * build_tables = 0 only reports, per map, the number of rays with data (SLR:1496) and the number of samples within 1e-9
  * of an integer coordinate (the host then replaces such views by single-column views with exact maps); 1 builds the
- * maps the kernels use (call once with all maps).  Call between hb2_batch_begin (one dummy angle) and hb2_batch_create. */
+ * maps the kernels use (call once with all maps) and, if content_hash != NULL, a 64-bit hash of every map's content
+ * (exact maps of neighbouring columns mostly come out identical -- the table noise has one sign per side of the image
+ * centre -- and the host merges such columns into one view).  Call between hb2_batch_begin (one dummy angle) and
+ * hb2_batch_create. */
 typedef struct {
   double m00, m01, m10, m11, m22, zshift;
   int32_t xrow, zrow;
 } hb2_bilinear_map;
 int hb2_batch_bilinear_maps(hb2_batch* b, int32_t n_maps, const hb2_bilinear_map* maps, int32_t n_tab_rows,
                             const double* xrows, const double* zrows, int32_t build_tables, int32_t* nvalid_rays,
-                            int32_t* tie_samples);
+                            int32_t* tie_samples, uint64_t* content_hash);
 /* ray validity of the maps built by hb2_batch_bilinear_maps(build_tables = 1), out[n_maps*D2] */
 int hb2_batch_bilinear_ray_valid(hb2_batch* b, uint8_t* out_host);
 /* Views of the batch, indexed like the views handed to hb2_batch_create (all of them pseudo views: hb2_view.tie = 0,
