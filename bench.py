@@ -454,14 +454,20 @@ def main():
 
     # ---- end-to-end through the public API: host image in, host scores out ----
     e2e_vals, e2e_best = [], None
-    rows_per_call = max(1, batch_size // (len(cfg["rises"]) * len(cfg["csyms"]))) * args.e2e_batches * world
+    per_row = len(cfg["rises"]) * len(cfg["csyms"])
+    rows_per_call = max(1, batch_size // per_row) * args.e2e_batches * world
+    e2e_rises = cfg["rises"]
+    if per_row > batch_size:  # a twist row is larger than a batch (cfg3: 100 rises x 6 csyms): one row, every n-th rise
+        rows_per_call = 1
+        n_r = max(1, (batch_size * args.e2e_batches * world) // len(cfg["csyms"]))
+        e2e_rises = cfg["rises"][np.unique(np.linspace(0, len(cfg["rises"]) - 1, min(n_r, len(cfg["rises"]))).astype(int))]
     order = np.random.default_rng(77).permutation(len(cfg["twists"]))
     launches_e2e = 0
     for s in range(args.e2e_calls + 1):  # the first call is the warm-up
         rows = np.sort(order[(s * rows_per_call + np.arange(rows_per_call)) % len(order)])
         barrier()
         t0 = time.perf_counter()
-        out = search_grid(np.array(img, copy=True), APIX, cfg["twists"][rows], cfg["rises"], csyms=cfg["csyms"],
+        out = search_grid(np.array(img, copy=True), APIX, cfg["twists"][rows], e2e_rises, csyms=cfg["csyms"],
                           positive_constraint=args.positive, device=local_rank, stream=stream, batch_candidates=batch_size,
                           pipelined=not args.no_pipeline, shard=(rank, world), dist=dist)
         best = float(np.nanmax(out["scores"]))  # host read of the call's result (every rank holds the gathered map)

@@ -1059,6 +1059,18 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
     else k_bil_pack<uint32_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint32_t*)d_Fp);
     CKM(cudaGetLastError());
   }
+  {  // ray window of every (map, voxel tile) for the tile adjoint
+    uint16_t *d_jlo, *d_nr; int* d_rmax;
+    CKM(b->pool.alloc(&d_jlo, (size_t)nM * P->ntile, false, st));
+    CKM(b->pool.alloc(&d_nr, (size_t)nM * P->ntile, false, st));
+    CKM(b->pool.alloc(&d_rmax, 1, true, st));
+    k_tile_rays<<<dim3(P->ntile, nM), HB2_BLOCK, 0, st>>>(KB, apitch, P->ntile, d_Tj, d_jlo, d_nr, d_rmax);
+    CKM(cudaGetLastError());
+    int rmax = 0;
+    CKM(cudaMemcpyAsync(&rmax, d_rmax, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKM(cudaStreamSynchronize(st));
+    B.bil_tile_jlo = d_jlo; B.bil_tile_nr = d_nr; B.bil_rmax = std::max(rmax, 1);
+  }
   CKM(cudaStreamSynchronize(st));
   tmp.free_all();
 #undef CKM
@@ -1213,6 +1225,12 @@ static int bil_finish(hb2_batch* b, int nviews) {
   CK(upload(b->pool, &B.bil_ab, b->h_bil_ab, st));
   CK(upload(b->pool, &B.bil_cand_nview, b->h_bil_cand_nview, st));
   CK(b->pool.alloc(&B.bil_ub, (size_t)b->u_total, true, st));
+  {
+    int max_nv = 0;
+    for (int c = 0; c < nc; ++c) max_nv = std::max(max_nv, b->h_bil_cand_nview[c]);
+    static const bool no_tile = getenv("HB2_NO_BIL_TILE") && atoi(getenv("HB2_NO_BIL_TILE"));
+    B.bil_adj_tile = (!no_tile && max_nv <= HB2_BILT_MAXV) ? 1 : 0;
+  }
   k_bil_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
   CKL();
   // transpose lists of the trilinear symmetry rows, candidate by candidate (stable radix sort of the entries by voxel)
@@ -1921,10 +1939,15 @@ static void launch_adj(hb2_batch* b, int mode) {
   if (b->n_tie_views > 0) {  // contribution of the tie views, added by the adjoint kernels below
     if (b->bilinear) {
       const dim3 ga(cdiv(B.ndisk, (HB2_BLOCK / 32) * (32 / (B.L3P / 4))), B.nc);  // (voxel, quad) lanes
+      const size_t smt = (size_t)HB2_BILT_NS * HB2_BILT_SV * ((size_t)B.bil_KB * HB2_BLOCK * 6 + (size_t)B.bil_rmax * B.L3P * sizeof(float));
+      const bool use_tile = B.bil_adj_tile && smt <= 200 * 1024;
 #define ABIL(Q)                                                                                      \
   do {                                                                                               \
     k_bil_unblend<Q, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.bil_ub, mode); \
-    k_adj_bil<Q, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.bil_ub, B.vtie, mode);          \
+    if (use_tile) {                                                                                  \
+      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, float, false>);                              \
+      k_adj_bil_tile<Q, float, false><<<dim3(B.ntile, B.nc), HB2_BILT_THREADS, smt, st>>>(B, TD{}, B.bil_ub, B.vtie, mode); \
+    } else k_adj_bil<Q, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.bil_ub, B.vtie, mode);   \
   } while (0)
       if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);
 #undef ABIL
@@ -2119,10 +2142,15 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
     if (b->n_tie_views > 0) {
       if (b->bilinear) {
         const dim3 ga(cdiv(B.ndisk, (HB2_BLOCK / 32) * (32 / (B.L3P / 4))), nc);
+        const size_t smt = (size_t)HB2_BILT_NS * HB2_BILT_SV * ((size_t)B.bil_KB * HB2_BLOCK * 6 + (size_t)B.bil_rmax * B.L3P * sizeof(double));
+        const bool use_tile = B.bil_adj_tile && smt <= 200 * 1024;
 #define ABIL(Q)                                                                                        \
   do {                                                                                                 \
     k_bil_unblend<Q, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, rows, B.bil_ub64, gate); \
-    k_adj_bil<Q, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, B.bil_ub64, B.vtie64, gate);           \
+    if (use_tile) {                                                                                    \
+      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, double, true>);                                \
+      k_adj_bil_tile<Q, double, true><<<dim3(B.ntile, nc), HB2_BILT_THREADS, smt, st>>>(B, T, B.bil_ub64, B.vtie64, gate); \
+    } else k_adj_bil<Q, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, B.bil_ub64, B.vtie64, gate);    \
   } while (0)
         if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);
 #undef ABIL

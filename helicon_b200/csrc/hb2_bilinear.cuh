@@ -549,6 +549,119 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __r
   dst[2] = z + 2 < B.L3 ? acc2 : (T)0; dst[3] = z + 3 < B.L3 ? acc3 : (T)0;
 }
 
+// Adjoint of the bilinear views, step 2, TILE path (the default when the views of a candidate fit the tables): one CTA =
+// one 16 x 16 voxel tile (<= 256 voxels, one consumer thread each, all slices in registers), a producer warp streams, per
+// stage of HB2_BILT_SV views, the tile's runs of the transposed maps (KB x 512 bytes of rays + KB x 1 KB of weights) and
+// the contiguous window of un-blended rows the tile's voxels touch in that view ([jlo, jlo + nr) x L3P) into a ring of
+// shared-memory stages by cp.async.bulk (TMA, full / empty mbarriers) -- the same structure as k_adj_tile, with weights.
+// The inner loop reads shared memory only.  Addition order: views, then k (= k_adj_bil).
+#define HB2_BILT_SV 2
+#define HB2_BILT_NS 4
+#define HB2_BILT_THREADS (HB2_BLOCK + 32)
+#define HB2_BILT_MAXV 512
+template <int NQT, typename T, bool TRF>
+__global__ void __launch_bounds__(HB2_BILT_THREADS) k_adj_bil_tile(BD B, TD Tt, const T* __restrict__ ub, T* __restrict__ vt, int mode) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int c = blockIdx.y, tile = blockIdx.x;
+  if (B.cand_tie_count[c] == 0) return;
+  if (!tie_active<TRF>(B, Tt, c, mode, true)) return;
+  __shared__ unsigned long long full_bar[HB2_BILT_NS], empty_bar[HB2_BILT_NS];
+  __shared__ int s_map[HB2_BILT_MAXV];
+  __shared__ uint16_t s_jlo[HB2_BILT_MAXV], s_nr[HB2_BILT_MAXV];
+  constexpr int L3P = 4 * NQT;
+  const int KB = B.bil_KB;
+  const int ndisk_t = B.tile_begin[tile + 1] - B.tile_begin[tile];
+  const int p = B.tile_begin[tile] + threadIdx.x;
+  const bool producer = threadIdx.x >= HB2_BLOCK;
+  const bool live = threadIdx.x < ndisk_t;
+  const int vb = B.cand_view_begin[c], nv = B.bil_cand_nview[c];
+  const int rmax = B.bil_rmax;
+  const bool dedupe = !TRF && mode != MODE_PLAIN;
+  // dynamic shared memory per (stage, view slot): [KB][256] rays (uint16), [KB][256] weights (float), [rmax*L3P] rows
+  const size_t slot_bytes = (size_t)KB * HB2_BLOCK * (sizeof(uint16_t) + sizeof(float)) + (size_t)rmax * L3P * sizeof(T);
+  for (int e = threadIdx.x; e < nv; e += HB2_BILT_THREADS) {
+    const int view = vb + e;
+    const int map = B.bil_view_map[view];
+    const bool skip = dedupe && B.view_dupof[view] >= 0;
+    s_map[e] = map;
+    s_jlo[e] = skip ? (uint16_t)0xFFFFu : B.bil_tile_jlo[(size_t)map * B.ntile + tile];
+    s_nr[e] = skip ? (uint16_t)0 : B.bil_tile_nr[(size_t)map * B.ntile + tile];
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < HB2_BILT_NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], HB2_BLOCK / 32); }
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  const int nstage = (nv + HB2_BILT_SV - 1) / HB2_BILT_SV;
+  T acc[L3P];
+#pragma unroll
+  for (int i = 0; i < L3P; ++i) acc[i] = (T)0;
+  if (producer) {
+    const int w = threadIdx.x - HB2_BLOCK;
+    for (int st = 0; st < nstage; ++st) {
+      const int buf = st % HB2_BILT_NS;
+      if (st >= HB2_BILT_NS) mbar_wait(&empty_bar[buf], (unsigned)(((st / HB2_BILT_NS) - 1) & 1));
+      const int v = st * HB2_BILT_SV + w;
+      const bool has = w < HB2_BILT_SV && v < nv && s_nr[min(v, nv - 1)] != 0;
+      const unsigned nr = has ? s_nr[v] : 0;
+      unsigned tot = has ? (unsigned)KB * HB2_BLOCK * (unsigned)(sizeof(uint16_t) + sizeof(float)) + nr * L3P * (unsigned)sizeof(T) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (w == 0) mbar_expect_tx(&full_bar[buf], tot);
+      __syncwarp();
+      if (has) {
+        unsigned char* sb = dsm + (size_t)(buf * HB2_BILT_SV + w) * slot_bytes;
+        const size_t mrow = (size_t)s_map[v] * KB * B.apitch + (size_t)tile * HB2_BLOCK;
+        for (int k = 0; k < KB; ++k) {
+          bulk_g2s(sb + (size_t)k * HB2_BLOCK * sizeof(uint16_t), B.bilT_j + mrow + (size_t)k * B.apitch,
+                   HB2_BLOCK * (unsigned)sizeof(uint16_t), &full_bar[buf]);
+          bulk_g2s(sb + (size_t)KB * HB2_BLOCK * sizeof(uint16_t) + (size_t)k * HB2_BLOCK * sizeof(float),
+                   B.bilT_w + mrow + (size_t)k * B.apitch, HB2_BLOCK * (unsigned)sizeof(float), &full_bar[buf]);
+        }
+        bulk_g2s(sb + (size_t)KB * HB2_BLOCK * (sizeof(uint16_t) + sizeof(float)),
+                 ub + B.view_uoff[vb + v] + (size_t)s_jlo[v] * L3P, nr * L3P * (unsigned)sizeof(T), &full_bar[buf]);
+      }
+    }
+  } else {
+    for (int st = 0; st < nstage; ++st) {
+      const int buf = st % HB2_BILT_NS;
+      mbar_wait(&full_bar[buf], (unsigned)((st / HB2_BILT_NS) & 1));
+      if (live) {
+        const int nvs = min(HB2_BILT_SV, nv - st * HB2_BILT_SV);
+#pragma unroll
+        for (int w = 0; w < HB2_BILT_SV; ++w) {
+          if (w >= nvs || s_nr[st * HB2_BILT_SV + w] == 0) continue;
+          const int jl = (int)s_jlo[st * HB2_BILT_SV + w];
+          const unsigned char* sb = dsm + (size_t)(buf * HB2_BILT_SV + w) * slot_bytes;
+          const uint16_t* mp = reinterpret_cast<const uint16_t*>(sb) + threadIdx.x;
+          const float* wp = reinterpret_cast<const float*>(sb + (size_t)KB * HB2_BLOCK * sizeof(uint16_t)) + threadIdx.x;
+          const T* uw = reinterpret_cast<const T*>(sb + (size_t)KB * HB2_BLOCK * (sizeof(uint16_t) + sizeof(float)));
+          for (int k = 0; k < KB; ++k) {
+            const unsigned j = mp[(size_t)k * HB2_BLOCK];
+            if (j == 0xFFFFu) break;  // entries are packed from k = 0
+            const T wk = (T)wp[(size_t)k * HB2_BLOCK];
+            const T* r = uw + ((int)j - jl) * L3P;
+#pragma unroll
+            for (int z4 = 0; z4 < L3P; z4 += 4) {
+              T x0, x1, x2, x3;
+              ld4<T>(r + z4, x0, x1, x2, x3);
+              acc[z4] += wk * x0; acc[z4 + 1] += wk * x1; acc[z4 + 2] += wk * x2; acc[z4 + 3] += wk * x3;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&empty_bar[buf]);
+    }
+  }
+  if (live && !producer) {
+    T* dst = vt + (size_t)c * B.npad + (size_t)p * L3P;
+#pragma unroll
+    for (int z = 0; z < L3P; ++z) dst[z] = z < B.L3 ? acc[z] : (T)0;
+  }
+}
+
 // Adjoint of the trilinear symmetry rows, ADDED to vt (run after k_adj_bil): one thread per voxel entry g = p*L3P + z
 // walking its transpose list (~6 entries, sorted by row: deterministic).
 template <typename T, bool TRF>

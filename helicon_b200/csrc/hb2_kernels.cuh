@@ -135,6 +135,10 @@ struct BD {
   const int* bil_colk;          // [nviews][ZMP] image column of slot t or -1
   const double* bil_ab;         // [nviews][ZMP][2] blend of slot t: a P[t-1] + b P[t] (t = 0: a P[0] + b P[1])
   const int* bil_cand_nview;    // [nc] bilinear views of the candidate (first in its view range)
+  const uint16_t* bil_tile_jlo; // [nM][ntile] first ray of the map that touches the voxel tile (tile adjoint)
+  const uint16_t* bil_tile_nr;  // [nM][ntile] number of consecutive rays touching it
+  int bil_rmax;                 // max of bil_tile_nr
+  int bil_adj_tile;             // 1: k_adj_bil_tile (else the gather kernel k_adj_bil)
   float* bil_ub;                // rows layout of u: the un-blended (slice-space) rows the adjoint gathers (k_bil_unblend)
   double* bil_ub64;             // same for the float64 operators of the bounded branch
   const int2* ls_ent;           // trilinear symmetry rows: 16 (internal voxel index, float weight bits) entries per row
