@@ -246,8 +246,6 @@ struct hb2_batch {
   std::vector<uint8_t> h_bil_rv;                 // [nM][D2]
   std::vector<int> h_bil_view_map, h_bil_colk, h_bil_cand_nview;
   std::vector<double> h_bil_ab;
-  std::vector<int> h_bil_rows_of_map;            // band forward: partial rows of a view of every map
-  size_t bil_band_smem = 0;
   std::vector<int2*> ls_ent_c;                   // per candidate: trilinear symmetry rows, 16 entries each
   std::vector<int> ls_m_c;
   struct LsScratch {
@@ -1060,53 +1058,6 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
     if (b->idx16) k_bil_pack<uint16_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint16_t*)d_Fp);
     else k_bil_pack<uint32_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint32_t*)d_Fp);
     CKM(cudaGetLastError());
-    // band forward: bands of the voxel order that fit ~200 KB of shared memory (as build_band_tab), the piece of every
-    // ray's sorted footprint list inside every band, compact partial rows
-    B.bil_band = BilBand{};
-    static const bool no_band = getenv("HB2_NO_BIL_BAND") && atoi(getenv("HB2_NO_BIL_BAND"));
-    const long long cap = (long long)(200 * 1024) / (B.L3P * 4ll), cap16 = cap / 16 * 16;
-    if (!no_band && cap16 >= 16) {
-      std::vector<int> bands{0};
-      const std::vector<int>& tr = P->h_tilerow_begin;
-      for (size_t r = 0; r + 1 < tr.size(); ++r) {
-        const int lo = tr[r], hi = tr[r + 1];
-        if (hi - bands.back() <= cap) continue;
-        if (lo > bands.back()) bands.push_back(lo);
-        while (hi - bands.back() > cap) bands.push_back(bands.back() + (int)cap16);
-      }
-      bands.push_back(B.ndisk);
-      const int NB = (int)bands.size() - 1;
-      if (NB <= HB2_MAX_BANDS && (long long)nM * NB * D2 < (1ll << 31)) {
-        int max_bn = 0;
-        for (int q = 0; q < NB; ++q) max_bn = std::max(max_bn, bands[q + 1] - bands[q]);
-        const int* d_bands = nullptr;
-        CKM(upload(b->pool, &d_bands, bands, st));
-        int2* d_seg; ushort2* d_rng;
-        CKM(b->pool.alloc(&d_seg, (size_t)nM * NB * D2, false, st));
-        CKM(b->pool.alloc(&d_rng, (size_t)nM * NB, false, st));
-        k_bil_segs<<<cdiv((long long)nM * NB * D2, 256), 256, 0, st>>>(nM, NB, D2, d_bands, d_fptr, d_key2, d_seg);
-        k_bil_rng<<<dim3(NB, nM), HB2_BLOCK, 0, st>>>(NB, D2, d_seg, d_rng);
-        CKM(cudaGetLastError());
-        std::vector<ushort2> h_rng((size_t)nM * NB);
-        CKM(cudaMemcpyAsync(h_rng.data(), d_rng, sizeof(ushort2) * h_rng.size(), cudaMemcpyDeviceToHost, st));
-        CKM(cudaStreamSynchronize(st));
-        std::vector<int> band_off((size_t)nM * NB);
-        b->h_bil_rows_of_map.assign(nM, 0);
-        for (int m = 0; m < nM; ++m) {
-          int acc = 0;
-          for (int q = 0; q < NB; ++q) {
-            band_off[(size_t)m * NB + q] = acc;
-            acc += (int)h_rng[(size_t)m * NB + q].y - (int)h_rng[(size_t)m * NB + q].x;
-          }
-          b->h_bil_rows_of_map[m] = acc;
-        }
-        const int* d_boff = nullptr;
-        CKM(upload(b->pool, &d_boff, band_off, st));
-        B.bil_band.nband = NB; B.bil_band.band_begin = d_bands; B.bil_band.seg = d_seg; B.bil_band.rng = d_rng;
-        B.bil_band.band_off = d_boff;
-        b->bil_band_smem = (size_t)max_bn * B.L3P * 4;
-      }
-    }
   }
   {  // ray window of every (map, voxel tile) for the tile adjoint
     uint16_t *d_jlo, *d_nr; int* d_rmax;
@@ -1274,26 +1225,10 @@ static int bil_finish(hb2_batch* b, int nviews) {
   CK(upload(b->pool, &B.bil_ab, b->h_bil_ab, st));
   CK(upload(b->pool, &B.bil_cand_nview, b->h_bil_cand_nview, st));
   CK(b->pool.alloc(&B.bil_ub, (size_t)b->u_total, true, st));
-  if (B.bil_band.nband > 0) {  // band forward: first partial row of every view, partial buffer
-    int max_nv = 0;
-    for (int c = 0; c < nc; ++c) max_nv = std::max(max_nv, b->h_bil_cand_nview[c]);
-    if (max_nv > HB2_BILT_MAXV) B.bil_band.nband = 0;
-    else {
-      std::vector<long long> view_poff(nviews, 0);
-      long long total = 0;
-      for (int v = 0; v < nviews; ++v) {
-        view_poff[v] = total;
-        if (b->h_bil_view_map[v] >= 0) total += b->h_bil_rows_of_map[b->h_bil_view_map[v]];
-      }
-      CK(upload(b->pool, &B.bil_band.view_poff, view_poff, st));
-      CK(b->pool.alloc(&B.bil_band.part, (size_t)std::max<long long>(total, 1) * B.L3P, false, st));
-    }
-    b->max_views = max_nv;
-  }
   {
     int max_nv = 0;
     for (int c = 0; c < nc; ++c) max_nv = std::max(max_nv, b->h_bil_cand_nview[c]);
-    static const bool no_tile = getenv("HB2_NO_BIL_TILE") && atoi(getenv("HB2_NO_BIL_TILE"));
+    const bool no_tile = getenv("HB2_NO_BIL_TILE") && atoi(getenv("HB2_NO_BIL_TILE"));  // tests compare the tile adjoint with the gather kernel
     B.bil_adj_tile = (!no_tile && max_nv <= HB2_BILT_MAXV) ? 1 : 0;
   }
   k_bil_rhs<<<cdiv((long long)nviews * B.rows_per_view, 256), 256, 0, st>>>(B, P->d_pix, nviews, b->d_bmax);
@@ -1952,26 +1887,11 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
     const float* src = mode == MODE_LSMR ? B.v : B.xs;
     if (b->bilinear) {
       const dim3 gv(b->n_tie_views, B.fwd_ppv);
-      if (B.bil_band.nband > 0) {  // voxel bands staged in shared memory by TMA + row epilogue
-        const dim3 gb(B.bil_band.nband, B.nc), gr(b->max_views, B.nc);
-#define FBB(I, Q)                                                                                   \
-  do {                                                                                               \
-    hb2_allow_big_smem((const void*)k_fwd_bil_band<I, Q>);                                           \
-    k_fwd_bil_band<I, Q><<<gb, HB2_FWDB_THREADS, b->bil_band_smem, st>>>(B, mode);                   \
-    k_fwd_bil_reduce<Q><<<gr, HB2_BLOCK, 0, st>>>(B, mode);                                          \
-  } while (0)
-#define FBBQ(I) do { if (B.L3P == 4) FBB(I, 1); else if (B.L3P == 8) FBB(I, 2); else if (B.L3P == 12) FBB(I, 3); else FBB(I, 4); } while (0)
-        if (b->idx16) FBBQ(uint16_t); else FBBQ(uint32_t);
-#undef FBBQ
-#undef FBB
-        b->extra_launches += 1;
-      } else {
 #define FBIL(I, Q) k_fwd_bil<I, Q, float, false><<<gv, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode)
 #define FBILQ(I) do { if (B.L3P == 4) FBIL(I, 1); else if (B.L3P == 8) FBIL(I, 2); else if (B.L3P == 12) FBIL(I, 3); else FBIL(I, 4); } while (0)
-        if (b->idx16) FBILQ(uint16_t); else FBILQ(uint32_t);
+      if (b->idx16) FBILQ(uint16_t); else FBILQ(uint32_t);
 #undef FBILQ
 #undef FBIL
-      }
       k_fwd_lsym<float, false><<<gv, HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);
       b->extra_launches += 1;
     } else if (b->explicit_rows) k_fwd_csr<float, false><<<dim3(b->n_tie_views, B.fwd_ppv), HB2_BLOCK, 0, st>>>(B, TD{}, src, B.u, mode);

@@ -28,13 +28,6 @@
 // A^T u (BD::vtie / vtie64), which the adjoint kernels add -- LSMR / TRF state machines, norms and score are unchanged.
 #pragma once
 #include "hb2_explicit.cuh"
-#include "hb2_fwd_band.cuh"
-
-// tile adjoint (k_adj_bil_tile): views per stage, stages in flight; MAXV = bilinear views per candidate the shared tables hold
-#define HB2_BILT_SV 2
-#define HB2_BILT_NS 4
-#define HB2_BILT_THREADS (HB2_BLOCK + 32)
-#define HB2_BILT_MAXV 512
 
 struct BilMap {  // == hb2_bilinear_map (include/helicon_b200.h)
   double m00, m01, m10, m11, m22, zshift;
@@ -391,271 +384,6 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   }
 }
 
-// ---------------------------------------------------------------------------
-// Band forward of the bilinear views (float32 operator; the default when the tables fit): the footprint lists are sorted
-// by voxel rank and a band is a contiguous run of ranks, so the entries of ray j inside a band are ONE contiguous piece of
-// its list (BilBand::seg, built by binary search).  CTA = (candidate, band): the band of v is staged in shared memory by
-// TMA bulk copies (<= 200 KB), then ALL bilinear views of the candidate are applied to it; a warp item = RPW adjacent rays
-// of one view, lane = (ray, slice quad) walking its own piece of the list: adjacent rays sit on adjacent voxel rows, i.e.
-// on different 16-byte bank groups of the band-column-major layout (conflict-free 128-bit shared loads at view angles
-// below 45 degrees, like k_fwd_band).  Partial slice sums go to a compact buffer; k_fwd_bil_reduce adds them in band
-// order, blends the slices into the column slots and applies the LSMR / plain / score epilogue of k_fwd_bil.
-// ---------------------------------------------------------------------------
-__global__ void k_bil_segs(int nM, int nband, int D2, const int* __restrict__ band_begin, const int* __restrict__ fptr,
-                           const unsigned* __restrict__ key, int2* __restrict__ seg) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)nM * nband * D2) return;
-  const int j = (int)(t % D2), b = (int)((t / D2) % nband), m = (int)(t / ((long long)D2 * nband));
-  const int e0 = fptr[(size_t)m * D2 + j], e1 = fptr[(size_t)m * D2 + j + 1];
-  const unsigned lo_r = (unsigned)band_begin[b], hi_r = (unsigned)band_begin[b + 1];
-  int lo = e0, hi = e1;  // first entry with rank >= lo_r
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (key[mid] < lo_r) lo = mid + 1; else hi = mid; }
-  int lo2 = lo, hi2 = e1;  // first entry with rank >= hi_r
-  while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (key[mid] < hi_r) lo2 = mid + 1; else hi2 = mid; }
-  seg[t] = make_int2(lo, lo2 - lo);
-}
-__global__ void __launch_bounds__(HB2_BLOCK) k_bil_rng(int nband, int D2, const int2* __restrict__ seg, ushort2* __restrict__ rng) {
-  const int b = blockIdx.x, m = blockIdx.y;
-  __shared__ int s_lo, s_hi;
-  if (threadIdx.x == 0) { s_lo = 0x7fffffff; s_hi = -1; }
-  __syncthreads();
-  const int2* sg = seg + ((size_t)m * nband + b) * D2;
-  for (int j = threadIdx.x; j < D2; j += HB2_BLOCK)
-    if (sg[j].y > 0) { atomicMin(&s_lo, j); atomicMax(&s_hi, j + 1); }
-  __syncthreads();
-  if (threadIdx.x == 0) rng[(size_t)m * nband + b] = s_hi > s_lo ? make_ushort2((unsigned short)s_lo, (unsigned short)s_hi) : make_ushort2(0, 0);
-}
-
-template <typename IdxT, int Q>
-__global__ void __launch_bounds__(HB2_FWDB_THREADS, 1) k_fwd_bil_band(BD B, int mode) {
-  extern __shared__ __align__(128) unsigned char dsm[];
-  __shared__ unsigned long long bar;
-  __shared__ int s_pref[HB2_BILT_MAXV + 1];
-  __shared__ unsigned short s_jlo[HB2_BILT_MAXV], s_cnt[HB2_BILT_MAXV];
-  __shared__ int s_map[HB2_BILT_MAXV];
-  __shared__ int s_next;
-  const BilBand& Bt = B.bil_band;
-  const int c = blockIdx.y, b = blockIdx.x;
-  if (B.cand_tie_count[c] == 0) return;
-  if (!tie_active<false>(B, TD{}, c, mode, false)) return;
-  constexpr int L3P = 4 * Q, RPW = 32 / Q;
-  constexpr unsigned REC = L3P * 4u;
-  const int D2 = B.D2, NB = Bt.nband;
-  const unsigned bb = (unsigned)Bt.band_begin[b], bn = (unsigned)Bt.band_begin[b + 1] - bb;
-  const int vb = B.cand_view_begin[c], nv = B.bil_cand_nview[c];
-  const float* src = mode == MODE_LSMR ? B.v : B.xs;
-  const unsigned char* __restrict__ vsrc = reinterpret_cast<const unsigned char*>(src + (size_t)c * B.npad + (size_t)bb * L3P);
-  if (threadIdx.x == 0) { mbar_init(&bar, 1); s_next = HB2_FWDB_THREADS / 32; }
-  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  for (int e = threadIdx.x; e < nv; e += HB2_FWDB_THREADS) {
-    const int view = vb + e;
-    const int map = B.bil_view_map[view];
-    ushort2 r = Bt.rng[(size_t)map * NB + b];
-    if (B.view_dupof[view] >= 0) r = make_ushort2(0, 0);  // duplicate of an earlier view: served by that view (the epilogue copies the rows)
-    s_map[e] = map; s_jlo[e] = r.x; s_cnt[e] = (unsigned short)(r.y - r.x); s_pref[e + 1] = ((int)r.y - (int)r.x + RPW - 1) / RPW;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {  // warp 0: TMA bulk load of the band (32 KB pieces), then the prefix over views
-    const unsigned total = bn * REC;
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, total);
-    __syncwarp();
-    const unsigned piece = 32768u;
-    for (unsigned off = threadIdx.x * piece; off < total; off += 32u * piece)
-      bulk_g2s(dsm + off, vsrc + off, min(piece, total - off), &bar);
-    if (threadIdx.x == 0) {
-      s_pref[0] = 0;
-      for (int e = 0; e < nv; ++e) s_pref[e + 1] += s_pref[e];
-    }
-  }
-  __syncthreads();
-  const int total_items = s_pref[nv];
-  mbar_wait(&bar, 0u);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rl = lane / Q, q = lane - rl * Q;
-  const bool lane_on = rl < RPW;
-  const unsigned tile_s = smem_u32(dsm) + 16u * (unsigned)q;
-  const IdxT* __restrict__ Fp = (const IdxT*)B.bilF_p;
-  const float* __restrict__ Fw = B.bilF_w;
-  int vcur = 0;
-  for (int it = warp; it < total_items;) {  // items are handed out through a shared counter (their lengths differ)
-    while (it >= s_pref[vcur + 1]) ++vcur;
-    const int map = s_map[vcur];
-    const int jlo = (int)s_jlo[vcur];
-    const int j = jlo + RPW * (it - s_pref[vcur]) + rl;
-    const bool ray_on = lane_on && j < jlo + (int)s_cnt[vcur];
-    int2 sg = make_int2(0, 0);
-    if (ray_on) sg = __ldg(Bt.seg + ((size_t)map * NB + b) * D2 + j);
-    const int nmax = __reduce_max_sync(0xffffffffu, sg.y);
-    const IdxT* __restrict__ fp = Fp + sg.x;
-    const float* __restrict__ fw = Fw + sg.x;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < nmax; s0 += 4) {
-      unsigned rel[4];
-      float w[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ok[u] = s0 + u < sg.y;
-        rel[u] = ok[u] ? (unsigned)fp[s0 + u] - bb : 0u;
-        w[u] = ok[u] ? fw[s0 + u] : 0.f;
-        ok[u] = ok[u] && rel[u] < bn;
-      }
-      float4 x[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) x[u] = ok[u] ? lds128(tile_s + rel[u] * REC) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { acc.x += w[u] * x[u].x; acc.y += w[u] * x[u].y; acc.z += w[u] * x[u].z; acc.w += w[u] * x[u].w; }
-    }
-    if (ray_on) {
-      const long long prow = Bt.view_poff[vb + vcur] + Bt.band_off[(size_t)map * NB + b] + (j - jlo);
-      *reinterpret_cast<float4*>(Bt.part + (size_t)prow * L3P + 4 * q) = acc;
-    }
-    int nx = 0;
-    if (lane == 0) nx = atomicAdd(&s_next, 1);
-    it = __shfl_sync(0xffffffffu, nx, 0);
-  }
-}
-
-// Row epilogue of the band forward: one CTA per (bilinear view, candidate), one thread per ray: the ray's partial slice
-// sums added over the bands it crosses (band order, 4 loads in flight), blended into the column slots, then the epilogue
-// of k_fwd_bil (LSMR row update / plain store / score accumulation, duplicates, half-set masks, partial norms).
-template <int Q>
-__global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil_reduce(BD B, int mode) {
-  const BilBand& Bt = B.bil_band;
-  const int c = blockIdx.y, vi = blockIdx.x;
-  if (vi >= B.bil_cand_nview[c]) return;
-  __shared__ float red[HB2_BLOCK / 32];
-  __shared__ ushort2 s_rng[HB2_MAX_BANDS];
-  __shared__ int s_off[HB2_MAX_BANDS];
-  __shared__ int s_colk[16];
-  __shared__ float s_a[16], s_b[16];
-  const int view = B.cand_view_begin[c] + vi;
-  if (B.view_dupof[view] >= 0) return;
-  const int map = B.bil_view_map[view];
-  const int ppv = B.fwd_ppv;
-  int dupv[HB2_MAXDUP];
-#pragma unroll
-  for (int d = 0; d < HB2_MAXDUP; ++d) dupv[d] = B.view_dups[view * HB2_MAXDUP + d];
-  const bool act = tie_active<false>(B, TD{}, c, mode, false);
-  if (threadIdx.x < ppv) {  // the view's partial-sum slots other than slot 0 stay 0 on this path
-#pragma unroll
-    for (int d = -1; d < HB2_MAXDUP; ++d) {
-      const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
-      if (vw < 0) continue;
-      if (threadIdx.x > 0 || !act) {
-        if (mode == MODE_LSMR) B.part_u[vw * ppv + threadIdx.x] = 0.f;
-        if (mode == MODE_SCORE) { B.part_s[3 * (vw * ppv + threadIdx.x)] = 0.f; B.part_s[3 * (vw * ppv + threadIdx.x) + 1] = 0.f; B.part_s[3 * (vw * ppv + threadIdx.x) + 2] = 0.f; }
-      }
-    }
-  }
-  if (!act) return;
-  constexpr int L3P = 4 * Q;
-  const int D2 = B.D2, NB = Bt.nband, ZMP = B.ZMP;
-  for (int e = threadIdx.x; e < NB; e += HB2_BLOCK) { s_rng[e] = Bt.rng[(size_t)map * NB + e]; s_off[e] = Bt.band_off[(size_t)map * NB + e]; }
-  if (threadIdx.x < 16) {
-    const bool in = (int)threadIdx.x < ZMP;
-    s_colk[threadIdx.x] = in ? B.bil_colk[(size_t)view * ZMP + threadIdx.x] : -1;
-    s_a[threadIdx.x] = in ? (float)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2] : 0.f;
-    s_b[threadIdx.x] = in ? (float)B.bil_ab[((size_t)view * ZMP + threadIdx.x) * 2 + 1] : 0.f;
-  }
-  __syncthreads();
-  const float alpha = B.st[c].alpha, inv_beta = B.st[c].inv_beta;
-  const float* __restrict__ part = Bt.part + (size_t)Bt.view_poff[view] * L3P;
-  float* urow = B.u + B.view_uoff[view];
-  const float* brow = B.b + B.view_uoff[view];
-  const uint8_t* __restrict__ pm = cand_mask(B, c);
-  const uint8_t* __restrict__ rv = B.bil_rayvalid + (size_t)map * D2;
-  float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
-  for (int j = threadIdx.x; j < D2; j += HB2_BLOCK) {
-    if (!rv[j]) continue;
-    float P[L3P + 1];
-#pragma unroll
-    for (int z = 0; z <= L3P; ++z) P[z] = 0.f;
-    for (int b0 = 0; b0 < NB; b0 += 4) {
-      float4 t[4][Q];
-      bool on[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        on[w] = false;
-        ushort2 r = make_ushort2(0, 0);
-        if (b0 + w < NB) { r = s_rng[b0 + w]; on[w] = j >= (int)r.x && j < (int)r.y; }
-        if (on[w]) {
-          const float4* pp = reinterpret_cast<const float4*>(part + ((size_t)s_off[b0 + w] + (j - (int)r.x)) * L3P);
-#pragma unroll
-          for (int qq = 0; qq < Q; ++qq) t[w][qq] = __ldcs(pp + qq);
-        }
-      }
-#pragma unroll
-      for (int w = 0; w < 4; ++w)
-        if (on[w]) {
-#pragma unroll
-          for (int qq = 0; qq < Q; ++qq) { P[4 * qq] += t[w][qq].x; P[4 * qq + 1] += t[w][qq].y; P[4 * qq + 2] += t[w][qq].z; P[4 * qq + 3] += t[w][qq].w; }
-        }
-    }
-#pragma unroll
-    for (int qq = 0; qq < Q; ++qq) {
-      const size_t r0 = (size_t)j * ZMP + 4 * qq;
-      float val[4];
-      bool keep[4];
-#pragma unroll
-      for (int tz = 0; tz < 4; ++tz) {
-        const int t = 4 * qq + tz;
-        const int k = s_colk[t];
-        keep[tz] = k >= 0 && !(pm && !pm[(size_t)k * D2 + j]);
-        val[tz] = t == 0 ? s_a[0] * P[0] + s_b[0] * P[1] : s_a[t] * P[t - 1] + s_b[t] * P[t];
-      }
-      if (!(keep[0] || keep[1] || keep[2] || keep[3])) continue;
-      if (mode == MODE_LSMR || mode == MODE_PLAIN) {
-        const float4 uo = *reinterpret_cast<const float4*>(urow + r0);
-        float un[4] = {uo.x, uo.y, uo.z, uo.w};
-#pragma unroll
-        for (int tz = 0; tz < 4; ++tz) {
-          if (!keep[tz]) continue;
-          if (mode == MODE_LSMR) {
-            un[tz] = fadd_(fmul_(fmul_(un[tz], inv_beta), -alpha), val[tz]);
-            ss += un[tz] * un[tz];
-          } else {
-            un[tz] = val[tz];
-          }
-        }
-        const float4 uw = make_float4(un[0], un[1], un[2], un[3]);
-        *reinterpret_cast<float4*>(urow + r0) = uw;
-#pragma unroll
-        for (int d = 0; d < HB2_MAXDUP; ++d)
-          if (dupv[d] >= 0) *reinterpret_cast<float4*>(B.u + B.view_uoff[dupv[d]] + r0) = uw;  // identical rows of the duplicate
-      } else {
-        const float4 bv4 = *reinterpret_cast<const float4*>(brow + r0);
-        const float bv[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
-#pragma unroll
-        for (int tz = 0; tz < 4; ++tz) {
-          if (!keep[tz]) continue;
-          const float pred = B.clip_pred ? fmaxf(val[tz], 0.f) : val[tz];
-          ss += pred * pred; s_pb += pred * bv[tz]; s_bb += bv[tz] * bv[tz];
-        }
-      }
-    }
-  }
-  if (mode == MODE_LSMR) {
-    const float tot = block_sum(ss, red);
-    if (threadIdx.x == 0) {
-      B.part_u[view * ppv] = tot;
-#pragma unroll
-      for (int d = 0; d < HB2_MAXDUP; ++d)
-        if (dupv[d] >= 0) B.part_u[dupv[d] * ppv] = tot;
-    }
-  } else if (mode == MODE_SCORE) {
-    const float t0 = block_sum(s_pb, red), t1 = block_sum(ss, red), t2 = block_sum(s_bb, red);
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int d = -1; d < HB2_MAXDUP; ++d) {
-        const int vw = d < 0 ? view : dupv[d < 0 ? 0 : d];
-        if (vw < 0) continue;
-        B.part_s[3 * (vw * ppv)] = t0; B.part_s[3 * (vw * ppv) + 1] = t1; B.part_s[3 * (vw * ppv) + 2] = t2;
-      }
-    }
-  }
-}
-
 // Forward of the trilinear symmetry rows: one thread per row (16 entries, 128-bit loads of columns and weights).
 // The rows of candidate c occupy its pseudo views after the bilinear ones; never scored.
 template <typename T, bool TRF>
@@ -827,6 +555,10 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __r
 // the contiguous window of un-blended rows the tile's voxels touch in that view ([jlo, jlo + nr) x L3P) into a ring of
 // shared-memory stages by cp.async.bulk (TMA, full / empty mbarriers) -- the same structure as k_adj_tile, with weights.
 // The inner loop reads shared memory only.  Addition order: views, then k (= k_adj_bil).
+#define HB2_BILT_SV 2
+#define HB2_BILT_NS 4
+#define HB2_BILT_THREADS (HB2_BLOCK + 32)
+#define HB2_BILT_MAXV 512
 template <int NQT, typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BILT_THREADS) k_adj_bil_tile(BD B, TD Tt, const T* __restrict__ ub, T* __restrict__ vt, int mode) {
   extern __shared__ __align__(128) unsigned char dsm[];

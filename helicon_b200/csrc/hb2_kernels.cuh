@@ -25,17 +25,6 @@ struct BandTab {
   void* part;                  // partial ray sums: [partial row][L3P] of the element type
 };
 
-// Tables of the band forward of the matrix-free trilinear rows (hb2_bilinear.cuh: k_fwd_bil_band)
-struct BilBand {
-  int nband;                   // 0: not available (gather kernel k_fwd_bil)
-  const int* band_begin;       // [nband+1] first internal rank of every band
-  const int2* seg;             // [nM][nband][D2] (first entry, count) of ray j's footprint list inside the band
-  const ushort2* rng;          // [nM][nband] rays [jlo, jhi) with entries in the band
-  const int* band_off;         // [nM][nband] partial-row offset of the band inside a view of that map
-  const long long* view_poff;  // [nviews] first partial row of the view
-  float* part;                 // partial slice sums: [partial row][L3P]
-};
-
 // Batch descriptor passed by value to every kernel.
 struct BD {
   // geometry (batch-uniform).  Voxel space is stored z-fastest: g = p*L3P + z (p = disk rank, L3P = L3 rounded
@@ -150,7 +139,6 @@ struct BD {
   const uint16_t* bil_tile_nr;  // [nM][ntile] number of consecutive rays touching it
   int bil_rmax;                 // max of bil_tile_nr
   int bil_adj_tile;             // 1: k_adj_bil_tile (else the gather kernel k_adj_bil)
-  BilBand bil_band;             // band forward tables (float32 operator)
   float* bil_ub;                // rows layout of u: the un-blended (slice-space) rows the adjoint gathers (k_bil_unblend)
   double* bil_ub64;             // same for the float64 operators of the bounded branch
   const int2* ls_ent;           // trilinear symmetry rows: 16 (internal voxel index, float weight bits) entries per row
