@@ -372,10 +372,14 @@ static void disk_tables(int G, double rmin, int rmax, std::vector<int>& rank, st
 // HB2_VOXEL_ORDER=0 restores round 1's row-major 8 x 32 tiles (tile by tile).  The reference order is kept for
 // everything exported and for the enumeration order of the symmetry rows.
 static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2ref, std::vector<int>& tile_begin,
-                       std::vector<int>& tilerow_begin, bool& tile_ok) {
+                       std::vector<int>& tilerow_begin, bool& tile_ok, int interpolation) {
   // read per problem (not latched), so that tests can compare the orders inside one process
   const char* e_o = getenv("HB2_VOXEL_ORDER"); const char* e_h = getenv("HB2_TILE_H"); const char* e_w = getenv("HB2_TILE_W");
-  const int ORDER = e_o ? atoi(e_o) : 1;
+  // Problems of trilinear searches (hb2_geometry.interpolation = 1) default to the row-major tiles: the footprint list of
+  // a ray is sorted by voxel rank, and with x-contiguous ranks 10 consecutive entries touch ~half as many cache lines
+  // (k_fwd_bil: 72 -> 59 us per candidate-pass at cfg2; 8 x 32, 16 x 16, 4 x 64 tiles within 2 us of each other, the
+  // tile adjoint prefers the compact ones -- profiles/r2_summary.md section 8)
+  const int ORDER = e_o ? atoi(e_o) : (interpolation == 1 ? 0 : 1);
   const int TH = e_h ? std::max(1, atoi(e_h)) : (ORDER ? 16 : 8);
   const int TW = e_w ? std::max(1, atoi(e_w)) : (ORDER ? 16 : 32);
   tile_ok = (long long)TH * TW <= HB2_BLOCK;
@@ -409,7 +413,7 @@ static void tile_order(const std::vector<short2>& yx_ref, std::vector<int>& int2
 extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const hb2_geometry* g, int device, void* stream) {
   if (!out || !image || !g) return fail(HB2_ERR_ARG, "null argument");
   if (hb2_device_count() <= 0) return fail(HB2_ERR_NO_DEVICE, "no CUDA device visible; helicon_b200 has no CPU fallback");
-  if (g->interpolation != 0) return fail(HB2_ERR_GEOMETRY, "only interpolation='nn' is implemented on the CUDA path");
+  if (g->interpolation != 0 && g->interpolation != 1) return fail(HB2_ERR_GEOMETRY, "hb2_geometry.interpolation: 0 (nn) or 1 (linear)");
   if (g->D2 <= 0 || g->L2 <= 0 || g->D3 <= 0 || g->D2 > 32000 || g->L2 > 32000)
     return fail(HB2_ERR_ARG, "bad reconstruct sizes");
   if (g->D2 / 2 > g->ny / 2 + 0 && (g->D2 > g->ny)) return fail(HB2_ERR_ARG, "D2 larger than the image");
@@ -434,8 +438,8 @@ extern "C" int hb2_problem_create(hb2_problem** out, const float* image, const h
   {
     std::vector<int> i2r_sym, tb_sym, tr_sym;
     bool ok_sym;
-    tile_order(yd, P->int2ref, P->h_tile_begin, P->h_tilerow_begin, P->tile_ok);
-    tile_order(ys, i2r_sym, tb_sym, tr_sym, ok_sym);
+    tile_order(yd, P->int2ref, P->h_tile_begin, P->h_tilerow_begin, P->tile_ok, g->interpolation);
+    tile_order(ys, i2r_sym, tb_sym, tr_sym, ok_sym, g->interpolation);
     P->ntile = (int)P->h_tile_begin.size() - 1;
     if (i2r_sym != P->int2ref) {
       delete P;

@@ -103,14 +103,16 @@ class Problem:
 
     def __init__(self, image, scale2d_to_3d, D2, L2, D3, rmin, rmax, device=0, stream=None, interpolation="nn"):
         lib = _lib.require_gpu()
-        if interpolation != "nn":
+        if interpolation not in ("nn", "linear"):
             raise NotImplementedError(
-                f"helicon_b200: interpolation={interpolation!r} is not implemented on the CUDA path (only 'nn'); "
+                f"helicon_b200: interpolation={interpolation!r} is not implemented on the CUDA path (only 'nn' and 'linear'); "
                 "there is no CPU fallback"
             )
         image = np.ascontiguousarray(image, dtype=np.float32)
         ny, nx = image.shape
-        self.geom = _lib.Geometry(ny, nx, float(scale2d_to_3d), int(D2), int(L2), int(D3), float(rmin), int(rmax), 0)
+        # interpolation is a layout hint only (internal voxel order); every batch type runs on either order
+        self.geom = _lib.Geometry(ny, nx, float(scale2d_to_3d), int(D2), int(L2), int(D3), float(rmin), int(rmax),
+                                  1 if interpolation == "linear" else 0)
         self.device = int(device)
         self.stream = _stream_handle(stream)
         self._h = C.c_void_p()

@@ -312,7 +312,8 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     def problem(key):
         if key not in probs:
             D2, L2, D3, D3i, s, L3 = key
-            probs[key] = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream)
+            probs[key] = Problem(image, s, D2, L2, D3, D3i / 2, D3 // 2 - 1, device=device, stream=stream,
+                                 interpolation="linear" if interpolation != "nn" else "nn")
         return probs[key]
 
     chunks = make_chunks(tasks, lambda key: problem(key).ndisk, batch_candidates, mem_budget_bytes, pipelined,

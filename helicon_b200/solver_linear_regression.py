@@ -264,7 +264,7 @@ def lsq_reconstruct(
     if D3 <= 0 or L3 <= 0:
         raise ValueError("reconstruct_diameter_3d_pixel and reconstruct_length_3d_pixel must be given")
     prob = _make_problem(image, scale2d_to_3d, D2, L2, D3, reconstruct_diameter_3d_inner_pixel,
-                         device=device)
+                         interpolation=_interp(interpolation), device=device)
     try:
         n3 = L3 * prob.ndisk
         # SLR:130, 148-150, 168-170: the reference multiplies the RAW arguments (-1 * -1 = 1 with the defaults)

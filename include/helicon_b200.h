@@ -54,7 +54,9 @@ typedef struct {
   int32_t D3;              /* reconstruct_diameter_3d_pixel */
   double rmin;             /* reconstruct_diameter_3d_inner_pixel / 2 (SLR:116) */
   int32_t rmax;            /* D3 // 2 - 1 (SLR:117) */
-  int32_t interpolation;   /* 0 = "nn" (SLR:1514-1557, 1142-1218) */
+  int32_t interpolation;   /* 0 = "nn" (SLR:1514-1557, 1142-1218); 1 = "linear": a hint for the internal voxel order only
+                            * (row-major tiles suit the footprint gathers of the matrix-free trilinear rows); every
+                            * batch type works on either order */
 } hb2_geometry;
 
 /* One candidate (twist, rise, csym).  Views/pairs are slices of the flat

@@ -14,7 +14,7 @@ pos = bool(int(sys.argv[3])) if len(sys.argv) > 3 else False
 img = bench.synthetic_filament()
 tasks = bench.grid_tasks()
 g = tasks[0].geom
-prob = Problem(img, g["s"], g["D2"], g["L2"], g["D3"], 0.0, g["D3"] // 2 - 1)
+prob = Problem(img, g["s"], g["D2"], g["L2"], g["D3"], 0.0, g["D3"] // 2 - 1, interpolation="linear")
 n3 = g["L3"] * prob.ndisk
 target = min(MAX_EQUATIONS, int(max(g["D2"] * g["L2"], n3) * g["sym_oversample"]))
 sel = tasks[20000:20000 + nc]

@@ -37,7 +37,7 @@ def test_matrix_free_trilinear_rows_equal_explicit_rows(name):
 
     N, L3, twist, rise, csym, mpl, msp, inner = CASES[name]
     img = _image(N)
-    prob = Problem(img, 1.0, N, N, N, inner / 2, N // 2 - 1)
+    prob = Problem(img, 1.0, N, N, N, inner / 2, N // 2 - 1, interpolation="linear")  # row-major tiles, as lsq_reconstruct / search_grid create it
     spec = CandidateSpec(twist, rise, csym, mpl, msp, False)
     other = CandidateSpec(twist * 0.93 + 1.0, rise * 1.07, 1, mpl, msp, False)
     eb = ExplicitBatch(prob, L3, spec, interpolation="linear")
@@ -95,7 +95,7 @@ def test_matrix_free_trilinear_batched_solve_equals_explicit_solves(positive):
 
     N, L3 = 48, 8
     img = _image(N, seed=9)
-    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)  # band-column-major voxel order (the nearest-neighbour default)
     specs = [CandidateSpec(tw, rs, 1, 0, 30000, positive) for tw, rs in ((-2.1, 2.9), (-1.4, 3.3), (-3.0, 3.0))]
     bb = BilinearBatch(prob, L3, specs)
     try:
@@ -137,7 +137,7 @@ def test_matrix_free_trilinear_fixed_iterations_equal_explicit_rows():
 
     N, L3 = 48, 8
     img = _image(N, seed=9)
-    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1, interpolation="linear")
     specs = [CandidateSpec(tw, rs, 1, 0, 30000, False) for tw, rs in ((-2.1, 2.9), (-1.4, 3.3))]
     bb = BilinearBatch(prob, L3, specs)
     try:
@@ -172,7 +172,7 @@ def test_matrix_free_trilinear_tile_adjoint_agrees_with_gather_adjoint(monkeypat
     specs = [CandidateSpec(tw, rs, cs, 0, 60000, False) for tw, rs, cs in ((-1.9, 3.65, 1), (27.3, 3.1, 1), (58.0, 3.5, 2))]
 
     def run():
-        prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+        prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1, interpolation="linear")
         bb = BilinearBatch(prob, L3, specs)
         rng = np.random.default_rng(4)
         x = rng.normal(size=bb.n).astype(np.float32)
