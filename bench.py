@@ -512,14 +512,14 @@ def main():
         search_grid(np.array(img, copy=True), APIX, TWISTS[[400]], RISES[[10, 30]], positive_constraint=0,
                     device=local_rank, stream=stream, interpolation="linear")
         t0 = time.perf_counter()
-        outl = search_grid(np.array(img, copy=True), APIX, TWISTS[[398, 402]], RISES[::2], positive_constraint=0,
-                           device=local_rank, stream=stream, interpolation="linear", batch_candidates=25)
+        outl = search_grid(np.array(img, copy=True), APIX, TWISTS[[398, 402]], RISES, positive_constraint=0,
+                           device=local_rank, stream=stream, interpolation="linear", batch_candidates=50)
         dtl = time.perf_counter() - t0
         trilinear = dict(value=outl["n_candidates"] / dtl, unit="candidates/s", candidates=int(outl["n_candidates"]),
                          n_gpus=1, mean_lsmr_iterations=float(np.nanmean(np.where(np.isfinite(outl["scores"]), outl["itn"], np.nan))),
                          best_score=float(np.nanmax(outl["scores"])), kernel_ms=float(outl["kernel_ms"]),
-                         note="search_grid(interpolation='linear', positive_constraint=0) on one GPU: 2 twists x 25 rises in "
-                              "batches of 25 candidates through the matrix-free trilinear operator (bilinear footprint maps x "
+                         note="search_grid(interpolation='linear', positive_constraint=0) on one GPU: 2 twists x 50 rises in "
+                              "batches of 50 candidates through the matrix-free trilinear operator (bilinear footprint maps x "
                               "slice blends, csrc/hb2_bilinear.cuh), host image -> host score map, one warmed call")
 
     # ---- parity gate against the CPU run of the same candidate ----------------------------------------------------

@@ -1948,9 +1948,12 @@ static void launch_adj(hb2_batch* b, int mode) {
 #define ABIL(Q)                                                                                      \
   do {                                                                                               \
     k_bil_unblend<Q, float, false><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, TD{}, B.u, B.bil_ub, mode); \
-    if (use_tile) {                                                                                  \
-      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, float, false>);                              \
-      k_adj_bil_tile<Q, float, false><<<dim3(B.ntile, B.nc), HB2_BILT_THREADS, smt, st>>>(B, TD{}, B.bil_ub, B.vtie, mode); \
+    if (use_tile && B.bil_KB == 3) {                                                                 \
+      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, 3, float, false>);                           \
+      k_adj_bil_tile<Q, 3, float, false><<<dim3(B.ntile, B.nc), HB2_BILT_THREADS, smt, st>>>(B, TD{}, B.bil_ub, B.vtie, mode); \
+    } else if (use_tile) {                                                                           \
+      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, 0, float, false>);                           \
+      k_adj_bil_tile<Q, 0, float, false><<<dim3(B.ntile, B.nc), HB2_BILT_THREADS, smt, st>>>(B, TD{}, B.bil_ub, B.vtie, mode); \
     } else k_adj_bil<Q, float, false><<<ga, HB2_BLOCK, 0, st>>>(B, TD{}, B.bil_ub, B.vtie, mode);   \
   } while (0)
       if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);
@@ -2152,8 +2155,8 @@ static int run_trf(hb2_batch* b, const hb2_solve_options* opt, std::vector<TrfSt
   do {                                                                                                 \
     k_bil_unblend<Q, double, true><<<b->n_tie_views, HB2_BLOCK, 0, st>>>(B, T, rows, B.bil_ub64, gate); \
     if (use_tile) {                                                                                    \
-      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, double, true>);                                \
-      k_adj_bil_tile<Q, double, true><<<dim3(B.ntile, nc), HB2_BILT_THREADS, smt, st>>>(B, T, B.bil_ub64, B.vtie64, gate); \
+      hb2_allow_big_smem((const void*)k_adj_bil_tile<Q, 0, double, true>);                             \
+      k_adj_bil_tile<Q, 0, double, true><<<dim3(B.ntile, nc), HB2_BILT_THREADS, smt, st>>>(B, T, B.bil_ub64, B.vtie64, gate); \
     } else k_adj_bil<Q, double, true><<<ga, HB2_BLOCK, 0, st>>>(B, T, B.bil_ub64, B.vtie64, gate);    \
   } while (0)
         if (B.L3P == 4) ABIL(1); else if (B.L3P == 8) ABIL(2); else if (B.L3P == 12) ABIL(3); else ABIL(4);

@@ -410,20 +410,30 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_lsym(BD B, TD Tt, const T* __
   float alpha = 0.f, inv_beta = 0.f;
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f;
-  for (int r = sub * HB2_BLOCK + threadIdx.x; r < nrow; r += ppv * HB2_BLOCK) {
+  // 8 lanes per row: lane l of a warp loads the l-th 16-byte piece (two entries) of 4 consecutive rows -- one coalesced
+  // 512-byte request per warp instruction -- and a 3-step shuffle tree adds the 8 partial sums of a row (fixed order)
+  const int sub8 = threadIdx.x & 7;
+  constexpr int RPB = HB2_BLOCK / 8;  // rows per CTA pass
+  for (int base = sub * RPB; base < nrow; base += ppv * RPB) {  // block-uniform trip count: the shuffles see full warps
+    const int r = base + (int)(threadIdx.x >> 3);
+    const bool rok = r < nrow;
     T acc = (T)0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int4 cc = ent4[(size_t)r * 8 + e];  // two (column, weight) entries
-      acc += (T)__int_as_float(cc.y) * vsrc[cc.x];
+    if (rok) {
+      const int4 cc = ent4[(size_t)r * 8 + sub8];  // two (column, weight) entries
+      acc = (T)__int_as_float(cc.y) * vsrc[cc.x];
       acc += (T)__int_as_float(cc.w) * vsrc[cc.z];
     }
-    if (TRF || mode == MODE_PLAIN) {
-      urow[r] = acc;
-    } else {
-      const float un = fadd_(fmul_(fmul_((float)urow[r], inv_beta), -alpha), (float)acc);
-      urow[r] = (T)un;
-      ss += un * un;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (rok && sub8 == 0) {
+      if (TRF || mode == MODE_PLAIN) {
+        urow[r] = acc;
+      } else {
+        const float un = fadd_(fmul_(fmul_((float)urow[r], inv_beta), -alpha), (float)acc);
+        urow[r] = (T)un;
+        ss += un * un;
+      }
     }
   }
   if (!TRF && mode == MODE_LSMR) {
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_adj_bil(BD B, TD Tt, const T* __r
 #define HB2_BILT_NS 4
 #define HB2_BILT_THREADS (HB2_BLOCK + 32)
 #define HB2_BILT_MAXV 512
-template <int NQT, typename T, bool TRF>
+template <int NQT, int KT, typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BILT_THREADS) k_adj_bil_tile(BD B, TD Tt, const T* __restrict__ ub, T* __restrict__ vt, int mode) {
   extern __shared__ __align__(128) unsigned char dsm[];
   const int c = blockIdx.y, tile = blockIdx.x;
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(HB2_BILT_THREADS) k_adj_bil_tile(BD B, TD Tt, 
   __shared__ int s_map[HB2_BILT_MAXV];
   __shared__ uint16_t s_jlo[HB2_BILT_MAXV], s_nr[HB2_BILT_MAXV];
   constexpr int L3P = 4 * NQT;
-  const int KB = B.bil_KB;
+  const int KB = KT > 0 ? KT : B.bil_KB;  // KT = 3 (the usual maximum of rays per voxel): the entry loop is unrolled
   const int ndisk_t = B.tile_begin[tile + 1] - B.tile_begin[tile];
   const int p = B.tile_begin[tile] + threadIdx.x;
   const bool producer = threadIdx.x >= HB2_BLOCK;
@@ -637,7 +647,9 @@ __global__ void __launch_bounds__(HB2_BILT_THREADS) k_adj_bil_tile(BD B, TD Tt, 
           const uint16_t* mp = reinterpret_cast<const uint16_t*>(sb) + threadIdx.x;
           const float* wp = reinterpret_cast<const float*>(sb + (size_t)KB * HB2_BLOCK * sizeof(uint16_t)) + threadIdx.x;
           const T* uw = reinterpret_cast<const T*>(sb + (size_t)KB * HB2_BLOCK * (sizeof(uint16_t) + sizeof(float)));
-          for (int k = 0; k < KB; ++k) {
+#pragma unroll
+          for (int k = 0; k < (KT > 0 ? KT : 4); ++k) {
+            if (KT == 0 && k >= KB) break;
             const unsigned j = mp[(size_t)k * HB2_BLOCK];
             if (j == 0xFFFFu) break;  // entries are packed from k = 0
             const T wk = (T)wp[(size_t)k * HB2_BLOCK];
