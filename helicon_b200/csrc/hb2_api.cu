@@ -1008,8 +1008,9 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
   const int apitch = P->ntile * HB2_BLOCK;
   // (everything the batch keeps is allocated before the big sort temporaries, so that those nest like a stack in the arena)
   int *d_kmax, *d_fcount, *d_fptr, *d_cursor;
+  const int NP = (D2 + 1) / 2;  // forward lists are kept per pair of adjacent rays
   CKM(b->pool.alloc(&d_kmax, 1, true, st));
-  CKM(b->pool.alloc(&d_fcount, (size_t)nM * D2 + 1, true, st));
+  CKM(b->pool.alloc(&d_fcount, (size_t)nM * NP + 1, true, st));
   const long long nmp = (long long)nM * P->ndisk;
   k_bil_T<0><<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, B.L3, P->ndisk, apitch, 0, d_maps, d_x, d_z, P->d_rank_data, P->d_yx_data,
                                              P->d_aslot, nullptr, nullptr, d_kmax, d_fcount);
@@ -1019,17 +1020,17 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
   CKM(cudaStreamSynchronize(st));
   KB = std::max(KB, 1);
   if (KB > 4) { tmp.free_all(); return fail(HB2_ERR_CAPACITY, "more than 4 rays of one view touch one voxel (internal error)"); }
-  CKM(b->pool.alloc(&d_fptr, (size_t)nM * D2 + 1, false, st));
+  CKM(b->pool.alloc(&d_fptr, (size_t)nM * NP + 1, false, st));
   uint16_t* d_Tj; float* d_Tw;
   CKM(b->pool.alloc(&d_Tj, (size_t)nM * KB * apitch, false, st));
   CKM(b->pool.alloc(&d_Tw, (size_t)nM * KB * apitch, true, st));
   CKM(cudaMemsetAsync(d_Tj, 0xFF, sizeof(uint16_t) * (size_t)nM * KB * apitch, st));
   size_t sb = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, sb, d_fcount, d_fptr, nM * D2 + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, sb, d_fcount, d_fptr, nM * NP + 1, st);
   void* d_scan; { uint8_t* p; CKM(b->pool.alloc(&p, sb, false, st)); d_scan = p; }
-  CKM(cub::DeviceScan::ExclusiveSum(d_scan, sb, d_fcount, d_fptr, nM * D2 + 1, st));
+  CKM(cub::DeviceScan::ExclusiveSum(d_scan, sb, d_fcount, d_fptr, nM * NP + 1, st));
   int nent = 0;
-  CKM(cudaMemcpyAsync(&nent, d_fptr + (size_t)nM * D2, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CKM(cudaMemcpyAsync(&nent, d_fptr + (size_t)nM * NP, sizeof(int), cudaMemcpyDeviceToHost, st));
   k_bil_T<1><<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, B.L3, P->ndisk, apitch, KB, d_maps, d_x, d_z, P->d_rank_data, P->d_yx_data,
                                              P->d_aslot, d_Tj, d_Tw, d_kmax, nullptr);
   CKM(cudaGetLastError());
@@ -1044,21 +1045,21 @@ extern "C" int hb2_batch_bilinear_maps(hb2_batch* b, int32_t nM, const hb2_bilin
     CKM(cudaStreamSynchronize(st));
   }
   // forward lists = the transpose, every ray sorted by voxel rank (deterministic summation order)
-  float* d_Fw; void* d_Fp;
+  float2* d_Fw; void* d_Fp;
   CKM(b->pool.alloc(&d_Fw, (size_t)std::max(nent, 1), false, st));
   { uint8_t* p; CKM(b->pool.alloc(&p, (size_t)std::max(nent, 1) * (b->idx16 ? 2 : 4), false, st)); d_Fp = p; }
   if (nent > 0) {
-    unsigned *d_key, *d_key2; float* d_val;
-    CKM(tmp.alloc(&d_cursor, (size_t)nM * D2, true, st));
+    unsigned *d_key, *d_key2; float2* d_val;
+    CKM(tmp.alloc(&d_cursor, (size_t)nM * NP, true, st));
     CKM(tmp.alloc(&d_key, (size_t)nent, false, st));
     CKM(tmp.alloc(&d_key2, (size_t)nent, false, st));
     CKM(tmp.alloc(&d_val, (size_t)nent, false, st));
     k_bil_F_fill<<<cdiv(nmp, 128), 128, 0, st>>>(nM, D2, P->ndisk, apitch, KB, P->d_aslot, d_Tj, d_Tw, d_fptr, d_cursor, d_key, d_val);
     CKM(cudaGetLastError());
     size_t sb2 = 0;
-    cub::DeviceSegmentedSort::SortPairs(nullptr, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * D2, d_fptr, d_fptr + 1, st);
+    cub::DeviceSegmentedSort::SortPairs(nullptr, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * NP, d_fptr, d_fptr + 1, st);
     void* d_s2; { uint8_t* p; CKM(tmp.alloc(&p, sb2, false, st)); d_s2 = p; }
-    CKM(cub::DeviceSegmentedSort::SortPairs(d_s2, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * D2, d_fptr, d_fptr + 1, st));
+    CKM(cub::DeviceSegmentedSort::SortPairs(d_s2, sb2, d_key, d_key2, d_val, d_Fw, nent, nM * NP, d_fptr, d_fptr + 1, st));
     if (b->idx16) k_bil_pack<uint16_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint16_t*)d_Fp);
     else k_bil_pack<uint32_t><<<cdiv(nent, 256), 256, 0, st>>>(nent, d_key2, (uint32_t*)d_Fp);
     CKM(cudaGetLastError());

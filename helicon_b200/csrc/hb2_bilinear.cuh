@@ -93,7 +93,8 @@ __global__ void k_bil_rayvalid(int nM, int D2, int L3, const BilMap* __restrict_
   }
 }
 
-// Transposed maps, voxel-driven.  PASS 0: kmax = max rays per (map, voxel), fcount[m][j] += 1 per entry;
+// Transposed maps, voxel-driven.  PASS 0: kmax = max rays per (map, voxel), fcount[m][j / 2] += 1 per ray PAIR the voxel
+// belongs to (the forward lists are kept per pair of adjacent rays: a voxel met by both rays is gathered once);
 // PASS 1: Tj / Tw[(m*KB + k)*apitch + aslot[p]] (0xFFFF = empty).  Rays ascending, samples ascending inside a ray.
 template <int PASS>
 __global__ void k_bil_T(int nM, int D2, int L3, int ndisk, int apitch, int KB, const BilMap* __restrict__ maps,
@@ -113,7 +114,8 @@ __global__ void k_bil_T(int nM, int D2, int L3, int ndisk, int apitch, int KB, c
   const double is = c0 - x0, js = c0 + y0, rad = 1.4143 + 0.02;
   const int i0 = max(0, (int)ceil(is - rad)), i1 = min(D2 - 1, (int)floor(is + rad));
   const int j0 = max(0, (int)ceil(js - rad)), j1 = min(D2 - 1, (int)floor(js + rad));
-  int cnt = 0;
+  int cnt = 0, last_pair = -1;
+  const int NP = (D2 + 1) / 2;
   for (int j = j0; j <= j1; ++j) {
     double w = 0.0;
     bool hit = false;
@@ -127,8 +129,9 @@ __global__ void k_bil_T(int nM, int D2, int L3, int ndisk, int apitch, int KB, c
       hit = true;
     }
     if (hit && w != 0.0) {
-      if (PASS == 0) atomicAdd(&fcount[(size_t)m * D2 + j], 1);
-      else if (cnt < KB) {
+      if (PASS == 0) {
+        if ((j >> 1) != last_pair) { atomicAdd(&fcount[(size_t)m * NP + (j >> 1)], 1); last_pair = j >> 1; }
+      } else if (cnt < KB) {
         Tj[((size_t)m * KB + cnt) * apitch + aslot[p]] = (uint16_t)j;
         Tw[((size_t)m * KB + cnt) * apitch + aslot[p]] = (float)w;
       }
@@ -161,19 +164,34 @@ __global__ void k_bil_hash(int nM, int D2, int apitch, int KB, const uint16_t* _
   if ((threadIdx.x & 31) == 0 && h) atomicAdd(&out[m], h);
 }
 
-// forward lists: entry (voxel p, weight) of ray (m, j) at fptr[m*D2 + j] + cursor; sorted by p afterwards
+// forward lists, one per (map, pair of adjacent rays 2P, 2P + 1): entry (voxel p, weight for ray 2P, weight for ray 2P + 1)
+// at fptr[m*NP + P] + cursor; sorted by p afterwards
 __global__ void k_bil_F_fill(int nM, int D2, int ndisk, int apitch, int KB, const int* __restrict__ aslot,
                              const uint16_t* __restrict__ Tj, const float* __restrict__ Tw, const int* __restrict__ fptr,
-                             int* __restrict__ cursor, unsigned* __restrict__ key, float* __restrict__ val) {
+                             int* __restrict__ cursor, unsigned* __restrict__ key, float2* __restrict__ val) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nM * ndisk) return;
   const int p = (int)(t % ndisk), m = (int)(t / ndisk);
-  for (int k = 0; k < KB; ++k) {
-    const size_t mi = ((size_t)m * KB + k) * apitch + aslot[p];
-    const unsigned j = Tj[mi];
-    if (j == 0xFFFFu) continue;
-    const int e = fptr[(size_t)m * D2 + j] + atomicAdd(&cursor[(size_t)m * D2 + j], 1);
-    key[e] = (unsigned)p; val[e] = Tw[mi];
+  const int NP = (D2 + 1) / 2;
+  int pair = -1;
+  float w0 = 0.f, w1 = 0.f;
+  for (int k = 0; k <= KB; ++k) {  // the entries of a voxel are rays in ascending order
+    unsigned j = 0xFFFFu;
+    float w = 0.f;
+    if (k < KB) {
+      const size_t mi = ((size_t)m * KB + k) * apitch + aslot[p];
+      j = Tj[mi]; w = Tw[mi];
+    }
+    const int pj = j == 0xFFFFu ? -2 : (int)(j >> 1);
+    if (pj != pair) {
+      if (pair >= 0) {
+        const int e = fptr[(size_t)m * NP + pair] + atomicAdd(&cursor[(size_t)m * NP + pair], 1);
+        key[e] = (unsigned)p; val[e] = make_float2(w0, w1);
+      }
+      pair = pj; w0 = w1 = 0.f;
+      if (pj == -2) break;
+    }
+    if (j & 1u) w1 = w; else w0 = w;
   }
 }
 template <typename IdxT>
@@ -223,11 +241,13 @@ __device__ __forceinline__ void ld4<double>(const double* __restrict__ p, double
   a = q0.x; b = q0.y; c = q1.x; d = q1.y;
 }
 
-// Forward of the bilinear views.  Grid (pseudo views, fwd_ppv); one warp per ray j; lane = (slice quad q, entry group
-// g): lanes q*G .. q*G + G - 1 walk the ray's footprint list G entries at a time, 128-bit gathers of 4 slices x weight;
-// a shuffle tree over g leaves P[4q .. 4q+3]; lane t < ZMP then blends and finishes column slot t.  Quads whose slices
-// no used slot of the view needs (single-column views of the exact maps) issue no gathers.  Halton duplicates of a copy
-// (identical rows, SLR:1559-1571) are served by the first copy's CTAs in the float32 modes (BD::view_dups).
+// Forward of the bilinear views.  Grid (pseudo views, fwd_ppv); one warp per PAIR of adjacent rays (2P, 2P + 1): their
+// footprints overlap in ~1.4 of ~2.4 voxels per column, so the pair's merged list (voxel, w_even, w_odd) has ~27 % fewer
+// gathers than two lists.  Lane = (slice quad q, entry group g): lanes q*G .. q*G + G - 1 walk the list G entries at a
+// time, one 128-bit gather of 4 slices feeds both rays; a shuffle tree over g leaves P[ray][4q .. 4q+3]; lane (ray, t)
+// then blends and finishes column slot t.  Quads whose slices no used slot of the view needs (single-column views of the
+// exact maps) issue no gathers.  Halton duplicates of a copy (identical rows, SLR:1559-1571) are served by the first
+// copy's CTAs in the float32 modes (BD::view_dups).
 template <typename IdxT, int Q, typename T, bool TRF>
 __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __restrict__ src, T* __restrict__ rows, int mode) {
   const int view = B.tie_views[blockIdx.x];
@@ -236,7 +256,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   if (!TRF && B.view_dupof[view] >= 0) return;  // duplicate of an earlier view: written by that view's CTAs
   const int c = B.view_cand[view];
   __shared__ float red[HB2_BLOCK / 32];
-  __shared__ T s_P[HB2_BLOCK / 32][16];
+  __shared__ T s_P[HB2_BLOCK / 32][2][16];
   __shared__ T s_a[16], s_b[16];
   __shared__ int s_colk[16];
   __shared__ unsigned s_qmask;
@@ -258,7 +278,7 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   }
   constexpr int L3P = 4 * Q, G = 32 / Q;
   constexpr int P2 = G >= 32 ? 32 : (G >= 16 ? 16 : (G >= 8 ? 8 : 4));
-  const int D2 = B.D2, ZMP = B.ZMP;
+  const int D2 = B.D2, ZMP = B.ZMP, NP = (D2 + 1) / 2;
   if (threadIdx.x < 16) {
     const bool in = (int)threadIdx.x < ZMP;
     const int ck = in ? B.bil_colk[(size_t)view * ZMP + threadIdx.x] : -1;
@@ -279,8 +299,8 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   }
   __syncthreads();
   const IdxT* __restrict__ Fp = (const IdxT*)B.bilF_p;
-  const float* __restrict__ Fw = B.bilF_w;
-  const int* __restrict__ ptr = B.bilF_ptr + (size_t)map * D2;
+  const float2* __restrict__ Fw = B.bilF_w;
+  const int* __restrict__ ptr = B.bilF_ptr + (size_t)map * NP;
   const uint8_t* __restrict__ rv = B.bil_rayvalid + (size_t)map * D2;
   const T* __restrict__ vsrc = src + (size_t)c * B.npad;
   T* urow = rows + B.view_uoff[view];
@@ -292,69 +312,88 @@ __global__ void __launch_bounds__(HB2_BLOCK) k_fwd_bil(BD B, TD Tt, const T* __r
   if (!TRF) { alpha = B.st[c].alpha; inv_beta = B.st[c].inv_beta; }
   float ss = 0.f, s_pb = 0.f, s_bb = 0.f;
   const uint8_t* __restrict__ pm = cand_mask(B, c);
-  for (int j = sub * (HB2_BLOCK / 32) + warp; j < D2; j += ppv * (HB2_BLOCK / 32)) {
-    if (!rv[j]) continue;  // warp-uniform
-    const int e0 = ptr[j], e1 = ptr[j + 1];
-    T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;
+  for (int pr = sub * (HB2_BLOCK / 32) + warp; pr < NP; pr += ppv * (HB2_BLOCK / 32)) {
+    const int j0 = 2 * pr;
+    const bool v0 = rv[j0] != 0, v1 = j0 + 1 < D2 && rv[j0 + 1] != 0;
+    if (!v0 && !v1) continue;  // warp-uniform
+    const int e0 = ptr[pr], e1 = ptr[pr + 1];
+    T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0, b0 = (T)0, b1 = (T)0, b2 = (T)0, b3 = (T)0;
     if (lane_on) {
       int e = e0 + g;
-      for (; e + 3 * G < e1; e += 4 * G) {  // four independent (rank, weight, gather) chains in flight
+      for (; e + 3 * G < e1; e += 4 * G) {  // four independent (rank, weights, gather) chains in flight
         const size_t p0 = Fp[e], p1 = Fp[e + G], p2 = Fp[e + 2 * G], p3 = Fp[e + 3 * G];
-        const T w0 = (T)Fw[e], w1 = (T)Fw[e + G], w2 = (T)Fw[e + 2 * G], w3 = (T)Fw[e + 3 * G];
+        const float2 w0 = Fw[e], w1 = Fw[e + G], w2 = Fw[e + 2 * G], w3 = Fw[e + 3 * G];
         T x0, x1, x2, x3, y0, y1, y2, y3, z0, z1, z2, z3, t0, t1, t2, t3;
         ld4<T>(vsrc + p0 * L3P + 4 * q, x0, x1, x2, x3);
         ld4<T>(vsrc + p1 * L3P + 4 * q, y0, y1, y2, y3);
         ld4<T>(vsrc + p2 * L3P + 4 * q, z0, z1, z2, z3);
         ld4<T>(vsrc + p3 * L3P + 4 * q, t0, t1, t2, t3);
-        a0 += w0 * x0; a1 += w0 * x1; a2 += w0 * x2; a3 += w0 * x3;
-        a0 += w1 * y0; a1 += w1 * y1; a2 += w1 * y2; a3 += w1 * y3;
-        a0 += w2 * z0; a1 += w2 * z1; a2 += w2 * z2; a3 += w2 * z3;
-        a0 += w3 * t0; a1 += w3 * t1; a2 += w3 * t2; a3 += w3 * t3;
+        a0 += (T)w0.x * x0; a1 += (T)w0.x * x1; a2 += (T)w0.x * x2; a3 += (T)w0.x * x3;
+        b0 += (T)w0.y * x0; b1 += (T)w0.y * x1; b2 += (T)w0.y * x2; b3 += (T)w0.y * x3;
+        a0 += (T)w1.x * y0; a1 += (T)w1.x * y1; a2 += (T)w1.x * y2; a3 += (T)w1.x * y3;
+        b0 += (T)w1.y * y0; b1 += (T)w1.y * y1; b2 += (T)w1.y * y2; b3 += (T)w1.y * y3;
+        a0 += (T)w2.x * z0; a1 += (T)w2.x * z1; a2 += (T)w2.x * z2; a3 += (T)w2.x * z3;
+        b0 += (T)w2.y * z0; b1 += (T)w2.y * z1; b2 += (T)w2.y * z2; b3 += (T)w2.y * z3;
+        a0 += (T)w3.x * t0; a1 += (T)w3.x * t1; a2 += (T)w3.x * t2; a3 += (T)w3.x * t3;
+        b0 += (T)w3.y * t0; b1 += (T)w3.y * t1; b2 += (T)w3.y * t2; b3 += (T)w3.y * t3;
       }
       for (; e < e1; e += G) {
         const size_t p0 = Fp[e];
-        const T w0 = (T)Fw[e];
+        const float2 w0 = Fw[e];
         T x0, x1, x2, x3;
         ld4<T>(vsrc + p0 * L3P + 4 * q, x0, x1, x2, x3);
-        a0 += w0 * x0; a1 += w0 * x1; a2 += w0 * x2; a3 += w0 * x3;
+        a0 += (T)w0.x * x0; a1 += (T)w0.x * x1; a2 += (T)w0.x * x2; a3 += (T)w0.x * x3;
+        b0 += (T)w0.y * x0; b1 += (T)w0.y * x1; b2 += (T)w0.y * x2; b3 += (T)w0.y * x3;
       }
     }
     // sum over the entry groups of a quad: lanes q*G + g, g < G (G = 32, 16, 10, 8); fixed tree -> deterministic
     if (G > P2) {
-      const T b0 = __shfl_down_sync(0xffffffffu, a0, P2), b1 = __shfl_down_sync(0xffffffffu, a1, P2);
-      const T b2 = __shfl_down_sync(0xffffffffu, a2, P2), b3 = __shfl_down_sync(0xffffffffu, a3, P2);
-      if (q < Q && g + P2 < G) { a0 += b0; a1 += b1; a2 += b2; a3 += b3; }
+      const T c0 = __shfl_down_sync(0xffffffffu, a0, P2), c1 = __shfl_down_sync(0xffffffffu, a1, P2);
+      const T c2 = __shfl_down_sync(0xffffffffu, a2, P2), c3 = __shfl_down_sync(0xffffffffu, a3, P2);
+      const T d0 = __shfl_down_sync(0xffffffffu, b0, P2), d1 = __shfl_down_sync(0xffffffffu, b1, P2);
+      const T d2 = __shfl_down_sync(0xffffffffu, b2, P2), d3 = __shfl_down_sync(0xffffffffu, b3, P2);
+      if (q < Q && g + P2 < G) { a0 += c0; a1 += c1; a2 += c2; a3 += c3; b0 += d0; b1 += d1; b2 += d2; b3 += d3; }
     }
 #pragma unroll
     for (int o = P2 / 2; o > 0; o >>= 1) {
       a0 += __shfl_down_sync(0xffffffffu, a0, o); a1 += __shfl_down_sync(0xffffffffu, a1, o);
       a2 += __shfl_down_sync(0xffffffffu, a2, o); a3 += __shfl_down_sync(0xffffffffu, a3, o);
+      b0 += __shfl_down_sync(0xffffffffu, b0, o); b1 += __shfl_down_sync(0xffffffffu, b1, o);
+      b2 += __shfl_down_sync(0xffffffffu, b2, o); b3 += __shfl_down_sync(0xffffffffu, b3, o);
     }
-    if (q < Q && g == 0) { s_P[warp][4 * q] = a0; s_P[warp][4 * q + 1] = a1; s_P[warp][4 * q + 2] = a2; s_P[warp][4 * q + 3] = a3; }
+    if (q < Q && g == 0) {
+      s_P[warp][0][4 * q] = a0; s_P[warp][0][4 * q + 1] = a1; s_P[warp][0][4 * q + 2] = a2; s_P[warp][0][4 * q + 3] = a3;
+      s_P[warp][1][4 * q] = b0; s_P[warp][1][4 * q + 1] = b1; s_P[warp][1][4 * q + 2] = b2; s_P[warp][1][4 * q + 3] = b3;
+    }
     __syncwarp();
-    if (lane < ZMP && s_colk[lane] >= 0 && !(pm && !pm[(size_t)s_colk[lane] * D2 + j])) {
-      const T lo = lane == 0 ? s_P[warp][0] : s_P[warp][lane - 1];
-      const T hi = lane == 0 ? s_P[warp][1] : s_P[warp][lane];
-      const T acc = s_a[lane] * lo + s_b[lane] * hi;
-      const size_t ri = (size_t)j * ZMP + lane;
-      if (TRF) {
-        urow[ri] = acc;
-      } else if (mode == MODE_LSMR) {
-        const float un = fadd_(fmul_(fmul_((float)urow[ri], inv_beta), -alpha), (float)acc);
-        urow[ri] = (T)un;
+    {  // lane = (ray of the pair, column slot)
+      const int rr = lane >> 4, t = lane & 15;
+      const int j = j0 + rr;
+      const bool rok = rr == 0 ? v0 : v1;
+      if (rok && t < ZMP && s_colk[t] >= 0 && !(pm && !pm[(size_t)s_colk[t] * D2 + j])) {
+        const T lo = t == 0 ? s_P[warp][rr][0] : s_P[warp][rr][t - 1];
+        const T hi = t == 0 ? s_P[warp][rr][1] : s_P[warp][rr][t];
+        const T acc = s_a[t] * lo + s_b[t] * hi;
+        const size_t ri = (size_t)j * ZMP + t;
+        if (TRF) {
+          urow[ri] = acc;
+        } else if (mode == MODE_LSMR) {
+          const float un = fadd_(fmul_(fmul_((float)urow[ri], inv_beta), -alpha), (float)acc);
+          urow[ri] = (T)un;
 #pragma unroll
-        for (int d = 0; d < HB2_MAXDUP; ++d)
-          if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = (T)un;  // identical row of the duplicate view
-        ss += un * un;
-      } else if (mode == MODE_PLAIN) {
-        urow[ri] = acc;
+          for (int d = 0; d < HB2_MAXDUP; ++d)
+            if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = (T)un;  // identical row of the duplicate view
+          ss += un * un;
+        } else if (mode == MODE_PLAIN) {
+          urow[ri] = acc;
 #pragma unroll
-        for (int d = 0; d < HB2_MAXDUP; ++d)
-          if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = acc;
-      } else {
-        const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
-        const float bv = brow[ri];
-        ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+          for (int d = 0; d < HB2_MAXDUP; ++d)
+            if (dupv[d] >= 0) (rows + B.view_uoff[dupv[d]])[ri] = acc;
+        } else {
+          const float pred = B.clip_pred ? fmaxf((float)acc, 0.f) : (float)acc;
+          const float bv = brow[ri];
+          ss += pred * pred; s_pb += pred * bv; s_bb += bv * bv;
+        }
       }
     }
     __syncwarp();

@@ -125,9 +125,9 @@ struct BD {
   // matrix-free trilinear rows (hb2_bilinear.cuh): bilinear in-plane footprints per map + per-column slice blends
   int bil;                      // 1: every data view of the batch is a bilinear view (all views are pseudo views)
   int bil_KB;                   // (ray, weight) slots per (map, voxel) of the transposed maps
-  const void* bilF_p;           // forward lists: voxel rank per entry (uint16 while the disk has < 65535 voxels, else uint32)
-  const float* bilF_w;          //                weight per entry
-  const int* bilF_ptr;          // [nM*D2 + 1] entries of ray (map, j)
+  const void* bilF_p;           // forward lists (one per pair of adjacent rays): voxel rank per entry (uint16 while the disk has < 65535 voxels, else uint32)
+  const float2* bilF_w;         //                weights per entry: for ray 2P (.x) and ray 2P + 1 (.y) of the pair
+  const int* bilF_ptr;          // [nM*NP + 1], NP = ceil(D2 / 2): entries of the ray pair (map, P)
   const uint16_t* bilT_j;       // [nM][KB][apitch] transposed maps: ray of the k-th entry of voxel p, 0xFFFF = none
   const float* bilT_w;          // [nM][KB][apitch]
   const uint8_t* bil_rayvalid;  // [nM][D2]
