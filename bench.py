@@ -403,8 +403,10 @@ def main():
                        batch.n, res["itn"].astype(np.float64), res["n_sym_rows"].astype(np.float64), res["trf_nit"].astype(np.float64),
                        int(np.count_nonzero(batch.plan.views["dup_of"] < 0)) / max(1, batch.nc), batch.problem.ndisk, batch.L3))
 
+        t_s0 = time.perf_counter()
         stats = solve_chunks(block, queue, problem, device=local_rank, pipelined=not args.no_pipeline, profile=int(profile),
                              on_result=on_result)
+        stats["solve_wall_ms"] = 1e3 * (time.perf_counter() - t_s0)  # this rank's own work, before it waits in the all-gather
         if dist is not None:
             mine = torch.as_tensor(smap, device=f"cuda:{local_rank}")
             buf = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
@@ -438,6 +440,18 @@ def main():
         t_ms = float(mx[0].item())
     total_cands, itn_total, launches_total = int(red[1].item()), float(red[2].item()), int(red[3].item())
     value = total_cands / (t_ms / 1e3)
+    # per-rank decomposition of the timed region (where a scaling loss comes from: uneven chunk deal, slower GPUs, host)
+    mine_pr = torch.tensor([stats["solve_wall_ms"], stats["lsmr_ms"] + stats["trf_ms"] + stats["score_ms"],
+                            float(stats["n_chunks"]), float(stats["n_candidates"]), float(stats["itn_sum"]),
+                            float(clocks.get("sm_mhz") or 0.0), float("sw_power_cap" in clocks.get("reasons", []))],
+                           device="cuda", dtype=torch.float64)
+    if dist is not None:
+        all_pr = torch.empty(world * mine_pr.numel(), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(all_pr, mine_pr)
+    else:
+        all_pr = mine_pr
+    per_rank = [dict(solve_wall_ms=round(r[0], 1), kernel_ms=round(r[1], 1), chunks=int(r[2]), candidates=int(r[3]),
+                     lsmr_iterations=int(r[4]), sm_mhz=r[5], sw_power_cap=bool(r[6])) for r in all_pr.reshape(-1, 7).tolist()]
     sc_all, itn_all, fl_all = smap.read()
     smap.close()
     per_rank_cands = stats["n_candidates"]
@@ -646,6 +660,7 @@ def main():
         top=dict(best_score=float(top[0][0]) if len(top[0]) else None, best_index=int(top[1][0]) if len(top[1]) else None,
                  note="selected by the device top-K kernel over the all-gathered score map"),
     )
+    line["per_rank"] = per_rank
     if unb is not None:
         line["unbounded_path"] = unb
     if trilinear is not None:
