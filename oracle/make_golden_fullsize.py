@@ -45,6 +45,9 @@ REF_CASES = {
     "full_cfg2_true_pos": (256, -1.2, 4.75, 1, -1),
     "full_cfg2_b_unb": (256, -2.03, 4.62, 1, 0),
     "full_cfg2_b_pos": (256, -2.03, 4.62, 1, -1),
+    # trilinear interpolation (the app's default) at the benchmark shape: the matrix-free trilinear path (bilinear.py)
+    "full_cfg2_b_lin_unb": (256, -2.03, 4.62, 1, 0, "linear"),
+    "full_cfg1_b_lin_unb": (200, -2.03, 4.62, 1, 0, "linear"),
 }
 # name: (N, twist, rise_A, csym, fixed_iters)
 FIXED_CASES = {
@@ -74,7 +77,8 @@ def run_reference(name):
 
     LL = importlib.import_module("scipy.optimize._lsq.lsq_linear")
 
-    N, twist, rise, csym, pc = REF_CASES[name]
+    N, twist, rise, csym, pc = REF_CASES[name][:5]
+    interp = REF_CASES[name][5] if len(REF_CASES[name]) > 5 else "nn"
     g = geometry(N, rise)
     img = image_for(N)
     spy = dict(lsmr=[], trf=[])
@@ -98,7 +102,7 @@ def run_reference(name):
         projection_image=img, scale2d_to_3d=g["s"], twist_degree=twist, rise_pixel=rise / g["apix3d"], csym=csym,
         positive_constraint=pc, reconstruct_diameter_3d_inner_pixel=g["D3i"], reconstruct_diameter_2d_pixel=g["D2"],
         reconstruct_length_2d_pixel=g["L2"], reconstruct_diameter_3d_pixel=g["D3"], reconstruct_length_3d_pixel=g["L3"],
-        sym_oversample=g["sym_oversample"], interpolation="nn", algorithm=dict(model="lsq"), cpu=1)
+        sym_oversample=g["sym_oversample"], interpolation=interp, algorithm=dict(model="lsq"), cpu=1)
     dt = time.time() - t0
     LL.lsmr, LL.trf_linear = real_lsmr, real_trf
     from oracle import denovo3d_oracle as O
