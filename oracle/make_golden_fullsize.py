@@ -48,6 +48,7 @@ REF_CASES = {
     # trilinear interpolation (the app's default) at the benchmark shape: the matrix-free trilinear path (bilinear.py)
     "full_cfg2_b_lin_unb": (256, -2.03, 4.62, 1, 0, "linear"),
     "full_cfg1_b_lin_unb": (200, -2.03, 4.62, 1, 0, "linear"),
+    "full_cfg1_b_lin_pos": (200, -2.03, 4.62, 1, -1, "linear"),
 }
 # name: (N, twist, rise_A, csym, fixed_iters)
 FIXED_CASES = {
