@@ -168,7 +168,7 @@ def test_bounded_path_statistics_vs_reference_band():
     assert d_gpu.max() <= max(5e-2, 2 * d_ref.max())
 
 
-LIN_CASES = [n for n in ("full_cfg1_b_lin_unb", "full_cfg2_b_lin_unb") if os.path.exists(os.path.join(GOLDEN, n + ".npz"))]
+LIN_CASES = [n for n in ("full_cfg1_b_lin_unb", "full_cfg2_b_lin_unb", "full_cfg1_b_lin_pos") if os.path.exists(os.path.join(GOLDEN, n + ".npz"))]
 
 
 @pytest.mark.parametrize("name", LIN_CASES)
@@ -197,4 +197,13 @@ def test_full_size_trilinear_solve_vs_reference(name):
           f"data rows={int(r['n_data_rows'])} (reference solve: {float(d['seconds']):.0f} s on one core)")
     assert int(r["istop"]) == int(d["istop"])
     assert abs(int(r["itn"]) - int(d["itn"])) <= 3
-    assert dscore <= 1e-5 and rel <= 4.6e-2
+    if int(pc) != 0:
+        # reference-default rule: scipy's bounded TRF branch on the trilinear system (float64 instantiations of the matrix-free
+        # kernels).  The reference's own band for bounded trilinear solves is |dscore| 4.6e-2 / rel-L2 0.26 under a row
+        # permutation (tests/golden/gen_solve_lin_48_pos.npz): the step kinds of the TRF loop are data-dependent
+        print(f"    bounded branch: TRF iterations gpu={int(r['trf_nit'])} ref={int(d['trf_nit'])} flags={int(r['flags'])}")
+        assert int(r["flags"]) & 4 and rec.min() >= 0.0
+        assert abs(int(r["trf_nit"]) - int(d["trf_nit"])) <= 5
+        assert dscore <= 4.6e-2 and rel <= 0.26
+    else:
+        assert dscore <= 1e-5 and rel <= 4.6e-2
