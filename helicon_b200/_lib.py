@@ -104,7 +104,7 @@ EXPORTS = [
     "hb2_batch_bilinear_maps", "hb2_batch_bilinear_ray_valid", "hb2_batch_bilinear_views", "hb2_batch_bilinear_sym_rows",
     "hb2_batch_bilinear_sym_export",
     "hb2_scoremap_create", "hb2_scoremap_destroy", "hb2_scoremap_device_ptr", "hb2_batch_scatter_scores",
-    "hb2_scoremap_merge", "hb2_scoremap_topk", "hb2_scoremap_read",
+    "hb2_scoremap_merge", "hb2_scoremap_topk", "hb2_scoremap_read", "hb2_scoremap_restore",
 ]
 
 _lib = None
@@ -173,6 +173,7 @@ def load():
     lib.hb2_scoremap_device_ptr.restype = vp
     lib.hb2_batch_scatter_scores.argtypes = [vp, vp, vp, vp]
     lib.hb2_scoremap_merge.argtypes = [vp, vp, i32, vp]
+    lib.hb2_scoremap_restore.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.hb2_scoremap_topk.argtypes = [vp, i32, vp, vp, vp]
     lib.hb2_scoremap_read.argtypes = [vp, vp, vp, vp, vp]
     _lib = lib

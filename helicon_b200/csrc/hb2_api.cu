@@ -2623,6 +2623,45 @@ extern "C" int hb2_batch_scatter_scores(hb2_batch* b, hb2_scoremap* m, const int
   CK(cudaStreamSynchronize(st));  // task_index_host may go away; the staging buffer is shared by the search's batches
   return HB2_OK;
 }
+// entries of an earlier, interrupted search (checkpoint.py): packed (index, score bits, iterations, flags) records
+__global__ void k_scoremap_restore(const long long* __restrict__ rec, long long n_entries, long long n,
+                                   float* __restrict__ sc, int* __restrict__ it, unsigned* __restrict__ fl) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const long long t = rec[2 * e];
+  if (t < 0 || t >= n) return;
+  const unsigned long long w = (unsigned long long)rec[2 * e + 1];  // iterations << 32 | score bits
+  sc[t] = __uint_as_float((unsigned)(w & 0xffffffffull));
+  it[t] = (int)(unsigned)(w >> 32);
+  fl[t] = (unsigned)rec[2 * n_entries + e];
+}
+extern "C" int hb2_scoremap_restore(hb2_scoremap* m, int64_t n_entries, const int64_t* task_index_host,
+                                    const float* scores_host, const int32_t* itn_host, const uint32_t* flags_host) {
+  if (!m || n_entries < 0 || (n_entries > 0 && (!task_index_host || !scores_host || !itn_host || !flags_host)))
+    return fail(HB2_ERR_ARG, "bad argument");
+  if (n_entries == 0) return HB2_OK;
+  CK(cudaSetDevice(m->device));
+  std::vector<long long> stage((size_t)3 * n_entries);
+  for (int64_t e = 0; e < n_entries; ++e) {
+    if (task_index_host[e] < 0 || task_index_host[e] >= m->n) return fail(HB2_ERR_ARG, "restored task index outside the map");
+    unsigned sb;
+    memcpy(&sb, &scores_host[e], 4);
+    stage[2 * e] = task_index_host[e];
+    stage[2 * e + 1] = (long long)(((unsigned long long)(unsigned)itn_host[e] << 32) | sb);
+    stage[2 * n_entries + e] = flags_host[e];
+  }
+  long long* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(long long) * stage.size()));
+  cudaError_t e1 = cudaMemcpy(d, stage.data(), sizeof(long long) * stage.size(), cudaMemcpyHostToDevice);
+  if (e1 == cudaSuccess) {
+    k_scoremap_restore<<<cdiv(n_entries, 256), 256>>>(d, n_entries, m->n, m->d_score, m->d_itn, m->d_flags);
+    e1 = cudaGetLastError();
+    if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();
+  }
+  cudaFree(d);
+  if (e1 != cudaSuccess) return fail(HB2_ERR_CUDA, std::string("hb2_scoremap_restore: ") + cudaGetErrorString(e1));
+  return HB2_OK;
+}
 extern "C" int hb2_scoremap_merge(hb2_scoremap* m, const void* gathered_dev, int32_t n_maps, void* stream) {
   if (!m || !gathered_dev || n_maps <= 0) return fail(HB2_ERR_ARG, "bad argument");
   CK(cudaSetDevice(m->device));

@@ -68,6 +68,15 @@ class ScoreMap:
         assert len(idx) == batch.nc == len(fl)
         _lib.check(_lib.load().hb2_batch_scatter_scores(batch._h, self._h, _lib.ptr(idx), _lib.ptr(fl)))
 
+    def restore(self, task_indices, scores, itn, flags):
+        """Entries of an interrupted search of the same grid (checkpoint.ScoreTileStore) written into the device maps."""
+        idx = np.ascontiguousarray(task_indices, dtype=np.int64)
+        sc = np.ascontiguousarray(scores, dtype=np.float32)
+        it = np.ascontiguousarray(itn, dtype=np.int32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint32)
+        assert len(idx) == len(sc) == len(it) == len(fl)
+        _lib.check(_lib.load().hb2_scoremap_restore(self._h, len(idx), _lib.ptr(idx), _lib.ptr(sc), _lib.ptr(it), _lib.ptr(fl)))
+
     def merge(self, gathered_ptr, n_maps, stream=None):
         """Fold ``n_maps`` maps of other ranks (device buffer of n_maps x 3n words, e.g. filled by an all-gather) in."""
         _lib.check(_lib.load().hb2_scoremap_merge(self._h, C.c_void_p(int(gathered_ptr)), int(n_maps), _stream_handle(stream)))

@@ -10,14 +10,17 @@ semantics are those of ``lsq_reconstruct`` (solver_linear_regression.py:31-547).
 from __future__ import annotations
 
 import itertools
+import logging
 import time
-
-import numpy as np
 
 from concurrent.futures import ThreadPoolExecutor
 
+import numpy as np
+
 from .engine import Batch, ExplicitBatch, Problem, ScoreMap, Stream
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
+
+logger = logging.getLogger(__name__)
 
 
 class BatchPipeline:
@@ -282,7 +285,7 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                 tube_diameter_inner=0.0, tube_length=None, target_apix3d=0, sym_oversample=-1,
                 positive_constraint=-1, thresh_fraction=-1, top_k=10, device=0, stream=None, batch_candidates=None,
                 mem_budget_bytes=48 << 30, shard=(0, 1), return_x_top=False, progress=None, pipelined=True,
-                interpolation="nn", dist=None):
+                interpolation="nn", dist=None, checkpoint=None, checkpoint_seconds=30.0):
     """Solve + score every candidate of the grid on one GPU (or this rank's share of it).
 
     ``interpolation="nn"`` runs batches of candidates through the matrix-free projector; ``"linear"`` (trilinear rows,
@@ -296,7 +299,11 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     iteration map and top-K selection are device-resident (``engine.ScoreMap``: one scatter kernel per solved batch,
     one top-K kernel per search).  ``thresh_fraction >= 0``
     applies the image preparation of ``process_one_task`` (pipeline.py:276-284) and clips the predictions at 0
-    (SLR:502-503).  Returns dict(scores[(n_csym,) T, R] (NaN = not solved here / skipped task), itn, flags, top,
+    (SLR:502-503).  ``checkpoint=path`` makes the search resumable (checkpoint.ScoreTileStore): the tiles of solved
+    batches are written to ``path`` (``path.rank<r>`` per rank) every ``checkpoint_seconds``; a later call with the same
+    image, grid and parameters restores them into the device maps (``hb2_scoremap_restore``) and solves only the rest
+    (``n_restored`` in the result; ``return_x_top`` volumes exist only for candidates solved in this call).
+    Returns dict(scores[(n_csym,) T, R] (NaN = not solved here / skipped task), itn, flags, top,
     n_candidates, seconds).
     """
     ny, nx = np.asarray(image).shape
@@ -308,6 +315,22 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                               tube_diameter_inner, tube_length, target_apix3d, sym_oversample, positive_constraint)
     t0 = time.perf_counter()
     probs = {}
+    store = None
+    if checkpoint is not None:
+        from .checkpoint import ScoreTileStore, fingerprint
+
+        rank, world = shard
+        if dist is not None and dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        fp = fingerprint(image, (np.asarray(csyms, dtype=np.float64), twists, rises), apix=float(apix),
+                         reconstruct_length_rise=reconstruct_length_rise, tube_diameter=tube_diameter,
+                         tube_diameter_inner=tube_diameter_inner, tube_length=tube_length, target_apix3d=target_apix3d,
+                         sym_oversample=sym_oversample, positive_constraint=positive_constraint,
+                         clip_pred=int(thresh_fraction >= 0), interpolation=str(interpolation))
+        store = ScoreTileStore(checkpoint, fp, ntot, rank=rank, world=world, flush_seconds=checkpoint_seconds)
+        tasks_all = len(tasks)
+        tasks = [t for t in tasks if not store.is_done(t.ti)]
+        logger.info("search_grid: %d of %d candidates restored from %s", tasks_all - len(tasks), tasks_all, checkpoint)
 
     def problem(key):
         if key not in probs:
@@ -322,10 +345,15 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     smap = ScoreMap(ntot, device=device)  # score / iteration / flag maps + top-K live on the device
     top_x = {}
     done = [0]
+    if store is not None and store.n_restored:
+        r = np.flatnonzero(store.restored)
+        smap.restore(r, store.scores[r], store.itn[r], store.flags[r])
 
     def on_result(chunk, res, batch):
         done[0] += len(chunk)
         smap.scatter(batch, [x.ti for x in chunk], res["flags"])
+        if store is not None:
+            store.add([x.ti for x in chunk], res["score"], res["itn"], res["flags"])
         if return_x_top and top_k:  # keep the volumes of this batch's best candidates while the batch is alive
             for c in np.argsort(-res["score"], kind="stable")[:top_k]:
                 top_x[chunk[c].ti] = (float(res[c]["score"]), batch.rec3d(int(c)))
@@ -353,7 +381,7 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                 cur.synchronize()
         scores, itn, flags = smap.read()
         if dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            n_solved = int(np.isfinite(scores).sum())
+            n_solved = int(np.isfinite(scores).sum()) - (store.n_restored if store is not None else 0)
         top = []
         if top_k:
             axes = (tuple(int(c) for c in csyms), twists, rises)
@@ -366,6 +394,8 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                     ent["rec3d"] = top_x[ti][1]
                 top.append(ent)
     finally:
+        if store is not None:
+            store.close()  # also after an interrupted search: what was solved so far is on disk
         smap.close()
         for pr in probs.values():
             pr.close()
@@ -373,7 +403,7 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     out = dict(scores=scores.reshape(shape), itn=itn.reshape(shape), flags=flags.reshape(shape), top=top,
                n_candidates=n_solved, n_solved_here=stats["n_candidates"], seconds=time.perf_counter() - t0,
                kernel_ms=stats["kernel_ms"], launches=stats["launches"] + 2 * stats["n_chunks"] + 2,
-               axes=(tuple(int(c) for c in csyms), twists, rises))
+               axes=(tuple(int(c) for c in csyms), twists, rises), n_restored=store.n_restored if store is not None else 0)
     return out
 
 

@@ -20,6 +20,7 @@ from . import bilinear
 from .engine import Batch, ExplicitBatch, Problem, build_trilinear_sym_rows
 from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 from .planner import sorted_hsym_csym_pairs  # noqa: F401  (SLR:1749-1791, re-exported)
+from .lsqr import solve_lsqr
 from .regularized import MODELS, solve_model
 
 logger = logging.getLogger(__name__)
@@ -480,18 +481,20 @@ def refine_tilt_psi_dy(
     verbose=0,
     cpu=1,
     device=0,
+    unbounded_solver="lsqr",
+    solve_info=None,
 ):
     """SLR:550-841: Gauss-Newton refinement of (tilt, psi, dy) with a finite-difference Jacobian -> ``(tilt, psi, dy,
     x, score)``.  The loop (perturb, 3x3 normal equations, projected step, convergence test, re-solve) is the
     reference's, on the host with scalars; every matrix build, prediction ``A_data @ x`` and solve runs on the GPU
     (explicit rows, ``engine.ExplicitBatch``).
 
-    Solver note: the reference solves with ``scipy.sparse.linalg.lsqr(atol=btol=1e-6)`` (or ``lsq_linear`` at its default
-    tolerance when the positive rule fires); here the same systems are solved by the batch's LSMR at the same
-    tolerances (atol = btol = 1e-6, iteration limit 2n; bounded branch with tol = 1e-10).  LSQR and LSMR run the same
-    Golub-Kahan process and converge to the same minimiser; the iterates at the stopping point differ at the level of
-    the tolerance (measured against the reference in tests/test_gpu_parity.py).  ``x_init`` is unused, as in the
-    reference."""
+    Solver: as the reference -- unbounded systems by ``scipy.sparse.linalg.lsqr(atol=btol=1e-6)`` (SLR:711-714), here
+    scipy's own recurrence over the CUDA operator (lsqr.py: both products on the GPU); ``lsq_linear`` at its default
+    tolerance when the positive rule fires (SLR:704-709), here the batch's LSMR + TRF state machines (tol = 1e-10).
+    ``unbounded_solver="lsmr"`` keeps round 1's device-resident LSMR at the same tolerances (same minimiser, iterates
+    differ at the level of the tolerance).  ``solve_info`` (a list) collects one dict per unbounded solve.  ``x_init``
+    is unused, as in the reference."""
     image = np.asarray(projection_image)
     n2 = int(reconstruct_diameter_2d_pixel) * int(reconstruct_length_2d_pixel)  # SLR:639: raw product (1 with the -1 defaults)
     D2 = int(reconstruct_diameter_2d_pixel) if reconstruct_diameter_2d_pixel > 0 else image.shape[0]
@@ -516,7 +519,13 @@ def refine_tilt_psi_dy(
         m = batch.rows_padded(0)[1]  # data + symmetry rows (padded count: an upper bound is enough for the limit)
         if positive:  # lsq_linear(A, b, bounds, max_iter=200): tol = 1e-10, lsmr_tol = 1e-2 * tol, lsmr_maxiter = min(m, n)
             batch.solve(atol=1e-12, btol=1e-12, max_iter=int(min(max(m, 1), n)), trf_tol=1e-10, trf_max_iter=200)
-        else:         # lsqr(A, b, atol=1e-6, btol=1e-6): iter_lim = 2 n
+        elif unbounded_solver == "lsqr":  # lsqr(A, b, atol=1e-6, btol=1e-6): scipy's recurrence, GPU products
+            info = {}
+            x = solve_lsqr(batch, 0, atol=1e-6, btol=1e-6, info=info)
+            if solve_info is not None:
+                solve_info.append(info)
+            return x
+        else:         # device-resident LSMR at the same tolerances, iter_lim = 2 n
             batch.solve(atol=1e-6, btol=1e-6, max_iter=2 * n)
         return batch.x(0)
 

@@ -362,6 +362,11 @@ void hb2_scoremap_destroy(hb2_scoremap* m);
 void* hb2_scoremap_device_ptr(hb2_scoremap* m);
 /* task_index_host[n_cand], flags_host[n_cand] (hb2_result.flags of the batch's solve) */
 int hb2_batch_scatter_scores(hb2_batch* b, hb2_scoremap* m, const int64_t* task_index_host, const uint32_t* flags_host);
+/* resume: entries of an earlier, interrupted search of the SAME grid (task index, score, iterations, flags; host
+ * arrays of n_entries) written into the maps before the remaining candidates are solved -- replaces the reference's
+ * on-disk function cache of finished candidates (lib/cache.py:132-209, used by app.py:2473-2539) */
+int hb2_scoremap_restore(hb2_scoremap* m, int64_t n_entries, const int64_t* task_index_host, const float* scores_host,
+                         const int32_t* itn_host, const uint32_t* flags_host);
 int hb2_scoremap_merge(hb2_scoremap* m, const void* gathered_dev, int32_t n_maps, void* stream);
 int hb2_scoremap_topk(hb2_scoremap* m, int32_t k, float* top_scores_host, int64_t* top_index_host, void* stream);
 int hb2_scoremap_read(hb2_scoremap* m, float* scores_host, int32_t* itn_host, uint32_t* flags_host, void* stream);

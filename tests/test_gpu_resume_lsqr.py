@@ -1,0 +1,87 @@
+"""GPU tests of round 2's last additions: resumable grid searches (hb2_scoremap_restore + checkpoint.ScoreTileStore)
+and scipy's LSQR over the CUDA operator (lsqr.py), the solver of refine_tilt_psi_dy's unbounded systems (SLR:711-714)."""
+
+import numpy as np
+import pytest
+
+from tests.helpers import load
+
+
+@pytest.mark.gpu
+def test_search_grid_interrupted_and_resumed_equals_one_run(tmp_path):
+    """A search that dies after its first batch leaves that batch's tile on disk; the resumed search restores it into
+    the DEVICE maps, solves only the rest and returns bit-identical maps and the same top-K as an uninterrupted run."""
+    from helicon_b200.grid import search_grid
+
+    d = load("grid_64")
+    img, apix = d["image"], round(float(d["apix"]), 4)
+    tw, ri = np.array([-2.13, -1.37, -0.67, 0.0]), np.linspace(4.31, 5.13, 3)  # twist 0 is skipped (app.py:2389)
+    kw = dict(positive_constraint=0, batch_candidates=3, top_k=4)
+    ref = search_grid(img, apix, tw, ri, **kw)
+    ck = str(tmp_path / "run.tiles")
+
+    class Stop(Exception):
+        pass
+
+    def die_after_first_batch(done, total):
+        raise Stop()
+
+    with pytest.raises(Stop):
+        search_grid(img, apix, tw, ri, checkpoint=ck, progress=die_after_first_batch, **kw)
+    part = np.load(ck + ".npz")
+    assert len(part["ti"]) == 3  # one batch of 3 candidates made it to disk
+    out = search_grid(img, apix, tw, ri, checkpoint=ck, **kw)
+    assert out["n_restored"] == 3 and out["n_solved_here"] == ref["n_candidates"] - 3
+    assert np.array_equal(out["scores"], ref["scores"], equal_nan=True)
+    assert np.array_equal(out["itn"], ref["itn"]) and np.array_equal(out["flags"], ref["flags"])
+    assert [(e["ti"], e["score"]) for e in out["top"]] == [(e["ti"], e["score"]) for e in ref["top"]]
+    # a third call finds everything on disk and launches no solve at all
+    again = search_grid(img, apix, tw, ri, checkpoint=ck, **kw)
+    assert again["n_solved_here"] == 0 and again["n_restored"] == ref["n_candidates"]
+    assert np.array_equal(again["scores"], ref["scores"], equal_nan=True)
+    assert [e["ti"] for e in again["top"]] == [e["ti"] for e in ref["top"]]
+    # other parameters -> other fingerprint -> nothing restored
+    other = search_grid(img, apix, tw, ri, checkpoint=ck, positive_constraint=1, batch_candidates=3, top_k=4)
+    assert other["n_restored"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("interp", ["nn", "linear"])
+def test_lsqr_over_the_cuda_operator_equals_scipy_on_the_exported_rows(interp):
+    """scipy.sparse.linalg.lsqr on (a) the LinearOperator of GPU products and (b) the explicit CSR rows exported from the
+    same batch (what the reference hands to lsqr): same stopping rule and iteration count (+-2 %: float32 summation
+    order inside a product), same solution to the solver's tolerance."""
+    from scipy.sparse import vstack
+    from scipy.sparse.linalg import lsqr
+
+    from helicon_b200 import planner
+    from helicon_b200.engine import ExplicitBatch, Problem
+    from helicon_b200.lsqr import solve_lsqr
+    from helicon_b200.planner import CandidateSpec
+
+    d = load("refine_dy_40")
+    apix, twist, rise, csym, L3, so, pc, mi = d["args"]
+    img = d["image"]
+    N = img.shape[0]
+    prob = Problem(img, 1.0, N, N, N, 0.0, N // 2 - 1)
+    n = int(L3) * prob.ndisk
+    target = min(planner.MAX_EQUATIONS, int(max(N * N, N * N * int(L3)) * int(so)))
+    spec = CandidateSpec(float(twist), float(rise / apix), int(csym), target, target, False)
+    batch = ExplicitBatch(prob, int(L3), spec, 1.5, -2.0, 0.4, interp)
+    try:
+        info = {}
+        x = solve_lsqr(batch, 0, atol=1e-6, btol=1e-6, info=info)
+        A, b, _ = batch.data_csr(0)
+        S, bs = batch.sym_csr(0)
+        M = vstack([A, S]).tocsr() if S is not None else A
+        rhs = np.concatenate([b, bs]) if S is not None else b
+        ref = lsqr(M, rhs, atol=1e-6, btol=1e-6)
+    finally:
+        batch.close()
+        prob.close()
+    rel = float(np.linalg.norm(x - ref[0]) / np.linalg.norm(ref[0]))
+    print(f"lsqr[{interp}] n={n} rows={M.shape[0]}: itn gpu={info['itn']} scipy={ref[2]} istop {info['istop']}/{ref[1]} "
+          f"rel-L2(x)={rel:.2e} products {info['forward_products']}+{info['adjoint_products']}")
+    assert x.shape == (n,) and x.dtype == np.float64
+    assert info["istop"] == ref[1] and abs(info["itn"] - ref[2]) <= max(2, 0.02 * ref[2])
+    assert rel <= 2e-3
