@@ -626,9 +626,9 @@ def test_half_sets_on_explicit_rows_vs_reference_golden(solver, name):
 @pytest.mark.parametrize("name", ["refine_dy_40", "refine_dy_32_pos"])
 def test_refine_tilt_psi_dy_vs_reference_golden(solver, name):
     """refine_tilt_psi_dy (SLR:550-841): the reference's Gauss-Newton loop with every build / prediction / solve on the
-    GPU.  The reference solves with LSQR(1e-6) (bounded: lsq_linear at 1e-10), the GPU path with LSMR at the same
-    tolerances, so the comparison is at the level of those tolerances and of the refinement's own convergence
-    thresholds (tol_tilt = 0.05 deg, tol_psi = 0.1 deg, tol_dy = 0.05 px)."""
+    GPU.  The reference solves with LSQR(1e-6) -- here scipy's LSQR over the CUDA operator -- and, when the positive rule
+    fires, lsq_linear at 1e-10 -- here the batch's LSMR + TRF state machines; that case is compared at the level of the
+    refinement's own convergence thresholds (tol_tilt = 0.05 deg, tol_psi = 0.1 deg, tol_dy = 0.05 px)."""
     d = load(name)
     apix, twist, rise, csym, L3, so, pc, mi = d["args"]
     img = d["image"]
@@ -646,6 +646,11 @@ def test_refine_tilt_psi_dy_vs_reference_golden(solver, name):
     assert isinstance(x, np.ndarray) and np.all(np.isfinite(x))
     assert abs(tilt - rt) <= 0.05 and abs(psi - rp) <= 0.1 and abs(dy - rdy) <= 0.05
     assert abs(score - rs) <= 2e-3 and relx <= 5e-2
+    if int(pc) == 0:
+        # unbounded systems: scipy's LSQR over the CUDA operator, as the reference runs it (lsqr.py) -- measured
+        # parameters equal to 1e-7, score to 1e-7, rel-L2(x) 3.5e-5 (the device-resident LSMR of round 1: ~1e-3)
+        assert abs(tilt - rt) <= 1e-4 and abs(psi - rp) <= 1e-4 and abs(dy - rdy) <= 1e-4
+        assert abs(score - rs) <= 1e-5 and relx <= 1e-3
 
 
 @pytest.mark.gpu
