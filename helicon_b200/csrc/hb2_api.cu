@@ -293,6 +293,10 @@ struct hb2_batch {
   size_t ev_next = 0;
   bool profiling = false;
   bool solved = false;
+  // side stream of the LSMR loop: the symmetry-row forward (HBM / L2 bound) runs beside the data-row band kernel
+  // (shared-memory bound; one 196 KB CTA of 768 threads per SM leaves room for two 256-thread blocks)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 extern "C" const char* hb2_last_error(void) { return g_err.c_str(); }
@@ -1791,6 +1795,9 @@ extern "C" void hb2_batch_destroy(hb2_batch* b) {
   cudaStreamSynchronize(b->stream);
   b->pool.free_all();
   for (cudaEvent_t e : b->ev_pool) cudaEventDestroy(e);
+  if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->h_nactive) cudaFreeHost(b->h_nactive);
   delete b;
 }
@@ -1867,16 +1874,19 @@ extern "C" int hb2_batch_rhs(hb2_batch* b, int32_t c, float* out) {
 enum { KC_FWD_DATA = 0, KC_FWD_SYM = 1, KC_ADJ = 2, KC_UPDATE = 3, KC_SCALAR = 4, KC_NORM = 5, KC_N = 6 };
 struct ProfScope {
   hb2_batch* b;
-  ProfScope(hb2_batch* b_, int cls) : b(b_) {
+  cudaStream_t s;
+  int first = 0;
+  ProfScope(hb2_batch* b_, int cls, cudaStream_t s_ = nullptr) : b(b_), s(s_ ? s_ : b_->stream) {
     if (!b->profiling) return;
     while (b->ev_pool.size() < b->ev_next + 2) { cudaEvent_t e; cudaEventCreate(&e); b->ev_pool.push_back(e); }
-    b->ev_used.push_back({cls, (int)b->ev_next});
-    cudaEventRecord(b->ev_pool[b->ev_next], b->stream);
+    first = (int)b->ev_next;
+    b->ev_used.push_back({cls, first});
+    cudaEventRecord(b->ev_pool[first], s);
     b->ev_next += 2;
   }
   ~ProfScope() {
     if (!b->profiling) return;
-    cudaEventRecord(b->ev_pool[b->ev_used.back().second + 1], b->stream);
+    cudaEventRecord(b->ev_pool[first + 1], s);
   }
 };
 
@@ -1930,11 +1940,11 @@ static void launch_fwd_data(hb2_batch* b, int mode) {
   if (b->idx16) FWD(uint16_t); else FWD(uint32_t);
 #undef FWD
 }
-static void launch_fwd_sym(hb2_batch* b, int mode) {
-  ProfScope ps(b, KC_FWD_SYM);
+static void launch_fwd_sym(hb2_batch* b, int mode, cudaStream_t on = nullptr) {
+  ProfScope ps(b, KC_FWD_SYM, on);
   const BD& B = b->B;
   dim3 g(B.part_us_per_cand, B.nc);
-  k_fwd_sym<<<g, HB2_BLOCK, 0, b->stream>>>(B, mode);
+  k_fwd_sym<<<g, HB2_BLOCK, 0, on ? on : b->stream>>>(B, mode);
 }
 static void launch_adj(hb2_batch* b, int mode) {
   ProfScope ps(b, KC_ADJ);
@@ -2295,14 +2305,31 @@ extern "C" int hb2_batch_solve(hb2_batch* b, const hb2_solve_options* opt, hb2_r
   launches += 4;
   CKL();
   int it = 0;
+  // HB2_OVERLAP=0 keeps the symmetry-row forward on the main stream (experiments)
+  static const int env_overlap = [] { const char* e = getenv("HB2_OVERLAP"); return e ? atoi(e) : 1; }();
+  const bool overlap = env_overlap != 0;
+  if (overlap && !b->side) {
+    CK(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  }
   *b->h_nactive = 1;
   CK(cudaMemcpyAsync(b->h_nactive, b->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   while (*b->h_nactive > 0 && it < maxit) {
     int burst = std::min(check, maxit - it);
     for (int q = 0; q < burst; ++q) {
-      launch_fwd_data(b, MODE_LSMR);
-      launch_fwd_sym(b, MODE_LSMR);
+      if (overlap) {  // fork: v and the scalars of this iteration are ready at this point of the main stream
+        cudaEventRecord(b->ev_fork, st);
+        launch_fwd_data(b, MODE_LSMR);
+        cudaStreamWaitEvent(b->side, b->ev_fork, 0);
+        launch_fwd_sym(b, MODE_LSMR, b->side);  // disjoint rows of u~ and its own partial sums
+        cudaEventRecord(b->ev_join, b->side);
+        cudaStreamWaitEvent(st, b->ev_join, 0);  // join before the norm of u~
+      } else {
+        launch_fwd_data(b, MODE_LSMR);
+        launch_fwd_sym(b, MODE_LSMR);
+      }
       if (chain) { ProfScope ps(b, KC_NORM); k_chain_sumsq<CHAIN_U><<<nc, 64, HB2_CHAIN_SMEM, st>>>(B, ch_u, MODE_LSMR); ++launches; }
       { ProfScope ps(b, KC_SCALAR); k_scal_beta<<<nc, HB2_BLOCK, 0, st>>>(B, ch_u); }
       launch_adj(b, MODE_LSMR);

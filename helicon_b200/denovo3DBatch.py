@@ -73,6 +73,8 @@ def main(argv=None):
     ap.add_argument("--top-k", type=int, default=10)
     ap.add_argument("--output", default="denovo3DBatch_out", help="output prefix")
     ap.add_argument("--save-map", action="store_true", help="write the symmetrised 3-D map of the best candidate per image")
+    ap.add_argument("--resume", action="store_true", help="keep the score tiles of solved batches in <output>_img<i>.tiles"
+                    "[.rank<r>].npz and restart an interrupted search from them (same image, grid and parameters)")
     args = ap.parse_args(argv)
 
     from . import distributed, pipeline, transforms
@@ -105,7 +107,8 @@ def main(argv=None):
                           tube_diameter=args.tube_diameter, tube_diameter_inner=args.tube_diameter_inner,
                           tube_length=args.tube_length, sym_oversample=args.sym_oversample,
                           positive_constraint=args.positive_constraint, top_k=args.top_k, device=local_rank,
-                          shard=(rank, world), return_x_top=args.save_map, interpolation=args.interpolation, dist=dist)
+                          shard=(rank, world), return_x_top=args.save_map, interpolation=args.interpolation, dist=dist,
+                          checkpoint=f"{args.output}_img{i}.tiles" if args.resume else None)
         # with more than one process the per-rank score maps were all-gathered inside search_grid (one NCCL call)
         if rank != 0:
             continue
