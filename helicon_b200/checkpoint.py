@@ -83,6 +83,13 @@ class ScoreTileStore:
             if os.path.abspath(f) == os.path.abspath(self.path):
                 self._mine[ti] = True
 
+    def keep_only(self, mask):
+        """Several ranks: keep what EVERY rank restored (``mask`` = the AND of the ranks' ``done`` maps), so that all
+        ranks cut the same task list into the same chunks; anything else is solved again."""
+        drop = self.done & ~np.asarray(mask, dtype=bool)
+        self.scores[drop], self.itn[drop], self.flags[drop] = np.nan, 0, 0
+        self.done[drop] = self.restored[drop] = self._mine[drop] = False
+
     @property
     def n_restored(self):
         return int(self.restored.sum())
@@ -136,3 +143,16 @@ class ScoreTileStore:
         sc = sc[first]
         order = np.lexsort((ti, -sc.astype(np.float64)))[: int(k)]
         return sc[order], ti[order]
+
+
+def agree_across_ranks(store, dist, device=0):
+    """One all-reduce (MIN = logical AND) of the ranks' ``done`` maps: every rank then filters the SAME tasks, which
+    the chunk queue needs (it deals indices of a chunk list that all ranks cut identically).  A tile file another rank
+    could not read (or had not been flushed when that rank looked) costs a re-solve, never a wrong map."""
+    import torch
+
+    on = f"cuda:{int(device)}" if dist.get_backend() == "nccl" else "cpu"
+    agreed = torch.from_numpy(store.done.astype(np.uint8)).to(on)
+    dist.all_reduce(agreed, op=dist.ReduceOp.MIN)
+    store.keep_only(agreed.cpu().numpy().astype(bool))
+    return store

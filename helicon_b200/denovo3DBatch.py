@@ -73,6 +73,7 @@ def main(argv=None):
     ap.add_argument("--top-k", type=int, default=10)
     ap.add_argument("--output", default="denovo3DBatch_out", help="output prefix")
     ap.add_argument("--save-map", action="store_true", help="write the symmetrised 3-D map of the best candidate per image")
+    ap.add_argument("--batch-candidates", type=int, default=0, help="candidates per batch (default: sized from GPU memory)")
     ap.add_argument("--resume", action="store_true", help="keep the score tiles of solved batches in <output>_img<i>.tiles"
                     "[.rank<r>].npz and restart an interrupted search from them (same image, grid and parameters)")
     args = ap.parse_args(argv)
@@ -108,7 +109,8 @@ def main(argv=None):
                           tube_length=args.tube_length, sym_oversample=args.sym_oversample,
                           positive_constraint=args.positive_constraint, top_k=args.top_k, device=local_rank,
                           shard=(rank, world), return_x_top=args.save_map, interpolation=args.interpolation, dist=dist,
-                          checkpoint=f"{args.output}_img{i}.tiles" if args.resume else None)
+                          checkpoint=f"{args.output}_img{i}.tiles" if args.resume else None,
+                          batch_candidates=args.batch_candidates or None)
         # with more than one process the per-rank score maps were all-gathered inside search_grid (one NCCL call)
         if rank != 0:
             continue
@@ -116,7 +118,8 @@ def main(argv=None):
         np.savez_compressed(prefix + "_scores.npz", scores=out["scores"], itn=out["itn"], flags=out["flags"], twists=twists,
                             rises=rises, csyms=np.array(csyms))
         top = [dict(score=e["score"], twist=e["twist"], rise=e["rise"], csym=e["csym"]) for e in out["top"]]
-        report.append(dict(image=i, n_candidates=int(np.isfinite(out["scores"]).sum()), seconds=out["seconds"], top=top))
+        report.append(dict(image=i, n_candidates=int(np.isfinite(out["scores"]).sum()), seconds=out["seconds"], top=top,
+                           n_restored=int(out.get("n_restored", 0))))
         best = out["top"][0] if out["top"] else None
         if best is not None:
             print(f"image {i}: best twist={best['twist']:.4f} rise={best['rise']:.4f} csym={best['csym']} "

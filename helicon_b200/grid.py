@@ -317,7 +317,7 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
     probs = {}
     store = None
     if checkpoint is not None:
-        from .checkpoint import ScoreTileStore, fingerprint
+        from .checkpoint import ScoreTileStore, agree_across_ranks, fingerprint
 
         rank, world = shard
         if dist is not None and dist.is_available() and dist.is_initialized():
@@ -328,6 +328,8 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                          sym_oversample=sym_oversample, positive_constraint=positive_constraint,
                          clip_pred=int(thresh_fraction >= 0), interpolation=str(interpolation))
         store = ScoreTileStore(checkpoint, fp, ntot, rank=rank, world=world, flush_seconds=checkpoint_seconds)
+        if world > 1 and dist is not None and dist.is_available() and dist.is_initialized():
+            agree_across_ranks(store, dist, device)  # every rank must filter the SAME tasks
         tasks_all = len(tasks)
         tasks = [t for t in tasks if not store.is_done(t.ti)]
         logger.info("search_grid: %d of %d candidates restored from %s", tasks_all - len(tasks), tasks_all, checkpoint)

@@ -94,6 +94,19 @@ def test_store_per_rank_files_are_all_read_on_resume(tmp_path):
         assert sorted(z["ti"].tolist()) == [0, 6, 10]
 
 
+def test_keep_only_drops_what_another_rank_did_not_see(tmp_path):
+    st = checkpoint.ScoreTileStore(tmp_path / "t", "fp", 6)
+    st.add([0, 1, 4], [0.1, 0.2, 0.3], [1, 2, 3], [0, 0, 1])
+    st.close()
+    st = checkpoint.ScoreTileStore(tmp_path / "t", "fp", 6)
+    agreed = np.array([1, 0, 0, 0, 1, 1], dtype=bool)  # the AND over ranks: entry 1 was not restored everywhere
+    st.keep_only(agreed)
+    assert st.n_restored == 2 and not st.is_done(1) and np.isnan(st.scores[1]) and st.is_done(4)
+    st.add([1], [0.25], [2], [0])  # solved again in this run
+    st.close()
+    assert checkpoint.ScoreTileStore(tmp_path / "t", "fp", 6).n_restored == 3
+
+
 def test_merge_topk_orders_like_the_device_kernel(tmp_path):
     st = checkpoint.ScoreTileStore(tmp_path / "t", "fp", 8)
     st.add([5, 2], [0.5, 0.5], [1, 1], [0, 0])

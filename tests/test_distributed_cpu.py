@@ -198,3 +198,53 @@ def test_make_chunks_cost_sorted_and_complete():
     assert costs == sorted(costs, reverse=True)
     for key, ch, _ in chunks:  # one chunk = one batch shape
         assert len({(t.geom["L3"], t.geom["D3"]) for t in ch}) == 1 and len(ch) <= 4
+
+
+def _resume_worker(rank, world, port, q, base):
+    import torch.distributed as dist
+
+    from helicon_b200 import checkpoint
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # first "run": every rank writes its own tile file
+    st = checkpoint.ScoreTileStore(base, "fp", 16, rank=rank, world=world)
+    st.add([rank, 8 + rank], [0.5 + 0.1 * rank, 0.7], [3, 4], [0, 0])
+    st.close()
+    dist.barrier()
+    if rank == 1:  # rank 1 loses sight of rank 0's file (stale directory listing / unreadable file)
+        os.rename(base + ".rank0.npz", base + ".hidden")
+    st = checkpoint.ScoreTileStore(base, "fp", 16, rank=rank, world=world) if rank == 1 else None
+    dist.barrier()
+    if rank == 1:
+        os.rename(base + ".hidden", base + ".rank0.npz")
+    dist.barrier()
+    if rank == 0:
+        st = checkpoint.ScoreTileStore(base, "fp", 16, rank=rank, world=world)
+    before = st.n_restored
+    checkpoint.agree_across_ranks(st, dist)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, before, np.flatnonzero(st.done).tolist()))
+
+
+def test_two_rank_resume_agrees_on_the_restored_set(tmp_path):
+    """Resumable searches under several ranks: a tile file one rank could not read is dropped by ALL ranks (one
+    all-reduce), so the task lists -- and the chunk lists the queue deals from -- stay identical."""
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    base = str(tmp_path / "tiles")
+    procs = [ctx.Process(target=_resume_worker, args=(r, world, port, q, base)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict((r, (b, d)) for r, b, d in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0][0] == 4 and got[1][0] == 2  # rank 0 saw both files, rank 1 only its own
+    assert got[0][1] == got[1][1] == [1, 9]   # after the all-reduce both keep exactly rank 1's entries
