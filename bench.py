@@ -12,7 +12,8 @@ run reports it as the co-equal ``unbounded_path`` line.
 A "step" = one chunk of the grid = one batch of consecutive candidates (default 4 twist rows x 50 rises = 200).  The
 job's chunks are a FIXED pseudo-random sample of the grid's twist rows (seeded permutation), so that the work per step
 is statistically the same whatever the number of GPUs; the N*K chunks of a run are dealt to the ranks dynamically
-through an atomic counter (grid.ChunkQueue, no data-path collective); every rank keeps its scores in a device score map
+through an atomic counter (grid.ChunkQueue, no data-path collective), the last step of every rank in quarters (whole
+twist rows) so that the job ends on small chunks; every rank keeps its scores in a device score map
 and ONE NCCL all-gather + a device top-K kernel end the timed region (weak scaling: per-GPU work fixed).
 
 JSON line keys follow the driver contract (task statement / DESIGN.md section 6).
@@ -130,6 +131,25 @@ def job_chunks(cfg, n_chunks, batch, positive, ndisk_of, seed=2026):
         new.sort(key=lambda c: c[1][0].ti)  # grid order inside the block (make_chunks sorts by cost)
         chunks += new
     return chunks[:n_chunks], base
+
+
+def split_tail(chunks, world, per_row):
+    """The LAST step of the timed region (one chunk per rank) is dealt in quarters (whole twist rows): the ranks pull
+    chunks from the atomic counter as they finish, so what a rank can be late by at the end of the job is one small
+    chunk instead of one whole step (cost-sorted / dynamic deal of SURVEY 8e: big chunks first, small ones last).
+    The candidates -- and their total -- are the same at every N, N = 1 included."""
+    if len(chunks) < world:
+        return chunks
+    out = list(chunks[:-world])
+    for key, tl, cost in chunks[-world:]:
+        piece = max(per_row, len(tl) // 4) // per_row * per_row if per_row > 0 else 0
+        if piece <= 0 or len(tl) < 2 * piece:
+            out.append((key, tl, cost))
+            continue
+        for i0 in range(0, len(tl), piece):
+            part = tl[i0:i0 + piece]
+            out.append((key, part, cost * len(part) / len(tl)))
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -377,6 +397,8 @@ def main():
     W, K = args.warmup, args.steps
     chunks, n_job = job_chunks(cfg, (W + K) * world, batch_size, args.positive, lambda key: problem(key).ndisk)
     warm_chunks, timed_chunks = chunks[:W * world], chunks[W * world:]
+    n_timed_steps = len(timed_chunks)
+    timed_chunks = split_tail(timed_chunks, world, len(cfg["rises"]) * len(cfg["csyms"]))
 
     # ---- CPU baseline + parity gate: ONE full candidate of the timed block through the reference's CPU path, started
     # now in a background process so that its ~2-3 minutes overlap the GPU measurements (rank 0, N = 1 only) --------
@@ -612,7 +634,9 @@ def main():
         vs_baseline=None, dtype="f32 (u,v,h) / f64 (x,hbar; bounded branch), as scipy executes it", data="synthetic",
         config=dict(workload=cfg["workload"] + ", nn interpolation, model=lsq, cosine score",
                     step=f"one chunk of {batch_size} grid candidates (whole twist rows, seeded pseudo-random row order); "
-                         f"{K} steps per GPU dealt by an atomic-counter chunk queue", pipelined=not args.no_pipeline,
+                         f"{K} steps per GPU dealt by an atomic-counter chunk queue, the last step of every GPU in "
+                         f"quarters ({n_timed_steps} chunks of the job -> {len(timed_chunks)} dealt pieces, same candidates at "
+                         f"every N)", pipelined=not args.no_pipeline,
                     positive_constraint=args.positive,
                     bounded_fraction=float(np.mean((fl_all[np.isfinite(sc_all)] & 4) != 0)) if np.isfinite(sc_all).any() else 0.0,
                     cache="inputs of every step are new candidates; per-step working set >> L2 (126 MB)",
