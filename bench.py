@@ -133,16 +133,16 @@ def job_chunks(cfg, n_chunks, batch, positive, ndisk_of, seed=2026):
     return chunks[:n_chunks], base
 
 
-def split_tail(chunks, world, per_row):
+def split_tail(chunks, world, per_row, parts=4):
     """The LAST step of the timed region (one chunk per rank) is dealt in quarters (whole twist rows): the ranks pull
     chunks from the atomic counter as they finish, so what a rank can be late by at the end of the job is one small
     chunk instead of one whole step (cost-sorted / dynamic deal of SURVEY 8e: big chunks first, small ones last).
     The candidates -- and their total -- are the same at every N, N = 1 included."""
-    if len(chunks) < world:
+    if len(chunks) < world or parts <= 1:
         return chunks
     out = list(chunks[:-world])
     for key, tl, cost in chunks[-world:]:
-        piece = max(per_row, len(tl) // 4) // per_row * per_row if per_row > 0 else 0
+        piece = max(per_row, len(tl) // parts) // per_row * per_row if per_row > 0 else 0
         if piece <= 0 or len(tl) < 2 * piece:
             out.append((key, tl, cost))
             continue
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline + parity gate (full oracle solve)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the unbounded-path and trilinear secondary measurements")
     ap.add_argument("--no-pipeline", action="store_true", help="prepare and solve batches strictly one after the other")
+    ap.add_argument("--tail-split", type=int, default=4, help="pieces the last step of every rank is dealt in (1 = whole steps)")
     ap.add_argument("--e2e-calls", type=int, default=3, help="timed search_grid() calls of the e2e measurement")
     ap.add_argument("--e2e-batches", type=int, default=2, help="batches per rank and search_grid() call of the e2e measurement")
     ap.add_argument("--ref-workers", type=int, default=0, help="--impl reference: worker processes (default: all cores)")
@@ -398,7 +399,7 @@ def main():
     chunks, n_job = job_chunks(cfg, (W + K) * world, batch_size, args.positive, lambda key: problem(key).ndisk)
     warm_chunks, timed_chunks = chunks[:W * world], chunks[W * world:]
     n_timed_steps = len(timed_chunks)
-    timed_chunks = split_tail(timed_chunks, world, len(cfg["rises"]) * len(cfg["csyms"]))
+    timed_chunks = split_tail(timed_chunks, world, len(cfg["rises"]) * len(cfg["csyms"]), args.tail_split)
 
     # ---- CPU baseline + parity gate: ONE full candidate of the timed block through the reference's CPU path, started
     # now in a background process so that its ~2-3 minutes overlap the GPU measurements (rank 0, N = 1 only) --------
@@ -635,7 +636,7 @@ def main():
         config=dict(workload=cfg["workload"] + ", nn interpolation, model=lsq, cosine score",
                     step=f"one chunk of {batch_size} grid candidates (whole twist rows, seeded pseudo-random row order); "
                          f"{K} steps per GPU dealt by an atomic-counter chunk queue, the last step of every GPU in "
-                         f"quarters ({n_timed_steps} chunks of the job -> {len(timed_chunks)} dealt pieces, same candidates at "
+                         f"{args.tail_split} pieces ({n_timed_steps} chunks of the job -> {len(timed_chunks)} dealt pieces, same candidates at "
                          f"every N)", pipelined=not args.no_pipeline,
                     positive_constraint=args.positive,
                     bounded_fraction=float(np.mean((fl_all[np.isfinite(sc_all)] & 4) != 0)) if np.isfinite(sc_all).any() else 0.0,

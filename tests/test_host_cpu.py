@@ -301,3 +301,23 @@ def test_tv_denoise_reduces_noise_and_keeps_the_mean():
     out = M.denoise_tv_chambolle(noisy)
     assert np.abs(out - clean).mean() < 0.6 * np.abs(noisy - clean).mean()
     assert abs(out.mean() - noisy.mean()) < 1e-6
+
+
+def test_bench_split_tail_keeps_the_candidates_and_whole_twist_rows():
+    """bench.py deals the last step of every rank in pieces of whole twist rows: same candidates, same order."""
+    import bench
+
+    class T:
+        def __init__(self, ti):
+            self.ti = ti
+
+    chunks = [("key", [T(i * 200 + j) for j in range(200)], 200.0) for i in range(8)]
+    out = bench.split_tail(chunks, 2, 50)
+    assert [len(c[1]) for c in out] == [200] * 6 + [50] * 8
+    assert [t.ti for c in out for t in c[1]] == list(range(1600))
+    assert all(c[1][0].ti % 50 == 0 for c in out) and abs(sum(c[2] for c in out) - 1600.0) < 1e-9
+    assert [len(c[1]) for c in bench.split_tail(chunks, 2, 50, parts=2)] == [200] * 6 + [100] * 4
+    assert bench.split_tail(chunks, 2, 50, parts=1) is chunks
+    assert [len(c[1]) for c in bench.split_tail(chunks, 2, 10)] == [200] * 6 + [50] * 8  # cfg1: 5 rows of 10 rises
+    ragged = [("key", [T(j) for j in range(24)], 1.0)] * 4  # cfg3: a twist row (600) exceeds the batch -> not split
+    assert [len(c[1]) for c in bench.split_tail(ragged, 2, 600)] == [24] * 4
