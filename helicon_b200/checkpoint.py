@@ -125,7 +125,7 @@ class ScoreTileStore:
     def close(self):
         self.flush()
 
-    # ---- merging with the device maps -----------------------------------------------------------------------------
+    # ---- host-side inspection of tile files (no GPU): search_grid itself restores into the DEVICE maps ------------
     def overlay(self, scores, itn, flags):
         """Fill the entries restored from disk into the maps read back from the device (which hold this run's)."""
         r = self.restored & ~np.isfinite(scores)

@@ -23,6 +23,12 @@ from .planner import MAX_EQUATIONS, CandidateSpec, positive_rule
 logger = logging.getLogger(__name__)
 
 
+def _version():
+    from . import __version__
+
+    return __version__
+
+
 class BatchPipeline:
     """Double-buffered batch preparation.
 
@@ -326,7 +332,7 @@ def search_grid(image, apix, twists, rises, csyms=(1,), reconstruct_length_rise=
                          reconstruct_length_rise=reconstruct_length_rise, tube_diameter=tube_diameter,
                          tube_diameter_inner=tube_diameter_inner, tube_length=tube_length, target_apix3d=target_apix3d,
                          sym_oversample=sym_oversample, positive_constraint=positive_constraint,
-                         clip_pred=int(thresh_fraction >= 0), interpolation=str(interpolation))
+                         clip_pred=int(thresh_fraction >= 0), interpolation=str(interpolation), library=_version())
         store = ScoreTileStore(checkpoint, fp, ntot, rank=rank, world=world, flush_seconds=checkpoint_seconds)
         if world > 1 and dist is not None and dist.is_available() and dist.is_initialized():
             agree_across_ranks(store, dist, device)  # every rank must filter the SAME tasks
