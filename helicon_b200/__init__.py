@@ -5,7 +5,7 @@ solve+score hot path behind the reference's own Python signatures.
     from helicon_b200 import search_grid                          # batched grid driver
 """
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from ._lib import HeliconB200Error  # noqa: F401
 

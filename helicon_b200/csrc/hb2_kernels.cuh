@@ -1258,17 +1258,20 @@ __global__ void __launch_bounds__(64) k_chain_sumsq(BD B, float* __restrict__ ou
     mbar_wait(&full_bar[buf], (unsigned)((st / HB2_CHAIN_STAGES) & 1));
     const int cnt = (int)min((long long)HB2_CHAIN_STAGE_F4, n4 - st * HB2_CHAIN_STAGE_F4);
     const float4* __restrict__ rb = ring[buf];
-    int i = lane;
-    for (; i + 64 * 3 < cnt; i += 64 * 4) {
-      const float4 t0 = rb[i], t1 = rb[i + 64], t2 = rb[i + 128], t3 = rb[i + 192];
-      acc = __fmaf_rn(t0.x, t0.x, acc); acc = __fmaf_rn(t0.y, t0.y, acc); acc = __fmaf_rn(t0.z, t0.z, acc); acc = __fmaf_rn(t0.w, t0.w, acc);
-      acc = __fmaf_rn(t1.x, t1.x, acc); acc = __fmaf_rn(t1.y, t1.y, acc); acc = __fmaf_rn(t1.z, t1.z, acc); acc = __fmaf_rn(t1.w, t1.w, acc);
-      acc = __fmaf_rn(t2.x, t2.x, acc); acc = __fmaf_rn(t2.y, t2.y, acc); acc = __fmaf_rn(t2.z, t2.z, acc); acc = __fmaf_rn(t2.w, t2.w, acc);
-      acc = __fmaf_rn(t3.x, t3.x, acc); acc = __fmaf_rn(t3.y, t3.y, acc); acc = __fmaf_rn(t3.z, t3.z, acc); acc = __fmaf_rn(t3.w, t3.w, acc);
+    // All 16 float4 of this lane are requested before the first FMA: the chain (4 cycles per FMA, sequential by
+    // definition) starts when the first load lands and never waits for shared memory again inside the stage.  Slots
+    // past the end of the vector read as zero: fma(0, 0, acc) leaves acc unchanged.
+    static_assert(HB2_CHAIN_STAGE_F4 == 64 * 16, "16 float4 per lane and stage");
+    float4 t[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int i = lane + 64 * k;
+      t[k] = i < cnt ? rb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (; i < cnt; i += 64) {
-      const float4 t = rb[i];
-      acc = __fmaf_rn(t.x, t.x, acc); acc = __fmaf_rn(t.y, t.y, acc); acc = __fmaf_rn(t.z, t.z, acc); acc = __fmaf_rn(t.w, t.w, acc);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      acc = __fmaf_rn(t[k].x, t[k].x, acc); acc = __fmaf_rn(t[k].y, t[k].y, acc);
+      acc = __fmaf_rn(t[k].z, t[k].z, acc); acc = __fmaf_rn(t[k].w, t[k].w, acc);
     }
     __syncthreads();  // the stage may be overwritten from the next round on
   }
