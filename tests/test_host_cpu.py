@@ -321,3 +321,20 @@ def test_bench_split_tail_keeps_the_candidates_and_whole_twist_rows():
     assert [len(c[1]) for c in bench.split_tail(chunks, 2, 10)] == [200] * 6 + [50] * 8  # cfg1: 5 rows of 10 rises
     ragged = [("key", [T(j) for j in range(24)], 1.0)] * 4  # cfg3: a twist row (600) exceeds the batch -> not split
     assert [len(c[1]) for c in bench.split_tail(ragged, 2, 600)] == [24] * 4
+
+
+def test_product_back_project_tables_equal_the_reference_outputs():
+    """the PRODUCT's host helper (not only the oracle's) against the reference's own outputs
+    (tests/golden/backproject.npz, oracle/make_golden.py): coordinate tables and pixel values bit for bit."""
+    from helicon_b200 import solver_linear_regression as S
+
+    d = load("backproject")
+    i = 0
+    while f"case{i}_img" in d.files:
+        N, s, D2, L2 = d[f"case{i}_args"]
+        (X, Y, Z), pv = S.back_project_2d_coords_to_3d_coords(d[f"case{i}_img"], float(s), int(D2), int(L2))
+        for got, key in ((X, "X"), (Y, "Y"), (Z, "Z"), (pv, "pix")):
+            ref = d[f"case{i}_{key}"]
+            assert np.asarray(got).dtype == ref.dtype and np.array_equal(got, ref), (i, key)
+        i += 1
+    assert i == 3
